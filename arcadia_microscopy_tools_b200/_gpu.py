@@ -1,0 +1,312 @@
+"""Device-side building blocks: torch tensors own the memory, libamt_b200 does the work.
+
+PyTorch is plumbing only (allocation, pinned staging, streams); every pixel is touched by a
+hand-written sm_100a kernel behind the C ABI.  All functions here take/return CUDA tensors
+and are batched over a leading plane axis, so a ``Pipeline(parallel=True)`` stack or a chunk
+of fields of view is one launch per stage.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import AMT_F64, AMT_U16, check
+
+_tls = threading.local()
+
+
+def torch_mod():
+    import torch
+
+    return torch
+
+
+def require_cuda(device: int | None = None):
+    """Return the torch device to use; fail loudly when there is none (no CPU fallback)."""
+    torch = torch_mod()
+    if not torch.cuda.is_available():
+        raise _lib.AmtLibraryError(
+            "arcadia_microscopy_tools_b200 needs an NVIDIA B200 (sm_100a) CUDA device; "
+            "there is no CPU fallback"
+        )
+    _lib.load()
+    idx = torch.cuda.current_device() if device is None else int(device)
+    return torch.device("cuda", idx)
+
+
+def stream_ptr() -> int:
+    return int(torch_mod().cuda.current_stream().cuda_stream)
+
+
+def ptr(t) -> int:
+    return 0 if t is None else int(t.data_ptr())
+
+
+def is_device_array(x) -> bool:
+    torch = torch_mod()
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+# ------------------------------------------------------------------ host <-> device
+def to_device(a: np.ndarray, device=None):
+    """Upload a NumPy array (uint16 travels as int16 bits: torch's uint16 support is partial)."""
+    torch = torch_mod()
+    dev = require_cuda() if device is None else device
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint16:
+        return torch.from_numpy(a.view(np.int16)).to(dev, non_blocking=False)
+    if a.dtype == np.bool_:
+        return torch.from_numpy(a.view(np.uint8)).to(dev)
+    return torch.from_numpy(a).to(dev)
+
+
+def to_host(t) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+def dtype_code(t) -> int:
+    torch = torch_mod()
+    if t.dtype in (torch.int16, torch.uint16):
+        return AMT_U16
+    if t.dtype == torch.float64:
+        return AMT_F64
+    raise TypeError(f"unsupported device dtype {t.dtype}")
+
+
+# ------------------------------------------------------------------ Gaussian weights (host, NumPy)
+def gaussian_half_weights(sigma: float, truncate: float = 4.0) -> np.ndarray:
+    """``weights[c - j]`` for j = 0..r of scipy's ``_gaussian_kernel1d(sigma, 0, r)``, computed
+    with the same NumPy expression scipy uses so the weights are bit-identical."""
+    sd = float(sigma)
+    if sd <= 1e-15:  # scipy skips the axis: identity
+        return np.ones(1, dtype=np.float64)
+    radius = int(truncate * sd + 0.5)
+    sigma2 = sd * sd
+    x = np.arange(-radius, radius + 1)
+    phi_x = np.exp(-0.5 / sigma2 * x**2)
+    phi_x = phi_x / phi_x.sum()
+    return np.ascontiguousarray(phi_x[radius::-1])
+
+
+def rank_pair(n: int, q: float) -> tuple[int, int, float]:
+    """Floor / ceil ranks and lerp fraction of ``np.percentile(a, q)`` over n samples."""
+    quant = np.true_divide(np.float64(q), 100)
+    v = (n - 1) * quant
+    lo = int(np.floor(v))
+    lo = min(max(lo, 0), n - 1)
+    hi = min(lo + 1, n - 1)
+    return lo, hi, float(v - lo)
+
+
+def np_lerp(a: float, b: float, t: float) -> float:
+    a, b, t = np.float64(a), np.float64(b), np.float64(t)
+    diff = b - a
+    return float(b - diff * (1 - t)) if t >= 0.5 else float(a + diff * t)
+
+
+# ------------------------------------------------------------------ kernels
+def input_scale(np_dtype) -> float:
+    """img_as_float's multiplier for the integer dtypes on the path."""
+    if np_dtype == np.uint16:
+        return 1.0 / 65535.0
+    if np_dtype == np.uint8:
+        return 1.0 / 255.0
+    return 1.0
+
+
+def dog2d(x, scale: float, low_sigma: float, high_sigma: float):
+    """x: (n_img, H, W) int16-as-uint16 or float64 -> (dog float64, minmax keys)."""
+    torch = torch_mod()
+    lib = _lib.load()
+    n_img, h, w = x.shape
+    hw_lo = gaussian_half_weights(low_sigma)
+    hw_hi = gaussian_half_weights(high_sigma)
+    d_lo = torch.from_numpy(hw_lo).to(x.device)
+    d_hi = torch.from_numpy(hw_hi).to(x.device)
+    out = torch.empty((n_img, h, w), dtype=torch.float64, device=x.device)
+    tmp_lo = torch.empty_like(out)
+    tmp_hi = torch.empty_like(out)
+    mm = torch.empty((n_img, 2), dtype=torch.int64, device=x.device)
+    check(
+        lib.amt_dog2d(ptr(x), dtype_code(x), scale, ptr(out), n_img, h, w, ptr(d_lo), len(hw_lo) - 1, ptr(d_hi),
+                      len(hw_hi) - 1, ptr(tmp_lo), ptr(tmp_hi), ptr(mm), stream_ptr()),
+        "amt_dog2d",
+    )
+    return out, mm
+
+
+def gaussian_nd(x, scale: float, sigma: float):
+    """All-axes Gaussian of one N-D array (scipy's axis order 0, 1, ...)."""
+    torch = torch_mod()
+    lib = _lib.load()
+    hw = gaussian_half_weights(sigma)
+    d_hw = torch.from_numpy(hw).to(x.device)
+    shape = tuple(x.shape)
+    cur = x
+    code = dtype_code(x)
+    for axis in range(len(shape)):
+        outer = int(np.prod(shape[:axis], dtype=np.int64))
+        n = shape[axis]
+        inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+        out = torch.empty(shape, dtype=torch.float64, device=x.device)
+        check(
+            lib.amt_gaussian_axis(ptr(cur), code, scale, ptr(out), outer, n, inner, ptr(d_hw), len(hw) - 1, stream_ptr()),
+            "amt_gaussian_axis",
+        )
+        cur, code = out, AMT_F64
+    return cur
+
+
+def sub_f64(a, b):
+    torch = torch_mod()
+    out = torch.empty_like(a)
+    check(_lib.load().amt_sub_f64(ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr()), "amt_sub_f64")
+    return out
+
+
+def minmax_keys(x2d):
+    """x2d: (n_img, n) -> int64 keys (n_img, 2)."""
+    torch = torch_mod()
+    lib = _lib.load()
+    n_img, n = x2d.shape
+    mm = torch.empty((n_img, 2), dtype=torch.int64, device=x2d.device)
+    fn = lib.amt_minmax_f64 if dtype_code(x2d) == AMT_F64 else lib.amt_minmax_u16
+    check(fn(ptr(x2d), n_img, n, ptr(mm), stream_ptr()), "amt_minmax")
+    return mm
+
+
+def minmax_values(mm, is_f64: bool) -> np.ndarray:
+    torch = torch_mod()
+    out = torch.empty((mm.shape[0], 2), dtype=torch.float64, device=mm.device)
+    check(_lib.load().amt_minmax_decode(ptr(mm), 1 if is_f64 else 0, mm.shape[0], ptr(out), stream_ptr()), "amt_minmax_decode")
+    return to_host(out)
+
+
+def order_statistics(x2d, ranks: list[int], mm=None) -> np.ndarray:
+    """Exact order statistics of every plane: (n_img, len(ranks)) float64 on the host."""
+    torch = torch_mod()
+    lib = _lib.load()
+    n_img, n = x2d.shape
+    r = (C.c_int64 * len(ranks))(*ranks)
+    out = torch.empty((n_img, len(ranks)), dtype=torch.float64, device=x2d.device)
+    if dtype_code(x2d) == AMT_F64:
+        if mm is None:
+            mm = minmax_keys(x2d)
+        nbytes = lib.amt_select_f64_scratch_bytes(n_img, n)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=x2d.device)
+        check(lib.amt_select_f64(ptr(x2d), n_img, n, r, len(ranks), ptr(mm), ptr(out), ptr(scratch), nbytes, stream_ptr()),
+              "amt_select_f64")
+    else:
+        nbytes = lib.amt_select_u16_scratch_bytes(n_img)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=x2d.device)
+        check(lib.amt_select_u16(ptr(x2d), n_img, n, r, len(ranks), ptr(out), ptr(scratch), nbytes, stream_ptr()),
+              "amt_select_u16")
+    return to_host(out)
+
+
+def percentiles(x2d, qs: list[float], mm=None) -> np.ndarray:
+    """``np.percentile(plane, qs)`` for every plane -> (n_img, len(qs)) float64."""
+    n = x2d.shape[1]
+    ranks: list[int] = []
+    gammas: list[float] = []
+    for q in qs:
+        lo, hi, g = rank_pair(n, q)
+        ranks += [lo, hi]
+        gammas.append(g)
+    vals = order_statistics(x2d, ranks, mm)
+    out = np.empty((x2d.shape[0], len(qs)), dtype=np.float64)
+    for i in range(x2d.shape[0]):
+        for j, g in enumerate(gammas):
+            out[i, j] = np_lerp(vals[i, 2 * j], vals[i, 2 * j + 1], g)
+    return out
+
+
+def apply_map(x2d, params_host: list[_lib.MapParams]):
+    """Elementwise map with per-plane parameters -> float64 (n_img, n)."""
+    torch = torch_mod()
+    n_img, n = x2d.shape
+    arr = (_lib.MapParams * n_img)(*params_host)
+    raw = np.frombuffer(arr, dtype=np.uint8).copy()
+    d_params = torch.from_numpy(raw).to(x2d.device)
+    out = torch.empty((n_img, n), dtype=torch.float64, device=x2d.device)
+    check(_lib.load().amt_map(ptr(x2d), dtype_code(x2d), ptr(out), n_img, n, ptr(d_params), None, stream_ptr()), "amt_map")
+    return out
+
+
+def otsu_threshold(x2d, mm=None):
+    """Per-plane Otsu threshold (device float64 tensor of n_img values) and the min/max keys."""
+    torch = torch_mod()
+    lib = _lib.load()
+    n_img, n = x2d.shape
+    if mm is None:
+        mm = minmax_keys(x2d)
+    thr = torch.empty(n_img, dtype=torch.float64, device=x2d.device)
+    if dtype_code(x2d) == AMT_F64:
+        hist = torch.empty((n_img, 256), dtype=torch.int32, device=x2d.device)
+        check(lib.amt_hist256_f64(ptr(x2d), n_img, n, ptr(mm), ptr(hist), stream_ptr()), "amt_hist256_f64")
+        check(lib.amt_otsu(ptr(hist), 1, None, ptr(mm), n_img, ptr(thr), None, 0, stream_ptr()), "amt_otsu")
+    else:
+        hist = torch.empty((n_img, 65536), dtype=torch.int32, device=x2d.device)
+        check(lib.amt_hist_u16(ptr(x2d), n_img, n, ptr(hist), stream_ptr()), "amt_hist_u16")
+        nbytes = lib.amt_otsu_scratch_bytes(2, n_img)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=x2d.device)
+        check(lib.amt_otsu(ptr(hist), 2, None, ptr(mm), n_img, ptr(thr), ptr(scratch), nbytes, stream_ptr()), "amt_otsu")
+    return thr, mm
+
+
+def threshold_gt(x2d, thr):
+    torch = torch_mod()
+    n_img, n = x2d.shape
+    mask = torch.empty((n_img, n), dtype=torch.uint8, device=x2d.device)
+    check(_lib.load().amt_threshold_gt(ptr(x2d), dtype_code(x2d), n_img, n, ptr(thr), ptr(mask), stream_ptr()),
+          "amt_threshold_gt")
+    return mask
+
+
+def label(x, kind: int, clear_border: bool, thresholds=None, max_value: int = 0):
+    """x: (n_img, H, W) uint8 mask (kind 0), float64 plane (kind 1) or int32 labels (kind 2)
+    -> (labels int32 (n_img, H, W), counts int32 (n_img,))."""
+    torch = torch_mod()
+    lib = _lib.load()
+    n_img, h, w = x.shape
+    labels = torch.empty((n_img, h, w), dtype=torch.int32, device=x.device)
+    counts = torch.empty(n_img, dtype=torch.int32, device=x.device)
+    nbytes = lib.amt_label_scratch_bytes(n_img, h, w, max_value)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    check(
+        lib.amt_label(ptr(x), kind, ptr(thresholds), max_value, n_img, h, w, 1 if clear_border else 0, ptr(labels),
+                      ptr(counts), ptr(scratch), nbytes, stream_ptr()),
+        "amt_label",
+    )
+    return labels, counts
+
+
+def region_table(labels, counts, channels, max_labels: int, with_shape: bool = False):
+    """labels (n_img, H, W) int32, channels (n_img, C, H, W) uint16-as-int16 or None ->
+    float64 table (n_img, cols, max_labels) on the device."""
+    torch = torch_mod()
+    lib = _lib.load()
+    n_img, h, w = labels.shape
+    n_ch = 0 if channels is None else channels.shape[1]
+    acc = torch.empty((n_img, _lib.acc_fields(n_ch), max_labels), dtype=torch.int64, device=labels.device)
+    table = torch.empty((n_img, _lib.table_cols(n_ch), max_labels), dtype=torch.float64, device=labels.device)
+    check(
+        lib.amt_region_reduce(ptr(labels), ptr(channels), n_ch, n_ch * h * w, h * w, n_img, h, w, max_labels, ptr(acc),
+                              stream_ptr()),
+        "amt_region_reduce",
+    )
+    check(lib.amt_region_finalize(ptr(acc), ptr(counts), n_ch, n_img, max_labels, ptr(table), stream_ptr()),
+          "amt_region_finalize")
+    if with_shape:
+        nbytes = lib.amt_region_shape_scratch_bytes(n_img, h, w, max_labels)
+        scratch = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=labels.device)
+        check(
+            lib.amt_region_shape(ptr(labels), ptr(acc), n_ch, ptr(counts), n_img, h, w, max_labels, ptr(table),
+                                 ptr(scratch), nbytes, stream_ptr()),
+            "amt_region_shape",
+        )
+    return table, acc

@@ -1,0 +1,193 @@
+"""Batch path: whole fields of view through preprocess -> threshold/label -> quantify in one call.
+
+Python face of the native ``amt_executor`` (``csrc/executor.cu``).  One executor per GPU; fields
+of view are independent, so multi-GPU runs shard FOVs across processes with no collective
+(SURVEY.md 8e).  The per-FOV workload is the reference call chain
+
+    P_c  = rescale_by_percentile(subtract_background_dog(x_c, low, high, bg_pct), (p_lo, p_hi), out)
+    m    = apply_threshold(P_seg, "otsu")
+    SegmentationMask(m, {ch: x_c}, remove_edge_cells=True).cell_properties
+    SegmentationMask(given_labels, {ch: x_c}, remove_edge_cells=True).cell_properties
+
+(ref: ``operations.py:10-97, 135-216``; ``masks.py:38-65, 247-328``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _gpu, _lib
+from ._lib import check
+
+
+@dataclass
+class FovPipelineConfig:
+    n_channels: int = 4
+    height: int = 2048
+    width: int = 2048
+    seg_channel: int = 1
+    chunk_fovs: int = 8
+    max_labels: int = 4096
+    max_label_value: int = 65535
+    quantify_given_mask: bool = True
+    low_sigma: float = 0.6
+    high_sigma: float = 16.0
+    bg_percentile: float = 0.0
+    percentile_range: tuple[float, float] = (1.0, 99.0)
+    out_range: tuple[float, float] = (0.0, 1.0)
+
+
+# column names of the float64 table (include/amt_b200.h)
+def table_columns(channel_names: list[str]) -> list[str]:
+    cols = ["label", "area", "bbox-0", "bbox-1", "bbox-2", "bbox-3", "centroid_y", "centroid_x",
+            "inertia_tensor_eigvals-0", "inertia_tensor_eigvals-1", "axis_major_length", "axis_minor_length",
+            "eccentricity", "orientation", "perimeter", "area_convex"]
+    for name in channel_names:
+        low = name.lower()
+        cols += [f"intensity_sum_{low}", f"intensity_mean_{low}", f"intensity_max_{low}", f"intensity_min_{low}",
+                 f"intensity_std_{low}"]
+    return cols
+
+
+class FovBatchExecutor:
+    """Owns one native executor (streams, scratch, staging) on one GPU."""
+
+    def __init__(self, config: FovPipelineConfig, device: int | None = None) -> None:
+        dev = _gpu.require_cuda(device)
+        self.config = config
+        self.device = dev
+        self._lib = _lib.load()
+        cfg = _lib.FovConfig(
+            device=dev.index, n_channels=config.n_channels, height=config.height, width=config.width,
+            seg_channel=config.seg_channel, chunk_fovs=config.chunk_fovs, max_labels=config.max_labels,
+            max_label_value=config.max_label_value, quantify_given_mask=1 if config.quantify_given_mask else 0,
+            keep_preprocessed=0, low_sigma=config.low_sigma, high_sigma=config.high_sigma,
+            bg_percentile=config.bg_percentile, pct_lo=config.percentile_range[0], pct_hi=config.percentile_range[1],
+            out_lo=config.out_range[0], out_hi=config.out_range[1],
+        )
+        hw_lo = _gpu.gaussian_half_weights(config.low_sigma)
+        hw_hi = _gpu.gaussian_half_weights(config.high_sigma)
+        handle = C.c_void_p()
+        check(
+            self._lib.amt_executor_create(
+                C.byref(cfg), hw_lo.ctypes.data_as(C.POINTER(C.c_double)), len(hw_lo) - 1,
+                hw_hi.ctypes.data_as(C.POINTER(C.c_double)), len(hw_hi) - 1, C.byref(handle)),
+            "amt_executor_create",
+        )
+        self._handle = handle
+        self.n_cols = _lib.table_cols(config.n_channels)
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None):
+            self._lib.amt_executor_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self) -> "FovBatchExecutor":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.amt_executor_device_bytes(self._handle))
+
+    # ------------------------------------------------------------------ device-resident batch
+    def alloc_outputs(self, n_fov: int, labels: bool = False, preprocessed: bool = False) -> dict:
+        torch = _gpu.torch_mod()
+        c = self.config
+        dev = self.device
+        out = {
+            "tables_thr": torch.empty((n_fov, self.n_cols, c.max_labels), dtype=torch.float64, device=dev),
+            "counts_thr": torch.empty(n_fov, dtype=torch.int32, device=dev),
+            "tables_given": torch.empty((n_fov, self.n_cols, c.max_labels), dtype=torch.float64, device=dev),
+            "counts_given": torch.empty(n_fov, dtype=torch.int32, device=dev),
+            "thresholds": torch.empty(n_fov, dtype=torch.float64, device=dev),
+            "labels_thr": None, "labels_given": None, "preprocessed": None,
+        }
+        if labels:
+            out["labels_thr"] = torch.empty((n_fov, c.height, c.width), dtype=torch.int32, device=dev)
+            out["labels_given"] = torch.empty((n_fov, c.height, c.width), dtype=torch.int32, device=dev)
+        if preprocessed:
+            out["preprocessed"] = torch.empty((n_fov, c.n_channels, c.height, c.width), dtype=torch.float64, device=dev)
+        return out
+
+    def run_device(self, fovs, given_labels, outputs: dict, sync: bool = True) -> float:
+        """fovs: CUDA (n_fov, C, H, W) uint16 bits; given_labels: CUDA (n_fov, H, W) int32 or None.
+        Work is queued on the executor's own streams (inputs must be complete: this method
+        synchronises the caller's current stream first).  Returns device milliseconds when
+        ``sync`` (CUDA events on the compute stream)."""
+        torch = _gpu.torch_mod()
+        n_fov = fovs.shape[0]
+        torch.cuda.current_stream(self.device).synchronize()
+        p = _gpu.ptr
+        check(
+            self._lib.amt_executor_run_device(
+                self._handle, p(fovs), p(given_labels), n_fov, p(outputs["tables_thr"]), p(outputs["counts_thr"]),
+                p(outputs["tables_given"]), p(outputs["counts_given"]), p(outputs["thresholds"]),
+                p(outputs["labels_thr"]), p(outputs["labels_given"]), p(outputs["preprocessed"])),
+            "amt_executor_run_device",
+        )
+        if not sync:
+            return float("nan")
+        check(self._lib.amt_executor_sync(self._handle), "amt_executor_sync")
+        return float(self._lib.amt_executor_last_ms(self._handle))
+
+    # ------------------------------------------------------------------ host-fed batch
+    def run_host(self, fovs: np.ndarray, given_labels: np.ndarray | None, out: dict | None = None) -> dict:
+        """fovs: host (n_fov, C, H, W) uint16 (pinned memory overlaps copies with compute);
+        given_labels: host (n_fov, H, W) int32 or None.  Returns host arrays."""
+        c = self.config
+        n_fov = fovs.shape[0]
+        assert fovs.dtype == np.uint16 and fovs.flags.c_contiguous
+        if given_labels is not None:
+            assert given_labels.dtype == np.int32 and given_labels.flags.c_contiguous
+        if out is None:
+            out = self.alloc_host_outputs(n_fov)
+        vp = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+        check(
+            self._lib.amt_executor_run_host(
+                self._handle, vp(fovs), vp(given_labels), n_fov, vp(out["tables_thr"]), vp(out["counts_thr"]),
+                vp(out["tables_given"]), vp(out["counts_given"]), vp(out["thresholds"])),
+            "amt_executor_run_host",
+        )
+        return out
+
+    def alloc_host_outputs(self, n_fov: int, pinned: bool = True) -> dict:
+        torch = _gpu.torch_mod()
+        c = self.config
+
+        def host(shape, dtype):
+            t = torch.empty(shape, dtype=dtype, pin_memory=pinned)
+            return t.numpy()
+
+        return {
+            "tables_thr": host((n_fov, self.n_cols, c.max_labels), torch.float64),
+            "counts_thr": host((n_fov,), torch.int32),
+            "tables_given": host((n_fov, self.n_cols, c.max_labels), torch.float64),
+            "counts_given": host((n_fov,), torch.int32),
+            "thresholds": host((n_fov,), torch.float64),
+        }
+
+    # ------------------------------------------------------------------ table -> dict
+    def table_to_properties(self, table: np.ndarray, count: int, channel_names: list[str]) -> dict[str, np.ndarray]:
+        """One FOV's (cols, max_labels) table -> ``cell_properties``-style dict of columns."""
+        cols = table_columns(channel_names)
+        out: dict[str, np.ndarray] = {}
+        for i, name in enumerate(cols):
+            col = np.ascontiguousarray(table[i, :count])
+            if name == "label" or name.startswith("bbox-"):
+                col = col.astype(np.int64)
+            elif name.startswith("intensity_sum_"):
+                col = col.astype(np.uint64)
+            out[name] = col
+        return out

@@ -1,0 +1,335 @@
+// Fused field-of-view executor: the native runtime of the batch path.
+//
+// Runs workload W for a batch of FOVs with no host round trip inside a chunk:
+//   for every channel   P_c = rescale_by_percentile(subtract_background_dog(x_c, lo, hi, pct_bg),
+//                                                   (pct_lo, pct_hi), (out_lo, out_hi))
+//                       ref: operations.py:57-97 then operations.py:10-54
+//   segmentation chan.  m = apply_threshold(P_s, "otsu")            ref: operations.py:135-216
+//   SegmentationMask(m, {ch: x_c}, remove_edge_cells=True)          ref: masks.py:38-65, 247-328
+//   SegmentationMask(given_labels, {ch: x_c}, remove_edge_cells=True)
+// FOVs are independent, so a batch is cut into chunks of `chunk_fovs` and every kernel is
+// launched over all planes of a chunk (grid.y / grid.z = plane).  The host-fed entry point
+// double-buffers H2D copies, compute and D2H copies on three streams.
+
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "internal.cuh"
+
+struct amt_executor {
+  amt_fov_config cfg;
+  int r_lo, r_hi;
+  int64_t ranks[6];
+  double g_bg, g_lo, g_hi;
+  cudaStream_t s_compute, s_in, s_out;
+  cudaEvent_t ev_start, ev_stop;
+  cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+  // device buffers
+  double *hw_lo, *hw_hi;
+  double *tmp_lo, *tmp_hi, *dog, *pre;
+  uint64_t* mm;
+  double* stats;
+  amt_map_params* params;
+  void* sel_scratch;
+  size_t sel_bytes;
+  uint32_t* hist256;
+  double* thr;
+  int32_t *lab_thr, *lab_given;
+  void* label_scratch;
+  size_t label_bytes;
+  uint64_t* acc;
+  // host-path staging (two slots)
+  uint16_t* in_slot[2];
+  int32_t* given_slot[2];
+  double *tab_thr_slot[2], *tab_given_slot[2], *thr_slot[2];
+  int32_t *cnt_thr_slot[2], *cnt_given_slot[2];
+  bool host_slots;
+  size_t device_bytes;
+  float last_ms;
+};
+
+namespace amt {
+
+static int dmalloc(amt_executor* ex, void** p, size_t bytes) {
+  AMT_CUDA_TRY(cudaMalloc(p, bytes));
+  ex->device_bytes += bytes;
+  return AMT_OK;
+}
+
+static void rank_pair(int64_t n, double q, int64_t* lo, int64_t* hi, double* gamma) {
+  // numpy: virtual index (n-1) * (q/100); floor / ceil neighbours; gamma = v - floor(v)
+  const double quant = q / 100.0;
+  const double v = (double)(n - 1) * quant;
+  int64_t l = (int64_t)std::floor(v);
+  if (l < 0) l = 0;
+  if (l > n - 1) l = n - 1;
+  *lo = l;
+  *hi = (l + 1 < n - 1) ? l + 1 : n - 1;
+  *gamma = v - (double)l;
+}
+
+static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* given, int g, double* tab_thr,
+                         int32_t* cnt_thr, double* tab_given, int32_t* cnt_given, double* thr_out, int32_t* lab_thr_out,
+                         int32_t* lab_given_out, double* pre_out) {
+  const amt_fov_config& c = ex->cfg;
+  const int C = c.n_channels;
+  const int64_t H = c.height, W = c.width, HW = H * W;
+  const int64_t planes = (int64_t)g * C;
+  cudaStream_t st = ex->s_compute;
+  double* pre = pre_out ? pre_out : ex->pre;
+  int32_t* lab_thr = lab_thr_out ? lab_thr_out : ex->lab_thr;
+  int32_t* lab_given = lab_given_out ? lab_given_out : ex->lab_given;
+  double* thr = thr_out ? thr_out : ex->thr;
+
+  // stage A: DoG -> order statistics -> plan -> map (+ histogram of the segmentation planes)
+  AMT_TRY(dog2d(in, AMT_U16, 1.0 / 65535.0, ex->dog, planes, H, W, ex->hw_lo, ex->r_lo, ex->hw_hi, ex->r_hi, ex->tmp_lo,
+                ex->tmp_hi, ex->mm, st));
+  AMT_TRY(amt_select_f64(ex->dog, planes, HW, ex->ranks, 6, ex->mm, ex->stats, ex->sel_scratch, ex->sel_bytes, st));
+  AMT_TRY(plan_dog_rescale(ex->stats, ex->mm, planes, ex->g_bg, ex->g_lo, ex->g_hi, c.out_lo, c.out_hi, ex->params, st));
+  AMT_CUDA_TRY(cudaMemsetAsync(ex->hist256, 0, (size_t)g * 256 * sizeof(uint32_t), st));
+  AMT_TRY(map_launch(ex->dog, AMT_F64, pre, planes, HW, ex->params, ex->hist256, C, c.seg_channel, st));
+  // stage B: Otsu -> threshold + CCL + clear_border
+  AMT_TRY(otsu_launch(ex->hist256, 0, ex->params, C, c.seg_channel, nullptr, g, thr, nullptr, 0, st));
+  AMT_TRY(label_launch(pre + (int64_t)c.seg_channel * HW, 1, (int64_t)C * HW, thr, 0, g, H, W, 1, lab_thr, cnt_thr,
+                       ex->label_scratch, ex->label_bytes, st));
+  // stage C: per-cell tables over the raw channels
+  AMT_TRY(region_reduce(lab_thr, in, C, (int64_t)C * HW, HW, g, H, W, c.max_labels, ex->acc, st));
+  AMT_TRY(region_finalize(ex->acc, cnt_thr, C, g, c.max_labels, tab_thr, st));
+  if (c.quantify_given_mask && given) {
+    AMT_TRY(label_launch(given, 2, HW, nullptr, c.max_label_value, g, H, W, 1, lab_given, cnt_given, ex->label_scratch,
+                         ex->label_bytes, st));
+    AMT_TRY(region_reduce(lab_given, in, C, (int64_t)C * HW, HW, g, H, W, c.max_labels, ex->acc, st));
+    AMT_TRY(region_finalize(ex->acc, cnt_given, C, g, c.max_labels, tab_given, st));
+  }
+  return AMT_OK;
+}
+
+static int alloc_host_slots(amt_executor* ex) {
+  if (ex->host_slots) return AMT_OK;
+  const amt_fov_config& c = ex->cfg;
+  const int64_t HW = (int64_t)c.height * c.width;
+  const size_t tab = (size_t)c.chunk_fovs * AMT_TABLE_COLS(c.n_channels) * c.max_labels * sizeof(double);
+  for (int s = 0; s < 2; ++s) {
+    AMT_TRY(dmalloc(ex, (void**)&ex->in_slot[s], (size_t)c.chunk_fovs * c.n_channels * HW * sizeof(uint16_t)));
+    AMT_TRY(dmalloc(ex, (void**)&ex->given_slot[s], (size_t)c.chunk_fovs * HW * sizeof(int32_t)));
+    AMT_TRY(dmalloc(ex, (void**)&ex->tab_thr_slot[s], tab));
+    AMT_TRY(dmalloc(ex, (void**)&ex->tab_given_slot[s], tab));
+    AMT_TRY(dmalloc(ex, (void**)&ex->thr_slot[s], (size_t)c.chunk_fovs * sizeof(double)));
+    AMT_TRY(dmalloc(ex, (void**)&ex->cnt_thr_slot[s], (size_t)c.chunk_fovs * sizeof(int32_t)));
+    AMT_TRY(dmalloc(ex, (void**)&ex->cnt_given_slot[s], (size_t)c.chunk_fovs * sizeof(int32_t)));
+  }
+  ex->host_slots = true;
+  return AMT_OK;
+}
+
+}  // namespace amt
+
+extern "C" {
+
+int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host, int r_lo, const double* half_w_hi_host,
+                        int r_hi, amt_executor** out) {
+  using namespace amt;
+  if (!cfg || !half_w_lo_host || !half_w_hi_host || !out || r_lo < 0 || r_hi < 0) return AMT_ERR_INVALID;
+  if (cfg->n_channels < 1 || cfg->n_channels > 8 || cfg->height < 1 || cfg->width < 1 || cfg->chunk_fovs < 1 ||
+      cfg->max_labels < 1 || cfg->seg_channel < 0 || cfg->seg_channel >= cfg->n_channels || cfg->max_label_value < 0)
+    return AMT_ERR_INVALID;
+  if (!(cfg->bg_percentile >= 0 && cfg->bg_percentile <= 100) ||
+      !(0 <= cfg->pct_lo && cfg->pct_lo < cfg->pct_hi && cfg->pct_hi <= 100))
+    return AMT_ERR_INVALID;
+  AMT_CUDA_TRY(cudaSetDevice(cfg->device));
+  amt_executor* ex = new (std::nothrow) amt_executor();
+  if (!ex) return AMT_ERR_CAPACITY;
+  std::memset(ex, 0, sizeof(*ex));
+  ex->cfg = *cfg;
+  ex->r_lo = r_lo;
+  ex->r_hi = r_hi;
+  const int C = cfg->n_channels;
+  const int64_t HW = (int64_t)cfg->height * cfg->width;
+  const int64_t planes = (int64_t)cfg->chunk_fovs * C;
+  rank_pair(HW, cfg->bg_percentile, &ex->ranks[0], &ex->ranks[1], &ex->g_bg);
+  rank_pair(HW, cfg->pct_lo, &ex->ranks[2], &ex->ranks[3], &ex->g_lo);
+  rank_pair(HW, cfg->pct_hi, &ex->ranks[4], &ex->ranks[5], &ex->g_hi);
+
+  int st = AMT_OK;
+  auto fail = [&](int s) {
+    amt_executor_destroy(ex);
+    return s;
+  };
+#define EX_TRY(e)                 \
+  do {                            \
+    st = (e);                     \
+    if (st != AMT_OK) return fail(st); \
+  } while (0)
+#define EX_CUDA(e)                                  \
+  do {                                              \
+    cudaError_t _e = (e);                           \
+    if (_e != cudaSuccess) {                        \
+      set_last_cuda_error(_e);                      \
+      return fail(AMT_ERR_CUDA);                    \
+    }                                               \
+  } while (0)
+  EX_CUDA(cudaStreamCreateWithFlags(&ex->s_compute, cudaStreamNonBlocking));
+  EX_CUDA(cudaStreamCreateWithFlags(&ex->s_in, cudaStreamNonBlocking));
+  EX_CUDA(cudaStreamCreateWithFlags(&ex->s_out, cudaStreamNonBlocking));
+  EX_CUDA(cudaEventCreate(&ex->ev_start));
+  EX_CUDA(cudaEventCreate(&ex->ev_stop));
+  for (int s = 0; s < 2; ++s) {
+    EX_CUDA(cudaEventCreateWithFlags(&ex->ev_in[s], cudaEventDisableTiming));
+    EX_CUDA(cudaEventCreateWithFlags(&ex->ev_done[s], cudaEventDisableTiming));
+    EX_CUDA(cudaEventCreateWithFlags(&ex->ev_out[s], cudaEventDisableTiming));
+  }
+  EX_TRY(dmalloc(ex, (void**)&ex->hw_lo, (size_t)(r_lo + 1) * sizeof(double)));
+  EX_TRY(dmalloc(ex, (void**)&ex->hw_hi, (size_t)(r_hi + 1) * sizeof(double)));
+  EX_CUDA(cudaMemcpy(ex->hw_lo, half_w_lo_host, (size_t)(r_lo + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  EX_CUDA(cudaMemcpy(ex->hw_hi, half_w_hi_host, (size_t)(r_hi + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  const size_t plane_f64 = (size_t)planes * HW * sizeof(double);
+  EX_TRY(dmalloc(ex, (void**)&ex->tmp_lo, plane_f64));
+  EX_TRY(dmalloc(ex, (void**)&ex->tmp_hi, plane_f64));
+  EX_TRY(dmalloc(ex, (void**)&ex->dog, plane_f64));
+  EX_TRY(dmalloc(ex, (void**)&ex->pre, plane_f64));
+  EX_TRY(dmalloc(ex, (void**)&ex->mm, (size_t)planes * 2 * sizeof(uint64_t)));
+  EX_TRY(dmalloc(ex, (void**)&ex->stats, (size_t)planes * 6 * sizeof(double)));
+  EX_TRY(dmalloc(ex, (void**)&ex->params, (size_t)planes * sizeof(amt_map_params)));
+  ex->sel_bytes = amt_select_f64_scratch_bytes(planes, HW);
+  EX_TRY(dmalloc(ex, &ex->sel_scratch, ex->sel_bytes));
+  EX_TRY(dmalloc(ex, (void**)&ex->hist256, (size_t)cfg->chunk_fovs * 256 * sizeof(uint32_t)));
+  EX_TRY(dmalloc(ex, (void**)&ex->thr, (size_t)cfg->chunk_fovs * sizeof(double)));
+  EX_TRY(dmalloc(ex, (void**)&ex->lab_thr, (size_t)cfg->chunk_fovs * HW * sizeof(int32_t)));
+  EX_TRY(dmalloc(ex, (void**)&ex->lab_given, (size_t)cfg->chunk_fovs * HW * sizeof(int32_t)));
+  ex->label_bytes = amt_label_scratch_bytes(cfg->chunk_fovs, cfg->height, cfg->width, cfg->max_label_value);
+  EX_TRY(dmalloc(ex, &ex->label_scratch, ex->label_bytes));
+  EX_TRY(dmalloc(ex, (void**)&ex->acc,
+                 (size_t)cfg->chunk_fovs * AMT_ACC_FIELDS(C) * cfg->max_labels * sizeof(uint64_t)));
+#undef EX_TRY
+#undef EX_CUDA
+  *out = ex;
+  return AMT_OK;
+}
+
+void amt_executor_destroy(amt_executor* ex) {
+  if (!ex) return;
+  cudaSetDevice(ex->cfg.device);
+  cudaDeviceSynchronize();
+  void* bufs[] = {ex->hw_lo, ex->hw_hi, ex->tmp_lo, ex->tmp_hi, ex->dog, ex->pre, ex->mm, ex->stats, ex->params,
+                  ex->sel_scratch, ex->hist256, ex->thr, ex->lab_thr, ex->lab_given, ex->label_scratch, ex->acc};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  for (int s = 0; s < 2; ++s) {
+    void* sb[] = {ex->in_slot[s], ex->given_slot[s], ex->tab_thr_slot[s], ex->tab_given_slot[s], ex->thr_slot[s],
+                  ex->cnt_thr_slot[s], ex->cnt_given_slot[s]};
+    for (void* b : sb)
+      if (b) cudaFree(b);
+    if (ex->ev_in[s]) cudaEventDestroy(ex->ev_in[s]);
+    if (ex->ev_done[s]) cudaEventDestroy(ex->ev_done[s]);
+    if (ex->ev_out[s]) cudaEventDestroy(ex->ev_out[s]);
+  }
+  if (ex->ev_start) cudaEventDestroy(ex->ev_start);
+  if (ex->ev_stop) cudaEventDestroy(ex->ev_stop);
+  if (ex->s_compute) cudaStreamDestroy(ex->s_compute);
+  if (ex->s_in) cudaStreamDestroy(ex->s_in);
+  if (ex->s_out) cudaStreamDestroy(ex->s_out);
+  delete ex;
+}
+
+size_t amt_executor_device_bytes(const amt_executor* ex) { return ex ? ex->device_bytes : 0; }
+
+int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_t* given_labels, int64_t n_fov,
+                            double* tables_thr, int32_t* counts_thr, double* tables_given, int32_t* counts_given,
+                            double* thresholds, int32_t* labels_thr, int32_t* labels_given, double* preprocessed) {
+  using namespace amt;
+  if (!ex || !fovs || !tables_thr || !counts_thr || n_fov <= 0) return AMT_ERR_INVALID;
+  const amt_fov_config& c = ex->cfg;
+  if (c.quantify_given_mask && given_labels && (!tables_given || !counts_given)) return AMT_ERR_INVALID;
+  AMT_CUDA_TRY(cudaSetDevice(c.device));
+  const int C = c.n_channels;
+  const int64_t HW = (int64_t)c.height * c.width;
+  const int64_t tab = (int64_t)AMT_TABLE_COLS(C) * c.max_labels;
+  AMT_CUDA_TRY(cudaEventRecord(ex->ev_start, ex->s_compute));
+  for (int64_t f0 = 0; f0 < n_fov; f0 += c.chunk_fovs) {
+    const int g = (int)((n_fov - f0 < c.chunk_fovs) ? n_fov - f0 : c.chunk_fovs);
+    AMT_TRY(process_chunk(ex, fovs + f0 * C * HW, given_labels ? given_labels + f0 * HW : nullptr, g,
+                          tables_thr + f0 * tab, counts_thr + f0, tables_given ? tables_given + f0 * tab : nullptr,
+                          counts_given ? counts_given + f0 : nullptr, thresholds ? thresholds + f0 : nullptr,
+                          labels_thr ? labels_thr + f0 * HW : nullptr, labels_given ? labels_given + f0 * HW : nullptr,
+                          preprocessed ? preprocessed + f0 * C * HW : nullptr));
+  }
+  AMT_CUDA_TRY(cudaEventRecord(ex->ev_stop, ex->s_compute));
+  return AMT_OK;
+}
+
+int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const int32_t* given_labels_host, int64_t n_fov,
+                          double* tables_thr_host, int32_t* counts_thr_host, double* tables_given_host,
+                          int32_t* counts_given_host, double* thresholds_host) {
+  using namespace amt;
+  if (!ex || !fovs_host || !tables_thr_host || !counts_thr_host || n_fov <= 0) return AMT_ERR_INVALID;
+  const amt_fov_config& c = ex->cfg;
+  const bool given = c.quantify_given_mask && given_labels_host;
+  if (given && (!tables_given_host || !counts_given_host)) return AMT_ERR_INVALID;
+  AMT_CUDA_TRY(cudaSetDevice(c.device));
+  AMT_TRY(alloc_host_slots(ex));
+  const int C = c.n_channels;
+  const int64_t HW = (int64_t)c.height * c.width;
+  const int64_t tab = (int64_t)AMT_TABLE_COLS(C) * c.max_labels;
+  AMT_CUDA_TRY(cudaEventRecord(ex->ev_start, ex->s_compute));
+  int64_t chunk = 0;
+  for (int64_t f0 = 0; f0 < n_fov; f0 += c.chunk_fovs, ++chunk) {
+    const int g = (int)((n_fov - f0 < c.chunk_fovs) ? n_fov - f0 : c.chunk_fovs);
+    const int s = (int)(chunk & 1);
+    // input slot s is free once the compute that last read it has finished
+    if (chunk >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_in, ex->ev_done[s], 0));
+    AMT_CUDA_TRY(cudaMemcpyAsync(ex->in_slot[s], fovs_host + f0 * C * HW, (size_t)g * C * HW * sizeof(uint16_t),
+                                 cudaMemcpyHostToDevice, ex->s_in));
+    if (given)
+      AMT_CUDA_TRY(cudaMemcpyAsync(ex->given_slot[s], given_labels_host + f0 * HW, (size_t)g * HW * sizeof(int32_t),
+                                   cudaMemcpyHostToDevice, ex->s_in));
+    AMT_CUDA_TRY(cudaEventRecord(ex->ev_in[s], ex->s_in));
+    // output slot s is free once its previous D2H has finished
+    AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_compute, ex->ev_in[s], 0));
+    if (chunk >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_compute, ex->ev_out[s], 0));
+    AMT_TRY(process_chunk(ex, ex->in_slot[s], given ? ex->given_slot[s] : nullptr, g, ex->tab_thr_slot[s],
+                          ex->cnt_thr_slot[s], ex->tab_given_slot[s], ex->cnt_given_slot[s], ex->thr_slot[s], nullptr,
+                          nullptr, nullptr));
+    AMT_CUDA_TRY(cudaEventRecord(ex->ev_done[s], ex->s_compute));
+    AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_out, ex->ev_done[s], 0));
+    AMT_CUDA_TRY(cudaMemcpyAsync(tables_thr_host + f0 * tab, ex->tab_thr_slot[s], (size_t)g * tab * sizeof(double),
+                                 cudaMemcpyDeviceToHost, ex->s_out));
+    AMT_CUDA_TRY(cudaMemcpyAsync(counts_thr_host + f0, ex->cnt_thr_slot[s], (size_t)g * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, ex->s_out));
+    if (given) {
+      AMT_CUDA_TRY(cudaMemcpyAsync(tables_given_host + f0 * tab, ex->tab_given_slot[s], (size_t)g * tab * sizeof(double),
+                                   cudaMemcpyDeviceToHost, ex->s_out));
+      AMT_CUDA_TRY(cudaMemcpyAsync(counts_given_host + f0, ex->cnt_given_slot[s], (size_t)g * sizeof(int32_t),
+                                   cudaMemcpyDeviceToHost, ex->s_out));
+    }
+    if (thresholds_host)
+      AMT_CUDA_TRY(cudaMemcpyAsync(thresholds_host + f0, ex->thr_slot[s], (size_t)g * sizeof(double),
+                                   cudaMemcpyDeviceToHost, ex->s_out));
+    AMT_CUDA_TRY(cudaEventRecord(ex->ev_out[s], ex->s_out));
+  }
+  AMT_CUDA_TRY(cudaEventRecord(ex->ev_stop, ex->s_compute));
+  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_in));
+  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_compute));
+  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_out));
+  return AMT_OK;
+}
+
+int amt_executor_sync(amt_executor* ex) {
+  using namespace amt;
+  if (!ex) return AMT_ERR_INVALID;
+  AMT_CUDA_TRY(cudaSetDevice(ex->cfg.device));
+  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_in));
+  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_compute));
+  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_out));
+  return AMT_OK;
+}
+
+float amt_executor_last_ms(amt_executor* ex) {
+  if (!ex) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(ex->ev_stop) != cudaSuccess) return -1.0f;
+  if (cudaEventElapsedTime(&ms, ex->ev_start, ex->ev_stop) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,44 @@
+// Cross-file launch helpers used by the fused executor (strided variants of the C-ABI calls).
+#pragma once
+
+#include "common.cuh"
+
+namespace amt {
+
+int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st);
+
+int dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,
+          const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, double* tmp_lo, double* tmp_hi,
+          uint64_t* minmax, cudaStream_t st);
+
+// hist256 (optional): plane i gets a histogram iff i % hist_every == hist_offset, stored at
+// hist256[(i / hist_every) * 256].
+int map_launch(const void* in, int in_dtype, double* out, int64_t n_img, int64_t n, const amt_map_params* params,
+               uint32_t* hist256, int hist_every, int hist_offset, cudaStream_t st);
+
+int plan_dog_rescale(const double* stats, const uint64_t* mm, int64_t n_img, double g_bg, double g_lo, double g_hi,
+                     double o1, double o2, amt_map_params* params, cudaStream_t st);
+
+// mode 0 reads params[img * pstride + poffset]
+int otsu_launch(const uint32_t* hist, int mode, const amt_map_params* params, int64_t pstride, int64_t poffset,
+                const uint64_t* mm, int64_t n_img, double* thresholds, void* scratch, size_t scratch_bytes,
+                cudaStream_t st);
+
+// in_stride: elements between consecutive input images
+int label_launch(const void* in, int in_kind, int64_t in_stride, const double* thresholds, int64_t max_value,
+                 int64_t n_img, int64_t h, int64_t w, int clear_border, int32_t* labels_out, int32_t* counts,
+                 void* scratch, size_t scratch_bytes, cudaStream_t st);
+
+int region_reduce(const int32_t* labels, const uint16_t* channels, int n_channels, int64_t img_stride, int64_t chan_stride,
+                  int64_t n_img, int64_t h, int64_t w, int64_t max_labels, uint64_t* acc, cudaStream_t st);
+int region_finalize(const uint64_t* acc, const int32_t* counts, int n_channels, int64_t n_img, int64_t max_labels,
+                    double* table, cudaStream_t st);
+
+}  // namespace amt
+
+namespace amt {
+size_t region_shape_scratch_bytes(int64_t n_img, int64_t h, int64_t w, int64_t max_labels);
+int region_shape(const int32_t* labels, const uint64_t* acc, int n_channels, const int32_t* counts, int64_t n_img,
+                 int64_t h, int64_t w, int64_t max_labels, double* table, void* scratch, size_t scratch_bytes,
+                 cudaStream_t st);
+}  // namespace amt

@@ -1,0 +1,381 @@
+// Elementwise stage: background subtraction / clip / percentile rescale, the fused 256-bin
+// histogram, Otsu's scan and thresholding.
+//
+// Reference path: operations.py:97 (np.clip(dog - level, 0, None)), operations.py:50-54
+// ski.exposure.rescale_intensity [3p], operations.py:186/:214 ski.filters.threshold_otsu [3p],
+// operations.py:216 (intensities > threshold).  SURVEY.md 8a items 4-6.
+//
+// Every arithmetic step is the separately rounded float64 operation NumPy performs (sub, max,
+// min, sub, div, mul, add), so the output plane is bit-identical given identical percentiles.
+// The 256-bin histogram reproduces np.histogram's uniform-bin fast path: candidate bin from
+// ((x-first)/(last-first))*256, then the correction against np.linspace edges, which are
+// regenerated on device with linspace's own arithmetic (i*step + start, last edge = stop).
+// Histogram updates are warp-aggregated (__match_any_sync) into per-warp private shared-memory
+// histograms, then flushed with one global atomic per non-empty bin.  HBM-bound: 8 B read +
+// 8 B written per sample.
+
+#include "common.cuh"
+
+namespace amt {
+
+__device__ __forceinline__ double map_value(double x, const amt_map_params& p) {
+  if (p.flags & AMT_MAP_FILL) return p.o1;
+  double y = x;
+  if (p.flags & AMT_MAP_SUBCLIP) y = fmax(dsub(y, p.lvl), 0.0);
+  if (p.flags & AMT_MAP_RESCALE) {
+    y = fmin(fmax(y, p.p1), p.p2);
+    if (p.p1 != p.p2) {
+      y = ddiv(dsub(y, p.p1), dsub(p.p2, p.p1));
+      y = dadd(dmul(y, dsub(p.o2, p.o1)), p.o1);
+    } else {
+      y = fmin(fmax(y, p.o1), p.o2);
+    }
+  }
+  return y;
+}
+
+struct HistRange {
+  double first, last, denom, step;
+  bool step_zero;
+};
+
+__device__ __forceinline__ HistRange make_hist_range(double first, double last) {
+  HistRange r;
+  if (first == last) {  // numpy _get_outer_edges widens a degenerate range
+    first = dsub(first, 0.5);
+    last = dadd(last, 0.5);
+  }
+  r.first = first;
+  r.last = last;
+  r.denom = dsub(last, first);
+  r.step = ddiv(r.denom, 256.0);
+  r.step_zero = (r.step == 0.0);
+  return r;
+}
+
+// np.linspace(first, last, 257)[i]
+__device__ __forceinline__ double hist_edge(const HistRange& r, int i) {
+  if (i >= 256) return r.last;
+  if (r.step_zero) return dadd(dmul(ddiv((double)i, 256.0), r.denom), r.first);
+  return dadd(dmul((double)i, r.step), r.first);
+}
+
+__device__ __forceinline__ int hist_bin(const HistRange& r, double x) {
+  double f = dmul(ddiv(dsub(x, r.first), r.denom), 256.0);
+  int idx = (int)f;
+  idx = idx < 0 ? 0 : idx;
+  if (idx >= 256) idx = 255;
+  if (x < hist_edge(r, idx)) {
+    idx -= 1;
+  }
+  idx = idx < 0 ? 0 : idx;
+  if (idx != 255 && x >= hist_edge(r, idx + 1)) idx += 1;
+  return idx;
+}
+
+__device__ __forceinline__ void hist_add_warp(uint32_t* wh, int bin, bool valid) {
+  const int key = valid ? bin : -1;
+  const unsigned m = __match_any_sync(0xffffffffu, key);
+  if (valid && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&wh[bin], (uint32_t)__popc(m));
+}
+
+template <typename InT>
+__device__ __forceinline__ double map_load(const InT* p);
+template <>
+__device__ __forceinline__ double map_load<double>(const double* p) {
+  return *p;
+}
+template <>
+__device__ __forceinline__ double map_load<uint16_t>(const uint16_t* p) {
+  return (double)*p;
+}
+
+template <typename InT, bool HIST>
+__global__ void __launch_bounds__(256)
+map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, const amt_map_params* __restrict__ params,
+           uint32_t* __restrict__ hist256, int hist_every, int hist_offset) {
+  __shared__ uint32_t s_hist[HIST ? 8 * 256 : 1];
+  const int64_t img = blockIdx.y;
+  const amt_map_params p = params[img];
+  const InT* src = in + img * n;
+  double* dst = out + img * n;
+  const bool do_hist = HIST && hist256 != nullptr && (img % hist_every) == hist_offset;
+  HistRange hr;
+  uint32_t* wh = s_hist + (threadIdx.x >> 5) * 256;
+  if (HIST) {
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) s_hist[i] = 0;
+    hr = make_hist_range(p.hist_first, p.hist_last);
+    __syncthreads();
+  }
+  const int64_t step = (int64_t)gridDim.x * 256;
+  const int64_t start = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  // warp-uniform trip count so that __match_any_sync sees the full warp
+  const int64_t warp_start = start - (threadIdx.x & 31);
+  for (int64_t i = start, wi = warp_start; wi < n; i += step, wi += step) {
+    const bool valid = i < n;
+    double y = 0.0;
+    if (valid) {
+      y = map_value(map_load<InT>(src + i), p);
+      dst[i] = y;
+    }
+    if (HIST && do_hist) hist_add_warp(wh, valid ? hist_bin(hr, y) : 0, valid);
+  }
+  if (HIST && do_hist) {
+    __syncthreads();
+    uint32_t c = 0;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) c += s_hist[wv * 256 + threadIdx.x];
+    if (c) atomicAdd(&hist256[(img / hist_every) * 256 + threadIdx.x], c);
+  }
+}
+
+// standalone 256-bin float histogram (range from min/max keys)
+__global__ void __launch_bounds__(256)
+hist256_kernel(const double* __restrict__ data, int64_t n, const uint64_t* __restrict__ mm, uint32_t* __restrict__ hist256) {
+  __shared__ uint32_t s_hist[8 * 256];
+  const int64_t img = blockIdx.y;
+  const double* src = data + img * n;
+  for (int i = threadIdx.x; i < 8 * 256; i += 256) s_hist[i] = 0;
+  const HistRange hr = make_hist_range(key_to_f64(mm[2 * img]), key_to_f64(mm[2 * img + 1]));
+  uint32_t* wh = s_hist + (threadIdx.x >> 5) * 256;
+  __syncthreads();
+  const int64_t step = (int64_t)gridDim.x * 256;
+  const int64_t start = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  for (int64_t i = start, wi = start - (threadIdx.x & 31); wi < n; i += step, wi += step) {
+    const bool valid = i < n;
+    hist_add_warp(wh, valid ? hist_bin(hr, src[i]) : 0, valid);
+  }
+  __syncthreads();
+  uint32_t c = 0;
+#pragma unroll
+  for (int wv = 0; wv < 8; ++wv) c += s_hist[wv * 256 + threadIdx.x];
+  if (c) atomicAdd(&hist256[img * 256 + threadIdx.x], c);
+}
+
+__global__ void plan_dog_rescale_kernel(const double* __restrict__ stats, const uint64_t* __restrict__ mm, int64_t n_img,
+                                        double g_bg, double g_lo, double g_hi, double o1, double o2,
+                                        amt_map_params* __restrict__ params) {
+  const int64_t img = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= n_img) return;
+  const double* s = stats + img * 6;
+  amt_map_params p;
+  p.lvl = np_lerp(s[0], s[1], g_bg);  // np.percentile(dog, percentile)
+  // order statistics commute with the monotone map x -> max(x - lvl, 0)
+  const double a1 = fmax(dsub(s[2], p.lvl), 0.0), b1 = fmax(dsub(s[3], p.lvl), 0.0);
+  const double a2 = fmax(dsub(s[4], p.lvl), 0.0), b2 = fmax(dsub(s[5], p.lvl), 0.0);
+  p.p1 = np_lerp(a1, b1, g_lo);
+  p.p2 = np_lerp(a2, b2, g_hi);
+  p.o1 = o1;
+  p.o2 = o2;
+  const double cmin = fmax(dsub(key_to_f64(mm[2 * img]), p.lvl), 0.0);
+  const double cmax = fmax(dsub(key_to_f64(mm[2 * img + 1]), p.lvl), 0.0);
+  p.flags = (cmin == cmax) ? AMT_MAP_FILL : (AMT_MAP_SUBCLIP | AMT_MAP_RESCALE);
+  p.pad = 0;
+  // range of the output plane: the map is monotone, so it is attained at the clipped min / max
+  amt_map_params q = p;
+  q.flags &= ~AMT_MAP_SUBCLIP;
+  const double fa = map_value(cmin, q), fb = map_value(cmax, q);
+  p.hist_first = fmin(fa, fb);
+  p.hist_last = fmax(fa, fb);
+  params[img] = p;
+}
+
+// ------------------------------------------------------------------ Otsu scan
+// One block (64 threads) per plane.  Warp 1 lane 0 runs the reversed cumulative sums
+// (weight2 float32, mean2 numerator float64) into scratch, then warp 0 lane 0 runs the forward
+// ones and keeps the first maximum of w1[i]*w2[i+1]*(m1[i]-m2[i+1])^2.  The sums are
+// sequential on purpose: NumPy's cumsum is, and float32/float64 addition does not reassociate.
+__global__ void otsu_kernel(const uint32_t* __restrict__ hist, int mode, const amt_map_params* __restrict__ params,
+                            int64_t pstride, int64_t poffset, const uint64_t* __restrict__ mm,
+                            float* __restrict__ w2_scratch, double* __restrict__ m2_scratch,
+                            double* __restrict__ thresholds) {
+  __shared__ float s_w2[256];
+  __shared__ double s_m2[256];
+  const int64_t img = blockIdx.x;
+  int nb, lo_bin = 0;
+  HistRange hr;
+  const uint32_t* h;
+  float* w2;
+  double* m2;
+  if (mode == 2) {
+    const int vmin = (int)mm[2 * img], vmax = (int)mm[2 * img + 1];
+    lo_bin = vmin;
+    nb = vmax - vmin + 1;
+    h = hist + img * 65536 + vmin;
+    w2 = w2_scratch + img * 65536;
+    m2 = m2_scratch + img * 65536;
+  } else {
+    nb = 256;
+    h = hist + img * 256;
+    w2 = s_w2;
+    m2 = s_m2;
+    double first, last;
+    if (mode == 0) {
+      first = params[img * pstride + poffset].hist_first;
+      last = params[img * pstride + poffset].hist_last;
+    } else {
+      first = key_to_f64(mm[2 * img]);
+      last = key_to_f64(mm[2 * img + 1]);
+    }
+    if (first == last) {  // constant plane: skimage returns that value (nothing is > it)
+      if (threadIdx.x == 0) thresholds[img] = first;
+      return;
+    }
+    hr = make_hist_range(first, last);
+  }
+  auto center = [&](int i) -> double {
+    if (mode == 2) return (double)(lo_bin + i);
+    return ddiv(dadd(hist_edge(hr, i), hist_edge(hr, i + 1)), 2.0);
+  };
+  if (nb < 2) {  // constant plane: skimage returns the single value
+    if (threadIdx.x == 0) thresholds[img] = center(0);
+    return;
+  }
+  if (threadIdx.x == 32) {
+    float wsum = 0.0f;
+    double msum = 0.0;
+    for (int i = nb - 1; i >= 1; --i) {
+      const float c = (float)h[i];
+      wsum = __fadd_rn(wsum, c);
+      msum = dadd(msum, dmul((double)c, center(i)));
+      w2[i] = wsum;
+      m2[i] = ddiv(msum, (double)wsum);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float wsum = 0.0f;
+    double msum = 0.0, best = -1.0;
+    int best_i = 0;
+    for (int i = 0; i < nb - 1; ++i) {
+      const float c = (float)h[i];
+      wsum = __fadd_rn(wsum, c);
+      msum = dadd(msum, dmul((double)c, center(i)));
+      const double mean1 = ddiv(msum, (double)wsum);
+      const float ww = __fmul_rn(wsum, w2[i + 1]);
+      const double d = dsub(mean1, m2[i + 1]);
+      const double var = dmul((double)ww, dmul(d, d));
+      if (i == 0 || var > best) {
+        best = var;
+        best_i = i;
+      }
+    }
+    thresholds[img] = center(best_i);
+  }
+}
+
+template <typename InT>
+__global__ void __launch_bounds__(256)
+threshold_gt_kernel(const InT* __restrict__ data, int64_t n, const double* __restrict__ thresholds, uint8_t* __restrict__ mask) {
+  const int64_t img = blockIdx.y;
+  const double t = thresholds[img];
+  const InT* src = data + img * n;
+  uint8_t* dst = mask + img * n;
+  const int64_t step = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += step)
+    dst[i] = map_load<InT>(src + i) > t ? 1 : 0;
+}
+
+static unsigned stream_blocks(int64_t n, int64_t n_img, int per_thread) {
+  int64_t bx = ceil_div(n, 256 * (int64_t)per_thread);
+  const int64_t cap = ceil_div((int64_t)kNumSMs * 8, n_img);
+  if (bx > cap) bx = cap;
+  return (unsigned)(bx < 1 ? 1 : bx);
+}
+
+int map_launch(const void* in, int in_dtype, double* out, int64_t n_img, int64_t n, const amt_map_params* params,
+               uint32_t* hist256, int hist_every, int hist_offset, cudaStream_t st) {
+  if (!in || !out || !params || n_img <= 0 || n <= 0 || n_img > 65535 || hist_every < 1) return AMT_ERR_INVALID;
+  dim3 grid(stream_blocks(n, n_img, 8), (unsigned)n_img);
+  if (in_dtype == AMT_F64) {
+    if (hist256)
+      map_kernel<double, true><<<grid, 256, 0, st>>>((const double*)in, out, n, params, hist256, hist_every, hist_offset);
+    else
+      map_kernel<double, false><<<grid, 256, 0, st>>>((const double*)in, out, n, params, nullptr, 1, 0);
+  } else if (in_dtype == AMT_U16) {
+    if (hist256)
+      map_kernel<uint16_t, true><<<grid, 256, 0, st>>>((const uint16_t*)in, out, n, params, hist256, hist_every, hist_offset);
+    else
+      map_kernel<uint16_t, false><<<grid, 256, 0, st>>>((const uint16_t*)in, out, n, params, nullptr, 1, 0);
+  } else {
+    return AMT_ERR_UNSUPPORTED;
+  }
+  AMT_LAUNCH_CHECK();
+  return AMT_OK;
+}
+
+int plan_dog_rescale(const double* stats, const uint64_t* mm, int64_t n_img, double g_bg, double g_lo, double g_hi,
+                     double o1, double o2, amt_map_params* params, cudaStream_t st) {
+  if (!stats || !mm || !params || n_img <= 0) return AMT_ERR_INVALID;
+  plan_dog_rescale_kernel<<<(unsigned)ceil_div(n_img, 128), 128, 0, st>>>(stats, mm, n_img, g_bg, g_lo, g_hi, o1, o2, params);
+  AMT_LAUNCH_CHECK();
+  return AMT_OK;
+}
+
+int otsu_launch(const uint32_t* hist, int mode, const amt_map_params* params, int64_t pstride, int64_t poffset,
+                const uint64_t* mm, int64_t n_img, double* thresholds, void* scratch, size_t scratch_bytes,
+                cudaStream_t st) {
+  if (!hist || !thresholds || n_img <= 0 || mode < 0 || mode > 2) return AMT_ERR_INVALID;
+  if (mode == 0 && !params) return AMT_ERR_INVALID;
+  if (mode != 0 && !mm) return AMT_ERR_INVALID;
+  float* w2 = nullptr;
+  double* m2 = nullptr;
+  if (mode == 2) {
+    if (!scratch || scratch_bytes < (size_t)n_img * 65536 * 12) return AMT_ERR_CAPACITY;
+    m2 = (double*)scratch;
+    w2 = (float*)((char*)scratch + (size_t)n_img * 65536 * 8);
+  }
+  otsu_kernel<<<(unsigned)n_img, 64, 0, st>>>(hist, mode, params, pstride, poffset, mm, w2, m2, thresholds);
+  AMT_LAUNCH_CHECK();
+  return AMT_OK;
+}
+
+}  // namespace amt
+
+extern "C" {
+
+int amt_map(const void* in, int in_dtype, double* out, int64_t n_img, int64_t n, const amt_map_params* params,
+            uint32_t* hist256, amt_stream_t stream) {
+  return amt::map_launch(in, in_dtype, out, n_img, n, params, hist256, 1, 0, amt::as_stream(stream));
+}
+
+int amt_plan_dog_rescale(const double* order_stats, const uint64_t* minmax_keys, int64_t n_img, double g_bg,
+                         double g_lo, double g_hi, double o1, double o2, amt_map_params* params, amt_stream_t stream) {
+  return amt::plan_dog_rescale(order_stats, minmax_keys, n_img, g_bg, g_lo, g_hi, o1, o2, params, amt::as_stream(stream));
+}
+
+int amt_hist256_f64(const double* data, int64_t n_img, int64_t n, const uint64_t* minmax_keys, uint32_t* hist256,
+                    amt_stream_t stream) {
+  using namespace amt;
+  if (!data || !minmax_keys || !hist256 || n_img <= 0 || n <= 0 || n_img > 65535) return AMT_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  AMT_CUDA_TRY(cudaMemsetAsync(hist256, 0, (size_t)n_img * 256 * sizeof(uint32_t), st));
+  hist256_kernel<<<dim3(stream_blocks(n, n_img, 8), (unsigned)n_img), 256, 0, st>>>(data, n, minmax_keys, hist256);
+  AMT_LAUNCH_CHECK();
+  return AMT_OK;
+}
+
+size_t amt_otsu_scratch_bytes(int mode, int64_t n_img) { return mode == 2 ? (size_t)n_img * 65536 * 12 : 0; }
+
+int amt_otsu(const uint32_t* hist, int mode, const amt_map_params* params, const uint64_t* minmax_keys, int64_t n_img,
+             double* thresholds, void* scratch, size_t scratch_bytes, amt_stream_t stream) {
+  return amt::otsu_launch(hist, mode, params, 1, 0, minmax_keys, n_img, thresholds, scratch, scratch_bytes,
+                          amt::as_stream(stream));
+}
+
+int amt_threshold_gt(const void* data, int in_dtype, int64_t n_img, int64_t n, const double* thresholds, uint8_t* mask,
+                     amt_stream_t stream) {
+  using namespace amt;
+  if (!data || !thresholds || !mask || n_img <= 0 || n <= 0 || n_img > 65535) return AMT_ERR_INVALID;
+  dim3 grid(stream_blocks(n, n_img, 8), (unsigned)n_img);
+  if (in_dtype == AMT_F64)
+    threshold_gt_kernel<double><<<grid, 256, 0, as_stream(stream)>>>((const double*)data, n, thresholds, mask);
+  else if (in_dtype == AMT_U16)
+    threshold_gt_kernel<uint16_t><<<grid, 256, 0, as_stream(stream)>>>((const uint16_t*)data, n, thresholds, mask);
+  else
+    return AMT_ERR_UNSUPPORTED;
+  AMT_LAUNCH_CHECK();
+  return AMT_OK;
+}
+
+}  // extern "C"

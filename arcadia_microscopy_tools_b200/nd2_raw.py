@@ -1,0 +1,90 @@
+"""Minimal host-side reader for the raw frames of uncompressed Nikon ND2 files.
+
+File decoding stays on the host (BASELINE.json north_star).  The reference decodes through
+the third-party ``nd2`` package (``nikon.py:25-43`` -> ``nd2.ND2File.asarray``) and also parses
+rich metadata; this reader only does what the B200 path needs: hand back the uint16 pixel
+block in the ``(frames, C, Y, X)`` layout ``nd2.asarray()`` produces so it can be copied into
+pinned staging.  Metadata parsing is out of scope.
+
+Container layout (ND2 v3): a sequence of chunks
+``[u32 magic 0x0ABECEDA][u32 name_len][u64 data_len][name (name_len bytes)][data]``; the last
+8 bytes of the file hold the offset of the chunk-map chunk whose payload is a list of
+``name!`` + ``u64 offset`` + ``u64 length`` records.  Frame ``i`` is chunk ``ImageDataSeq|i!``:
+an 8-byte float64 timestamp followed by little-endian samples in (Y, X, C) interleaved order.
+"""
+
+from __future__ import annotations
+
+import struct
+from pathlib import Path
+
+import numpy as np
+
+_MAGIC = 0x0ABECEDA
+
+
+def _read_chunk(buf: bytes, offset: int) -> bytes:
+    magic, name_len, data_len = struct.unpack_from("<IIQ", buf, offset)
+    if magic != _MAGIC:
+        raise ValueError(f"not an ND2 chunk at offset {offset} (magic {magic:#x})")
+    start = offset + 16 + name_len
+    return buf[start : start + data_len]
+
+
+def _chunk_map(buf: bytes) -> dict[bytes, tuple[int, int]]:
+    (map_offset,) = struct.unpack_from("<Q", buf, len(buf) - 8)
+    payload = _read_chunk(buf, map_offset)
+    out: dict[bytes, tuple[int, int]] = {}
+    pos = 0
+    while pos < len(payload):
+        end = payload.find(b"!", pos)
+        if end < 0:
+            break
+        name = payload[pos : end + 1]
+        if name.startswith(b"ND2 CHUNK MAP SIGNATURE"):
+            break
+        off, length = struct.unpack_from("<QQ", payload, end + 1)
+        out[name] = (off, length)
+        pos = end + 1 + 16
+    return out
+
+
+def _lite_variant_uint(payload: bytes, key: str) -> int:
+    """Value of a 32-bit integer entry of a CLX-lite variant block: entries are
+    ``[u8 type][u8 name_len][utf-16le name, NUL terminated][value]``."""
+    needle = key.encode("utf-16le") + b"\x00\x00"
+    pos = payload.find(needle)
+    if pos < 0:
+        raise KeyError(key)
+    (val,) = struct.unpack_from("<I", payload, pos + len(needle))
+    return int(val)
+
+
+def read_nd2_frames(path: str | Path) -> np.ndarray:
+    """Return the pixel data as ``(n_frames, C, Y, X)`` uint16, C-contiguous."""
+    buf = Path(path).read_bytes()
+    cmap = _chunk_map(buf)
+    attrs = _read_chunk(buf, cmap[b"ImageAttributesLV!"][0])
+    width = _lite_variant_uint(attrs, "uiWidth")
+    height = _lite_variant_uint(attrs, "uiHeight")
+    comps = _lite_variant_uint(attrs, "uiComp")
+    bpc = _lite_variant_uint(attrs, "uiBpcInMemory")
+    nseq = _lite_variant_uint(attrs, "uiSequenceCount")
+    if bpc != 16:
+        raise ValueError(f"only 16-bit ND2 frames are supported, got {bpc} bits")
+    frames = np.empty((nseq, comps, height, width), dtype=np.uint16)
+    n_samples = height * width * comps
+    for i in range(nseq):
+        off, _ = cmap[f"ImageDataSeq|{i}!".encode()]
+        data = _read_chunk(buf, off)
+        px = np.frombuffer(data, dtype="<u2", count=n_samples, offset=8)
+        frames[i] = px.reshape(height, width, comps).transpose(2, 0, 1)
+    return frames
+
+
+def read_nd2(path: str | Path) -> np.ndarray:
+    """Pixel block squeezed like ``nd2.ND2File.asarray()``: singleton frame/channel axes
+    dropped, e.g. ``(C, Y, X)`` for a single multichannel frame, ``(T, Y, X)`` for a
+    single-channel series."""
+    frames = read_nd2_frames(path)
+    return np.ascontiguousarray(np.squeeze(frames)) if frames.ndim > 2 else frames

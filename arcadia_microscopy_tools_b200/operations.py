@@ -1,0 +1,206 @@
+"""Image operations of the preprocessing / thresholding path, on the GPU.
+
+Signatures, defaults, validation order and error messages follow the reference's
+``operations.py`` (``rescale_by_percentile`` :10-54, ``subtract_background_dog`` :57-97,
+``crop_to_center`` :100-132, ``apply_threshold`` :135-216).  Arithmetic follows the scikit-image
+/ SciPy / NumPy routines those lines dispatch to and runs in hand-written CUDA
+kernels behind ``libamt_b200.so``; there is no CPU path.
+
+Inputs may be NumPy arrays (result: NumPy array, as in the reference) or CUDA tensors produced
+by another operation of this module (result stays on the device; ``Pipeline`` uses this to keep
+a whole chain resident).  ``_batched=True`` (used by ``Pipeline(parallel=True)``) treats the
+first axis as independent slices, exactly like the reference's per-slice thread map.
+"""
+
+from __future__ import annotations
+
+from typing import Literal
+
+import numpy as np
+
+from . import _gpu, _lib
+
+_THRESHOLD_METHODS = ("otsu", "li", "yen", "isodata", "mean", "minimum", "triangle", "local", "niblack", "sauvola")
+
+
+def _device_op(func):
+    func.__amt_device_op__ = True
+    return func
+
+
+def _prepare(intensities, *, allow_bool: bool = False):
+    """-> (device tensor, numpy dtype of the logical input, was_numpy).  Integer dtypes other
+    than uint8/uint16 are promoted to float64 when that is exact (|v| < 2**53)."""
+    if _gpu.is_device_array(intensities):
+        torch = _gpu.torch_mod()
+        if intensities.dtype in (torch.int16, torch.uint16):
+            return intensities, np.dtype(np.uint16), False
+        if intensities.dtype == torch.float64:
+            return intensities, np.dtype(np.float64), False
+        raise TypeError(f"unsupported device dtype {intensities.dtype}")
+    a = np.asarray(intensities)
+    if a.dtype == np.uint16 or a.dtype == np.float64:
+        return _gpu.to_device(a), a.dtype, True
+    if a.dtype == np.uint8:
+        return _gpu.to_device(a.astype(np.uint16)), a.dtype, True
+    if a.dtype == np.bool_ and allow_bool:
+        return _gpu.to_device(a.astype(np.float64)), a.dtype, True
+    if a.dtype.kind in "iu":
+        if a.size and max(abs(int(a.min())), abs(int(a.max()))) >= 2**53:
+            raise TypeError("integer values beyond 2**53 are not representable on the float64 path")
+        return _gpu.to_device(a.astype(np.float64)), a.dtype, True
+    raise TypeError(
+        f"dtype {a.dtype} is outside the B200 hot path (supported: uint8, uint16, integer, float64)"
+    )
+
+
+def _finish(out, was_numpy: bool):
+    return _gpu.to_host(out) if was_numpy else out
+
+
+def _slices(t, batched: bool):
+    """View as (n_img, n) planes: one plane for the whole array unless batched."""
+    if batched:
+        return t.reshape(t.shape[0], -1)
+    return t.reshape(1, -1)
+
+
+# ---------------------------------------------------------------------------------------------
+@_device_op
+def rescale_by_percentile(
+    intensities,
+    percentile_range: tuple[float, float] = (0, 100),
+    out_range: tuple[float, float] = (0, 1),
+    *,
+    _batched: bool = False,
+):
+    """Percentile-based contrast stretching (ref: ``operations.py:10-54``).
+
+    ``p1, p2 = np.percentile(x, percentile_range)`` then
+    ``skimage.exposure.rescale_intensity(x, in_range=(p1, p2), out_range=out_range)``; empty
+    input -> zeros, constant input -> ``out_range[0]`` everywhere.  Output float64.
+    """
+    if not (0 <= percentile_range[0] < percentile_range[1] <= 100):
+        raise ValueError(
+            f"Invalid percentile range: {percentile_range}. "
+            f"Values must be in ascending order between 0 and 100."
+        )
+    if not _gpu.is_device_array(intensities) and np.asarray(intensities).size == 0:
+        return np.zeros_like(np.asarray(intensities), dtype=float)
+    t, _, was_numpy = _prepare(intensities)
+    planes = _slices(t, _batched)
+    is_f64 = _gpu.dtype_code(planes) == _lib.AMT_F64
+    mm = _gpu.minmax_keys(planes)
+    mnmx = _gpu.minmax_values(mm, is_f64)
+    pcts = _gpu.percentiles(planes, [percentile_range[0], percentile_range[1]], mm if is_f64 else None)
+    o1, o2 = float(out_range[0]), float(out_range[1])
+    params = []
+    for i in range(planes.shape[0]):
+        p = _lib.MapParams()
+        p.o1, p.o2 = o1, o2
+        if mnmx[i, 0] == mnmx[i, 1]:
+            p.flags = _lib.AMT_MAP_FILL
+        else:
+            p.flags = _lib.AMT_MAP_RESCALE
+            p.p1, p.p2 = float(pcts[i, 0]), float(pcts[i, 1])
+        params.append(p)
+    out = _gpu.apply_map(planes, params).reshape(t.shape)
+    return _finish(out, was_numpy)
+
+
+@_device_op
+def subtract_background_dog(
+    intensities,
+    low_sigma: float = 0.6,
+    high_sigma: float = 16.0,
+    percentile: float = 0,
+    *,
+    _batched: bool = False,
+):
+    """Difference-of-Gaussians background subtraction (ref: ``operations.py:57-97``).
+
+    ``dog = skimage.filters.difference_of_gaussians(x, low, high)`` (float64, every axis
+    filtered, edge-clamped, truncate 4), ``level = np.percentile(dog, percentile)``,
+    ``np.clip(dog - level, 0, None)``.  Bit-identical to the scipy-backed reference.
+    """
+    if not (0 <= percentile <= 100):
+        raise ValueError(f"Percentile must be between 0 and 100, got {percentile}")
+    if low_sigma >= high_sigma:
+        raise ValueError(f"low_sigma ({low_sigma}) must be smaller than high_sigma ({high_sigma})")
+    if not _gpu.is_device_array(intensities) and np.asarray(intensities).size == 0:
+        return np.zeros_like(np.asarray(intensities), dtype=float)
+    t, np_dtype, was_numpy = _prepare(intensities, allow_bool=True)
+    scale = _gpu.input_scale(np_dtype)
+    slice_ndim = t.ndim - 1 if _batched else t.ndim
+    if slice_ndim == 2:
+        stack = t if _batched else t.reshape(1, *t.shape)
+        dog, mm = _gpu.dog2d(stack, scale, low_sigma, high_sigma)
+        planes = dog.reshape(dog.shape[0], -1)
+    else:
+        torch = _gpu.torch_mod()
+        parts = [t[i] for i in range(t.shape[0])] if _batched else [t]
+        dogs = [_gpu.sub_f64(_gpu.gaussian_nd(p, scale, low_sigma), _gpu.gaussian_nd(p, scale, high_sigma)) for p in parts]
+        planes = torch.stack([d.reshape(-1) for d in dogs])
+        mm = _gpu.minmax_keys(planes)
+    levels = _gpu.percentiles(planes, [percentile], mm)
+    params = []
+    for i in range(planes.shape[0]):
+        p = _lib.MapParams()
+        p.flags = _lib.AMT_MAP_SUBCLIP
+        p.lvl = float(levels[i, 0])
+        params.append(p)
+    out = _gpu.apply_map(planes, params).reshape(t.shape)
+    return _finish(out, was_numpy)
+
+
+def crop_to_center(intensities, output_shape: tuple[int, int], *, _batched: bool = False):
+    """Centred crop of the last two axes, clamped to the image size; returns a view
+    (ref: ``operations.py:100-132``).  Pure indexing, works on NumPy arrays and CUDA tensors."""
+    height, width = intensities.shape[-2:]
+    crop_height = min(height, output_shape[0])
+    crop_width = min(width, output_shape[1])
+    top = (height - crop_height) // 2
+    left = (width - crop_width) // 2
+    return intensities[..., top : top + crop_height, left : left + crop_width]
+
+
+crop_to_center.__amt_device_op__ = True  # type: ignore[attr-defined]
+
+
+@_device_op
+def apply_threshold(
+    intensities,
+    method: Literal["otsu", "li", "yen", "isodata", "mean", "minimum", "triangle", "local", "niblack", "sauvola"] = "otsu",
+    *,
+    _batched: bool = False,
+    **kwargs,
+):
+    """Binary image ``intensities > threshold`` (ref: ``operations.py:135-216``).
+
+    Empty or constant input -> all False (checked before the method name, as in the
+    reference).  Only Otsu runs on the B200 path (``skimage.filters.threshold_otsu``: exact
+    per-value histogram for integer images, 256 uniform bins for float images); the other nine
+    scikit-image methods the reference lists are out of scope and raise NotImplementedError.
+    """
+    if not _gpu.is_device_array(intensities) and np.asarray(intensities).size == 0:
+        return np.zeros_like(np.asarray(intensities), dtype=bool)
+    method_lower = method.lower()
+    if method_lower != "otsu":
+        # the reference returns all-False for a constant image before it looks at the method
+        host = _gpu.to_host(intensities) if _gpu.is_device_array(intensities) else np.asarray(intensities)
+        if host.min() == host.max():
+            return np.zeros_like(host, dtype=bool)
+        if method_lower not in _THRESHOLD_METHODS:
+            raise ValueError(
+                f"Unsupported thresholding method: '{method}'. "
+                f"Supported methods: {', '.join(_THRESHOLD_METHODS)}"
+            )
+        raise NotImplementedError(
+            f"Thresholding method '{method}' is outside the B200 hot path (only 'otsu' is implemented)"
+        )
+    t, _, was_numpy = _prepare(intensities)
+    planes = _slices(t, _batched)
+    # a constant plane gets threshold == its value, so nothing is above it (all False)
+    thr, _ = _gpu.otsu_threshold(planes)
+    mask = _gpu.threshold_gt(planes, thr).reshape(t.shape).view(_gpu.torch_mod().bool)
+    return _gpu.to_host(mask) if was_numpy else mask

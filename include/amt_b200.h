@@ -1,0 +1,257 @@
+/*
+ * amt_b200.h — C ABI of libamt_b200.so: the B200 (sm_100a) implementation of the
+ * arcadia-microscopy-tools per-image hot path (preprocess -> threshold/label -> quantify).
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*); nothing
+ *    synchronises except the `*_host` executor entry points, which say so.
+ *  - Return value: AMT_OK (0) or a negative amt_status.  No exceptions, no exit().
+ *  - The library is stateless apart from amt_executor handles: the caller owns all
+ *    buffers including scratch (sizes come from the *_scratch_bytes helpers), so every
+ *    entry point is re-entrant and may be called concurrently from many host threads
+ *    (the reference fans one operation out over a ThreadPoolExecutor,
+ *    ref: src/arcadia_microscopy_tools/pipeline.py:145-146).
+ *  - Images are C-contiguous planes, batched along a leading `n_img` axis.
+ *
+ * Each entry point names the reference interface it stands in for (paths relative to
+ * /root/reference/src/arcadia_microscopy_tools/; [3p] = the un-vendored scikit-image /
+ * scipy / numpy routine that reference line dispatches to).
+ */
+#ifndef AMT_B200_H
+#define AMT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* amt_stream_t; /* cudaStream_t */
+
+typedef enum amt_status {
+  AMT_OK = 0,
+  AMT_ERR_INVALID = -1,     /* bad argument (maps to ValueError / TypeError in the shim) */
+  AMT_ERR_CUDA = -2,        /* a CUDA runtime call or launch failed */
+  AMT_ERR_CAPACITY = -3,    /* a caller-provided capacity (labels, scratch, radius) is too small */
+  AMT_ERR_UNSUPPORTED = -4  /* dtype / rank combination outside the hot path */
+} amt_status;
+
+typedef enum amt_dtype {
+  AMT_U8 = 0,  /* also bool masks (0/1) */
+  AMT_U16 = 1,
+  AMT_I32 = 2,
+  AMT_F64 = 3
+} amt_dtype;
+
+int amt_version(void);
+const char* amt_strerror(int status);
+/* Last CUDA error string seen by this host thread (diagnostics only). */
+const char* amt_last_cuda_error(void);
+/* Number of kernels this library has launched in the calling process (bench gpu_launches). */
+uint64_t amt_launch_count(void);
+
+/* ------------------------------------------------------------------ Gaussian / DoG
+ * ref: operations.py:91  ski.filters.difference_of_gaussians -> [3p] scipy.ndimage.
+ * gaussian_filter(mode='nearest', truncate=4.0) -> correlate1d symmetric loop.  float64,
+ * scipy's summation order, no FMA contraction: bit-identical to scipy.
+ *
+ * `half_w` holds weights[c-j] for j = 0..radius (the centre and one side of the symmetric
+ * kernel, computed on the host with NumPy exactly as scipy's _gaussian_kernel1d does).
+ */
+
+/* One 1-D pass along the middle axis of a C-contiguous (outer, n, inner) array.
+ * inner == 1 filters along the contiguous axis.  in_dtype AMT_U16 (values multiplied by
+ * in_scale, i.e. img_as_float's 1/65535) or AMT_F64 (in_scale ignored). */
+int amt_gaussian_axis(const void* in, int in_dtype, double in_scale, double* out,
+                      int64_t outer, int64_t n, int64_t inner,
+                      const double* half_w, int radius, amt_stream_t stream);
+
+/* Fused 2-D difference of Gaussians over a batch of planes: out = G_lo(x) - G_hi(x).
+ * tmp_lo / tmp_hi: caller scratch, n_img*h*w doubles each (axis-0 pass results).
+ * minmax_keys (optional, may be NULL): n_img*2 uint64, receives the order-preserving keys
+ * of min and max of each output plane (see amt_minmax_f64). */
+int amt_dog2d(const void* in, int in_dtype, double in_scale, double* out,
+              int64_t n_img, int64_t h, int64_t w,
+              const double* half_w_lo, int r_lo, const double* half_w_hi, int r_hi,
+              double* tmp_lo, double* tmp_hi, uint64_t* minmax_keys, amt_stream_t stream);
+
+/* out = a - b elementwise (N-D DoG fallback: two full Gaussians then subtract). */
+int amt_sub_f64(const double* a, const double* b, double* out, int64_t n, amt_stream_t stream);
+
+/* ------------------------------------------------------------------ min / max
+ * ref: operations.py:43, :201 (intensities.min() == intensities.max() guards).
+ * minmax_keys: n_img*2 uint64 = {key(min), key(max)}; key(x) is the order-preserving map
+ * bits ^ (sign ? ~0 : 1<<63) for float64, the value itself for uint16.
+ * amt_minmax_decode writes n_img*2 doubles {min, max}. */
+int amt_minmax_f64(const double* data, int64_t n_img, int64_t n, uint64_t* minmax_keys, amt_stream_t stream);
+int amt_minmax_u16(const uint16_t* data, int64_t n_img, int64_t n, uint64_t* minmax_keys, amt_stream_t stream);
+int amt_minmax_decode(const uint64_t* minmax_keys, int is_f64, int64_t n_img, double* out_minmax, amt_stream_t stream);
+
+/* ------------------------------------------------------------------ exact order statistics
+ * ref: operations.py:47, :94  np.percentile (method 'linear') needs the floor/ceil order
+ * statistics of the flattened plane.  `ranks_host`: n_ranks (<= AMT_MAX_RANKS) zero-based
+ * ranks, the same for every plane.  out_vals: n_img*n_ranks doubles.
+ * f64: needs minmax_keys of the data (amt_minmax_f64 / amt_dog2d) and scratch of
+ * amt_select_f64_scratch_bytes(n_img, n).  u16: scratch of amt_select_u16_scratch_bytes. */
+#define AMT_MAX_RANKS 8
+size_t amt_select_f64_scratch_bytes(int64_t n_img, int64_t n);
+int amt_select_f64(const double* data, int64_t n_img, int64_t n, const int64_t* ranks_host, int n_ranks,
+                   const uint64_t* minmax_keys, double* out_vals, void* scratch, size_t scratch_bytes,
+                   amt_stream_t stream);
+size_t amt_select_u16_scratch_bytes(int64_t n_img);
+int amt_select_u16(const uint16_t* data, int64_t n_img, int64_t n, const int64_t* ranks_host, int n_ranks,
+                   double* out_vals, void* scratch, size_t scratch_bytes, amt_stream_t stream);
+
+/* ------------------------------------------------------------------ elementwise maps
+ * Per-plane parameters live in device memory so that they can be produced by device code
+ * (amt_plan_dog_rescale) without a host round trip.
+ *   flags bit0 SUBCLIP : y = max(x - lvl, 0)                   ref: operations.py:97
+ *   flags bit1 RESCALE : y = ((clip(y,p1,p2) - p1)/(p2 - p1))*(o2-o1) + o1, or
+ *                        clip(y,o1,o2) when p1 == p2           ref: operations.py:50-54 [3p]
+ *   flags bit2 FILL    : y = o1 (constant plane)               ref: operations.py:43-44
+ */
+typedef struct amt_map_params {
+  double lvl, p1, p2, o1, o2;
+  double hist_first, hist_last; /* range of the fused 256-bin histogram (written by plan) */
+  int32_t flags;
+  int32_t pad;
+} amt_map_params;
+#define AMT_MAP_SUBCLIP 1
+#define AMT_MAP_RESCALE 2
+#define AMT_MAP_FILL 4
+
+/* in_dtype AMT_U16 or AMT_F64; out float64.  hist256 (optional): n_img*256 uint32 counts of
+ * the OUTPUT plane with numpy's uniform-bin semantics over [hist_first, hist_last]
+ * (edges = np.linspace restated on device); must be zeroed by the caller. */
+int amt_map(const void* in, int in_dtype, double* out, int64_t n_img, int64_t n,
+            const amt_map_params* params, uint32_t* hist256, amt_stream_t stream);
+
+/* Device-side planning for subtract_background_dog -> rescale_by_percentile on a DoG plane:
+ * from 6 order statistics per plane (ranks lo/hi of `percentile`, of p_lo and of p_hi, as
+ * produced by amt_select_f64) and the host-computed lerp fractions, fill amt_map_params
+ * (SUBCLIP|RESCALE, or FILL for a constant plane) exactly as NumPy would.
+ * ref: operations.py:94-97 then operations.py:41-54. */
+int amt_plan_dog_rescale(const double* order_stats /* n_img*6 */, const uint64_t* minmax_keys,
+                         int64_t n_img, double g_bg, double g_lo, double g_hi, double o1, double o2,
+                         amt_map_params* params, amt_stream_t stream);
+
+/* ------------------------------------------------------------------ histogram + Otsu
+ * ref: operations.py:186/:214 ski.filters.threshold_otsu [3p]: float images -> 256 uniform
+ * bins over [min,max]; integer images -> one bin per value over [min,max]; float32 counts
+ * and class weights, float64 class means, first maximum.  thresholds: n_img doubles. */
+int amt_hist256_f64(const double* data, int64_t n_img, int64_t n, const uint64_t* minmax_keys,
+                    uint32_t* hist256, amt_stream_t stream);
+int amt_hist_u16(const uint16_t* data, int64_t n_img, int64_t n, uint32_t* hist65536, amt_stream_t stream);
+/* mode 0: float histogram, 256 bins, range from params[i].hist_first/last;
+ * mode 1: float histogram, 256 bins, range from minmax_keys;
+ * mode 2: uint16 exact histogram (65536 bins), range from minmax_keys. */
+size_t amt_otsu_scratch_bytes(int mode, int64_t n_img); /* 0 for the 256-bin modes */
+int amt_otsu(const uint32_t* hist, int mode, const amt_map_params* params, const uint64_t* minmax_keys,
+             int64_t n_img, double* thresholds, void* scratch, size_t scratch_bytes, amt_stream_t stream);
+/* mask = data > threshold[img]  (uint8 0/1).  ref: operations.py:216 */
+int amt_threshold_gt(const void* data, int in_dtype, int64_t n_img, int64_t n, const double* thresholds,
+                     uint8_t* mask, amt_stream_t stream);
+
+/* ------------------------------------------------------------------ labelling
+ * ref: masks.py:38-65 (_process_mask): clear_border [3p] then measure.label [3p] (bool) or
+ * relabel_sequential [3p] (integer masks).  Output labels int32, 1..K consecutive; K per
+ * plane in `counts`.  Bool masks: 8-connectivity, components numbered in raster order of
+ * their first pixel.  Integer masks: clear_border removes border-touching connected
+ * FRAGMENTS of equal value, then values are renumbered in ascending order.
+ * in_kind: 0 = uint8 mask, 1 = float64 plane compared `> thresholds[img]` on the fly,
+ *          2 = int32 label plane (values in [0, max_value]). */
+size_t amt_label_scratch_bytes(int64_t n_img, int64_t h, int64_t w, int64_t max_value);
+int amt_label(const void* in, int in_kind, const double* thresholds, int64_t max_value,
+              int64_t n_img, int64_t h, int64_t w, int clear_border,
+              int32_t* labels_out, int32_t* counts, void* scratch, size_t scratch_bytes,
+              amt_stream_t stream);
+
+/* ------------------------------------------------------------------ per-cell quantification
+ * ref: masks.py:286-289, :317-326 ski.measure.regionprops_table [3p].
+ * One pass over labels + C uint16 channel planes accumulates exact integer statistics per
+ * label; amt_region_finalize turns them into the float64 table.
+ * channels: plane c of image i starts at channels + i*img_stride + c*chan_stride (elements).
+ * acc: n_img * AMT_ACC_FIELDS(C) * max_labels uint64 (zero/identity-initialised by the call).
+ * table: n_img * AMT_TABLE_COLS(C) * max_labels float64, column-major per image (SoA). */
+#define AMT_ACC_BASE 10
+#define AMT_ACC_PER_CHANNEL 4
+#define AMT_ACC_FIELDS(C) (AMT_ACC_BASE + AMT_ACC_PER_CHANNEL * (C))
+/* acc field order: count, sum_r, sum_c, sum_rr, sum_cc, sum_rc, r_min, r_max, c_min, c_max,
+ * then per channel: sum, sum_sq, min, max. */
+#define AMT_TABLE_BASE 16
+#define AMT_TABLE_PER_CHANNEL 5
+#define AMT_TABLE_COLS(C) (AMT_TABLE_BASE + AMT_TABLE_PER_CHANNEL * (C))
+/* table column order: label, area, bbox-0..3, centroid-0, centroid-1, inertia eigval 1, 2,
+ * axis_major_length, axis_minor_length, eccentricity, orientation, perimeter, area_convex,
+ * then per channel: intensity_sum, intensity_mean, intensity_max, intensity_min,
+ * intensity_std.  perimeter / area_convex are filled by amt_region_shape (NaN otherwise). */
+int amt_region_reduce(const int32_t* labels, const uint16_t* channels, int n_channels,
+                      int64_t img_stride, int64_t chan_stride, int64_t n_img, int64_t h, int64_t w,
+                      int64_t max_labels, uint64_t* acc, amt_stream_t stream);
+int amt_region_finalize(const uint64_t* acc, const int32_t* counts, int n_channels, int64_t n_img,
+                        int64_t max_labels, double* table, amt_stream_t stream);
+/* perimeter (4-neighbourhood, skimage weights) and convex-hull pixel count per label.
+ * ref: masks.py:15-28 defaults 'perimeter', 'area_convex', 'solidity'. scratch from
+ * amt_region_shape_scratch_bytes. */
+size_t amt_region_shape_scratch_bytes(int64_t n_img, int64_t h, int64_t w, int64_t max_labels);
+int amt_region_shape(const int32_t* labels, const uint64_t* acc, int n_channels, const int32_t* counts,
+                     int64_t n_img, int64_t h, int64_t w, int64_t max_labels, double* table,
+                     void* scratch, size_t scratch_bytes, amt_stream_t stream);
+
+/* ------------------------------------------------------------------ fused FOV executor
+ * The native runtime for the batch path (bench + MicroscopyImage batch pipeline): owns its
+ * streams, device scratch and pinned double-buffered staging, and runs the whole workload W
+ * of SURVEY.md 8(d) for a batch of fields of view with no host round trip inside a chunk:
+ * per channel DoG -> percentile background -> clip -> percentile rescale; Otsu on the
+ * segmentation channel; threshold + CCL + clear_border; per-cell table over all raw channels;
+ * plus the same table for a caller-given integer label mask (clear_border + relabel).
+ */
+typedef struct amt_executor amt_executor;
+
+typedef struct amt_fov_config {
+  int32_t device;          /* CUDA device ordinal */
+  int32_t n_channels;      /* C */
+  int32_t height, width;   /* Y, X */
+  int32_t seg_channel;     /* channel whose preprocessed plane is thresholded */
+  int32_t chunk_fovs;      /* FOVs processed per launch wave (scratch is sized for this) */
+  int32_t max_labels;      /* table capacity per FOV and per mask */
+  int32_t max_label_value; /* largest value allowed in a given label mask */
+  int32_t quantify_given_mask; /* 1: also clear_border + relabel + quantify the given mask */
+  int32_t keep_preprocessed;   /* 1: copy preprocessed planes out (device runs only) */
+  double low_sigma, high_sigma;  /* subtract_background_dog */
+  double bg_percentile;
+  double pct_lo, pct_hi;         /* rescale_by_percentile percentile_range */
+  double out_lo, out_hi;         /* rescale_by_percentile out_range */
+} amt_fov_config;
+
+/* half_w_*_host: NumPy-computed half kernels (radius+1 doubles each). */
+int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host, int r_lo,
+                        const double* half_w_hi_host, int r_hi, amt_executor** out);
+void amt_executor_destroy(amt_executor* ex);
+size_t amt_executor_device_bytes(const amt_executor* ex);
+
+/* Device-resident batch.  fovs: n_fov*C*H*W uint16; given_labels: n_fov*H*W int32 or NULL.
+ * Outputs (device): tables_thr / tables_given: n_fov*AMT_TABLE_COLS(C)*max_labels float64;
+ * counts_thr / counts_given: n_fov int32; thresholds: n_fov float64; labels_thr /
+ * labels_given (optional, may be NULL): n_fov*H*W int32; preprocessed (optional):
+ * n_fov*C*H*W float64.  Asynchronous on the executor's streams; amt_executor_sync waits. */
+int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_t* given_labels,
+                            int64_t n_fov, double* tables_thr, int32_t* counts_thr,
+                            double* tables_given, int32_t* counts_given, double* thresholds,
+                            int32_t* labels_thr, int32_t* labels_given, double* preprocessed);
+/* Host-fed batch: inputs and outputs are HOST pointers (pinned memory recommended; pageable
+ * works but serialises).  Copies are double-buffered against compute on separate streams.
+ * Synchronous: returns when every output byte is on the host. */
+int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const int32_t* given_labels_host,
+                          int64_t n_fov, double* tables_thr_host, int32_t* counts_thr_host,
+                          double* tables_given_host, int32_t* counts_given_host, double* thresholds_host);
+int amt_executor_sync(amt_executor* ex);
+/* CUDA-event time (ms) of the last run_device / run_host call's device work. */
+float amt_executor_last_ms(amt_executor* ex);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMT_B200_H */

@@ -1,0 +1,84 @@
+"""Oracle: image histogram + Otsu threshold.  TEST INFRASTRUCTURE ONLY.
+
+Restates ``skimage.filters.threshold_otsu(image)`` (nbins=256) as called by the reference at
+``operations.py:186`` / ``:214``.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def histogram_float_256(image: np.ndarray, nbins: int = 256):
+    """``skimage.exposure.histogram`` for float images: ``np.histogram(image, bins=nbins,
+    range=None)`` and bin centres ``(edges[:-1] + edges[1:]) / 2``."""
+    hist, edges = np.histogram(np.asarray(image).reshape(-1), bins=nbins, range=None)
+    centers = (edges[:-1] + edges[1:]) / 2.0
+    return hist, centers
+
+
+def linspace_edges(first: float, last: float, nbins: int = 256) -> np.ndarray:
+    """The bin edges numpy builds for a uniform histogram (``np.linspace(first, last,
+    nbins+1)``); if ``first == last`` numpy widens the range by +-0.5 first."""
+    first = float(first)
+    last = float(last)
+    if first == last:
+        first, last = first - 0.5, last + 0.5
+    return np.linspace(first, last, nbins + 1, endpoint=True, dtype=np.float64)
+
+
+def histogram_float_restated(image: np.ndarray, nbins: int = 256):
+    """Candidate-then-correct binning of numpy's uniform-bin fast path
+    (``numpy/lib/_histograms_impl.py``): ``i = int(((x-first)/(last-first))*nbins)``,
+    ``nbins -> nbins-1``, then ``if x < edges[i]: i -= 1`` and
+    ``if x >= edges[i+1] and i != nbins-1: i += 1``.  This is what the CUDA kernel does."""
+    x = np.asarray(image, dtype=np.float64).reshape(-1)
+    first, last = float(x.min()), float(x.max())
+    edges = linspace_edges(first, last, nbins)
+    first, last = float(edges[0]), float(edges[-1])
+    f = ((x - first) / (last - first)) * nbins
+    idx = f.astype(np.intp)
+    idx[idx == nbins] -= 1
+    dec = x < edges[idx]
+    idx[dec] -= 1
+    inc = (x >= edges[idx + 1]) & (idx != nbins - 1)
+    idx[inc] += 1
+    hist = np.bincount(idx, minlength=nbins).astype(np.int64)
+    centers = (edges[:-1] + edges[1:]) / 2.0
+    return hist, centers
+
+
+def histogram_int(image: np.ndarray):
+    """``skimage.exposure.histogram`` for integer images: exact per-value ``bincount`` over
+    ``[min, max]`` with ``bin_centers = arange(min, max+1)`` (nbins ignored)."""
+    flat = np.asarray(image).reshape(-1)
+    imin, imax = int(flat.min()), int(flat.max())
+    hist = np.bincount((flat.astype(np.int64) - imin), minlength=imax - imin + 1)
+    centers = np.arange(imin, imax + 1)
+    return hist, centers
+
+
+def otsu_from_histogram(hist: np.ndarray, centers: np.ndarray):
+    """The Otsu scan with numpy's mixed precision: float32 counts and class weights,
+    float64 class means, float32 product ``w1*w2`` promoted on the last multiply; first
+    maximum wins."""
+    counts = np.asarray(hist).astype("float32", copy=False)
+    weight1 = np.cumsum(counts)
+    weight2 = np.cumsum(counts[::-1])[::-1]
+    mean1 = np.cumsum(counts * centers) / weight1
+    mean2 = (np.cumsum((counts * centers)[::-1]) / weight2[::-1])[::-1]
+    variance12 = weight1[:-1] * weight2[1:] * (mean1[:-1] - mean2[1:]) ** 2
+    idx = int(np.argmax(variance12))
+    return centers[idx]
+
+
+def threshold_otsu(image: np.ndarray, nbins: int = 256):
+    image = np.asarray(image)
+    first_pixel = image.reshape(-1)[0]
+    if np.all(image == first_pixel):
+        return first_pixel
+    if np.issubdtype(image.dtype, np.integer):
+        hist, centers = histogram_int(image)
+    else:
+        hist, centers = histogram_float_256(image, nbins)
+    return otsu_from_histogram(hist, centers)

@@ -1,0 +1,182 @@
+"""GPU parity: labelling, border clearing, relabelling and per-cell tables against the oracle.
+Integers bit-exact; float statistics within rtol 1e-5 (atol scaled to the column)."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import labeling, regionprops
+
+from conftest import make_label_image, random_blobs
+
+pytestmark = pytest.mark.gpu
+
+from arcadia_microscopy_tools_b200 import masks  # noqa: E402
+from arcadia_microscopy_tools_b200.channels import DAPI, FITC  # noqa: E402
+from arcadia_microscopy_tools_b200.masks import SegmentationMask  # noqa: E402
+from arcadia_microscopy_tools_b200.synthetic import make_fov  # noqa: E402
+
+FLOAT_RTOL = 1e-5
+
+
+def _close(got, want, name):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (name, got.shape, want.shape)
+    atol = 1e-9 * max(1.0, float(np.max(np.abs(want))) if want.size else 1.0)
+    if not np.allclose(got, want, rtol=FLOAT_RTOL, atol=atol):
+        i = int(np.argmax(np.abs(got - want)))
+        raise AssertionError(f"{name}: max diff at {i}: got {got[i]!r} want {want[i]!r}")
+
+
+@pytest.mark.parametrize("shape,n", [((64, 64), 12), ((97, 131), 60), ((33, 250), 40), ((256, 256), 300)])
+@pytest.mark.parametrize("edge", [False, True])
+def test_bool_masks_label_like_scipy(shape, n, edge):
+    m = random_blobs(31 + n, shape, n)
+    m[shape[0] // 2, shape[1] // 2] = True
+    try:
+        want = oracle.process_mask(m, edge)
+    except ValueError:
+        with pytest.raises(ValueError, match="No cells remain"):
+            masks._process_mask(m, edge)
+        return
+    got = masks._process_mask(m, edge)
+    assert got.dtype == np.int64 and np.array_equal(got, want)
+
+
+def test_label_pathological_shapes():
+    # spirals / checkerboards / long diagonals exercise the union-find
+    n = 96
+    yy, xx = np.mgrid[:n, :n]
+    cases = {
+        "checker": (yy + xx) % 2 == 0,
+        "stripes": yy % 2 == 0,
+        "diag": ((yy - xx) % 7 == 0) | ((yy + xx) % 11 == 0),
+        "full": np.ones((n, n), bool),
+        "ring": (np.hypot(yy - 48, xx - 48) < 40) & (np.hypot(yy - 48, xx - 48) > 30),
+    }
+    spiral = np.zeros((n, n), bool)
+    for k in range(0, 44, 4):
+        spiral[k, k : n - k] = True
+        spiral[k : n - k, n - k - 1] = True
+        spiral[n - k - 1, k + 2 : n - k] = True
+        spiral[k + 4 : n - k, k + 2] = True
+    cases["spiral"] = spiral
+    for name, m in cases.items():
+        got = masks._process_mask(m, False)
+        assert np.array_equal(got, labeling.label(m)), name
+
+
+@pytest.mark.parametrize("edge", [False, True])
+def test_integer_masks_clear_border_and_relabel(edge):
+    rng = np.random.default_rng(33)
+    base = random_blobs(5, (120, 150), 70)
+    lab = labeling.label(base)
+    perm = rng.permutation(lab.max() + 1) * 3 + 1
+    perm[0] = 0
+    img = perm[lab].astype(np.int64)          # non-consecutive values
+    img[40:44, :] = 7                          # one value, border-touching AND interior fragments
+    img[80:83, 20:30] = 7
+    want = oracle.process_mask(img, edge)
+    got = masks._process_mask(img, edge)
+    assert got.dtype == np.int64 and np.array_equal(got, want)
+    _, labels32, _ = make_fov(34, 1, 160, 200, 30)
+    assert np.array_equal(masks._process_mask(labels32.astype(np.int64), edge), oracle.process_mask(labels32.astype(np.int64), edge))
+
+
+def _compare_tables(got: dict, want: dict, skip=()):
+    assert list(got.keys()) == list(want.keys())
+    for key in want:
+        if key in skip:
+            continue
+        g, w = got[key], want[key]
+        assert g.dtype == w.dtype, (key, g.dtype, w.dtype)
+        if np.issubdtype(w.dtype, np.integer) or key == "area" or key.startswith(("intensity_max", "intensity_min", "intensity_sum", "area_convex")):
+            assert np.array_equal(g, w), key
+        else:
+            _close(g, w, key)
+
+
+BASIC = ["label", "area", "bbox", "centroid", "axis_major_length", "axis_minor_length", "eccentricity", "volume"]
+INT_ALL = ["intensity_mean", "intensity_max", "intensity_min", "intensity_std", "intensity_sum"]
+
+
+def test_cell_properties_on_synthetic_fov():
+    fov, given, _ = make_fov(35, 3, 240, 300, 45)
+    chans = {DAPI: fov[1], FITC: fov[2]}
+    m = SegmentationMask(given.astype(np.int64), chans, remove_edge_cells=True, property_names=BASIC + ["orientation"],
+                         intensity_property_names=INT_ALL)
+    want_labels = oracle.process_mask(given.astype(np.int64), True)
+    assert np.array_equal(m.label_image, want_labels) and m.num_cells == want_labels.max()
+    want = oracle.cell_properties(want_labels, {"dapi": fov[1], "fitc": fov[2]}, BASIC + ["orientation"], INT_ALL)
+    _compare_tables(m.cell_properties, want)
+    assert m.centroids_yx.shape == (m.num_cells, 2)
+    um = m.convert_properties_to_microns(0.5)
+    assert np.array_equal(um["area_um2"], m.cell_properties["area"] * 0.25) and "volume_um3" in um and "label" in um
+
+
+def test_cell_properties_threshold_mask_path():
+    fov, _, _ = make_fov(36, 2, 200, 200, 30)
+    P = oracle.rescale_by_percentile(oracle.subtract_background_dog(fov[1]), (1, 99))
+    mask = oracle.apply_threshold(P)
+    m = SegmentationMask(mask, {DAPI: fov[1]}, property_names=BASIC, intensity_property_names=INT_ALL)
+    want_labels = oracle.process_mask(mask, True)
+    assert np.array_equal(m.label_image, want_labels)
+    want = oracle.cell_properties(want_labels, {"dapi": fov[1]}, BASIC, INT_ALL)
+    # orientation / eccentricity of tiny symmetric specks are round-off determined in the reference itself
+    _compare_tables(m.cell_properties, want)
+
+
+def test_reference_disc_expectations():
+    """ref: tests/test_masks.py:179-197 (centroids, volume) and :263-295 (filter on area)."""
+    two = make_label_image((60, 60), [(15, 15, 6), (45, 45, 6)])
+    m = SegmentationMask(two, remove_edge_cells=False, property_names=BASIC + ["orientation"])
+    p = m.cell_properties
+    assert set(p) == {"label", "area", "bbox-0", "bbox-1", "bbox-2", "bbox-3", "axis_major_length", "axis_minor_length",
+                      "eccentricity", "volume", "orientation", "centroid_y", "centroid_x"}
+    assert np.allclose(np.c_[p["centroid_y"], p["centroid_x"]], [[15, 15], [45, 45]]) and np.all(p["volume"] > 0)
+    assert p["area"].tolist() == [109.0, 109.0] and np.allclose(p["orientation"], -np.pi / 4)
+    assert all(len(v) == m.num_cells for v in p.values())
+    three = make_label_image((80, 80), [(20, 20, 5), (20, 60, 8), (60, 40, 11)])
+    base = SegmentationMask(three, remove_edge_cells=False, property_names=["label", "area"])
+    assert set(base.cell_properties) == {"label", "area"}
+    assert base.filter("area", min_value=150).num_cells == 2
+    assert base.filter("area", max_value=250).num_cells == 2
+    mid = base.filter("area", min_value=150, max_value=250)
+    assert mid.num_cells == 1 and 150 <= mid.cell_properties["area"][0] <= 250
+    assert mid.remove_edge_cells is False and mid.property_names == ["label", "area"]
+    assert base.filter("area", min_value=100).filter("area", max_value=250).num_cells == 1
+    with pytest.raises(ValueError, match="min_value or max_value"):
+        base.filter("area")
+    with pytest.raises(ValueError, match="not found"):
+        base.filter("nonexistent_property", min_value=0)
+    with pytest.raises(ValueError, match="No cells remain"):
+        base.filter("area", max_value=1)
+    rng = np.random.default_rng(42)
+    chans = {DAPI: rng.integers(100, 1000, size=two.shape).astype(np.uint16), FITC: rng.integers(0, 500, size=two.shape).astype(np.uint16)}
+    mi = SegmentationMask(two, chans, remove_edge_cells=False, property_names=["label", "area"])
+    for prop in masks.DEFAULT_INTENSITY_PROPERTY_NAMES:
+        assert f"{prop}_dapi" in mi.cell_properties and f"{prop}_fitc" in mi.cell_properties
+    kept = mi.filter("area", min_value=1)
+    assert set(kept.intensity_image_dict) == set(mi.intensity_image_dict)
+
+
+def test_golden_config1_tables(golden):
+    fov = golden["fov"]
+    chans = {c: fov[i] for i, c in enumerate([masks.Channel("BRIGHTFIELD", "#FFFFFF"), DAPI, FITC, masks.Channel("TRITC", "#FFBF00")])}
+    for bg in (0, 90):
+        P = oracle.rescale_by_percentile(oracle.subtract_background_dog(fov[1], percentile=bg), (1, 99))
+        m = SegmentationMask(oracle.apply_threshold(P), chans, property_names=["label", "area", "bbox", "centroid"],
+                             intensity_property_names=INT_ALL)
+        assert np.array_equal(m.label_image, golden[f"bg{bg}/labels_thr"])
+        p = m.cell_properties
+        assert np.array_equal(p["area"], golden[f"bg{bg}/thr/area"])
+        for k in range(4):
+            assert np.array_equal(p[f"bbox-{k}"], golden[f"bg{bg}/thr/bbox-{k}"])
+        for name in ("brightfield", "dapi", "fitc", "tritc"):
+            assert np.array_equal(p[f"intensity_sum_{name}"], golden[f"bg{bg}/thr/intensity_sum_{name}"])
+            _close(p[f"intensity_std_{name}"], golden[f"bg{bg}/thr/intensity_std_{name}"], f"std {name}")
+        g = SegmentationMask(golden["given"].astype(np.int64), chans, property_names=["label", "area"], intensity_property_names=["intensity_sum"])
+        assert np.array_equal(g.label_image, golden[f"bg{bg}/labels_given"])
+        assert np.array_equal(g.cell_properties["area"], golden[f"bg{bg}/given/area"])

@@ -1,0 +1,169 @@
+"""GPU parity: operations.* and Pipeline against the CPU oracle (bit-exact for float64
+planes and masks: every arithmetic step is the separately rounded operation NumPy/SciPy do)."""
+
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import filters
+
+pytestmark = pytest.mark.gpu
+
+from arcadia_microscopy_tools_b200 import _gpu, operations  # noqa: E402
+from arcadia_microscopy_tools_b200.pipeline import ImageOperation, Pipeline  # noqa: E402
+from arcadia_microscopy_tools_b200.synthetic import make_fov  # noqa: E402
+
+
+def _bits_equal(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype, (what, a.shape, b.shape, a.dtype, b.dtype)
+    if not np.array_equal(a, b):
+        bad = np.flatnonzero(a.ravel() != b.ravel())
+        diff = np.abs(a.ravel()[bad].astype(np.float64) - b.ravel()[bad].astype(np.float64))
+        raise AssertionError(f"{what}: {bad.size}/{a.size} differ, max |d|={diff.max():.3e}, first idx {bad[:5]}")
+
+
+@pytest.mark.parametrize("sigma", [0.6, 1.0, 2.7, 16.0])
+@pytest.mark.parametrize("shape", [(64, 64), (97, 131), (300, 70)])
+def test_gaussian_axis_passes_bit_exact(sigma, shape):
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 65535, size=shape).astype(np.uint16)
+    dev = _gpu.to_device(img)
+    got = _gpu.to_host(_gpu.gaussian_nd(dev, 1.0 / 65535.0, sigma))
+    _bits_equal(got, filters.gaussian(img, sigma), f"gaussian sigma={sigma}")
+    f = rng.normal(size=shape)
+    got = _gpu.to_host(_gpu.gaussian_nd(_gpu.to_device(f), 1.0, sigma))
+    _bits_equal(got, filters.gaussian(f, sigma), f"gaussian f64 sigma={sigma}")
+
+
+def test_gaussian_3d_and_1d():
+    rng = np.random.default_rng(12)
+    vol = rng.integers(0, 4000, size=(7, 45, 38)).astype(np.uint16)
+    got = _gpu.to_host(_gpu.gaussian_nd(_gpu.to_device(vol), 1.0 / 65535.0, 2.0))
+    _bits_equal(got, filters.gaussian(vol, 2.0), "3-D gaussian")
+    line = rng.random(1000)
+    got = _gpu.to_host(_gpu.gaussian_nd(_gpu.to_device(line), 1.0, 5.0))
+    _bits_equal(got, filters.gaussian(line, 5.0), "1-D gaussian")
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (100, 333), (17, 40)])
+@pytest.mark.parametrize("sigmas", [(0.6, 16.0), (1.0, 10.0), (2.0, 3.5)])
+def test_dog2d_bit_exact(shape, sigmas):
+    rng = np.random.default_rng(13)
+    stack = rng.integers(100, 5000, size=(3, *shape)).astype(np.uint16)
+    dog, mm = _gpu.dog2d(_gpu.to_device(stack), 1.0 / 65535.0, *sigmas)
+    got = _gpu.to_host(dog)
+    mnmx = _gpu.minmax_values(mm, True)
+    for i in range(3):
+        want = filters.difference_of_gaussians(stack[i], *sigmas)
+        _bits_equal(got[i], want, f"dog plane {i} {shape} {sigmas}")
+        assert mnmx[i, 0] == want.min() and mnmx[i, 1] == want.max()
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.float64])
+def test_percentiles_exact(dtype):
+    rng = np.random.default_rng(14)
+    data = (rng.gamma(2.0, 400.0, size=(3, 211, 173))).astype(dtype)
+    if dtype == np.float64:
+        data[1] = np.clip(data[1] - 900, 0, None)  # >50 % exact zeros (ties at the minimum)
+        data[2, :50] = data[2].max()  # ties at the maximum
+    planes = _gpu.to_device(data).reshape(3, -1)
+    qs = [0, 0.5, 1, 50, 90, 99, 100]
+    for lo in range(0, len(qs), 3):
+        sub = qs[lo : lo + 3]
+        got = _gpu.percentiles(planes, sub)
+        for i in range(3):
+            want = np.percentile(data[i], sub)
+            assert np.array_equal(got[i], want), (dtype, i, sub, got[i], want)
+
+
+def test_percentiles_hard_distributions():
+    rng = np.random.default_rng(15)
+    n = 300 * 300
+    cases = {
+        "outlier": np.concatenate([rng.random(n - 1), [1e300]]),
+        "constant": np.full(n, 3.25),
+        "two_values": rng.integers(0, 2, n).astype(np.float64),
+        "negative": -np.abs(rng.normal(size=n)) * 1e-9,
+        "peaked": np.concatenate([rng.normal(0, 1e-9, n - 100), rng.normal(0, 1.0, 100)]),
+    }
+    for name, arr in cases.items():
+        planes = _gpu.to_device(arr.reshape(1, -1))
+        got = _gpu.percentiles(planes, [1, 37.5, 99])
+        want = np.percentile(arr, [1, 37.5, 99])
+        assert np.array_equal(got[0], want), (name, got[0], want)
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (90, 130)])
+def test_subtract_background_dog_bit_exact(shape):
+    fov, _, _ = make_fov(21, 2, shape[0], shape[1], 25)
+    for pct in (0, 35.5, 90):
+        got = operations.subtract_background_dog(fov[1], percentile=pct)
+        _bits_equal(got, oracle.subtract_background_dog(fov[1], percentile=pct), f"dog pct={pct}")
+    f = fov[0].astype(np.float64) * 0.37
+    _bits_equal(operations.subtract_background_dog(f, 1.0, 4.0), oracle.subtract_background_dog(f, 1.0, 4.0), "float input")
+    vol = fov[:2]  # 3-D input: every axis is filtered, one global percentile
+    _bits_equal(operations.subtract_background_dog(vol, 0.6, 2.0, 10), oracle.subtract_background_dog(vol, 0.6, 2.0, 10), "3-D")
+
+
+def test_rescale_by_percentile_bit_exact():
+    fov, _, _ = make_fov(22, 2, 128, 160, 12)
+    for rng_, out in (((0, 100), (0, 1)), ((1, 99), (0, 1)), ((2, 98), (0, 65535)), ((5, 60), (-1, 2))):
+        _bits_equal(operations.rescale_by_percentile(fov[0], rng_, out), oracle.rescale_by_percentile(fov[0], rng_, out),
+                    f"u16 {rng_} {out}")
+    x = oracle.subtract_background_dog(fov[1], percentile=90)  # mostly zeros
+    _bits_equal(operations.rescale_by_percentile(x, (1, 99)), oracle.rescale_by_percentile(x, (1, 99)), "clipped f64")
+    const = np.full((20, 30), 7, np.uint16)
+    _bits_equal(operations.rescale_by_percentile(const, (1, 99), (0.25, 1)), oracle.rescale_by_percentile(const, (1, 99), (0.25, 1)), "constant")
+    u8 = (fov[0] >> 4).astype(np.uint8)
+    _bits_equal(operations.rescale_by_percentile(u8, (1, 99)), oracle.rescale_by_percentile(u8, (1, 99)), "uint8")
+
+
+def test_apply_threshold_matches_oracle():
+    fov, _, _ = make_fov(23, 2, 200, 240, 30)
+    for c in range(2):
+        got = operations.apply_threshold(fov[c])
+        assert got.dtype == np.bool_
+        _bits_equal(got, oracle.apply_threshold(fov[c]), f"otsu u16 channel {c}")
+    P = oracle.rescale_by_percentile(oracle.subtract_background_dog(fov[1]), (1, 99))
+    _bits_equal(operations.apply_threshold(P), oracle.apply_threshold(P), "otsu f64")
+    assert not operations.apply_threshold(np.full((9, 9), 3.5)).any()
+    rng = np.random.default_rng(16)
+    noisy = rng.normal(size=(150, 150)) * 1e-3 + 5
+    _bits_equal(operations.apply_threshold(noisy), oracle.apply_threshold(noisy), "otsu f64 noise")
+
+
+def test_golden_config1_preprocess(golden):
+    fov = golden["fov"]
+    for bg in (0, 90):
+        for c in range(4):
+            x = operations.subtract_background_dog(fov[c], 0.6, 16.0, percentile=bg)
+            P = operations.rescale_by_percentile(x, (1, 99), (0, 1))
+            sha = hashlib.sha256(np.ascontiguousarray(P).tobytes()).hexdigest()
+            assert sha == str(golden[f"bg{bg}/pre_sha256"][c]), (bg, c)
+    raw_t = [int((~operations.apply_threshold(fov[c])).sum()) for c in range(4)]
+    assert [65536 - v for v in raw_t] == golden["raw_fg"].tolist()
+
+
+def test_pipeline_device_chain_equals_op_by_op():
+    fov, _, _ = make_fov(24, 3, 96, 128, 10)
+    ops = [ImageOperation(operations.subtract_background_dog, low_sigma=1, high_sigma=10),
+           ImageOperation(operations.rescale_by_percentile, percentile_range=(1, 99), out_range=(0, 1))]
+    want = np.stack([oracle.rescale_by_percentile(oracle.subtract_background_dog(fov[i], 1, 10), (1, 99)) for i in range(3)])
+    got = Pipeline(ops, parallel=True)(fov)
+    _bits_equal(got, want, "parallel device pipeline")
+    one = Pipeline(ops)(fov[0])
+    _bits_equal(one, want[0], "sequential device pipeline")
+    seg = Pipeline(ops + [ImageOperation(operations.apply_threshold)], parallel=True)(fov)
+    assert seg.dtype == np.bool_
+    _bits_equal(seg, np.stack([oracle.apply_threshold(w) for w in want]), "pipeline + threshold")
+    u = Pipeline([ops[1]], parallel=True, preserve_dtype=True)(fov)
+    assert u.dtype == np.uint16
+    # reference integration tests (test_pipeline.py:264-328): loose range/dtype/shape checks
+    img = np.random.default_rng(0).integers(0, 65535, size=(3, 128, 128)).astype(np.uint16)
+    r = Pipeline([ImageOperation(operations.rescale_by_percentile, percentile_range=(2, 98), out_range=(0, 1))], parallel=True)(img)
+    assert r.dtype == np.float64 and r.min() >= 0 and r.max() <= 1 and r.shape == img.shape

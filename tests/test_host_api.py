@@ -1,0 +1,227 @@
+"""Host-side behaviour of the drop-in API (no GPU needed): the reference's own
+``tests/test_pipeline.py`` expectations for ImageOperation / Pipeline, MicroscopyImage
+validation and channel slicing, SegmentationMask argument checks, and the C-ABI surface."""
+
+from __future__ import annotations
+
+import ctypes
+import re
+import warnings
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import arcadia_microscopy_tools_b200 as amt
+from arcadia_microscopy_tools_b200 import _lib, masks, operations
+from arcadia_microscopy_tools_b200.channels import BRIGHTFIELD, DAPI, FITC, TRITC, Channel
+from arcadia_microscopy_tools_b200.pipeline import ImageOperation, Pipeline
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def double_intensity(x):
+    return x * 2
+
+
+def add_ten(x):
+    return x + 10
+
+
+def to_float_normalized(x):
+    return x.astype(float) / x.max()
+
+
+# ---------------------------------------------------------------- ImageOperation
+def test_image_operation_stores_and_calls():
+    op = ImageOperation(np.add, 5)
+    assert op.func == np.add and op.args == (5,) and op.kwargs == {}
+    assert ImageOperation(np.clip, a_min=0, a_max=100).kwargs == {"a_min": 0, "a_max": 100}
+    np.testing.assert_array_equal(op(np.array([1, 2, 3])), [6, 7, 8])
+    assert "double_intensity" in repr(ImageOperation(double_intensity))
+
+
+def test_image_operation_is_immutable_and_hashable():
+    op = ImageOperation(double_intensity)
+    with pytest.raises(AttributeError):
+        op.func = add_ten
+    with pytest.raises(AttributeError):
+        del op.func
+    assert op == ImageOperation(double_intensity) and op != ImageOperation(add_ten)
+    assert ImageOperation(np.add, 5) == ImageOperation(np.add, 5) != ImageOperation(np.add, 10)
+    assert hash(ImageOperation(np.add, 5, k=1)) == hash(ImageOperation(np.add, 5, k=1))
+
+
+# ---------------------------------------------------------------- Pipeline
+def test_pipeline_defaults_and_validation():
+    p = Pipeline(operations=[ImageOperation(double_intensity), ImageOperation(add_ten)])
+    assert len(p) == 2 and p.copy is False and p.preserve_dtype is False and p.parallel is False
+    assert p.max_workers is None
+    with pytest.raises(ValueError, match="at least one operation"):
+        Pipeline(operations=[])
+    with pytest.raises(ValueError, match="at least one operation"):
+        Pipeline(operations=[], parallel=True)
+    for bad in (0, -1):
+        with pytest.raises(ValueError, match="max_workers must be at least 1"):
+            Pipeline(operations=[ImageOperation(double_intensity)], max_workers=bad)
+    with pytest.raises(TypeError, match="All operations must be callable"):
+        Pipeline(operations=("not_a_function",))
+    with pytest.raises(TypeError, match="All operations must be callable"):
+        Pipeline(operations=(ImageOperation(double_intensity), 42))
+    assert isinstance(Pipeline(operations=(ImageOperation(double_intensity),)).operations, list)
+    assert "parallel=True" in repr(Pipeline([ImageOperation(add_ten)], parallel=True))
+
+
+def test_pipeline_sequential_semantics():
+    img = np.array([1, 2, 3], dtype=np.uint16)
+    out = Pipeline([ImageOperation(double_intensity), ImageOperation(add_ten)])(img)
+    np.testing.assert_array_equal(out, [12, 14, 16])
+    assert out.dtype == np.uint16
+    f = Pipeline([ImageOperation(to_float_normalized)])(np.array([10, 20, 30], dtype=np.uint16))
+    np.testing.assert_allclose(f, [1 / 3, 2 / 3, 1.0])
+    keep = Pipeline([ImageOperation(to_float_normalized)], preserve_dtype=True)(np.array([10, 20, 30], dtype=np.uint16))
+    assert keep.dtype == np.uint16
+
+
+def test_pipeline_parallel_semantics():
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        Pipeline([ImageOperation(double_intensity)], parallel=True, copy=True)
+        assert len(w) == 1 and "copy=True has no effect" in str(w[0].message)
+    p = Pipeline([ImageOperation(double_intensity)], parallel=True)
+    for bad in (np.zeros((2, 2), np.uint16), np.zeros(3, np.uint16)):
+        with pytest.raises(ValueError, match="at least 3D input"):
+            p(bad)
+    stack = np.random.default_rng(0).integers(0, 100, size=(10, 32, 32)).astype(np.uint16)
+    out = Pipeline([ImageOperation(double_intensity), ImageOperation(add_ten)], parallel=True, max_workers=2)(stack)
+    np.testing.assert_array_equal(out, stack * 2 + 10)
+    assert out.dtype == np.uint16
+    one = np.array([[[10, 20], [30, 40]]], dtype=np.uint16)
+    assert Pipeline([ImageOperation(to_float_normalized)], parallel=True)(one).dtype == np.float64
+    assert Pipeline([ImageOperation(to_float_normalized)], parallel=True, preserve_dtype=True)(one).dtype == np.uint16
+
+
+def test_device_ops_are_recognised_without_touching_the_gpu():
+    ops = [ImageOperation(operations.subtract_background_dog, low_sigma=1, high_sigma=10),
+           ImageOperation(operations.rescale_by_percentile, percentile_range=(1, 99))]
+    assert all(op.runs_on_device for op in ops) and Pipeline(ops)._device_chain()
+    assert not Pipeline([ops[0], ImageOperation(double_intensity)])._device_chain()
+
+
+# ---------------------------------------------------------------- operations: host-side contract
+def test_operation_argument_validation_matches_reference_messages():
+    x = np.arange(12, dtype=np.uint16).reshape(3, 4)
+    with pytest.raises(ValueError, match="Invalid percentile range"):
+        operations.rescale_by_percentile(x, (50, 10))
+    with pytest.raises(ValueError, match="Percentile must be between 0 and 100"):
+        operations.subtract_background_dog(x, percentile=-1)
+    with pytest.raises(ValueError, match=re.escape("low_sigma (3) must be smaller than high_sigma (2)")):
+        operations.subtract_background_dog(x, 3, 2)
+    empty = np.zeros((0, 4), np.uint16)
+    assert operations.rescale_by_percentile(empty).dtype == np.float64
+    assert operations.apply_threshold(empty).dtype == np.bool_
+    with pytest.raises(ValueError, match="Unsupported thresholding method: 'nope'"):
+        operations.apply_threshold(x, method="nope")
+    with pytest.raises(NotImplementedError, match="only 'otsu'"):
+        operations.apply_threshold(x, method="li")
+    assert not operations.apply_threshold(np.full((3, 3), 5, np.uint16), method="li").any()
+
+
+def test_crop_to_center_is_a_view():
+    x = np.arange(4 * 10 * 12).reshape(4, 10, 12)
+    c = operations.crop_to_center(x, (4, 6))
+    assert c.shape == (4, 4, 6) and c.base is not None
+    np.testing.assert_array_equal(c, x[:, 3:7, 3:9])
+    assert operations.crop_to_center(x, (100, 100)).shape == x.shape
+
+
+# ---------------------------------------------------------------- MicroscopyImage
+def _image(shape=(4, 8, 8), axes="CYX", channels=(BRIGHTFIELD, DAPI, FITC, TRITC)):
+    data = np.arange(int(np.prod(shape)), dtype=np.uint16).reshape(shape)
+    return amt.MicroscopyImage.from_arrays(data, list(channels), axes)
+
+
+def test_microscopy_image_channel_views():
+    im = _image()
+    assert im.num_channels == 4 and im.channel_axis == 0 and im.dimensions.is_multichannel
+    v = im.get_channel_intensities("FITC")
+    assert v.shape == (8, 8) and np.shares_memory(v, im.intensities)
+    np.testing.assert_array_equal(v, im.intensities[2])
+    np.testing.assert_array_equal(im.get_channel_intensities(DAPI), im.intensities[1])
+    with pytest.raises(ValueError, match="Channel 'CY5' not found in image. Available channels"):
+        im.get_channel_intensities("CY5")
+    tc = _image((5, 2, 8, 8), "TCYX", (DAPI, FITC))
+    assert tc.channel_axis == 1 and tc.get_channel_intensities(FITC).shape == (5, 8, 8)
+    assert not tc.get_channel_intensities(FITC).flags.c_contiguous
+    single = _image((3, 8, 8), "TYX", (FITC,))
+    assert single.get_channel_intensities(FITC) is single.intensities
+    out = im.apply_pipeline(Pipeline([ImageOperation(double_intensity)]), "DAPI")
+    np.testing.assert_array_equal(out, im.intensities[1] * 2)
+
+
+def test_microscopy_image_validation():
+    im = _image()
+    with pytest.raises(ValueError, match="does not match"):
+        amt.MicroscopyImage(np.zeros((4, 8, 9), np.uint16), im.metadata)
+    with pytest.warns(amt.MetadataWarning, match="Expected uint16"):
+        amt.MicroscopyImage(im.intensities.astype(np.float32), im.metadata)
+    with pytest.raises(ValueError, match="hex code"):
+        Channel("X", "red")
+    assert "MicroscopyImage" in repr(im) and "DAPI" in repr(im.metadata)
+
+
+# ---------------------------------------------------------------- SegmentationMask: checks before any GPU work
+def test_segmentation_mask_validation_messages():
+    good = np.zeros((6, 6), np.int64)
+    good[2:4, 2:4] = 1
+    with pytest.raises(TypeError, match="mask_image must be a numpy array"):
+        masks.SegmentationMask([[0, 1]])
+    with pytest.raises(ValueError, match="must be a 2D array"):
+        masks.SegmentationMask(np.zeros((2, 3, 3), np.int64))
+    with pytest.raises(ValueError, match="non-negative"):
+        masks.SegmentationMask(good - 1)
+    with pytest.raises(ValueError, match="contains no cells"):
+        masks.SegmentationMask(np.zeros((4, 4), np.int64))
+    with pytest.raises(TypeError, match="must be a Mapping"):
+        masks.SegmentationMask(good, intensity_image_dict=[1])
+    with pytest.raises(ValueError, match="same shape as mask_image"):
+        masks.SegmentationMask(good, intensity_image_dict={DAPI: np.zeros((5, 5), np.uint16)})
+    with pytest.raises(ValueError, match="must be 2D"):
+        masks.SegmentationMask(good, intensity_image_dict={DAPI: np.zeros((6, 6, 1), np.uint16)})
+    m = masks.SegmentationMask(good, intensity_image_dict={DAPI: np.zeros((6, 6), np.uint16)}, remove_edge_cells=False)
+    assert m.property_names == masks.DEFAULT_CELL_PROPERTY_NAMES
+    assert m.intensity_property_names == masks.DEFAULT_INTENSITY_PROPERTY_NAMES
+    assert masks.SegmentationMask(good).intensity_property_names == []
+    with pytest.raises(AttributeError, match="Cannot modify 'mask_image'"):
+        m.mask_image = good
+    with pytest.warns(UserWarning, match="Centroid property not available"):
+        empty = masks.SegmentationMask(good, property_names=["label"]).centroids_yx
+    assert empty.shape == (0, 2)
+
+
+# ---------------------------------------------------------------- C ABI surface
+def test_shared_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "amt_b200.h").read_text()
+    declared = set(re.findall(r"\b(amt_[a-z0-9_]+)\s*\(", header))
+    declared -= {"amt_executor", "amt_fov_config", "amt_map_params"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()  # raises if the .so is missing: there is no CPU fallback
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.amt_version() >= 100
+    assert lib.amt_strerror(_lib.AMT_ERR_CAPACITY) == b"capacity exceeded"
+    assert ctypes.sizeof(_lib.MapParams) == 64 and ctypes.sizeof(_lib.FovConfig) == 96
+
+
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    x = np.arange(64, dtype=np.uint16).reshape(8, 8)
+    with pytest.raises(_lib.AmtLibraryError, match="no CPU fallback"):
+        operations.rescale_by_percentile(x)
+    m = np.zeros((8, 8), bool)
+    m[2:5, 2:5] = True
+    with pytest.raises(_lib.AmtLibraryError, match="no CPU fallback"):
+        masks.SegmentationMask(m).label_image
