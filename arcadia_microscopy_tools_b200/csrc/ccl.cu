@@ -113,7 +113,8 @@ ccl_merge_kernel(const void* __restrict__ in, const int64_t in_stride, int32_t* 
     ne_s = y > 0 && x < w - 1 && Lp[p - w + 1] >= 0;
   }
   if (n_s) {
-    if (!(w_s && nw_s)) uf_union(Lp, p, p - w);
+    // W and NW both set: p ~ W (run link) ~ NW ~ N already, except across a segment boundary
+    if (!(w_s && nw_s && threadIdx.x != 0)) uf_union(Lp, p, p - w);
   } else {
     if (w_s) {
       if (threadIdx.x == 0) uf_union(Lp, p, p - 1);  // inside a segment the run is already linked
