@@ -13,7 +13,40 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 
 }  // namespace amt
 
+namespace amt {
+
+// FP64 issue-rate probe: 8 independent non-FMA chains per thread (DMUL + DADD per step), the
+// instruction mix of the Gaussian inner loop without its memory traffic.  Used by bench.py to
+// measure the DP-pipe roofline the sigma=16 filter is bound by.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(int iters, double a, double b, double* __restrict__ out) {
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = (double)(threadIdx.x + i) * 1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = __dadd_rn(__dmul_rn(x[i], a), b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // keep the chains alive
+}
+
+}  // namespace amt
+
 extern "C" {
+
+// Launches the probe on `stream`; *dp_instructions receives the number of DP instructions
+// (DMUL + DADD, thread-level) one launch executes.
+int amt_fp64_probe(int iters, double* scratch, uint64_t* dp_instructions, amt_stream_t stream) {
+  using namespace amt;
+  if (iters <= 0 || !scratch) return AMT_ERR_INVALID;
+  const int blocks = kNumSMs * 8;
+  fp64_probe_kernel<<<blocks, 256, 0, as_stream(stream)>>>(iters, 0.999999, 1e-9, scratch);
+  AMT_LAUNCH_CHECK();
+  if (dp_instructions) *dp_instructions = (uint64_t)blocks * 256ull * 8ull * 2ull * (uint64_t)iters;
+  return AMT_OK;
+}
 
 int amt_version(void) { return 100; }  // 0.1.0
 

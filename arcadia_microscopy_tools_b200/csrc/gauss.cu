@@ -22,73 +22,29 @@
 //    writes lo - hi and reduces the plane min / max (order-preserving keys, one atomic pair
 //    per block) for the percentile stage that follows.
 
-#include "common.cuh"
+#include "conv.cuh"
 
 namespace amt {
 
-constexpr int GR = 8;  // outputs per thread along the filter axis
-
 template <typename T>
-__device__ __forceinline__ double load_as_f64(const T* p, double scale);
-template <>
-__device__ __forceinline__ double load_as_f64<double>(const double* p, double) {
-  return __ldg(p);
-}
-template <>
-__device__ __forceinline__ double load_as_f64<uint16_t>(const uint16_t* p, double scale) {
-  return dmul((double)__ldg(p), scale);  // img_as_float: multiply by 1/65535
+__device__ __forceinline__ double load_as_f64(const T* p, double scale) {
+  return convert_to_f64<T>(__ldg(p), scale);
 }
 
 // acc[o] for the R outputs centred at col[o*stride]; hw[j] = weights[c-j].
 template <int R>
 __device__ __forceinline__ void conv_window(const double* __restrict__ col, const int stride,
                                             const double* __restrict__ hw, const int r, double (&acc)[R]) {
-  double L[R], Rt[R];
-  {
-    const double w0 = hw[0];
-#pragma unroll
-    for (int o = 0; o < R; ++o) acc[o] = dmul(col[o * stride], w0);
-  }
-  if (r == 0) return;
-#pragma unroll
-  for (int o = 0; o < R; ++o) {
-    L[o] = col[(o - r) * stride];
-    Rt[o] = col[(o + r) * stride];
-  }
-  int j = r;
-  // r % R leading steps with an explicit window shift
-  for (int t = r % R; t > 0; --t, --j) {
-    const double wj = hw[j];
-#pragma unroll
-    for (int o = 0; o < R; ++o) acc[o] = dadd(acc[o], dmul(dadd(L[o], Rt[o]), wj));
-#pragma unroll
-    for (int o = 0; o < R - 1; ++o) L[o] = L[o + 1];
-    L[R - 1] = col[(R - j) * stride];
-#pragma unroll
-    for (int o = R - 1; o > 0; --o) Rt[o] = Rt[o - 1];
-    Rt[0] = col[(j - 1) * stride];
-  }
-  // groups of R steps; logical L_o lives in L[(o+u)%R], logical R_o in Rt[(o-u+R)%R]
-  for (; j >= R; j -= R) {
-#pragma unroll
-    for (int u = 0; u < R; ++u) {
-      const int jj = j - u;
-      const double wj = hw[jj];
-#pragma unroll
-      for (int o = 0; o < R; ++o)
-        acc[o] = dadd(acc[o], dmul(dadd(L[(o + u) % R], Rt[(o - u + R) % R]), wj));
-      L[u] = col[(R - jj) * stride];
-      Rt[R - 1 - u] = col[(jj - 1) * stride];
-    }
-  }
+  conv_exact<R>([&](int k) -> double { return col[k * stride]; }, hw, r, acc);
 }
 
 // ------------------------------------------------------------------ V pass
 constexpr int GV_TW = 32;
 constexpr int GV_TH = 64;  // = 8 thread rows * GR
+constexpr int GV_BATCH = 24;  // tile rows per thread when radius <= 64
 
 template <typename InT, bool DUAL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gauss_v_kernel(const InT* __restrict__ in, const double scale, double* __restrict__ out_a,
                double* __restrict__ out_b, const int64_t n, const int64_t inner,
                const double* __restrict__ hw_a, const int r_a, const double* __restrict__ hw_b, const int r_b) {
@@ -109,10 +65,27 @@ gauss_v_kernel(const InT* __restrict__ in, const double scale, double* __restric
   const int64_t plane = (int64_t)blockIdx.z * n * inner;
   const InT* src = in + plane;
   const bool xok = x < inner;
-  for (int s = ty; s < rows; s += 8) {
-    int64_t y = y0 - rmax + s;
-    y = y < 0 ? 0 : (y > n - 1 ? n - 1 : y);  // mode='nearest'
-    tile[s * GV_TW + tx] = xok ? load_as_f64<InT>(src + y * inner + x, scale) : 0.0;
+  if (rows <= 8 * GV_BATCH) {
+    // all global loads of the tile in flight at once (one exposed latency, not rows/8 of them)
+    InT raw[GV_BATCH];
+#pragma unroll
+    for (int i = 0; i < GV_BATCH; ++i) {
+      const int s = ty + 8 * i;
+      int64_t y = y0 - rmax + s;
+      y = y < 0 ? 0 : (y > n - 1 ? n - 1 : y);  // mode='nearest'
+      raw[i] = (xok && s < rows) ? __ldg(src + y * inner + x) : InT(0);
+    }
+#pragma unroll
+    for (int i = 0; i < GV_BATCH; ++i) {
+      const int s = ty + 8 * i;
+      if (s < rows) tile[s * GV_TW + tx] = convert_to_f64<InT>(raw[i], scale);
+    }
+  } else {
+    for (int s = ty; s < rows; s += 8) {
+      int64_t y = y0 - rmax + s;
+      y = y < 0 ? 0 : (y > n - 1 ? n - 1 : y);
+      tile[s * GV_TW + tx] = xok ? load_as_f64<InT>(src + y * inner + x, scale) : 0.0;
+    }
   }
   __syncthreads();
 
@@ -140,12 +113,39 @@ constexpr int GH_ROWS = 32;
 constexpr int GH_TX = 64;  // = 8 warps * GR
 constexpr int GH_PITCH = 33;
 constexpr int GH_STAGE_PITCH = GH_TX + 1;
+constexpr int GH_BATCH = 6;  // column groups per thread and row when radius <= 64
 
 template <typename InT>
 __device__ __forceinline__ void gh_load_tile(double* tile, const InT* __restrict__ src, const double scale,
                                              const int64_t row0, const int64_t nrows, const int64_t n,
                                              const int64_t x0, const int r, const int warp, const int lane) {
   const int width = GH_TX + 2 * r;
+  if (width <= 32 * GH_BATCH) {
+    // 4 rows x GH_BATCH column groups per thread, every load issued before the first store
+    InT raw[4][GH_BATCH];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t row = row0 + warp + 8 * k;
+      const bool rok = row < nrows;
+      const InT* p = src + (rok ? row : 0) * n;
+#pragma unroll
+      for (int i = 0; i < GH_BATCH; ++i) {
+        const int xx = lane + 32 * i;
+        int64_t gx = x0 - r + xx;
+        gx = gx < 0 ? 0 : (gx > n - 1 ? n - 1 : gx);
+        raw[k][i] = (rok && xx < width) ? __ldg(p + gx) : InT(0);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int i = 0; i < GH_BATCH; ++i) {
+        const int xx = lane + 32 * i;
+        if (xx < width) tile[xx * GH_PITCH + warp + 8 * k] = convert_to_f64<InT>(raw[k][i], scale);
+      }
+    }
+    return;
+  }
   for (int rr = warp; rr < GH_ROWS; rr += 8) {
     const int64_t row = row0 + rr;
     const bool rok = row < nrows;
@@ -161,7 +161,7 @@ __device__ __forceinline__ void gh_load_tile(double* tile, const InT* __restrict
 // grid: (row blocks, x tiles, planes).  DUAL: out = conv(in_a, hw_a) - conv(in_b, hw_b) and
 // per-plane min/max keys (minmax may be null).
 template <typename InT, bool DUAL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gauss_h_kernel(const InT* __restrict__ in_a, const double* __restrict__ in_b, const double scale,
                double* __restrict__ out, const int64_t nrows, const int64_t n,
                const double* __restrict__ hw_a, const int r_a, const double* __restrict__ hw_b, const int r_b,
@@ -299,21 +299,19 @@ int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st) {
   return AMT_OK;
 }
 
-int dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,
-          const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, double* tmp_lo, double* tmp_hi,
-          uint64_t* minmax, cudaStream_t st) {
-  if (!in || !out || !tmp_lo || !tmp_hi || !hw_lo || !hw_hi) return AMT_ERR_INVALID;
-  if (n_img <= 0 || h <= 0 || w <= 0 || r_lo < 0 || r_hi < 0) return AMT_ERR_INVALID;
-  if (minmax) AMT_TRY(minmax_init(minmax, n_img, st));
-  if (in_dtype == AMT_U16) {
-    AMT_TRY((launch_v<uint16_t, true>((const uint16_t*)in, in_scale, tmp_lo, tmp_hi, n_img, h, w, hw_lo, r_lo,
-                                      hw_hi, r_hi, st)));
-  } else if (in_dtype == AMT_F64) {
-    AMT_TRY((launch_v<double, true>((const double*)in, 1.0, tmp_lo, tmp_hi, n_img, h, w, hw_lo, r_lo, hw_hi,
-                                    r_hi, st)));
-  } else {
-    return AMT_ERR_UNSUPPORTED;
-  }
+int dog_axis0_generic(const void* in, int in_dtype, double in_scale, int64_t n_img, int64_t h, int64_t w,
+                      const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, double* tmp_lo, double* tmp_hi,
+                      cudaStream_t st) {
+  if (in_dtype == AMT_U16)
+    return launch_v<uint16_t, true>((const uint16_t*)in, in_scale, tmp_lo, tmp_hi, n_img, h, w, hw_lo, r_lo, hw_hi,
+                                    r_hi, st);
+  if (in_dtype == AMT_F64)
+    return launch_v<double, true>((const double*)in, 1.0, tmp_lo, tmp_hi, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, st);
+  return AMT_ERR_UNSUPPORTED;
+}
+
+int dog_axis1_generic(const double* tmp_lo, const double* tmp_hi, double* out, int64_t n_img, int64_t h, int64_t w,
+                      const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, uint64_t* minmax, cudaStream_t st) {
   return launch_h<double, true>(tmp_lo, tmp_hi, 1.0, out, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, minmax, st);
 }
 
@@ -343,13 +341,6 @@ int amt_gaussian_axis(const void* in, int in_dtype, double in_scale, double* out
     return launch_v<double, false>((const double*)in, 1.0, out, nullptr, outer, n, inner, half_w, radius, nullptr,
                                    0, st);
   return AMT_ERR_UNSUPPORTED;
-}
-
-int amt_dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,
-              const double* half_w_lo, int r_lo, const double* half_w_hi, int r_hi, double* tmp_lo, double* tmp_hi,
-              uint64_t* minmax_keys, amt_stream_t stream) {
-  return amt::dog2d(in, in_dtype, in_scale, out, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, tmp_lo, tmp_hi,
-                    minmax_keys, amt::as_stream(stream));
 }
 
 int amt_sub_f64(const double* a, const double* b, double* out, int64_t n, amt_stream_t stream) {

@@ -51,6 +51,10 @@ const char* amt_strerror(int status);
 const char* amt_last_cuda_error(void);
 /* Number of kernels this library has launched in the calling process (bench gpu_launches). */
 uint64_t amt_launch_count(void);
+/* FP64 issue-rate probe (non-FMA DMUL + DADD chains, the Gaussian's instruction mix without
+ * memory traffic): bench.py times it to get the measured DP-pipe roofline.  scratch: at least
+ * 148*8*256 doubles.  *dp_instructions = thread-level DP instructions of one launch. */
+int amt_fp64_probe(int iters, double* scratch, uint64_t* dp_instructions, amt_stream_t stream);
 
 /* ------------------------------------------------------------------ Gaussian / DoG
  * ref: operations.py:91  ski.filters.difference_of_gaussians -> [3p] scipy.ndimage.
@@ -76,6 +80,16 @@ int amt_dog2d(const void* in, int in_dtype, double in_scale, double* out,
               int64_t n_img, int64_t h, int64_t w,
               const double* half_w_lo, int r_lo, const double* half_w_hi, int r_hi,
               double* tmp_lo, double* tmp_hi, uint64_t* minmax_keys, amt_stream_t stream);
+
+/* The two kernels of amt_dog2d, callable on their own (per-kernel timing, custom staging):
+ * axis 0 pass of both filters (input -> tmp_lo, tmp_hi), then axis 1 pass + subtraction
+ * (+ min/max keys). */
+int amt_dog2d_axis0(const void* in, int in_dtype, double in_scale, int64_t n_img, int64_t h, int64_t w,
+                    const double* half_w_lo, int r_lo, const double* half_w_hi, int r_hi,
+                    double* tmp_lo, double* tmp_hi, amt_stream_t stream);
+int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int64_t n_img, int64_t h, int64_t w,
+                    const double* half_w_lo, int r_lo, const double* half_w_hi, int r_hi,
+                    uint64_t* minmax_keys, amt_stream_t stream);
 
 /* out = a - b elementwise (N-D DoG fallback: two full Gaussians then subtract). */
 int amt_sub_f64(const double* a, const double* b, double* out, int64_t n, amt_stream_t stream);
