@@ -14,6 +14,8 @@
 // histograms, then flushed with one global atomic per non-empty bin.  HBM-bound: 8 B read +
 // 8 B written per sample.
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace amt {
@@ -30,6 +32,29 @@ __device__ __forceinline__ double map_value(double x, const amt_map_params& p) {
     } else {
       y = fmin(fmax(y, p.o1), p.o2);
     }
+  }
+  return y;
+}
+
+// The per-plane flags are block-uniform: resolve them once, outside the sample loop.
+//   mode 0: FILL   1: SUBCLIP   2: RESCALE (p1 != p2)   3: SUBCLIP + RESCALE (p1 != p2)
+//   mode 4: anything else (generic path, e.g. the degenerate p1 == p2 branch)
+__device__ __forceinline__ int map_mode(const amt_map_params& p) {
+  if (p.flags & AMT_MAP_FILL) return 0;
+  if (p.flags == AMT_MAP_SUBCLIP) return 1;
+  if ((p.flags & AMT_MAP_RESCALE) && p.p1 != p.p2) return (p.flags & AMT_MAP_SUBCLIP) ? 3 : 2;
+  return 4;
+}
+
+template <int MODE>
+__device__ __forceinline__ double map_value_mode(double x, const amt_map_params& p, const double den, const double gain) {
+  if (MODE == 0) return p.o1;
+  if (MODE == 4) return map_value(x, p);
+  double y = x;
+  if (MODE == 1 || MODE == 3) y = fmax(dsub(y, p.lvl), 0.0);
+  if (MODE == 2 || MODE == 3) {
+    y = fmin(fmax(y, p.p1), p.p2);
+    y = dadd(dmul(ddiv(dsub(y, p.p1), den), gain), p.o1);
   }
   return y;
 }
@@ -90,7 +115,26 @@ __device__ __forceinline__ double map_load<uint16_t>(const uint16_t* p) {
   return (double)*p;
 }
 
-template <typename InT, bool HIST>
+template <typename InT>
+__device__ __forceinline__ void load4(const InT* p, double* v);
+template <>
+__device__ __forceinline__ void load4<double>(const double* p, double* v) {
+  const int4 a = ld_nc_int4(p), b = ld_nc_int4(p + 2);
+  v[0] = __hiloint2double(a.y, a.x);
+  v[1] = __hiloint2double(a.w, a.z);
+  v[2] = __hiloint2double(b.y, b.x);
+  v[3] = __hiloint2double(b.w, b.z);
+}
+template <>
+__device__ __forceinline__ void load4<uint16_t>(const uint16_t* p, double* v) {
+  const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+  v[0] = (double)(a.x & 0xffffu);
+  v[1] = (double)(a.x >> 16);
+  v[2] = (double)(a.y & 0xffffu);
+  v[3] = (double)(a.y >> 16);
+}
+
+template <typename InT, bool HIST, bool VEC>
 __global__ void __launch_bounds__(256)
 map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, const amt_map_params* __restrict__ params,
            uint32_t* __restrict__ hist256, int hist_every, int hist_offset) {
@@ -107,18 +151,49 @@ map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, cons
     hr = make_hist_range(p.hist_first, p.hist_last);
     __syncthreads();
   }
-  const int64_t step = (int64_t)gridDim.x * 256;
-  const int64_t start = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  // warp-uniform trip count so that __match_any_sync sees the full warp
-  const int64_t warp_start = start - (threadIdx.x & 31);
-  for (int64_t i = start, wi = warp_start; wi < n; i += step, wi += step) {
-    const bool valid = i < n;
-    double y = 0.0;
-    if (valid) {
-      y = map_value(map_load<InT>(src + i), p);
-      dst[i] = y;
+  const double den = dsub(p.p2, p.p1), gain = dsub(p.o2, p.o1);
+  auto run = [&](auto mode_tag) {
+    constexpr int MODE = decltype(mode_tag)::value;
+    if (VEC) {
+      // 4 consecutive samples per thread and iteration: two 16-byte loads (one 8-byte load for
+      // uint16), two 16-byte stores; two iterations in flight per thread
+      const int64_t n4 = n >> 2;
+      const int64_t step = (int64_t)gridDim.x * 256;
+      for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < n4; q += 2 * step) {
+        double v[8];
+        const int64_t q2 = q + step;
+        const bool second = q2 < n4;
+        load4<InT>(src + 4 * q, v);
+        if (second) load4<InT>(src + 4 * q2, v + 4);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = map_value_mode<MODE>(v[e], p, den, gain);
+        *reinterpret_cast<double2*>(dst + 4 * q) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(dst + 4 * q + 2) = make_double2(v[2], v[3]);
+        if (second) {
+          *reinterpret_cast<double2*>(dst + 4 * q2) = make_double2(v[4], v[5]);
+          *reinterpret_cast<double2*>(dst + 4 * q2 + 2) = make_double2(v[6], v[7]);
+        }
+        if (HIST && do_hist) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (e < 4 || second) atomicAdd(&wh[hist_bin(hr, v[e])], 1u);
+        }
+      }
+    } else {
+      const int64_t step = (int64_t)gridDim.x * 256;
+      for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
+        const double y = map_value_mode<MODE>(map_load<InT>(src + i), p, den, gain);
+        dst[i] = y;
+        if (HIST && do_hist) atomicAdd(&wh[hist_bin(hr, y)], 1u);
+      }
     }
-    if (HIST && do_hist) hist_add_warp(wh, valid ? hist_bin(hr, y) : 0, valid);
+  };
+  switch (map_mode(p)) {
+    case 0: run(std::integral_constant<int, 0>{}); break;
+    case 1: run(std::integral_constant<int, 1>{}); break;
+    case 2: run(std::integral_constant<int, 2>{}); break;
+    case 3: run(std::integral_constant<int, 3>{}); break;
+    default: run(std::integral_constant<int, 4>{}); break;
   }
   if (HIST && do_hist) {
     __syncthreads();
@@ -286,20 +361,27 @@ static unsigned stream_blocks(int64_t n, int64_t n_img, int per_thread) {
 int map_launch(const void* in, int in_dtype, double* out, int64_t n_img, int64_t n, const amt_map_params* params,
                uint32_t* hist256, int hist_every, int hist_offset, cudaStream_t st) {
   if (!in || !out || !params || n_img <= 0 || n <= 0 || n_img > 65535 || hist_every < 1) return AMT_ERR_INVALID;
-  dim3 grid(stream_blocks(n, n_img, 8), (unsigned)n_img);
+  const bool vec = (n % 4 == 0) && (((uintptr_t)in) % 16 == 0) && (((uintptr_t)out) % 16 == 0);
+  dim3 grid(stream_blocks(n, n_img, vec ? 16 : 8), (unsigned)n_img);
+#define AMT_MAP_LAUNCH(T, H, V)                                                                             \
+  map_kernel<T, H, V><<<grid, 256, 0, st>>>((const T*)in, out, n, params, (H) ? hist256 : nullptr, (H) ? hist_every : 1, \
+                                            (H) ? hist_offset : 0)
   if (in_dtype == AMT_F64) {
-    if (hist256)
-      map_kernel<double, true><<<grid, 256, 0, st>>>((const double*)in, out, n, params, hist256, hist_every, hist_offset);
-    else
-      map_kernel<double, false><<<grid, 256, 0, st>>>((const double*)in, out, n, params, nullptr, 1, 0);
+    if (hist256) {
+      if (vec) AMT_MAP_LAUNCH(double, true, true); else AMT_MAP_LAUNCH(double, true, false);
+    } else {
+      if (vec) AMT_MAP_LAUNCH(double, false, true); else AMT_MAP_LAUNCH(double, false, false);
+    }
   } else if (in_dtype == AMT_U16) {
-    if (hist256)
-      map_kernel<uint16_t, true><<<grid, 256, 0, st>>>((const uint16_t*)in, out, n, params, hist256, hist_every, hist_offset);
-    else
-      map_kernel<uint16_t, false><<<grid, 256, 0, st>>>((const uint16_t*)in, out, n, params, nullptr, 1, 0);
+    if (hist256) {
+      if (vec) AMT_MAP_LAUNCH(uint16_t, true, true); else AMT_MAP_LAUNCH(uint16_t, true, false);
+    } else {
+      if (vec) AMT_MAP_LAUNCH(uint16_t, false, true); else AMT_MAP_LAUNCH(uint16_t, false, false);
+    }
   } else {
     return AMT_ERR_UNSUPPORTED;
   }
+#undef AMT_MAP_LAUNCH
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }

@@ -148,14 +148,23 @@ sel_hist_kernel(const double* __restrict__ data, int64_t n, SelPlane* __restrict
   const double mn = planes[img].mn, mx = planes[img].mx, scale = planes[img].scale;
   uint32_t eqmin = 0, eqmax = 0;
   const int64_t step = (int64_t)gridDim.x * 256;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
-    const double x = p[i];
-    if (x == mn) {
-      ++eqmin;
-    } else if (x == mx) {
-      ++eqmax;
-    } else {
-      atomicAdd(&sh[sel_bin(x, mn, scale)], 1u);
+  // four independent loads in flight per thread (the pass is HBM-bound)
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += 4 * step) {
+    double x[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) x[e] = (i + e * step < n) ? __ldg(p + i + e * step) : mn;
+    const int valid = (int)((n - i + step - 1) / step);  // samples of this iteration inside the plane
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e < valid) {
+        if (x[e] == mn) {
+          ++eqmin;
+        } else if (x[e] == mx) {
+          ++eqmax;
+        } else {
+          atomicAdd(&sh[sel_bin(x[e], mn, scale)], 1u);
+        }
+      }
     }
   }
   eqmin = (uint32_t)warp_sum_i32((int)eqmin);
@@ -281,15 +290,15 @@ sel_compact_kernel(const double* __restrict__ data, int64_t n, SelPlane* __restr
                    double* __restrict__ cand, int64_t cap) {
   __shared__ uint32_t s_cnt[AMT_MAX_RANKS];
   __shared__ uint32_t s_base[AMT_MAX_RANKS];
-  __shared__ int s_lbin[AMT_MAX_RANKS];
+  __shared__ uint8_t s_lut[SEL_NB];  // bin -> candidate list id (0xff: not wanted)
   const int64_t img = blockIdx.y;
   SelPlane& pl = planes[img];
   const int n_lists = pl.n_lists;
   if (n_lists == 0) return;
-  if (threadIdx.x < AMT_MAX_RANKS) {
-    s_cnt[threadIdx.x] = 0;
-    s_lbin[threadIdx.x] = threadIdx.x < n_lists ? pl.list_bin[threadIdx.x] : -2;
-  }
+  for (int i = threadIdx.x; i < SEL_NB / 4; i += 256) reinterpret_cast<uint32_t*>(s_lut)[i] = 0xffffffffu;
+  if (threadIdx.x < AMT_MAX_RANKS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x < n_lists) s_lut[pl.list_bin[threadIdx.x]] = (uint8_t)threadIdx.x;
   __syncthreads();
   const double mn = pl.mn, mx = pl.mx, scale = pl.scale;
   const double* p = data + img * n;
@@ -299,16 +308,14 @@ sel_compact_kernel(const double* __restrict__ data, int64_t n, SelPlane* __restr
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int64_t i = base + e * 256 + threadIdx.x;
+    x[e] = (i < n) ? __ldg(p + i) : mn;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
     slot[e] = -1;
-    if (i < n) {
-      x[e] = p[i];
-      if (x[e] != mn && x[e] != mx) {
-        const int b = sel_bin(x[e], mn, scale);
-        int l = -1;
-        for (int j = 0; j < n_lists; ++j)
-          if (s_lbin[j] == b) l = j;
-        if (l >= 0) slot[e] = (l << 24) | (int)atomicAdd(&s_cnt[l], 1u);
-      }
+    if (x[e] != mn && x[e] != mx) {  // also rejects the padding of a partial chunk
+      const int l = s_lut[sel_bin(x[e], mn, scale)];
+      if (l != 0xff) slot[e] = (l << 24) | (int)atomicAdd(&s_cnt[l], 1u);
     }
   }
   __syncthreads();
