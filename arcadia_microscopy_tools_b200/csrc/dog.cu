@@ -22,6 +22,8 @@
 //    straight from global memory (L1) instead of a second ring, which keeps two CTAs per SM.
 // The inner loop is conv_exact (conv.cuh).
 
+#include <cstdlib>
+
 #include "conv.cuh"
 
 namespace amt {

@@ -22,13 +22,17 @@ struct amt_executor {
   int r_lo, r_hi;
   int64_t ranks[6];
   double g_bg, g_lo, g_hi;
-  cudaStream_t s_compute, s_in, s_out;
+  // s_dog runs the FP64-bound DoG of chunk i+1 while s_compute (higher priority, HBM-bound
+  // kernels) finishes chunk i: the two stages stress different units, so they overlap on an SM
+  cudaStream_t s_compute, s_dog, s_in, s_out;
   cudaEvent_t ev_start, ev_stop;
   cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+  cudaEvent_t ev_dog_done[2], ev_dog_free[2];
+  int64_t chunks_issued;
   // device buffers
   double *hw_lo, *hw_hi;
-  double *tmp_lo, *tmp_hi, *dog, *pre;
-  uint64_t* mm;
+  double *tmp_lo, *tmp_hi, *dog[2], *pre;
+  uint64_t* mm[2];
   double* stats;
   amt_map_params* params;
   void* sel_scratch;
@@ -69,6 +73,20 @@ static void rank_pair(int64_t n, double q, int64_t* lo, int64_t* hi, double* gam
   *gamma = v - (double)l;
 }
 
+// stage A1 on s_dog: DoG of one chunk into dog[slot] / mm[slot]
+static int enqueue_dog(amt_executor* ex, const uint16_t* in, int g, cudaEvent_t wait_input) {
+  const amt_fov_config& c = ex->cfg;
+  const int slot = (int)(ex->chunks_issued & 1);
+  const int64_t planes = (int64_t)g * c.n_channels;
+  if (wait_input) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, wait_input, 0));
+  if (ex->chunks_issued >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, ex->ev_dog_free[slot], 0));
+  AMT_TRY(dog2d(in, AMT_U16, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, ex->hw_lo, ex->r_lo, ex->hw_hi,
+                ex->r_hi, ex->tmp_lo, ex->tmp_hi, ex->mm[slot], ex->s_dog));
+  AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_done[slot], ex->s_dog));
+  return AMT_OK;
+}
+
+// everything after the DoG, on s_compute
 static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* given, int g, double* tab_thr,
                          int32_t* cnt_thr, double* tab_given, int32_t* cnt_given, double* thr_out, int32_t* lab_thr_out,
                          int32_t* lab_given_out, double* pre_out) {
@@ -76,19 +94,22 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
   const int C = c.n_channels;
   const int64_t H = c.height, W = c.width, HW = H * W;
   const int64_t planes = (int64_t)g * C;
+  const int slot = (int)(ex->chunks_issued & 1);
   cudaStream_t st = ex->s_compute;
   double* pre = pre_out ? pre_out : ex->pre;
   int32_t* lab_thr = lab_thr_out ? lab_thr_out : ex->lab_thr;
   int32_t* lab_given = lab_given_out ? lab_given_out : ex->lab_given;
   double* thr = thr_out ? thr_out : ex->thr;
+  double* dog = ex->dog[slot];
+  uint64_t* mm = ex->mm[slot];
 
-  // stage A: DoG -> order statistics -> plan -> map (+ histogram of the segmentation planes)
-  AMT_TRY(dog2d(in, AMT_U16, 1.0 / 65535.0, ex->dog, planes, H, W, ex->hw_lo, ex->r_lo, ex->hw_hi, ex->r_hi, ex->tmp_lo,
-                ex->tmp_hi, ex->mm, st));
-  AMT_TRY(amt_select_f64(ex->dog, planes, HW, ex->ranks, 6, ex->mm, ex->stats, ex->sel_scratch, ex->sel_bytes, st));
-  AMT_TRY(plan_dog_rescale(ex->stats, ex->mm, planes, ex->g_bg, ex->g_lo, ex->g_hi, c.out_lo, c.out_hi, ex->params, st));
+  // stage A2: order statistics -> plan -> map (+ histogram of the segmentation planes)
+  AMT_CUDA_TRY(cudaStreamWaitEvent(st, ex->ev_dog_done[slot], 0));
+  AMT_TRY(amt_select_f64(dog, planes, HW, ex->ranks, 6, mm, ex->stats, ex->sel_scratch, ex->sel_bytes, st));
+  AMT_TRY(plan_dog_rescale(ex->stats, mm, planes, ex->g_bg, ex->g_lo, ex->g_hi, c.out_lo, c.out_hi, ex->params, st));
   AMT_CUDA_TRY(cudaMemsetAsync(ex->hist256, 0, (size_t)g * 256 * sizeof(uint32_t), st));
-  AMT_TRY(map_launch(ex->dog, AMT_F64, pre, planes, HW, ex->params, ex->hist256, C, c.seg_channel, st));
+  AMT_TRY(map_launch(dog, AMT_F64, pre, planes, HW, ex->params, ex->hist256, C, c.seg_channel, st));
+  AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_free[slot], st));
   // stage B: Otsu -> threshold + CCL + clear_border
   AMT_TRY(otsu_launch(ex->hist256, 0, ex->params, C, c.seg_channel, nullptr, g, thr, nullptr, 0, st));
   AMT_TRY(label_launch(pre + (int64_t)c.seg_channel * HW, 1, (int64_t)C * HW, thr, 0, g, H, W, 1, lab_thr, cnt_thr,
@@ -102,6 +123,7 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
     AMT_TRY(region_reduce(lab_given, in, C, (int64_t)C * HW, HW, g, H, W, c.max_labels, ex->acc, st));
     AMT_TRY(region_finalize(ex->acc, cnt_given, C, g, c.max_labels, tab_given, st));
   }
+  ex->chunks_issued += 1;
   return AMT_OK;
 }
 
@@ -169,7 +191,10 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
       return fail(AMT_ERR_CUDA);                    \
     }                                               \
   } while (0)
-  EX_CUDA(cudaStreamCreateWithFlags(&ex->s_compute, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  EX_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  EX_CUDA(cudaStreamCreateWithPriority(&ex->s_compute, cudaStreamNonBlocking, prio_hi));
+  EX_CUDA(cudaStreamCreateWithPriority(&ex->s_dog, cudaStreamNonBlocking, prio_lo));
   EX_CUDA(cudaStreamCreateWithFlags(&ex->s_in, cudaStreamNonBlocking));
   EX_CUDA(cudaStreamCreateWithFlags(&ex->s_out, cudaStreamNonBlocking));
   EX_CUDA(cudaEventCreate(&ex->ev_start));
@@ -178,6 +203,8 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
     EX_CUDA(cudaEventCreateWithFlags(&ex->ev_in[s], cudaEventDisableTiming));
     EX_CUDA(cudaEventCreateWithFlags(&ex->ev_done[s], cudaEventDisableTiming));
     EX_CUDA(cudaEventCreateWithFlags(&ex->ev_out[s], cudaEventDisableTiming));
+    EX_CUDA(cudaEventCreateWithFlags(&ex->ev_dog_done[s], cudaEventDisableTiming));
+    EX_CUDA(cudaEventCreateWithFlags(&ex->ev_dog_free[s], cudaEventDisableTiming));
   }
   EX_TRY(dmalloc(ex, (void**)&ex->hw_lo, (size_t)(r_lo + 1) * sizeof(double)));
   EX_TRY(dmalloc(ex, (void**)&ex->hw_hi, (size_t)(r_hi + 1) * sizeof(double)));
@@ -186,9 +213,11 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
   const size_t plane_f64 = (size_t)planes * HW * sizeof(double);
   EX_TRY(dmalloc(ex, (void**)&ex->tmp_lo, plane_f64));
   EX_TRY(dmalloc(ex, (void**)&ex->tmp_hi, plane_f64));
-  EX_TRY(dmalloc(ex, (void**)&ex->dog, plane_f64));
+  for (int s = 0; s < 2; ++s) {
+    EX_TRY(dmalloc(ex, (void**)&ex->dog[s], plane_f64));
+    EX_TRY(dmalloc(ex, (void**)&ex->mm[s], (size_t)planes * 2 * sizeof(uint64_t)));
+  }
   EX_TRY(dmalloc(ex, (void**)&ex->pre, plane_f64));
-  EX_TRY(dmalloc(ex, (void**)&ex->mm, (size_t)planes * 2 * sizeof(uint64_t)));
   EX_TRY(dmalloc(ex, (void**)&ex->stats, (size_t)planes * 6 * sizeof(double)));
   EX_TRY(dmalloc(ex, (void**)&ex->params, (size_t)planes * sizeof(amt_map_params)));
   ex->sel_bytes = amt_select_f64_scratch_bytes(planes, HW);
@@ -211,7 +240,8 @@ void amt_executor_destroy(amt_executor* ex) {
   if (!ex) return;
   cudaSetDevice(ex->cfg.device);
   cudaDeviceSynchronize();
-  void* bufs[] = {ex->hw_lo, ex->hw_hi, ex->tmp_lo, ex->tmp_hi, ex->dog, ex->pre, ex->mm, ex->stats, ex->params,
+  void* bufs[] = {ex->hw_lo, ex->hw_hi, ex->tmp_lo, ex->tmp_hi, ex->dog[0], ex->dog[1], ex->pre, ex->mm[0], ex->mm[1],
+                  ex->stats, ex->params,
                   ex->sel_scratch, ex->hist256, ex->thr, ex->lab_thr, ex->lab_given, ex->label_scratch, ex->acc};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -223,10 +253,13 @@ void amt_executor_destroy(amt_executor* ex) {
     if (ex->ev_in[s]) cudaEventDestroy(ex->ev_in[s]);
     if (ex->ev_done[s]) cudaEventDestroy(ex->ev_done[s]);
     if (ex->ev_out[s]) cudaEventDestroy(ex->ev_out[s]);
+    if (ex->ev_dog_done[s]) cudaEventDestroy(ex->ev_dog_done[s]);
+    if (ex->ev_dog_free[s]) cudaEventDestroy(ex->ev_dog_free[s]);
   }
   if (ex->ev_start) cudaEventDestroy(ex->ev_start);
   if (ex->ev_stop) cudaEventDestroy(ex->ev_stop);
   if (ex->s_compute) cudaStreamDestroy(ex->s_compute);
+  if (ex->s_dog) cudaStreamDestroy(ex->s_dog);
   if (ex->s_in) cudaStreamDestroy(ex->s_in);
   if (ex->s_out) cudaStreamDestroy(ex->s_out);
   delete ex;
@@ -246,8 +279,10 @@ int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_
   const int64_t HW = (int64_t)c.height * c.width;
   const int64_t tab = (int64_t)AMT_TABLE_COLS(C) * c.max_labels;
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_start, ex->s_compute));
+  AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, ex->ev_start, 0));
   for (int64_t f0 = 0; f0 < n_fov; f0 += c.chunk_fovs) {
     const int g = (int)((n_fov - f0 < c.chunk_fovs) ? n_fov - f0 : c.chunk_fovs);
+    AMT_TRY(enqueue_dog(ex, fovs + f0 * C * HW, g, nullptr));
     AMT_TRY(process_chunk(ex, fovs + f0 * C * HW, given_labels ? given_labels + f0 * HW : nullptr, g,
                           tables_thr + f0 * tab, counts_thr + f0, tables_given ? tables_given + f0 * tab : nullptr,
                           counts_given ? counts_given + f0 : nullptr, thresholds ? thresholds + f0 : nullptr,
@@ -272,6 +307,7 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const int
   const int64_t HW = (int64_t)c.height * c.width;
   const int64_t tab = (int64_t)AMT_TABLE_COLS(C) * c.max_labels;
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_start, ex->s_compute));
+  AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, ex->ev_start, 0));
   int64_t chunk = 0;
   for (int64_t f0 = 0; f0 < n_fov; f0 += c.chunk_fovs, ++chunk) {
     const int g = (int)((n_fov - f0 < c.chunk_fovs) ? n_fov - f0 : c.chunk_fovs);
@@ -287,6 +323,7 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const int
     // output slot s is free once its previous D2H has finished
     AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_compute, ex->ev_in[s], 0));
     if (chunk >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_compute, ex->ev_out[s], 0));
+    AMT_TRY(enqueue_dog(ex, ex->in_slot[s], g, ex->ev_in[s]));
     AMT_TRY(process_chunk(ex, ex->in_slot[s], given ? ex->given_slot[s] : nullptr, g, ex->tab_thr_slot[s],
                           ex->cnt_thr_slot[s], ex->tab_given_slot[s], ex->cnt_given_slot[s], ex->thr_slot[s], nullptr,
                           nullptr, nullptr));
@@ -309,6 +346,7 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const int
   }
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_stop, ex->s_compute));
   AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_in));
+  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_dog));
   AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_compute));
   AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_out));
   return AMT_OK;
@@ -319,6 +357,7 @@ int amt_executor_sync(amt_executor* ex) {
   if (!ex) return AMT_ERR_INVALID;
   AMT_CUDA_TRY(cudaSetDevice(ex->cfg.device));
   AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_in));
+  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_dog));
   AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_compute));
   AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_out));
   return AMT_OK;
