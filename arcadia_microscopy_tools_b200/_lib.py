@@ -70,7 +70,7 @@ class FovConfig(C.Structure):
         ("max_labels", C.c_int32),
         ("max_label_value", C.c_int32),
         ("quantify_given_mask", C.c_int32),
-        ("keep_preprocessed", C.c_int32),
+        ("with_shape", C.c_int32),
         ("low_sigma", C.c_double),
         ("high_sigma", C.c_double),
         ("bg_percentile", C.c_double),

@@ -33,6 +33,7 @@ class FovPipelineConfig:
     max_labels: int = 4096
     max_label_value: int = 65535
     quantify_given_mask: bool = True
+    with_shape: bool = False  # also perimeter / area_convex columns (not part of workload W)
     low_sigma: float = 0.6
     high_sigma: float = 16.0
     bg_percentile: float = 0.0
@@ -64,7 +65,7 @@ class FovBatchExecutor:
             device=dev.index, n_channels=config.n_channels, height=config.height, width=config.width,
             seg_channel=config.seg_channel, chunk_fovs=config.chunk_fovs, max_labels=config.max_labels,
             max_label_value=config.max_label_value, quantify_given_mask=1 if config.quantify_given_mask else 0,
-            keep_preprocessed=0, low_sigma=config.low_sigma, high_sigma=config.high_sigma,
+            with_shape=1 if config.with_shape else 0, low_sigma=config.low_sigma, high_sigma=config.high_sigma,
             bg_percentile=config.bg_percentile, pct_lo=config.percentile_range[0], pct_hi=config.percentile_range[1],
             out_lo=config.out_range[0], out_hi=config.out_range[1],
         )

@@ -43,6 +43,8 @@ struct amt_executor {
   void* label_scratch;
   size_t label_bytes;
   uint64_t* acc;
+  void* shape_scratch;
+  size_t shape_bytes;
   // host-path staging (two slots)
   uint16_t* in_slot[2];
   int32_t* given_slot[2];
@@ -117,11 +119,16 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
   // stage C: per-cell tables over the raw channels
   AMT_TRY(region_reduce(lab_thr, in, C, (int64_t)C * HW, HW, g, H, W, c.max_labels, ex->acc, st));
   AMT_TRY(region_finalize(ex->acc, cnt_thr, C, g, c.max_labels, tab_thr, st));
+  if (c.with_shape)
+    AMT_TRY(region_shape(lab_thr, ex->acc, C, cnt_thr, g, H, W, c.max_labels, tab_thr, ex->shape_scratch, ex->shape_bytes, st));
   if (c.quantify_given_mask && given) {
     AMT_TRY(label_launch(given, 2, HW, nullptr, c.max_label_value, g, H, W, 1, lab_given, cnt_given, ex->label_scratch,
                          ex->label_bytes, st));
     AMT_TRY(region_reduce(lab_given, in, C, (int64_t)C * HW, HW, g, H, W, c.max_labels, ex->acc, st));
     AMT_TRY(region_finalize(ex->acc, cnt_given, C, g, c.max_labels, tab_given, st));
+    if (c.with_shape)
+      AMT_TRY(region_shape(lab_given, ex->acc, C, cnt_given, g, H, W, c.max_labels, tab_given, ex->shape_scratch,
+                           ex->shape_bytes, st));
   }
   ex->chunks_issued += 1;
   return AMT_OK;
@@ -230,6 +237,10 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
   EX_TRY(dmalloc(ex, &ex->label_scratch, ex->label_bytes));
   EX_TRY(dmalloc(ex, (void**)&ex->acc,
                  (size_t)cfg->chunk_fovs * AMT_ACC_FIELDS(C) * cfg->max_labels * sizeof(uint64_t)));
+  if (cfg->with_shape) {
+    ex->shape_bytes = amt_region_shape_scratch_bytes(cfg->chunk_fovs, cfg->height, cfg->width, cfg->max_labels);
+    EX_TRY(dmalloc(ex, &ex->shape_scratch, ex->shape_bytes));
+  }
 #undef EX_TRY
 #undef EX_CUDA
   *out = ex;
@@ -242,7 +253,8 @@ void amt_executor_destroy(amt_executor* ex) {
   cudaDeviceSynchronize();
   void* bufs[] = {ex->hw_lo, ex->hw_hi, ex->tmp_lo, ex->tmp_hi, ex->dog[0], ex->dog[1], ex->pre, ex->mm[0], ex->mm[1],
                   ex->stats, ex->params,
-                  ex->sel_scratch, ex->hist256, ex->thr, ex->lab_thr, ex->lab_given, ex->label_scratch, ex->acc};
+                  ex->sel_scratch, ex->hist256, ex->thr, ex->lab_thr, ex->lab_given, ex->label_scratch, ex->acc,
+                  ex->shape_scratch};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (int s = 0; s < 2; ++s) {

@@ -233,7 +233,7 @@ typedef struct amt_fov_config {
   int32_t max_labels;      /* table capacity per FOV and per mask */
   int32_t max_label_value; /* largest value allowed in a given label mask */
   int32_t quantify_given_mask; /* 1: also clear_border + relabel + quantify the given mask */
-  int32_t keep_preprocessed;   /* 1: copy preprocessed planes out (device runs only) */
+  int32_t with_shape;          /* 1: also fill perimeter / area_convex (amt_region_shape) */
   double low_sigma, high_sigma;  /* subtract_background_dog */
   double bg_percentile;
   double pct_lo, pct_hi;         /* rescale_by_percentile percentile_range */

@@ -180,3 +180,49 @@ def test_golden_config1_tables(golden):
         g = SegmentationMask(golden["given"].astype(np.int64), chans, property_names=["label", "area"], intensity_property_names=["intensity_sum"])
         assert np.array_equal(g.label_image, golden[f"bg{bg}/labels_given"])
         assert np.array_equal(g.cell_properties["area"], golden[f"bg{bg}/given/area"])
+
+
+def test_default_property_list_including_perimeter_and_convex_area():
+    """The reference's DEFAULT property list (masks.py:15-28): perimeter, area_convex, solidity,
+    circularity come from the shape kernels; area_convex is exact, perimeter a 3-term float sum."""
+    fov, given, _ = make_fov(37, 2, 220, 260, 40)
+    m = SegmentationMask(given.astype(np.int64), {DAPI: fov[1]}, remove_edge_cells=True)
+    assert m.property_names == masks.DEFAULT_CELL_PROPERTY_NAMES
+    want = oracle.cell_properties(m.label_image, {"dapi": fov[1]})
+    got = m.cell_properties
+    assert list(got.keys()) == list(want.keys())
+    assert np.array_equal(got["area_convex"], want["area_convex"])
+    for key in ("perimeter", "solidity", "circularity", "volume", "axis_major_length", "intensity_std_dapi"):
+        _close(got[key], want[key], key)
+    # threshold mask (ragged blobs, single-pixel specks, holes)
+    P = oracle.rescale_by_percentile(oracle.subtract_background_dog(fov[1]), (1, 99))
+    mask = oracle.apply_threshold(P)
+    t = SegmentationMask(mask, remove_edge_cells=False, property_names=["label", "area", "area_convex", "perimeter", "solidity", "circularity"])
+    w2 = oracle.cell_properties(oracle.process_mask(mask, False), None, ["label", "area", "area_convex", "perimeter", "solidity", "circularity"])
+    assert np.array_equal(t.cell_properties["area_convex"], w2["area_convex"])
+    assert np.array_equal(t.cell_properties["area"], w2["area"])
+    for key in ("perimeter", "solidity", "circularity"):
+        _close(t.cell_properties[key], w2[key], key)
+    # the reference's own disc expectations (test_masks.py:187-197 and SURVEY 8a-10)
+    discs = make_label_image((80, 80), [(20, 20, 5), (20, 60, 8), (60, 40, 11)])
+    d = SegmentationMask(discs, remove_edge_cells=False).cell_properties
+    assert d["area_convex"].tolist() == [69.0, 201.0, 381.0]
+    assert np.allclose(d["perimeter"], [27.313708498984763, 48.97056274847714, 68.2842712474619], rtol=1e-12)
+    two = SegmentationMask(make_label_image((60, 60), [(15, 15, 6), (45, 45, 6)]), remove_edge_cells=False).cell_properties
+    assert np.all(two["circularity"] > 0.85) and np.all(two["circularity"] <= 1.1)  # ref: test_masks.py:187-197
+    assert np.allclose(two["perimeter"], 35.31370849898476, rtol=1e-12) and np.all(two["volume"] > 0)
+    # shapes that stress the hull walk: lines, an L, a plus, a fragmented integer label
+    odd = np.zeros((40, 50), dtype=np.int64)
+    odd[3, 5:30] = 1
+    odd[6:30, 40] = 2
+    odd[10:20, 10] = 3
+    odd[19, 10:25] = 3
+    odd[25:34, 20] = 4
+    odd[29, 15:26] = 4
+    odd[36, 3] = 5
+    odd[8, 45] = 6
+    odd[30, 47] = 6  # one label, two far-apart fragments
+    o = SegmentationMask(odd, remove_edge_cells=False, property_names=["label", "area", "area_convex", "perimeter"])
+    wo = oracle.cell_properties(odd, None, ["label", "area", "area_convex", "perimeter"])
+    assert np.array_equal(o.cell_properties["area_convex"], wo["area_convex"])
+    _close(o.cell_properties["perimeter"], wo["perimeter"], "perimeter (odd shapes)")
