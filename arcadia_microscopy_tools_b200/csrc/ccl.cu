@@ -383,22 +383,27 @@ ccl_final_kernel(int32_t* __restrict__ L, const int32_t* __restrict__ aux, const
 __global__ void __launch_bounds__(256)
 relabel_final_kernel(const int32_t* __restrict__ in, const int64_t in_stride, int32_t* __restrict__ L,
                      const int32_t* __restrict__ aux, const int64_t npx, const int32_t* __restrict__ rank,
-                     const int64_t nval, const int use_ccl) {
+                     const int64_t nval, const int use_ccl, const int vec) {
   const int64_t img = blockIdx.y;
   const int32_t* lab = in + img * in_stride;
   int32_t* Lp = L + img * npx;
   const int32_t* ap = aux + img * npx;
   const int32_t* rk = rank + img * nval;
-  const int64_t step = (int64_t)gridDim.x * 256;
-  for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < npx; p += step) {
-    const int v = lab[p];
-    int out = 0;
-    if (v > 0 && v < nval) {
-      bool keep = true;
-      if (use_ccl) keep = ap[Lp[p]] != -1;
-      if (keep) out = __ldg(rk + v);
+  auto one = [&](int v, int root) -> int {
+    if (v <= 0 || v >= nval) return 0;
+    if (use_ccl && __ldg(ap + root) == -1) return 0;
+    return __ldg(rk + v);
+  };
+  const int64_t step = (int64_t)gridDim.x * 256 * 4;
+  for (int64_t p0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; p0 < npx; p0 += step) {
+    if (vec && p0 + 3 < npx) {
+      const int4 v = *reinterpret_cast<const int4*>(lab + p0);
+      int4 r = make_int4(0, 0, 0, 0);
+      if (use_ccl) r = *reinterpret_cast<const int4*>(Lp + p0);
+      *reinterpret_cast<int4*>(Lp + p0) = make_int4(one(v.x, r.x), one(v.y, r.y), one(v.z, r.z), one(v.w, r.w));
+    } else {
+      for (int i = 0; i < 4 && p0 + i < npx; ++i) Lp[p0 + i] = one(lab[p0 + i], use_ccl ? Lp[p0 + i] : 0);
     }
-    Lp[p] = out;
   }
 }
 
@@ -515,7 +520,7 @@ int label_launch(const void* in, int in_kind, int64_t in_stride, const double* t
     scan_kernel<<<(unsigned)n_img, 1024, 0, st>>>(s.present, (int)nval, counts, 1);
     AMT_LAUNCH_CHECK();
     relabel_final_kernel<<<sgrid, 256, 0, st>>>((const int32_t*)in, in_stride, labels_out, s.aux, npx, s.present, nval,
-                                                clear_border);
+                                                clear_border, vec && (in_stride % 4 == 0) && (((uintptr_t)in) % 16 == 0));
     AMT_LAUNCH_CHECK();
     return AMT_OK;
   }

@@ -306,6 +306,71 @@ __global__ void otsu_kernel(const uint32_t* __restrict__ hist, int mode, const a
     if (threadIdx.x == 0) thresholds[img] = center(0);
     return;
   }
+  if (mode != 2) {
+    // 256 bins: only the cumulative sums are sequential (NumPy's order); products, class
+    // means, variances and the arg-max run one bin per thread
+    __shared__ float s_c[256], s_w1[256];
+    __shared__ double s_prod[256], s_m1[256];
+    __shared__ double s_bestv[8];
+    __shared__ int s_besti[8];
+    const int i = threadIdx.x;
+    s_c[i] = (float)h[i];
+    s_prod[i] = dmul((double)s_c[i], center(i));
+    __syncthreads();
+    if (i == 0) {
+      float wsum = 0.0f;
+      double msum = 0.0;
+      for (int k = 0; k < 256; ++k) {
+        wsum = __fadd_rn(wsum, s_c[k]);
+        msum = dadd(msum, s_prod[k]);
+        s_w1[k] = wsum;
+        s_m1[k] = msum;
+      }
+    } else if (i == 32) {
+      float wsum = 0.0f;
+      double msum = 0.0;
+      for (int k = 255; k >= 1; --k) {
+        wsum = __fadd_rn(wsum, s_c[k]);
+        msum = dadd(msum, s_prod[k]);
+        w2[k] = wsum;
+        m2[k] = msum;
+      }
+    }
+    __syncthreads();
+    double var = -1.0;
+    int idx = i;
+    if (i < 255) {
+      const double mean1 = ddiv(s_m1[i], (double)s_w1[i]);
+      const double mean2 = ddiv(m2[i + 1], (double)w2[i + 1]);
+      const float ww = __fmul_rn(s_w1[i], w2[i + 1]);
+      const double d = dsub(mean1, mean2);
+      var = dmul((double)ww, dmul(d, d));
+    }
+    // first maximum: larger variance wins, ties go to the smaller index
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, var, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > var || (ov == var && oi < idx)) {
+        var = ov;
+        idx = oi;
+      }
+    }
+    if ((i & 31) == 0) {
+      s_bestv[i >> 5] = var;
+      s_besti[i >> 5] = idx;
+    }
+    __syncthreads();
+    if (i == 0) {
+      for (int k = 1; k < 8; ++k)
+        if (s_bestv[k] > var || (s_bestv[k] == var && s_besti[k] < idx)) {
+          var = s_bestv[k];
+          idx = s_besti[k];
+        }
+      thresholds[img] = center(idx);
+    }
+    return;
+  }
   if (threadIdx.x == 32) {
     float wsum = 0.0f;
     double msum = 0.0;
@@ -407,7 +472,7 @@ int otsu_launch(const uint32_t* hist, int mode, const amt_map_params* params, in
     m2 = (double*)scratch;
     w2 = (float*)((char*)scratch + (size_t)n_img * 65536 * 8);
   }
-  otsu_kernel<<<(unsigned)n_img, 64, 0, st>>>(hist, mode, params, pstride, poffset, mm, w2, m2, thresholds);
+  otsu_kernel<<<(unsigned)n_img, 256, 0, st>>>(hist, mode, params, pstride, poffset, mm, w2, m2, thresholds);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
