@@ -94,6 +94,7 @@ SIGNATURES: dict[str, tuple] = {
     "amt_last_cuda_error": (C.c_char_p, []),
     "amt_launch_count": (C.c_uint64, []),
     "amt_fp64_probe": (_i, [_i, _p, C.POINTER(C.c_uint64), _p]),
+    "amt_tune": (_i, [C.c_char_p, _i]),
     "amt_gaussian_axis": (_i, [_p, _i, _d, _p, _i64, _i64, _i64, _p, _i, _p]),
     "amt_dog2d": (_i, [_p, _i, _d, _p, _i64, _i64, _i64, _p, _i, _p, _i, _p, _p, _p, _p]),
     "amt_dog2d_axis0": (_i, [_p, _i, _d, _i64, _i64, _i64, _p, _i, _p, _i, _p, _p, _p]),
@@ -152,6 +153,13 @@ def load() -> C.CDLL:
                 fn = getattr(lib, name)
                 fn.restype = restype
                 fn.argtypes = argtypes
+            # AMT_TUNE="key=value,key=value": kernel tuning knobs for benches / sweeps (amt_tune)
+            import os
+
+            for item in filter(None, os.environ.get("AMT_TUNE", "").split(",")):
+                key, _, value = item.partition("=")
+                if lib.amt_tune(key.strip().encode(), int(value)) != AMT_OK:
+                    raise ValueError(f"AMT_TUNE: unknown knob or bad value {item!r}")
             _lib = lib
     return _lib
 

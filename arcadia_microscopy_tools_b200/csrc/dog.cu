@@ -1,245 +1,409 @@
-// Fused 2-D difference of Gaussians: persistent ring-buffer kernels for the hot path.
+// Fused 2-D difference of Gaussians: strip-walking ring-buffer kernels for the hot path.
 //
 // Reference path: operations.py:91 ski.filters.difference_of_gaussians [3p] (see gauss.cu for
 // the arithmetic contract: float64, scipy's operation order, no FMA — bit-identical).
 //
 // These kernels are FP64-pipe-bound (3 DP instructions per tap pair, 2*(1+3*64)+2*(1+3*2) = 400
 // per sample for sigma = 0.6 / 16).  On B200 a DP warp instruction holds the SMSP's issue port
-// for two cycles, so every non-DP instruction in the loop costs DP throughput; the design goal
-// is therefore "nothing but DADD/DMUL and three LDS per tap step":
-//  * one kernel shape for both axes.  Pass 1 filters along axis 0 and writes its two results
-//    TRANSPOSED; pass 2 filters the transposed planes along their axis 0 (= image axis 1) and
-//    writes lo - hi transposed back.  Lanes always run along the contiguous axis (conflict-free
-//    LDS, coalesced LDG) and every thread's 8 outputs are contiguous in the transposed layout
-//    (four 16-byte stores).
-//  * a CTA walks 512 samples along the filter axis and keeps the samples it needs in a
-//    shared-memory ring [rows][32]; the next 64 rows are prefetched into registers while the
-//    current 64 are computed (uint16 -> float64 conversion once per sample, on the way in), so
-//    each sample is fetched once per strip and its latency is hidden.
-//  * the first 2r ring rows are mirrored behind the ring, so a step's window is one contiguous
-//    run and every shared-memory access in the unrolled inner loop is base + constant.
-//  * the narrow (sigma_lo) operand of pass 2 needs only 2*r_lo+8 samples per thread; they come
-//    straight from global memory (L1) instead of a second ring, which keeps two CTAs per SM.
+// for two cycles, so every non-DP instruction costs DP throughput (ncu: issue-slot model
+// 2*DP + other = 97 % of the cycles).  The design goal is therefore "nothing but DADD / DMUL and
+// three LDS per tap step", and as little as possible outside that loop:
+//  * ONE kernel shape for both axes.  A CTA owns a strip of 32 positions along the contiguous
+//    axis (= lanes) and walks the WHOLE filter axis, S = WARPS*R samples per step, keeping the
+//    samples it needs in a shared-memory ring of S-row blocks.  Every pass writes its result
+//    TRANSPOSED (out[col][row]): pass 1 filters the image along axis 0 and writes G^T, pass 2
+//    filters G^T along its axis 0 (= image axis 1) and writes lo - hi back in image layout.
+//    Loads are always lane-contiguous, and a thread's R outputs are contiguous in the output
+//    (R/2 16-byte stores), so no shared-memory transposition is needed anywhere.
+//  * the block of S rows the NEXT step needs is fetched while this step computes: uint16 input
+//    as two/four 8-byte loads per thread held in registers and converted (x * 1/65535) on the
+//    way into the ring, float64 input with cp.async straight into the ring.  One barrier per
+//    step; the prologue (S + 2r rows) is paid once per strip, not once per 512 rows.
+//  * the blocks a step's window can run into past the end of the ring are mirrored behind it,
+//    so the window is one contiguous run and every shared-memory access of the unrolled tap
+//    loop is base + constant.
+//  * the narrow (sigma_lo, r <= 4) filter needs R + 2*r_lo samples per thread; they are taken
+//    from the ring (pass 1) or straight from global memory (pass 2) into registers.
+//  * one CTA per SM (256 threads, ~100 KB of shared memory): the kernel leaves half of every
+//    SM's registers and shared memory free, so the HBM-bound kernels of the previous chunk
+//    (other stream) run next to it instead of time-slicing with it.
 // The inner loop is conv_exact (conv.cuh).
 
 #include <cstdlib>
+#include <cstring>
 
 #include "conv.cuh"
 
 namespace amt {
 
-constexpr int PV_TH = 64;  // samples per step along the filter axis (8 thread rows * GR)
 constexpr int PV_TW = 32;  // lanes along the contiguous axis
-constexpr int SEG = 512;   // samples along the filter axis per CTA
-constexpr size_t kSmemMax = 113 * 1024;  // two CTAs per SM
+constexpr int RLO_MAX = 4;  // largest narrow radius handled in registers
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// acc[o] = x[o]*w[0] + sum_{j = r..1} (x[o-j] + x[o+j]) * w[j], scipy's order, for r <= RLO_MAX;
+// xs[i] holds sample i - RLO_MAX relative to output 0 (static indices only: stays in registers).
 template <int R>
-__device__ __forceinline__ void store_run(double* dst, const double (&v)[R], const int first, const int end, const int vec2) {
-  if (vec2 && first + R <= end) {
+__device__ __forceinline__ void conv_small(const double (&xs)[R + 2 * RLO_MAX], const double* __restrict__ hw,
+                                           const int r, double (&acc)[R]) {
+  const double w0 = hw[0];
 #pragma unroll
-    for (int o = 0; o < R; o += 2) *reinterpret_cast<double2*>(dst + o) = make_double2(v[o], v[o + 1]);
-  } else {
+  for (int o = 0; o < R; ++o) acc[o] = dmul(xs[o + RLO_MAX], w0);
 #pragma unroll
-    for (int o = 0; o < R; ++o)
-      if (first + o < end) dst[o] = v[o];
+  for (int j = RLO_MAX; j >= 1; --j) {
+    if (j <= r) {
+      const double wj = hw[j];
+#pragma unroll
+      for (int o = 0; o < R; ++o)
+        acc[o] = dadd(acc[o], dmul(dadd(xs[o + RLO_MAX - j], xs[o + RLO_MAX + j]), wj));
+    }
   }
 }
 
-// grid (ceil(inner/32), ceil(n/SEG), planes); block (32, 8).
-// FIRST pass : in = image (InT), out_a = G_hi^T, out_b = G_lo^T          (both inner x n)
-// SECOND pass: in = G_hi^T (double), in_lo = G_lo^T, out_a = G_lo - G_hi  transposed back
-template <typename InT, bool SECOND>
-__global__ void __launch_bounds__(256, 2)
-dog_pass_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, const double scale,
-                double* __restrict__ out_a, double* __restrict__ out_b, const int n, const int inner,
-                const double* __restrict__ hw_lo, const int r_lo, const double* __restrict__ hw_hi, const int r_hi,
-                const int ring_rows, uint64_t* __restrict__ minmax, const int vec2) {
-  extern __shared__ double smem[];
-  __shared__ uint64_t s_mm[16];
-  const int rmax = SECOND ? r_hi : (r_lo > r_hi ? r_lo : r_hi);
-  const int mirror_rows = 2 * rmax;  // ring rows [0, mirror) are also kept at [ring_rows, ring_rows + mirror)
-  double* ring = smem;
-  double* wlo = ring + (ring_rows + mirror_rows) * PV_TW;
-  double* whi = wlo + (r_lo + 1);
+// A warp's 32 (lanes) x R (outputs per thread) tile leaves TRANSPOSED: out[col][row .. row+R).
+// Written straight from the accumulators, every store instruction would touch 32 different
+// 128-byte lines (16 bytes of each) and the LSU spends one cycle per line: ncu showed those
+// stores holding their source registers (and the scoreboards the next loads share) for ~2000
+// cycles per step.  Staged through a per-warp shared-memory tile (pitch R+2 doubles:
+// conflict-free 16-byte writes), R/2 lanes cover one column's whole R-output run, so an
+// instruction touches 64/R lines instead of 32 and needs no CTA barrier, only __syncwarp.
+template <int R>
+__device__ __forceinline__ void store_transposed(double* __restrict__ sw, const double (&v)[R], double* __restrict__ dst,
+                                                 const int n, const int lane, const bool live) {
+  constexpr int P = R + 2;     // stage pitch (doubles)
+  constexpr int LPR = R / 2;   // lanes per column run
+  constexpr int CPI = 32 / LPR;  // columns per store instruction
+#pragma unroll
+  for (int o = 0; o < R; o += 2) *reinterpret_cast<double2*>(sw + lane * P + o) = make_double2(v[o], v[o + 1]);
+  __syncwarp();
+  const int c = lane / LPR, q = 2 * (lane % LPR);
+#pragma unroll
+  for (int i = 0; i < LPR; ++i) {
+    const double2 t = *reinterpret_cast<const double2*>(sw + (i * CPI + c) * P + q);
+    if (live) *reinterpret_cast<double2*>(dst + (int64_t)(i * CPI + c) * n + q) = t;
+  }
+  __syncwarp();
+}
+
+// The wide filter over a wrap-around ring of N rows (row pitch 32 doubles, `ring0` already offset
+// by the lane): acc[o], o < R, centred at ring row c + o; r % R == 0, c % R == 0, N % R == 0.
+// Same arithmetic and register-window scheme as conv_exact (conv.cuh); the left / right sample
+// pointers advance by R rows per unrolled iteration and wrap there, so inside an iteration every
+// access is pointer + constant.  Rows [N, N+R) of the ring mirror rows [0, R).
+template <int R>
+__device__ __forceinline__ void conv_ring(const double* __restrict__ ring0, const int N, const int c,
+                                          const double* __restrict__ hw, const int r, double (&acc)[R]) {
+  double L[R], Rt[R];
+  {
+    const double* pc = ring0 + c * PV_TW;
+    const double w0 = hw[0];
+#pragma unroll
+    for (int o = 0; o < R; ++o) acc[o] = dmul(pc[o * PV_TW], w0);
+  }
+  int rl = c - r, rr = c + r - R;
+  rl = rl < 0 ? rl + N : rl;
+  rr = rr >= N ? rr - N : rr;
+  const double* pL = ring0 + rl * PV_TW;  // sample (-j) of output 0
+  const double* pR = ring0 + rr * PV_TW;  // sample (+j - R) of output 0
+  const double* const ring_end = ring0 + N * PV_TW;
+#pragma unroll
+  for (int o = 0; o < R; ++o) {
+    L[o] = pL[o * PV_TW];
+    Rt[o] = pR[(R + o) * PV_TW];
+  }
+  double wj = hw[r];
+  for (int j = r; j >= R; j -= R) {
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      double t[R];
+#pragma unroll
+      for (int o = 0; o < R; ++o) t[o] = dadd(L[(o + u) % R], Rt[(o - u + R) % R]);
+      // the two window slots that just became dead take the next step's samples right away
+      L[u] = pL[(R + u) * PV_TW];
+      Rt[R - 1 - u] = pR[(R - 1 - u) * PV_TW];
+      const double wn = hw[j - u - 1];
+#pragma unroll
+      for (int o = 0; o < R; ++o) t[o] = dmul(t[o], wj);
+#pragma unroll
+      for (int o = 0; o < R; ++o) acc[o] = dadd(acc[o], t[o]);
+      wj = wn;
+    }
+    pL += R * PV_TW;
+    pL = pL == ring_end ? ring0 : pL;
+    pR = pR == ring0 ? ring_end : pR;
+    pR -= R * PV_TW;
+  }
+}
+
+// grid (inner/32, planes); block (32, WARPS).  n = length of the filter axis, inner = length of
+// the contiguous axis (multiple of 32), input plane layout [n][inner], output [inner][n].
+// FIRST pass : in = image (InT), out_a = G_hi^T, out_b = G_lo^T
+// SECOND pass: in = G_hi^T (double), in_lo = G_lo^T, out_a = G_lo - G_hi in image layout
+// Ring: N = (nb+1)*S rows; block b (S rows) holds samples y = b*S - r_hi + [0, S), clamped
+// (mode='nearest'), in slot b % (nb+1).  Rows [N, N+R) mirror [0, R) and rows [-4, 0) mirror
+// [N-4, N), so that aligned 2R-row runs and the narrow filter's R+8-row runs never wrap.
+template <int R, int WARPS, int MIN_CTAS, typename InT, bool SECOND>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
+dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, const double scale,
+                 double* __restrict__ out_a, double* __restrict__ out_b, const int n, const int inner,
+                 const double* __restrict__ hw_lo, const int r_lo, const double* __restrict__ hw_hi, const int r_hi,
+                 const int nb, uint64_t* __restrict__ minmax) {
+  constexpr int S = WARPS * R;  // rows per step
+  constexpr int NT = WARPS * 32;
+  constexpr int FRONT = RLO_MAX, BACK = R;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ uint64_t s_mm[2 * WARPS];
+  const int m = nb + 1;
+  const int N = m * S;
+  double* ring = smem + FRONT * PV_TW;  // row 0
+  double* whi = ring + (size_t)(N + BACK) * PV_TW;
+  double* wlo = whi + ((r_hi + 2) & ~1);
+  double* stage = wlo + ((r_lo + 2) & ~1) + (size_t)threadIdx.y * (PV_TW * (R + 2));  // this warp's store tile
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * PV_TW + tx;
-  for (int i = tid; i <= r_lo; i += 256) wlo[i] = hw_lo[i];
-  for (int i = tid; i <= r_hi; i += 256) whi[i] = hw_hi[i];
+  for (int i = tid; i <= r_hi; i += NT) whi[i] = hw_hi[i];
+  for (int i = tid; i <= r_lo; i += NT) wlo[i] = hw_lo[i];
 
-  const int mask = ring_rows - 1;
-  auto ring_store = [&](int s, double v) {
-    const int p = s & mask;
-    ring[p * PV_TW + tx] = v;
-    if (p < mirror_rows) ring[(p + ring_rows) * PV_TW + tx] = v;
+  const int x0 = blockIdx.x * PV_TW;
+  const int64_t plane = (int64_t)blockIdx.y * n * inner;
+  const InT* src = in + plane + x0;
+
+  // ---- ring fill
+  constexpr bool U16 = sizeof(InT) == 2;
+  constexpr int ITEMS = U16 ? R / 4 : R / 2;  // per thread and block: 4 uint16 or 2 doubles each
+  constexpr int TPR = U16 ? 8 : 16;           // threads per row
+  constexpr int NRAW = U16 ? ITEMS : 1;
+  const int fill_row = tid / TPR, fill_col = (U16 ? 4 : 2) * (tid % TPR);
+  // b = logical block, pb = its ring slot (b % m, tracked by the caller: no runtime modulo)
+  auto fetch_block = [&](int b, int pb, uint2 (&raw)[NRAW]) {  // global -> registers (uint16) or -> ring (float64, async)
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int rb = it * (NT / TPR) + fill_row;
+      int y = b * S + rb - r_hi;
+      y = y < 0 ? 0 : (y > n - 1 ? n - 1 : y);
+      if constexpr (U16) {
+        raw[it] = __ldg(reinterpret_cast<const uint2*>(src + y * inner + fill_col));
+      } else {
+        const int prow = pb * S + rb;
+        const double* g = reinterpret_cast<const double*>(src) + y * inner + fill_col;
+        double* d = ring + prow * PV_TW + fill_col;
+        cp_async16(d, g);
+        if (prow < BACK) cp_async16(d + N * PV_TW, g);
+        if (prow >= N - FRONT) cp_async16(d - N * PV_TW, g);
+      }
+    }
   };
-  const int x = blockIdx.x * PV_TW + tx;
-  const bool xok = x < inner;
-  const int y_begin = blockIdx.y * SEG;
-  const int y_end = (y_begin + SEG < n) ? y_begin + SEG : n;
-  const int64_t plane = (int64_t)blockIdx.z * n * inner;
-  const InT* src = in + plane + (xok ? x : 0);
-  const int base = y_begin - rmax;  // sample index of ring row 0
-  const int pro_rows = PV_TH + 2 * rmax;
+  auto commit_block = [&](int pb, const uint2 (&raw)[NRAW]) {  // registers -> ring (uint16 only)
+    if constexpr (U16) {
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const int prow = pb * S + it * (NT / TPR) + fill_row;
+        const double2 v01 = make_double2(dmul((double)(raw[it].x & 0xffffu), scale), dmul((double)(raw[it].x >> 16), scale));
+        const double2 v23 = make_double2(dmul((double)(raw[it].y & 0xffffu), scale), dmul((double)(raw[it].y >> 16), scale));
+        double* d = ring + prow * PV_TW + fill_col;
+        *reinterpret_cast<double2*>(d) = v01;
+        *reinterpret_cast<double2*>(d + 2) = v23;
+        if (prow < BACK) {
+          *reinterpret_cast<double2*>(d + N * PV_TW) = v01;
+          *reinterpret_cast<double2*>(d + N * PV_TW + 2) = v23;
+        }
+        if (prow >= N - FRONT) {
+          *reinterpret_cast<double2*>(d - N * PV_TW) = v01;
+          *reinterpret_cast<double2*>(d - N * PV_TW + 2) = v23;
+        }
+      }
+    }
+  };
 
-  for (int s0 = 0; s0 < pro_rows; s0 += 64) {  // prologue: 8 rows per thread in flight
-    InT raw[8];
+  for (int b0 = 0; b0 < nb; b0 += 3) {  // prologue: the window of step 0, three blocks in flight
+    uint2 pro[3][NRAW];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      int y = base + s0 + ty + 8 * m;
-      y = y < 0 ? 0 : (y > n - 1 ? n - 1 : y);  // mode='nearest'
-      raw[m] = __ldg(src + (int64_t)y * inner);
-    }
+    for (int i = 0; i < 3; ++i)
+      if (b0 + i < nb) fetch_block(b0 + i, b0 + i, pro[i]);
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const int s = s0 + ty + 8 * m;
-      if (s < pro_rows) ring_store(s, convert_to_f64<InT>(raw[m], scale));
-    }
+    for (int i = 0; i < 3; ++i)
+      if (b0 + i < nb) commit_block(b0 + i, pro[i]);
   }
+  if constexpr (!U16) cp_async_wait_all();
   __syncthreads();
 
   uint64_t kmin = ~0ull, kmax = 0ull;
-  const int n_steps = (y_end - y_begin + PV_TH - 1) / PV_TH;
+  const int n_steps = (n + S - 1) / S;
+  const int64_t out_col = plane + (int64_t)x0 * n;  // transposed output: [col][row]
+  const double* ring_lane = ring + tx;
+  int pk = 0;  // k % m
   for (int k = 0; k < n_steps; ++k) {
     const bool more = k + 1 < n_steps;
-    InT pre[8];
-    if (more) {
+    uint2 raw[NRAW];
+    const int pf = pk == 0 ? m - 1 : pk - 1;  // (k + nb) % m: the slot of block k-1, free since the last barrier
+    if (more) fetch_block(k + nb, pf, raw);
+    const int yb = k * S + ty * R;
+    const bool live = yb < n;  // n % 32 == 0 and R | 32: a thread's run is all in or all out
+
+    double xs[R + 2 * RLO_MAX];
+    if constexpr (SECOND) {  // narrow operand straight from global memory (L2), in flight during the hi filter
+      const double* lo_col = in_lo + plane + x0 + tx;
+      if (yb >= RLO_MAX && yb + R + RLO_MAX <= n) {  // interior: one base, constant strides
+        const double* p = lo_col + (yb - RLO_MAX) * inner;
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        int y = base + pro_rows + k * PV_TH + ty + 8 * m;
-        y = y > n - 1 ? n - 1 : y;
-        pre[m] = __ldg(src + (int64_t)y * inner);
+        for (int i = 0; i < R + 2 * RLO_MAX; ++i) xs[i] = __ldg(p + i * inner);
+      } else {
+#pragma unroll
+        for (int i = 0; i < R + 2 * RLO_MAX; ++i) {
+          int y = yb + i - RLO_MAX;
+          y = y < 0 ? 0 : (y > n - 1 ? n - 1 : y);
+          xs[i] = __ldg(lo_col + y * inner);
+        }
       }
     }
-    // the step's window starts at a multiple of 64 inside the ring and runs on into the mirror
-    // rows, so every access of the unrolled loop is col + constant
-    const double* col = ring + (((k * PV_TH) & mask) + rmax + ty * GR) * PV_TW + tx;
-    const int yb = y_begin + k * PV_TH + ty * GR;
-    double acc[GR];
-    conv_exact<GR>([&](int kk) -> double { return col[kk * PV_TW]; }, whi, r_hi, acc);
-    double* dst_a = out_a + plane + (int64_t)x * n + yb;  // transposed: 8 contiguous outputs
-    if (!SECOND) {
-      // pass 1 keeps the image layout: one coalesced 256-byte row segment per store
-      if (xok) {
+
+    int c = pk * S + r_hi + ty * R;  // ring row of this thread's output 0 (sample y sits at ring row y + r_hi)
+    c = c >= N ? c - N : c;
+    double acc[R];
+    conv_ring<R>(ring_lane, N, c, whi, r_hi, acc);
+    if constexpr (!SECOND) {
+      store_transposed<R>(stage, acc, out_a + out_col + yb, n, tx, live);
+      const double* col = ring_lane + c * PV_TW;
 #pragma unroll
-        for (int o = 0; o < GR; ++o)
-          if (yb + o < y_end) out_a[plane + (int64_t)(yb + o) * inner + x] = acc[o];
-      }
-      conv_exact<GR>([&](int kk) -> double { return col[kk * PV_TW]; }, wlo, r_lo, acc);
-      if (xok) {
-#pragma unroll
-        for (int o = 0; o < GR; ++o)
-          if (yb + o < y_end) out_b[plane + (int64_t)(yb + o) * inner + x] = acc[o];
-      }
+      for (int i = 0; i < R + 2 * RLO_MAX; ++i) xs[i] = col[(i - RLO_MAX) * PV_TW];  // front / back mirrors: never wraps
+      conv_small<R>(xs, wlo, r_lo, acc);
+      store_transposed<R>(stage, acc, out_b + out_col + yb, n, tx, live);
     } else {
-      // narrow operand: 2*r_lo + 8 samples per thread, straight from global memory (L1)
-      const double* lo_col = in_lo + plane + (xok ? x : 0);
-      double acc_lo[GR];
-      conv_exact<GR>(
-          [&](int kk) -> double {
-            int y = yb + kk;
-            y = y < 0 ? 0 : (y > n - 1 ? n - 1 : y);
-            return __ldg(lo_col + (int64_t)y * inner);
-          },
-          wlo, r_lo, acc_lo);
+      double acc_lo[R];
+      conv_small<R>(xs, wlo, r_lo, acc_lo);
 #pragma unroll
-      for (int o = 0; o < GR; ++o) acc[o] = dsub(acc_lo[o], acc[o]);
-      if (xok) {
-        store_run<GR>(dst_a, acc, yb, y_end, vec2);
+      for (int o = 0; o < R; ++o) acc[o] = dsub(acc_lo[o], acc[o]);
+      store_transposed<R>(stage, acc, out_a + out_col + yb, n, tx, live);
+      if (live) {
         if (minmax != nullptr) {
 #pragma unroll
-          for (int o = 0; o < GR; ++o) {
-            if (yb + o < y_end) {
-              const uint64_t key = f64_to_key(acc[o]);
-              kmin = key < kmin ? key : kmin;
-              kmax = key > kmax ? key : kmax;
-            }
+          for (int o = 0; o < R; ++o) {
+            const uint64_t key = f64_to_key(acc[o]);
+            kmin = key < kmin ? key : kmin;
+            kmax = key > kmax ? key : kmax;
           }
         }
       }
     }
     if (more) {
-      __syncthreads();  // every warp is done with the oldest 64 rows
-#pragma unroll
-      for (int m = 0; m < 8; ++m) ring_store(pro_rows + k * PV_TH + ty + 8 * m, convert_to_f64<InT>(pre[m], scale));
+      commit_block(pf, raw);
+      if constexpr (!U16) cp_async_wait_all();
       __syncthreads();
     }
+    pk = (pk + 1 == m) ? 0 : pk + 1;
   }
   if (SECOND && minmax != nullptr) {
     kmin = warp_min_u64(kmin);
     kmax = warp_max_u64(kmax);
     if (tx == 0) {
       s_mm[ty] = kmin;
-      s_mm[8 + ty] = kmax;
+      s_mm[WARPS + ty] = kmax;
     }
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
-      for (int i = 1; i < 8; ++i) {
+      for (int i = 1; i < WARPS; ++i) {
         kmin = s_mm[i] < kmin ? s_mm[i] : kmin;
-        kmax = s_mm[8 + i] > kmax ? s_mm[8 + i] : kmax;
+        kmax = s_mm[WARPS + i] > kmax ? s_mm[WARPS + i] : kmax;
       }
-      atomicMin((unsigned long long*)&minmax[2 * blockIdx.z], (unsigned long long)kmin);
-      atomicMax((unsigned long long*)&minmax[2 * blockIdx.z + 1], (unsigned long long)kmax);
+      atomicMin((unsigned long long*)&minmax[2 * blockIdx.y], (unsigned long long)kmin);
+      atomicMax((unsigned long long*)&minmax[2 * blockIdx.y + 1], (unsigned long long)kmax);
     }
   }
 }
 
-static int pow2_at_least(int v) {
-  int p = 64;
-  while (p < v) p <<= 1;
-  return p;
-}
-
 int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st);  // gauss.cu
+
+// ---- tuning knobs (amt_tune).  dog_variant: 0 = 4 warps x 8 outputs per thread (3 CTAs / SM fit),
+// 1 = 4 warps x 16 (2 CTAs), 2 = 8 warps x 8 (2 CTAs).  dog_ctas: resident CTAs per SM (0 = as
+// many as fit; otherwise the shared-memory request is padded so that no more than that many fit,
+// which leaves the rest of the SM to the HBM-bound kernels of the other stream).
+static int g_dog_variant = 0;
+static int g_dog_ctas = 0;
+static int g_dog_generic = 0;
+
+constexpr size_t kSmemMax = 227 * 1024;
+constexpr size_t kSmemPerSM = 228 * 1024;
 
 struct DogPlan {
   bool fast;
-  int ring1, ring2;
-  size_t smem1, smem2;
+  int R, warps, nb;
+  size_t smem;
 };
 
+static bool aligned16(const void* q) { return ((uintptr_t)q) % 16 == 0; }
+
 static DogPlan dog_plan(int in_dtype, int64_t n_img, int64_t h, int64_t w, int r_lo, int r_hi) {
-  DogPlan p;
-  const int rmax = r_lo > r_hi ? r_lo : r_hi;
-  p.ring1 = pow2_at_least(PV_TH + 2 * rmax);
-  p.ring2 = pow2_at_least(PV_TH + 2 * r_hi);
-  const size_t wbytes = (size_t)((r_lo + 1) + (r_hi + 1)) * sizeof(double);
-  p.smem1 = (size_t)(p.ring1 + 2 * rmax) * PV_TW * sizeof(double) + wbytes;
-  p.smem2 = (size_t)(p.ring2 + 2 * r_hi) * PV_TW * sizeof(double) + wbytes;
-  p.fast = p.smem1 <= kSmemMax && p.smem2 <= kSmemMax && n_img <= 65535 && ceil_div(h, SEG) <= 65535 &&
-           ceil_div(w, SEG) <= 65535 && h * w < (1ll << 31) && (in_dtype == AMT_U16 || in_dtype == AMT_F64);
+  DogPlan p{};
+  p.R = g_dog_variant == 1 ? 16 : 8;
+  p.warps = g_dog_variant == 2 ? 8 : 4;
+  const int S = p.R * p.warps;
+  p.nb = 1 + (2 * r_hi + S - 1) / S;
+  const size_t rows = (size_t)(p.nb + 1) * S + RLO_MAX + p.R;
+  p.smem = (rows * PV_TW + ((r_hi + 2) & ~1) + ((r_lo + 2) & ~1) + (size_t)p.warps * PV_TW * (p.R + 2)) * sizeof(double);
+  if (g_dog_ctas > 0) {  // no more than g_dog_ctas CTAs per SM (each CTA also reserves 1 KB)
+    const size_t pad = kSmemPerSM / (g_dog_ctas + 1) + 1 - 1024;
+    if (p.smem < pad && pad <= kSmemMax) p.smem = pad;
+  }
+  p.fast = !g_dog_generic && p.smem <= kSmemMax && n_img <= 65535 && h % 32 == 0 && w % 32 == 0 &&
+           h * w < (1ll << 31) && r_lo <= RLO_MAX && r_hi >= r_lo && r_hi >= p.R && r_hi % p.R == 0 &&
+           (in_dtype == AMT_U16 || in_dtype == AMT_F64);
   return p;
 }
 
-// pass 1: image (h x w) -> tmp_hi, tmp_lo (same layout)
-static int dog_axis0(const void* in, int in_dtype, double in_scale, int64_t n_img, int64_t h, int64_t w,
-                     const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, double* tmp_lo, double* tmp_hi,
-                     cudaStream_t st) {
-  const DogPlan p = dog_plan(in_dtype, n_img, h, w, r_lo, r_hi);
-  if (!p.fast) return dog_axis0_generic(in, in_dtype, in_scale, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, tmp_lo, tmp_hi, st);
-  const int vec2 = (h % 2 == 0) && (((uintptr_t)tmp_lo) % 16 == 0) && (((uintptr_t)tmp_hi) % 16 == 0);
-  dim3 grid((unsigned)ceil_div(w, PV_TW), (unsigned)ceil_div(h, SEG), (unsigned)n_img), block(PV_TW, 8);
-  if (in_dtype == AMT_U16) {
-    AMT_CUDA_TRY(cudaFuncSetAttribute(dog_pass_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)p.smem1));
-    dog_pass_kernel<uint16_t, false><<<grid, block, p.smem1, st>>>((const uint16_t*)in, nullptr, in_scale, tmp_hi, tmp_lo,
-                                                                   (int)h, (int)w, hw_lo, r_lo, hw_hi, r_hi, p.ring1,
-                                                                   nullptr, vec2);
-  } else {
-    AMT_CUDA_TRY(cudaFuncSetAttribute(dog_pass_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)p.smem1));
-    dog_pass_kernel<double, false><<<grid, block, p.smem1, st>>>((const double*)in, nullptr, 1.0, tmp_hi, tmp_lo, (int)h,
-                                                                 (int)w, hw_lo, r_lo, hw_hi, r_hi, p.ring1, nullptr, vec2);
-  }
+template <int R, int WARPS, int MIN_CTAS, typename InT, bool SECOND>
+static int launch_strip(const DogPlan& p, const InT* in, const double* in_lo, double scale, double* out_a, double* out_b,
+                        int64_t planes, int64_t n, int64_t inner, const double* hw_lo, int r_lo, const double* hw_hi,
+                        int r_hi, uint64_t* minmax, cudaStream_t st) {
+  auto kernel = dog_strip_kernel<R, WARPS, MIN_CTAS, InT, SECOND>;
+  AMT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  dim3 grid((unsigned)(inner / PV_TW), (unsigned)planes), block(PV_TW, WARPS);
+  kernel<<<grid, block, p.smem, st>>>(in, in_lo, scale, out_a, out_b, (int)n, (int)inner, hw_lo, r_lo, hw_hi, r_hi, p.nb,
+                                      minmax);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
 
-// pass 2: image-layout planes filtered along axis 1 by the tile kernel of gauss.cu (loads are
-// transposed through shared memory, lo - hi leaves through a staged, coalesced store)
-static int dog_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int64_t n_img, int64_t h, int64_t w,
-                     const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, uint64_t* minmax, cudaStream_t st) {
-  return dog_axis1_generic(tmp_lo, tmp_hi, out, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, minmax, st);
+template <typename InT, bool SECOND>
+static int launch_variant(const DogPlan& p, const InT* in, const double* in_lo, double scale, double* out_a,
+                          double* out_b, int64_t planes, int64_t n, int64_t inner, const double* hw_lo, int r_lo,
+                          const double* hw_hi, int r_hi, uint64_t* minmax, cudaStream_t st) {
+  if (p.R == 16)
+    return launch_strip<16, 4, 2, InT, SECOND>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
+                                                r_hi, minmax, st);
+  if (p.warps == 8)
+    return launch_strip<8, 8, 2, InT, SECOND>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
+                                               r_hi, minmax, st);
+  return launch_strip<8, 4, 3, InT, SECOND>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi, r_hi,
+                                             minmax, st);
+}
+
+// pass 1: image (h x w) -> tmp_hi, tmp_lo.  Fast path: both TRANSPOSED (w x h); generic: image layout.
+static int dog_axis0(const DogPlan& p, const void* in, int in_dtype, double in_scale, int64_t n_img, int64_t h,
+                     int64_t w, const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, double* tmp_lo,
+                     double* tmp_hi, cudaStream_t st) {
+  if (!p.fast) return dog_axis0_generic(in, in_dtype, in_scale, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, tmp_lo, tmp_hi, st);
+  if (in_dtype == AMT_U16)
+    return launch_variant<uint16_t, false>(p, (const uint16_t*)in, nullptr, in_scale, tmp_hi, tmp_lo, n_img, h, w,
+                                           hw_lo, r_lo, hw_hi, r_hi, nullptr, st);
+  return launch_variant<double, false>(p, (const double*)in, nullptr, 1.0, tmp_hi, tmp_lo, n_img, h, w, hw_lo, r_lo,
+                                       hw_hi, r_hi, nullptr, st);
+}
+
+// pass 2.  Fast path: the transposed planes (w x h) filtered along their axis 0, lo - hi written back
+// transposed (= image layout); generic: image-layout planes through the tile kernel of gauss.cu.
+static int dog_axis1(const DogPlan& p, const double* tmp_lo, const double* tmp_hi, double* out, int64_t n_img,
+                     int64_t h, int64_t w, const double* hw_lo, int r_lo, const double* hw_hi, int r_hi,
+                     uint64_t* minmax, cudaStream_t st) {
+  if (!p.fast) return dog_axis1_generic(tmp_lo, tmp_hi, out, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, minmax, st);
+  return launch_variant<double, true>(p, tmp_hi, tmp_lo, 1.0, out, nullptr, n_img, w, h, hw_lo, r_lo, hw_hi, r_hi,
+                                      minmax, st);
 }
 
 int dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,
@@ -249,13 +413,34 @@ int dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_
   if (n_img <= 0 || h <= 0 || w <= 0 || r_lo < 0 || r_hi < 0) return AMT_ERR_INVALID;
   if (in_dtype != AMT_U16 && in_dtype != AMT_F64) return AMT_ERR_UNSUPPORTED;
   if (minmax) AMT_TRY(minmax_init(minmax, n_img, st));
-  AMT_TRY(dog_axis0(in, in_dtype, in_scale, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, tmp_lo, tmp_hi, st));
-  return dog_axis1(tmp_lo, tmp_hi, out, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, minmax, st);
+  DogPlan p = dog_plan(in_dtype, n_img, h, w, r_lo, r_hi);
+  // the strip kernels use 16-byte accesses; odd pointers take the generic tile kernels for BOTH passes
+  p.fast = p.fast && aligned16(in) && aligned16(out) && aligned16(tmp_lo) && aligned16(tmp_hi);
+  AMT_TRY(dog_axis0(p, in, in_dtype, in_scale, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, tmp_lo, tmp_hi, st));
+  return dog_axis1(p, tmp_lo, tmp_hi, out, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, minmax, st);
 }
 
 }  // namespace amt
 
 extern "C" {
+
+int amt_tune(const char* key, int value) {
+  using namespace amt;
+  if (!key) return AMT_ERR_INVALID;
+  const auto is = [&](const char* k) { return std::strcmp(key, k) == 0; };
+  if (is("dog_variant")) {
+    if (value < 0 || value > 2) return AMT_ERR_INVALID;
+    g_dog_variant = value;
+  } else if (is("dog_ctas")) {
+    if (value < 0 || value > 8) return AMT_ERR_INVALID;
+    g_dog_ctas = value;
+  } else if (is("dog_generic")) {
+    g_dog_generic = value != 0;
+  } else {
+    return AMT_ERR_INVALID;
+  }
+  return AMT_OK;
+}
 
 int amt_dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,
               const double* half_w_lo, int r_lo, const double* half_w_hi, int r_hi, double* tmp_lo, double* tmp_hi,
@@ -264,13 +449,17 @@ int amt_dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_
                     minmax_keys, amt::as_stream(stream));
 }
 
+// The two passes separately (bench / profiling).  The layout of tmp_lo / tmp_hi between them is
+// private to the library: call both with the same arguments.
 int amt_dog2d_axis0(const void* in, int in_dtype, double in_scale, int64_t n_img, int64_t h, int64_t w,
                     const double* half_w_lo, int r_lo, const double* half_w_hi, int r_hi, double* tmp_lo, double* tmp_hi,
                     amt_stream_t stream) {
   using namespace amt;
   if (!in || !tmp_lo || !tmp_hi || !half_w_lo || !half_w_hi || n_img <= 0 || h <= 0 || w <= 0) return AMT_ERR_INVALID;
   if (in_dtype != AMT_U16 && in_dtype != AMT_F64) return AMT_ERR_UNSUPPORTED;
-  return dog_axis0(in, in_dtype, in_scale, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, tmp_lo, tmp_hi,
+  const DogPlan p = dog_plan(in_dtype, n_img, h, w, r_lo, r_hi);
+  if (p.fast && !(aligned16(in) && aligned16(tmp_lo) && aligned16(tmp_hi))) return AMT_ERR_INVALID;
+  return dog_axis0(p, in, in_dtype, in_scale, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, tmp_lo, tmp_hi,
                    as_stream(stream));
 }
 
@@ -279,8 +468,11 @@ int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int
                     amt_stream_t stream) {
   using namespace amt;
   if (!tmp_lo || !tmp_hi || !out || !half_w_lo || !half_w_hi || n_img <= 0 || h <= 0 || w <= 0) return AMT_ERR_INVALID;
+  const DogPlan p = dog_plan(AMT_U16, n_img, h, w, r_lo, r_hi);  // the dtype of pass 1's input does not matter here
+  if (p.fast && !(aligned16(out) && aligned16(tmp_lo) && aligned16(tmp_hi))) return AMT_ERR_INVALID;
   if (minmax_keys) AMT_TRY(minmax_init(minmax_keys, n_img, as_stream(stream)));
-  return dog_axis1(tmp_lo, tmp_hi, out, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, minmax_keys, as_stream(stream));
+  return dog_axis1(p, tmp_lo, tmp_hi, out, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, minmax_keys,
+                   as_stream(stream));
 }
 
 }  // extern "C"

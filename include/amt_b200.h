@@ -83,13 +83,21 @@ int amt_dog2d(const void* in, int in_dtype, double in_scale, double* out,
 
 /* The two kernels of amt_dog2d, callable on their own (per-kernel timing, custom staging):
  * axis 0 pass of both filters (input -> tmp_lo, tmp_hi), then axis 1 pass + subtraction
- * (+ min/max keys). */
+ * (+ min/max keys).  The layout of tmp_lo / tmp_hi between the two calls is private to the
+ * library (transposed planes on the fast path): call both with the same shapes and radii. */
 int amt_dog2d_axis0(const void* in, int in_dtype, double in_scale, int64_t n_img, int64_t h, int64_t w,
                     const double* half_w_lo, int r_lo, const double* half_w_hi, int r_hi,
                     double* tmp_lo, double* tmp_hi, amt_stream_t stream);
 int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int64_t n_img, int64_t h, int64_t w,
                     const double* half_w_lo, int r_lo, const double* half_w_hi, int r_hi,
                     uint64_t* minmax_keys, amt_stream_t stream);
+
+/* Tuning knobs (process-wide; set before launching work; bench / profiling only — defaults are
+ * the shipped configuration).  Keys: "dog_variant" 0 = 8 warps x 8 outputs per thread,
+ * 1 = 4 warps x 16, 2 = 8 warps x 16; "dog_solo" 1 = one DoG CTA per SM (leaves half of the SM
+ * to the HBM-bound kernels of the other stream), 0 = as many as fit; "dog_generic" 1 = force
+ * the generic tile kernels. */
+int amt_tune(const char* key, int value);
 
 /* out = a - b elementwise (N-D DoG fallback: two full Gaussians then subtract). */
 int amt_sub_f64(const double* a, const double* b, double* out, int64_t n, amt_stream_t stream);
