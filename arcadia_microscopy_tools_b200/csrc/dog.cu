@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, const double scale,
                  double* __restrict__ out_a, double* __restrict__ out_b, const int n, const int inner,
                  const double* __restrict__ hw_lo, const int r_lo, const double* __restrict__ hw_hi, const int r_hi,
-                 const int nb, uint64_t* __restrict__ minmax) {
+                 const int nb, uint64_t* __restrict__ minmax, const int n_items) {
   constexpr int S = WARPS * R;  // rows per step
   constexpr int NT = WARPS * 32;
   constexpr int FRONT = RLO_MAX, BACK = R;
@@ -170,9 +170,14 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
   for (int i = tid; i <= r_hi; i += NT) whi[i] = hw_hi[i];
   for (int i = tid; i <= r_lo; i += NT) wlo[i] = hw_lo[i];
 
-  const int x0 = blockIdx.x * PV_TW;
-  const int64_t plane = (int64_t)blockIdx.y * n * inner;
+  // item = plane * (inner/32) + strip; one item per CTA unless the launch is persistent (round robin)
+  const int strips = inner / PV_TW;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int plane_idx = item / strips;
+  const int x0 = (item - plane_idx * strips) * PV_TW;
+  const int64_t plane = (int64_t)plane_idx * n * inner;
   const InT* src = in + plane + x0;
+  if (item != (int)blockIdx.x) __syncthreads();  // the previous strip's last step is done with the ring
 
   // ---- ring fill
   constexpr bool U16 = sizeof(InT) == 2;
@@ -312,10 +317,11 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
         kmin = s_mm[i] < kmin ? s_mm[i] : kmin;
         kmax = s_mm[WARPS + i] > kmax ? s_mm[WARPS + i] : kmax;
       }
-      atomicMin((unsigned long long*)&minmax[2 * blockIdx.y], (unsigned long long)kmin);
-      atomicMax((unsigned long long*)&minmax[2 * blockIdx.y + 1], (unsigned long long)kmax);
+      atomicMin((unsigned long long*)&minmax[2 * plane_idx], (unsigned long long)kmin);
+      atomicMax((unsigned long long*)&minmax[2 * plane_idx + 1], (unsigned long long)kmax);
     }
   }
+  }  // item loop
 }
 
 int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st);  // gauss.cu
@@ -324,16 +330,19 @@ int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st);  // gauss.cu
 // 1 = 4 warps x 16 (2 CTAs), 2 = 8 warps x 8 (2 CTAs).  dog_ctas: resident CTAs per SM (0 = as
 // many as fit; otherwise the shared-memory request is padded so that no more than that many fit,
 // which leaves the rest of the SM to the HBM-bound kernels of the other stream).
-static int g_dog_variant = 0;
+static int g_dog_variant = 1;
 static int g_dog_ctas = 0;
+static int g_dog_persistent = 0;
 static int g_dog_generic = 0;
+extern int g_stream_ctas;     // gauss.cu
+extern int g_exec_swap_prio;  // executor.cu
 
 constexpr size_t kSmemMax = 227 * 1024;
 constexpr size_t kSmemPerSM = 228 * 1024;
 
 struct DogPlan {
   bool fast;
-  int R, warps, nb;
+  int R, warps, nb, ctas;
   size_t smem;
 };
 
@@ -347,11 +356,17 @@ static DogPlan dog_plan(int in_dtype, int64_t n_img, int64_t h, int64_t w, int r
   p.nb = 1 + (2 * r_hi + S - 1) / S;
   const size_t rows = (size_t)(p.nb + 1) * S + RLO_MAX + p.R;
   p.smem = (rows * PV_TW + ((r_hi + 2) & ~1) + ((r_lo + 2) & ~1) + (size_t)p.warps * PV_TW * (p.R + 2)) * sizeof(double);
-  if (g_dog_ctas > 0) {  // no more than g_dog_ctas CTAs per SM (each CTA also reserves 1 KB)
-    const size_t pad = kSmemPerSM / (g_dog_ctas + 1) + 1 - 1024;
+  // resident CTAs per SM: what fits (shared memory, and the register budget __launch_bounds__ was given),
+  // capped by the dog_ctas knob
+  const int max_ctas = g_dog_variant == 0 ? 3 : 2;
+  int fit = (int)(kSmemPerSM / (p.smem + 1024));
+  fit = fit > max_ctas ? max_ctas : fit;
+  p.ctas = (g_dog_ctas > 0 && g_dog_ctas < fit) ? g_dog_ctas : fit;
+  if (p.ctas < fit) {  // pad the request so that no more than p.ctas CTAs fit (each CTA also reserves 1 KB)
+    const size_t pad = kSmemPerSM / (p.ctas + 1) + 1 - 1024;
     if (p.smem < pad && pad <= kSmemMax) p.smem = pad;
   }
-  p.fast = !g_dog_generic && p.smem <= kSmemMax && n_img <= 65535 && h % 32 == 0 && w % 32 == 0 &&
+  p.fast = !g_dog_generic && p.smem <= kSmemMax && fit >= 1 && n_img * ((h > w ? h : w) / 32) < (1ll << 31) && h % 32 == 0 && w % 32 == 0 &&
            h * w < (1ll << 31) && r_lo <= RLO_MAX && r_hi >= r_lo && r_hi >= p.R && r_hi % p.R == 0 &&
            (in_dtype == AMT_U16 || in_dtype == AMT_F64);
   return p;
@@ -363,9 +378,13 @@ static int launch_strip(const DogPlan& p, const InT* in, const double* in_lo, do
                         int r_hi, uint64_t* minmax, cudaStream_t st) {
   auto kernel = dog_strip_kernel<R, WARPS, MIN_CTAS, InT, SECOND>;
   AMT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  dim3 grid((unsigned)(inner / PV_TW), (unsigned)planes), block(PV_TW, WARPS);
+  const int64_t items = planes * (inner / PV_TW);
+  // one CTA per strip by default (the hardware scheduler balances the tail better than a static
+  // round robin); dog_persistent = 1 launches exactly the resident CTAs and lets them loop
+  const int64_t resident = g_dog_persistent ? (int64_t)kNumSMs * p.ctas : items;
+  dim3 grid((unsigned)(items < resident ? items : resident)), block(PV_TW, WARPS);
   kernel<<<grid, block, p.smem, st>>>(in, in_lo, scale, out_a, out_b, (int)n, (int)inner, hw_lo, r_lo, hw_hi, r_hi, p.nb,
-                                      minmax);
+                                      minmax, (int)items);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
@@ -431,9 +450,16 @@ int amt_tune(const char* key, int value) {
   if (is("dog_variant")) {
     if (value < 0 || value > 2) return AMT_ERR_INVALID;
     g_dog_variant = value;
+  } else if (is("dog_persistent")) {
+    g_dog_persistent = value != 0;
   } else if (is("dog_ctas")) {
     if (value < 0 || value > 8) return AMT_ERR_INVALID;
     g_dog_ctas = value;
+  } else if (is("stream_ctas")) {
+    if (value < 1 || value > 32) return AMT_ERR_INVALID;
+    g_stream_ctas = value;
+  } else if (is("exec_swap_prio")) {
+    g_exec_swap_prio = value != 0;
   } else if (is("dog_generic")) {
     g_dog_generic = value != 0;
   } else {

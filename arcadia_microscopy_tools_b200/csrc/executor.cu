@@ -12,8 +12,11 @@
 // double-buffers H2D copies, compute and D2H copies on three streams.
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "internal.cuh"
 
@@ -22,8 +25,9 @@ struct amt_executor {
   int r_lo, r_hi;
   int64_t ranks[6];
   double g_bg, g_lo, g_hi;
-  // s_dog runs the FP64-bound DoG of chunk i+1 while s_compute (higher priority, HBM-bound
-  // kernels) finishes chunk i: the two stages stress different units, so they overlap on an SM
+  // s_dog runs the FP64-bound DoG of chunk i+1 while s_compute (higher priority) finishes chunk i.
+  // Measured (AMT_TRACE, scripts/overlap_probe.py): both sides are instruction-issue-bound, so the
+  // overlap only recovers the other kernels' memory stalls (~0.5 ms of a 5.9 ms chunk)
   cudaStream_t s_compute, s_dog, s_in, s_out;
   cudaEvent_t ev_start, ev_stop;
   cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
@@ -53,14 +57,45 @@ struct amt_executor {
   bool host_slots;
   size_t device_bytes;
   float last_ms;
+  // AMT_TRACE=1: an event after every stage of both streams, dumped (ms since the batch start) by
+  // amt_executor_run_device once the batch has finished.  Debugging aid; off by default.
+  bool trace;
+  std::vector<cudaEvent_t>* trace_events;
+  std::vector<const char*>* trace_names;
 };
 
 namespace amt {
+
+// amt_tune "exec_swap_prio": 1 (default) = the stream of the short HBM-bound kernels has the high
+// priority and the long-running DoG CTAs the low one, 0 = the opposite
+int g_exec_swap_prio = 1;
 
 static int dmalloc(amt_executor* ex, void** p, size_t bytes) {
   AMT_CUDA_TRY(cudaMalloc(p, bytes));
   ex->device_bytes += bytes;
   return AMT_OK;
+}
+
+static void trace_mark(amt_executor* ex, cudaStream_t st, const char* name) {
+  if (!ex->trace) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  ex->trace_events->push_back(e);
+  ex->trace_names->push_back(name);
+}
+
+static void trace_dump(amt_executor* ex) {
+  if (!ex->trace) return;
+  cudaDeviceSynchronize();
+  for (size_t i = 0; i < ex->trace_events->size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ex->ev_start, (*ex->trace_events)[i]);
+    std::fprintf(stderr, "amt-trace %9.3f ms  %s\n", ms, (*ex->trace_names)[i]);
+    cudaEventDestroy((*ex->trace_events)[i]);
+  }
+  ex->trace_events->clear();
+  ex->trace_names->clear();
 }
 
 static void rank_pair(int64_t n, double q, int64_t* lo, int64_t* hi, double* gamma) {
@@ -82,9 +117,11 @@ static int enqueue_dog(amt_executor* ex, const uint16_t* in, int g, cudaEvent_t 
   const int64_t planes = (int64_t)g * c.n_channels;
   if (wait_input) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, wait_input, 0));
   if (ex->chunks_issued >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, ex->ev_dog_free[slot], 0));
+  trace_mark(ex, ex->s_dog, "dog: begin");
   AMT_TRY(dog2d(in, AMT_U16, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, ex->hw_lo, ex->r_lo, ex->hw_hi,
                 ex->r_hi, ex->tmp_lo, ex->tmp_hi, ex->mm[slot], ex->s_dog));
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_done[slot], ex->s_dog));
+  trace_mark(ex, ex->s_dog, "dog: end");
   return AMT_OK;
 }
 
@@ -107,29 +144,36 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
 
   // stage A2: order statistics -> plan -> map (+ histogram of the segmentation planes)
   AMT_CUDA_TRY(cudaStreamWaitEvent(st, ex->ev_dog_done[slot], 0));
+  trace_mark(ex, st, "  rest: begin (dog of this chunk done)");
   AMT_TRY(amt_select_f64(dog, planes, HW, ex->ranks, 6, mm, ex->stats, ex->sel_scratch, ex->sel_bytes, st));
+  trace_mark(ex, st, "  rest: select done");
   AMT_TRY(plan_dog_rescale(ex->stats, mm, planes, ex->g_bg, ex->g_lo, ex->g_hi, c.out_lo, c.out_hi, ex->params, st));
   AMT_CUDA_TRY(cudaMemsetAsync(ex->hist256, 0, (size_t)g * 256 * sizeof(uint32_t), st));
   AMT_TRY(map_launch(dog, AMT_F64, pre, planes, HW, ex->params, ex->hist256, C, c.seg_channel, st));
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_free[slot], st));
+  trace_mark(ex, st, "  rest: map done");
   // stage B: Otsu -> threshold + CCL + clear_border
   AMT_TRY(otsu_launch(ex->hist256, 0, ex->params, C, c.seg_channel, nullptr, g, thr, nullptr, 0, st));
   AMT_TRY(label_launch(pre + (int64_t)c.seg_channel * HW, 1, (int64_t)C * HW, thr, 0, g, H, W, 1, lab_thr, cnt_thr,
                        ex->label_scratch, ex->label_bytes, st));
+  trace_mark(ex, st, "  rest: otsu+label(thr) done");
   // stage C: per-cell tables over the raw channels
   AMT_TRY(region_reduce(lab_thr, in, C, (int64_t)C * HW, HW, g, H, W, c.max_labels, ex->acc, st));
   AMT_TRY(region_finalize(ex->acc, cnt_thr, C, g, c.max_labels, tab_thr, st));
   if (c.with_shape)
     AMT_TRY(region_shape(lab_thr, ex->acc, C, cnt_thr, g, H, W, c.max_labels, tab_thr, ex->shape_scratch, ex->shape_bytes, st));
+  trace_mark(ex, st, "  rest: regions(thr) done");
   if (c.quantify_given_mask && given) {
     AMT_TRY(label_launch(given, 2, HW, nullptr, c.max_label_value, g, H, W, 1, lab_given, cnt_given, ex->label_scratch,
                          ex->label_bytes, st));
+    trace_mark(ex, st, "  rest: label(given) done");
     AMT_TRY(region_reduce(lab_given, in, C, (int64_t)C * HW, HW, g, H, W, c.max_labels, ex->acc, st));
     AMT_TRY(region_finalize(ex->acc, cnt_given, C, g, c.max_labels, tab_given, st));
     if (c.with_shape)
       AMT_TRY(region_shape(lab_given, ex->acc, C, cnt_given, g, H, W, c.max_labels, tab_given, ex->shape_scratch,
                            ex->shape_bytes, st));
   }
+  trace_mark(ex, st, "  rest: end");
   ex->chunks_issued += 1;
   return AMT_OK;
 }
@@ -173,6 +217,9 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
   ex->cfg = *cfg;
   ex->r_lo = r_lo;
   ex->r_hi = r_hi;
+  ex->trace = std::getenv("AMT_TRACE") != nullptr;
+  ex->trace_events = new std::vector<cudaEvent_t>();
+  ex->trace_names = new std::vector<const char*>();
   const int C = cfg->n_channels;
   const int64_t HW = (int64_t)cfg->height * cfg->width;
   const int64_t planes = (int64_t)cfg->chunk_fovs * C;
@@ -200,8 +247,8 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
   } while (0)
   int prio_lo = 0, prio_hi = 0;
   EX_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  EX_CUDA(cudaStreamCreateWithPriority(&ex->s_compute, cudaStreamNonBlocking, prio_hi));
-  EX_CUDA(cudaStreamCreateWithPriority(&ex->s_dog, cudaStreamNonBlocking, prio_lo));
+  EX_CUDA(cudaStreamCreateWithPriority(&ex->s_compute, cudaStreamNonBlocking, g_exec_swap_prio ? prio_hi : prio_lo));
+  EX_CUDA(cudaStreamCreateWithPriority(&ex->s_dog, cudaStreamNonBlocking, g_exec_swap_prio ? prio_lo : prio_hi));
   EX_CUDA(cudaStreamCreateWithFlags(&ex->s_in, cudaStreamNonBlocking));
   EX_CUDA(cudaStreamCreateWithFlags(&ex->s_out, cudaStreamNonBlocking));
   EX_CUDA(cudaEventCreate(&ex->ev_start));
@@ -274,6 +321,8 @@ void amt_executor_destroy(amt_executor* ex) {
   if (ex->s_dog) cudaStreamDestroy(ex->s_dog);
   if (ex->s_in) cudaStreamDestroy(ex->s_in);
   if (ex->s_out) cudaStreamDestroy(ex->s_out);
+  delete ex->trace_events;
+  delete ex->trace_names;
   delete ex;
 }
 
@@ -302,6 +351,7 @@ int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_
                           preprocessed ? preprocessed + f0 * C * HW : nullptr));
   }
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_stop, ex->s_compute));
+  trace_dump(ex);
   return AMT_OK;
 }
 

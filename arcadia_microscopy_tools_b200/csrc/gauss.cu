@@ -254,6 +254,7 @@ __global__ void sub_f64_kernel(const double* __restrict__ a, const double* __res
 }
 
 constexpr size_t kMaxSmem = 227 * 1024;
+int g_stream_ctas = 16;  // grid cap (CTAs per SM) of the grid-stride streaming kernels (amt_tune "stream_ctas")
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
@@ -348,7 +349,7 @@ int amt_sub_f64(const double* a, const double* b, double* out, int64_t n, amt_st
   if (!a || !b || !out || n < 0) return AMT_ERR_INVALID;
   if (n == 0) return AMT_OK;
   int64_t blocks = ceil_div(n, 256);
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks > kNumSMs * g_stream_ctas) blocks = kNumSMs * g_stream_ctas;
   sub_f64_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(a, b, out, n);
   AMT_LAUNCH_CHECK();
   return AMT_OK;

@@ -370,7 +370,7 @@ def run_b200(args) -> None:
             "cells_per_fov": {"threshold_mask": float(counts[0].mean()), "given_mask": float(counts[1].mean())},
             "clocks": clocks.summary(),
             "e2e": e2e,
-            "roofline": {"kernel": f"gauss_{'h' if dom == 'axis1' else 'v'}_kernel<dual> ({dom} pass of the DoG, {k['planes']} planes)",
+            "roofline": {"kernel": f"dog_strip_kernel ({dom} pass of the DoG: sigma 0.6 and 16 filters of {k['planes']} planes)",
                          "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
                          "ms_per_launch": dom_ms,
