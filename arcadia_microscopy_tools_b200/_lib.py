@@ -95,6 +95,7 @@ SIGNATURES: dict[str, tuple] = {
     "amt_launch_count": (C.c_uint64, []),
     "amt_fp64_probe": (_i, [_i, _p, C.POINTER(C.c_uint64), _p]),
     "amt_tune": (_i, [C.c_char_p, _i]),
+    "amt_selftest_div": (_i, [_p, _p, _i64, _p, _p]),
     "amt_gaussian_axis": (_i, [_p, _i, _d, _p, _i64, _i64, _i64, _p, _i, _p]),
     "amt_dog2d": (_i, [_p, _i, _d, _p, _i64, _i64, _i64, _p, _i, _p, _i, _p, _p, _p, _p]),
     "amt_dog2d_axis0": (_i, [_p, _i, _d, _i64, _i64, _i64, _p, _i, _p, _i, _p, _p, _p]),

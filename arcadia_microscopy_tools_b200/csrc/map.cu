@@ -46,15 +46,54 @@ __device__ __forceinline__ int map_mode(const amt_map_params& p) {
   return 4;
 }
 
+// Correctly rounded a / b for a plane-constant divisor: y = RN(1/b) once per CTA, then per sample
+//   q = RN(a*y);  r = a - b*q (exact, FMA);  q = RN(q + r*y);  and the same correction once more
+// (Markstein: with a correctly rounded reciprocal and a faithful q the first correction already
+// yields RN(a/b); the second is the safety step the hardware division sequence also takes).
+// 5 DP instructions instead of __ddiv_rn's ~11 DP + ~10 integer/branch instructions per sample.
+// Exact only while nothing under/overflows: `fast` requires 2^-300 <= |b| <= 2^300, and a sample
+// must be 0 or >= 2^-400 in magnitude; anything else takes __ddiv_rn.  tests/test_gpu_ops.py
+// checks the sequence against __ddiv_rn bit for bit (amt_selftest_div).
+struct DivConst {
+  double b, y;
+  bool fast;
+};
+
+__device__ __forceinline__ DivConst make_div_const(double b) {
+  DivConst d;
+  d.b = b;
+  d.y = __drcp_rn(b);
+  const int e = (__double2hiint(b) >> 20) & 0x7ff;
+  d.fast = e >= 1023 - 300 && e <= 1023 + 300;
+  return d;
+}
+
+__device__ __forceinline__ double div_const(double a, const DivConst& d) {
+  // 0 or |a| >= 2^-400: one unsigned compare on the magnitude bits (0 - 1 wraps to the maximum)
+  const unsigned long long mag = (unsigned long long)__double_as_longlong(a) & 0x7fffffffffffffffull;
+  if (!d.fast || mag - 1ull < (((unsigned long long)(1023 - 400)) << 52) - 1ull || mag >= (((unsigned long long)(1023 + 400)) << 52))
+    return ddiv(a, d.b);
+  const double q0 = dmul(a, d.y);
+  double r = __fma_rn(-d.b, q0, a);
+  const double q1 = __fma_rn(r, d.y, q0);
+  r = __fma_rn(-d.b, q1, a);
+  const double q2 = __fma_rn(r, d.y, q1);
+  // a = -0.0: the corrections turn the quotient into +0.0; the sign is always that of a*y
+  return __hiloint2double((__double2hiint(q2) & 0x7fffffff) | (__double2hiint(q0) & 0x80000000), __double2loint(q2));
+}
+
 template <int MODE>
-__device__ __forceinline__ double map_value_mode(double x, const amt_map_params& p, const double den, const double gain) {
+__device__ __forceinline__ double map_value_mode(double x, const amt_map_params& p, const DivConst& den, const double gain) {
   if (MODE == 0) return p.o1;
   if (MODE == 4) return map_value(x, p);
   double y = x;
-  if (MODE == 1 || MODE == 3) y = fmax(dsub(y, p.lvl), 0.0);
+  if (MODE == 1 || MODE == 3) y = dsub(y, p.lvl);
+  if (MODE == 1) y = fmax(y, 0.0);
   if (MODE == 2 || MODE == 3) {
+    // MODE 3: p1 is a percentile of the clipped (non-negative) plane, so max(max(t, 0), p1) = max(t, p1)
+    if (MODE == 3 && p.p1 < 0.0) y = fmax(y, 0.0);
     y = fmin(fmax(y, p.p1), p.p2);
-    y = dadd(dmul(ddiv(dsub(y, p.p1), den), gain), p.o1);
+    y = dadd(dmul(div_const(dsub(y, p.p1), den), gain), p.o1);
   }
   return y;
 }
@@ -95,6 +134,18 @@ __device__ __forceinline__ int hist_bin(const HistRange& r, double x) {
   }
   idx = idx < 0 ? 0 : idx;
   if (idx != 255 && x >= hist_edge(r, idx + 1)) idx += 1;
+  return idx;
+}
+
+// same binning with the 257 edges tabulated in shared memory and the plane-constant division
+__device__ __forceinline__ int hist_bin_table(const HistRange& r, const DivConst& dn, const double* __restrict__ edges, double x) {
+  const double f = dmul(div_const(dsub(x, r.first), dn), 256.0);
+  int idx = (int)f;
+  idx = idx < 0 ? 0 : idx;
+  idx = idx > 255 ? 255 : idx;
+  idx -= (x < edges[idx]) ? 1 : 0;
+  idx = idx < 0 ? 0 : idx;
+  idx += (idx != 255 && x >= edges[idx + 1]) ? 1 : 0;
   return idx;
 }
 
@@ -139,6 +190,7 @@ __global__ void __launch_bounds__(256)
 map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, const amt_map_params* __restrict__ params,
            uint32_t* __restrict__ hist256, int hist_every, int hist_offset) {
   __shared__ uint32_t s_hist[HIST ? 8 * 256 : 1];
+  __shared__ double s_edges[HIST ? 257 : 1];
   const int64_t img = blockIdx.y;
   const amt_map_params p = params[img];
   const InT* src = in + img * n;
@@ -149,9 +201,12 @@ map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, cons
   if (HIST) {
     for (int i = threadIdx.x; i < 8 * 256; i += 256) s_hist[i] = 0;
     hr = make_hist_range(p.hist_first, p.hist_last);
+    for (int i = threadIdx.x; i < 257; i += 256) s_edges[i] = hist_edge(hr, i);
     __syncthreads();
   }
-  const double den = dsub(p.p2, p.p1), gain = dsub(p.o2, p.o1);
+  const DivConst hden = make_div_const(HIST ? hr.denom : 1.0);
+  const DivConst den = make_div_const(dsub(p.p2, p.p1));
+  const double gain = dsub(p.o2, p.o1);
   auto run = [&](auto mode_tag) {
     constexpr int MODE = decltype(mode_tag)::value;
     if (VEC) {
@@ -176,7 +231,7 @@ map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, cons
         if (HIST && do_hist) {
 #pragma unroll
           for (int e = 0; e < 8; ++e)
-            if (e < 4 || second) atomicAdd(&wh[hist_bin(hr, v[e])], 1u);
+            if (e < 4 || second) atomicAdd(&wh[hist_bin_table(hr, hden, s_edges, v[e])], 1u);
         }
       }
     } else {
@@ -184,7 +239,7 @@ map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, cons
       for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
         const double y = map_value_mode<MODE>(map_load<InT>(src + i), p, den, gain);
         dst[i] = y;
-        if (HIST && do_hist) atomicAdd(&wh[hist_bin(hr, y)], 1u);
+        if (HIST && do_hist) atomicAdd(&wh[hist_bin_table(hr, hden, s_edges, y)], 1u);
       }
     }
   };
@@ -404,6 +459,20 @@ __global__ void otsu_kernel(const uint32_t* __restrict__ hist, int mode, const a
   }
 }
 
+// bitwise comparison of div_const against __ddiv_rn (test hook)
+__global__ void selftest_div_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n,
+                                    unsigned long long* __restrict__ mismatches) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long bad = 0;
+  for (; i < n; i += step) {
+    const DivConst d = make_div_const(b[i]);
+    const double q = div_const(a[i], d), want = ddiv(a[i], b[i]);
+    bad += __double_as_longlong(q) != __double_as_longlong(want);
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 template <typename InT>
 __global__ void __launch_bounds__(256)
 threshold_gt_kernel(const InT* __restrict__ data, int64_t n, const double* __restrict__ thresholds, uint8_t* __restrict__ mask) {
@@ -521,6 +590,15 @@ int amt_threshold_gt(const void* data, int in_dtype, int64_t n_img, int64_t n, c
     threshold_gt_kernel<uint16_t><<<grid, 256, 0, as_stream(stream)>>>((const uint16_t*)data, n, thresholds, mask);
   else
     return AMT_ERR_UNSUPPORTED;
+  AMT_LAUNCH_CHECK();
+  return AMT_OK;
+}
+
+int amt_selftest_div(const double* a, const double* b, int64_t n, uint64_t* mismatches, amt_stream_t stream) {
+  using namespace amt;
+  if (!a || !b || !mismatches || n <= 0) return AMT_ERR_INVALID;
+  AMT_CUDA_TRY(cudaMemsetAsync(mismatches, 0, sizeof(uint64_t), as_stream(stream)));
+  selftest_div_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(a, b, n, (unsigned long long*)mismatches);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }

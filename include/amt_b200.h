@@ -99,6 +99,10 @@ int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int
  * the generic tile kernels. */
 int amt_tune(const char* key, int value);
 
+/* Test hook: *mismatches = number of i for which the plane-constant division sequence of the map
+ * kernel (reciprocal + two FMA corrections) differs bitwise from __ddiv_rn(a[i], b[i]). */
+int amt_selftest_div(const double* a, const double* b, int64_t n, uint64_t* mismatches, amt_stream_t stream);
+
 /* out = a - b elementwise (N-D DoG fallback: two full Gaussians then subtract). */
 int amt_sub_f64(const double* a, const double* b, double* out, int64_t n, amt_stream_t stream);
 

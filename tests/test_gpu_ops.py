@@ -167,3 +167,65 @@ def test_pipeline_device_chain_equals_op_by_op():
     img = np.random.default_rng(0).integers(0, 65535, size=(3, 128, 128)).astype(np.uint16)
     r = Pipeline([ImageOperation(operations.rescale_by_percentile, percentile_range=(2, 98), out_range=(0, 1))], parallel=True)(img)
     assert r.dtype == np.float64 and r.min() >= 0 and r.max() <= 1 and r.shape == img.shape
+
+
+def test_plane_constant_division_matches_ddiv_bitwise():
+    """The map kernel divides by a per-plane constant with reciprocal + two FMA corrections
+    (map.cu div_const); it must equal IEEE division (what NumPy does) for every input."""
+    import ctypes as C
+
+    import torch
+
+    from arcadia_microscopy_tools_b200 import _lib as L
+
+    lib = L.load()
+    rng = np.random.default_rng(99)
+    n = 1 << 22
+    parts_a, parts_b = [], []
+    # rescale-like operands: 0 <= a <= b
+    b = rng.random(n) * 10.0 ** rng.integers(-6, 3, n)
+    parts_a.append(b * rng.random(n)); parts_b.append(b)
+    # arbitrary magnitudes and signs inside and outside the fast window (tiny / huge -> __ddiv_rn path)
+    e = rng.integers(-1000, 1000, n)
+    parts_a.append(np.ldexp(rng.random(n) + 0.5, e) * rng.choice([-1.0, 1.0], n))
+    parts_b.append(np.ldexp(rng.random(n) + 0.5, rng.integers(-400, 400, n)))
+    # divisors with all-ones / all-zeros mantissas, numerators next to multiples of the divisor
+    ones = np.nextafter(np.ldexp(1.0, rng.integers(-20, 20, n)), 0.0)
+    k = rng.integers(1, 1 << 20, n).astype(np.float64)
+    near = ones * k
+    near = np.where(rng.random(n) < 0.5, np.nextafter(near, np.inf), np.nextafter(near, -np.inf))
+    parts_a.append(near); parts_b.append(ones)
+    parts_a.append(np.array([0.0, -0.0, 1.0, 5e-324, 2.0 ** -401, 2.0 ** -399, 1e308])); parts_b.append(np.full(7, 3.0))
+    a = np.concatenate(parts_a); b = np.concatenate(parts_b)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    L.check(lib.amt_selftest_div(_gpu.ptr(da), _gpu.ptr(db), a.size, _gpu.ptr(bad), _gpu.stream_ptr()))
+    assert int(bad.item()) == 0, f"{int(bad.item())} of {a.size} quotients differ from IEEE division"
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(64, 96), (160, 64), (256, 256)])
+def test_dog2d_strip_variants_bit_exact(variant, shape):
+    """Shapes with both sides multiples of 32 take the strip kernels of dog.cu; every tuning
+    variant must give scipy's bits, for uint16 and float64 input, plus the plane min/max."""
+    from arcadia_microscopy_tools_b200 import _lib as L
+
+    lib = L.load()
+    assert lib.amt_tune(b"dog_variant", variant) == 0
+    try:
+        rng = np.random.default_rng(31 + variant)
+        stack = rng.integers(0, 65535, size=(5, *shape)).astype(np.uint16)
+        for sigmas in [(0.6, 16.0), (1.0, 8.0), (0.0, 4.0)]:
+            dog, mm = _gpu.dog2d(_gpu.to_device(stack), 1.0 / 65535.0, *sigmas)
+            got = _gpu.to_host(dog)
+            for i in range(stack.shape[0]):
+                want = filters.difference_of_gaussians(stack[i], *sigmas)
+                _bits_equal(got[i], want, f"variant {variant} dog {sigmas} plane {i}")
+            mnmx = _gpu.minmax_values(mm, True)
+            assert np.array_equal(mnmx[:, 0], got.reshape(5, -1).min(1)) and np.array_equal(mnmx[:, 1], got.reshape(5, -1).max(1))
+        f = rng.normal(size=(2, *shape))
+        dog, _ = _gpu.dog2d(_gpu.to_device(f), 1.0, 0.6, 16.0)
+        for i in range(2):
+            _bits_equal(_gpu.to_host(dog)[i], filters.difference_of_gaussians(f[i], 0.6, 16.0), f"variant {variant} f64 plane {i}")
+    finally:
+        lib.amt_tune(b"dog_variant", 1)
