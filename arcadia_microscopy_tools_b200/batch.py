@@ -34,6 +34,7 @@ class FovPipelineConfig:
     max_label_value: int = 65535
     quantify_given_mask: bool = True
     with_shape: bool = False  # also perimeter / area_convex columns (not part of workload W)
+    given_label_dtype: type = np.int32  # host label masks of run_host: np.int32 or np.uint16 (Cellpose's dtype)
     low_sigma: float = 0.6
     high_sigma: float = 16.0
     bg_percentile: float = 0.0
@@ -65,7 +66,9 @@ class FovBatchExecutor:
             device=dev.index, n_channels=config.n_channels, height=config.height, width=config.width,
             seg_channel=config.seg_channel, chunk_fovs=config.chunk_fovs, max_labels=config.max_labels,
             max_label_value=config.max_label_value, quantify_given_mask=1 if config.quantify_given_mask else 0,
-            with_shape=1 if config.with_shape else 0, low_sigma=config.low_sigma, high_sigma=config.high_sigma,
+            with_shape=1 if config.with_shape else 0,
+            given_label_dtype=_lib.AMT_U16 if np.dtype(config.given_label_dtype) == np.uint16 else _lib.AMT_I32,
+            low_sigma=config.low_sigma, high_sigma=config.high_sigma,
             bg_percentile=config.bg_percentile, pct_lo=config.percentile_range[0], pct_hi=config.percentile_range[1],
             out_lo=config.out_range[0], out_hi=config.out_range[1],
         )
@@ -146,12 +149,16 @@ class FovBatchExecutor:
     # ------------------------------------------------------------------ host-fed batch
     def run_host(self, fovs: np.ndarray, given_labels: np.ndarray | None, out: dict | None = None) -> dict:
         """fovs: host (n_fov, C, H, W) uint16 (pinned memory overlaps copies with compute);
-        given_labels: host (n_fov, H, W) int32 or None.  Returns host arrays."""
+        given_labels: host (n_fov, H, W) of ``config.given_label_dtype`` (int32 or uint16) or None.
+        Returns host arrays."""
         c = self.config
         n_fov = fovs.shape[0]
         assert fovs.dtype == np.uint16 and fovs.flags.c_contiguous
         if given_labels is not None:
-            assert given_labels.dtype == np.int32 and given_labels.flags.c_contiguous
+            if given_labels.dtype != np.dtype(c.given_label_dtype):
+                raise TypeError(f"given_labels must be {np.dtype(c.given_label_dtype)} (config.given_label_dtype), "
+                                f"got {given_labels.dtype}")
+            assert given_labels.flags.c_contiguous
         if out is None:
             out = self.alloc_host_outputs(n_fov)
         vp = lambda a: None if a is None else a.ctypes.data  # noqa: E731

@@ -52,6 +52,7 @@ struct amt_executor {
   // host-path staging (two slots)
   uint16_t* in_slot[2];
   int32_t* given_slot[2];
+  uint16_t* given16_slot[2];  // raw uint16 label masks (given_label_dtype == AMT_U16), widened on the device
   double *tab_thr_slot[2], *tab_given_slot[2], *thr_slot[2];
   int32_t *cnt_thr_slot[2], *cnt_given_slot[2];
   bool host_slots;
@@ -178,6 +179,20 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
   return AMT_OK;
 }
 
+__global__ void widen_u16_kernel(const uint16_t* __restrict__ in, int32_t* __restrict__ out, int64_t n8) {
+  // 8 labels per thread: one 16-byte load, two 16-byte stores
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n8; i += step) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + i);
+    int4 a, b;
+    a.x = v.x & 0xffff; a.y = v.x >> 16; a.z = v.y & 0xffff; a.w = v.y >> 16;
+    b.x = v.z & 0xffff; b.y = v.z >> 16; b.z = v.w & 0xffff; b.w = v.w >> 16;
+    reinterpret_cast<int4*>(out)[2 * i] = a;
+    reinterpret_cast<int4*>(out)[2 * i + 1] = b;
+  }
+}
+
 static int alloc_host_slots(amt_executor* ex) {
   if (ex->host_slots) return AMT_OK;
   const amt_fov_config& c = ex->cfg;
@@ -186,6 +201,8 @@ static int alloc_host_slots(amt_executor* ex) {
   for (int s = 0; s < 2; ++s) {
     AMT_TRY(dmalloc(ex, (void**)&ex->in_slot[s], (size_t)c.chunk_fovs * c.n_channels * HW * sizeof(uint16_t)));
     AMT_TRY(dmalloc(ex, (void**)&ex->given_slot[s], (size_t)c.chunk_fovs * HW * sizeof(int32_t)));
+    if (c.given_label_dtype == AMT_U16)
+      AMT_TRY(dmalloc(ex, (void**)&ex->given16_slot[s], (size_t)c.chunk_fovs * HW * sizeof(uint16_t)));
     AMT_TRY(dmalloc(ex, (void**)&ex->tab_thr_slot[s], tab));
     AMT_TRY(dmalloc(ex, (void**)&ex->tab_given_slot[s], tab));
     AMT_TRY(dmalloc(ex, (void**)&ex->thr_slot[s], (size_t)c.chunk_fovs * sizeof(double)));
@@ -207,6 +224,9 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
   if (cfg->n_channels < 1 || cfg->n_channels > 8 || cfg->height < 1 || cfg->width < 1 || cfg->chunk_fovs < 1 ||
       cfg->max_labels < 1 || cfg->seg_channel < 0 || cfg->seg_channel >= cfg->n_channels || cfg->max_label_value < 0)
     return AMT_ERR_INVALID;
+  if (cfg->given_label_dtype != 0 && cfg->given_label_dtype != AMT_I32 && cfg->given_label_dtype != AMT_U16)
+    return AMT_ERR_INVALID;
+  if (cfg->given_label_dtype == AMT_U16 && cfg->max_label_value > 65535) return AMT_ERR_INVALID;
   if (!(cfg->bg_percentile >= 0 && cfg->bg_percentile <= 100) ||
       !(0 <= cfg->pct_lo && cfg->pct_lo < cfg->pct_hi && cfg->pct_hi <= 100))
     return AMT_ERR_INVALID;
@@ -305,7 +325,7 @@ void amt_executor_destroy(amt_executor* ex) {
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (int s = 0; s < 2; ++s) {
-    void* sb[] = {ex->in_slot[s], ex->given_slot[s], ex->tab_thr_slot[s], ex->tab_given_slot[s], ex->thr_slot[s],
+    void* sb[] = {ex->in_slot[s], ex->given_slot[s], ex->given16_slot[s], ex->tab_thr_slot[s], ex->tab_given_slot[s], ex->thr_slot[s],
                   ex->cnt_thr_slot[s], ex->cnt_given_slot[s]};
     for (void* b : sb)
       if (b) cudaFree(b);
@@ -355,14 +375,16 @@ int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_
   return AMT_OK;
 }
 
-int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const int32_t* given_labels_host, int64_t n_fov,
+int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const void* given_labels_host, int64_t n_fov,
                           double* tables_thr_host, int32_t* counts_thr_host, double* tables_given_host,
                           int32_t* counts_given_host, double* thresholds_host) {
   using namespace amt;
   if (!ex || !fovs_host || !tables_thr_host || !counts_thr_host || n_fov <= 0) return AMT_ERR_INVALID;
   const amt_fov_config& c = ex->cfg;
   const bool given = c.quantify_given_mask && given_labels_host;
+  const bool u16_labels = c.given_label_dtype == AMT_U16;
   if (given && (!tables_given_host || !counts_given_host)) return AMT_ERR_INVALID;
+  if (u16_labels && ((int64_t)c.height * c.width) % 8 != 0) return AMT_ERR_UNSUPPORTED;
   AMT_CUDA_TRY(cudaSetDevice(c.device));
   AMT_TRY(alloc_host_slots(ex));
   const int C = c.n_channels;
@@ -378,9 +400,15 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const int
     if (chunk >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_in, ex->ev_done[s], 0));
     AMT_CUDA_TRY(cudaMemcpyAsync(ex->in_slot[s], fovs_host + f0 * C * HW, (size_t)g * C * HW * sizeof(uint16_t),
                                  cudaMemcpyHostToDevice, ex->s_in));
-    if (given)
-      AMT_CUDA_TRY(cudaMemcpyAsync(ex->given_slot[s], given_labels_host + f0 * HW, (size_t)g * HW * sizeof(int32_t),
-                                   cudaMemcpyHostToDevice, ex->s_in));
+    if (given && u16_labels) {
+      AMT_CUDA_TRY(cudaMemcpyAsync(ex->given16_slot[s], (const uint16_t*)given_labels_host + f0 * HW,
+                                   (size_t)g * HW * sizeof(uint16_t), cudaMemcpyHostToDevice, ex->s_in));
+      widen_u16_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given16_slot[s], ex->given_slot[s], (int64_t)g * HW / 8);
+      AMT_LAUNCH_CHECK();
+    } else if (given) {
+      AMT_CUDA_TRY(cudaMemcpyAsync(ex->given_slot[s], (const int32_t*)given_labels_host + f0 * HW,
+                                   (size_t)g * HW * sizeof(int32_t), cudaMemcpyHostToDevice, ex->s_in));
+    }
     AMT_CUDA_TRY(cudaEventRecord(ex->ev_in[s], ex->s_in));
     // output slot s is free once its previous D2H has finished
     AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_compute, ex->ev_in[s], 0));

@@ -246,6 +246,8 @@ typedef struct amt_fov_config {
   int32_t max_label_value; /* largest value allowed in a given label mask */
   int32_t quantify_given_mask; /* 1: also clear_border + relabel + quantify the given mask */
   int32_t with_shape;          /* 1: also fill perimeter / area_convex (amt_region_shape) */
+  int32_t given_label_dtype;   /* amt_executor_run_host only: AMT_I32 (0 = default) or AMT_U16 host label
+                                  masks (Cellpose's own mask dtype below 65536 cells; halves their PCIe bytes) */
   double low_sigma, high_sigma;  /* subtract_background_dog */
   double bg_percentile;
   double pct_lo, pct_hi;         /* rescale_by_percentile percentile_range */
@@ -270,7 +272,7 @@ int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_
 /* Host-fed batch: inputs and outputs are HOST pointers (pinned memory recommended; pageable
  * works but serialises).  Copies are double-buffered against compute on separate streams.
  * Synchronous: returns when every output byte is on the host. */
-int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const int32_t* given_labels_host,
+int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const void* given_labels_host,
                           int64_t n_fov, double* tables_thr_host, int32_t* counts_thr_host,
                           double* tables_given_host, int32_t* counts_given_host, double* thresholds_host);
 int amt_executor_sync(amt_executor* ex);

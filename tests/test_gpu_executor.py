@@ -158,3 +158,25 @@ def test_executor_full_size_properties():
     # the given mask: every surviving cell keeps its generated area
     lab0 = host["labels_given"][0]
     assert np.array_equal(lab0 > 0, oracle.labeling.clear_border(given) > 0)
+
+
+def test_run_host_uint16_label_masks_match_int32():
+    """Host label masks may travel as uint16 (Cellpose's mask dtype): same tables, half the PCIe bytes."""
+    n_fov, C, shape = 3, 2, (128, 160)
+    fovs, givens = [], []
+    for i in range(n_fov):
+        f, g, _ = make_fov(2000 + i, C, shape[0], shape[1], 30)
+        fovs.append(f), givens.append(g)
+    fovs, givens = np.stack(fovs), np.stack(givens).astype(np.int32)
+    outs = []
+    for dt in (np.int32, np.uint16):
+        cfg = FovPipelineConfig(n_channels=C, height=shape[0], width=shape[1], seg_channel=1, chunk_fovs=2, max_labels=256,
+                                max_label_value=int(givens.max()), given_label_dtype=dt)
+        with FovBatchExecutor(cfg) as ex:
+            outs.append(ex.run_host(fovs, givens.astype(dt)))
+            with pytest.raises(TypeError):
+                ex.run_host(fovs, givens.astype(np.int64))
+    assert np.array_equal(outs[0]["counts_given"], outs[1]["counts_given"]) and outs[0]["counts_given"].min() > 0
+    for i in range(n_fov):
+        cnt = int(outs[0]["counts_given"][i])
+        assert np.array_equal(outs[0]["tables_given"][i][:, :cnt], outs[1]["tables_given"][i][:, :cnt], equal_nan=True)
