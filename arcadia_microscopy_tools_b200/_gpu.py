@@ -161,6 +161,31 @@ def gaussian_nd(x, scale: float, sigma: float):
     return cur
 
 
+def minmax_filter_nd(x, size: int, is_max: bool, minuend=None):
+    """Flat erosion / dilation with a size**ndim box over every axis of one N-D array (uint16 bits
+    or float64), scipy's window alignment (grey_erosion / grey_dilation with ``size``),
+    mode='reflect'.  ``minuend``: the last pass writes ``minuend - result``."""
+    torch = torch_mod()
+    lib = _lib.load()
+    shape = tuple(x.shape)
+    code = dtype_code(x)
+    left = size // 2 - (1 if (is_max and size % 2 == 0) else 0)
+    cur = x
+    for axis in range(len(shape)):
+        outer = int(np.prod(shape[:axis], dtype=np.int64))
+        n = shape[axis]
+        inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+        out = torch.empty(shape, dtype=x.dtype, device=x.device)
+        last = axis == len(shape) - 1
+        check(
+            lib.amt_minmax_filter_axis(ptr(cur), code, ptr(out), ptr(minuend) if (last and minuend is not None) else None,
+                                       outer, n, inner, size, left, 1 if is_max else 0, stream_ptr()),
+            "amt_minmax_filter_axis",
+        )
+        cur = out
+    return cur
+
+
 def sub_f64(a, b):
     torch = torch_mod()
     out = torch.empty_like(a)

@@ -103,6 +103,14 @@ int amt_tune(const char* key, int value);
  * kernel (reciprocal + two FMA corrections) differs bitwise from __ddiv_rn(a[i], b[i]). */
 int amt_selftest_div(const double* a, const double* b, int64_t n, uint64_t* mismatches, amt_stream_t stream);
 
+/* Flat grey-scale erosion (is_max = 0) / dilation (is_max = 1) along one axis of an (outer, n, inner)
+ * array: out[i] = min / max of in over the window [i - left, i - left + size), mode='reflect'
+ * (= scipy.ndimage.minimum_filter1d / maximum_filter1d with origin = left - size/2).  dtype AMT_U16 or
+ * AMT_F64, out has the same dtype; minuend (optional, same dtype): out = minuend - result, the final
+ * step of scipy.ndimage.white_tophat.  Extension: the reference has no morphology op. */
+int amt_minmax_filter_axis(const void* in, int dtype, void* out, const void* minuend, int64_t outer, int64_t n,
+                           int64_t inner, int size, int left, int is_max, amt_stream_t stream);
+
 /* out = a - b elementwise (N-D DoG fallback: two full Gaussians then subtract). */
 int amt_sub_f64(const double* a, const double* b, double* out, int64_t n, amt_stream_t stream);
 

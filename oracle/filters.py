@@ -92,3 +92,9 @@ def difference_of_gaussians(image: np.ndarray, low_sigma: float, high_sigma: flo
     im1 = ndi.gaussian_filter(f, low_sigma, mode="nearest", cval=0, truncate=4.0)
     im2 = ndi.gaussian_filter(f, high_sigma, mode="nearest", cval=0, truncate=4.0)
     return im1 - im2
+
+
+def white_tophat(image: np.ndarray, size: int) -> np.ndarray:
+    """Extension (no reference call site): the real ``scipy.ndimage.white_tophat`` with a flat
+    ``size``-wide box, mode='reflect' -- what ``operations.subtract_background_tophat`` must equal."""
+    return ndi.white_tophat(image, size=size)

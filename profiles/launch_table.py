@@ -22,7 +22,12 @@ def main() -> None:
         if len(r) <= vi:
             continue
         scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[ui], 1e-3)
-        name = re.match(r"(?:void )?(?:amt::)?([A-Za-z0-9_]+)", r[ki]).group(1)
+        full = r[ki]
+        if "at::" in full or "cub::" in full or full.startswith(("void at", "void (anonymous")):
+            continue  # torch kernels of the synthetic input generator, not the library
+        name = re.match(r"(?:void )?(?:amt::)?([A-Za-z0-9_]+)", full).group(1)
+        if name in ("native", "cuda", "vectorized_elementwise_kernel", "distribution_elementwise_grid_stride_kernel"):
+            continue
         data.append((name, float(r[vi].replace(",", "")) * scale))
     data = data[first:first + count] if count else data[first:]
     agg: "OrderedDict[str, list]" = OrderedDict()

@@ -229,3 +229,37 @@ def test_dog2d_strip_variants_bit_exact(variant, shape):
             _bits_equal(_gpu.to_host(dog)[i], filters.difference_of_gaussians(f[i], 0.6, 16.0), f"variant {variant} f64 plane {i}")
     finally:
         lib.amt_tune(b"dog_variant", 1)
+
+
+@pytest.mark.parametrize("size", [1, 2, 3, 8, 15, 50, 101])
+@pytest.mark.parametrize("dtype", [np.uint16, np.float64])
+def test_white_tophat_matches_scipy(size, dtype):
+    rng = np.random.default_rng(size)
+    for shape in [(64, 64), (97, 131), (300, 40), (20, 17)]:
+        img = rng.integers(0, 65535, size=shape).astype(dtype)
+        if dtype == np.float64:
+            img = img / 65535.0 - 0.3
+        got = operations.subtract_background_tophat(img, size)
+        want = filters.white_tophat(img, size)
+        assert got.dtype == want.dtype
+        _bits_equal(got, want, f"white_tophat size={size} {shape} {dtype}")
+
+
+def test_white_tophat_batched_and_3d():
+    rng = np.random.default_rng(77)
+    stack = rng.integers(0, 4000, size=(4, 90, 70)).astype(np.uint16)
+    got = operations.subtract_background_tophat(stack, 9, _batched=True)
+    for i in range(4):
+        _bits_equal(got[i], filters.white_tophat(stack[i], 9), f"batched plane {i}")
+    got3 = operations.subtract_background_tophat(stack, 5)  # one 3-D array: the box spans all three axes
+    _bits_equal(got3, filters.white_tophat(stack, 5), "3-D top-hat")
+
+
+def test_gaussian_smooth_matches_scipy():
+    rng = np.random.default_rng(78)
+    img = rng.integers(0, 65535, size=(128, 96)).astype(np.uint16)
+    _bits_equal(operations.gaussian_smooth(img, 2.0), filters.gaussian(img, 2.0), "gaussian_smooth u16")
+    f = rng.normal(size=(3, 40, 50))
+    got = operations.gaussian_smooth(f, 1.5, _batched=True)
+    for i in range(3):
+        _bits_equal(got[i], filters.gaussian(f[i], 1.5), f"gaussian_smooth batched {i}")
