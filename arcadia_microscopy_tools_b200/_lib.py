@@ -102,6 +102,7 @@ SIGNATURES: dict[str, tuple] = {
     "amt_dog2d_axis0": (_i, [_p, _i, _d, _i64, _i64, _i64, _p, _i, _p, _i, _p, _p, _p]),
     "amt_dog2d_axis1": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _i, _p, _i, _p, _p]),
     "amt_minmax_filter_axis": (_i, [_p, _i, _p, _p, _i64, _i64, _i64, _i, _i, _i, _p]),
+    "amt_deinterleave_u16": (_i, [_p, _p, _i64, _i64, _i, _p]),
     "amt_sub_f64": (_i, [_p, _p, _p, _i64, _p]),
     "amt_minmax_f64": (_i, [_p, _i64, _i64, _p, _p]),
     "amt_minmax_u16": (_i, [_p, _i64, _i64, _p, _p]),

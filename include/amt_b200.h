@@ -111,6 +111,12 @@ int amt_selftest_div(const double* a, const double* b, int64_t n, uint64_t* mism
 int amt_minmax_filter_axis(const void* in, int dtype, void* out, const void* minuend, int64_t outer, int64_t n,
                            int64_t inner, int size, int left, int is_max, amt_stream_t stream);
 
+/* Pixel-interleaved frames (n_frames, n_pix, C) uint16 -> channel planes (n_frames, C, n_pix): the
+ * layout step of nd2.ND2File.asarray (nikon.py:25-43) for raw ND2 "ImageDataSeq" payloads that were
+ * memcpy'd to the device unchanged. */
+int amt_deinterleave_u16(const uint16_t* in_yxc, uint16_t* out_cyx, int64_t n_frames, int64_t n_pix, int n_channels,
+                         amt_stream_t stream);
+
 /* out = a - b elementwise (N-D DoG fallback: two full Gaussians then subtract). */
 int amt_sub_f64(const double* a, const double* b, double* out, int64_t n, amt_stream_t stream);
 

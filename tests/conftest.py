@@ -11,6 +11,8 @@ import pytest
 ROOT = Path(__file__).resolve().parents[1]
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
+if str(Path(__file__).parent) not in sys.path:
+    sys.path.insert(0, str(Path(__file__).parent))  # test helpers (nd2_synth)
 
 GOLDEN = Path(__file__).parent / "golden" / "config1_multichannel.npz"
 

@@ -263,3 +263,20 @@ def test_gaussian_smooth_matches_scipy():
     got = operations.gaussian_smooth(f, 1.5, _batched=True)
     for i in range(3):
         _bits_equal(got[i], filters.gaussian(f[i], 1.5), f"gaussian_smooth batched {i}")
+
+
+def test_nd2_fast_path_matches_host_reader(tmp_path):
+    """Raw ND2 frame payloads -> pinned staging -> H2D -> amt_deinterleave_u16 == host de-interleave."""
+    from nd2_synth import write_nd2
+
+    from arcadia_microscopy_tools_b200 import nd2_raw
+
+    rng = np.random.default_rng(4)
+    for shape in [(2, 4, 256, 256), (3, 1, 64, 80), (1, 3, 33, 47), (1, 2, 1030, 517)]:
+        frames = rng.integers(0, 65535, size=shape).astype(np.uint16)
+        path = tmp_path / f"s{shape[1]}_{shape[2]}.nd2"
+        write_nd2(path, frames)
+        dev = nd2_raw.read_nd2_to_device(path)
+        got = _gpu.to_host(dev).view(np.uint16)
+        assert got.shape == frames.shape
+        _bits_equal(got, frames, f"nd2 fast path {shape}")

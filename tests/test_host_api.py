@@ -225,3 +225,28 @@ def test_compute_entry_points_fail_loudly_without_a_gpu():
     m[2:5, 2:5] = True
     with pytest.raises(_lib.AmtLibraryError, match="no CPU fallback"):
         masks.SegmentationMask(m).label_image
+
+
+def test_nd2_raw_reader_and_frame_layout(tmp_path):
+    """Host side of the ND2 fast path: chunk map, attributes, zero-copy frame offsets."""
+    from nd2_synth import write_nd2
+
+    from arcadia_microscopy_tools_b200 import nd2_raw
+
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 65535, size=(3, 4, 20, 28)).astype(np.uint16)
+    path = tmp_path / "synthetic.nd2"
+    write_nd2(path, frames)
+    assert np.array_equal(nd2_raw.read_nd2_frames(path), frames)
+    mm, offsets, (h, w, c) = nd2_raw.nd2_frame_layout(path)
+    assert (h, w, c) == (20, 28, 4) and len(offsets) == 3
+    for i, off in enumerate(offsets):
+        raw = np.frombuffer(mm[off : off + h * w * c * 2].tobytes(), dtype="<u2").reshape(h, w, c)
+        assert np.array_equal(raw.transpose(2, 0, 1), frames[i])
+    ref_dir = Path("/root/reference/src/arcadia_microscopy_tools/tests/data")
+    for f in sorted(ref_dir.glob("*.nd2")) if ref_dir.exists() else []:
+        want = nd2_raw.read_nd2_frames(f)
+        mm, offsets, (h, w, c) = nd2_raw.nd2_frame_layout(f)
+        got = np.stack([np.frombuffer(mm[o : o + h * w * c * 2].tobytes(), dtype="<u2").reshape(h, w, c).transpose(2, 0, 1)
+                        for o in offsets])
+        assert np.array_equal(got, want), f.name
