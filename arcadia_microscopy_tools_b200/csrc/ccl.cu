@@ -4,33 +4,50 @@
 // ski.measure.label (:63) [3p] for bool masks or ski.segmentation.relabel_sequential (:65) [3p]
 // for integer masks.  SURVEY.md 8a items 7-9.
 //
-// Block-based union-find CCL, 8-connectivity, on "same non-zero value" adjacency (binary masks
-// are the one-value case; integer masks give clear_border's re-labelling by value+connectivity):
-//  A. tile:     a CTA labels a 64x32 tile entirely in shared memory — warp-level run linking
-//               (one ballot per 32-pixel row segment), then lock-free unions (shared-memory
-//               atomicMin, roots only) with the row above using the N / W / NW / NE decision
-//               tree — and writes each pixel's tile root as a GLOBAL pixel index (one 4-byte
-//               store per pixel; the input is read once, thresholded on the fly if it is a
+// Run-based block union-find, 8-connectivity, on "same non-zero value" adjacency (binary masks
+// are the one-value case; integer masks give clear_border's re-labelling by value+connectivity).
+// The work is proportional to the number of RUNS, not pixels; pixels only pay for the streaming
+// read of the input and the streaming write of the labels:
+//  A. tile:     a CTA takes a 64x64 tile.  Warps load it row by row (lane = pixel) and turn every
+//               row into 64-bit masks with ballots: foreground, run starts and, for integer
+//               masks, "same value as N / NW / NE".  One thread per row then walks that row's
+//               RUNS with bit scans and unions each run with the runs of the row above it
+//               touches (shared-memory union-find, roots = smallest index).  Every pixel is
+//               written once with its tile root as a GLOBAL pixel index; tile roots are appended
+//               to a per-image list.  The input is read once (thresholded on the fly if it is a
 //               float64 plane).
-//  B. seams:    only the pixels on tile seams union across tiles (global atomicMin).  This is
-//               the warp-level boundary-merge pass: ~6 % of the pixels.
-//  C. compress: every pixel points at its root.  Roots are the smallest pixel index of the
-//               component = its first pixel in raster order, which is exactly the numbering
-//               key of scipy.ndimage.label / skimage.  Border pixels flag their root; each CTA
-//               leaves its roots as an ordered list (block scan, no arrival-order atomics).
-//  D. number:   one CTA per plane walks the root lists in raster order and gives the
-//               surviving roots consecutive ids (integer masks: marks the surviving VALUES,
-//               which a presence-table scan then ranks = relabel_sequential).
-//  E. final:    gather the id through the root, in place, 16-byte accesses.
-// Pixel traffic: A 4-12 B, C 8 B, E 8 B + a cached gather: HBM-bound streaming.
+//  B. seams:    only the pixels on tile seams union across tiles (global atomicMin): the
+//               warp-level boundary-merge pass, ~5 % of the pixels.
+//  C. roots:    only the listed tile roots are flattened to their global root (the smallest
+//               pixel index of the component = its first pixel in raster order, which is the
+//               numbering key of scipy.ndimage.label / skimage); global roots set their bit in a
+//               one-bit-per-pixel bitmap.  Border pixels clear the bit of their component.
+//  D. number:   a popcount prefix over the bitmap words ranks the surviving roots in raster
+//               order (integer masks: surviving roots mark their VALUE, a presence-table scan
+//               ranks the values = relabel_sequential).
+//  E. final:    pixel -> tile root -> global root -> id, in place, 16-byte accesses.
+// Pixel traffic: A 4-12 B, E 8 B + cached gathers; everything else touches runs / roots only.
 
 #include "common.cuh"
 
 namespace amt {
 
-constexpr int TW = 64, TH = 32;      // tile of kernel A
-constexpr int CBLK = 1024;           // pixels per CTA in the linear kernels (256 threads x 4)
-constexpr int ROOT_CAP = CBLK;       // root-list slots per CTA (trivial upper bound: every pixel a root)
+constexpr int TW = 64, TH = 64;  // tile of kernel A
+
+template <int KIND> struct CclRaw { typedef uint8_t type; };
+template <> struct CclRaw<1> { typedef double type; };
+template <> struct CclRaw<2> { typedef int32_t type; };
+
+template <int KIND>
+__device__ __forceinline__ typename CclRaw<KIND>::type ccl_raw(const void* in, const int64_t idx) {
+  return __ldg((const typename CclRaw<KIND>::type*)in + idx);
+}
+template <int KIND>
+__device__ __forceinline__ int ccl_cook(const typename CclRaw<KIND>::type raw, const double thr) {
+  if (KIND == 0) return raw ? 1 : 0;
+  if (KIND == 1) return raw > thr ? 1 : 0;
+  return (int)raw;
+}
 
 template <int KIND>
 __device__ __forceinline__ int ccl_value(const void* in, const double thr, const int64_t idx) {
@@ -92,12 +109,23 @@ __device__ __forceinline__ void suf_union(int* L, int a, int b) {
 }
 
 // ---------------------------------------------------------------- A. tile labelling
-// grid (ceil(w/64), ceil(h/32), planes); block 256 = 8 warps; warp -> rows warp, warp+8, ...
+__device__ __forceinline__ uint64_t run_mask_from(const uint64_t stops, const int a) {
+  // bits a .. b where b + 1 is the first set bit of `stops` above a (or 64)
+  const uint64_t above = (a == 63) ? 0ull : (stops >> (a + 1)) << (a + 1);
+  const int end = above ? (__ffsll((long long)above) - 1) : 64;  // exclusive
+  const uint64_t upto = (end == 64) ? ~0ull : ((1ull << end) - 1ull);
+  return upto & ~((1ull << a) - 1ull);
+}
+
+// grid (ceil(w/64), ceil(h/64), planes); block 256 = 8 warps; warp -> rows warp, warp+8, ...
 template <int KIND>
 __global__ void __launch_bounds__(256)
 ccl_tile_kernel(const void* __restrict__ in, const int64_t in_stride, const double* __restrict__ thresholds,
-                int32_t* __restrict__ L, int32_t* __restrict__ aux, const int h, const int w) {
-  __shared__ int s_lab[TH * TW];
+                int32_t* __restrict__ L, int32_t* __restrict__ rootlist, int32_t* __restrict__ rootcnt, const int h,
+                const int w) {
+  __shared__ int s_lab[TH * TW];                  // union-find over run starts (tile-local pixel index)
+  __shared__ uint64_t s_fg[TH], s_brk[TH];        // per row: foreground, run starts
+  __shared__ uint64_t s_n[KIND == 2 ? TH : 1], s_nw[KIND == 2 ? TH : 1], s_ne[KIND == 2 ? TH : 1];
   __shared__ int s_val[KIND == 2 ? TH * TW : 1];
   const int64_t img = blockIdx.z;
   const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
@@ -106,74 +134,165 @@ ccl_tile_kernel(const void* __restrict__ in, const int64_t in_stride, const doub
   const int64_t in_base = img * in_stride;
   const int64_t plane = img * (int64_t)h * w;
 
+  int vals[8][2];
+  {
+    // every global load of the tile is issued before the first use (16 in flight per thread)
+    typename CclRaw<KIND>::type raw[8][2];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int lr = warp + 8 * q, y = ty0 + lr;
+    for (int q = 0; q < 8; ++q) {
+      const int y = ty0 + warp + 8 * q;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int lc = half * 32 + lane, x = tx0 + lc;
-      const int v = (y < h && x < w) ? ccl_value<KIND>(in, thr, in_base + (int64_t)y * w + x) : 0;
-      const int vl = __shfl_up_sync(0xffffffffu, v, 1);
-      const unsigned brk = __ballot_sync(0xffffffffu, lane == 0 || v != vl);
-      const int start = 31 - __clz((int)(brk & (0xffffffffu >> (31 - lane))));
-      s_lab[lr * TW + lc] = v ? (lr * TW + half * 32 + start) : -1;
-      if (KIND == 2) s_val[lr * TW + lc] = v;
+      for (int half = 0; half < 2; ++half) {
+        const int x = tx0 + half * 32 + lane;
+        raw[q][half] = (y < h && x < w) ? ccl_raw<KIND>(in, in_base + (int64_t)y * w + x) : (typename CclRaw<KIND>::type)0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int y = ty0 + warp + 8 * q;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int x = tx0 + half * 32 + lane;
+        vals[q][half] = (y < h && x < w) ? ccl_cook<KIND>(raw[q][half], thr) : 0;
+      }
     }
   }
-  __syncthreads();
-
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 8; ++q) {
     const int lr = warp + 8 * q;
+    uint32_t fgw[2], bkw[2];
+    int last = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int lc = half * 32 + lane;
-      const int p = lr * TW + lc;
-      bool fg, n_s, w_s, nw_s, ne_s;
-      if (KIND == 2) {
-        const int v = s_val[p];
-        fg = v != 0;
-        w_s = fg && lc > 0 && s_val[p - 1] == v;
-        n_s = fg && lr > 0 && s_val[p - TW] == v;
-        nw_s = fg && lr > 0 && lc > 0 && s_val[p - TW - 1] == v;
-        ne_s = fg && lr > 0 && lc < TW - 1 && s_val[p - TW + 1] == v;
-      } else {
-        fg = s_lab[p] >= 0;  // labels only ever move between non-negative values
-        w_s = fg && lc > 0 && s_lab[p - 1] >= 0;
-        n_s = fg && lr > 0 && s_lab[p - TW] >= 0;
-        nw_s = fg && lr > 0 && lc > 0 && s_lab[p - TW - 1] >= 0;
-        ne_s = fg && lr > 0 && lc < TW - 1 && s_lab[p - TW + 1] >= 0;
+      const int v = vals[q][half];
+      int vl = __shfl_up_sync(0xffffffffu, v, 1);
+      if (lane == 0) vl = half ? last : 0;  // the run may continue from the left half; tile edge: a start
+      last = __shfl_sync(0xffffffffu, v, 31);
+      const bool start = v != 0 && v != vl;
+      fgw[half] = __ballot_sync(0xffffffffu, v != 0);
+      bkw[half] = __ballot_sync(0xffffffffu, start);
+      if (start) s_lab[lr * TW + lc] = lr * TW + lc;
+      if (KIND == 2) s_val[lr * TW + lc] = v;
+    }
+    if (lane == 0) {
+      s_fg[lr] = ((uint64_t)fgw[1] << 32) | fgw[0];
+      s_brk[lr] = ((uint64_t)bkw[1] << 32) | bkw[0];
+    }
+  }
+  __syncthreads();
+  if (KIND == 2) {  // same-value masks against the row above (ballots; the values are still in registers)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int lr = warp + 8 * q;
+      uint32_t nw_[2], n_[2], ne_[2];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int lc = half * 32 + lane, v = vals[q][half];
+        const int* up = s_val + (lr - 1) * TW + lc;
+        const bool ok = v != 0 && lr > 0;
+        n_[half] = __ballot_sync(0xffffffffu, ok && up[0] == v);
+        nw_[half] = __ballot_sync(0xffffffffu, ok && lc > 0 && up[-1] == v);
+        ne_[half] = __ballot_sync(0xffffffffu, ok && lc < TW - 1 && up[1] == v);
       }
-      if (fg) {
-        if (n_s) {
-          // W and NW both set: p ~ W (run link) ~ NW ~ N already, except across a segment seam
-          if (!(w_s && nw_s && lane != 0)) suf_union(s_lab, p, p - TW);
-        } else {
-          if (w_s) {
-            if (lane == 0) suf_union(s_lab, p, p - 1);  // inside a segment the run is linked
-          } else if (nw_s) {
-            suf_union(s_lab, p, p - TW - 1);
-          }
-          if (ne_s) suf_union(s_lab, p, p - TW + 1);
+      if (lane == 0) {
+        s_n[lr] = ((uint64_t)n_[1] << 32) | n_[0];
+        s_nw[lr] = ((uint64_t)nw_[1] << 32) | nw_[0];
+        s_ne[lr] = ((uint64_t)ne_[1] << 32) | ne_[0];
+      }
+    }
+    __syncthreads();
+  }
+
+  // link: one thread per row walks its runs and unions each with the runs it touches in the row above
+  if (threadIdx.x < TH && threadIdx.x > 0) {
+    const int lr = threadIdx.x;
+    const uint64_t fg = s_fg[lr], brk = s_brk[lr];
+    const uint64_t ufg = s_fg[lr - 1], ubrk = s_brk[lr - 1];
+    uint64_t en, enw, ene;
+    if (KIND == 2) {
+      en = s_n[lr]; enw = s_nw[lr]; ene = s_ne[lr];
+    } else {
+      en = fg & ufg; enw = fg & (ufg << 1); ene = fg & (ufg >> 1);
+    }
+    if (en | enw | ene) {
+      const uint64_t stops = brk | ~fg, ustops = ubrk | ~ufg;
+      uint64_t todo = brk;
+      while (todo) {
+        const int a = __ffsll((long long)todo) - 1;
+        todo &= todo - 1;
+        const uint64_t R = run_mask_from(stops, a);
+        // pixels of the row above that carry this run's value and touch it
+        uint64_t A = (en & R) | ((enw & R) >> 1) | ((ene & R) << 1);
+        while (A) {
+          const int x = __ffsll((long long)A) - 1;
+          const int ua = 63 - __clzll((long long)(ubrk & ((x == 63) ? ~0ull : ((2ull << x) - 1ull))));
+          suf_union(s_lab, lr * TW + a, (lr - 1) * TW + ua);
+          A &= ~run_mask_from(ustops, ua);
         }
       }
     }
   }
   __syncthreads();
-
+  // flatten the runs (find everything first, write after a barrier: every entry then holds its root);
+  // tile roots join the per-image list
+  {
+    const int lr = threadIdx.x & (TH - 1);
+    int roots[4];  // runs 4*k + (threadIdx.x / TH) of row lr: four threads share a row
+    int nr = 0;
+    bool overflow = false;
+    uint64_t todo = s_brk[lr];
+    int k = 0;
+    while (todo) {
+      const int a = __ffsll((long long)todo) - 1;
+      todo &= todo - 1;
+      if ((k++ & 3) != (int)(threadIdx.x / TH)) continue;
+      const int r = suf_find(s_lab, lr * TW + a);
+      if (nr < 4) roots[nr++] = (a << 16) | r; else overflow = true;
+    }
+    __syncthreads();
+    for (int i = 0; i < nr; ++i) {
+      const int a = roots[i] >> 16, r = roots[i] & 0xffff, idx = lr * TW + a;
+      if (r == idx) {
+        const int pos = atomicAdd(rootcnt + img, 1);
+        rootlist[plane + pos] = (ty0 + lr) * w + tx0 + a;
+      } else {
+        s_lab[idx] = r;
+      }
+    }
+    if (overflow) {  // more than 16 runs in the row: the remaining ones (k >= 16) one at a time
+      uint64_t rest = s_brk[lr];
+      int kk = 0;
+      while (rest) {
+        const int a = __ffsll((long long)rest) - 1;
+        rest &= rest - 1;
+        const int mine = (kk++ & 3) == (int)(threadIdx.x / TH);
+        if (!mine || kk <= 16) continue;
+        const int idx = lr * TW + a;
+        const int r = suf_find(s_lab, idx);
+        if (r == idx) {
+          const int pos = atomicAdd(rootcnt + img, 1);
+          rootlist[plane + pos] = (ty0 + lr) * w + tx0 + a;
+        }
+      }
+    }
+  }
+  __syncthreads();
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 8; ++q) {
     const int lr = warp + 8 * q, y = ty0 + lr;
+    const uint64_t fg = s_fg[lr], brk = s_brk[lr];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int lc = half * 32 + lane, x = tx0 + lc;
       if (y < h && x < w) {
-        const int p = lr * TW + lc;
         int out = -1;
-        if (s_lab[p] >= 0) {
-          const int r = suf_find(s_lab, p);
-          out = (ty0 + r / TW) * w + tx0 + (r % TW);
-          if (r == p) aux[plane + (int64_t)y * w + x] = 0;  // flag / id slot of a (tile) root
+        if ((uint32_t)(fg >> (half * 32)) != 0u) {  // warp-uniform: most row segments are all background
+          if ((fg >> lc) & 1ull) {
+            const int a = 63 - __clzll((long long)(brk & ((lc == 63) ? ~0ull : ((2ull << lc) - 1ull))));
+            const int r = suf_find(s_lab, lr * TW + a);  // one hop for flattened entries
+            out = (ty0 + (r >> 6)) * w + tx0 + (r & 63);
+          }
         }
         L[plane + (int64_t)y * w + x] = out;
       }
@@ -255,125 +374,162 @@ __device__ __forceinline__ int block_excl_scan(int v, int* s_warp, int* total) {
   return s_warp[warp] + incl - v;
 }
 
-// ---------------------------------------------------------------- C. compress + roots + border flags
-// grid (ceil(npx/1024), planes); block 256; thread -> 4 consecutive pixels
+// ---------------------------------------------------------------- C. roots: flatten, mark, border
+// grid (ceil(cap/256), planes): the listed tile roots point at their global root; global roots set
+// their bit (integer masks decide later, from the surviving bits, which VALUES are present)
 __global__ void __launch_bounds__(256)
-ccl_compress_kernel(int32_t* __restrict__ L, int32_t* __restrict__ aux, const int h, const int w, const int clear_border,
-                    int32_t* __restrict__ blockcnt, int32_t* __restrict__ rootbuf, const int nblk, const int vec) {
+ccl_roots_kernel(int32_t* __restrict__ L, const int32_t* __restrict__ rootlist, const int32_t* __restrict__ rootcnt,
+                 uint32_t* __restrict__ rootbits, const int64_t npx, const int64_t words) {
+  const int64_t img = blockIdx.y;
+  const int n = rootcnt[img];
+  int32_t* Lp = L + img * npx;
+  const int32_t* list = rootlist + img * npx;
+  uint32_t* bits = rootbits + img * words;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const int t = list[i];
+    const int g = uf_find(Lp, t);
+    if (g == t)
+      atomicOr(bits + (t >> 5), 1u << (t & 31));
+    else
+      Lp[t] = g;  // racing readers see the old parent or g: both are ancestors
+  }
+}
+
+// components with a pixel on the image border lose their root bit (clear_border)
+__global__ void __launch_bounds__(256)
+ccl_border_kernel(const int32_t* __restrict__ L, uint32_t* __restrict__ rootbits, const int h, const int w,
+                  const int64_t words) {
+  const int64_t img = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int n_border = 2 * w + 2 * h;
+  if (t >= n_border) return;
+  int x, y;
+  if (t < w) { y = 0; x = t; }
+  else if (t < 2 * w) { y = h - 1; x = t - w; }
+  else if (t < 2 * w + h) { x = 0; y = t - 2 * w; }
+  else { x = w - 1; y = t - 2 * w - h; }
+  const int32_t* Lp = L + img * (int64_t)h * w;
+  const int r = Lp[y * w + x];
+  if (r < 0) return;
+  const int g = uf_find(Lp, r);
+  atomicAnd(rootbits + img * words + (g >> 5), ~(1u << (g & 31)));
+}
+
+// ---------------------------------------------------------------- D. numbering
+// prefix[i] = number of root bits in words [0, i) of the plane; counts[img] = their total.  Two
+// levels: 1024-word blocks scanned by one CTA each (coalesced 16-byte loads), then one CTA per plane
+// scans the block totals; ccl_gid_kernel adds the two.
+constexpr int RANK_BLOCK = 1024;  // words per CTA (256 threads x 4)
+
+__global__ void __launch_bounds__(256)
+ccl_rank_block_kernel(const uint32_t* __restrict__ rootbits, int32_t* __restrict__ prefix, int32_t* __restrict__ blocksum,
+                      const int64_t words, const int nblocks) {
   __shared__ int s_warp[32];
   __shared__ int s_total;
   const int64_t img = blockIdx.y;
-  const int npx = h * w;
-  int32_t* Lp = L + img * (int64_t)npx;
-  int32_t* ap = aux + img * (int64_t)npx;
-  const int p0 = (blockIdx.x * 256 + threadIdx.x) * 4;
-  int lab[4] = {-1, -1, -1, -1};
-  if (vec && p0 + 3 < npx) {
-    const int4 q = *reinterpret_cast<const int4*>(Lp + p0);
-    lab[0] = q.x; lab[1] = q.y; lab[2] = q.z; lab[3] = q.w;
-  } else {
+  const uint32_t* bits = rootbits + img * words;
+  int32_t* pre = prefix + img * words;
+  const int64_t i0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  int c[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (p0 + i < npx) lab[i] = Lp[p0 + i];
-  }
-  int n_roots = 0;
-  int roots[4];
+  for (int k = 0; k < 4; ++k) c[k] = (i0 + k < words) ? __popc(bits[i0 + k]) : 0;
+  int run = block_excl_scan(c[0] + c[1] + c[2] + c[3], s_warp, &s_total);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (lab[i] >= 0) {
-      const int p = p0 + i;
-      const int r = (lab[i] == p) ? p : uf_find(Lp, lab[i]);
-      lab[i] = r;
-      if (r == p) roots[n_roots++] = p;
-      if (clear_border) {
-        const int y = p / w, x = p - y * w;
-        if (y == 0 || x == 0 || y == h - 1 || x == w - 1) ap[r] = -1;
-      }
-    }
+  for (int k = 0; k < 4; ++k) {
+    if (i0 + k < words) pre[i0 + k] = run;
+    run += c[k];
   }
-  if (vec && p0 + 3 < npx) {
-    *reinterpret_cast<int4*>(Lp + p0) = make_int4(lab[0], lab[1], lab[2], lab[3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (p0 + i < npx) Lp[p0 + i] = lab[i];
-  }
-  const int off = block_excl_scan(n_roots, s_warp, &s_total);
-  int32_t* dst = rootbuf + (img * nblk + blockIdx.x) * (int64_t)ROOT_CAP + off;
-  for (int i = 0; i < n_roots; ++i) dst[i] = roots[i];
-  if (threadIdx.x == 0) blockcnt[img * nblk + blockIdx.x] = s_total;
+  if (threadIdx.x == 0) blocksum[img * nblocks + blockIdx.x] = s_total;
 }
 
-// ---------------------------------------------------------------- D. numbering (one CTA per plane)
-// MODE 0: aux[root] = consecutive id of the surviving roots in raster order (0 for removed),
-//         counts[img] = number of survivors.
-// MODE 1: integer masks — present[value of root] = 1 for surviving roots (ranked later).
-template <int MODE>
 __global__ void __launch_bounds__(1024)
-ccl_number_kernel(int32_t* __restrict__ aux, const int32_t* __restrict__ blockcnt, const int32_t* __restrict__ rootbuf,
-                  const int nblk, const int64_t npx, int32_t* __restrict__ counts, const int32_t* __restrict__ in,
-                  const int64_t in_stride, int32_t* __restrict__ present, const int64_t nval) {
+ccl_rank_top_kernel(int32_t* __restrict__ blocksum, const int nblocks, int32_t* __restrict__ counts) {
   __shared__ int s_warp[32];
   __shared__ int s_total;
   const int64_t img = blockIdx.x;
-  int32_t* ap = aux + img * npx;
-  const int32_t* bc = blockcnt + img * nblk;
-  const int32_t* rb = rootbuf + img * nblk * (int64_t)ROOT_CAP;
-  if (MODE == 1) {
-    const int32_t* lab = in + img * in_stride;
-    for (int b = threadIdx.x; b < nblk; b += 1024) {
-      const int c = bc[b];
-      for (int i = 0; i < c; ++i) {
-        const int r = rb[(int64_t)b * ROOT_CAP + i];
-        if (ap[r] != -1) {
-          const int v = lab[r];
-          if (v > 0 && v < nval) present[img * nval + v] = 1;
-        }
-      }
-    }
-    return;
-  }
+  int32_t* bs = blocksum + img * nblocks;
   int carry = 0;
-  for (int base = 0; base < nblk; base += 1024) {
-    const int b = base + threadIdx.x;
-    int surv = 0;
-    if (b < nblk) {
-      const int c = bc[b];
-      for (int i = 0; i < c; ++i) surv += (ap[rb[(int64_t)b * ROOT_CAP + i]] != -1);
-    }
-    int k = carry + block_excl_scan(surv, s_warp, &s_total);
-    if (b < nblk) {
-      const int c = bc[b];
-      for (int i = 0; i < c; ++i) {
-        const int r = rb[(int64_t)b * ROOT_CAP + i];
-        ap[r] = (ap[r] != -1) ? ++k : 0;
-      }
-    }
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int x = i < nblocks ? bs[i] : 0;
+    const int ex = block_excl_scan(x, s_warp, &s_total);
+    if (i < nblocks) bs[i] = carry + ex;
     carry += s_total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) counts[img] = carry;
+  if (counts != nullptr && threadIdx.x == 0) counts[img] = carry;
 }
 
-// ---------------------------------------------------------------- E. final gather (in place)
+// integer masks: the value of every surviving component is present
 __global__ void __launch_bounds__(256)
-ccl_final_kernel(int32_t* __restrict__ L, const int32_t* __restrict__ aux, const int64_t npx, const int vec) {
+ccl_present_kernel(const int32_t* __restrict__ in, const int64_t in_stride, const int32_t* __restrict__ rootlist,
+                   const int32_t* __restrict__ rootcnt, const uint32_t* __restrict__ rootbits, const int64_t npx,
+                   const int64_t words, int32_t* __restrict__ present, const int64_t nval) {
+  const int64_t img = blockIdx.y;
+  const int n = rootcnt[img];
+  const int32_t* list = rootlist + img * npx;
+  const uint32_t* bits = rootbits + img * words;
+  const int32_t* lab = in + img * in_stride;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const int t = list[i];
+    if ((bits[t >> 5] >> (t & 31)) & 1u) {
+      const int v = lab[t];
+      if (v > 0 && v < nval) present[img * nval + v] = 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- E. ids of the tile roots, final gather
+// gid[t] for every listed tile root t: the consecutive id of its component (MODE 0; 0 = removed), or
+// 1 / -1 = survived / removed (MODE 1, integer masks).  gid is a separate array, so the in-place
+// pixel pass below never reads an entry another thread rewrites.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+ccl_gid_kernel(const int32_t* __restrict__ L, const int32_t* __restrict__ rootlist, const int32_t* __restrict__ rootcnt,
+               const uint32_t* __restrict__ rootbits, const int32_t* __restrict__ prefix,
+               const int32_t* __restrict__ blocksum, const int nblocks, int32_t* __restrict__ gid, const int64_t npx,
+               const int64_t words) {
+  const int64_t img = blockIdx.y;
+  const int n = rootcnt[img];
+  const int32_t* Lp = L + img * npx;
+  const int32_t* list = rootlist + img * npx;
+  const uint32_t* bits = rootbits + img * words;
+  const int32_t* pre = prefix + img * words;
+  int32_t* gp = gid + img * npx;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const int t = list[i];
+    const int g = Lp[t];  // flattened by ccl_roots_kernel (a global root points at itself)
+    const uint32_t wd = bits[g >> 5], bit = 1u << (g & 31);
+    const bool alive = (wd & bit) != 0;
+    if (MODE == 0)
+      gp[t] = alive ? blocksum[img * nblocks + (g >> 5) / RANK_BLOCK] + pre[g >> 5] + __popc(wd & (bit - 1u)) + 1 : 0;
+    else
+      gp[t] = alive ? 1 : -1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_final_kernel(int32_t* __restrict__ L, const int32_t* __restrict__ gid, const int64_t npx, const int vec) {
   const int64_t img = blockIdx.y;
   int32_t* Lp = L + img * npx;
-  const int32_t* ap = aux + img * npx;
+  const int32_t* gp = gid + img * npx;
   const int64_t step = (int64_t)gridDim.x * 256 * 4;
   for (int64_t p0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; p0 < npx; p0 += step) {
     if (vec && p0 + 3 < npx) {
       int4 q = *reinterpret_cast<const int4*>(Lp + p0);
-      q.x = q.x >= 0 ? __ldg(ap + q.x) : 0;
-      q.y = q.y >= 0 ? __ldg(ap + q.y) : 0;
-      q.z = q.z >= 0 ? __ldg(ap + q.z) : 0;
-      q.w = q.w >= 0 ? __ldg(ap + q.w) : 0;
+      if ((q.x & q.y & q.z & q.w) < 0) {  // four background pixels
+        *reinterpret_cast<int4*>(Lp + p0) = make_int4(0, 0, 0, 0);
+        continue;
+      }
+      q.x = q.x >= 0 ? __ldg(gp + q.x) : 0;
+      q.y = q.y >= 0 ? __ldg(gp + q.y) : 0;
+      q.z = q.z >= 0 ? __ldg(gp + q.z) : 0;
+      q.w = q.w >= 0 ? __ldg(gp + q.w) : 0;
       *reinterpret_cast<int4*>(Lp + p0) = q;
     } else {
       for (int i = 0; i < 4 && p0 + i < npx; ++i) {
         const int r = Lp[p0 + i];
-        Lp[p0 + i] = r >= 0 ? ap[r] : 0;
+        Lp[p0 + i] = r >= 0 ? gp[r] : 0;
       }
     }
   }
@@ -442,36 +598,54 @@ scan_kernel(int32_t* __restrict__ vals, int len, int32_t* __restrict__ counts, i
 static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
 
 struct LabelScratch {
-  int32_t* aux;
-  int32_t* blockcnt;
-  int32_t* rootbuf;
+  int32_t* gid;       // npx per image: id / survival flag of the tile roots (sparse)
+  int32_t* rootlist;  // npx per image: the tile roots (capacity: every pixel a root)
+  int32_t* rootcnt;   // 1 per image
+  uint32_t* rootbits; // one bit per pixel and image: "is a surviving global root"
+  int32_t* prefix;    // one int per bitmap word (prefix inside its 1024-word block)
+  int32_t* blocksum;  // one int per 1024-word block (exclusive prefix over the plane after ccl_rank_top_kernel)
+  int nblocks;
   int32_t* present;
-  int nblk;
+  int64_t words;
+  size_t zero_bytes;  // rootcnt + rootbits are contiguous and cleared per call
   size_t total;
 };
 
 static LabelScratch label_scratch_layout(void* base, int64_t n_img, int64_t h, int64_t w, int64_t max_value) {
   LabelScratch s;
   const int64_t npx = h * w;
-  s.nblk = (int)ceil_div(npx, CBLK);
+  s.words = ceil_div(npx, 32);
   size_t off = 0;
-  s.aux = (int32_t*)((char*)base + off);
+  s.gid = (int32_t*)((char*)base + off);
   off += align256((size_t)n_img * npx * sizeof(int32_t));
-  s.blockcnt = (int32_t*)((char*)base + off);
-  off += align256((size_t)n_img * s.nblk * sizeof(int32_t));
-  s.rootbuf = (int32_t*)((char*)base + off);
-  off += align256((size_t)n_img * s.nblk * ROOT_CAP * sizeof(int32_t));
+  s.rootlist = (int32_t*)((char*)base + off);
+  off += align256((size_t)n_img * npx * sizeof(int32_t));
+  s.rootcnt = (int32_t*)((char*)base + off);
+  const size_t zero_start = off;
+  off += align256((size_t)n_img * sizeof(int32_t));
+  s.rootbits = (uint32_t*)((char*)base + off);
+  off += align256((size_t)n_img * s.words * sizeof(uint32_t));
+  s.zero_bytes = off - zero_start;
+  s.prefix = (int32_t*)((char*)base + off);
+  off += align256((size_t)n_img * s.words * sizeof(int32_t));
+  s.nblocks = (int)ceil_div(s.words, RANK_BLOCK);
+  s.blocksum = (int32_t*)((char*)base + off);
+  off += align256((size_t)n_img * s.nblocks * sizeof(int32_t));
   s.present = (int32_t*)((char*)base + off);
   off += align256((size_t)n_img * (size_t)(max_value + 1) * sizeof(int32_t));
   s.total = off;
   return s;
 }
 
+// tile -> seams -> roots (-> border): afterwards L[p] = tile root of p (or -1), L[tile root] = global
+// root, and rootbits marks the surviving global roots
 template <int KIND>
 static int ccl_core(const void* in, int64_t in_stride, const double* thresholds, int64_t n_img, int h, int w,
-                    int clear_border, int32_t* L, const LabelScratch& s, int vec, cudaStream_t st) {
+                    int clear_border, int32_t* L, const LabelScratch& s, cudaStream_t st) {
+  const int64_t npx = (int64_t)h * w;
+  AMT_CUDA_TRY(cudaMemsetAsync(s.rootcnt, 0, s.zero_bytes, st));
   dim3 tgrid((unsigned)ceil_div(w, TW), (unsigned)ceil_div(h, TH), (unsigned)n_img);
-  ccl_tile_kernel<KIND><<<tgrid, 256, 0, st>>>(in, in_stride, thresholds, L, s.aux, h, w);
+  ccl_tile_kernel<KIND><<<tgrid, 256, 0, st>>>(in, in_stride, thresholds, L, s.rootlist, s.rootcnt, h, w);
   AMT_LAUNCH_CHECK();
   const int n_hseams = (int)ceil_div(h, TH) - 1, n_vseams = (int)ceil_div(w, TW) - 1;
   const int64_t seam_px = (int64_t)n_hseams * w + (int64_t)n_vseams * 2 * h;
@@ -480,9 +654,13 @@ static int ccl_core(const void* in, int64_t in_stride, const double* thresholds,
                                                                                                  n_hseams, n_vseams);
     AMT_LAUNCH_CHECK();
   }
-  ccl_compress_kernel<<<dim3((unsigned)s.nblk, (unsigned)n_img), 256, 0, st>>>(L, s.aux, h, w, clear_border, s.blockcnt,
-                                                                               s.rootbuf, s.nblk, vec);
+  ccl_roots_kernel<<<dim3(64, (unsigned)n_img), 256, 0, st>>>(L, s.rootlist, s.rootcnt, s.rootbits, npx, s.words);
   AMT_LAUNCH_CHECK();
+  if (clear_border) {
+    ccl_border_kernel<<<dim3((unsigned)ceil_div(2 * (int64_t)w + 2 * h, 256), (unsigned)n_img), 256, 0, st>>>(
+        L, s.rootbits, h, w, s.words);
+    AMT_LAUNCH_CHECK();
+  }
   return AMT_OK;
 }
 
@@ -504,14 +682,18 @@ int label_launch(const void* in, int in_kind, int64_t in_stride, const double* t
   if (sb > cap) sb = cap;
   if (sb < 1) sb = 1;
   const dim3 sgrid((unsigned)sb, (unsigned)n_img);
+  const dim3 rgrid(64, (unsigned)n_img);
 
   if (in_kind == 2) {
     const int64_t nval = max_value + 1;
     AMT_CUDA_TRY(cudaMemsetAsync(s.present, 0, (size_t)n_img * nval * sizeof(int32_t), st));
     if (clear_border) {
-      AMT_TRY(ccl_core<2>(in, in_stride, nullptr, n_img, (int)h, (int)w, 1, labels_out, s, vec, st));
-      ccl_number_kernel<1><<<(unsigned)n_img, 1024, 0, st>>>(s.aux, s.blockcnt, s.rootbuf, s.nblk, npx, counts,
-                                                             (const int32_t*)in, in_stride, s.present, nval);
+      AMT_TRY(ccl_core<2>(in, in_stride, nullptr, n_img, (int)h, (int)w, 1, labels_out, s, st));
+      ccl_present_kernel<<<rgrid, 256, 0, st>>>((const int32_t*)in, in_stride, s.rootlist, s.rootcnt, s.rootbits, npx,
+                                                s.words, s.present, nval);
+      AMT_LAUNCH_CHECK();
+      ccl_gid_kernel<1><<<rgrid, 256, 0, st>>>(labels_out, s.rootlist, s.rootcnt, s.rootbits, s.prefix, s.blocksum,
+                                               s.nblocks, s.gid, npx, s.words);
       AMT_LAUNCH_CHECK();
     } else {
       present_mark_kernel<<<sgrid, 256, 0, st>>>((const int32_t*)in, in_stride, npx, s.present, nval);
@@ -519,19 +701,24 @@ int label_launch(const void* in, int in_kind, int64_t in_stride, const double* t
     }
     scan_kernel<<<(unsigned)n_img, 1024, 0, st>>>(s.present, (int)nval, counts, 1);
     AMT_LAUNCH_CHECK();
-    relabel_final_kernel<<<sgrid, 256, 0, st>>>((const int32_t*)in, in_stride, labels_out, s.aux, npx, s.present, nval,
+    relabel_final_kernel<<<sgrid, 256, 0, st>>>((const int32_t*)in, in_stride, labels_out, s.gid, npx, s.present, nval,
                                                 clear_border, vec && (in_stride % 4 == 0) && (((uintptr_t)in) % 16 == 0));
     AMT_LAUNCH_CHECK();
     return AMT_OK;
   }
   if (in_kind == 0)
-    AMT_TRY(ccl_core<0>(in, in_stride, nullptr, n_img, (int)h, (int)w, clear_border, labels_out, s, vec, st));
+    AMT_TRY(ccl_core<0>(in, in_stride, nullptr, n_img, (int)h, (int)w, clear_border, labels_out, s, st));
   else
-    AMT_TRY(ccl_core<1>(in, in_stride, thresholds, n_img, (int)h, (int)w, clear_border, labels_out, s, vec, st));
-  ccl_number_kernel<0><<<(unsigned)n_img, 1024, 0, st>>>(s.aux, s.blockcnt, s.rootbuf, s.nblk, npx, counts, nullptr, 0,
-                                                         nullptr, 0);
+    AMT_TRY(ccl_core<1>(in, in_stride, thresholds, n_img, (int)h, (int)w, clear_border, labels_out, s, st));
+  ccl_rank_block_kernel<<<dim3((unsigned)s.nblocks, (unsigned)n_img), 256, 0, st>>>(s.rootbits, s.prefix, s.blocksum,
+                                                                                    s.words, s.nblocks);
   AMT_LAUNCH_CHECK();
-  ccl_final_kernel<<<sgrid, 256, 0, st>>>(labels_out, s.aux, npx, vec);
+  ccl_rank_top_kernel<<<(unsigned)n_img, 1024, 0, st>>>(s.blocksum, s.nblocks, counts);
+  AMT_LAUNCH_CHECK();
+  ccl_gid_kernel<0><<<rgrid, 256, 0, st>>>(labels_out, s.rootlist, s.rootcnt, s.rootbits, s.prefix, s.blocksum, s.nblocks,
+                                           s.gid, npx, s.words);
+  AMT_LAUNCH_CHECK();
+  ccl_final_kernel<<<sgrid, 256, 0, st>>>(labels_out, s.gid, npx, vec);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
