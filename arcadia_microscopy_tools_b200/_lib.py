@@ -30,6 +30,17 @@ def acc_fields(n_channels: int) -> int:
     return AMT_ACC_BASE + AMT_ACC_PER_CHANNEL * n_channels
 
 
+AMT_ACC3D_BASE, AMT_TABLE3D_BASE = 16, 16
+
+
+def acc3d_fields(n_channels: int) -> int:
+    return AMT_ACC3D_BASE + AMT_ACC_PER_CHANNEL * n_channels
+
+
+def table3d_cols(n_channels: int) -> int:
+    return AMT_TABLE3D_BASE + AMT_TABLE_PER_CHANNEL * n_channels
+
+
 def table_cols(n_channels: int) -> int:
     return AMT_TABLE_BASE + AMT_TABLE_PER_CHANNEL * n_channels
 
@@ -122,6 +133,8 @@ SIGNATURES: dict[str, tuple] = {
     "amt_label": (_i, [_p, _i, _p, _i64, _i64, _i64, _i64, _i, _p, _p, _p, _sz, _p]),
     "amt_region_reduce": (_i, [_p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),
     "amt_region_finalize": (_i, [_p, _p, _i, _i64, _i64, _p, _p]),
+    "amt_region_reduce3d": (_i, [_p, _p, _i, _i64, _i64, _i64, _i64, _i64, _p, _p]),
+    "amt_region_finalize3d": (_i, [_p, _i64, _i, _i64, _p, _p]),
     "amt_region_shape_scratch_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "amt_region_shape": (_i, [_p, _p, _i, _p, _i64, _i64, _i64, _i64, _p, _p, _sz, _p]),
     "amt_executor_create": (_i, [C.POINTER(FovConfig), C.POINTER(_d), _i, C.POINTER(_d), _i, C.POINTER(_p)]),

@@ -232,6 +232,21 @@ int amt_region_reduce(const int32_t* labels, const uint16_t* channels, int n_cha
                       int64_t max_labels, uint64_t* acc, amt_stream_t stream);
 int amt_region_finalize(const uint64_t* acc, const int32_t* counts, int n_channels, int64_t n_img,
                         int64_t max_labels, double* table, amt_stream_t stream);
+/* 3-D label volumes (z-stacks; extension, SegmentationMask itself is 2-D only: masks.py:171-172).
+ * labels: d*h*w int32 (1..K consecutive, 0 = background); channels: C volumes of d*h*w uint16,
+ * chan_stride elements apart.  acc: AMT_ACC3D_FIELDS(C) * max_labels uint64 (initialised by the call).
+ * table (column-major, AMT_TABLE3D_COLS(C) x max_labels float64): label, area, bbox-0..5 (half-open,
+ * z y x), centroid-0..2, inertia_tensor_eigvals-0..2, axis_major_length, axis_minor_length, then per
+ * channel sum, mean, max, min, std -- skimage.measure.regionprops_table's 3-D definitions. */
+#define AMT_ACC3D_BASE 16
+#define AMT_ACC3D_FIELDS(C) (AMT_ACC3D_BASE + AMT_ACC_PER_CHANNEL * (C))
+#define AMT_TABLE3D_BASE 16
+#define AMT_TABLE3D_COLS(C) (AMT_TABLE3D_BASE + AMT_TABLE_PER_CHANNEL * (C))
+int amt_region_reduce3d(const int32_t* labels, const uint16_t* channels, int n_channels, int64_t chan_stride,
+                        int64_t d, int64_t h, int64_t w, int64_t max_labels, uint64_t* acc, amt_stream_t stream);
+int amt_region_finalize3d(const uint64_t* acc, int64_t count, int n_channels, int64_t max_labels, double* table,
+                          amt_stream_t stream);
+
 /* perimeter (4-neighbourhood, skimage weights) and convex-hull pixel count per label.
  * ref: masks.py:15-28 defaults 'perimeter', 'area_convex', 'solidity'. scratch from
  * amt_region_shape_scratch_bytes. */

@@ -276,3 +276,43 @@ def regionprops_table(label_image: np.ndarray, intensity_image=None, properties=
             else:
                 out[prop][row] = _region_scalar(prop, ctx)
     return out
+
+
+def regionprops_table_3d(label_volume: np.ndarray, intensity_volumes: dict | None = None) -> dict:
+    """3-D restatement (BASELINE config 4; no reference entry point, SURVEY.md note N3) of
+    ``regionprops_table(label_volume, intensity_image=..., properties=(label, area, bbox, centroid,
+    inertia_tensor_eigvals, axis_major_length, axis_minor_length, intensity_*))``: same per-region
+    code path as the 2-D properties above (find_objects crop, local-coordinate central moments,
+    inertia tensor, ``eigvalsh``) with skimage's 3-D axis-length formulas."""
+    intensity_volumes = intensity_volumes or {}
+    objects = ndi.find_objects(label_volume)
+    rows = []
+    for i, sl in enumerate(objects):
+        if sl is None:
+            continue
+        label = i + 1
+        crop = label_volume[sl] == label
+        area = float(np.sum(crop))
+        coords = np.argwhere(crop)
+        local_centroid = coords.mean(axis=0)
+        mu = moments_central(crop.astype(np.uint8), local_centroid, order=2)
+        ev = inertia_tensor_eigvals(inertia_tensor(mu, 3))
+        row = {"label": label, "area": area}
+        for d in range(3):
+            row[f"bbox-{d}"] = sl[d].start
+            row[f"bbox-{d + 3}"] = sl[d].stop
+            row[f"centroid-{d}"] = sl[d].start + local_centroid[d]
+            row[f"inertia_tensor_eigvals-{d}"] = ev[d]
+        row["axis_major_length"] = math.sqrt(10 * (ev[0] + ev[1] - ev[2]))
+        row["axis_minor_length"] = math.sqrt(10 * max(-ev[0] + ev[1] + ev[2], 0))
+        for name, vol in intensity_volumes.items():
+            vals = vol[sl][crop]
+            row[f"intensity_sum_{name}"] = int(vals.sum(dtype=np.uint64))
+            row[f"intensity_mean_{name}"] = float(np.mean(vals))
+            row[f"intensity_max_{name}"] = float(np.max(vals))
+            row[f"intensity_min_{name}"] = float(np.min(vals))
+            row[f"intensity_std_{name}"] = float(np.std(vals))
+        rows.append(row)
+    if not rows:
+        return {}
+    return {k: np.array([r[k] for r in rows]) for k in rows[0]}
