@@ -283,6 +283,45 @@ def otsu_threshold(x2d, mm=None):
     return thr, mm
 
 
+def plane_histograms(x2d, mm=None):
+    """The histogram skimage's histogram-based thresholds start from, per plane, on the device:
+    float64 planes -> 256 uniform bins over [min, max] (np.histogram semantics, ``amt_hist256_f64``),
+    uint16 planes -> exact per-value counts (``amt_hist_u16``).  Returns ``[(counts int64, centers)]``
+    on the host: the scalar scans over these <= 65536 bins are the host-side plan step (NumPy, in
+    skimage's own dtypes); every per-pixel pass stays on the GPU."""
+    torch = torch_mod()
+    lib = _lib.load()
+    n_img, n = x2d.shape
+    if mm is None:
+        mm = minmax_keys(x2d)
+    out = []
+    if dtype_code(x2d) == AMT_F64:
+        hist = torch.empty((n_img, 256), dtype=torch.int32, device=x2d.device)
+        check(lib.amt_hist256_f64(ptr(x2d), n_img, n, ptr(mm), ptr(hist), stream_ptr()), "amt_hist256_f64")
+        h = to_host(hist).astype(np.int64)
+        mnmx = minmax_values(mm, True)
+        for i in range(n_img):
+            first, last = float(mnmx[i, 0]), float(mnmx[i, 1])
+            if first == last:
+                first, last = first - 0.5, last + 0.5
+            edges = np.linspace(first, last, 257, endpoint=True, dtype=np.float64)
+            out.append((h[i], (edges[:-1] + edges[1:]) / 2.0))
+    else:
+        hist = torch.empty((n_img, 65536), dtype=torch.int32, device=x2d.device)
+        check(lib.amt_hist_u16(ptr(x2d), n_img, n, ptr(hist), stream_ptr()), "amt_hist_u16")
+        h = to_host(hist).astype(np.int64)
+        mnmx = minmax_values(mm, False)
+        for i in range(n_img):
+            lo, hi = int(mnmx[i, 0]), int(mnmx[i, 1])
+            out.append((h[i, lo : hi + 1], np.arange(lo, hi + 1)))
+    return out
+
+
+def plane_sums_u16(x2d) -> np.ndarray:
+    """Exact integer sum of every uint16 plane (from the device histogram) -> int64 per plane."""
+    return np.array([int((c * v).sum()) for c, v in plane_histograms(x2d)], dtype=np.int64)
+
+
 def threshold_gt(x2d, thr):
     torch = torch_mod()
     n_img, n = x2d.shape

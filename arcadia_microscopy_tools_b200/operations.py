@@ -23,6 +23,9 @@ from . import _gpu, _lib
 _THRESHOLD_METHODS = ("otsu", "li", "yen", "isodata", "mean", "minimum", "triangle", "local", "niblack", "sauvola")
 
 
+_GPU_THRESHOLD_METHODS = ("otsu", "isodata", "yen", "mean")
+
+
 def _device_op(func):
     func.__amt_device_op__ = True
     return func
@@ -214,6 +217,56 @@ def crop_to_center(intensities, output_shape: tuple[int, int], *, _batched: bool
 crop_to_center.__amt_device_op__ = True  # type: ignore[attr-defined]
 
 
+def _isodata_from_histogram(counts: np.ndarray, centers: np.ndarray):
+    """skimage ``threshold_isodata`` scan (float32 counts, float64 means), first threshold."""
+    counts = counts.astype("float32", copy=False)
+    csuml = np.cumsum(counts)
+    csumh = csuml[-1] - csuml
+    csum_intensity = np.cumsum(counts * centers)
+    lower = csum_intensity[:-1] / csuml[:-1]
+    higher = (csum_intensity[-1] - csum_intensity[:-1]) / csumh[:-1]
+    all_mean = (lower + higher) / 2.0
+    distances = all_mean - centers[:-1]
+    return centers[:-1][(distances >= 0) & (distances < centers[1] - centers[0])][0]
+
+
+def _yen_from_histogram(counts: np.ndarray, centers: np.ndarray):
+    """skimage ``threshold_yen`` scan over the normalised float32 histogram."""
+    pmf = counts.astype("float32", copy=False) / counts.sum()
+    p1 = np.cumsum(pmf)
+    p1_sq = np.cumsum(pmf**2)
+    p2_sq = np.cumsum(pmf[::-1] ** 2)[::-1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        crit = np.log(((p1_sq[:-1] * p2_sq[1:]) ** -1) * (p1[:-1] * (1.0 - p1[:-1])) ** 2)
+    return centers[crit.argmax()]
+
+
+def _apply_histogram_threshold(intensities, method: str, batched: bool):
+    """isodata / yen / mean: the per-pixel passes (min/max, histogram, comparison) run on the GPU;
+    the scan over the <= 65536 histogram bins is skimage's own NumPy arithmetic on the host
+    (ref: ``operations.py:185-196`` -> ``ski.filters.threshold_*`` [3p])."""
+    t, np_dtype, was_numpy = _prepare(intensities)
+    planes = _slices(t, batched)
+    hists = _gpu.plane_histograms(planes)
+    thr = np.empty(planes.shape[0], dtype=np.float64)
+    for i, (counts, centers) in enumerate(hists):
+        if len(centers) == 1 or counts.sum() == counts.max():  # constant plane: nothing is above it
+            thr[i] = float(centers[int(np.argmax(counts))])
+        elif method == "isodata":
+            thr[i] = float(_isodata_from_histogram(counts, centers))
+        elif method == "yen":
+            thr[i] = float(_yen_from_histogram(counts, centers))
+        elif np_dtype.kind in "iu" and planes.dtype != _gpu.torch_mod().float64:
+            # np.mean of an integer image: exact integer sum (float64 accumulation is exact below 2**53)
+            thr[i] = float(np.float64(int((counts * centers).sum())) / np.float64(planes.shape[1]))
+        else:
+            raise NotImplementedError("method 'mean' is implemented for uint8 / uint16 images only "
+                                      "(NumPy's pairwise float summation is not reproduced on the GPU)")
+    d_thr = _gpu.torch_mod().from_numpy(thr).to(planes.device)
+    mask = _gpu.threshold_gt(planes, d_thr).reshape(t.shape).view(_gpu.torch_mod().bool)
+    return _gpu.to_host(mask) if was_numpy else mask
+
+
 @_device_op
 def apply_threshold(
     intensities,
@@ -225,14 +278,14 @@ def apply_threshold(
     """Binary image ``intensities > threshold`` (ref: ``operations.py:135-216``).
 
     Empty or constant input -> all False (checked before the method name, as in the
-    reference).  Only Otsu runs on the B200 path (``skimage.filters.threshold_otsu``: exact
-    per-value histogram for integer images, 256 uniform bins for float images); the other nine
-    scikit-image methods the reference lists are out of scope and raise NotImplementedError.
+    reference).  ``otsu``, ``isodata``, ``yen`` and ``mean`` run on the B200 path (skimage's
+    histogram: exact per-value counts for integer images, 256 uniform bins for float images); the
+    other six scikit-image methods the reference lists raise NotImplementedError.
     """
     if not _gpu.is_device_array(intensities) and np.asarray(intensities).size == 0:
         return np.zeros_like(np.asarray(intensities), dtype=bool)
     method_lower = method.lower()
-    if method_lower != "otsu":
+    if method_lower not in _GPU_THRESHOLD_METHODS:
         # the reference returns all-False for a constant image before it looks at the method
         host = _gpu.to_host(intensities) if _gpu.is_device_array(intensities) else np.asarray(intensities)
         if host.min() == host.max():
@@ -243,8 +296,11 @@ def apply_threshold(
                 f"Supported methods: {', '.join(_THRESHOLD_METHODS)}"
             )
         raise NotImplementedError(
-            f"Thresholding method '{method}' is outside the B200 hot path (only 'otsu' is implemented)"
+            f"Thresholding method '{method}' is outside the B200 hot path "
+            f"(implemented: {', '.join(_GPU_THRESHOLD_METHODS)})"
         )
+    if method_lower != "otsu":
+        return _apply_histogram_threshold(intensities, method_lower, _batched)
     t, _, was_numpy = _prepare(intensities)
     planes = _slices(t, _batched)
     # a constant plane gets threshold == its value, so nothing is above it (all False)

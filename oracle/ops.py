@@ -55,14 +55,16 @@ def subtract_background_dog(intensities, low_sigma=0.6, high_sigma=16.0, percent
 
 
 def apply_threshold(intensities, method="otsu"):
-    """ref: operations.py:135-216 (Otsu only; the other nine methods are out of scope)."""
+    """ref: operations.py:135-216 (otsu, isodata, yen, mean; the other six methods are out of scope)."""
     if intensities.size == 0:
         return np.zeros_like(intensities, dtype=bool)
     if intensities.min() == intensities.max():
         return np.zeros_like(intensities, dtype=bool)
-    if method.lower() != "otsu":
+    funcs = {"otsu": threshold.threshold_otsu, "isodata": threshold.threshold_isodata,
+             "yen": threshold.threshold_yen, "mean": threshold.threshold_mean}
+    if method.lower() not in funcs:
         raise ValueError(f"Unsupported thresholding method: '{method}'.")
-    return intensities > threshold.threshold_otsu(intensities)
+    return intensities > funcs[method.lower()](intensities)
 
 
 def process_mask(mask_image, remove_edge_cells):

@@ -82,3 +82,57 @@ def threshold_otsu(image: np.ndarray, nbins: int = 256):
     else:
         hist, centers = histogram_float_256(image, nbins)
     return otsu_from_histogram(hist, centers)
+
+
+# ---- further histogram-based methods of the reference's ``apply_threshold`` (operations.py:185-196).
+# scikit-image is not installable here: these restate skimage 0.25.2 ``filters/thresholding.py`` from
+# the published source (parity unpinned beyond this restatement).
+def _image_histogram(image: np.ndarray, nbins: int = 256):
+    image = np.asarray(image)
+    if np.issubdtype(image.dtype, np.integer):
+        return histogram_int(image)
+    return histogram_float_256(image, nbins)
+
+
+def isodata_from_histogram(hist: np.ndarray, centers: np.ndarray):
+    """``threshold_isodata``: the first bin centre t with 0 <= (mean(<=t) + mean(>t))/2 - t < bin width."""
+    if len(centers) == 1:
+        return centers[0]
+    counts = np.asarray(hist).astype("float32", copy=False)
+    csuml = np.cumsum(counts)
+    csumh = csuml[-1] - csuml
+    intensity_sum = counts * centers
+    csum_intensity = np.cumsum(intensity_sum)
+    lower = csum_intensity[:-1] / csuml[:-1]
+    higher = (csum_intensity[-1] - csum_intensity[:-1]) / csumh[:-1]
+    all_mean = (lower + higher) / 2.0
+    bin_width = centers[1] - centers[0]
+    distances = all_mean - centers[:-1]
+    thresholds = centers[:-1][(distances >= 0) & (distances < bin_width)]
+    return thresholds[0]
+
+
+def yen_from_histogram(hist: np.ndarray, centers: np.ndarray):
+    """``threshold_yen``: maximum of Yen's criterion over the normalised float32 histogram."""
+    if len(centers) == 1:
+        return centers[0]
+    counts = np.asarray(hist)
+    pmf = counts.astype("float32", copy=False) / counts.sum()
+    P1 = np.cumsum(pmf)
+    P1_sq = np.cumsum(pmf**2)
+    P2_sq = np.cumsum(pmf[::-1] ** 2)[::-1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        crit = np.log(((P1_sq[:-1] * P2_sq[1:]) ** -1) * (P1[:-1] * (1.0 - P1[:-1])) ** 2)
+    return centers[crit.argmax()]
+
+
+def threshold_isodata(image: np.ndarray, nbins: int = 256):
+    return isodata_from_histogram(*_image_histogram(image, nbins))
+
+
+def threshold_yen(image: np.ndarray, nbins: int = 256):
+    return yen_from_histogram(*_image_histogram(image, nbins))
+
+
+def threshold_mean(image: np.ndarray):
+    return np.mean(image)

@@ -280,3 +280,22 @@ def test_nd2_fast_path_matches_host_reader(tmp_path):
         got = _gpu.to_host(dev).view(np.uint16)
         assert got.shape == frames.shape
         _bits_equal(got, frames, f"nd2 fast path {shape}")
+
+
+@pytest.mark.parametrize("method", ["isodata", "yen", "mean"])
+def test_histogram_threshold_methods_match_oracle(method):
+    rng = np.random.default_rng(55)
+    base = (rng.gamma(2.0, 500.0, size=(3, 140, 120)) + 800 * (rng.random((3, 140, 120)) < 0.1) * rng.random((3, 140, 120)) * 8).clip(0, 65535)
+    u16 = base.astype(np.uint16)
+    for i in range(3):
+        got = operations.apply_threshold(u16[i], method)
+        assert got.dtype == np.bool_ and np.array_equal(got, oracle.apply_threshold(u16[i], method)), (method, i)
+    got = operations.apply_threshold(u16, method, _batched=True)
+    for i in range(3):
+        assert np.array_equal(got[i], oracle.apply_threshold(u16[i], method))
+    if method != "mean":
+        f = base / 65535.0
+        for i in range(3):
+            assert np.array_equal(operations.apply_threshold(f[i], method), oracle.apply_threshold(f[i], method)), (method, i)
+    const = np.full((32, 32), 7, dtype=np.uint16)
+    assert not operations.apply_threshold(const, method).any()

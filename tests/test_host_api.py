@@ -122,7 +122,7 @@ def test_operation_argument_validation_matches_reference_messages():
     assert operations.apply_threshold(empty).dtype == np.bool_
     with pytest.raises(ValueError, match="Unsupported thresholding method: 'nope'"):
         operations.apply_threshold(x, method="nope")
-    with pytest.raises(NotImplementedError, match="only 'otsu'"):
+    with pytest.raises(NotImplementedError, match="outside the B200 hot path"):
         operations.apply_threshold(x, method="li")
     assert not operations.apply_threshold(np.full((3, 3), 5, np.uint16), method="li").any()
 
