@@ -157,14 +157,28 @@ def host_fov(seed: int):
     return fov, given
 
 
-def cpu_baseline_single() -> dict:
-    fov, given = host_fov(20260000)
+def cpu_baseline_single(n_fovs: int = 3) -> dict:
+    batch = [host_fov(20260000 + i) for i in range(n_fovs)]
     t0 = time.perf_counter()
-    oracle_fov((fov, given))
+    for item in batch:
+        oracle_fov(item)
     dt = time.perf_counter() - t0
-    return {"value": C * H * W / dt / 1e6, "unit": "Mpix/s", "cores": 1, "kind": "port", "seconds": dt,
-            "sample": f"1 FOV of {C}x{H}x{W} uint16 + its label mask, full workload W, single thread (oracle: "
+    return {"value": n_fovs * C * H * W / dt / 1e6, "unit": "Mpix/s", "cores": 1, "kind": "port", "seconds": dt,
+            "sample": f"{n_fovs} FOVs of {C}x{H}x{W} uint16 + their label masks, full workload W, single thread (oracle: "
                       "reference call chain on scipy/numpy; scikit-image itself is not installable here)"}
+
+
+def ncu_traffic(dom: str, planes: int) -> tuple[float | None, str | None]:
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_ncu_full_dog_strip.json, same 32-plane launch as the live timing)."""
+    path = ROOT / "profiles" / "r01_ncu_full_dog_strip.json"
+    if not path.exists() or planes != 32:
+        return None, None
+    want = "unsigned short" if dom == "axis0" else "double, 1"
+    for k in json.loads(path.read_text())["kernels"]:
+        if want in k["kernel"] and "dram_bytes" in k:
+            return float(k["dram_bytes"]), f"profiles/{path.name} ({k['kernel']})"
+    return None, None
 
 
 def run_reference(args) -> None:
@@ -272,6 +286,7 @@ def run_b200(args) -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -350,6 +365,7 @@ def run_b200(args) -> None:
         dom_ms = k["ms_" + dom]
         achieved = k[dom]["bytes"] / (dom_ms * 1e-3) / 1e9
         fp64_ach = k[dom]["dp_instr"] / (dom_ms * 1e-3) / 1e12
+        traffic, traffic_src = ncu_traffic(dom, k["planes"])
         ms_per_step = 1e3 * dev_s / args.steps
         value = world * args.steps * n_fov * C * H * W / dev_s / 1e6
         line = {
@@ -373,7 +389,8 @@ def run_b200(args) -> None:
             "e2e": e2e,
             "roofline": {"kernel": f"dog_strip_kernel ({dom} pass of the DoG: sigma 0.6 and 16 filters of {k['planes']} planes)",
                          "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": k[dom]["bytes"], "peak_source": peaks["source"],
                          "ms_per_launch": dom_ms,
                          "note": "this kernel is FP64-pipe-bound by construction (193 non-FMA DP instr per sample "
                                  "and axis at sigma=16, scipy's exact operation order); see roofline_fp64"},
