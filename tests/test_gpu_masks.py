@@ -226,3 +226,34 @@ def test_default_property_list_including_perimeter_and_convex_area():
     wo = oracle.cell_properties(odd, None, ["label", "area", "area_convex", "perimeter"])
     assert np.array_equal(o.cell_properties["area_convex"], wo["area_convex"])
     _close(o.cell_properties["perimeter"], wo["perimeter"], "perimeter (odd shapes)")
+
+
+def test_label_stress_many_runs_and_seams():
+    """Run-based CCL corner cases: > 16 runs per 64-pixel row segment (the per-thread overflow path),
+    components that cross tile seams hundreds of times, sizes that are not multiples of the 64x64 tile,
+    and a full-size frame against scipy.ndimage.label directly."""
+    from scipy import ndimage as ndi
+
+    rng = np.random.default_rng(71)
+    full = np.ones((3, 3), dtype=int)
+    noise = rng.random((515, 701)) < 0.5                     # ~16 runs per 64-pixel segment
+    comb = np.zeros((300, 333), bool)
+    comb[:, ::2] = True                                       # 32 one-pixel runs per segment, all rows
+    comb[150, :] = True                                       # ... joined by one row
+    snake = np.zeros((1024, 1024), bool)
+    for k in range(0, 1024, 4):
+        snake[k, :] = True
+        snake[k : k + 4, (1023 if (k // 4) % 2 == 0 else 0)] = True
+    big = rng.random((2048, 2048)) < 0.35
+    for name, m in {"noise": noise, "comb": comb, "snake": snake, "big": big}.items():
+        want, k = ndi.label(m, structure=full)
+        got = masks._process_mask(m, False)
+        assert int(got.max()) == k and np.array_equal(got, want), name
+    # integer masks: few values, heavy fragmentation (value + connectivity), border clearing
+    vals = rng.integers(0, 4, size=(257, 390)).astype(np.int64) * 5
+    for edge in (False, True):
+        try:
+            want = oracle.process_mask(vals, edge)
+        except ValueError:
+            continue
+        assert np.array_equal(masks._process_mask(vals, edge), want), edge
