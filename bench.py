@@ -212,7 +212,7 @@ def run_reference(args) -> None:
                          "sample": f"{workers} FOVs per step, one worker process per FOV (oracle port of the reference chain)"},
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ GPU side
@@ -274,6 +274,27 @@ def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int) -> dict:
     }
 
 
+def bind_near_gpu(local: int) -> list[int]:
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned staging it
+    allocates (first touch) and the copy-issuing thread live on the GPU's own NUMA node: on an
+    8-GPU box the host-fed path is bounded by host memory / PCIe root-complex locality."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n_cpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        near = {i for i in range(n_cpu) if (mask[i // 64] >> (i % 64)) & 1}
+        allowed = near & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return sorted(allowed)
+    except Exception:
+        pass
+    return []
+
+
 def run_b200(args) -> None:
     import torch
     import torch.distributed as dist
@@ -286,8 +307,8 @@ def run_b200(args) -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cpus = bind_near_gpu(local) if world > 1 else []
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib = _lib.load()
@@ -328,7 +349,8 @@ def run_b200(args) -> None:
     # ---- end to end through the host-fed C-ABI call (pinned host buffers)
     e2e = None
     if not args.no_e2e:
-        n_e2e = min(n_fov, args.e2e_fovs)
+        # pinned host staging is per rank: halve it on multi-GPU runs so that 8 ranks stay well inside host RAM
+        n_e2e = min(n_fov, args.e2e_fovs if world == 1 else min(args.e2e_fovs, 128))
         h_fovs = torch.empty((n_e2e, C, H, W), dtype=torch.int16, pin_memory=True)
         # label masks travel as uint16 (Cellpose's own mask dtype below 65536 cells): 8.4 instead of 16.8 MB per FOV
         h_given = torch.empty((n_e2e, H, W), dtype=torch.int16, pin_memory=True)
@@ -353,7 +375,8 @@ def run_b200(args) -> None:
         d2h = sum(int(h_out[k].nbytes) for k in h_out)
         e2e = {"value": world * args.steps * n_e2e * C * H * W / e2e_s / 1e6, "unit": "Mpix/s",
                "h2d_bytes_per_step": int(np_fovs.nbytes + np_given.nbytes), "d2h_bytes_per_step": d2h,
-               "fov_per_s": world * args.steps * n_e2e / e2e_s, "fovs_per_step": n_e2e, "timing": "wall clock around the synchronous C-ABI call"}
+               "fov_per_s": world * args.steps * n_e2e / e2e_s, "fovs_per_step": n_e2e, "timing": "wall clock around the synchronous C-ABI call",
+               "rank0_cpu_affinity": f"{len(cpus)} CPUs local to the GPU (NVML)" if cpus else "unchanged"}
 
     # ---- per-kernel roofline (rank 0) and CPU baseline (rank 0, N=1)
     line = None
@@ -406,7 +429,34 @@ def run_b200(args) -> None:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
+
+
+_REAL_STDOUT_FD: int | None = None
+
+
+def capture_stdout() -> None:
+    """Native libraries (NCCL's version banner, for one) write to fd 1.  Rank 0's stdout must be exactly
+    one JSON line, so fd 1 points at stderr while the benchmark runs and is restored by emit()."""
+    global _REAL_STDOUT_FD
+    sys.stdout.flush()
+    _REAL_STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        try:
+            import ctypes
+
+            ctypes.CDLL(None).fflush(None)  # C stdio buffers of native libraries
+        except Exception:
+            pass
+        os.dup2(_REAL_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(2, 1)  # anything printed at teardown goes to stderr again
 
 
 def main() -> None:
@@ -422,6 +472,7 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
