@@ -47,10 +47,10 @@ __device__ __forceinline__ int map_mode(const amt_map_params& p) {
 }
 
 // Correctly rounded a / b for a plane-constant divisor: y = RN(1/b) once per CTA, then per sample
-//   q = RN(a*y);  r = a - b*q (exact, FMA);  q = RN(q + r*y);  and the same correction once more
-// (Markstein: with a correctly rounded reciprocal and a faithful q the first correction already
-// yields RN(a/b); the second is the safety step the hardware division sequence also takes).
-// 5 DP instructions instead of __ddiv_rn's ~11 DP + ~10 integer/branch instructions per sample.
+//   q = RN(a*y);  r = a - b*q (exact, FMA);  q' = RN(q + r*y)
+// Markstein's theorem: y is the correctly rounded reciprocal and q = RN(a*y) is within one ulp of
+// a/b (relative error of y <= 2^-53, plus half an ulp of rounding), so q' = RN(a/b).
+// 3 DP instructions instead of __ddiv_rn's ~11 DP + ~10 integer/branch instructions per sample.
 // Exact only while nothing under/overflows: `fast` requires 2^-300 <= |b| <= 2^300, and a sample
 // must be 0 or >= 2^-400 in magnitude; anything else takes __ddiv_rn.  tests/test_gpu_ops.py
 // checks the sequence against __ddiv_rn bit for bit (amt_selftest_div).
@@ -74,12 +74,10 @@ __device__ __forceinline__ double div_const(double a, const DivConst& d) {
   if (!d.fast || mag - 1ull < (((unsigned long long)(1023 - 400)) << 52) - 1ull || mag >= (((unsigned long long)(1023 + 400)) << 52))
     return ddiv(a, d.b);
   const double q0 = dmul(a, d.y);
-  double r = __fma_rn(-d.b, q0, a);
+  const double r = __fma_rn(-d.b, q0, a);
   const double q1 = __fma_rn(r, d.y, q0);
-  r = __fma_rn(-d.b, q1, a);
-  const double q2 = __fma_rn(r, d.y, q1);
-  // a = -0.0: the corrections turn the quotient into +0.0; the sign is always that of a*y
-  return __hiloint2double((__double2hiint(q2) & 0x7fffffff) | (__double2hiint(q0) & 0x80000000), __double2loint(q2));
+  // a = -0.0: the correction turns the quotient into +0.0; the sign is always that of a*y
+  return __hiloint2double((__double2hiint(q1) & 0x7fffffff) | (__double2hiint(q0) & 0x80000000), __double2loint(q1));
 }
 
 template <int MODE>
@@ -93,7 +91,9 @@ __device__ __forceinline__ double map_value_mode(double x, const amt_map_params&
     // MODE 3: p1 is a percentile of the clipped (non-negative) plane, so max(max(t, 0), p1) = max(t, p1)
     if (MODE == 3 && p.p1 < 0.0) y = fmax(y, 0.0);
     y = fmin(fmax(y, p.p1), p.p2);
-    y = dadd(dmul(div_const(dsub(y, p.p1), den), gain), p.o1);
+    y = div_const(dsub(y, p.p1), den);
+    // q * 1.0 + 0.0 is q exactly (q >= +0 here): the default out_range (0, 1) needs no arithmetic
+    if (!(gain == 1.0 && p.o1 == 0.0)) y = dadd(dmul(y, gain), p.o1);
   }
   return y;
 }

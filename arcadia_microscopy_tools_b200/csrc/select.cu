@@ -50,7 +50,7 @@ struct SelRanks {
 __device__ __forceinline__ int sel_bin(double x, double mn, double scale) {
   // monotone in x; NaN / inf products collapse to bin 0 / NB-1
   const double t = dmul(dsub(x, mn), scale);
-  int b = (t >= (double)SEL_NB) ? SEL_NB - 1 : (int)t;
+  const int b = __double2int_rz(t);  // saturates (NaN -> 0): no separate range test on the FP64 pipe
   return b < 0 ? 0 : (b > SEL_NB - 1 ? SEL_NB - 1 : b);
 }
 
