@@ -120,6 +120,8 @@ SIGNATURES: dict[str, tuple] = {
     "amt_minmax_decode": (_i, [_p, _i, _i64, _p, _p]),
     "amt_select_f64_scratch_bytes": (_sz, [_i64, _i64]),
     "amt_select_f64": (_i, [_p, _i64, _i64, C.POINTER(_i64), _i, _p, _p, _p, _sz, _p]),
+    "amt_bucket12": (_i, [_p, _p, _i64, _p]),
+    "amt_select_f64_bucketed": (_i, [_p, _p, _i64, _i64, C.POINTER(_i64), _i, _p, _p, _p, _sz, _p]),
     "amt_select_u16_scratch_bytes": (_sz, [_i64]),
     "amt_select_u16": (_i, [_p, _i64, _i64, C.POINTER(_i64), _i, _p, _p, _sz, _p]),
     "amt_map": (_i, [_p, _i, _p, _i64, _i64, _p, _p, _p]),

@@ -64,6 +64,18 @@ __host__ __device__ __forceinline__ double key_to_f64(uint64_t k) {
 #endif
 }
 
+// 12-bit monotone bucket of a double (selection pre-binning written by the DoG's second pass):
+// sign + the exponent and top 6 mantissa bits above 2^-20, straight from the high word, i.e. 64
+// buckets per octave (1.5 % wide) for 2^-20 <= |x| < 2^12, which covers difference-of-Gaussians
+// values of [0, 1] images with room to spare.  Truncation, shift and clamp are monotone, so the
+// buckets are ordered like the values (and like f64_to_key: -0.0 sits below +0.0).
+__device__ __forceinline__ uint32_t bucket12(double x) {
+  const uint32_t hi = (uint32_t)__double2hiint(x);
+  int m = (int)((hi & 0x7fffffffu) >> 14) - ((1023 - 20) << 6);
+  m = m < 0 ? 0 : (m > 2047 ? 2047 : m);
+  return (hi >> 31) ? (uint32_t)(2047 - m) : (uint32_t)(2048 + m);
+}
+
 // ---------------------------------------------------------------- exactly-rounded f64 helpers
 // Separately rounded add / sub / mul: never contracted into FMA, whatever -fmad says.
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }

@@ -8,6 +8,10 @@ namespace amt {
 static thread_local cudaError_t g_last_cuda_error = cudaSuccess;
 static std::atomic<uint64_t> g_launches{0};
 
+// grid cap, in CTAs per SM, of the grid-stride streaming passes (sel_hist, map): 8 fills the machine;
+// 1-2 keeps them fully resident in what the DoG CTAs of the other stream leave free
+int g_pass_ctas = 8;
+
 void set_last_cuda_error(cudaError_t e) { g_last_cuda_error = e; }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, const double scale,
                  double* __restrict__ out_a, double* __restrict__ out_b, const int n, const int inner,
                  const double* __restrict__ hw_lo, const int r_lo, const double* __restrict__ hw_hi, const int r_hi,
-                 const int nb, uint64_t* __restrict__ minmax, const int n_items) {
+                 const int nb, uint64_t* __restrict__ minmax, uint16_t* __restrict__ buckets, const int n_items) {
   constexpr int S = WARPS * R;  // rows per step
   constexpr int NT = WARPS * 32;
   constexpr int FRONT = RLO_MAX, BACK = R;
@@ -285,6 +285,14 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
 #pragma unroll
       for (int o = 0; o < R; ++o) acc[o] = dsub(acc_lo[o], acc[o]);
       store_transposed<R>(stage, acc, out_a + out_col + yb, n, tx, live);
+      if (live && buckets != nullptr) {  // bucket12 of every output, same layout as out_a: R consecutive uint16 per lane
+        uint32_t pk[R / 2];
+#pragma unroll
+        for (int o = 0; o < R; o += 2) pk[o / 2] = bucket12(acc[o]) | (bucket12(acc[o + 1]) << 16);
+        uint16_t* kd = buckets + out_col + (int64_t)tx * n + yb;
+#pragma unroll
+        for (int o = 0; o < R / 2; o += 4) *reinterpret_cast<uint4*>(kd + 2 * o) = make_uint4(pk[o], pk[o + 1], pk[o + 2], pk[o + 3]);
+      }
       if (live) {
         if (minmax != nullptr) {
 #pragma unroll
@@ -336,6 +344,8 @@ static int g_dog_persistent = 0;
 static int g_dog_generic = 0;
 extern int g_stream_ctas;     // gauss.cu
 extern int g_exec_swap_prio;  // executor.cu
+extern int g_pass_ctas;       // core.cu
+extern int g_exec_buckets;    // executor.cu
 
 constexpr size_t kSmemMax = 227 * 1024;
 constexpr size_t kSmemPerSM = 228 * 1024;
@@ -375,7 +385,7 @@ static DogPlan dog_plan(int in_dtype, int64_t n_img, int64_t h, int64_t w, int r
 template <int R, int WARPS, int MIN_CTAS, typename InT, bool SECOND>
 static int launch_strip(const DogPlan& p, const InT* in, const double* in_lo, double scale, double* out_a, double* out_b,
                         int64_t planes, int64_t n, int64_t inner, const double* hw_lo, int r_lo, const double* hw_hi,
-                        int r_hi, uint64_t* minmax, cudaStream_t st) {
+                        int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st) {
   auto kernel = dog_strip_kernel<R, WARPS, MIN_CTAS, InT, SECOND>;
   AMT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   const int64_t items = planes * (inner / PV_TW);
@@ -384,7 +394,7 @@ static int launch_strip(const DogPlan& p, const InT* in, const double* in_lo, do
   const int64_t resident = g_dog_persistent ? (int64_t)kNumSMs * p.ctas : items;
   dim3 grid((unsigned)(items < resident ? items : resident)), block(PV_TW, WARPS);
   kernel<<<grid, block, p.smem, st>>>(in, in_lo, scale, out_a, out_b, (int)n, (int)inner, hw_lo, r_lo, hw_hi, r_hi, p.nb,
-                                      minmax, (int)items);
+                                      minmax, buckets, (int)items);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
@@ -392,15 +402,15 @@ static int launch_strip(const DogPlan& p, const InT* in, const double* in_lo, do
 template <typename InT, bool SECOND>
 static int launch_variant(const DogPlan& p, const InT* in, const double* in_lo, double scale, double* out_a,
                           double* out_b, int64_t planes, int64_t n, int64_t inner, const double* hw_lo, int r_lo,
-                          const double* hw_hi, int r_hi, uint64_t* minmax, cudaStream_t st) {
+                          const double* hw_hi, int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st) {
   if (p.R == 16)
     return launch_strip<16, 4, 2, InT, SECOND>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
-                                                r_hi, minmax, st);
+                                                r_hi, minmax, buckets, st);
   if (p.warps == 8)
     return launch_strip<8, 8, 2, InT, SECOND>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
-                                               r_hi, minmax, st);
+                                               r_hi, minmax, buckets, st);
   return launch_strip<8, 4, 3, InT, SECOND>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi, r_hi,
-                                             minmax, st);
+                                             minmax, buckets, st);
 }
 
 // pass 1: image (h x w) -> tmp_hi, tmp_lo.  Fast path: both TRANSPOSED (w x h); generic: image layout.
@@ -410,24 +420,27 @@ static int dog_axis0(const DogPlan& p, const void* in, int in_dtype, double in_s
   if (!p.fast) return dog_axis0_generic(in, in_dtype, in_scale, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, tmp_lo, tmp_hi, st);
   if (in_dtype == AMT_U16)
     return launch_variant<uint16_t, false>(p, (const uint16_t*)in, nullptr, in_scale, tmp_hi, tmp_lo, n_img, h, w,
-                                           hw_lo, r_lo, hw_hi, r_hi, nullptr, st);
+                                           hw_lo, r_lo, hw_hi, r_hi, nullptr, nullptr, st);
   return launch_variant<double, false>(p, (const double*)in, nullptr, 1.0, tmp_hi, tmp_lo, n_img, h, w, hw_lo, r_lo,
-                                       hw_hi, r_hi, nullptr, st);
+                                       hw_hi, r_hi, nullptr, nullptr, st);
 }
 
 // pass 2.  Fast path: the transposed planes (w x h) filtered along their axis 0, lo - hi written back
 // transposed (= image layout); generic: image-layout planes through the tile kernel of gauss.cu.
 static int dog_axis1(const DogPlan& p, const double* tmp_lo, const double* tmp_hi, double* out, int64_t n_img,
                      int64_t h, int64_t w, const double* hw_lo, int r_lo, const double* hw_hi, int r_hi,
-                     uint64_t* minmax, cudaStream_t st) {
+                     uint64_t* minmax, uint16_t* buckets, cudaStream_t st) {
   if (!p.fast) return dog_axis1_generic(tmp_lo, tmp_hi, out, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, minmax, st);
   return launch_variant<double, true>(p, tmp_hi, tmp_lo, 1.0, out, nullptr, n_img, w, h, hw_lo, r_lo, hw_hi, r_hi,
-                                      minmax, st);
+                                      minmax, buckets, st);
 }
 
+// buckets (optional): n_img*h*w uint16 receiving bucket12() of every output sample; *buckets_written
+// tells the caller whether the strip kernels ran (the generic fallback does not produce them).
 int dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,
           const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, double* tmp_lo, double* tmp_hi,
-          uint64_t* minmax, cudaStream_t st) {
+          uint64_t* minmax, cudaStream_t st, uint16_t* buckets, bool* buckets_written) {
+  if (buckets_written) *buckets_written = false;
   if (!in || !out || !tmp_lo || !tmp_hi || !hw_lo || !hw_hi) return AMT_ERR_INVALID;
   if (n_img <= 0 || h <= 0 || w <= 0 || r_lo < 0 || r_hi < 0) return AMT_ERR_INVALID;
   if (in_dtype != AMT_U16 && in_dtype != AMT_F64) return AMT_ERR_UNSUPPORTED;
@@ -435,8 +448,10 @@ int dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_
   DogPlan p = dog_plan(in_dtype, n_img, h, w, r_lo, r_hi);
   // the strip kernels use 16-byte accesses; odd pointers take the generic tile kernels for BOTH passes
   p.fast = p.fast && aligned16(in) && aligned16(out) && aligned16(tmp_lo) && aligned16(tmp_hi);
+  if (buckets && !(p.fast && aligned16(buckets))) buckets = nullptr;
+  if (buckets_written) *buckets_written = buckets != nullptr;
   AMT_TRY(dog_axis0(p, in, in_dtype, in_scale, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, tmp_lo, tmp_hi, st));
-  return dog_axis1(p, tmp_lo, tmp_hi, out, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, minmax, st);
+  return dog_axis1(p, tmp_lo, tmp_hi, out, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, minmax, buckets, st);
 }
 
 }  // namespace amt
@@ -458,6 +473,11 @@ int amt_tune(const char* key, int value) {
   } else if (is("stream_ctas")) {
     if (value < 1 || value > 32) return AMT_ERR_INVALID;
     g_stream_ctas = value;
+  } else if (is("exec_buckets")) {
+    g_exec_buckets = value != 0;
+  } else if (is("pass_ctas")) {
+    if (value < 1 || value > 16) return AMT_ERR_INVALID;
+    g_pass_ctas = value;
   } else if (is("exec_swap_prio")) {
     g_exec_swap_prio = value != 0;
   } else if (is("dog_generic")) {
@@ -472,7 +492,7 @@ int amt_dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_
               const double* half_w_lo, int r_lo, const double* half_w_hi, int r_hi, double* tmp_lo, double* tmp_hi,
               uint64_t* minmax_keys, amt_stream_t stream) {
   return amt::dog2d(in, in_dtype, in_scale, out, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, tmp_lo, tmp_hi,
-                    minmax_keys, amt::as_stream(stream));
+                    minmax_keys, amt::as_stream(stream), nullptr, nullptr);
 }
 
 // The two passes separately (bench / profiling).  The layout of tmp_lo / tmp_hi between them is
@@ -497,7 +517,7 @@ int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int
   const DogPlan p = dog_plan(AMT_U16, n_img, h, w, r_lo, r_hi);  // the dtype of pass 1's input does not matter here
   if (p.fast && !(aligned16(out) && aligned16(tmp_lo) && aligned16(tmp_hi))) return AMT_ERR_INVALID;
   if (minmax_keys) AMT_TRY(minmax_init(minmax_keys, n_img, as_stream(stream)));
-  return dog_axis1(p, tmp_lo, tmp_hi, out, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, minmax_keys,
+  return dog_axis1(p, tmp_lo, tmp_hi, out, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, minmax_keys, nullptr,
                    as_stream(stream));
 }
 

@@ -37,6 +37,8 @@ struct amt_executor {
   double *hw_lo, *hw_hi;
   double *tmp_lo, *tmp_hi, *dog[2], *pre;
   uint64_t* mm[2];
+  uint16_t* buckets[2];      // bucket12() of the DoG planes (written by the DoG's second pass)
+  bool buckets_valid[2];
   double* stats;
   amt_map_params* params;
   void* sel_scratch;
@@ -70,6 +72,9 @@ namespace amt {
 // amt_tune "exec_swap_prio": 1 (default) = the stream of the short HBM-bound kernels has the high
 // priority and the long-running DoG CTAs the low one, 0 = the opposite
 int g_exec_swap_prio = 1;
+// amt_tune "exec_buckets": 1 (default) = the DoG's second pass also writes bucket12() of its output and the
+// percentile selection reads those 2-byte buckets instead of the 8-byte planes; 0 = plain amt_select_f64
+int g_exec_buckets = 1;
 
 static int dmalloc(amt_executor* ex, void** p, size_t bytes) {
   AMT_CUDA_TRY(cudaMalloc(p, bytes));
@@ -120,7 +125,8 @@ static int enqueue_dog(amt_executor* ex, const uint16_t* in, int g, cudaEvent_t 
   if (ex->chunks_issued >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, ex->ev_dog_free[slot], 0));
   trace_mark(ex, ex->s_dog, "dog: begin");
   AMT_TRY(dog2d(in, AMT_U16, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, ex->hw_lo, ex->r_lo, ex->hw_hi,
-                ex->r_hi, ex->tmp_lo, ex->tmp_hi, ex->mm[slot], ex->s_dog));
+                ex->r_hi, ex->tmp_lo, ex->tmp_hi, ex->mm[slot], ex->s_dog, g_exec_buckets ? ex->buckets[slot] : nullptr,
+                &ex->buckets_valid[slot]));
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_done[slot], ex->s_dog));
   trace_mark(ex, ex->s_dog, "dog: end");
   return AMT_OK;
@@ -146,7 +152,11 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
   // stage A2: order statistics -> plan -> map (+ histogram of the segmentation planes)
   AMT_CUDA_TRY(cudaStreamWaitEvent(st, ex->ev_dog_done[slot], 0));
   trace_mark(ex, st, "  rest: begin (dog of this chunk done)");
-  AMT_TRY(amt_select_f64(dog, planes, HW, ex->ranks, 6, mm, ex->stats, ex->sel_scratch, ex->sel_bytes, st));
+  if (ex->buckets_valid[slot] && HW % 8 == 0)
+    AMT_TRY(select_f64_bucketed(dog, ex->buckets[slot], planes, HW, ex->ranks, 6, mm, ex->stats, ex->sel_scratch,
+                                ex->sel_bytes, st));
+  else
+    AMT_TRY(amt_select_f64(dog, planes, HW, ex->ranks, 6, mm, ex->stats, ex->sel_scratch, ex->sel_bytes, st));
   trace_mark(ex, st, "  rest: select done");
   AMT_TRY(plan_dog_rescale(ex->stats, mm, planes, ex->g_bg, ex->g_lo, ex->g_hi, c.out_lo, c.out_hi, ex->params, st));
   AMT_CUDA_TRY(cudaMemsetAsync(ex->hist256, 0, (size_t)g * 256 * sizeof(uint32_t), st));
@@ -290,6 +300,7 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
   for (int s = 0; s < 2; ++s) {
     EX_TRY(dmalloc(ex, (void**)&ex->dog[s], plane_f64));
     EX_TRY(dmalloc(ex, (void**)&ex->mm[s], (size_t)planes * 2 * sizeof(uint64_t)));
+    EX_TRY(dmalloc(ex, (void**)&ex->buckets[s], (size_t)planes * HW * sizeof(uint16_t)));
   }
   EX_TRY(dmalloc(ex, (void**)&ex->pre, plane_f64));
   EX_TRY(dmalloc(ex, (void**)&ex->stats, (size_t)planes * 6 * sizeof(double)));
@@ -319,6 +330,7 @@ void amt_executor_destroy(amt_executor* ex) {
   cudaSetDevice(ex->cfg.device);
   cudaDeviceSynchronize();
   void* bufs[] = {ex->hw_lo, ex->hw_hi, ex->tmp_lo, ex->tmp_hi, ex->dog[0], ex->dog[1], ex->pre, ex->mm[0], ex->mm[1],
+                  ex->buckets[0], ex->buckets[1],
                   ex->stats, ex->params,
                   ex->sel_scratch, ex->hist256, ex->thr, ex->lab_thr, ex->lab_given, ex->label_scratch, ex->acc,
                   ex->shape_scratch};

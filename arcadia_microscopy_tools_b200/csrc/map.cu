@@ -20,6 +20,8 @@
 
 namespace amt {
 
+extern int g_pass_ctas;  // CTAs per SM of the streaming passes (amt_tune "pass_ctas"), core.cu
+
 __device__ __forceinline__ double map_value(double x, const amt_map_params& p) {
   if (p.flags & AMT_MAP_FILL) return p.o1;
   double y = x;
@@ -487,7 +489,7 @@ threshold_gt_kernel(const InT* __restrict__ data, int64_t n, const double* __res
 
 static unsigned stream_blocks(int64_t n, int64_t n_img, int per_thread) {
   int64_t bx = ceil_div(n, 256 * (int64_t)per_thread);
-  const int64_t cap = ceil_div((int64_t)kNumSMs * 8, n_img);
+  const int64_t cap = ceil_div((int64_t)kNumSMs * g_pass_ctas, n_img);
   if (bx > cap) bx = cap;
   return (unsigned)(bx < 1 ? 1 : bx);
 }

@@ -21,6 +21,8 @@
 
 namespace amt {
 
+extern int g_pass_ctas;  // CTAs per SM of the streaming passes (amt_tune "pass_ctas"), core.cu
+
 constexpr int SEL_NB = 4096;
 constexpr int SEL_CHUNK = 2048;  // elements per block in the streaming kernels (256 threads x 8)
 
@@ -332,6 +334,126 @@ sel_compact_kernel(const double* __restrict__ data, int64_t n, SelPlane* __restr
   }
 }
 
+__global__ void bucket12_kernel(const double* __restrict__ data, uint16_t* __restrict__ out, int64_t n) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) out[i] = (uint16_t)bucket12(data[i]);
+}
+
+// ---- bucketed variant: the DoG's second pass has already written bucket12(x) (uint16) for every
+// sample, so the histogram pass reads 2 instead of 8 bytes per sample and the compaction pass reads
+// the buckets plus only the few float64 values whose bucket holds a wanted rank.  Minimum / maximum
+// ties are not counted apart here (eq_min = eq_max = 0): every sample goes through its bucket.
+__global__ void __launch_bounds__(256)
+sel_hist_buckets_kernel(const uint16_t* __restrict__ buckets, int64_t n, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[SEL_NB];
+  const int64_t img = blockIdx.y;
+  const uint16_t* p = buckets + img * n;
+  for (int i = threadIdx.x; i < SEL_NB; i += 256) sh[i] = 0;
+  __syncthreads();
+  const int64_t n8 = n >> 3;  // 8 buckets per 16-byte load (planes are 16-byte aligned: n % 8 == 0)
+  const int64_t step = (int64_t)gridDim.x * 256;
+  for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < n8; q += 2 * step) {
+    const bool second = q + step < n8;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p) + q);
+    uint4 b = make_uint4(0, 0, 0, 0);
+    if (second) b = __ldg(reinterpret_cast<const uint4*>(p) + q + step);
+    const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      atomicAdd(&sh[wa[e] & 0xfffu], 1u);
+      atomicAdd(&sh[(wa[e] >> 16) & 0xfffu], 1u);
+    }
+    if (second) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        atomicAdd(&sh[wb[e] & 0xfffu], 1u);
+        atomicAdd(&sh[(wb[e] >> 16) & 0xfffu], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t* h = hist + img * SEL_NB;
+  for (int i = threadIdx.x; i < SEL_NB; i += 256) {
+    const uint32_t c = sh[i];
+    if (c) atomicAdd(&h[i], c);
+  }
+}
+
+// grid (chunks, planes); block 256.  No block barriers: a warp takes 32 x 8 consecutive samples per
+// iteration (one 16-byte bucket load per lane, two iterations in flight), and for every candidate list
+// the lanes' counts are scanned with shuffles, one lane reserves the warp's range with a single global
+// atomic, and the wanted float64 values (a few per cent of the samples) are gathered and appended.
+__global__ void __launch_bounds__(256)
+sel_compact_buckets_kernel(const uint16_t* __restrict__ buckets, const double* __restrict__ data, int64_t n,
+                           SelPlane* __restrict__ planes, double* __restrict__ cand, int64_t cap) {
+  __shared__ uint8_t s_lut[SEL_NB];  // bucket -> candidate list id (0xff: not wanted)
+  const int64_t img = blockIdx.y;
+  SelPlane& pl = planes[img];
+  const int n_lists = pl.n_lists;
+  if (n_lists == 0) return;
+  for (int i = threadIdx.x; i < SEL_NB / 4; i += 256) reinterpret_cast<uint32_t*>(s_lut)[i] = 0xffffffffu;
+  __syncthreads();
+  if (threadIdx.x < n_lists) s_lut[pl.list_bin[threadIdx.x]] = (uint8_t)threadIdx.x;
+  __syncthreads();
+  const uint16_t* kp = buckets + img * n;
+  const double* dp = data + img * n;
+  const int lane = threadIdx.x & 31;
+  const int64_t n8 = n >> 3;
+  const int64_t warp0 = ((int64_t)blockIdx.x * 256 + (threadIdx.x & ~31));  // first 8-sample group of this warp
+  const int64_t step = (int64_t)gridDim.x * 256;
+  for (int64_t q0 = warp0; q0 < n8; q0 += 2 * step) {  // warp-uniform trip count
+    uint4 a[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t q = q0 + u * step + lane;
+      a[u] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      if (q < n8) a[u] = __ldg(reinterpret_cast<const uint4*>(kp) + q);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t q = q0 + u * step + lane;
+      const uint32_t w[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+      uint32_t lists = 0;  // 4 bits per sample: list id, 0xf = not wanted
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t bk = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+        uint32_t l = 0xf;
+        if (bk < (uint32_t)SEL_NB) {  // the padding value 0xffff is not a bucket
+          const uint32_t t = s_lut[bk];
+          l = t == 0xff ? 0xf : t;
+        }
+        lists |= l << (4 * e);
+      }
+      if (!__any_sync(0xffffffffu, lists != 0xffffffffu)) continue;
+      for (int l = 0; l < n_lists; ++l) {
+        uint32_t mine = 0;  // bit e: sample e goes to list l
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mine |= (((lists >> (4 * e)) & 0xfu) == (uint32_t)l) ? (1u << e) : 0u;
+        const int c = __popc(mine);
+        if (!__any_sync(0xffffffffu, c != 0)) continue;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(&pl.list_fill[l], (uint32_t)incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int64_t pos = (int64_t)base + (incl - c);
+        double* dst = cand + (img * AMT_MAX_RANKS + l) * cap;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if ((mine >> e) & 1u) {
+            if (pos < cap) dst[pos] = __ldg(dp + 8 * q + e);
+            ++pos;
+          }
+        }
+      }
+    }
+  }
+}
+
 // one block per (rank, plane): 8 passes of 8 bits, most significant first
 __global__ void __launch_bounds__(1024)
 sel_radix_kernel(const SelPlane* __restrict__ planes, int n_ranks, double* __restrict__ out) {
@@ -535,7 +657,7 @@ int amt_select_f64(const double* data, int64_t n_img, int64_t n, const int64_t* 
   sel_prepare_kernel<<<(unsigned)n_img, 256, 0, st>>>(minmax_keys, planes, hist, n_img);
   AMT_LAUNCH_CHECK();
   int64_t bx = ceil_div(n, 256 * 16);
-  const int64_t capb = ceil_div((int64_t)kNumSMs * 8, n_img);
+  const int64_t capb = ceil_div((int64_t)kNumSMs * g_pass_ctas, n_img);
   if (bx > capb) bx = capb;
   if (bx < 1) bx = 1;
   sel_hist_kernel<<<dim3((unsigned)bx, (unsigned)n_img), 256, 0, st>>>(data, n, planes, hist);
@@ -572,6 +694,71 @@ int amt_select_u16(const uint16_t* data, int64_t n_img, int64_t n, const int64_t
   uint32_t* hist = (uint32_t*)scratch;
   AMT_TRY(hist_u16(data, n_img, n, hist, st));
   sel_u16_locate_kernel<<<(unsigned)n_img, 1024, 0, st>>>(hist, ranks, out_vals);
+  AMT_LAUNCH_CHECK();
+  return AMT_OK;
+}
+
+}  // extern "C"
+
+namespace amt {
+
+// Same contract as amt_select_f64 (same scratch layout and size), with the bucket12() plane the DoG's
+// second pass wrote next to `data`.  n must be a multiple of 8 and both planes 16-byte aligned.
+int select_f64_bucketed(const double* data, const uint16_t* buckets, int64_t n_img, int64_t n, const int64_t* ranks_host,
+                        int n_ranks, const uint64_t* minmax_keys, double* out_vals, void* scratch, size_t scratch_bytes,
+                        cudaStream_t st) {
+  if (!data || !buckets || !ranks_host || !minmax_keys || !out_vals || !scratch) return AMT_ERR_INVALID;
+  if (n_img <= 0 || n <= 0 || n % 8 != 0 || n_ranks <= 0 || n_ranks > AMT_MAX_RANKS || n_img > 65535) return AMT_ERR_INVALID;
+  if (n >= (1ll << 32)) return AMT_ERR_CAPACITY;
+  if (scratch_bytes < amt_select_f64_scratch_bytes(n_img, n)) return AMT_ERR_CAPACITY;
+  SelRanks ranks;
+  ranks.n = n_ranks;
+  for (int i = 0; i < n_ranks; ++i) {
+    if (ranks_host[i] < 0 || ranks_host[i] >= n) return AMT_ERR_INVALID;
+    ranks.r[i] = ranks_host[i];
+  }
+  const int64_t cap = sel_cap(n);
+  char* base = (char*)scratch;
+  SelPlane* planes = (SelPlane*)base;
+  uint32_t* hist = (uint32_t*)(base + (size_t)n_img * sizeof(SelPlane));
+  double* cand = (double*)(base + sel_head_bytes(n_img));
+  sel_prepare_kernel<<<(unsigned)n_img, 256, 0, st>>>(minmax_keys, planes, hist, n_img);
+  AMT_LAUNCH_CHECK();
+  int64_t bx = ceil_div(n, 256 * 8 * 16);
+  const int64_t capb = ceil_div((int64_t)kNumSMs * g_pass_ctas, n_img);
+  if (bx > capb) bx = capb;
+  if (bx < 1) bx = 1;
+  sel_hist_buckets_kernel<<<dim3((unsigned)bx, (unsigned)n_img), 256, 0, st>>>(buckets, n, hist);
+  AMT_LAUNCH_CHECK();
+  sel_locate_kernel<<<(unsigned)n_img, 1024, 0, st>>>(data, n, ranks, planes, hist, cand, cap);
+  AMT_LAUNCH_CHECK();
+  int64_t cx = ceil_div(n, 256 * 8 * 8);
+  if (cx > capb) cx = capb;
+  if (cx < 1) cx = 1;
+  sel_compact_buckets_kernel<<<dim3((unsigned)cx, (unsigned)n_img), 256, 0, st>>>(buckets, data, n, planes, cand, cap);
+  AMT_LAUNCH_CHECK();
+  sel_radix_kernel<<<dim3((unsigned)n_ranks, (unsigned)n_img), 1024, 0, st>>>(planes, n_ranks, out_vals);
+  AMT_LAUNCH_CHECK();
+  return AMT_OK;
+}
+
+}  // namespace amt
+
+extern "C" {
+
+// Test / standalone entry: bucket12() of every sample of `data` (what amt_dog2d's second pass writes on
+// the executor path), so that the bucketed selection can be checked against amt_select_f64.
+int amt_select_f64_bucketed(const double* data, const uint16_t* buckets, int64_t n_img, int64_t n,
+                            const int64_t* ranks_host, int n_ranks, const uint64_t* minmax_keys, double* out_vals,
+                            void* scratch, size_t scratch_bytes, amt_stream_t stream) {
+  return amt::select_f64_bucketed(data, buckets, n_img, n, ranks_host, n_ranks, minmax_keys, out_vals, scratch,
+                                  scratch_bytes, amt::as_stream(stream));
+}
+
+int amt_bucket12(const double* data, uint16_t* buckets, int64_t n, amt_stream_t stream) {
+  using namespace amt;
+  if (!data || !buckets || n <= 0) return AMT_ERR_INVALID;
+  bucket12_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(data, buckets, n);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }

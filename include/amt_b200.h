@@ -141,6 +141,14 @@ int amt_select_f64(const double* data, int64_t n_img, int64_t n, const int64_t* 
                    const uint64_t* minmax_keys, double* out_vals, void* scratch, size_t scratch_bytes,
                    amt_stream_t stream);
 size_t amt_select_u16_scratch_bytes(int64_t n_img);
+/* Bucketed variant of amt_select_f64 (same scratch, same results): `buckets` holds amt_bucket12() of every
+ * sample (12-bit monotone bucket: sign, float32 exponent and top 6 mantissa bits).  The executor's DoG writes
+ * the buckets in its second pass, so the two selection passes read 2 B instead of 8 B per sample.
+ * n must be a multiple of 8, both planes 16-byte aligned. */
+int amt_bucket12(const double* data, uint16_t* buckets, int64_t n, amt_stream_t stream);
+int amt_select_f64_bucketed(const double* data, const uint16_t* buckets, int64_t n_img, int64_t n,
+                            const int64_t* ranks_host, int n_ranks, const uint64_t* minmax_keys, double* out_vals,
+                            void* scratch, size_t scratch_bytes, amt_stream_t stream);
 int amt_select_u16(const uint16_t* data, int64_t n_img, int64_t n, const int64_t* ranks_host, int n_ranks,
                    double* out_vals, void* scratch, size_t scratch_bytes, amt_stream_t stream);
 

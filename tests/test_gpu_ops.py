@@ -299,3 +299,47 @@ def test_histogram_threshold_methods_match_oracle(method):
             assert np.array_equal(operations.apply_threshold(f[i], method), oracle.apply_threshold(f[i], method)), (method, i)
     const = np.full((32, 32), 7, dtype=np.uint16)
     assert not operations.apply_threshold(const, method).any()
+
+
+def test_bucketed_selection_matches_sorted_order():
+    """amt_select_f64_bucketed (2-byte monotone buckets + sparse value gather, the executor's percentile
+    path) must return exactly the order statistics np.sort gives, also for distributions that put most
+    samples in one bucket (whole-plane radix fallback), signed zeros and values outside the bucket range."""
+    import ctypes as C
+
+    import torch
+
+    from arcadia_microscopy_tools_b200 import _lib as L
+
+    lib = L.load()
+    rng = np.random.default_rng(123)
+    n = 512 * 512
+    planes = {
+        "dog_like": rng.normal(0, 1.5e-3, n) + (rng.random(n) < 0.08) * rng.gamma(2.0, 0.01, n),
+        "narrow": 0.25 + rng.normal(0, 1e-9, n),                      # one bucket holds everything
+        "zeros": np.where(rng.random(n) < 0.6, 0.0, rng.normal(0, 1e-4, n)) * rng.choice([-1.0, 1.0], n),
+        "wide": rng.normal(0, 1.0, n) * 10.0 ** rng.integers(-30, 6, n),  # far beyond 2^-20 .. 2^12
+        "tiny": rng.normal(0, 1e-9, n),                                # all below the finest bucket
+    }
+    data = np.stack(list(planes.values()))
+    ranks = [0, 1, n // 100, n // 100 + 1, n // 2, (99 * n) // 100, n - 2, n - 1]
+    d = torch.from_numpy(data).cuda()
+    buckets = torch.empty(data.shape, dtype=torch.int16, device="cuda")
+    L.check(lib.amt_bucket12(_gpu.ptr(d), _gpu.ptr(buckets), data.size, _gpu.stream_ptr()))
+    b = buckets.cpu().numpy().view(np.uint16)
+    assert b.max() < 4096
+    for i in range(data.shape[0]):  # buckets are monotone in the value (-0.0 sits one bucket below +0.0)
+        order = np.argsort(data[i], kind="stable")
+        v, bb = data[i][order], b[i][order].astype(np.int64)
+        both_zero = (v[1:] == 0) & (v[:-1] == 0)
+        assert np.all((np.diff(bb) >= 0) | both_zero), list(planes)[i]
+    mm = _gpu.minmax_keys(d)
+    out = torch.empty((data.shape[0], len(ranks)), dtype=torch.float64, device="cuda")
+    nbytes = lib.amt_select_f64_scratch_bytes(data.shape[0], n)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    r = (C.c_int64 * len(ranks))(*ranks)
+    L.check(lib.amt_select_f64_bucketed(_gpu.ptr(d), _gpu.ptr(buckets), data.shape[0], n, r, len(ranks), _gpu.ptr(mm),
+                                        _gpu.ptr(out), _gpu.ptr(scratch), nbytes, _gpu.stream_ptr()))
+    got = out.cpu().numpy()
+    want = np.sort(data, axis=1)[:, ranks]
+    assert np.array_equal(got, want), [(list(planes)[i], got[i], want[i]) for i in range(len(planes)) if not np.array_equal(got[i], want[i])][:2]
