@@ -32,7 +32,11 @@
 
 namespace amt {
 
-constexpr int TW = 64, TH = 64;  // tile of kernel A
+#ifndef AMT_CCL_TH
+#define AMT_CCL_TH 32
+#endif
+constexpr int TW = 64, TH = AMT_CCL_TH;  // tile of kernel A (TW is the width of the 64-bit row masks)
+constexpr int TILE_WARPS = TH / 8, TILE_THREADS = TILE_WARPS * 32;
 
 template <int KIND> struct CclRaw { typedef uint8_t type; };
 template <> struct CclRaw<1> { typedef double type; };
@@ -117,9 +121,9 @@ __device__ __forceinline__ uint64_t run_mask_from(const uint64_t stops, const in
   return upto & ~((1ull << a) - 1ull);
 }
 
-// grid (ceil(w/64), ceil(h/64), planes); block 256 = 8 warps; warp -> rows warp, warp+8, ...
+// grid (ceil(w/TW), ceil(h/TH), planes); block TH/8 warps; warp -> rows warp, warp + TH/8, ... (8 rows each)
 template <int KIND>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TILE_THREADS)
 ccl_tile_kernel(const void* __restrict__ in, const int64_t in_stride, const double* __restrict__ thresholds,
                 int32_t* __restrict__ L, int32_t* __restrict__ rootlist, int32_t* __restrict__ rootcnt, const int h,
                 const int w) {
@@ -140,7 +144,7 @@ ccl_tile_kernel(const void* __restrict__ in, const int64_t in_stride, const doub
     typename CclRaw<KIND>::type raw[8][2];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int y = ty0 + warp + 8 * q;
+      const int y = ty0 + warp + TILE_WARPS * q;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int x = tx0 + half * 32 + lane;
@@ -149,7 +153,7 @@ ccl_tile_kernel(const void* __restrict__ in, const int64_t in_stride, const doub
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int y = ty0 + warp + 8 * q;
+      const int y = ty0 + warp + TILE_WARPS * q;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int x = tx0 + half * 32 + lane;
@@ -159,7 +163,7 @@ ccl_tile_kernel(const void* __restrict__ in, const int64_t in_stride, const doub
   }
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const int lr = warp + 8 * q;
+    const int lr = warp + TILE_WARPS * q;
     uint32_t fgw[2], bkw[2];
     int last = 0;
 #pragma unroll
@@ -184,7 +188,7 @@ ccl_tile_kernel(const void* __restrict__ in, const int64_t in_stride, const doub
   if (KIND == 2) {  // same-value masks against the row above (ballots; the values are still in registers)
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int lr = warp + 8 * q;
+      const int lr = warp + TILE_WARPS * q;
       uint32_t nw_[2], n_[2], ne_[2];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -280,7 +284,7 @@ ccl_tile_kernel(const void* __restrict__ in, const int64_t in_stride, const doub
   __syncthreads();
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const int lr = warp + 8 * q, y = ty0 + lr;
+    const int lr = warp + TILE_WARPS * q, y = ty0 + lr;
     const uint64_t fg = s_fg[lr], brk = s_brk[lr];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -645,7 +649,7 @@ static int ccl_core(const void* in, int64_t in_stride, const double* thresholds,
   const int64_t npx = (int64_t)h * w;
   AMT_CUDA_TRY(cudaMemsetAsync(s.rootcnt, 0, s.zero_bytes, st));
   dim3 tgrid((unsigned)ceil_div(w, TW), (unsigned)ceil_div(h, TH), (unsigned)n_img);
-  ccl_tile_kernel<KIND><<<tgrid, 256, 0, st>>>(in, in_stride, thresholds, L, s.rootlist, s.rootcnt, h, w);
+  ccl_tile_kernel<KIND><<<tgrid, TILE_THREADS, 0, st>>>(in, in_stride, thresholds, L, s.rootlist, s.rootcnt, h, w);
   AMT_LAUNCH_CHECK();
   const int n_hseams = (int)ceil_div(h, TH) - 1, n_vseams = (int)ceil_div(w, TW) - 1;
   const int64_t seam_px = (int64_t)n_hseams * w + (int64_t)n_vseams * 2 * h;
