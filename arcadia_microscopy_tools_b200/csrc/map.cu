@@ -187,17 +187,26 @@ __device__ __forceinline__ void load4<uint16_t>(const uint16_t* p, double* v) {
   v[3] = (double)(a.y >> 16);
 }
 
+// 16-byte streaming store (evict-first): the output planes are not re-read before the caches turn over
+__device__ __forceinline__ void st_stream(double* p, double a, double b) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+
 template <typename InT, bool HIST, bool VEC>
 __global__ void __launch_bounds__(256)
 map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, const amt_map_params* __restrict__ params,
            uint32_t* __restrict__ hist256, int hist_every, int hist_offset) {
   __shared__ uint32_t s_hist[HIST ? 8 * 256 : 1];
   __shared__ double s_edges[HIST ? 257 : 1];
-  const int64_t img = blockIdx.y;
+  // HIST launch: grid.y runs over the histogram planes only (img = y * hist_every + hist_offset).
+  // plain launch: grid.y runs over all planes; when hist_every > 0 the histogram planes belong to the
+  // other launch and are skipped (hist_every == 0: no histogram requested, every plane is mapped here).
+  const int64_t img = HIST ? (int64_t)blockIdx.y * hist_every + hist_offset : (int64_t)blockIdx.y;
+  if (!HIST && hist_every > 0 && (img % hist_every) == hist_offset) return;
   const amt_map_params p = params[img];
   const InT* src = in + img * n;
   double* dst = out + img * n;
-  const bool do_hist = HIST && hist256 != nullptr && (img % hist_every) == hist_offset;
+  const bool do_hist = HIST && hist256 != nullptr;
   HistRange hr;
   uint32_t* wh = s_hist + (threadIdx.x >> 5) * 256;
   if (HIST) {
@@ -224,11 +233,11 @@ map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, cons
         if (second) load4<InT>(src + 4 * q2, v + 4);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = map_value_mode<MODE>(v[e], p, den, gain);
-        *reinterpret_cast<double2*>(dst + 4 * q) = make_double2(v[0], v[1]);
-        *reinterpret_cast<double2*>(dst + 4 * q + 2) = make_double2(v[2], v[3]);
+        st_stream(dst + 4 * q, v[0], v[1]);
+        st_stream(dst + 4 * q + 2, v[2], v[3]);
         if (second) {
-          *reinterpret_cast<double2*>(dst + 4 * q2) = make_double2(v[4], v[5]);
-          *reinterpret_cast<double2*>(dst + 4 * q2 + 2) = make_double2(v[6], v[7]);
+          st_stream(dst + 4 * q2, v[4], v[5]);
+          st_stream(dst + 4 * q2 + 2, v[6], v[7]);
         }
         if (HIST && do_hist) {
 #pragma unroll
@@ -498,27 +507,41 @@ int map_launch(const void* in, int in_dtype, double* out, int64_t n_img, int64_t
                uint32_t* hist256, int hist_every, int hist_offset, cudaStream_t st) {
   if (!in || !out || !params || n_img <= 0 || n <= 0 || n_img > 65535 || hist_every < 1) return AMT_ERR_INVALID;
   const bool vec = (n % 4 == 0) && (((uintptr_t)in) % 16 == 0) && (((uintptr_t)out) % 16 == 0);
+  // planes with a histogram go through the HIST instantiation (66 registers, 10 KB of shared memory), all
+  // others through the plain one (38 registers: twice the resident warps to cover the memory latency)
+  if (hist256 && hist_offset >= n_img) return AMT_ERR_INVALID;
+  const int64_t n_hist = hist256 ? (n_img - hist_offset + hist_every - 1) / hist_every : 0;
+  const bool plain_needed = n_hist < n_img;
   dim3 grid(stream_blocks(n, n_img, vec ? 16 : 8), (unsigned)n_img);
-#define AMT_MAP_LAUNCH(T, H, V)                                                                             \
-  map_kernel<T, H, V><<<grid, 256, 0, st>>>((const T*)in, out, n, params, (H) ? hist256 : nullptr, (H) ? hist_every : 1, \
-                                            (H) ? hist_offset : 0)
+  dim3 hgrid(stream_blocks(n, n_hist > 0 ? n_hist : 1, vec ? 16 : 8), (unsigned)(n_hist > 0 ? n_hist : 1));
+#define AMT_MAP_LAUNCH(T, V)                                                                                      \
+  do {                                                                                                            \
+    if (plain_needed) {                                                                                           \
+      map_kernel<T, false, V><<<grid, 256, 0, st>>>((const T*)in, out, n, params, nullptr, hist256 ? hist_every : 0, \
+                                                    hist_offset);                                                 \
+      count_launch();                                                                                             \
+    }                                                                                                             \
+    if (n_hist > 0)                                                                                               \
+      map_kernel<T, true, V><<<hgrid, 256, 0, st>>>((const T*)in, out, n, params, hist256, hist_every, hist_offset); \
+  } while (0)
   if (in_dtype == AMT_F64) {
-    if (hist256) {
-      if (vec) AMT_MAP_LAUNCH(double, true, true); else AMT_MAP_LAUNCH(double, true, false);
-    } else {
-      if (vec) AMT_MAP_LAUNCH(double, false, true); else AMT_MAP_LAUNCH(double, false, false);
-    }
+    if (vec) AMT_MAP_LAUNCH(double, true); else AMT_MAP_LAUNCH(double, false);
   } else if (in_dtype == AMT_U16) {
-    if (hist256) {
-      if (vec) AMT_MAP_LAUNCH(uint16_t, true, true); else AMT_MAP_LAUNCH(uint16_t, true, false);
-    } else {
-      if (vec) AMT_MAP_LAUNCH(uint16_t, false, true); else AMT_MAP_LAUNCH(uint16_t, false, false);
-    }
+    if (vec) AMT_MAP_LAUNCH(uint16_t, true); else AMT_MAP_LAUNCH(uint16_t, false);
   } else {
     return AMT_ERR_UNSUPPORTED;
   }
 #undef AMT_MAP_LAUNCH
-  AMT_LAUNCH_CHECK();
+  if (n_hist > 0) {
+    AMT_LAUNCH_CHECK();
+  } else {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+      set_last_cuda_error(e);
+      (void)cudaGetLastError();
+      return AMT_ERR_CUDA;
+    }
+  }
   return AMT_OK;
 }
 
