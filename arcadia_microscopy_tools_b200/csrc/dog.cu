@@ -19,14 +19,14 @@
 //    as two/four 8-byte loads per thread held in registers and converted (x * 1/65535) on the
 //    way into the ring, float64 input with cp.async straight into the ring.  One barrier per
 //    step; the prologue (S + 2r rows) is paid once per strip, not once per 512 rows.
-//  * the blocks a step's window can run into past the end of the ring are mirrored behind it,
-//    so the window is one contiguous run and every shared-memory access of the unrolled tap
-//    loop is base + constant.
+//  * the left / right tap pointers advance by R rows per unrolled iteration and wrap there; R
+//    mirror rows behind the ring make every access inside an iteration pointer + constant.
 //  * the narrow (sigma_lo, r <= 4) filter needs R + 2*r_lo samples per thread; they are taken
 //    from the ring (pass 1) or straight from global memory (pass 2) into registers.
-//  * one CTA per SM (256 threads, ~100 KB of shared memory): the kernel leaves half of every
-//    SM's registers and shared memory free, so the HBM-bound kernels of the previous chunk
-//    (other stream) run next to it instead of time-slicing with it.
+//  * the ring wraps (only R mirror rows), so 2-3 CTAs of 128 threads fit per SM and run out of
+//    phase: while one is in a non-DP phase (fill, stores, barrier) the others keep the pipe busy.
+//  * any plane whose width is a multiple of 4 and height a multiple of 2 takes this path (narrow
+//    last strip, short last step); other shapes and radii use the tile kernels of gauss.cu.
 // The inner loop is conv_exact (conv.cuh).
 
 #include <cstdlib>
@@ -75,7 +75,7 @@ __device__ __forceinline__ void conv_small(const double (&xs)[R + 2 * RLO_MAX], 
 // instruction touches 64/R lines instead of 32 and needs no CTA barrier, only __syncwarp.
 template <int R>
 __device__ __forceinline__ void store_transposed(double* __restrict__ sw, const double (&v)[R], double* __restrict__ dst,
-                                                 const int n, const int lane, const bool live) {
+                                                 const int n, const int lane, const int rows_left, const int cols_valid) {
   constexpr int P = R + 2;     // stage pitch (doubles)
   constexpr int LPR = R / 2;   // lanes per column run
   constexpr int CPI = 32 / LPR;  // columns per store instruction
@@ -83,10 +83,19 @@ __device__ __forceinline__ void store_transposed(double* __restrict__ sw, const 
   for (int o = 0; o < R; o += 2) *reinterpret_cast<double2*>(sw + lane * P + o) = make_double2(v[o], v[o + 1]);
   __syncwarp();
   const int c = lane / LPR, q = 2 * (lane % LPR);
+  if (rows_left >= R && cols_valid == PV_TW) {  // whole tile inside the plane (warp-uniform): no per-store tests
 #pragma unroll
-  for (int i = 0; i < LPR; ++i) {
-    const double2 t = *reinterpret_cast<const double2*>(sw + (i * CPI + c) * P + q);
-    if (live) *reinterpret_cast<double2*>(dst + (int64_t)(i * CPI + c) * n + q) = t;
+    for (int i = 0; i < LPR; ++i) {
+      const double2 t = *reinterpret_cast<const double2*>(sw + (i * CPI + c) * P + q);
+      *reinterpret_cast<double2*>(dst + (int64_t)(i * CPI + c) * n + q) = t;
+    }
+  } else if (q < rows_left) {
+    // rows_left is even (n and the run start are): a pair of outputs is all inside or all outside the plane
+#pragma unroll
+    for (int i = 0; i < LPR; ++i) {
+      const double2 t = *reinterpret_cast<const double2*>(sw + (i * CPI + c) * P + q);
+      if (i * CPI + c < cols_valid) *reinterpret_cast<double2*>(dst + (int64_t)(i * CPI + c) * n + q) = t;
+    }
   }
   __syncwarp();
 }
@@ -141,8 +150,9 @@ __device__ __forceinline__ void conv_ring(const double* __restrict__ ring0, cons
   }
 }
 
-// grid (inner/32, planes); block (32, WARPS).  n = length of the filter axis, inner = length of
-// the contiguous axis (multiple of 32), input plane layout [n][inner], output [inner][n].
+// grid (ceil(inner/32) * planes); block (32, WARPS).  n = length of the filter axis (even), inner = length
+// of the contiguous axis (multiple of 4 for uint16 input, of 2 for float64), input plane layout [n][inner],
+// output [inner][n].  The last strip of a plane may be narrower than 32 and the last step shorter than S.
 // FIRST pass : in = image (InT), out_a = G_hi^T, out_b = G_lo^T
 // SECOND pass: in = G_hi^T (double), in_lo = G_lo^T, out_a = G_lo - G_hi in image layout
 // Ring: N = (nb+1)*S rows; block b (S rows) holds samples y = b*S - r_hi + [0, S), clamped
@@ -171,12 +181,13 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
   for (int i = tid; i <= r_lo; i += NT) wlo[i] = hw_lo[i];
 
   // item = plane * (inner/32) + strip; one item per CTA unless the launch is persistent (round robin)
-  const int strips = inner / PV_TW;
+  const int strips = (inner + PV_TW - 1) / PV_TW;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
   const int plane_idx = item / strips;
   const int x0 = (item - plane_idx * strips) * PV_TW;
   const int64_t plane = (int64_t)plane_idx * n * inner;
   const InT* src = in + plane + x0;
+  const int cols_valid = inner - x0 < PV_TW ? inner - x0 : PV_TW;  // a multiple of the load granule
   if (item != (int)blockIdx.x) __syncthreads();  // the previous strip's last step is done with the ring
 
   // ---- ring fill
@@ -185,6 +196,8 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
   constexpr int TPR = U16 ? 8 : 16;           // threads per row
   constexpr int NRAW = U16 ? ITEMS : 1;
   const int fill_row = tid / TPR, fill_col = (U16 ? 4 : 2) * (tid % TPR);
+  // lanes beyond a narrow last strip re-read its last granule (their ring columns are never used)
+  const int load_col = fill_col < cols_valid ? fill_col : cols_valid - (U16 ? 4 : 2);
   // b = logical block, pb = its ring slot (b % m, tracked by the caller: no runtime modulo)
   auto fetch_block = [&](int b, int pb, uint2 (&raw)[NRAW]) {  // global -> registers (uint16) or -> ring (float64, async)
 #pragma unroll
@@ -193,10 +206,10 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
       int y = b * S + rb - r_hi;
       y = y < 0 ? 0 : (y > n - 1 ? n - 1 : y);
       if constexpr (U16) {
-        raw[it] = __ldg(reinterpret_cast<const uint2*>(src + y * inner + fill_col));
+        raw[it] = __ldg(reinterpret_cast<const uint2*>(src + y * inner + load_col));
       } else {
         const int prow = pb * S + rb;
-        const double* g = reinterpret_cast<const double*>(src) + y * inner + fill_col;
+        const double* g = reinterpret_cast<const double*>(src) + y * inner + load_col;
         double* d = ring + prow * PV_TW + fill_col;
         cp_async16(d, g);
         if (prow < BACK) cp_async16(d + N * PV_TW, g);
@@ -249,11 +262,12 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
     const int pf = pk == 0 ? m - 1 : pk - 1;  // (k + nb) % m: the slot of block k-1, free since the last barrier
     if (more) fetch_block(k + nb, pf, raw);
     const int yb = k * S + ty * R;
-    const bool live = yb < n;  // n % 32 == 0 and R | 32: a thread's run is all in or all out
+    const int rows_left = n - yb;  // even; <= 0: nothing of this thread's run is inside the plane
+    const bool lane_ok = tx < cols_valid;
 
     double xs[R + 2 * RLO_MAX];
     if constexpr (SECOND) {  // narrow operand straight from global memory (L2), in flight during the hi filter
-      const double* lo_col = in_lo + plane + x0 + tx;
+      const double* lo_col = in_lo + plane + x0 + (lane_ok ? tx : cols_valid - 1);
       if (yb >= RLO_MAX && yb + R + RLO_MAX <= n) {  // interior: one base, constant strides
         const double* p = lo_col + (yb - RLO_MAX) * inner;
 #pragma unroll
@@ -273,28 +287,39 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
     double acc[R];
     conv_ring<R>(ring_lane, N, c, whi, r_hi, acc);
     if constexpr (!SECOND) {
-      store_transposed<R>(stage, acc, out_a + out_col + yb, n, tx, live);
+      store_transposed<R>(stage, acc, out_a + out_col + yb, n, tx, rows_left, cols_valid);
       const double* col = ring_lane + c * PV_TW;
 #pragma unroll
       for (int i = 0; i < R + 2 * RLO_MAX; ++i) xs[i] = col[(i - RLO_MAX) * PV_TW];  // front / back mirrors: never wraps
       conv_small<R>(xs, wlo, r_lo, acc);
-      store_transposed<R>(stage, acc, out_b + out_col + yb, n, tx, live);
+      store_transposed<R>(stage, acc, out_b + out_col + yb, n, tx, rows_left, cols_valid);
     } else {
       double acc_lo[R];
       conv_small<R>(xs, wlo, r_lo, acc_lo);
 #pragma unroll
       for (int o = 0; o < R; ++o) acc[o] = dsub(acc_lo[o], acc[o]);
-      store_transposed<R>(stage, acc, out_a + out_col + yb, n, tx, live);
-      if (live && buckets != nullptr) {  // bucket12 of every output, same layout as out_a: R consecutive uint16 per lane
-        uint32_t pk[R / 2];
+      store_transposed<R>(stage, acc, out_a + out_col + yb, n, tx, rows_left, cols_valid);
+      if (lane_ok && rows_left > 0) {
+        if (buckets != nullptr) {  // bucket12 of every output, same layout as out_a: R consecutive uint16 per lane
+          uint32_t packed[R / 2];
 #pragma unroll
-        for (int o = 0; o < R; o += 2) pk[o / 2] = bucket12(acc[o]) | (bucket12(acc[o + 1]) << 16);
-        uint16_t* kd = buckets + out_col + (int64_t)tx * n + yb;
+          for (int o = 0; o < R; o += 2) packed[o / 2] = bucket12(acc[o]) | (bucket12(acc[o + 1]) << 16);
+          uint16_t* kd = buckets + out_col + (int64_t)tx * n + yb;
+          if (rows_left >= R && (n & 7) == 0) {
 #pragma unroll
-        for (int o = 0; o < R / 2; o += 4) *reinterpret_cast<uint4*>(kd + 2 * o) = make_uint4(pk[o], pk[o + 1], pk[o + 2], pk[o + 3]);
-      }
-      if (live) {
+            for (int o = 0; o < R / 2; o += 4)
+              *reinterpret_cast<uint4*>(kd + 2 * o) = make_uint4(packed[o], packed[o + 1], packed[o + 2], packed[o + 3]);
+          } else {
+#pragma unroll
+            for (int o = 0; o < R / 2; ++o)
+              if (2 * o < rows_left) *reinterpret_cast<uint32_t*>(kd + 2 * o) = packed[o];
+          }
+        }
         if (minmax != nullptr) {
+          if (rows_left < R) {  // short last step: outputs beyond the plane repeat a valid one
+#pragma unroll
+            for (int o = 1; o < R; ++o) acc[o] = o < rows_left ? acc[o] : acc[0];
+          }
 #pragma unroll
           for (int o = 0; o < R; ++o) {
             const uint64_t key = f64_to_key(acc[o]);
@@ -360,15 +385,17 @@ static bool aligned16(const void* q) { return ((uintptr_t)q) % 16 == 0; }
 
 static DogPlan dog_plan(int in_dtype, int64_t n_img, int64_t h, int64_t w, int r_lo, int r_hi) {
   DogPlan p{};
-  p.R = g_dog_variant == 1 ? 16 : 8;
-  p.warps = g_dog_variant == 2 ? 8 : 4;
+  int variant = g_dog_variant;
+  if (variant == 1 && r_hi % 16 != 0) variant = 0;  // 16 outputs per thread need 16 | radius; 8 | radius still runs fast
+  p.R = variant == 1 ? 16 : 8;
+  p.warps = variant == 2 ? 8 : 4;
   const int S = p.R * p.warps;
   p.nb = 1 + (2 * r_hi + S - 1) / S;
   const size_t rows = (size_t)(p.nb + 1) * S + RLO_MAX + p.R;
   p.smem = (rows * PV_TW + ((r_hi + 2) & ~1) + ((r_lo + 2) & ~1) + (size_t)p.warps * PV_TW * (p.R + 2)) * sizeof(double);
   // resident CTAs per SM: what fits (shared memory, and the register budget __launch_bounds__ was given),
   // capped by the dog_ctas knob
-  const int max_ctas = g_dog_variant == 0 ? 3 : 2;
+  const int max_ctas = variant == 0 ? 3 : 2;
   int fit = (int)(kSmemPerSM / (p.smem + 1024));
   fit = fit > max_ctas ? max_ctas : fit;
   p.ctas = (g_dog_ctas > 0 && g_dog_ctas < fit) ? g_dog_ctas : fit;
@@ -376,9 +403,12 @@ static DogPlan dog_plan(int in_dtype, int64_t n_img, int64_t h, int64_t w, int r
     const size_t pad = kSmemPerSM / (p.ctas + 1) + 1 - 1024;
     if (p.smem < pad && pad <= kSmemMax) p.smem = pad;
   }
-  p.fast = !g_dog_generic && p.smem <= kSmemMax && fit >= 1 && n_img * ((h > w ? h : w) / 32) < (1ll << 31) && h % 32 == 0 && w % 32 == 0 &&
-           h * w < (1ll << 31) && r_lo <= RLO_MAX && r_hi >= r_lo && r_hi >= p.R && r_hi % p.R == 0 &&
-           (in_dtype == AMT_U16 || in_dtype == AMT_F64);
+  // widths: 8-byte loads of 4 uint16 (16-byte cp.async of 2 doubles) along the contiguous axis of either pass,
+  // 16-byte stores of output pairs along the other
+  const bool dims_ok = (in_dtype == AMT_U16) ? (w % 4 == 0 && h % 2 == 0) : (w % 2 == 0 && h % 2 == 0);
+  p.fast = !g_dog_generic && p.smem <= kSmemMax && fit >= 1 && n_img * (((h > w ? h : w) + 31) / 32) < (1ll << 31) &&
+           dims_ok && h >= 2 && w >= 4 && h * w < (1ll << 31) && r_lo <= RLO_MAX && r_hi >= r_lo && r_hi >= p.R &&
+           r_hi % p.R == 0 && (in_dtype == AMT_U16 || in_dtype == AMT_F64);
   return p;
 }
 
@@ -388,7 +418,7 @@ static int launch_strip(const DogPlan& p, const InT* in, const double* in_lo, do
                         int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st) {
   auto kernel = dog_strip_kernel<R, WARPS, MIN_CTAS, InT, SECOND>;
   AMT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  const int64_t items = planes * (inner / PV_TW);
+  const int64_t items = planes * ((inner + PV_TW - 1) / PV_TW);
   // one CTA per strip by default (the hardware scheduler balances the tail better than a static
   // round robin); dog_persistent = 1 launches exactly the resident CTAs and lets them loop
   const int64_t resident = g_dog_persistent ? (int64_t)kNumSMs * p.ctas : items;

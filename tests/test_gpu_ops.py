@@ -204,10 +204,11 @@ def test_plane_constant_division_matches_ddiv_bitwise():
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2])
-@pytest.mark.parametrize("shape", [(64, 96), (160, 64), (256, 256)])
+@pytest.mark.parametrize("shape", [(64, 96), (160, 64), (256, 256), (100, 332), (150, 68), (34, 36), (66, 1028)])
 def test_dog2d_strip_variants_bit_exact(variant, shape):
-    """Shapes with both sides multiples of 32 take the strip kernels of dog.cu; every tuning
-    variant must give scipy's bits, for uint16 and float64 input, plus the plane min/max."""
+    """Shapes with width % 4 == 0 and height % 2 == 0 take the strip kernels of dog.cu (narrow last
+    strip, short last step); every tuning variant must give scipy's bits, for uint16 and float64
+    input, plus the plane min/max."""
     from arcadia_microscopy_tools_b200 import _lib as L
 
     lib = L.load()
