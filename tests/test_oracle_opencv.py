@@ -95,3 +95,22 @@ def test_central_moments_and_axes_match_opencv():
             ang_cv = 0.5 * np.arctan2(2 * m["mu11"], m["mu20"] - m["mu02"])  # from the x (column) axis
             d = (props["orientation"][i] - (np.pi / 2 - ang_cv)) % np.pi
             assert min(d, np.pi - d) < 1e-6, (label, props["orientation"][i], ang_cv)
+
+
+@pytest.mark.parametrize("sigma", [0.6, 1.0, 2.5, 16.0])
+def test_gaussian_definition_matches_opencv(sigma):
+    """The Gaussian the DoG is built from (radius int(4*sigma + 0.5), weights exp(-x^2 / 2 sigma^2) normalised
+    to 1, edge-clamped borders) is also OpenCV's GaussianBlur with the same kernel size and BORDER_REPLICATE;
+    only the summation order differs, so the two agree to rounding error."""
+    from oracle import filters
+
+    rng = np.random.default_rng(int(sigma * 10))
+    img = rng.random((96, 120))
+    r = int(4.0 * sigma + 0.5)
+    got = filters.gaussian(img, sigma)
+    want = cv2.GaussianBlur(img, (2 * r + 1, 2 * r + 1), sigmaX=sigma, sigmaY=sigma, borderType=cv2.BORDER_REPLICATE)
+    assert np.allclose(got, want, rtol=0, atol=1e-13)
+    dog = filters.difference_of_gaussians(img, 0.6, sigma) if sigma > 0.6 else None
+    if dog is not None:
+        lo = cv2.GaussianBlur(img, (5, 5), sigmaX=0.6, sigmaY=0.6, borderType=cv2.BORDER_REPLICATE)
+        assert np.allclose(dog, lo - want, rtol=0, atol=1e-13)
