@@ -13,8 +13,9 @@
 //    samples it needs in a shared-memory ring of S-row blocks.  Every pass writes its result
 //    TRANSPOSED (out[col][row]): pass 1 filters the image along axis 0 and writes G^T, pass 2
 //    filters G^T along its axis 0 (= image axis 1) and writes lo - hi back in image layout.
-//    Loads are always lane-contiguous, and a thread's R outputs are contiguous in the output
-//    (R/2 16-byte stores), so no shared-memory transposition is needed anywhere.
+//    Loads are always lane-contiguous, and a thread's R outputs are contiguous in the output;
+//    they leave through a small per-warp staging tile so that every store instruction writes
+//    whole 128-byte lines (store_transposed).
 //  * the block of S rows the NEXT step needs is fetched while this step computes: uint16 input
 //    as two/four 8-byte loads per thread held in registers and converted (x * 1/65535) on the
 //    way into the ring, float64 input with cp.async straight into the ring.  One barrier per
@@ -27,7 +28,10 @@
 //    phase: while one is in a non-DP phase (fill, stores, barrier) the others keep the pipe busy.
 //  * any plane whose width is a multiple of 4 and height a multiple of 2 takes this path (narrow
 //    last strip, short last step); other shapes and radii use the tile kernels of gauss.cu.
-// The inner loop is conv_exact (conv.cuh).
+//  * the second pass also writes bucket12() of every output (2 bytes) for the percentile
+//    selection that follows (select.cu), which then reads those instead of the 8-byte samples.
+// The inner loop is conv_ring below: conv_exact of conv.cuh (used by the tile kernels of gauss.cu)
+// on a wrap-around ring.
 
 #include <cstdlib>
 #include <cstring>
