@@ -389,6 +389,7 @@ def run_b200(args) -> None:
         achieved = k[dom]["bytes"] / (dom_ms * 1e-3) / 1e9
         fp64_ach = k[dom]["dp_instr"] / (dom_ms * 1e-3) / 1e12
         traffic, traffic_src = ncu_traffic(dom, k["planes"])
+        dp_per_sample_axis = (1 + 3 * (len(hw[0]) - 1)) + (1 + 3 * (len(hw[1]) - 1))
         ms_per_step = 1e3 * dev_s / args.steps
         value = world * args.steps * n_fov * C * H * W / dev_s / 1e6
         line = {
@@ -421,6 +422,11 @@ def run_b200(args) -> None:
                               "unit": "T DP-instr/s", "frac": fp64_ach / k["fp64_peak_tinstr_s"],
                               "peak_source": "amt_fp64_probe (DMUL+DADD chains) timed in this run"},
             "kernels_ms": {"dog_axis0": k["ms_axis0"], "dog_axis1": k["ms_axis1"], "planes": k["planes"]},
+            # what binds the whole path: the exact-order float64 Gaussians need 2 * (1 + 3*r_lo + 1 + 3*r_hi) + 1 DP
+            # instructions per input sample; at the measured DP issue rate that caps one GPU at this many FOV/s
+            "path_fp64_ceiling": {"dp_instr_per_sample": 2 * dp_per_sample_axis + 1,
+                                  "fov_per_s_per_gpu": k["fp64_peak_tinstr_s"] * 1e12 / (C * H * W * (2 * dp_per_sample_axis + 1)),
+                                  "frac": (args.steps * n_fov / dev_s) / (k["fp64_peak_tinstr_s"] * 1e12 / (C * H * W * (2 * dp_per_sample_axis + 1)))},
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single()
