@@ -372,6 +372,7 @@ static int g_dog_ctas = 0;
 static int g_dog_persistent = 0;
 static int g_dog_generic = 0;
 extern int g_stream_ctas;     // gauss.cu
+extern int g_stream_pad_kb;   // gauss.cu
 extern int g_exec_swap_prio;  // executor.cu
 extern int g_pass_ctas;       // core.cu
 extern int g_exec_buckets;    // executor.cu
@@ -504,6 +505,9 @@ int amt_tune(const char* key, int value) {
   } else if (is("dog_ctas")) {
     if (value < 0 || value > 8) return AMT_ERR_INVALID;
     g_dog_ctas = value;
+  } else if (is("stream_pad_kb")) {
+    if (value < 0 || value > 200) return AMT_ERR_INVALID;
+    g_stream_pad_kb = value;
   } else if (is("stream_ctas")) {
     if (value < 1 || value > 32) return AMT_ERR_INVALID;
     g_stream_ctas = value;

@@ -254,6 +254,7 @@ __global__ void sub_f64_kernel(const double* __restrict__ a, const double* __res
 }
 
 constexpr size_t kMaxSmem = 227 * 1024;
+int g_stream_pad_kb = 0;
 int g_stream_ctas = 16;  // grid cap (CTAs per SM) of the grid-stride streaming kernels (amt_tune "stream_ctas")
 
 template <typename K>
@@ -350,7 +351,9 @@ int amt_sub_f64(const double* a, const double* b, double* out, int64_t n, amt_st
   if (n == 0) return AMT_OK;
   int64_t blocks = ceil_div(n, 256);
   if (blocks > kNumSMs * g_stream_ctas) blocks = kNumSMs * g_stream_ctas;
-  sub_f64_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(a, b, out, n);
+  const size_t pad = (size_t)g_stream_pad_kb * 1024;  // probe knob: dynamic shared memory the kernel never touches
+  if (pad > 48 * 1024) AMT_CUDA_TRY(cudaFuncSetAttribute(sub_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+  sub_f64_kernel<<<(unsigned)blocks, 256, pad, as_stream(stream)>>>(a, b, out, n);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }

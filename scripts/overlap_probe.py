@@ -28,7 +28,9 @@ b = torch.rand_like(a)
 c = torch.empty_like(a)
 lo_p, hi_p = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
 sA = torch.cuda.Stream(priority=0)
-sB = torch.cuda.Stream(priority=-1)
+import os
+
+sB = torch.cuda.Stream(priority=int(os.environ.get("PROBE_B_PRIORITY", "-1")))
 NA, NB = 6, 24
 
 
