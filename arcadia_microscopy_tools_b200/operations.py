@@ -23,7 +23,7 @@ from . import _gpu, _lib
 _THRESHOLD_METHODS = ("otsu", "li", "yen", "isodata", "mean", "minimum", "triangle", "local", "niblack", "sauvola")
 
 
-_GPU_THRESHOLD_METHODS = ("otsu", "isodata", "yen", "mean")
+_GPU_THRESHOLD_METHODS = ("otsu", "li", "yen", "isodata", "mean", "minimum", "triangle")
 
 
 def _device_op(func):
@@ -241,27 +241,193 @@ def _yen_from_histogram(counts: np.ndarray, centers: np.ndarray):
     return centers[crit.argmax()]
 
 
-def _apply_histogram_threshold(intensities, method: str, batched: bool):
-    """isodata / yen / mean: the per-pixel passes (min/max, histogram, comparison) run on the GPU;
-    the scan over the <= 65536 histogram bins is skimage's own NumPy arithmetic on the host
-    (ref: ``operations.py:185-196`` -> ``ski.filters.threshold_*`` [3p])."""
+def _triangle_from_histogram(counts: np.ndarray, centers: np.ndarray):
+    """skimage ``threshold_triangle`` on the image histogram: the bin farthest from the line that joins
+    the histogram peak with the far end of its longer tail (the histogram is flipped when the left
+    tail is the shorter one)."""
+    hist = np.asarray(counts)
+    nbins = len(hist)
+    arg_peak = int(np.argmax(hist))
+    peak_height = hist[arg_peak]
+    nonzero = np.flatnonzero(hist)
+    arg_low, arg_high = int(nonzero[0]), int(nonzero[-1])
+    flip = arg_peak - arg_low < arg_high - arg_peak
+    if flip:
+        hist = hist[::-1]
+        arg_low = nbins - arg_high - 1
+        arg_peak = nbins - arg_peak - 1
+    width = arg_peak - arg_low
+    x1 = np.arange(width)
+    y1 = hist[x1 + arg_low]
+    norm = np.sqrt(peak_height**2 + width**2)
+    peak_height = peak_height / norm
+    width = width / norm
+    length = peak_height * x1 - width * y1
+    arg_level = int(np.argmax(length)) + arg_low
+    if flip:
+        arg_level = nbins - arg_level - 1
+    return centers[arg_level]
+
+
+def _uniform3_float32(x: np.ndarray) -> np.ndarray:
+    """``scipy.ndimage.uniform_filter1d(x, 3)`` for a float32 line (mode='reflect'): scipy keeps ONE
+    running float64 window sum, ``s0 = x[-1]+x[0]+x[1]`` and ``s[k] = s[k-1] + (x[k+1] - x[k-2])``,
+    and writes ``s[k] / 3`` rounded to float32; ``np.cumsum`` performs the same additions in the same
+    order (checked bit for bit against scipy in ``tests/test_host_api.py``)."""
+    line = np.concatenate((x[:1], x, x[-1:])).astype(np.float64)
+    first = ((0.0 + line[0]) + line[1]) + line[2]
+    sums = np.cumsum(np.concatenate(([first], line[3:] - line[:-3])))
+    return (sums / 3.0).astype(np.float32)
+
+
+def _local_maxima(hist: np.ndarray) -> np.ndarray:
+    """skimage's ``find_local_maxima_idx`` (plateau-aware scan of ``threshold_minimum``), vectorised:
+    index i is a maximum when the first change before it (or the start) is a rise and hist[i+1] < hist[i]."""
+    d = np.sign(np.diff(hist.astype(np.float64)))
+    moving = np.flatnonzero(d)
+    if moving.size == 0:
+        return moving
+    s = d[moving]
+    prev = np.concatenate(([1.0], s[:-1]))  # the scan starts in the "rising" state
+    return moving[(s < 0) & (prev > 0)]
+
+
+def _minimum_from_histogram(counts: np.ndarray, centers: np.ndarray, max_num_iter: int = 10000):
+    """skimage ``threshold_minimum``: smooth the float32 histogram with a 3-bin mean until only two
+    maxima remain; the threshold is the lowest bin between them."""
+    smooth = np.asarray(counts).astype(np.float32, copy=False)
+    maxima = np.empty(0, dtype=np.intp)
+    counter = -1
+    for counter in range(max_num_iter):
+        smooth = _uniform3_float32(smooth)
+        maxima = _local_maxima(smooth)
+        if len(maxima) < 3:
+            break
+    if len(maxima) != 2:
+        raise RuntimeError("Unable to find two maxima in histogram")
+    if counter == max_num_iter - 1:
+        raise RuntimeError("Maximum iteration reached for histogram smoothing")
+    lowest = int(np.argmin(smooth[maxima[0] : maxima[1] + 1]))
+    return centers[maxima[0] + lowest]
+
+
+def _li_from_histogram(counts: np.ndarray, centers: np.ndarray, tolerance=None, initial_guess=None):
+    """skimage ``threshold_li`` for an integer image (minimum cross-entropy iteration on the exact
+    histogram of ``image - image.min()``, float32 weights as in skimage)."""
+    image_min = centers[0]
+    shifted = np.arange(len(centers))  # bin centres of the shifted image
+    tolerance = tolerance or 0.5
+    n = int(np.asarray(counts).sum())
+    if initial_guess is None:
+        # np.mean of the shifted integer image: float64 accumulation of integers is exact below 2**53
+        t_next = np.float64(int((np.asarray(counts, dtype=np.int64) * shifted).sum())) / np.float64(n)
+    elif callable(initial_guess):
+        raise NotImplementedError("a callable initial_guess would need the image on the host")
+    elif np.isscalar(initial_guess):
+        t_next = initial_guess - float(image_min)
+        image_max = shifted[-1] + image_min
+        if not 0 < t_next < shifted[-1]:
+            raise ValueError(
+                f"The initial guess for threshold_li must be within the range of the image. Got {initial_guess} "
+                f"for image min {image_min} and max {image_max}."
+            )
+    else:
+        raise TypeError("Incorrect type for `initial_guess`; should be a floating point value, or a function "
+                        "mapping an array to a floating point value.")
+    t_curr = -2 * tolerance
+    hist = np.asarray(counts).astype(np.float32, copy=False)
+    while abs(t_next - t_curr) > tolerance:
+        t_curr = t_next
+        foreground = shifted > t_curr
+        background = ~foreground
+        mean_fore = np.average(shifted[foreground], weights=hist[foreground])
+        mean_back = np.average(shifted[background], weights=hist[background])
+        if mean_back == 0:
+            break
+        t_next = (mean_back - mean_fore) / (np.log(mean_back) - np.log(mean_fore))
+    return t_next + image_min
+
+
+_THRESHOLD_KWARGS = {
+    "otsu": ("nbins",), "yen": ("nbins",), "isodata": ("nbins",), "triangle": ("nbins",), "mean": (),
+    "minimum": ("nbins", "max_num_iter"), "li": ("tolerance", "initial_guess"),
+}
+
+
+def _check_threshold_kwargs(method: str, kwargs: dict):
+    """The reference forwards ``**kwargs`` to the scikit-image function (``operations.py:214``): accept the
+    ones this path implements, refuse the rest loudly (an unknown name is a TypeError there as well)."""
+    for name in kwargs:
+        if name not in _THRESHOLD_KWARGS[method]:
+            raise TypeError(f"threshold_{method}() got an unexpected keyword argument '{name}'")
+    if kwargs.get("nbins", 256) != 256:
+        raise NotImplementedError("nbins other than 256 (scikit-image's default) is not built on the B200 path; "
+                                  "integer images ignore nbins anyway")
+
+
+def _otsu_from_histogram(counts: np.ndarray, centers: np.ndarray):
+    """skimage ``threshold_otsu`` scan (float32 class weights, float64 class means, first maximum); the
+    host twin of ``amt_otsu``, used for integer images that reach the GPU shifted by their minimum."""
+    counts = np.asarray(counts).astype(np.float32, copy=False)
+    weight1 = np.cumsum(counts)
+    weight2 = np.cumsum(counts[::-1])[::-1]
+    mean1 = np.cumsum(counts * centers) / weight1
+    mean2 = (np.cumsum((counts * centers)[::-1]) / weight2[::-1])[::-1]
+    variance12 = weight1[:-1] * weight2[1:] * (mean1[:-1] - mean2[1:]) ** 2
+    return centers[int(np.argmax(variance12))]
+
+
+def _shift_wide_integers(intensities):
+    """NumPy integer images other than uint8 / uint16 (scikit-image histograms them value by value,
+    whatever the dtype): travel as ``image - min`` in uint16 when the value range allows it; the
+    histogram scans then see the true bin centres again.  -> (array for the GPU, offset)."""
+    if _gpu.is_device_array(intensities):
+        return intensities, 0
+    a = np.asarray(intensities)
+    if a.dtype.kind not in "iu" or a.dtype in (np.uint8, np.uint16):
+        return a, 0
+    lo, hi = int(a.min()), int(a.max())
+    if hi - lo > 65535:
+        raise NotImplementedError(
+            f"{a.dtype} image spanning {hi - lo + 1} values: the exact per-value histogram of the B200 path holds 65536 bins")
+    shifted = a - np.uint64(lo) if a.dtype == np.uint64 else a.astype(np.int64) - lo
+    return shifted.astype(np.uint16), lo
+
+
+def _apply_histogram_threshold(intensities, method: str, batched: bool, kwargs: dict, offset: int = 0):
+    """li / isodata / yen / mean / minimum / triangle: the per-pixel passes (min/max, histogram,
+    comparison) run on the GPU; the scan over the <= 65536 histogram bins is skimage's own NumPy
+    arithmetic on the host (ref: ``operations.py:185-196`` -> ``ski.filters.threshold_*`` [3p])."""
     t, np_dtype, was_numpy = _prepare(intensities)
     planes = _slices(t, batched)
+    integer_image = np_dtype.kind in "iu" and planes.dtype != _gpu.torch_mod().float64
+    if method in ("mean", "li") and not integer_image:
+        raise NotImplementedError(
+            f"method '{method}' is implemented for uint8 / uint16 images only (scikit-image sums the float "
+            "pixels themselves there, in NumPy's pairwise order, which is not reproduced on the GPU)")
     hists = _gpu.plane_histograms(planes)
     thr = np.empty(planes.shape[0], dtype=np.float64)
     for i, (counts, centers) in enumerate(hists):
+        centers = centers + offset if offset else centers
         if len(centers) == 1 or counts.sum() == counts.max():  # constant plane: nothing is above it
             thr[i] = float(centers[int(np.argmax(counts))])
+        elif method == "otsu":
+            thr[i] = float(_otsu_from_histogram(counts, centers))
         elif method == "isodata":
             thr[i] = float(_isodata_from_histogram(counts, centers))
         elif method == "yen":
             thr[i] = float(_yen_from_histogram(counts, centers))
-        elif np_dtype.kind in "iu" and planes.dtype != _gpu.torch_mod().float64:
+        elif method == "triangle":
+            thr[i] = float(_triangle_from_histogram(counts, centers))
+        elif method == "minimum":
+            thr[i] = float(_minimum_from_histogram(counts, centers, kwargs.get("max_num_iter", 10000)))
+        elif method == "li":
+            thr[i] = float(_li_from_histogram(counts, centers, kwargs.get("tolerance"), kwargs.get("initial_guess")))
+        else:
             # np.mean of an integer image: exact integer sum (float64 accumulation is exact below 2**53)
             thr[i] = float(np.float64(int((counts * centers).sum())) / np.float64(planes.shape[1]))
-        else:
-            raise NotImplementedError("method 'mean' is implemented for uint8 / uint16 images only "
-                                      "(NumPy's pairwise float summation is not reproduced on the GPU)")
+    if offset:  # integer pixels: x > t  <=>  x > floor(t)  <=>  x - offset > floor(t) - offset, all exact
+        thr = np.floor(thr) - offset
     d_thr = _gpu.torch_mod().from_numpy(thr).to(planes.device)
     mask = _gpu.threshold_gt(planes, d_thr).reshape(t.shape).view(_gpu.torch_mod().bool)
     return _gpu.to_host(mask) if was_numpy else mask
@@ -278,9 +444,10 @@ def apply_threshold(
     """Binary image ``intensities > threshold`` (ref: ``operations.py:135-216``).
 
     Empty or constant input -> all False (checked before the method name, as in the
-    reference).  ``otsu``, ``isodata``, ``yen`` and ``mean`` run on the B200 path (skimage's
-    histogram: exact per-value counts for integer images, 256 uniform bins for float images); the
-    other six scikit-image methods the reference lists raise NotImplementedError.
+    reference).  ``otsu``, ``li``, ``yen``, ``isodata``, ``mean``, ``minimum`` and ``triangle`` run on
+    the B200 path (skimage's histogram: exact per-value counts for integer images, 256 uniform bins
+    for float images; ``li`` and ``mean`` for integer images only); the three local-window methods
+    (``local``, ``niblack``, ``sauvola``) raise NotImplementedError.
     """
     if not _gpu.is_device_array(intensities) and np.asarray(intensities).size == 0:
         return np.zeros_like(np.asarray(intensities), dtype=bool)
@@ -299,8 +466,10 @@ def apply_threshold(
             f"Thresholding method '{method}' is outside the B200 hot path "
             f"(implemented: {', '.join(_GPU_THRESHOLD_METHODS)})"
         )
-    if method_lower != "otsu":
-        return _apply_histogram_threshold(intensities, method_lower, _batched)
+    _check_threshold_kwargs(method_lower, kwargs)
+    intensities, offset = _shift_wide_integers(intensities)
+    if method_lower != "otsu" or offset:
+        return _apply_histogram_threshold(intensities, method_lower, _batched, kwargs, offset)
     t, _, was_numpy = _prepare(intensities)
     planes = _slices(t, _batched)
     # a constant plane gets threshold == its value, so nothing is above it (all False)

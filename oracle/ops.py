@@ -54,17 +54,18 @@ def subtract_background_dog(intensities, low_sigma=0.6, high_sigma=16.0, percent
     return np.clip(dog - background_level, 0, None)
 
 
-def apply_threshold(intensities, method="otsu"):
-    """ref: operations.py:135-216 (otsu, isodata, yen, mean; the other six methods are out of scope)."""
+def apply_threshold(intensities, method="otsu", **kwargs):
+    """ref: operations.py:135-216 (the seven histogram / global methods; local, niblack, sauvola are not restated)."""
     if intensities.size == 0:
         return np.zeros_like(intensities, dtype=bool)
     if intensities.min() == intensities.max():
         return np.zeros_like(intensities, dtype=bool)
     funcs = {"otsu": threshold.threshold_otsu, "isodata": threshold.threshold_isodata,
-             "yen": threshold.threshold_yen, "mean": threshold.threshold_mean}
+             "yen": threshold.threshold_yen, "mean": threshold.threshold_mean, "li": threshold.threshold_li,
+             "minimum": threshold.threshold_minimum, "triangle": threshold.threshold_triangle}
     if method.lower() not in funcs:
         raise ValueError(f"Unsupported thresholding method: '{method}'.")
-    return intensities > funcs[method.lower()](intensities)
+    return intensities > funcs[method.lower()](intensities, **kwargs)
 
 
 def process_mask(mask_image, remove_edge_cells):

@@ -136,3 +136,122 @@ def threshold_yen(image: np.ndarray, nbins: int = 256):
 
 def threshold_mean(image: np.ndarray):
     return np.mean(image)
+
+
+def threshold_triangle(image: np.ndarray, nbins: int = 256):
+    """``threshold_triangle`` (skimage 0.25.2 ``filters/thresholding.py``): histogram peak, the longer
+    tail (the histogram is flipped when the left tail is the shorter one), and the level with the largest distance to the peak-to-tail-end line."""
+    image = np.asarray(image)
+    hist, bin_centers = _image_histogram(image.reshape(-1), nbins)
+    nbins = len(hist)
+    arg_peak_height = np.argmax(hist)
+    peak_height = hist[arg_peak_height]
+    arg_low_level, arg_high_level = np.flatnonzero(hist)[[0, -1]]
+    if arg_low_level == arg_high_level:
+        return image.ravel()[0]
+    flip = arg_peak_height - arg_low_level < arg_high_level - arg_peak_height
+    if flip:
+        hist = hist[::-1]
+        arg_low_level = nbins - arg_high_level - 1
+        arg_peak_height = nbins - arg_peak_height - 1
+    del arg_high_level
+    width = arg_peak_height - arg_low_level
+    x1 = np.arange(width)
+    y1 = hist[x1 + arg_low_level]
+    norm = np.sqrt(peak_height**2 + width**2)
+    peak_height = peak_height / norm
+    width = width / norm
+    length = peak_height * x1 - width * y1
+    arg_level = np.argmax(length) + arg_low_level
+    if flip:
+        arg_level = nbins - arg_level - 1
+    return bin_centers[arg_level]
+
+
+def threshold_minimum(image: np.ndarray, nbins: int = 256, max_num_iter: int = 10000):
+    """``threshold_minimum``: the histogram is smoothed with the REAL ``scipy.ndimage.uniform_filter1d``
+    (size 3, float32) until two maxima remain; the maxima scan is skimage's plateau-aware loop."""
+    from scipy import ndimage as ndi
+
+    def find_local_maxima_idx(hist):
+        maximum_idxs = []
+        direction = 1
+        for i in range(hist.shape[0] - 1):
+            if direction > 0:
+                if hist[i + 1] < hist[i]:
+                    direction = -1
+                    maximum_idxs.append(i)
+            else:
+                if hist[i + 1] > hist[i]:
+                    direction = 1
+        return maximum_idxs
+
+    counts, bin_centers = _image_histogram(np.asarray(image).reshape(-1), nbins)
+    smooth_hist = counts.astype("float32", copy=False)
+    maximum_idxs = []
+    counter = -1
+    for counter in range(max_num_iter):
+        smooth_hist = ndi.uniform_filter1d(smooth_hist, 3)
+        maximum_idxs = find_local_maxima_idx(smooth_hist)
+        if len(maximum_idxs) < 3:
+            break
+    if len(maximum_idxs) != 2:
+        raise RuntimeError("Unable to find two maxima in histogram")
+    elif counter == max_num_iter - 1:
+        raise RuntimeError("Maximum iteration reached for histogram smoothing")
+    minimum_idx = np.argmin(smooth_hist[maximum_idxs[0] : maximum_idxs[1] + 1])
+    return bin_centers[maximum_idxs[0] + minimum_idx]
+
+
+def threshold_li(image: np.ndarray, *, tolerance=None, initial_guess=None):
+    """``threshold_li`` (minimum cross-entropy): iterate t <- (mean_back - mean_fore) / (log mean_back -
+    log mean_fore) on ``image - image.min()``; integer images iterate on their exact histogram with
+    float32 weights (``np.average``), float images on the pixels themselves."""
+    image = np.asarray(image)
+    image = image[~np.isnan(image)]
+    if image.size == 0:
+        return np.nan
+    if np.all(image == image.flat[0]):
+        return image.flat[0]
+    image = image[np.isfinite(image)]
+    if image.size == 0:
+        return 0.0
+    image_min = np.min(image)
+    image -= image_min
+    if image.dtype.kind in "iu":
+        tolerance = tolerance or 0.5
+    else:
+        tolerance = tolerance or np.min(np.diff(np.unique(image))) / 2
+    if initial_guess is None:
+        t_next = np.mean(image)
+    elif callable(initial_guess):
+        t_next = initial_guess(image)
+    elif np.isscalar(initial_guess):
+        t_next = initial_guess - float(image_min)
+        if not 0 < t_next < np.max(image):
+            raise ValueError("The initial guess for threshold_li must be within the range of the image.")
+    else:
+        raise TypeError("Incorrect type for `initial_guess`")
+    t_curr = -2 * tolerance
+    if image.dtype.kind in "iu":
+        hist, bin_centers = histogram_int(image.reshape(-1))
+        hist = hist.astype("float32", copy=False)
+        while abs(t_next - t_curr) > tolerance:
+            t_curr = t_next
+            foreground = bin_centers > t_curr
+            background = ~foreground
+            mean_fore = np.average(bin_centers[foreground], weights=hist[foreground])
+            mean_back = np.average(bin_centers[background], weights=hist[background])
+            if mean_back == 0:
+                break
+            t_next = (mean_back - mean_fore) / (np.log(mean_back) - np.log(mean_fore))
+    else:
+        while abs(t_next - t_curr) > tolerance:
+            t_curr = t_next
+            foreground = image > t_curr
+            mean_fore = np.mean(image[foreground])
+            mean_back = np.mean(image[~foreground])
+            if mean_back == 0.0:
+                break
+            t_next = (mean_back - mean_fore) / (np.log(mean_back) - np.log(mean_fore))
+    return t_next + image_min

@@ -294,12 +294,59 @@ def test_histogram_threshold_methods_match_oracle(method):
     got = operations.apply_threshold(u16, method, _batched=True)
     for i in range(3):
         assert np.array_equal(got[i], oracle.apply_threshold(u16[i], method))
-    if method != "mean":
+    if method != "mean":  # mean of float pixels: NumPy's pairwise summation is not reproduced on the device
         f = base / 65535.0
         for i in range(3):
             assert np.array_equal(operations.apply_threshold(f[i], method), oracle.apply_threshold(f[i], method)), (method, i)
     const = np.full((32, 32), 7, dtype=np.uint16)
     assert not operations.apply_threshold(const, method).any()
+
+
+@pytest.mark.parametrize("method", ["li", "minimum", "triangle"])
+def test_li_minimum_triangle_match_oracle(method):
+    """the remaining histogram-based methods of the reference's ``apply_threshold``; device
+    histogram + comparison, skimage's scalar scan on the host; masks must equal the oracle's bit for bit."""
+    rng = np.random.default_rng(77)
+    shape = (3, 150, 130)
+    fg = rng.random(shape) < 0.3
+    base = np.where(fg, rng.normal(900, 70, shape), rng.gamma(2.0, 70.0, shape)).clip(0, 65535)
+    u16 = base.astype(np.uint16)
+    for i in range(3):
+        got = operations.apply_threshold(u16[i], method)
+        want = oracle.apply_threshold(u16[i].copy(), method)
+        assert got.dtype == np.bool_ and 0 < want.sum() < want.size and np.array_equal(got, want), (method, i)
+    got = operations.apply_threshold(u16, method, _batched=True)
+    for i in range(3):
+        assert np.array_equal(got[i], oracle.apply_threshold(u16[i].copy(), method))
+    if method == "li":
+        kw = dict(tolerance=0.1, initial_guess=float(u16[0].mean()) * 1.4)
+        assert np.array_equal(operations.apply_threshold(u16[0], "li", **kw), oracle.apply_threshold(u16[0].copy(), "li", **kw))
+        with pytest.raises(NotImplementedError, match="uint8 / uint16 images only"):
+            operations.apply_threshold(base[0] / 65535.0, "li")
+    else:
+        f = base / 65535.0
+        for i in range(3):
+            assert np.array_equal(operations.apply_threshold(f[i], method), oracle.apply_threshold(f[i], method)), (method, i)
+    u8 = (base[0] / 8).clip(0, 255).astype(np.uint8)
+    assert np.array_equal(operations.apply_threshold(u8, method), oracle.apply_threshold(u8.copy(), method))
+    assert not operations.apply_threshold(np.full((32, 32), 7, dtype=np.uint16), method).any()
+    with pytest.raises(TypeError, match="unexpected keyword argument"):
+        operations.apply_threshold(u16[0], method, window_size=15)
+
+
+@pytest.mark.parametrize("method", ["otsu", "li", "yen", "isodata", "mean", "minimum", "triangle"])
+def test_thresholds_of_wide_integer_images(method):
+    """int32 / int64 images (negative values included) are histogrammed value by value in scikit-image;
+    here they travel as image - min in uint16 and the scans see the true bin centres."""
+    rng = np.random.default_rng(78)
+    shape = (120, 110)
+    fg = rng.random(shape) < 0.3
+    base = np.where(fg, rng.normal(900, 70, shape), rng.gamma(2.0, 70.0, shape))
+    for dtype, shift in ((np.int32, -700), (np.int64, 100000), (np.int16, -300), (np.uint32, 0)):
+        img = (base + shift).astype(dtype)
+        got = operations.apply_threshold(img, method)
+        want = oracle.apply_threshold(img.copy(), method)
+        assert 0 < want.sum() < want.size and np.array_equal(got, want), (method, dtype)
 
 
 def test_bucketed_selection_matches_sorted_order():

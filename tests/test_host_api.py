@@ -123,8 +123,8 @@ def test_operation_argument_validation_matches_reference_messages():
     with pytest.raises(ValueError, match="Unsupported thresholding method: 'nope'"):
         operations.apply_threshold(x, method="nope")
     with pytest.raises(NotImplementedError, match="outside the B200 hot path"):
-        operations.apply_threshold(x, method="li")
-    assert not operations.apply_threshold(np.full((3, 3), 5, np.uint16), method="li").any()
+        operations.apply_threshold(x, method="sauvola")
+    assert not operations.apply_threshold(np.full((3, 3), 5, np.uint16), method="sauvola").any()
 
 
 def test_crop_to_center_is_a_view():
@@ -250,3 +250,62 @@ def test_nd2_raw_reader_and_frame_layout(tmp_path):
         got = np.stack([np.frombuffer(mm[o : o + h * w * c * 2].tobytes(), dtype="<u2").reshape(h, w, c).transpose(2, 0, 1)
                         for o in offsets])
         assert np.array_equal(got, want), f.name
+
+
+# ---------------------------------------------------------------- threshold scans (host plan step)
+def _bimodal(rng, shape, scale=1.0):
+    fg = rng.random(shape) < 0.3
+    return np.where(fg, rng.normal(900 * scale, 70 * scale, shape), rng.gamma(2.0, 70.0 * scale, shape)).clip(0, 65535)
+
+
+def test_histogram_scans_of_the_product_match_the_oracle_restatements():
+    """The product's host scans over a device histogram (li, minimum, triangle, otsu twin) against the
+    oracle's restatements of scikit-image, on exact integer histograms and 256-bin float histograms."""
+    from oracle import threshold as T
+
+    rng = np.random.default_rng(2026)
+    for trial in range(5):
+        base = _bimodal(rng, (150, 130), 1.0 + 0.3 * trial)
+        u16 = base.astype(np.uint16)
+        counts, centers = T.histogram_int(u16)
+        assert operations._triangle_from_histogram(counts, centers) == T.threshold_triangle(u16)
+        assert operations._minimum_from_histogram(counts, centers) == T.threshold_minimum(u16)
+        assert operations._li_from_histogram(counts, centers) == T.threshold_li(u16.copy())
+        assert operations._li_from_histogram(counts, centers, initial_guess=float(u16.mean()) * 1.5, tolerance=0.1) == \
+            T.threshold_li(u16.copy(), initial_guess=float(u16.mean()) * 1.5, tolerance=0.1)
+        assert operations._otsu_from_histogram(counts, centers) == T.threshold_otsu(u16)
+        f64 = base / 65535.0
+        counts, centers = T.histogram_float_256(f64)
+        assert operations._triangle_from_histogram(counts, centers) == T.threshold_triangle(f64)
+        assert operations._minimum_from_histogram(counts, centers) == T.threshold_minimum(f64)
+    flat = rng.poisson(20.0, (64, 64)).astype(np.uint16)  # one mode: no two maxima survive the smoothing
+    counts, centers = T.histogram_int(flat)
+    with pytest.raises(RuntimeError, match="Unable to find two maxima"):
+        T.threshold_minimum(flat)
+    with pytest.raises(RuntimeError, match="Unable to find two maxima"):
+        operations._minimum_from_histogram(counts, centers)
+
+
+def test_three_bin_mean_is_scipys_uniform_filter_bit_for_bit():
+    from scipy import ndimage as ndi
+
+    rng = np.random.default_rng(8)
+    for n in (2, 3, 7, 256, 65536):
+        line = rng.integers(0, 90000, n).astype(np.float32)
+        for _ in range(6):
+            want = ndi.uniform_filter1d(line, 3)
+            assert np.array_equal(operations._uniform3_float32(line), want), n
+            line = want
+
+
+def test_threshold_keyword_arguments_are_checked():
+    with pytest.raises(TypeError, match="unexpected keyword argument 'window_size'"):
+        operations._check_threshold_kwargs("otsu", {"window_size": 5})
+    with pytest.raises(NotImplementedError, match="nbins"):
+        operations._check_threshold_kwargs("yen", {"nbins": 64})
+    operations._check_threshold_kwargs("li", {"tolerance": 0.25, "initial_guess": 300.0})
+    wide = np.array([[-70000, 3], [5, 9]], dtype=np.int64)
+    with pytest.raises(NotImplementedError, match="65536 bins"):
+        operations._shift_wide_integers(wide)
+    shifted, offset = operations._shift_wide_integers(np.array([[-5, 3], [5, 9]], dtype=np.int32))
+    assert shifted.dtype == np.uint16 and offset == -5 and shifted.tolist() == [[0, 8], [10, 14]]
