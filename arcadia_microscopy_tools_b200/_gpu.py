@@ -374,3 +374,44 @@ def region_table(labels, counts, channels, max_labels: int, with_shape: bool = F
             "amt_region_shape",
         )
     return table, acc
+
+
+def outline_square_keys(labels2d) -> np.ndarray:
+    """Sorted marching-squares keys of one (H, W) int32 device label image (``amt_outline_squares``):
+    ``label<<34 | r0<<19 | c0<<4 | case``, i.e. per label the non-trivial squares in raster order."""
+    torch = torch_mod()
+    lib = _lib.load()
+    h, w = labels2d.shape
+    count = torch.zeros(1, dtype=torch.int64, device=labels2d.device)
+    capacity = max(4096, (h * w) // 8)
+    while True:
+        keys = torch.empty(capacity, dtype=torch.int64, device=labels2d.device)
+        check(lib.amt_outline_squares(ptr(labels2d), h, w, ptr(keys), capacity, ptr(count), stream_ptr()),
+              "amt_outline_squares")
+        n = int(count.item())
+        if n <= capacity:
+            break
+        capacity = n
+    return np.sort(to_host(keys[:n]).view(np.uint64))
+
+
+def outline_borders(labels2d, n_labels: int, min_points: int = 5):
+    """OpenCV-ordered outer border of every label 1..n_labels of one (H, W) int32 device label image
+    (``amt_outline_trace_find`` / ``_write``): -> (points int32 (N, 2) as (y, x), offsets int64
+    (n_labels + 1)); labels whose longest border has fewer than ``min_points`` points get an empty range."""
+    torch = torch_mod()
+    lib = _lib.load()
+    h, w = labels2d.shape
+    best = torch.empty(max(n_labels, 1), dtype=torch.int64, device=labels2d.device)
+    check(lib.amt_outline_trace_find(ptr(labels2d), h, w, max(n_labels, 1), ptr(best), stream_ptr()),
+          "amt_outline_trace_find")
+    lengths = (to_host(best).view(np.uint64) >> np.uint64(32)).astype(np.int64)[:n_labels]
+    lengths[lengths < min_points] = 0
+    offsets = np.concatenate(([0], np.cumsum(lengths))).astype(np.int64)
+    total = int(offsets[-1])
+    points = torch.empty((max(total, 1), 2), dtype=torch.int32, device=labels2d.device)
+    if n_labels > 0 and total > 0:
+        d_off = torch.from_numpy(offsets).to(labels2d.device)
+        check(lib.amt_outline_trace_write(ptr(labels2d), h, w, n_labels, ptr(best), ptr(d_off), ptr(points), stream_ptr()),
+              "amt_outline_trace_write")
+    return to_host(points)[:total], offsets

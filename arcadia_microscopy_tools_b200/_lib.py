@@ -139,6 +139,9 @@ SIGNATURES: dict[str, tuple] = {
     "amt_region_finalize3d": (_i, [_p, _i64, _i, _i64, _p, _p]),
     "amt_region_shape_scratch_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "amt_region_shape": (_i, [_p, _p, _i, _p, _i64, _i64, _i64, _i64, _p, _p, _sz, _p]),
+    "amt_outline_squares": (_i, [_p, _i64, _i64, _p, _i64, _p, _p]),
+    "amt_outline_trace_find": (_i, [_p, _i64, _i64, _i64, _p, _p]),
+    "amt_outline_trace_write": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "amt_executor_create": (_i, [C.POINTER(FovConfig), C.POINTER(_d), _i, C.POINTER(_d), _i, C.POINTER(_p)]),
     "amt_executor_destroy": (None, [_p]),
     "amt_executor_device_bytes": (_sz, [_p]),

@@ -6,13 +6,15 @@ Drop-in for the hot-path part of the reference's ``masks.py``: ``_process_mask``
 ``convert_properties_to_microns`` (:420-467) — same arguments, defaults, key order, dtypes and
 error messages.  Labelling, border clearing, relabelling and every regionprops statistic are
 CUDA kernels (``ccl.cu``, ``regions.cu``, ``shape.cu``); the reference's per-region Python loop
-and its one-rescan-per-channel become a single streaming pass.  Outline extraction
-(:68-115, :229-245) is plotting support and stays out of scope.
+and its one-rescan-per-channel become a single streaming pass.  ``cell_outlines`` (:68-115,
+:229-245): the pixel passes (marching-squares cases, OpenCV-style border following) are kernels of
+``outlines.cu``; joining a cell's few dozen contour segments into an ordered polygon is host work.
 """
 
 from __future__ import annotations
 
 import warnings
+from collections import deque
 from collections.abc import Mapping
 from functools import cached_property
 from typing import ClassVar, Literal
@@ -92,6 +94,81 @@ def _process_mask(mask_image: np.ndarray, remove_edge_cells: bool) -> np.ndarray
     if remove_edge_cells and count == 0:
         raise ValueError("No cells remain after removing edge cells. Try setting remove_edge_cells=False.")
     return _gpu.to_host(labels[0]).astype(np.int64)
+
+
+
+# ---- skimage.measure.find_contours, host part: segments of the marching-squares cases and their
+# assembly into ordered contours (skimage ``_find_contours_cy._get_contour_segments`` with
+# fully_connected='low', positive_orientation='low', and ``_find_contours._assemble_contours``) [3p].
+# Points are kept as integer pairs (2*row, 2*col): every contour point of a binary image at level 0.5
+# is an edge midpoint, so the doubled coordinates are exact.
+def _case_segments(r2: int, c2: int, case: int):
+    """(from, to) point pairs of one square whose upper-left pixel is (r2/2, c2/2)."""
+    top, bottom = (r2, c2 + 1), (r2 + 2, c2 + 1)
+    left, right = (r2 + 1, c2), (r2 + 1, c2 + 2)
+    table = {
+        1: ((top, left),), 2: ((right, top),), 3: ((right, left),), 4: ((left, bottom),),
+        5: ((top, bottom),), 6: ((right, top), (left, bottom)), 7: ((right, bottom),),
+        8: ((bottom, right),), 9: ((top, left), (bottom, right)), 10: ((bottom, top),),
+        11: ((bottom, left),), 12: ((left, right),), 13: ((top, right),), 14: ((left, top),),
+    }
+    return table[case]
+
+
+def _join_segments(segments) -> list[list[tuple[int, int]]]:
+    """Chains directed segments head to tail in the order given.  When a segment links two chains the
+    one created first survives (the other is appended / prepended to it), which fixes both the order
+    of the returned contours and the point each closed contour starts from."""
+    chains: dict[int, deque] = {}
+    by_start: dict[tuple[int, int], int] = {}
+    by_end: dict[tuple[int, int], int] = {}
+    serial = 0
+    for src, dst in segments:
+        after = by_start.pop(dst, None)   # chain that begins where this segment ends
+        before = by_end.pop(src, None)    # chain that ends where this segment begins
+        if after is None and before is None:
+            chains[serial] = deque((src, dst))
+            by_start[src] = serial
+            by_end[dst] = serial
+            serial += 1
+        elif before is None:
+            chains[after].appendleft(src)
+            by_start[src] = after
+        elif after is None:
+            chains[before].append(dst)
+            by_end[dst] = before
+        elif after == before:  # the chain closes on itself
+            chains[before].append(dst)
+        elif after > before:  # the later chain is appended to the earlier one
+            tail = chains.pop(after)
+            chains[before].extend(tail)
+            by_end[chains[before][-1]] = before
+        else:  # the later chain (ending at src) goes in front of the earlier one
+            head = chains.pop(before)
+            by_start.pop(head[0], None)
+            chains[after].extendleft(reversed(head))
+            by_start[chains[after][0]] = after
+    return [list(chains[k]) for k in sorted(chains)]
+
+
+def _contours_from_square_keys(keys: np.ndarray, num_cells: int) -> list[np.ndarray]:
+    """keys: sorted ``label<<34 | r0<<19 | c0<<4 | case`` (``amt_outline_squares``) -> per label the
+    longest contour (first of equals) as float64 (y, x) points in image coordinates."""
+    labels = (keys >> np.uint64(34)).astype(np.int64)
+    rows2 = (2 * ((keys >> np.uint64(19)) & np.uint64(0x7FFF))).astype(np.int64).tolist()
+    cols2 = (2 * ((keys >> np.uint64(4)) & np.uint64(0x7FFF))).astype(np.int64).tolist()
+    cases = (keys & np.uint64(15)).astype(np.int64).tolist()
+    bounds = np.searchsorted(labels, np.arange(1, num_cells + 2))
+    outlines = []
+    for k in range(num_cells):
+        lo, hi = int(bounds[k]), int(bounds[k + 1])
+        segments = [seg for i in range(lo, hi) for seg in _case_segments(rows2[i], cols2[i], cases[i])]
+        contours = _join_segments(segments)
+        if contours:
+            outlines.append(np.array(max(contours, key=len), dtype=np.float64) / 2.0)
+        else:
+            outlines.append(np.array([]).reshape(0, 2))
+    return outlines
 
 
 class SegmentationMask:
@@ -188,10 +265,21 @@ class SegmentationMask:
         return int(self._labels_device[1])
 
     @cached_property
-    def cell_outlines(self):
-        raise NotImplementedError(
-            "cell_outlines (contour extraction for plotting) is outside the B200 hot path"
-        )
+    def cell_outlines(self) -> list[np.ndarray]:
+        """One (y, x) outline per cell, index i = label i + 1, an empty (0, 2) array where no contour
+        exists (ref: ``masks.py:229-245``).  ``outline_extractor="cellpose"``: OpenCV's outer border of
+        the label (``cellpose.utils.outlines_list``: longest contour, more than 4 points), traced on the
+        GPU; ``"skimage"``: ``find_contours`` at level 0.5 on the 1-px padded crop (``masks.py:82-115``),
+        marching-squares cases from the GPU, joined into ordered contours here."""
+        labels = self._labels_device[0][0]
+        if self.outline_extractor == "cellpose":
+            points, offsets = _gpu.outline_borders(labels, self.num_cells)
+            points = points.astype(np.int64)
+            return [
+                points[offsets[k] : offsets[k + 1]] if offsets[k + 1] > offsets[k] else np.zeros((0, 2))
+                for k in range(self.num_cells)
+            ]
+        return _contours_from_square_keys(_gpu.outline_square_keys(labels), self.num_cells)
 
     # ------------------------------------------------------------------ properties
     @cached_property

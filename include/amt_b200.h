@@ -263,6 +263,30 @@ int amt_region_shape(const int32_t* labels, const uint64_t* acc, int n_channels,
                      int64_t n_img, int64_t h, int64_t w, int64_t max_labels, double* table,
                      void* scratch, size_t scratch_bytes, amt_stream_t stream);
 
+/* ------------------------------------------------------------------ cell outlines
+ * ref: masks.py:229-245 SegmentationMask.cell_outlines -> masks.py:82-115 (_extract_outlines_skimage,
+ * skimage.measure.find_contours at level 0.5 on the padded crop label == n) and masks.py:68-79
+ * (_extract_outlines_cellpose -> cv2.findContours(label == n, RETR_EXTERNAL, CHAIN_APPROX_NONE)).
+ * labels: one h x w int32 label image (1..K, 0 = background), device memory.
+ *
+ * amt_outline_squares: marching-squares case of every 2x2 pixel square for every label at its
+ * corners: keys[i] = label<<34 | r0<<19 | c0<<4 | case (case = ul | ur<<1 | ll<<2 | lr<<3, never 0 or
+ * 15), in no particular order (sort them: per label, raster order of the squares = the order
+ * find_contours emits its segments in).  *count (device) = number of keys the image holds; only the
+ * first `capacity` are stored, call again with a larger buffer when *count > capacity.
+ *
+ * amt_outline_trace_find: best[L-1] = (points << 32 | raster index of the start pixel) of the longest
+ * outer border among the 8-connected fragments of label L, 0 when L is absent (ties: later start).
+ * amt_outline_trace_write: writes the border of label k+1 as (y, x) int32 pairs, in OpenCV's point
+ * order, at points[2*offsets[k] .. 2*offsets[k+1]) (offsets: n_labels+1 device int64; an empty range
+ * skips the label). */
+int amt_outline_squares(const int32_t* labels, int64_t h, int64_t w, uint64_t* keys, int64_t capacity,
+                        uint64_t* count, amt_stream_t stream);
+int amt_outline_trace_find(const int32_t* labels, int64_t h, int64_t w, int64_t max_labels, uint64_t* best,
+                           amt_stream_t stream);
+int amt_outline_trace_write(const int32_t* labels, int64_t h, int64_t w, int64_t n_labels, const uint64_t* best,
+                            const int64_t* offsets, int32_t* points, amt_stream_t stream);
+
 /* ------------------------------------------------------------------ fused FOV executor
  * The native runtime for the batch path (bench + MicroscopyImage batch pipeline): owns its
  * streams, device scratch and pinned double-buffered staging, and runs the whole workload W

@@ -32,7 +32,7 @@ Pinning status
   which ``tests/test_oracle.py`` re-checks.
 """
 
-from . import exposure, filters, labeling, percentile, regionprops, threshold  # noqa: F401
+from . import exposure, filters, labeling, outlines, percentile, regionprops, threshold  # noqa: F401
 from .ops import (  # noqa: F401
     apply_threshold,
     cell_properties,
