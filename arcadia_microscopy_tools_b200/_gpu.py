@@ -139,23 +139,28 @@ def dog2d(x, scale: float, low_sigma: float, high_sigma: float):
     return out, mm
 
 
-def gaussian_nd(x, scale: float, sigma: float):
-    """All-axes Gaussian of one N-D array (scipy's axis order 0, 1, ...)."""
+def gaussian_nd(x, scale: float, sigma, mode: int = 0):
+    """All-axes Gaussian of one N-D array (scipy's axis order 0, 1, ...).  sigma: one value or one per
+    axis; mode: 0 = scipy 'nearest', 1 = scipy 'reflect' (``AMT_EXTEND_*``)."""
     torch = torch_mod()
     lib = _lib.load()
-    hw = gaussian_half_weights(sigma)
-    d_hw = torch.from_numpy(hw).to(x.device)
     shape = tuple(x.shape)
+    sigmas = [float(sigma)] * len(shape) if np.isscalar(sigma) else [float(s) for s in sigma]
+    if len(sigmas) != len(shape):
+        raise ValueError("sigma must be a scalar or have one entry per axis")
     cur = x
     code = dtype_code(x)
     for axis in range(len(shape)):
+        hw = gaussian_half_weights(sigmas[axis])
+        d_hw = torch.from_numpy(hw).to(x.device)
         outer = int(np.prod(shape[:axis], dtype=np.int64))
         n = shape[axis]
         inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
         out = torch.empty(shape, dtype=torch.float64, device=x.device)
         check(
-            lib.amt_gaussian_axis(ptr(cur), code, scale, ptr(out), outer, n, inner, ptr(d_hw), len(hw) - 1, stream_ptr()),
-            "amt_gaussian_axis",
+            lib.amt_gaussian_axis_mode(ptr(cur), code, scale, ptr(out), outer, n, inner, ptr(d_hw), len(hw) - 1, mode,
+                                       stream_ptr()),
+            "amt_gaussian_axis_mode",
         )
         cur, code = out, AMT_F64
     return cur
@@ -415,3 +420,27 @@ def outline_borders(labels2d, n_labels: int, min_points: int = 5):
         check(lib.amt_outline_trace_write(ptr(labels2d), h, w, n_labels, ptr(best), ptr(d_off), ptr(points), stream_ptr()),
               "amt_outline_trace_write")
     return to_host(points)[:total], offsets
+
+
+def window_threshold_u16(x3d, window: tuple[int, int], kind: int, k: float, r: float, want_thresholds: bool = False):
+    """niblack (kind 0) / sauvola (kind 1) of (n_img, H, W) uint16 planes -> uint8 mask (and the float64
+    threshold image when asked for)."""
+    torch = torch_mod()
+    n_img, h, w = x3d.shape
+    mask = torch.empty((n_img, h, w), dtype=torch.uint8, device=x3d.device)
+    thr = torch.empty((n_img, h, w), dtype=torch.float64, device=x3d.device) if want_thresholds else None
+    check(
+        _lib.load().amt_window_threshold_u16(ptr(x3d), n_img, h, w, int(window[0]), int(window[1]), kind, float(k),
+                                             float(r), ptr(mask), ptr(thr), stream_ptr()),
+        "amt_window_threshold_u16",
+    )
+    return mask, thr
+
+
+def threshold_gt_image(x, thr, offset: float):
+    """mask = x > thr - offset, elementwise (x uint16 or float64, thr float64, same shape)."""
+    torch = torch_mod()
+    mask = torch.empty(tuple(x.shape), dtype=torch.uint8, device=x.device)
+    check(_lib.load().amt_threshold_gt_image(ptr(x), dtype_code(x), x.numel(), ptr(thr), float(offset), ptr(mask),
+                                             stream_ptr()), "amt_threshold_gt_image")
+    return mask

@@ -21,6 +21,7 @@ AMT_ERR_UNSUPPORTED = -4
 
 AMT_U8, AMT_U16, AMT_I32, AMT_F64 = 0, 1, 2, 3
 AMT_MAX_RANKS = 8
+AMT_EXTEND_NEAREST, AMT_EXTEND_REFLECT = 0, 1  # amt_gaussian_axis_mode
 AMT_MAP_SUBCLIP, AMT_MAP_RESCALE, AMT_MAP_FILL = 1, 2, 4
 AMT_ACC_BASE, AMT_ACC_PER_CHANNEL = 10, 4
 AMT_TABLE_BASE, AMT_TABLE_PER_CHANNEL = 16, 5
@@ -109,6 +110,7 @@ SIGNATURES: dict[str, tuple] = {
     "amt_tune": (_i, [C.c_char_p, _i]),
     "amt_selftest_div": (_i, [_p, _p, _i64, _p, _p]),
     "amt_gaussian_axis": (_i, [_p, _i, _d, _p, _i64, _i64, _i64, _p, _i, _p]),
+    "amt_gaussian_axis_mode": (_i, [_p, _i, _d, _p, _i64, _i64, _i64, _p, _i, _i, _p]),
     "amt_dog2d": (_i, [_p, _i, _d, _p, _i64, _i64, _i64, _p, _i, _p, _i, _p, _p, _p, _p]),
     "amt_dog2d_axis0": (_i, [_p, _i, _d, _i64, _i64, _i64, _p, _i, _p, _i, _p, _p, _p]),
     "amt_dog2d_axis1": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _i, _p, _i, _p, _p]),
@@ -131,6 +133,8 @@ SIGNATURES: dict[str, tuple] = {
     "amt_otsu_scratch_bytes": (_sz, [_i, _i64]),
     "amt_otsu": (_i, [_p, _i, _p, _p, _i64, _p, _p, _sz, _p]),
     "amt_threshold_gt": (_i, [_p, _i, _i64, _i64, _p, _p, _p]),
+    "amt_window_threshold_u16": (_i, [_p, _i64, _i64, _i64, _i, _i, _i, _d, _d, _p, _p, _p]),
+    "amt_threshold_gt_image": (_i, [_p, _i, _i64, _p, _d, _p, _p]),
     "amt_label_scratch_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "amt_label": (_i, [_p, _i, _p, _i64, _i64, _i64, _i64, _i, _p, _p, _p, _sz, _p]),
     "amt_region_reduce": (_i, [_p, _p, _i, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p]),

@@ -38,6 +38,16 @@ __device__ __forceinline__ void conv_window(const double* __restrict__ col, cons
   conv_exact<R>([&](int k) -> double { return col[k * stride]; }, hw, r, acc);
 }
 
+// boundary extension of a sample index: 0 = scipy mode 'nearest' (the path of the reference's DoG),
+// 1 = scipy mode 'reflect' (d c b a | a b c d | d c b a; threshold_local's default)
+__device__ __forceinline__ int64_t extend_index(int64_t i, const int64_t n, const int mode) {
+  if (mode == 0) return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+  const int64_t period = 2 * n;
+  i %= period;
+  i = i < 0 ? i + period : i;
+  return i < n ? i : period - 1 - i;
+}
+
 // ------------------------------------------------------------------ V pass
 constexpr int GV_TW = 32;
 constexpr int GV_TH = 64;  // = 8 thread rows * GR
@@ -47,7 +57,8 @@ template <typename InT, bool DUAL>
 __global__ void __launch_bounds__(256, 3)
 gauss_v_kernel(const InT* __restrict__ in, const double scale, double* __restrict__ out_a,
                double* __restrict__ out_b, const int64_t n, const int64_t inner,
-               const double* __restrict__ hw_a, const int r_a, const double* __restrict__ hw_b, const int r_b) {
+               const double* __restrict__ hw_a, const int r_a, const double* __restrict__ hw_b, const int r_b,
+               const int mode) {
   extern __shared__ double smem[];
   const int rmax = DUAL ? (r_a > r_b ? r_a : r_b) : r_a;
   const int rows = GV_TH + 2 * rmax;
@@ -72,7 +83,7 @@ gauss_v_kernel(const InT* __restrict__ in, const double scale, double* __restric
     for (int i = 0; i < GV_BATCH; ++i) {
       const int s = ty + 8 * i;
       int64_t y = y0 - rmax + s;
-      y = y < 0 ? 0 : (y > n - 1 ? n - 1 : y);  // mode='nearest'
+      y = extend_index(y, n, mode);
       raw[i] = (xok && s < rows) ? __ldg(src + y * inner + x) : InT(0);
     }
 #pragma unroll
@@ -83,7 +94,7 @@ gauss_v_kernel(const InT* __restrict__ in, const double scale, double* __restric
   } else {
     for (int s = ty; s < rows; s += 8) {
       int64_t y = y0 - rmax + s;
-      y = y < 0 ? 0 : (y > n - 1 ? n - 1 : y);
+      y = extend_index(y, n, mode);
       tile[s * GV_TW + tx] = xok ? load_as_f64<InT>(src + y * inner + x, scale) : 0.0;
     }
   }
@@ -118,7 +129,8 @@ constexpr int GH_BATCH = 6;  // column groups per thread and row when radius <= 
 template <typename InT>
 __device__ __forceinline__ void gh_load_tile(double* tile, const InT* __restrict__ src, const double scale,
                                              const int64_t row0, const int64_t nrows, const int64_t n,
-                                             const int64_t x0, const int r, const int warp, const int lane) {
+                                             const int64_t x0, const int r, const int warp, const int lane,
+                                             const int mode) {
   const int width = GH_TX + 2 * r;
   if (width <= 32 * GH_BATCH) {
     // 4 rows x GH_BATCH column groups per thread, every load issued before the first store
@@ -132,7 +144,7 @@ __device__ __forceinline__ void gh_load_tile(double* tile, const InT* __restrict
       for (int i = 0; i < GH_BATCH; ++i) {
         const int xx = lane + 32 * i;
         int64_t gx = x0 - r + xx;
-        gx = gx < 0 ? 0 : (gx > n - 1 ? n - 1 : gx);
+        gx = extend_index(gx, n, mode);
         raw[k][i] = (rok && xx < width) ? __ldg(p + gx) : InT(0);
       }
     }
@@ -152,7 +164,7 @@ __device__ __forceinline__ void gh_load_tile(double* tile, const InT* __restrict
     const InT* p = src + (rok ? row : 0) * n;
     for (int xx = lane; xx < width; xx += 32) {
       int64_t gx = x0 - r + xx;
-      gx = gx < 0 ? 0 : (gx > n - 1 ? n - 1 : gx);
+      gx = extend_index(gx, n, mode);
       tile[xx * GH_PITCH + rr] = rok ? load_as_f64<InT>(p + gx, scale) : 0.0;
     }
   }
@@ -165,7 +177,7 @@ __global__ void __launch_bounds__(256, 3)
 gauss_h_kernel(const InT* __restrict__ in_a, const double* __restrict__ in_b, const double scale,
                double* __restrict__ out, const int64_t nrows, const int64_t n,
                const double* __restrict__ hw_a, const int r_a, const double* __restrict__ hw_b, const int r_b,
-               uint64_t* __restrict__ minmax) {
+               uint64_t* __restrict__ minmax, const int mode) {
   extern __shared__ double smem[];
   double* tile_a = smem;
   double* tile_b = tile_a + (GH_TX + 2 * r_a) * GH_PITCH;
@@ -182,8 +194,8 @@ gauss_h_kernel(const InT* __restrict__ in_a, const double* __restrict__ in_b, co
   const int64_t row0 = (int64_t)blockIdx.x * GH_ROWS;
   const int64_t x0 = (int64_t)blockIdx.y * GH_TX;
   const int64_t plane = (int64_t)blockIdx.z * nrows * n;
-  gh_load_tile<InT>(tile_a, in_a + plane, scale, row0, nrows, n, x0, r_a, warp, lane);
-  if (DUAL) gh_load_tile<double>(tile_b, in_b + plane, 1.0, row0, nrows, n, x0, r_b, warp, lane);
+  gh_load_tile<InT>(tile_a, in_a + plane, scale, row0, nrows, n, x0, r_a, warp, lane, mode);
+  if (DUAL) gh_load_tile<double>(tile_b, in_b + plane, 1.0, row0, nrows, n, x0, r_b, warp, lane, mode);
   __syncthreads();
 
   double acc[GR];
@@ -268,14 +280,15 @@ static int set_smem(K kernel, size_t bytes) {
 
 template <typename InT, bool DUAL>
 static int launch_v(const InT* in, double scale, double* out_a, double* out_b, int64_t outer, int64_t n,
-                    int64_t inner, const double* hw_a, int r_a, const double* hw_b, int r_b, cudaStream_t st) {
+                    int64_t inner, const double* hw_a, int r_a, const double* hw_b, int r_b, cudaStream_t st,
+                    int mode = 0) {
   const int rmax = DUAL ? (r_a > r_b ? r_a : r_b) : r_a;
   const size_t smem = ((size_t)(GV_TH + 2 * rmax) * GV_TW + (r_a + 1) + (DUAL ? r_b + 1 : 0)) * sizeof(double);
   AMT_TRY(set_smem(gauss_v_kernel<InT, DUAL>, smem));
   const int64_t gy = ceil_div(n, GV_TH);
   if (gy > 65535 || outer > 65535) return AMT_ERR_CAPACITY;
   dim3 grid((unsigned)ceil_div(inner, GV_TW), (unsigned)gy, (unsigned)outer), block(GV_TW, 8);
-  gauss_v_kernel<InT, DUAL><<<grid, block, smem, st>>>(in, scale, out_a, out_b, n, inner, hw_a, r_a, hw_b, r_b);
+  gauss_v_kernel<InT, DUAL><<<grid, block, smem, st>>>(in, scale, out_a, out_b, n, inner, hw_a, r_a, hw_b, r_b, mode);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
@@ -283,14 +296,14 @@ static int launch_v(const InT* in, double scale, double* out_a, double* out_b, i
 template <typename InT, bool DUAL>
 static int launch_h(const InT* in_a, const double* in_b, double scale, double* out, int64_t planes,
                     int64_t nrows, int64_t n, const double* hw_a, int r_a, const double* hw_b, int r_b,
-                    uint64_t* minmax, cudaStream_t st) {
+                    uint64_t* minmax, cudaStream_t st, int mode = 0) {
   const size_t smem = ((size_t)(GH_TX + 2 * r_a) * GH_PITCH + (DUAL ? (size_t)(GH_TX + 2 * r_b) * GH_PITCH : 0) +
                        (r_a + 1) + (DUAL ? r_b + 1 : 0)) * sizeof(double);
   AMT_TRY(set_smem(gauss_h_kernel<InT, DUAL>, smem));
   const int64_t gy = ceil_div(n, GH_TX);
   if (gy > 65535 || planes > 65535) return AMT_ERR_CAPACITY;
   dim3 grid((unsigned)ceil_div(nrows, GH_ROWS), (unsigned)gy, (unsigned)planes), block(256);
-  gauss_h_kernel<InT, DUAL><<<grid, block, smem, st>>>(in_a, in_b, scale, out, nrows, n, hw_a, r_a, hw_b, r_b, minmax);
+  gauss_h_kernel<InT, DUAL><<<grid, block, smem, st>>>(in_a, in_b, scale, out, nrows, n, hw_a, r_a, hw_b, r_b, minmax, mode);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
@@ -321,28 +334,34 @@ int dog_axis1_generic(const double* tmp_lo, const double* tmp_hi, double* out, i
 
 extern "C" {
 
-int amt_gaussian_axis(const void* in, int in_dtype, double in_scale, double* out, int64_t outer, int64_t n,
-                      int64_t inner, const double* half_w, int radius, amt_stream_t stream) {
+int amt_gaussian_axis_mode(const void* in, int in_dtype, double in_scale, double* out, int64_t outer, int64_t n,
+                           int64_t inner, const double* half_w, int radius, int mode, amt_stream_t stream) {
   using namespace amt;
   if (!in || !out || !half_w || outer <= 0 || n <= 0 || inner <= 0 || radius < 0) return AMT_ERR_INVALID;
+  if (mode != AMT_EXTEND_NEAREST && mode != AMT_EXTEND_REFLECT) return AMT_ERR_INVALID;
   cudaStream_t st = as_stream(stream);
   if (inner == 1) {
     // rows = outer, filter along the contiguous axis; fold rows into (planes, nrows) to fit grid limits
     if (in_dtype == AMT_U16)
       return launch_h<uint16_t, false>((const uint16_t*)in, nullptr, in_scale, out, 1, outer, n, half_w, radius,
-                                       nullptr, 0, nullptr, st);
+                                       nullptr, 0, nullptr, st, mode);
     if (in_dtype == AMT_F64)
       return launch_h<double, false>((const double*)in, nullptr, 1.0, out, 1, outer, n, half_w, radius, nullptr, 0,
-                                     nullptr, st);
+                                     nullptr, st, mode);
     return AMT_ERR_UNSUPPORTED;
   }
   if (in_dtype == AMT_U16)
     return launch_v<uint16_t, false>((const uint16_t*)in, in_scale, out, nullptr, outer, n, inner, half_w, radius,
-                                     nullptr, 0, st);
+                                     nullptr, 0, st, mode);
   if (in_dtype == AMT_F64)
     return launch_v<double, false>((const double*)in, 1.0, out, nullptr, outer, n, inner, half_w, radius, nullptr,
-                                   0, st);
+                                   0, st, mode);
   return AMT_ERR_UNSUPPORTED;
+}
+
+int amt_gaussian_axis(const void* in, int in_dtype, double in_scale, double* out, int64_t outer, int64_t n,
+                      int64_t inner, const double* half_w, int radius, amt_stream_t stream) {
+  return amt_gaussian_axis_mode(in, in_dtype, in_scale, out, outer, n, inner, half_w, radius, AMT_EXTEND_NEAREST, stream);
 }
 
 int amt_sub_f64(const double* a, const double* b, double* out, int64_t n, amt_stream_t stream) {

@@ -23,7 +23,7 @@ from . import _gpu, _lib
 _THRESHOLD_METHODS = ("otsu", "li", "yen", "isodata", "mean", "minimum", "triangle", "local", "niblack", "sauvola")
 
 
-_GPU_THRESHOLD_METHODS = ("otsu", "li", "yen", "isodata", "mean", "minimum", "triangle")
+_LOCAL_THRESHOLD_METHODS = ("local", "niblack", "sauvola")
 
 
 def _device_op(func):
@@ -351,6 +351,9 @@ def _li_from_histogram(counts: np.ndarray, centers: np.ndarray, tolerance=None, 
 _THRESHOLD_KWARGS = {
     "otsu": ("nbins",), "yen": ("nbins",), "isodata": ("nbins",), "triangle": ("nbins",), "mean": (),
     "minimum": ("nbins", "max_num_iter"), "li": ("tolerance", "initial_guess"),
+    "niblack": ("window_size", "k"), "sauvola": ("window_size", "k", "r"),
+    # threshold_local's own `method` can never arrive: apply_threshold's `method` parameter takes the name
+    "local": ("block_size", "offset", "mode", "param", "cval"),
 }
 
 
@@ -433,6 +436,78 @@ def _apply_histogram_threshold(intensities, method: str, batched: bool, kwargs: 
     return _gpu.to_host(mask) if was_numpy else mask
 
 
+def _window_per_axis(size, ndim: int, what: str) -> tuple[int, ...]:
+    sizes = (size,) * ndim if np.isscalar(size) else tuple(size)
+    if len(sizes) != ndim:
+        raise ValueError(f"{what} must be a scalar or have one entry per image axis ({ndim}), got {sizes}")
+    return tuple(int(v) for v in sizes)
+
+
+def _apply_local_threshold(intensities, method: str, batched: bool, kwargs: dict):
+    """local / niblack / sauvola: per-pixel thresholds from a window around every pixel
+    (ref: ``operations.py:193-195`` -> ``ski.filters.threshold_local / _niblack / _sauvola`` [3p]).
+
+    niblack, sauvola: box mean m and standard deviation s over ``window_size`` (odd), ``m - k*s`` and
+    ``m*(1 + k*(s/r - 1))``; uint8 / uint16 images only (scikit-image's float64 integral images are exact
+    integer arithmetic there, so the result is bit-identical; a float image would need its summation
+    order).  local: Gaussian-weighted mean (threshold_local's default method, the only one reachable
+    through the reference's signature, whose own ``method`` parameter takes the name; sigma =
+    (block_size-1)/6 unless ``param`` is given, ``mode`` 'reflect' or 'nearest') minus ``offset``."""
+    torch = _gpu.torch_mod()
+    t, np_dtype, was_numpy = _prepare(intensities)
+    planes = t if batched else t.reshape((1,) + tuple(t.shape))
+    if planes.ndim != 3:
+        raise NotImplementedError(f"method '{method}' is built for 2-D images (got {planes.ndim - 1} axes per image)")
+    n_img, h, w = planes.shape
+    integer_image = np_dtype.kind in "iu" and planes.dtype != torch.float64
+    flat = planes.reshape(n_img, -1)
+    mm = _gpu.minmax_keys(flat)
+    if method == "local":
+        block = _window_per_axis(kwargs.get("block_size", 3), 2, "block_size")
+        if any(b % 2 == 0 for b in block):
+            raise ValueError(f"block_size must be odd! Given block_size {block} contains even values.")
+        modes = {"reflect": _lib.AMT_EXTEND_REFLECT, "nearest": _lib.AMT_EXTEND_NEAREST}
+        mode = kwargs.get("mode", "reflect")
+        if mode not in modes:
+            raise NotImplementedError(f"threshold_local: mode '{mode}' is not built (available: reflect, nearest)")
+        param = kwargs.get("param")
+        sigma = tuple((b - 1) / 6.0 for b in block) if param is None else param
+        masks = []
+        for i in range(n_img):  # the image as float64 without rescaling (astype), every axis filtered
+            smooth = _gpu.gaussian_nd(planes[i], 1.0, sigma, modes[mode])
+            masks.append(_gpu.threshold_gt_image(planes[i], smooth, float(kwargs.get("offset", 0))))
+        mask = torch.stack(masks)
+    else:
+        if not integer_image:
+            raise NotImplementedError(
+                f"method '{method}' is implemented for uint8 / uint16 images only (scikit-image's integral images "
+                "are exact there; a float image would need its float64 summation order reproduced)")
+        window = _window_per_axis(kwargs.get("window_size", 15), 2, "window_size")
+        if any(v % 2 == 0 for v in window):
+            raise ValueError(
+                "Window size for `threshold_sauvola` or `threshold_niblack` must not be even on any dimension. "
+                f"Got {window}")
+        if max(window) > 127 or window[0] // 2 >= max(h, 2) or window[1] // 2 >= max(w, 2):
+            raise NotImplementedError(f"window_size {window} on a {h}x{w} image: windows up to 127 and smaller than "
+                                      "twice the image are built")
+        # every float64 sum scikit-image forms (integral image of the squared, padded image) stays an exact integer
+        for counts, values in _gpu.plane_histograms(flat, mm):
+            if 4 * int((counts * values.astype(np.int64) ** 2).sum()) >= 2**53:
+                raise NotImplementedError("sum of squared intensities beyond 2**53 / 4: scikit-image's float64 integral "
+                                          "image rounds there, which the exact integer path does not reproduce")
+        k = kwargs.get("k", 0.2)
+        r = kwargs.get("r")
+        if r is None:  # dtype_limits(image, clip_negative=False): half the dtype's range
+            r = 0.5 * (float(np.iinfo(np_dtype).max) - float(np.iinfo(np_dtype).min))
+        mask, _ = _gpu.window_threshold_u16(planes, window, 1 if method == "sauvola" else 0, k, r)
+    # a constant image is all False before the method is looked at (operations.py:201-202)
+    limits = _gpu.minmax_values(mm, planes.dtype == torch.float64)
+    for i in np.flatnonzero(limits[:, 0] == limits[:, 1]):
+        mask[int(i)].zero_()
+    mask = mask.reshape(t.shape).view(torch.bool)
+    return _gpu.to_host(mask) if was_numpy else mask
+
+
 @_device_op
 def apply_threshold(
     intensities,
@@ -444,29 +519,26 @@ def apply_threshold(
     """Binary image ``intensities > threshold`` (ref: ``operations.py:135-216``).
 
     Empty or constant input -> all False (checked before the method name, as in the
-    reference).  ``otsu``, ``li``, ``yen``, ``isodata``, ``mean``, ``minimum`` and ``triangle`` run on
-    the B200 path (skimage's histogram: exact per-value counts for integer images, 256 uniform bins
-    for float images; ``li`` and ``mean`` for integer images only); the three local-window methods
-    (``local``, ``niblack``, ``sauvola``) raise NotImplementedError.
+    reference).  All ten methods of the reference run on the B200 path: ``otsu``, ``li``, ``yen``,
+    ``isodata``, ``mean``, ``minimum``, ``triangle`` from skimage's histogram (exact per-value counts for
+    integer images, 256 uniform bins for float images; ``li`` and ``mean`` for integer images only), and
+    the local-window methods ``local`` (Gaussian), ``niblack``, ``sauvola`` (integer images).
     """
     if not _gpu.is_device_array(intensities) and np.asarray(intensities).size == 0:
         return np.zeros_like(np.asarray(intensities), dtype=bool)
     method_lower = method.lower()
-    if method_lower not in _GPU_THRESHOLD_METHODS:
+    if method_lower not in _THRESHOLD_METHODS:
         # the reference returns all-False for a constant image before it looks at the method
         host = _gpu.to_host(intensities) if _gpu.is_device_array(intensities) else np.asarray(intensities)
         if host.min() == host.max():
             return np.zeros_like(host, dtype=bool)
-        if method_lower not in _THRESHOLD_METHODS:
-            raise ValueError(
-                f"Unsupported thresholding method: '{method}'. "
-                f"Supported methods: {', '.join(_THRESHOLD_METHODS)}"
-            )
-        raise NotImplementedError(
-            f"Thresholding method '{method}' is outside the B200 hot path "
-            f"(implemented: {', '.join(_GPU_THRESHOLD_METHODS)})"
+        raise ValueError(
+            f"Unsupported thresholding method: '{method}'. "
+            f"Supported methods: {', '.join(_THRESHOLD_METHODS)}"
         )
     _check_threshold_kwargs(method_lower, kwargs)
+    if method_lower in _LOCAL_THRESHOLD_METHODS:
+        return _apply_local_threshold(intensities, method_lower, _batched, kwargs)
     intensities, offset = _shift_wide_integers(intensities)
     if method_lower != "otsu" or offset:
         return _apply_histogram_threshold(intensities, method_lower, _batched, kwargs, offset)

@@ -71,6 +71,14 @@ int amt_fp64_probe(int iters, double* scratch, uint64_t* dp_instructions, amt_st
 int amt_gaussian_axis(const void* in, int in_dtype, double in_scale, double* out,
                       int64_t outer, int64_t n, int64_t inner,
                       const double* half_w, int radius, amt_stream_t stream);
+/* The same pass with the boundary extension named: AMT_EXTEND_NEAREST (scipy mode='nearest', what
+ * amt_gaussian_axis does) or AMT_EXTEND_REFLECT (scipy mode='reflect', the default of
+ * skimage.filters.threshold_local: operations.py:193). */
+#define AMT_EXTEND_NEAREST 0
+#define AMT_EXTEND_REFLECT 1
+int amt_gaussian_axis_mode(const void* in, int in_dtype, double in_scale, double* out,
+                           int64_t outer, int64_t n, int64_t inner,
+                           const double* half_w, int radius, int mode, amt_stream_t stream);
 
 /* Fused 2-D difference of Gaussians over a batch of planes: out = G_lo(x) - G_hi(x).
  * tmp_lo / tmp_hi: caller scratch, n_img*h*w doubles each (axis-0 pass results).
@@ -201,6 +209,16 @@ int amt_otsu(const uint32_t* hist, int mode, const amt_map_params* params, const
 /* mask = data > threshold[img]  (uint8 0/1).  ref: operations.py:216 */
 int amt_threshold_gt(const void* data, int in_dtype, int64_t n_img, int64_t n, const double* thresholds,
                      uint8_t* mask, amt_stream_t stream);
+/* Local-window thresholds (ref: operations.py:193-195 -> skimage threshold_local / _niblack / _sauvola [3p]).
+ * amt_window_threshold_u16: per pixel, mean m and standard deviation s of the window_h x window_w box
+ * (odd sizes <= 127, np.pad 'reflect' borders, exact integer window sums); kind 0 = niblack
+ * t = m - k*s, kind 1 = sauvola t = m*(1 + k*(s/r - 1)); mask = data > t; thresholds (optional,
+ * may be NULL) receives t.  Exact as long as 4*sum(data^2) < 2^53 per image (the caller checks).
+ * amt_threshold_gt_image: mask[i] = data[i] > thresholds[i] - offset (threshold_local's comparison). */
+int amt_window_threshold_u16(const uint16_t* data, int64_t n_img, int64_t h, int64_t w, int window_h, int window_w,
+                             int kind, double k, double r, uint8_t* mask, double* thresholds, amt_stream_t stream);
+int amt_threshold_gt_image(const void* data, int in_dtype, int64_t n, const double* thresholds, double offset,
+                           uint8_t* mask, amt_stream_t stream);
 
 /* ------------------------------------------------------------------ labelling
  * ref: masks.py:38-65 (_process_mask): clear_border [3p] then measure.label [3p] (bool) or

@@ -55,14 +55,16 @@ def subtract_background_dog(intensities, low_sigma=0.6, high_sigma=16.0, percent
 
 
 def apply_threshold(intensities, method="otsu", **kwargs):
-    """ref: operations.py:135-216 (the seven histogram / global methods; local, niblack, sauvola are not restated)."""
+    """ref: operations.py:135-216 (all ten methods)."""
     if intensities.size == 0:
         return np.zeros_like(intensities, dtype=bool)
     if intensities.min() == intensities.max():
         return np.zeros_like(intensities, dtype=bool)
     funcs = {"otsu": threshold.threshold_otsu, "isodata": threshold.threshold_isodata,
              "yen": threshold.threshold_yen, "mean": threshold.threshold_mean, "li": threshold.threshold_li,
-             "minimum": threshold.threshold_minimum, "triangle": threshold.threshold_triangle}
+             "minimum": threshold.threshold_minimum, "triangle": threshold.threshold_triangle,
+             "local": threshold.threshold_local, "niblack": threshold.threshold_niblack,
+             "sauvola": threshold.threshold_sauvola}
     if method.lower() not in funcs:
         raise ValueError(f"Unsupported thresholding method: '{method}'.")
     return intensities > funcs[method.lower()](intensities, **kwargs)

@@ -255,3 +255,94 @@ def threshold_li(image: np.ndarray, *, tolerance=None, initial_guess=None):
                 break
             t_next = (mean_back - mean_fore) / (np.log(mean_back) - np.log(mean_fore))
     return t_next + image_min
+
+
+# ---- local-window methods (operations.py:193-195).  Restated from skimage 0.25.2 ``filters/thresholding.py``
+# (``_mean_std``, ``threshold_niblack``, ``threshold_sauvola``, ``threshold_local``) on the real numpy / scipy
+# routines it calls (``np.pad``, ``cumsum``, ``scipy.ndimage.gaussian_filter``); parity unpinned beyond that.
+def _integral_image(image: np.ndarray) -> np.ndarray:
+    """``skimage.transform.integral_image(image, dtype=float64)``: cumulative sums along every axis in turn."""
+    S = image
+    for axis in range(image.ndim):
+        S = S.cumsum(axis=axis, dtype=np.float64)
+    return S
+
+
+def _correlate_sparse(image: np.ndarray, kernel_shape, kernel_indices, kernel_values) -> np.ndarray:
+    """``skimage.filters._sparse._correlate_sparse`` (mode 'valid'): the first corner is copied, the others
+    are added in the order given."""
+    out_shape = tuple(s - k + 1 for s, k in zip(image.shape, kernel_shape))
+    first_idx, first_val = kernel_indices[0], kernel_values[0]
+    assert tuple(first_idx) == (0,) * image.ndim
+    out = image[tuple(slice(0, s) for s in out_shape)].copy()
+    if first_val != 1:
+        out *= first_val
+    for idx, val in zip(kernel_indices[1:], kernel_values[1:]):
+        out += image[tuple(slice(i, i + s) for i, s in zip(idx, out_shape))] * val
+    return out
+
+
+def _mean_std(image: np.ndarray, w):
+    import itertools
+    import math
+
+    image = np.asarray(image)
+    if np.isscalar(w):
+        w = (w,) * image.ndim
+    for axis_size in w:
+        if axis_size % 2 == 0:
+            raise ValueError(
+                f"Window size for `threshold_sauvola` or `threshold_niblack` must not be even on any dimension. Got {w}")
+    float_dtype = np.float64  # _supported_float_type of integer / float64 images
+    pad_width = tuple((k // 2 + 1, k // 2) for k in w)
+    padded = np.pad(image.astype(float_dtype, copy=False), pad_width, mode="reflect")
+    integral = _integral_image(padded)
+    padded *= padded
+    integral_sq = _integral_image(padded)
+    kernel_indices = list(itertools.product(*tuple([(0, _w) for _w in w])))
+    kernel_values = [(-1) ** (image.ndim % 2 != np.sum(indices) % 2) for indices in kernel_indices]
+    total_window_size = math.prod(w)
+    kernel_shape = tuple(_w + 1 for _w in w)
+    m = _correlate_sparse(integral, kernel_shape, kernel_indices, kernel_values)
+    m = m.astype(float_dtype, copy=False)
+    m /= total_window_size
+    g2 = _correlate_sparse(integral_sq, kernel_shape, kernel_indices, kernel_values)
+    g2 = g2.astype(float_dtype, copy=False)
+    g2 /= total_window_size
+    s = np.sqrt(np.clip(g2 - m * m, 0, None))
+    return m, s
+
+
+def threshold_niblack(image: np.ndarray, window_size=15, k=0.2):
+    m, s = _mean_std(image, window_size)
+    return m - k * s
+
+
+def threshold_sauvola(image: np.ndarray, window_size=15, k=0.2, r=None):
+    image = np.asarray(image)
+    if r is None:
+        # dtype_limits(image, clip_negative=False)
+        if image.dtype.kind in "iu":
+            imin, imax = np.iinfo(image.dtype).min, np.iinfo(image.dtype).max
+        else:
+            imin, imax = -1.0, 1.0
+        r = 0.5 * (imax - imin)
+    m, s = _mean_std(image, window_size)
+    return m * (1 + k * ((s / r) - 1))
+
+
+def threshold_local(image: np.ndarray, block_size=3, method="gaussian", offset=0, mode="reflect", param=None, cval=0):
+    from scipy import ndimage as ndi
+
+    image = np.asarray(image)
+    if np.isscalar(block_size):
+        block_size = (block_size,) * image.ndim
+    if any(b % 2 == 0 for b in block_size):
+        raise ValueError(f"block_size must be odd! Given block_size {block_size} contains even values.")
+    if method != "gaussian":
+        raise NotImplementedError("oracle restates method='gaussian' only")
+    image = image.astype(np.float64, copy=False)
+    thresh_image = np.zeros(image.shape, dtype=np.float64)
+    sigma = tuple((b - 1) / 6.0 for b in block_size) if param is None else param
+    ndi.gaussian_filter(image, sigma, output=thresh_image, mode=mode, cval=cval, truncate=4.0)
+    return thresh_image - offset

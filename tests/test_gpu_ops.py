@@ -349,6 +349,67 @@ def test_thresholds_of_wide_integer_images(method):
         assert 0 < want.sum() < want.size and np.array_equal(got, want), (method, dtype)
 
 
+@pytest.mark.parametrize("method", ["niblack", "sauvola"])
+def test_window_thresholds_match_oracle(method):
+    """box mean / standard deviation thresholds.  Integer window sums are exact, every float
+    step is rounded once as in NumPy: threshold images and masks must equal the oracle's bit for bit."""
+    import torch
+
+    rng = np.random.default_rng(91)
+    shape = (3, 101, 77)
+    fg = rng.random(shape) < 0.3
+    u16 = np.where(fg, rng.normal(9000, 700, shape), rng.gamma(2.0, 700.0, shape)).clip(0, 65535).astype(np.uint16)
+    u16[1, :40, :30] = 65535  # saturated patch: variance clips at zero
+    for kw in ({}, {"window_size": 3}, {"window_size": (5, 31), "k": 0.35}, {"window_size": 127, "k": -0.1}):
+        for i in range(3):
+            want = oracle.apply_threshold(u16[i], method, **kw)
+            got = operations.apply_threshold(u16[i], method, **kw)
+            assert got.dtype == np.bool_ and np.array_equal(got, want), (method, kw, i, int((got != want).sum()))
+        got = operations.apply_threshold(u16, method, _batched=True, **kw)
+        assert all(np.array_equal(got[i], oracle.apply_threshold(u16[i], method, **kw)) for i in range(3))
+    # the threshold image itself (float64) is bit-identical
+    func = oracle.threshold.threshold_niblack if method == "niblack" else oracle.threshold.threshold_sauvola
+    d = torch.from_numpy(u16.view(np.int16)).cuda()
+    _, thr = _gpu.window_threshold_u16(d, (15, 15), 1 if method == "sauvola" else 0, 0.2, 32767.5, want_thresholds=True)
+    for i in range(3):
+        _bits_equal(thr[i].cpu().numpy(), func(u16[i]), f"{method} threshold image {i}")
+    if method == "sauvola":
+        assert np.array_equal(operations.apply_threshold(u16[0], method, r=128.0), oracle.apply_threshold(u16[0], method, r=128.0))
+    u8 = (u16[0] >> 8).astype(np.uint8)  # sauvola's default r follows the dtype: 127.5 for uint8
+    assert np.array_equal(operations.apply_threshold(u8, method), oracle.apply_threshold(u8, method))
+    assert not operations.apply_threshold(np.full((40, 40), 900, np.uint16), method).any()
+    with pytest.raises(ValueError, match="must not be even"):
+        operations.apply_threshold(u16[0], method, window_size=14)
+    with pytest.raises(NotImplementedError, match="uint8 / uint16 images only"):
+        operations.apply_threshold(u16[0] / 65535.0, method)
+    with pytest.raises(NotImplementedError, match="2\\*\\*53"):
+        operations.apply_threshold(np.full((2048, 2048), 65535, np.uint16) - (np.arange(2048) % 2).astype(np.uint16), method)
+
+
+def test_threshold_local_matches_oracle():
+    """threshold_local (Gaussian-weighted mean, mode='reflect'): scipy's correlate1d order on the raw values."""
+    rng = np.random.default_rng(92)
+    shape = (2, 90, 123)
+    fg = rng.random(shape) < 0.3
+    base = np.where(fg, rng.normal(9000, 700, shape), rng.gamma(2.0, 700.0, shape)).clip(0, 65535)
+    u16 = base.astype(np.uint16)
+    f64 = base / 65535.0
+    for kw in ({}, {"block_size": 35}, {"block_size": (5, 51), "offset": 120.0}, {"block_size": 21, "mode": "nearest"},
+               {"block_size": 9, "param": 3.0, "offset": -40}):
+        for i in range(2):
+            assert np.array_equal(operations.apply_threshold(u16[i], "local", **kw), oracle.apply_threshold(u16[i], "local", **kw)), (kw, i)
+        got = operations.apply_threshold(u16, "local", _batched=True, **kw)
+        assert all(np.array_equal(got[i], oracle.apply_threshold(u16[i], "local", **kw)) for i in range(2))
+    fkw = {"block_size": 35, "offset": 0.002}
+    assert np.array_equal(operations.apply_threshold(f64[0], "local", **fkw), oracle.apply_threshold(f64[0], "local", **fkw))
+    tiny = u16[0, :7, :5]  # the window reflects more than once around a tiny image
+    assert np.array_equal(operations.apply_threshold(tiny, "local", block_size=35), oracle.apply_threshold(tiny, "local", block_size=35))
+    with pytest.raises(ValueError, match="block_size must be odd"):
+        operations.apply_threshold(u16[0], "local", block_size=10)
+    with pytest.raises(NotImplementedError, match="mode 'wrap'"):
+        operations.apply_threshold(u16[0], "local", block_size=11, mode="wrap")
+
+
 def test_bucketed_selection_matches_sorted_order():
     """amt_select_f64_bucketed (2-byte monotone buckets + sparse value gather, the executor's percentile
     path) must return exactly the order statistics np.sort gives, also for distributions that put most

@@ -122,9 +122,8 @@ def test_operation_argument_validation_matches_reference_messages():
     assert operations.apply_threshold(empty).dtype == np.bool_
     with pytest.raises(ValueError, match="Unsupported thresholding method: 'nope'"):
         operations.apply_threshold(x, method="nope")
-    with pytest.raises(NotImplementedError, match="outside the B200 hot path"):
-        operations.apply_threshold(x, method="sauvola")
-    assert not operations.apply_threshold(np.full((3, 3), 5, np.uint16), method="sauvola").any()
+    # a constant image is all False before the method name is looked at (operations.py:201-209)
+    assert not operations.apply_threshold(np.full((3, 3), 5, np.uint16), method="nope").any()
 
 
 def test_crop_to_center_is_a_view():
