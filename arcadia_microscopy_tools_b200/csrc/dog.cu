@@ -53,7 +53,11 @@ __device__ __forceinline__ void cp_async_wait_all() {
 
 // acc[o] = x[o]*w[0] + sum_{j = r..1} (x[o-j] + x[o+j]) * w[j], scipy's order, for r <= RLO_MAX;
 // xs[i] holds sample i - RLO_MAX relative to output 0 (static indices only: stays in registers).
-template <int R>
+// FMA = true (amt_tune "dog_fma", off by default): the multiply and the accumulation contract into one
+// fused multiply-add, 2 DP instructions per tap pair instead of 3.  Results then differ from scipy's in
+// the last bits (relative 1e-15 on the filtered planes, far inside the reference's 1e-5 tolerance) and
+// bit-exact labels are no longer guaranteed by construction, only overwhelmingly likely.
+template <int R, bool FMA>
 __device__ __forceinline__ void conv_small(const double (&xs)[R + 2 * RLO_MAX], const double* __restrict__ hw,
                                            const int r, double (&acc)[R]) {
   const double w0 = hw[0];
@@ -64,8 +68,10 @@ __device__ __forceinline__ void conv_small(const double (&xs)[R + 2 * RLO_MAX], 
     if (j <= r) {
       const double wj = hw[j];
 #pragma unroll
-      for (int o = 0; o < R; ++o)
-        acc[o] = dadd(acc[o], dmul(dadd(xs[o + RLO_MAX - j], xs[o + RLO_MAX + j]), wj));
+      for (int o = 0; o < R; ++o) {
+        const double pair = dadd(xs[o + RLO_MAX - j], xs[o + RLO_MAX + j]);
+        acc[o] = FMA ? __fma_rn(pair, wj, acc[o]) : dadd(acc[o], dmul(pair, wj));
+      }
     }
   }
 }
@@ -109,7 +115,7 @@ __device__ __forceinline__ void store_transposed(double* __restrict__ sw, const 
 // Same arithmetic and register-window scheme as conv_exact (conv.cuh); the left / right sample
 // pointers advance by R rows per unrolled iteration and wrap there, so inside an iteration every
 // access is pointer + constant.  Rows [N, N+R) of the ring mirror rows [0, R).
-template <int R>
+template <int R, bool FMA>
 __device__ __forceinline__ void conv_ring(const double* __restrict__ ring0, const int N, const int c,
                                           const double* __restrict__ hw, const int r, double (&acc)[R]) {
   double L[R], Rt[R];
@@ -141,10 +147,15 @@ __device__ __forceinline__ void conv_ring(const double* __restrict__ ring0, cons
       L[u] = pL[(R + u) * PV_TW];
       Rt[R - 1 - u] = pR[(R - 1 - u) * PV_TW];
       const double wn = hw[j - u - 1];
+      if constexpr (FMA) {
 #pragma unroll
-      for (int o = 0; o < R; ++o) t[o] = dmul(t[o], wj);
+        for (int o = 0; o < R; ++o) acc[o] = __fma_rn(t[o], wj, acc[o]);
+      } else {
 #pragma unroll
-      for (int o = 0; o < R; ++o) acc[o] = dadd(acc[o], t[o]);
+        for (int o = 0; o < R; ++o) t[o] = dmul(t[o], wj);
+#pragma unroll
+        for (int o = 0; o < R; ++o) acc[o] = dadd(acc[o], t[o]);
+      }
       wj = wn;
     }
     pL += R * PV_TW;
@@ -162,7 +173,7 @@ __device__ __forceinline__ void conv_ring(const double* __restrict__ ring0, cons
 // Ring: N = (nb+1)*S rows; block b (S rows) holds samples y = b*S - r_hi + [0, S), clamped
 // (mode='nearest'), in slot b % (nb+1).  Rows [N, N+R) mirror [0, R) and rows [-4, 0) mirror
 // [N-4, N), so that aligned 2R-row runs and the narrow filter's R+8-row runs never wrap.
-template <int R, int WARPS, int MIN_CTAS, typename InT, bool SECOND>
+template <int R, int WARPS, int MIN_CTAS, typename InT, bool SECOND, bool FMA>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, const double scale,
                  double* __restrict__ out_a, double* __restrict__ out_b, const int n, const int inner,
@@ -289,17 +300,17 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
     int c = pk * S + r_hi + ty * R;  // ring row of this thread's output 0 (sample y sits at ring row y + r_hi)
     c = c >= N ? c - N : c;
     double acc[R];
-    conv_ring<R>(ring_lane, N, c, whi, r_hi, acc);
+    conv_ring<R, FMA>(ring_lane, N, c, whi, r_hi, acc);
     if constexpr (!SECOND) {
       store_transposed<R>(stage, acc, out_a + out_col + yb, n, tx, rows_left, cols_valid);
       const double* col = ring_lane + c * PV_TW;
 #pragma unroll
       for (int i = 0; i < R + 2 * RLO_MAX; ++i) xs[i] = col[(i - RLO_MAX) * PV_TW];  // front / back mirrors: never wraps
-      conv_small<R>(xs, wlo, r_lo, acc);
+      conv_small<R, FMA>(xs, wlo, r_lo, acc);
       store_transposed<R>(stage, acc, out_b + out_col + yb, n, tx, rows_left, cols_valid);
     } else {
       double acc_lo[R];
-      conv_small<R>(xs, wlo, r_lo, acc_lo);
+      conv_small<R, FMA>(xs, wlo, r_lo, acc_lo);
 #pragma unroll
       for (int o = 0; o < R; ++o) acc[o] = dsub(acc_lo[o], acc[o]);
       store_transposed<R>(stage, acc, out_a + out_col + yb, n, tx, rows_left, cols_valid);
@@ -371,6 +382,7 @@ static int g_dog_variant = 1;
 static int g_dog_ctas = 0;
 static int g_dog_persistent = 0;
 static int g_dog_generic = 0;
+static int g_dog_fma = 0;
 extern int g_stream_ctas;     // gauss.cu
 extern int g_stream_pad_kb;   // gauss.cu
 extern int g_exec_swap_prio;  // executor.cu
@@ -417,11 +429,11 @@ static DogPlan dog_plan(int in_dtype, int64_t n_img, int64_t h, int64_t w, int r
   return p;
 }
 
-template <int R, int WARPS, int MIN_CTAS, typename InT, bool SECOND>
+template <int R, int WARPS, int MIN_CTAS, typename InT, bool SECOND, bool FMA>
 static int launch_strip(const DogPlan& p, const InT* in, const double* in_lo, double scale, double* out_a, double* out_b,
                         int64_t planes, int64_t n, int64_t inner, const double* hw_lo, int r_lo, const double* hw_hi,
                         int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st) {
-  auto kernel = dog_strip_kernel<R, WARPS, MIN_CTAS, InT, SECOND>;
+  auto kernel = dog_strip_kernel<R, WARPS, MIN_CTAS, InT, SECOND, FMA>;
   AMT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   const int64_t items = planes * ((inner + PV_TW - 1) / PV_TW);
   // one CTA per strip by default (the hardware scheduler balances the tail better than a static
@@ -434,18 +446,29 @@ static int launch_strip(const DogPlan& p, const InT* in, const double* in_lo, do
   return AMT_OK;
 }
 
+template <typename InT, bool SECOND, bool FMA>
+static int launch_variant_fma(const DogPlan& p, const InT* in, const double* in_lo, double scale, double* out_a,
+                              double* out_b, int64_t planes, int64_t n, int64_t inner, const double* hw_lo, int r_lo,
+                              const double* hw_hi, int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st) {
+  if (p.R == 16)
+    return launch_strip<16, 4, 2, InT, SECOND, FMA>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo,
+                                                     hw_hi, r_hi, minmax, buckets, st);
+  if (p.warps == 8)
+    return launch_strip<8, 8, 2, InT, SECOND, FMA>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo,
+                                                    hw_hi, r_hi, minmax, buckets, st);
+  return launch_strip<8, 4, 3, InT, SECOND, FMA>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
+                                                  r_hi, minmax, buckets, st);
+}
+
 template <typename InT, bool SECOND>
 static int launch_variant(const DogPlan& p, const InT* in, const double* in_lo, double scale, double* out_a,
                           double* out_b, int64_t planes, int64_t n, int64_t inner, const double* hw_lo, int r_lo,
                           const double* hw_hi, int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st) {
-  if (p.R == 16)
-    return launch_strip<16, 4, 2, InT, SECOND>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
+  if (g_dog_fma)
+    return launch_variant_fma<InT, SECOND, true>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
+                                                 r_hi, minmax, buckets, st);
+  return launch_variant_fma<InT, SECOND, false>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
                                                 r_hi, minmax, buckets, st);
-  if (p.warps == 8)
-    return launch_strip<8, 8, 2, InT, SECOND>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
-                                               r_hi, minmax, buckets, st);
-  return launch_strip<8, 4, 3, InT, SECOND>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi, r_hi,
-                                             minmax, buckets, st);
 }
 
 // pass 1: image (h x w) -> tmp_hi, tmp_lo.  Fast path: both TRANSPOSED (w x h); generic: image layout.
@@ -520,6 +543,8 @@ int amt_tune(const char* key, int value) {
     g_exec_swap_prio = value != 0;
   } else if (is("dog_generic")) {
     g_dog_generic = value != 0;
+  } else if (is("dog_fma")) {
+    g_dog_fma = value != 0;
   } else {
     return AMT_ERR_INVALID;
   }

@@ -55,29 +55,75 @@ def measured_peaks() -> dict:
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    """Samples SM clocks and throttle reasons while the timed region runs: NVML in-process every 10 ms
+    (nvidia-ml-py), or `nvidia-smi` every 200 ms when NVML cannot be loaded."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int) -> None:
         self.index = index
-        self.rows: list[list[str]] = []
+        self.sm: list[float] = []
+        self.sm_max: float | None = None
+        self.reasons: set[str] = set()
+        self.source = "nvidia-smi"
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML indexes physical devices: honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in visible.split(",") if v.strip().isdigit()]
+            physical = int(ids[index]) if index < len(ids) else index
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(physical)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self) -> None:
+        n = self._nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)))
+        try:
+            bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._handle))
+        except Exception:
+            bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+        for name, bit in self.REASON_BITS.items():
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self) -> None:
+        out = subprocess.run(
+            ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
+            capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        r = [c.strip() for c in out.splitlines()[0].split(",")]
+        if r[0].replace(".", "").isdigit():
+            self.sm.append(float(r[0]))
+        if len(r) > 1 and r[1].replace(".", "").isdigit():
+            self.sm_max = max(self.sm_max or 0.0, float(r[1]))
+        for k, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                self.reasons.add(name)
 
     def _run(self) -> None:
         while not self._stop.is_set():
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
-                    capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.01 if self._nvml is not None else 0.2)
 
     def __enter__(self):
         self._thread.start()
@@ -88,12 +134,9 @@ class ClockSampler:
         self._thread.join(timeout=6)
 
     def summary(self) -> dict:
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        order = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": [n for n in order if n in self.reasons], "samples": len(self.sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------ inputs
@@ -378,6 +421,31 @@ def run_b200(args) -> None:
                "fov_per_s": world * args.steps * n_e2e / e2e_s, "fovs_per_step": n_e2e, "timing": "wall clock around the synchronous C-ABI call",
                "rank0_cpu_affinity": f"{len(cpus)} CPUs local to the GPU (NVML)" if cpus else "unchanged"}
 
+    # ---- the same device-resident pass with the DoG's multiply-adds contracted (amt_tune "dog_fma"): what scipy's
+    # exact operation order costs.  Not the reported value: the default path stays bit-identical to the reference.
+    contracted = None
+    if not args.no_contracted:
+        keep = {k: out[k].clone() for k in ("tables_thr", "counts_thr", "thresholds")}
+        _lib.check(lib.amt_tune(b"dog_fma", 1), "amt_tune")
+        try:
+            ex.run_device(fovs, given, out, sync=True)
+            barrier()
+            c_ms = [ex.run_device(fovs, given, out, sync=True) for _ in range(args.steps)]
+            barrier()
+        finally:
+            _lib.check(lib.amt_tune(b"dog_fma", 0), "amt_tune")
+        tc = torch.tensor([sum(c_ms) / 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        same = all(torch.equal(out[k].view(torch.int64) if out[k].dtype == torch.float64 else out[k],
+                               keep[k].view(torch.int64) if keep[k].dtype == torch.float64 else keep[k]) for k in keep)
+        contracted = {"value": world * args.steps * n_fov * C * H * W / float(tc[0]) / 1e6, "unit": "Mpix/s",
+                      "ms_per_step": 1e3 * float(tc[0]) / args.steps,
+                      "thresholds_counts_and_tables_bit_identical_to_exact_mode": bool(same),
+                      "note": "opt-in amt_tune('dog_fma', 1): DADD+DFMA per tap pair instead of DADD+DMUL+DADD; filtered planes "
+                              "differ from scipy's in the last bits, so this is NOT the reported value"}
+        del keep
+
     # ---- per-kernel roofline (rank 0) and CPU baseline (rank 0, N=1)
     line = None
     if rank == 0:
@@ -411,6 +479,7 @@ def run_b200(args) -> None:
             "cells_per_fov": {"threshold_mask": float(counts[0].mean()), "given_mask": float(counts[1].mean())},
             "clocks": clocks.summary(),
             "e2e": e2e,
+            "contracted_mode": contracted,
             "roofline": {"kernel": f"dog_strip_kernel ({dom} pass of the DoG: sigma 0.6 and 16 filters of {k['planes']} planes)",
                          "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
@@ -477,6 +546,7 @@ def main() -> None:
     ap.add_argument("--e2e-fovs", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-contracted", action="store_true", help="skip the extra pass with amt_tune('dog_fma', 1)")
     args = ap.parse_args()
     capture_stdout()
     if args.impl == "reference":

@@ -410,6 +410,34 @@ def test_threshold_local_matches_oracle():
         operations.apply_threshold(u16[0], "local", block_size=11, mode="wrap")
 
 
+def test_contracted_dog_mode_stays_within_tolerance_and_is_opt_in():
+    """amt_tune('dog_fma', 1): fused multiply-adds in the DoG (2 DP instructions per tap pair instead of 3).
+    Opt-in; the planes then differ from scipy's only in the last bits (tolerance 1e-12 relative to the plane's
+    scale here, 1e-5 in the north star), thresholds and masks of the test images are unchanged, and switching
+    it off restores bit-exactness."""
+    from arcadia_microscopy_tools_b200 import _lib
+
+    lib = _lib.load()
+    fov = make_fov(11, 2, 512, 768, n_cells=150)[0]
+    want = oracle.subtract_background_dog(fov[1], 0.6, 16.0, percentile=0)
+    exact = operations.subtract_background_dog(fov[1], 0.6, 16.0, percentile=0)
+    _bits_equal(exact, want, "exact mode")
+    _lib.check(lib.amt_tune(b"dog_fma", 1))
+    try:
+        fast = operations.subtract_background_dog(fov[1], 0.6, 16.0, percentile=0)
+        pipe = Pipeline([ImageOperation(operations.subtract_background_dog, 0.6, 16.0, percentile=0),
+                         ImageOperation(operations.rescale_by_percentile, percentile_range=(1, 99)),
+                         ImageOperation(operations.apply_threshold)])
+        fast_mask = pipe(fov[1])
+    finally:
+        _lib.check(lib.amt_tune(b"dog_fma", 0))
+    assert np.max(np.abs(fast - want)) <= 1e-12 * np.max(np.abs(want))
+    assert not np.array_equal(fast, want)  # it really is a different rounding
+    exact_mask = oracle.apply_threshold(oracle.rescale_by_percentile(want, (1, 99)))
+    assert np.array_equal(fast_mask, exact_mask)
+    _bits_equal(operations.subtract_background_dog(fov[1], 0.6, 16.0, percentile=0), want, "exact mode restored")
+
+
 def test_bucketed_selection_matches_sorted_order():
     """amt_select_f64_bucketed (2-byte monotone buckets + sparse value gather, the executor's percentile
     path) must return exactly the order statistics np.sort gives, also for distributions that put most
