@@ -104,7 +104,9 @@ int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int
  * the shipped configuration).  Keys: "dog_variant" 0 = 8 warps x 8 outputs per thread,
  * 1 = 4 warps x 16, 2 = 8 warps x 16; "dog_solo" 1 = one DoG CTA per SM (leaves half of the SM
  * to the HBM-bound kernels of the other stream), 0 = as many as fit; "dog_generic" 1 = force
- * the generic tile kernels. */
+ * the generic tile kernels; "dog_fma" 1 = contract the DoG's multiply-adds (2 instead of 3 DP
+ * instructions per tap pair; the filtered planes then differ from scipy's in the last bits: opt-in,
+ * off by default). */
 int amt_tune(const char* key, int value);
 
 /* Test hook: *mismatches = number of i for which the plane-constant division sequence of the map
