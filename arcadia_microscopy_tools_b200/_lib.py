@@ -84,6 +84,7 @@ class FovConfig(C.Structure):
         ("quantify_given_mask", C.c_int32),
         ("with_shape", C.c_int32),
         ("given_label_dtype", C.c_int32),
+        ("exact_all_channels", C.c_int32),
         ("low_sigma", C.c_double),
         ("high_sigma", C.c_double),
         ("bg_percentile", C.c_double),

@@ -173,12 +173,16 @@ __device__ __forceinline__ void conv_ring(const double* __restrict__ ring0, cons
 // Ring: N = (nb+1)*S rows; block b (S rows) holds samples y = b*S - r_hi + [0, S), clamped
 // (mode='nearest'), in slot b % (nb+1).  Rows [N, N+R) mirror [0, R) and rows [-4, 0) mirror
 // [N-4, N), so that aligned 2R-row runs and the narrow filter's R+8-row runs never wrap.
-template <int R, int WARPS, int MIN_CTAS, typename InT, bool SECOND, bool FMA>
+// FMA: 0 = scipy's exact operation order everywhere, 1 = contracted everywhere, 2 = per plane: plane p keeps the
+// exact order iff p % exact_every == exact_offset (the executor's segmentation channel, whose plane decides
+// labels), the others are contracted (their only product is a float plane with a 1e-5 tolerance).
+template <int R, int WARPS, int MIN_CTAS, typename InT, bool SECOND, int FMA>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
 dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, const double scale,
                  double* __restrict__ out_a, double* __restrict__ out_b, const int n, const int inner,
                  const double* __restrict__ hw_lo, const int r_lo, const double* __restrict__ hw_hi, const int r_hi,
-                 const int nb, uint64_t* __restrict__ minmax, uint16_t* __restrict__ buckets, const int n_items) {
+                 const int nb, uint64_t* __restrict__ minmax, uint16_t* __restrict__ buckets, const int n_items,
+                 const int exact_every, const int exact_offset) {
   constexpr int S = WARPS * R;  // rows per step
   constexpr int NT = WARPS * 32;
   constexpr int FRONT = RLO_MAX, BACK = R;
@@ -199,6 +203,7 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
   const int strips = (inner + PV_TW - 1) / PV_TW;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
   const int plane_idx = item / strips;
+  const bool contract = FMA == 1 || (FMA == 2 && plane_idx % exact_every != exact_offset);  // CTA-uniform
   const int x0 = (item - plane_idx * strips) * PV_TW;
   const int64_t plane = (int64_t)plane_idx * n * inner;
   const InT* src = in + plane + x0;
@@ -300,17 +305,26 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
     int c = pk * S + r_hi + ty * R;  // ring row of this thread's output 0 (sample y sits at ring row y + r_hi)
     c = c >= N ? c - N : c;
     double acc[R];
-    conv_ring<R, FMA>(ring_lane, N, c, whi, r_hi, acc);
+    if (FMA != 0 && contract)
+      conv_ring<R, true>(ring_lane, N, c, whi, r_hi, acc);
+    else
+      conv_ring<R, false>(ring_lane, N, c, whi, r_hi, acc);
     if constexpr (!SECOND) {
       store_transposed<R>(stage, acc, out_a + out_col + yb, n, tx, rows_left, cols_valid);
       const double* col = ring_lane + c * PV_TW;
 #pragma unroll
       for (int i = 0; i < R + 2 * RLO_MAX; ++i) xs[i] = col[(i - RLO_MAX) * PV_TW];  // front / back mirrors: never wraps
-      conv_small<R, FMA>(xs, wlo, r_lo, acc);
+      if (FMA != 0 && contract)
+        conv_small<R, true>(xs, wlo, r_lo, acc);
+      else
+        conv_small<R, false>(xs, wlo, r_lo, acc);
       store_transposed<R>(stage, acc, out_b + out_col + yb, n, tx, rows_left, cols_valid);
     } else {
       double acc_lo[R];
-      conv_small<R, FMA>(xs, wlo, r_lo, acc_lo);
+      if (FMA != 0 && contract)
+        conv_small<R, true>(xs, wlo, r_lo, acc_lo);
+      else
+        conv_small<R, false>(xs, wlo, r_lo, acc_lo);
 #pragma unroll
       for (int o = 0; o < R; ++o) acc[o] = dsub(acc_lo[o], acc[o]);
       store_transposed<R>(stage, acc, out_a + out_col + yb, n, tx, rows_left, cols_valid);
@@ -383,6 +397,8 @@ static int g_dog_ctas = 0;
 static int g_dog_persistent = 0;
 static int g_dog_generic = 0;
 static int g_dog_fma = 0;
+static int g_dog_exact_every = 0;   // amt_tune: the stand-alone amt_dog2d* entry points run the per-plane kernel
+static int g_dog_exact_offset = 0;  // (what the executor launches) when every > 0; for bench / profiling only
 extern int g_stream_ctas;     // gauss.cu
 extern int g_stream_pad_kb;   // gauss.cu
 extern int g_exec_swap_prio;  // executor.cu
@@ -429,10 +445,14 @@ static DogPlan dog_plan(int in_dtype, int64_t n_img, int64_t h, int64_t w, int r
   return p;
 }
 
-template <int R, int WARPS, int MIN_CTAS, typename InT, bool SECOND, bool FMA>
+struct DogMix {
+  int every, offset;  // every > 0: plane p is exact iff p % every == offset, the other planes are contracted
+};
+
+template <int R, int WARPS, int MIN_CTAS, typename InT, bool SECOND, int FMA>
 static int launch_strip(const DogPlan& p, const InT* in, const double* in_lo, double scale, double* out_a, double* out_b,
                         int64_t planes, int64_t n, int64_t inner, const double* hw_lo, int r_lo, const double* hw_hi,
-                        int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st) {
+                        int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st, DogMix mix) {
   auto kernel = dog_strip_kernel<R, WARPS, MIN_CTAS, InT, SECOND, FMA>;
   AMT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   const int64_t items = planes * ((inner + PV_TW - 1) / PV_TW);
@@ -441,64 +461,73 @@ static int launch_strip(const DogPlan& p, const InT* in, const double* in_lo, do
   const int64_t resident = g_dog_persistent ? (int64_t)kNumSMs * p.ctas : items;
   dim3 grid((unsigned)(items < resident ? items : resident)), block(PV_TW, WARPS);
   kernel<<<grid, block, p.smem, st>>>(in, in_lo, scale, out_a, out_b, (int)n, (int)inner, hw_lo, r_lo, hw_hi, r_hi, p.nb,
-                                      minmax, buckets, (int)items);
+                                      minmax, buckets, (int)items, mix.every > 0 ? mix.every : 1, mix.offset);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
 
-template <typename InT, bool SECOND, bool FMA>
+template <typename InT, bool SECOND, int FMA>
 static int launch_variant_fma(const DogPlan& p, const InT* in, const double* in_lo, double scale, double* out_a,
                               double* out_b, int64_t planes, int64_t n, int64_t inner, const double* hw_lo, int r_lo,
-                              const double* hw_hi, int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st) {
+                              const double* hw_hi, int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st,
+                              DogMix mix) {
   if (p.R == 16)
     return launch_strip<16, 4, 2, InT, SECOND, FMA>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo,
-                                                     hw_hi, r_hi, minmax, buckets, st);
+                                                     hw_hi, r_hi, minmax, buckets, st, mix);
   if (p.warps == 8)
     return launch_strip<8, 8, 2, InT, SECOND, FMA>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo,
-                                                    hw_hi, r_hi, minmax, buckets, st);
+                                                    hw_hi, r_hi, minmax, buckets, st, mix);
   return launch_strip<8, 4, 3, InT, SECOND, FMA>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
-                                                  r_hi, minmax, buckets, st);
+                                                  r_hi, minmax, buckets, st, mix);
 }
 
+// amt_tune "dog_fma" contracts every plane; otherwise mix.every > 0 selects the per-plane kernel
 template <typename InT, bool SECOND>
 static int launch_variant(const DogPlan& p, const InT* in, const double* in_lo, double scale, double* out_a,
                           double* out_b, int64_t planes, int64_t n, int64_t inner, const double* hw_lo, int r_lo,
-                          const double* hw_hi, int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st) {
+                          const double* hw_hi, int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st,
+                          DogMix mix) {
   if (g_dog_fma)
-    return launch_variant_fma<InT, SECOND, true>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
-                                                 r_hi, minmax, buckets, st);
-  return launch_variant_fma<InT, SECOND, false>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
-                                                r_hi, minmax, buckets, st);
+    return launch_variant_fma<InT, SECOND, 1>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
+                                              r_hi, minmax, buckets, st, mix);
+  if (mix.every > 0)
+    return launch_variant_fma<InT, SECOND, 2>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
+                                              r_hi, minmax, buckets, st, mix);
+  return launch_variant_fma<InT, SECOND, 0>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
+                                            r_hi, minmax, buckets, st, mix);
 }
 
 // pass 1: image (h x w) -> tmp_hi, tmp_lo.  Fast path: both TRANSPOSED (w x h); generic: image layout.
 static int dog_axis0(const DogPlan& p, const void* in, int in_dtype, double in_scale, int64_t n_img, int64_t h,
                      int64_t w, const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, double* tmp_lo,
-                     double* tmp_hi, cudaStream_t st) {
+                     double* tmp_hi, cudaStream_t st, DogMix mix) {
   if (!p.fast) return dog_axis0_generic(in, in_dtype, in_scale, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, tmp_lo, tmp_hi, st);
   if (in_dtype == AMT_U16)
     return launch_variant<uint16_t, false>(p, (const uint16_t*)in, nullptr, in_scale, tmp_hi, tmp_lo, n_img, h, w,
-                                           hw_lo, r_lo, hw_hi, r_hi, nullptr, nullptr, st);
+                                           hw_lo, r_lo, hw_hi, r_hi, nullptr, nullptr, st, mix);
   return launch_variant<double, false>(p, (const double*)in, nullptr, 1.0, tmp_hi, tmp_lo, n_img, h, w, hw_lo, r_lo,
-                                       hw_hi, r_hi, nullptr, nullptr, st);
+                                       hw_hi, r_hi, nullptr, nullptr, st, mix);
 }
 
 // pass 2.  Fast path: the transposed planes (w x h) filtered along their axis 0, lo - hi written back
 // transposed (= image layout); generic: image-layout planes through the tile kernel of gauss.cu.
 static int dog_axis1(const DogPlan& p, const double* tmp_lo, const double* tmp_hi, double* out, int64_t n_img,
                      int64_t h, int64_t w, const double* hw_lo, int r_lo, const double* hw_hi, int r_hi,
-                     uint64_t* minmax, uint16_t* buckets, cudaStream_t st) {
+                     uint64_t* minmax, uint16_t* buckets, cudaStream_t st, DogMix mix) {
   if (!p.fast) return dog_axis1_generic(tmp_lo, tmp_hi, out, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, minmax, st);
   return launch_variant<double, true>(p, tmp_hi, tmp_lo, 1.0, out, nullptr, n_img, w, h, hw_lo, r_lo, hw_hi, r_hi,
-                                      minmax, buckets, st);
+                                      minmax, buckets, st, mix);
 }
 
 // buckets (optional): n_img*h*w uint16 receiving bucket12() of every output sample; *buckets_written
 // tells the caller whether the strip kernels ran (the generic fallback does not produce them).
 int dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,
           const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, double* tmp_lo, double* tmp_hi,
-          uint64_t* minmax, cudaStream_t st, uint16_t* buckets, bool* buckets_written) {
+          uint64_t* minmax, cudaStream_t st, uint16_t* buckets, bool* buckets_written, int exact_every,
+          int exact_offset) {
   if (buckets_written) *buckets_written = false;
+  if (exact_every < 0 || (exact_every > 0 && (exact_offset < 0 || exact_offset >= exact_every))) return AMT_ERR_INVALID;
+  const DogMix mix{exact_every, exact_offset};
   if (!in || !out || !tmp_lo || !tmp_hi || !hw_lo || !hw_hi) return AMT_ERR_INVALID;
   if (n_img <= 0 || h <= 0 || w <= 0 || r_lo < 0 || r_hi < 0) return AMT_ERR_INVALID;
   if (in_dtype != AMT_U16 && in_dtype != AMT_F64) return AMT_ERR_UNSUPPORTED;
@@ -508,8 +537,8 @@ int dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_
   p.fast = p.fast && aligned16(in) && aligned16(out) && aligned16(tmp_lo) && aligned16(tmp_hi);
   if (buckets && !(p.fast && aligned16(buckets))) buckets = nullptr;
   if (buckets_written) *buckets_written = buckets != nullptr;
-  AMT_TRY(dog_axis0(p, in, in_dtype, in_scale, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, tmp_lo, tmp_hi, st));
-  return dog_axis1(p, tmp_lo, tmp_hi, out, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, minmax, buckets, st);
+  AMT_TRY(dog_axis0(p, in, in_dtype, in_scale, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, tmp_lo, tmp_hi, st, mix));
+  return dog_axis1(p, tmp_lo, tmp_hi, out, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, minmax, buckets, st, mix);
 }
 
 }  // namespace amt
@@ -545,6 +574,12 @@ int amt_tune(const char* key, int value) {
     g_dog_generic = value != 0;
   } else if (is("dog_fma")) {
     g_dog_fma = value != 0;
+  } else if (is("dog_exact_every")) {
+    if (value < 0 || value > 64) return AMT_ERR_INVALID;
+    g_dog_exact_every = value;
+  } else if (is("dog_exact_offset")) {
+    if (value < 0 || value > 63) return AMT_ERR_INVALID;
+    g_dog_exact_offset = value;
   } else {
     return AMT_ERR_INVALID;
   }
@@ -555,7 +590,8 @@ int amt_dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_
               const double* half_w_lo, int r_lo, const double* half_w_hi, int r_hi, double* tmp_lo, double* tmp_hi,
               uint64_t* minmax_keys, amt_stream_t stream) {
   return amt::dog2d(in, in_dtype, in_scale, out, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, tmp_lo, tmp_hi,
-                    minmax_keys, amt::as_stream(stream), nullptr, nullptr);
+                    minmax_keys, amt::as_stream(stream), nullptr, nullptr, amt::g_dog_exact_every,
+                    amt::g_dog_exact_every > 0 ? amt::g_dog_exact_offset % amt::g_dog_exact_every : 0);
 }
 
 // The two passes separately (bench / profiling).  The layout of tmp_lo / tmp_hi between them is
@@ -569,7 +605,7 @@ int amt_dog2d_axis0(const void* in, int in_dtype, double in_scale, int64_t n_img
   const DogPlan p = dog_plan(in_dtype, n_img, h, w, r_lo, r_hi);
   if (p.fast && !(aligned16(in) && aligned16(tmp_lo) && aligned16(tmp_hi))) return AMT_ERR_INVALID;
   return dog_axis0(p, in, in_dtype, in_scale, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, tmp_lo, tmp_hi,
-                   as_stream(stream));
+                   as_stream(stream), DogMix{g_dog_exact_every, g_dog_exact_every > 0 ? g_dog_exact_offset % g_dog_exact_every : 0});
 }
 
 int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int64_t n_img, int64_t h, int64_t w,
@@ -581,7 +617,7 @@ int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int
   if (p.fast && !(aligned16(out) && aligned16(tmp_lo) && aligned16(tmp_hi))) return AMT_ERR_INVALID;
   if (minmax_keys) AMT_TRY(minmax_init(minmax_keys, n_img, as_stream(stream)));
   return dog_axis1(p, tmp_lo, tmp_hi, out, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, minmax_keys, nullptr,
-                   as_stream(stream));
+                   as_stream(stream), DogMix{g_dog_exact_every, g_dog_exact_every > 0 ? g_dog_exact_offset % g_dog_exact_every : 0});
 }
 
 }  // extern "C"

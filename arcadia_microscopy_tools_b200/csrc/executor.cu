@@ -126,7 +126,10 @@ static int enqueue_dog(amt_executor* ex, const uint16_t* in, int g, cudaEvent_t 
   trace_mark(ex, ex->s_dog, "dog: begin");
   AMT_TRY(dog2d(in, AMT_U16, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, ex->hw_lo, ex->r_lo, ex->hw_hi,
                 ex->r_hi, ex->tmp_lo, ex->tmp_hi, ex->mm[slot], ex->s_dog, g_exec_buckets ? ex->buckets[slot] : nullptr,
-                &ex->buckets_valid[slot]));
+                &ex->buckets_valid[slot],
+                // only the segmentation channel's plane decides anything discrete (threshold -> labels); the other
+                // channels yield float planes only and take the contracted filter unless the caller asks otherwise
+                (c.exact_all_channels || c.n_channels < 2) ? 0 : c.n_channels, c.seg_channel));
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_done[slot], ex->s_dog));
   trace_mark(ex, ex->s_dog, "dog: end");
   return AMT_OK;

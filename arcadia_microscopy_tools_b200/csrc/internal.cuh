@@ -9,7 +9,8 @@ int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st);
 
 int dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,
           const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, double* tmp_lo, double* tmp_hi,
-          uint64_t* minmax, cudaStream_t st, uint16_t* buckets = nullptr, bool* buckets_written = nullptr);
+          uint64_t* minmax, cudaStream_t st, uint16_t* buckets = nullptr, bool* buckets_written = nullptr,
+          int exact_every = 0, int exact_offset = 0);  // exact_every > 0: only planes p % every == offset keep scipy's order
 
 // order statistics of float64 planes whose bucket12() values were written next to them by dog2d
 int select_f64_bucketed(const double* data, const uint16_t* buckets, int64_t n_img, int64_t n, const int64_t* ranks_host,

@@ -259,8 +259,10 @@ def run_reference(args) -> None:
 
 
 # ------------------------------------------------------------------------------------ GPU side
-def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int) -> dict:
-    """Per-kernel CUDA-event timings of the two Gaussian passes and the FP64 probe."""
+def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int, exact_every: int = 0, exact_offset: int = 0) -> dict:
+    """Per-kernel CUDA-event timings of the two Gaussian passes and the FP64 probe.  exact_every > 0: the launch
+    the executor makes by default (plane p keeps scipy's operation order iff p % exact_every == exact_offset, the
+    other planes use fused multiply-adds); 0: every plane in scipy's order."""
     import ctypes as CT
 
     import torch
@@ -305,10 +307,19 @@ def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int) -> dict:
         torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1) / steps
 
-    ms_v, ms_h, ms_p = timed(v_pass), timed(h_pass), timed(probe)
+    L.check(lib.amt_tune(b"dog_exact_every", exact_every), "amt_tune")
+    L.check(lib.amt_tune(b"dog_exact_offset", exact_offset), "amt_tune")
+    try:
+        ms_v, ms_h = timed(v_pass), timed(h_pass)
+    finally:
+        L.check(lib.amt_tune(b"dog_exact_every", 0), "amt_tune")
+        L.check(lib.amt_tune(b"dog_exact_offset", 0), "amt_tune")
+    ms_p = timed(probe)
     px = planes * H * W
     r_lo, r_hi = len(hw_lo) - 1, len(hw_hi) - 1
-    dp_per_px_axis = (1 + 3 * r_lo) + (1 + 3 * r_hi)
+    exact_share = 1.0 / exact_every if exact_every > 0 else 1.0
+    # DP instructions per sample and axis: DADD + DMUL + DADD per tap pair in scipy's order, DADD + DFMA contracted
+    dp_per_px_axis = exact_share * ((1 + 3 * r_lo) + (1 + 3 * r_hi)) + (1.0 - exact_share) * ((1 + 2 * r_lo) + (1 + 2 * r_hi))
     return {
         "planes": planes, "ms_axis0": ms_v, "ms_axis1": ms_h, "ms_probe": ms_p,
         "fp64_peak_tinstr_s": dp.value / (ms_p * 1e-3) / 1e12,
@@ -364,7 +375,8 @@ def run_b200(args) -> None:
     n_fov = args.fovs
     fovs, given, max_label = build_device_batch(n_fov, args.unique, dev, seed0=20260000 + 1000 * rank)
     cfg = FovPipelineConfig(n_channels=C, height=H, width=W, seg_channel=SEG_CHANNEL, chunk_fovs=args.chunk,
-                            max_labels=4096, max_label_value=max_label, given_label_dtype=np.uint16)
+                            max_labels=4096, max_label_value=max_label, given_label_dtype=np.uint16,
+                            exact_all_channels=args.exact_all_channels)
     ex = FovBatchExecutor(cfg, device=local)
     out = ex.alloc_outputs(n_fov)
 
@@ -423,27 +435,45 @@ def run_b200(args) -> None:
 
     # ---- the same device-resident pass with the DoG's multiply-adds contracted (amt_tune "dog_fma"): what scipy's
     # exact operation order costs.  Not the reported value: the default path stays bit-identical to the reference.
-    contracted = None
+    contracted = strict = None
     if not args.no_contracted:
+        import dataclasses
+
         keep = {k: out[k].clone() for k in ("tables_thr", "counts_thr", "thresholds")}
+
+        def same_as_default() -> bool:
+            return all(torch.equal(out[k].view(torch.int64) if out[k].dtype == torch.float64 else out[k],
+                                   keep[k].view(torch.int64) if keep[k].dtype == torch.float64 else keep[k]) for k in keep)
+
+        def timed_pass(executor) -> float:
+            executor.run_device(fovs, given, out, sync=True)
+            barrier()
+            ms = [executor.run_device(fovs, given, out, sync=True) for _ in range(args.steps)]
+            barrier()
+            t_pass = torch.tensor([sum(ms) / 1e3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_pass, op=dist.ReduceOp.MAX)
+            return float(t_pass[0])
+
         _lib.check(lib.amt_tune(b"dog_fma", 1), "amt_tune")
         try:
-            ex.run_device(fovs, given, out, sync=True)
-            barrier()
-            c_ms = [ex.run_device(fovs, given, out, sync=True) for _ in range(args.steps)]
-            barrier()
+            c_s = timed_pass(ex)
         finally:
             _lib.check(lib.amt_tune(b"dog_fma", 0), "amt_tune")
-        tc = torch.tensor([sum(c_ms) / 1e3], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-        same = all(torch.equal(out[k].view(torch.int64) if out[k].dtype == torch.float64 else out[k],
-                               keep[k].view(torch.int64) if keep[k].dtype == torch.float64 else keep[k]) for k in keep)
-        contracted = {"value": world * args.steps * n_fov * C * H * W / float(tc[0]) / 1e6, "unit": "Mpix/s",
-                      "ms_per_step": 1e3 * float(tc[0]) / args.steps,
-                      "thresholds_counts_and_tables_bit_identical_to_exact_mode": bool(same),
-                      "note": "opt-in amt_tune('dog_fma', 1): DADD+DFMA per tap pair instead of DADD+DMUL+DADD; filtered planes "
-                              "differ from scipy's in the last bits, so this is NOT the reported value"}
+        contracted = {"value": world * args.steps * n_fov * C * H * W / c_s / 1e6, "unit": "Mpix/s",
+                      "ms_per_step": 1e3 * c_s / args.steps,
+                      "thresholds_counts_and_tables_bit_identical_to_default": same_as_default(),
+                      "note": "opt-in amt_tune('dog_fma', 1): fused multiply-adds for EVERY channel, the segmentation channel "
+                              "included (its plane then differs from scipy's in the last bits); NOT the reported value"}
+        if not cfg.exact_all_channels:
+            # the strict configuration: scipy's exact operation order for every channel (all float planes bit-identical)
+            with FovBatchExecutor(dataclasses.replace(cfg, exact_all_channels=True), device=local) as ex_strict:
+                s_s = timed_pass(ex_strict)
+            strict = {"value": world * args.steps * n_fov * C * H * W / s_s / 1e6, "unit": "Mpix/s",
+                      "ms_per_step": 1e3 * s_s / args.steps,
+                      "thresholds_counts_and_tables_bit_identical_to_default": same_as_default(),
+                      "note": "FovPipelineConfig(exact_all_channels=True): the float planes of the channels that are not "
+                              "thresholded are bit-identical to scipy's too (default: equal to ~1e-15 relative)"}
         del keep
 
     # ---- per-kernel roofline (rank 0) and CPU baseline (rank 0, N=1)
@@ -451,13 +481,16 @@ def run_b200(args) -> None:
     if rank == 0:
         peaks = measured_peaks()
         hw = (_gpu.gaussian_half_weights(cfg.low_sigma), _gpu.gaussian_half_weights(cfg.high_sigma))
-        k = time_kernels(lib, _gpu, fovs, hw, steps=max(args.steps, 5), warmup=args.warmup)
+        mixed = not cfg.exact_all_channels and C > 1
+        k = time_kernels(lib, _gpu, fovs, hw, steps=max(args.steps, 5), warmup=args.warmup,
+                         exact_every=C if mixed else 0, exact_offset=SEG_CHANNEL if mixed else 0)
+        k_exact = time_kernels(lib, _gpu, fovs, hw, steps=max(args.steps, 5), warmup=args.warmup) if mixed else k
         dom = "axis1" if k["ms_axis1"] >= k["ms_axis0"] else "axis0"
         dom_ms = k["ms_" + dom]
         achieved = k[dom]["bytes"] / (dom_ms * 1e-3) / 1e9
         fp64_ach = k[dom]["dp_instr"] / (dom_ms * 1e-3) / 1e12
         traffic, traffic_src = ncu_traffic(dom, k["planes"])
-        dp_per_sample_axis = (1 + 3 * (len(hw[0]) - 1)) + (1 + 3 * (len(hw[1]) - 1))
+        dp_per_sample_axis = k[dom]["dp_instr"] / (k["planes"] * H * W) - 1
         ms_per_step = 1e3 * dev_s / args.steps
         value = world * args.steps * n_fov * C * H * W / dev_s / 1e6
         line = {
@@ -467,6 +500,10 @@ def run_b200(args) -> None:
             "config": {"workload": f"config2: {n_fov} FOVs/GPU x {C}x{H}x{W} uint16 + ~{N_CELLS}-cell int32 label mask per FOV; "
                                    "W = DoG(0.6,16)+pct rescale on 4 channels, Otsu+CCL+clear_border on ch1, per-cell tables "
                                    "for the threshold mask and the given mask",
+                       "arithmetic": ("float64, scipy's exact operation order for every channel" if cfg.exact_all_channels else
+                                      "float64; scipy's exact operation order for the segmentation channel (labels, counts, tables "
+                                      "bit-exact by construction), fused multiply-adds for the other channels' float planes "
+                                      "(equal to scipy's to ~1e-15 relative; tolerance 1e-5)"),
                        "fovs_per_gpu": n_fov, "unique_cell_layouts": args.unique, "chunk_fovs": args.chunk,
                        "l2_policy": f"inputs {fovs.numel() * 2 / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
                        "sharding": "FOV-independent, one process per GPU, no collective on the data path"},
@@ -479,20 +516,24 @@ def run_b200(args) -> None:
             "cells_per_fov": {"threshold_mask": float(counts[0].mean()), "given_mask": float(counts[1].mean())},
             "clocks": clocks.summary(),
             "e2e": e2e,
+            "exact_all_channels_mode": strict,
             "contracted_mode": contracted,
             "roofline": {"kernel": f"dog_strip_kernel ({dom} pass of the DoG: sigma 0.6 and 16 filters of {k['planes']} planes)",
                          "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": k[dom]["bytes"], "peak_source": peaks["source"],
                          "ms_per_launch": dom_ms,
-                         "note": "this kernel is FP64-pipe-bound by construction (193 non-FMA DP instr per sample "
-                                 "and axis at sigma=16, scipy's exact operation order); see roofline_fp64"},
+                         "note": "this kernel is FP64-pipe-bound by construction (193 DP instr per sample and axis at sigma=16 in "
+                                 "scipy's exact operation order, 129 contracted; the default launch keeps the exact order for "
+                                 "the segmentation channel's planes only); see roofline_fp64"},
             "roofline_fp64": {"bound": "fp64_pipe", "achieved": fp64_ach, "peak": k["fp64_peak_tinstr_s"],
                               "unit": "T DP-instr/s", "frac": fp64_ach / k["fp64_peak_tinstr_s"],
                               "peak_source": "amt_fp64_probe (DMUL+DADD chains) timed in this run"},
-            "kernels_ms": {"dog_axis0": k["ms_axis0"], "dog_axis1": k["ms_axis1"], "planes": k["planes"]},
-            # what binds the whole path: the exact-order float64 Gaussians need 2 * (1 + 3*r_lo + 1 + 3*r_hi) + 1 DP
-            # instructions per input sample; at the measured DP issue rate that caps one GPU at this many FOV/s
+            "kernels_ms": {"dog_axis0": k["ms_axis0"], "dog_axis1": k["ms_axis1"], "planes": k["planes"],
+                           "exact_planes": k["planes"] // C if mixed else k["planes"],
+                           "all_planes_exact": {"dog_axis0": k_exact["ms_axis0"], "dog_axis1": k_exact["ms_axis1"]}},
+            # what binds the whole path: the float64 Gaussians need 2 * (taps of both filters) + 1 DP instructions per input
+            # sample (401 in scipy's order, 269 contracted); at the measured DP issue rate that caps one GPU at this many FOV/s
             "path_fp64_ceiling": {"dp_instr_per_sample": 2 * dp_per_sample_axis + 1,
                                   "fov_per_s_per_gpu": k["fp64_peak_tinstr_s"] * 1e12 / (C * H * W * (2 * dp_per_sample_axis + 1)),
                                   "frac": (args.steps * n_fov / dev_s) / (k["fp64_peak_tinstr_s"] * 1e12 / (C * H * W * (2 * dp_per_sample_axis + 1)))},
@@ -546,7 +587,10 @@ def main() -> None:
     ap.add_argument("--e2e-fovs", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-contracted", action="store_true", help="skip the extra pass with amt_tune('dog_fma', 1)")
+    ap.add_argument("--no-contracted", action="store_true",
+                    help="skip the two comparison passes (every channel contracted / every channel in scipy's exact order)")
+    ap.add_argument("--exact-all-channels", action="store_true",
+                    help="measure FovPipelineConfig(exact_all_channels=True) as the reported configuration")
     args = ap.parse_args()
     capture_stdout()
     if args.impl == "reference":

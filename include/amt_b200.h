@@ -329,6 +329,11 @@ typedef struct amt_fov_config {
   int32_t with_shape;          /* 1: also fill perimeter / area_convex (amt_region_shape) */
   int32_t given_label_dtype;   /* amt_executor_run_host only: AMT_I32 (0 = default) or AMT_U16 host label
                                   masks (Cellpose's own mask dtype below 65536 cells; halves their PCIe bytes) */
+  int32_t exact_all_channels;  /* 0 (default): scipy's exact operation order for the segmentation channel, whose
+                                  plane decides the labels; the other channels, which only yield float planes,
+                                  run the Gaussians with fused multiply-adds (planes equal to scipy's to ~1e-15
+                                  relative, 1/3 fewer FP64 instructions).  1: exact order for every channel
+                                  (every preprocessed plane bit-identical to the reference's) */
   double low_sigma, high_sigma;  /* subtract_background_dog */
   double bg_percentile;
   double pct_lo, pct_hi;         /* rescale_by_percentile percentile_range */
