@@ -171,6 +171,41 @@ def _contours_from_square_keys(keys: np.ndarray, num_cells: int) -> list[np.ndar
     return outlines
 
 
+
+def _outlines_cellpose_device(labels, num_cells: int) -> list[np.ndarray]:
+    points, offsets = _gpu.outline_borders(labels, num_cells)
+    points = points.astype(np.int64)
+    return [points[offsets[k] : offsets[k + 1]] if offsets[k + 1] > offsets[k] else np.zeros((0, 2)) for k in range(num_cells)]
+
+
+def _outlines_skimage_device(labels, num_cells: int) -> list[np.ndarray]:
+    return _contours_from_square_keys(_gpu.outline_square_keys(labels), num_cells)
+
+
+def _labels_for_outlines(label_image: np.ndarray):
+    """A host label image as the reference's outline helpers take it (labels 1..K, every one present)."""
+    label_image = np.asarray(label_image)
+    if label_image.ndim != 2:
+        raise ValueError("label_image must be a 2D array")
+    if label_image.size and (label_image.min() < 0 or label_image.max() >= 2**30):
+        raise ValueError("labels must lie in [0, 2**30)")
+    return _gpu.to_device(np.ascontiguousarray(label_image, dtype=np.int32)), int(label_image.max()) if label_image.size else 0
+
+
+def _extract_outlines_cellpose(label_image: np.ndarray) -> list[np.ndarray]:
+    """Same name, argument and result as the reference's helper (ref: ``masks.py:68-79``): one (y, x) outline per
+    label 1..K from OpenCV-order border following on the GPU."""
+    labels, num_cells = _labels_for_outlines(label_image)
+    return _outlines_cellpose_device(labels, num_cells) if num_cells else []
+
+
+def _extract_outlines_skimage(label_image: np.ndarray) -> list[np.ndarray]:
+    """Same name, argument and result as the reference's helper (ref: ``masks.py:82-115``; its tests call it
+    directly, ``tests/test_masks.py:86-149``): marching-squares cases on the GPU, contours joined on the host."""
+    labels, num_cells = _labels_for_outlines(label_image)
+    return _outlines_skimage_device(labels, num_cells) if num_cells else []
+
+
 class SegmentationMask:
     """A label (or boolean) mask with optional per-channel intensity images.
 
@@ -273,13 +308,8 @@ class SegmentationMask:
         marching-squares cases from the GPU, joined into ordered contours here."""
         labels = self._labels_device[0][0]
         if self.outline_extractor == "cellpose":
-            points, offsets = _gpu.outline_borders(labels, self.num_cells)
-            points = points.astype(np.int64)
-            return [
-                points[offsets[k] : offsets[k + 1]] if offsets[k + 1] > offsets[k] else np.zeros((0, 2))
-                for k in range(self.num_cells)
-            ]
-        return _contours_from_square_keys(_gpu.outline_square_keys(labels), self.num_cells)
+            return _outlines_cellpose_device(labels, self.num_cells)
+        return _outlines_skimage_device(labels, self.num_cells)
 
     # ------------------------------------------------------------------ properties
     @cached_property

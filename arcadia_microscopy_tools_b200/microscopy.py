@@ -166,6 +166,35 @@ class MicroscopyImage:
             axes = axes.replace("C", "")
         return cls.from_arrays(np.ascontiguousarray(data), channels, axes, sample_metadata)
 
+    @classmethod
+    def from_lif_path(
+        cls,
+        lif_path: Path,
+        image_name: str,
+        channels: list[Channel] | None = None,
+        sample_metadata: dict[str, Any] | None = None,
+    ) -> "MicroscopyImage":
+        """Load the pixel block of one image of a Leica LIF file (ref: ``microscopy.py:178-202``).
+
+        ``channels`` names the channels in file order; it is required for multi-channel images because
+        detector / laser parsing (``leica.py``) is out of scope here.  Supported axes: T, Z, C, Y, X in the
+        order the file stores them.
+        """
+        from .lif_raw import read_lif_image
+
+        data, sizes = read_lif_image(lif_path, image_name)
+        unsupported = [ax for ax in sizes if ax not in "TZCYX"]
+        if unsupported:
+            raise ValueError(f"image '{image_name}' has axes {list(sizes)}; only T, Z, C, Y, X are supported")
+        n_channels = sizes.get("C", 1)
+        if channels is None:
+            if n_channels != 1:
+                raise ValueError("channels must be given for multi-channel LIF images")
+            channels = [CHANNELS["BRIGHTFIELD"]]
+        if len(channels) != n_channels:
+            raise ValueError(f"{len(channels)} channels given for {n_channels} channels in the file")
+        return cls.from_arrays(data, channels, "".join(sizes), sample_metadata)
+
     # ------------------------------------------------------------------ views
     @property
     def shape(self) -> tuple[int, ...]:

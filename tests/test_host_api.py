@@ -308,3 +308,49 @@ def test_threshold_keyword_arguments_are_checked():
         operations._shift_wide_integers(wide)
     shifted, offset = operations._shift_wide_integers(np.array([[-5, 3], [5, 9]], dtype=np.int32))
     assert shifted.dtype == np.uint16 and offset == -5 and shifted.tolist() == [[0, 8], [10, 14]]
+
+
+# ---------------------------------------------------------------- LIF raw reader (host I/O)
+def test_lif_raw_reader_round_trip(tmp_path):
+    """ref: leica.py:39-80 (list_image_names, load_lif_image -> liffile ... asarray()): the pixel block of a named
+    image in the axis order the file stores, for both container versions."""
+    from lif_synth import write_lif
+
+    from arcadia_microscopy_tools_b200 import lif_raw
+    from arcadia_microscopy_tools_b200.microscopy import MicroscopyImage
+
+    rng = np.random.default_rng(4)
+    zstack = rng.integers(0, 65535, (5, 3, 16, 24), dtype=np.uint16)      # Z, C, Y, X (Stellaris-shaped)
+    plane8 = rng.integers(0, 255, (12, 10), dtype=np.uint8)               # Y, X
+    lapse = rng.integers(0, 4095, (4, 2, 8, 8), dtype=np.uint16)          # T, C, Y, X
+    for version in (1, 2):
+        path = tmp_path / f"synthetic_v{version}.lif"
+        write_lif(path, [("zstack", zstack, "ZCYX"), ("overview", plane8, "YX"), ("lapse", lapse, "TCYX")], version=version)
+        assert lif_raw.list_image_names(path) == ["zstack", "overview", "lapse"]
+        got, sizes = lif_raw.read_lif_image(path, "zstack")
+        assert sizes == {"Z": 5, "C": 3, "Y": 16, "X": 24} and got.dtype == np.uint16 and np.array_equal(got, zstack)
+        got, sizes = lif_raw.read_lif_image(path, "overview")
+        assert sizes == {"Y": 12, "X": 10} and got.dtype == np.uint8 and np.array_equal(got, plane8)
+        info = lif_raw.lif_image_info(path, "lapse")
+        assert list(info.sizes) == ["T", "C", "Y", "X"] and info.memory_size == lapse.nbytes
+        with pytest.raises(ValueError, match="Image missing not found in .* Available images"):
+            lif_raw.read_lif_image(path, "missing")
+        image = MicroscopyImage.from_lif_path(path, "zstack", channels=[DAPI, FITC, TRITC])
+        assert image.sizes == {"Z": 5, "C": 3, "Y": 16, "X": 24}
+        assert np.array_equal(image.get_channel_intensities(FITC), zstack[:, 1])
+        with pytest.raises(ValueError, match="channels must be given"):
+            MicroscopyImage.from_lif_path(path, "lapse")
+        single = MicroscopyImage.from_lif_path(path, "overview")
+        assert single.sizes == {"Y": 12, "X": 10} and single.intensities.dtype == np.uint8
+    nested = tmp_path / "nested.lif"
+    write_lif(nested, [("a", plane8, "YX")], folder="Project")
+    assert lif_raw.list_image_names(nested) == ["Project/a"]
+    assert np.array_equal(lif_raw.read_lif_image(nested, "Project/a")[0], plane8)
+    broken = tmp_path / "broken.lif"
+    broken.write_bytes(b"\\x00" * 64)
+    with pytest.raises(ValueError, match="not a LIF file"):
+        lif_raw.list_image_names(broken)
+    truncated = tmp_path / "truncated.lif"
+    truncated.write_bytes((tmp_path / "synthetic_v2.lif").read_bytes()[:-100])
+    with pytest.raises(ValueError):
+        lif_raw.read_lif_image(truncated, "lapse")

@@ -122,6 +122,21 @@ def test_cell_outlines_match_the_oracle(extractor):
 
 
 @pytest.mark.gpu
+def test_module_level_outline_helpers_like_the_reference():
+    """ref: tests/test_masks.py:86-149 imports ``_extract_outlines_skimage`` from ``masks`` and feeds it label images."""
+    multi = make_label_image((60, 60), [(15, 15, 6), (45, 45, 6)])
+    for helper, want in ((masks._extract_outlines_skimage, oracle_outlines.extract_outlines_skimage),
+                         (masks._extract_outlines_cellpose, oracle_outlines.extract_outlines_cellpose)):
+        got = helper(multi)
+        assert len(got) == 2 and all(np.array_equal(a, b) for a, b in zip(got, want(multi)))
+    speck = np.zeros((5, 5), dtype=np.int64)
+    speck[2, 2] = 1
+    outlines = masks._extract_outlines_skimage(speck)
+    assert len(outlines) == 1 and outlines[0].ndim == 2 and outlines[0].shape[1] == 2
+    assert masks._extract_outlines_skimage(np.zeros((8, 8), dtype=np.int64)) == []
+
+
+@pytest.mark.gpu
 def test_cell_outlines_reference_contract():
     """ref: tests/test_masks.py:86-149, through SegmentationMask(outline_extractor='skimage')."""
     m = masks.SegmentationMask(make_label_image((50, 50), [(25, 25, 8)]), remove_edge_cells=False, outline_extractor="skimage")
