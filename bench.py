@@ -232,7 +232,7 @@ def run_reference(args) -> None:
     import multiprocessing as mp
 
     cores = os.cpu_count() or 1
-    workers = max(1, min(cores, 16))
+    workers = max(1, min(cores, 64))  # every host core (each worker holds ~1 GB of float64 planes)
     batch = [host_fov(20260000 + i % 2) for i in range(workers)]
     times = []
     with mp.get_context("fork").Pool(workers) as pool:
