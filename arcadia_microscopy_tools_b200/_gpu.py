@@ -444,3 +444,32 @@ def threshold_gt_image(x, thr, offset: float):
     check(_lib.load().amt_threshold_gt_image(ptr(x), dtype_code(x), x.numel(), ptr(thr), float(offset), ptr(mask),
                                              stream_ptr()), "amt_threshold_gt_image")
     return mask
+
+
+class PinnedBuffer:
+    """A page-locked host array from ``amt_host_alloc`` (no torch involved): ``.array`` is a NumPy view of the
+    pinned pages.  ``write_combined=True`` suits buffers the host only fills (decoded frames on their way to the
+    device); reading them back on the CPU is slow.  Freed by ``close()`` / the context manager."""
+
+    def __init__(self, shape, dtype, write_combined: bool = False) -> None:
+        import ctypes as C
+
+        self._lib = _lib.load()
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+        self._ptr = C.c_void_p()
+        check(self._lib.amt_host_alloc(nbytes, 1 if write_combined else 0, C.byref(self._ptr)), "amt_host_alloc")
+        raw = (C.c_uint8 * nbytes).from_address(self._ptr.value)
+        self.array = np.frombuffer(raw, dtype=dt).reshape(shape)
+
+    def close(self) -> None:
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            check(self._lib.amt_host_free(self._ptr), "amt_host_free")
+            self._ptr = None
+
+    def __enter__(self) -> "PinnedBuffer":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()

@@ -109,6 +109,8 @@ SIGNATURES: dict[str, tuple] = {
     "amt_launch_count": (C.c_uint64, []),
     "amt_fp64_probe": (_i, [_i, _p, C.POINTER(C.c_uint64), _p]),
     "amt_tune": (_i, [C.c_char_p, _i]),
+    "amt_host_alloc": (_i, [_sz, _i, C.POINTER(_p)]),
+    "amt_host_free": (_i, [_p]),
     "amt_selftest_div": (_i, [_p, _p, _i64, _p, _p]),
     "amt_gaussian_axis": (_i, [_p, _i, _d, _p, _i64, _i64, _i64, _p, _i, _p]),
     "amt_gaussian_axis_mode": (_i, [_p, _i, _d, _p, _i64, _i64, _i64, _p, _i, _i, _p]),

@@ -52,6 +52,22 @@ int amt_fp64_probe(int iters, double* scratch, uint64_t* dp_instructions, amt_st
   return AMT_OK;
 }
 
+// Pinned (page-locked) host staging for callers that do not go through torch: decoded frames are written
+// here once and read by the copy engine.  write_combined = 1 asks for write-combined pages (no CPU cache
+// snooping on the device's reads; slow for the CPU to read back, so only for buffers the host just fills).
+int amt_host_alloc(size_t bytes, int write_combined, void** out) {
+  if (!out || bytes == 0) return AMT_ERR_INVALID;
+  *out = nullptr;
+  AMT_CUDA_TRY(cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+  return AMT_OK;
+}
+
+int amt_host_free(void* ptr) {
+  if (!ptr) return AMT_OK;
+  AMT_CUDA_TRY(cudaFreeHost(ptr));
+  return AMT_OK;
+}
+
 int amt_version(void) { return 100; }  // 0.1.0
 
 const char* amt_strerror(int status) {

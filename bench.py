@@ -406,13 +406,20 @@ def run_b200(args) -> None:
     if not args.no_e2e:
         # pinned host staging is per rank: halve it on multi-GPU runs so that 8 ranks stay well inside host RAM
         n_e2e = min(n_fov, args.e2e_fovs if world == 1 else min(args.e2e_fovs, 128))
-        h_fovs = torch.empty((n_e2e, C, H, W), dtype=torch.int16, pin_memory=True)
         # label masks travel as uint16 (Cellpose's own mask dtype below 65536 cells): 8.4 instead of 16.8 MB per FOV
-        h_given = torch.empty((n_e2e, H, W), dtype=torch.int16, pin_memory=True)
-        h_fovs.copy_(fovs[:n_e2e])
-        h_given.copy_(given[:n_e2e].to(torch.int16))
-        np_fovs = h_fovs.numpy().view(np.uint16)
-        np_given = h_given.numpy().view(np.uint16)
+        if args.host_alloc == "torch":
+            h_fovs = torch.empty((n_e2e, C, H, W), dtype=torch.int16, pin_memory=True)
+            h_given = torch.empty((n_e2e, H, W), dtype=torch.int16, pin_memory=True)
+            h_fovs.copy_(fovs[:n_e2e])
+            h_given.copy_(given[:n_e2e].to(torch.int16))
+            np_fovs = h_fovs.numpy().view(np.uint16)
+            np_given = h_given.numpy().view(np.uint16)
+        else:  # the library's own pinned staging (amt_host_alloc), optionally write-combined
+            pin_fovs = _gpu.PinnedBuffer((n_e2e, C, H, W), np.uint16, write_combined=args.host_alloc == "wc")
+            pin_given = _gpu.PinnedBuffer((n_e2e, H, W), np.uint16, write_combined=args.host_alloc == "wc")
+            np_fovs, np_given = pin_fovs.array, pin_given.array
+            np_fovs[...] = fovs[:n_e2e].cpu().numpy().view(np.uint16)
+            np_given[...] = given[:n_e2e].to(torch.int16).cpu().numpy().view(np.uint16)
         h_out = ex.alloc_host_outputs(n_e2e)
         for _ in range(min(args.warmup, 2)):
             ex.run_host(np_fovs, np_given, h_out)
@@ -431,7 +438,8 @@ def run_b200(args) -> None:
         e2e = {"value": world * args.steps * n_e2e * C * H * W / e2e_s / 1e6, "unit": "Mpix/s",
                "h2d_bytes_per_step": int(np_fovs.nbytes + np_given.nbytes), "d2h_bytes_per_step": d2h,
                "fov_per_s": world * args.steps * n_e2e / e2e_s, "fovs_per_step": n_e2e, "timing": "wall clock around the synchronous C-ABI call",
-               "rank0_cpu_affinity": f"{len(cpus)} CPUs local to the GPU (NVML)" if cpus else "unchanged"}
+               "rank0_cpu_affinity": f"{len(cpus)} CPUs local to the GPU (NVML)" if cpus else "unchanged",
+               "host_buffers": {"torch": "torch pinned tensors", "pinned": "amt_host_alloc", "wc": "amt_host_alloc, write-combined"}[args.host_alloc]}
 
     # ---- the same device-resident pass with the DoG's multiply-adds contracted (amt_tune "dog_fma"): what scipy's
     # exact operation order costs.  Not the reported value: the default path stays bit-identical to the reference.
@@ -586,6 +594,8 @@ def main() -> None:
     ap.add_argument("--chunk", type=int, default=8, help="FOVs per launch wave")
     ap.add_argument("--e2e-fovs", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-alloc", default="torch", choices=["torch", "pinned", "wc"],
+                    help="pinned host input buffers of the e2e leg: torch's allocator, amt_host_alloc, or amt_host_alloc write-combined")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-contracted", action="store_true",
                     help="skip the two comparison passes (every channel contracted / every channel in scipy's exact order)")

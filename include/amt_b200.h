@@ -109,6 +109,12 @@ int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int
  * off by default). */
 int amt_tune(const char* key, int value);
 
+/* Pinned host staging without torch (ref: nikon.py:25-43 / leica.py:52-80 decode into host arrays; the
+ * north star feeds the device from pinned, double-buffered staging).  write_combined = 1: write-combined
+ * pages for buffers the host only fills.  Free with amt_host_free. */
+int amt_host_alloc(size_t bytes, int write_combined, void** out);
+int amt_host_free(void* ptr);
+
 /* Test hook: *mismatches = number of i for which the plane-constant division sequence of the map
  * kernel (reciprocal + two FMA corrections) differs bitwise from __ddiv_rn(a[i], b[i]). */
 int amt_selftest_div(const double* a, const double* b, int64_t n, uint64_t* mismatches, amt_stream_t stream);

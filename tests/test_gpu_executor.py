@@ -206,3 +206,21 @@ def test_run_host_uint16_label_masks_match_int32():
     for i in range(n_fov):
         cnt = int(outs[0]["counts_given"][i])
         assert np.array_equal(outs[0]["tables_given"][i][:, :cnt], outs[1]["tables_given"][i][:, :cnt], equal_nan=True)
+
+
+def test_run_host_from_library_pinned_staging():
+    """amt_host_alloc staging (plain and write-combined) feeds the host-fed entry point like any host buffer."""
+    n_fov, C, shape = 2, 2, (128, 160)
+    fovs = np.stack([make_fov(300 + i, C, shape[0], shape[1], 25)[0] for i in range(n_fov)])
+    cfg = FovPipelineConfig(n_channels=C, height=shape[0], width=shape[1], seg_channel=0, chunk_fovs=1, max_labels=256,
+                            quantify_given_mask=False)
+    with FovBatchExecutor(cfg) as ex:
+        want = ex.run_host(fovs, None)
+        for wc in (False, True):
+            with _gpu.PinnedBuffer(fovs.shape, np.uint16, write_combined=wc) as staging:
+                staging.array[...] = fovs
+                got = ex.run_host(staging.array, None)
+                assert np.array_equal(got["counts_thr"], want["counts_thr"]) and np.array_equal(got["thresholds"], want["thresholds"])
+                for i in range(n_fov):
+                    k = int(want["counts_thr"][i])
+                    assert np.array_equal(got["tables_thr"][i][:, :k], want["tables_thr"][i][:, :k], equal_nan=True)
