@@ -114,3 +114,49 @@ def test_gaussian_definition_matches_opencv(sigma):
     if dog is not None:
         lo = cv2.GaussianBlur(img, (5, 5), sigmaX=0.6, sigmaY=0.6, borderType=cv2.BORDER_REPLICATE)
         assert np.allclose(dog, lo - want, rtol=0, atol=1e-13)
+
+
+def test_local_threshold_building_blocks_against_opencv():
+    """The local-window methods rest on two filters; both restatements are checked against
+    OpenCV's independent implementations (summation order differs: tolerance 1e-12 relative, written here):
+    * threshold_local: scipy's Gaussian with mode='reflect' == cv2.GaussianBlur(ksize = 2*int(4s+0.5)+1, BORDER_REFLECT)
+    * niblack / sauvola: the integral-image window mean / std with np.pad 'reflect' == cv2.boxFilter / sqrBoxFilter
+      with BORDER_REFLECT_101."""
+    from scipy import ndimage as ndi
+
+    from oracle import threshold
+
+    rng = np.random.default_rng(31)
+    image = rng.random((90, 123)) * 1000.0
+    for block_size in (5, 35):
+        sigma = (block_size - 1) / 6.0
+        radius = int(4.0 * sigma + 0.5)
+        want = cv2.GaussianBlur(image, (2 * radius + 1, 2 * radius + 1), sigmaX=sigma, sigmaY=sigma, borderType=cv2.BORDER_REFLECT)
+        got = threshold.threshold_local(image, block_size)  # offset 0: the smoothed image itself
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+        assert np.array_equal(got, ndi.gaussian_filter(image, sigma, mode="reflect"))
+    u16 = rng.integers(0, 60000, (101, 77)).astype(np.uint16)
+    for window in (3, 15, (5, 31)):
+        wy, wx = (window, window) if np.isscalar(window) else window
+        mean, std = threshold._mean_std(u16, window)
+        f = u16.astype(np.float64)
+        mean_cv = cv2.boxFilter(f, -1, (wx, wy), normalize=True, borderType=cv2.BORDER_REFLECT_101)
+        sq_cv = cv2.sqrBoxFilter(f, -1, (wx, wy), normalize=True, borderType=cv2.BORDER_REFLECT_101)
+        std_cv = np.sqrt(np.clip(sq_cv - mean_cv * mean_cv, 0, None))
+        assert np.abs(mean - mean_cv).max() <= 1e-12 * mean.max() and np.abs(std - std_cv).max() <= 1e-9 * std.max()
+
+
+def test_triangle_threshold_is_within_one_level_of_opencv():
+    """cv2.threshold(THRESH_TRIANGLE) implements the same construction (peak, longer tail, farthest bin from the
+    line) with its own end conventions: it lands exactly one grey level beside scikit-image's answer.  A loose,
+    independent check that the restated scan finds the same corner of the histogram."""
+    from oracle import threshold
+
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        shape = (200, 180)
+        fg = rng.random(shape) < rng.uniform(0.05, 0.4)
+        img = np.where(fg, rng.normal(rng.uniform(120, 220), rng.uniform(5, 25), shape),
+                       rng.gamma(2.0, rng.uniform(5, 20), shape)).clip(0, 255).astype(np.uint8)
+        t_cv, _ = cv2.threshold(img, 0, 255, cv2.THRESH_BINARY | cv2.THRESH_TRIANGLE)
+        assert abs(int(t_cv) - int(threshold.threshold_triangle(img))) <= 1
