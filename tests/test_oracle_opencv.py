@@ -160,3 +160,31 @@ def test_triangle_threshold_is_within_one_level_of_opencv():
                        rng.gamma(2.0, rng.uniform(5, 20), shape)).clip(0, 255).astype(np.uint8)
         t_cv, _ = cv2.threshold(img, 0, 255, cv2.THRESH_BINARY | cv2.THRESH_TRIANGLE)
         assert abs(int(t_cv) - int(threshold.threshold_triangle(img))) <= 1
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_clear_border_and_relabel_sequential_against_independent_constructions(seed):
+    """clear_border (bool and integer masks) and relabel_sequential are definitions rather than algorithms; the
+    oracle's restatements are checked against constructions that share no code with them: OpenCV components that
+    own a border pixel (per label value for integer masks: skimage clears the border-touching FRAGMENT of a
+    label), and np.unique's inverse for the renumbering."""
+    from conftest import random_blobs
+
+    mask = random_blobs(100 + seed, (90, 120), 40)
+    n, comp = cv2.connectedComponents(mask.astype(np.uint8), connectivity=8)
+    touching = np.unique(np.concatenate([comp[0], comp[-1], comp[:, 0], comp[:, -1]]))
+    want = mask & ~np.isin(comp, touching[touching > 0])
+    got = labeling.clear_border(mask)
+    assert got.dtype == np.bool_ and np.array_equal(got, want)
+    # integer mask: label values in stripes so that labels touch each other and split into fragments
+    values = np.where(mask, 7 + 3 * ((np.arange(120)[None, :] // 9) % 4) + 20 * ((np.arange(90)[:, None] // 30)), 0).astype(np.int64)
+    want_int = values.copy()
+    for v in np.unique(values)[1:]:
+        _, comp_v = cv2.connectedComponents((values == v).astype(np.uint8), connectivity=8)
+        touch_v = np.unique(np.concatenate([comp_v[0], comp_v[-1], comp_v[:, 0], comp_v[:, -1]]))
+        want_int[np.isin(comp_v, touch_v[touch_v > 0])] = 0
+    got_int = labeling.clear_border(values)
+    assert got_int.dtype == values.dtype and np.array_equal(got_int, want_int)
+    uniq, inverse = np.unique(want_int, return_inverse=True)
+    assert uniq[0] == 0
+    assert np.array_equal(labeling.relabel_sequential(want_int), inverse.reshape(want_int.shape))
