@@ -91,9 +91,11 @@ __device__ __forceinline__ int code_dy(int s) { return (int)((0xa901u >> (2 * s)
 
 // Follows the outer border that starts at (y0, x0) (its west neighbour is not L).  Returns the number
 // of border points cv2 would list (CHAIN_APPROX_NONE); *min_idx = smallest raster index visited;
-// points (optional): (y, x) int32 pairs.
+// points (optional): (y, x) int32 pairs.  abort_early: give up (return 0) as soon as a pixel that precedes the
+// start in raster order turns up - the start is then only a local top of a border that begins earlier, and a
+// ragged component with thousands of local tops must not have each of them walk its whole border.
 __device__ int64_t trace_border(const Tracer& t, const int y0, const int x0, int64_t* min_idx, int32_t* points,
-                                const int64_t max_points) {
+                                const int64_t max_points, const bool abort_early) {
   int s = 4;
   const int s_stop = 4;
   bool found = false;
@@ -130,6 +132,10 @@ __device__ int64_t trace_border(const Tracer& t, const int y0, const int x0, int
     }
     ++n;
     const int64_t idx = (int64_t)y3 * t.w + x3;
+    if (abort_early && idx < mn) {
+      *min_idx = idx;
+      return 0;
+    }
     mn = idx < mn ? idx : mn;
     if ((y4 == y0 && x4 == x0 && y3 == y1 && x3 == x1) || n > 4 * (int64_t)t.h * t.w) break;
     y3 = y4;
@@ -152,7 +158,7 @@ outline_find_kernel(const int32_t* __restrict__ labels, const int h, const int w
   const Tracer t{labels, h, w, L};
   if (t.at(y, x - 1) || t.at(y - 1, x - 1) || t.at(y - 1, x) || t.at(y - 1, x + 1)) return;
   int64_t mn;
-  const int64_t n = trace_border(t, y, x, &mn, nullptr, 0);
+  const int64_t n = trace_border(t, y, x, &mn, nullptr, 0, true);
   const int64_t me = (int64_t)y * w + x;
   if (mn != me) return;  // a local top of a border that starts earlier in raster order
   const unsigned long long len = n > 0xffffffffll ? 0xffffffffull : (unsigned long long)n;
@@ -171,7 +177,7 @@ outline_write_kernel(const int32_t* __restrict__ labels, const int h, const int 
   const int64_t start = (int64_t)(b & 0xffffffffull);
   const Tracer t{labels, h, w, (int)(k + 1)};
   int64_t mn;
-  trace_border(t, (int)(start / w), (int)(start % w), &mn, points + 2 * offsets[k], offsets[k + 1] - offsets[k]);
+  trace_border(t, (int)(start / w), (int)(start % w), &mn, points + 2 * offsets[k], offsets[k + 1] - offsets[k], false);
 }
 
 }  // namespace amt

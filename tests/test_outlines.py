@@ -122,6 +122,24 @@ def test_cell_outlines_match_the_oracle(extractor):
 
 
 @pytest.mark.gpu
+def test_outlines_of_ragged_threshold_components():
+    """A noisy threshold mask: a few large, ragged components with hundreds of local tops, holes and specks (the
+    border follower must start each outer border exactly once, at its raster-first pixel)."""
+    rng = np.random.default_rng(12)
+    field = ndi.gaussian_filter(rng.random((384, 416)), 2.0)
+    lab, n = ndi.label(field > np.percentile(field, 55), structure=np.ones((3, 3)))
+    assert n > 20 and np.bincount(lab.ravel())[1:].max() > 5000
+    lab = lab.astype(np.int64)
+    for extractor, reference in (("cellpose", oracle_outlines.extract_outlines_cellpose),
+                                 ("skimage", oracle_outlines.extract_outlines_skimage)):
+        got = masks.SegmentationMask(lab, remove_edge_cells=False, outline_extractor=extractor).cell_outlines
+        want = reference(lab)
+        assert len(got) == len(want) == n
+        for k, (a, b) in enumerate(zip(got, want)):
+            assert a.shape == b.shape and np.array_equal(a, b), (extractor, k)
+
+
+@pytest.mark.gpu
 def test_module_level_outline_helpers_like_the_reference():
     """ref: tests/test_masks.py:86-149 imports ``_extract_outlines_skimage`` from ``masks`` and feeds it label images."""
     multi = make_label_image((60, 60), [(15, 15, 6), (45, 45, 6)])
