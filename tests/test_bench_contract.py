@@ -1,0 +1,55 @@
+"""The JSON line ``bench.py`` prints is a contract with the driver; the committed lines of the last measurement
+pass (``profiles/r01_bench_*.json``) must carry every key it names, with consistent values."""
+
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import pytest
+
+PROFILES = Path(__file__).resolve().parents[1] / "profiles"
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e"}
+
+
+def _line(name: str) -> dict:
+    path = PROFILES / name
+    if not path.exists():
+        pytest.skip(f"{name} not committed")
+    return json.loads(path.read_text())
+
+
+@pytest.mark.parametrize("name,n_gpus", [("r01_bench_default_n1.json", 1), ("r01_bench_n8.json", 8)])
+def test_b200_line_has_the_contract_keys(name, n_gpus):
+    d = _line(name)
+    assert BASE_KEYS | {"gpu_launches", "clocks", "roofline"} <= set(d)
+    assert d["n_gpus"] == n_gpus and d["unit"] == "Mpix/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None and d["warmup"] >= 3
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["gpu_launches"] > 0 and d["value"] > 0
+    # value = samples per second of the timed steps (256 FOVs of 4 x 2048 x 2048 per GPU and step)
+    samples = n_gpus * d["steps"] * d["config"]["fovs_per_gpu"] * 4 * 2048 * 2048
+    assert d["value"] == pytest.approx(samples / (d["ms_per_step"] * d["steps"] * 1e-3) / 1e6, rel=1e-6)
+    e2e = d["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e2e)
+    assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and 0 < e2e["value"] < d["value"]
+    clocks = d["clocks"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(clocks) and clocks["samples"] >= 10
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks["reasons"])
+    roof = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(roof) and roof["bound"] in ("hbm", "tensor")
+    assert roof["frac"] == pytest.approx(roof["achieved"] / roof["peak"], rel=1e-9) and 0 < roof["frac"] < 1
+    if n_gpus == 1:
+        cpu = d["cpu_baseline"]
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(cpu) and cpu["kind"] in ("reference", "port")
+        # the strict and the fully contracted passes decide the same labels as the default one
+        for key in ("exact_all_channels_mode", "contracted_mode"):
+            assert d[key]["thresholds_counts_and_tables_bit_identical_to_default"] is True
+
+
+def test_reference_arm_line():
+    d = _line("r01_bench_reference_arm.json")
+    assert BASE_KEYS | {"impl", "cpu_baseline"} <= set(d) and d["impl"] == "reference"
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
