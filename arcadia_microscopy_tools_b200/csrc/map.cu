@@ -100,6 +100,44 @@ __device__ __forceinline__ double map_value_mode(double x, const amt_map_params&
   return y;
 }
 
+// Modes 2 / 3 on a thread's 8 samples.  The numerator a = clamp(y, p1, p2) - p1 is +0 or positive and at most
+// p2 - p1, so the plane-constant division needs neither the upper-range test nor the sign fix of div_const, and
+// the rare sample the three-instruction sequence cannot serve (a tiny non-zero a below 2^-400, -0, NaN) is
+// flagged instead of branched on: one test per batch, __ddiv_rn for the whole batch when it fires.
+template <int MODE>
+__device__ __forceinline__ void map_rescale8(double (&v)[8], const amt_map_params& p, const DivConst& den, const double gain) {
+  constexpr int T_LO = (1023 - 400) << 20, T_HI = (1023 + 400) << 20;
+  double a[8];
+  bool slow = !den.fast || !(den.b > 0.0);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    double y = v[e];
+    if (MODE == 3) y = dsub(y, p.lvl);
+    if (MODE == 3 && p.p1 < 0.0) y = fmax(y, 0.0);  // p1 >= 0 otherwise: max(max(t, 0), p1) = max(t, p1)
+    y = fmin(fmax(y, p.p1), p.p2);
+    a[e] = dsub(y, p.p1);
+    const int hi = __double2hiint(a[e]);
+    const bool in_range = (unsigned)(hi - T_LO) < (unsigned)(T_HI - T_LO);  // false for negative, -0, inf, NaN
+    slow |= !(in_range || (hi | __double2loint(a[e])) == 0);
+  }
+  const bool plain_out = gain == 1.0 && p.o1 == 0.0;  // q * 1.0 + 0.0 is q exactly (q >= +0)
+  if (!slow) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const double q0 = dmul(a[e], den.y);
+      const double r = __fma_rn(-den.b, q0, a[e]);
+      const double q1 = __fma_rn(r, den.y, q0);
+      v[e] = plain_out ? q1 : dadd(dmul(q1, gain), p.o1);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const double q = ddiv(a[e], den.b);
+      v[e] = plain_out ? q : dadd(dmul(q, gain), p.o1);
+    }
+  }
+}
+
 struct HistRange {
   double first, last, denom, step;
   bool step_zero;
@@ -230,9 +268,18 @@ map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, cons
         const int64_t q2 = q + step;
         const bool second = q2 < n4;
         load4<InT>(src + 4 * q, v);
-        if (second) load4<InT>(src + 4 * q2, v + 4);
+        if (second) {
+          load4<InT>(src + 4 * q2, v + 4);
+        } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = map_value_mode<MODE>(v[e], p, den, gain);
+          for (int e = 0; e < 4; ++e) v[4 + e] = v[e];  // a last odd group: defined values, results dropped
+        }
+        if constexpr (MODE == 2 || MODE == 3) {
+          map_rescale8<MODE>(v, p, den, gain);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = map_value_mode<MODE>(v[e], p, den, gain);
+        }
         st_stream(dst + 4 * q, v[0], v[1]);
         st_stream(dst + 4 * q + 2, v[2], v[3]);
         if (second) {

@@ -123,6 +123,27 @@ def test_rescale_by_percentile_bit_exact():
     _bits_equal(operations.rescale_by_percentile(u8, (1, 99)), oracle.rescale_by_percentile(u8, (1, 99)), "uint8")
 
 
+def test_rescale_division_rare_paths_bit_exact():
+    """The map kernel divides by the plane constant p2 - p1 with a three-instruction sequence and hands the samples
+    it cannot serve (tiny non-zero numerators, a tiny or huge divisor) to __ddiv_rn: planes that hit those paths."""
+    rng = np.random.default_rng(5)
+    n = 96 * 128
+    big = rng.random(n)
+    tiny_mix = np.where(rng.random(n) < 0.6, 0.0, big)              # p1 = 0: numerators are the samples themselves
+    tiny_mix[rng.choice(n, 200, replace=False)] = rng.random(200) * 1e-200   # far below 2^-400
+    tiny_mix[rng.choice(n, 50, replace=False)] = 5e-324                     # the smallest subnormal
+    planes = {
+        "tiny numerators": tiny_mix,
+        "subnormal divisor": rng.random(n) * 1e-310,
+        "huge divisor": rng.random(n) * 1e305,
+        "ordinary": rng.normal(0.0, 1.0, n),
+    }
+    for name, flat in planes.items():
+        x = flat.reshape(96, 128)
+        for pr, out in (((1, 99), (0, 1)), ((0, 100), (0, 1)), ((5, 95), (-2.0, 7.5))):
+            _bits_equal(operations.rescale_by_percentile(x, pr, out), oracle.rescale_by_percentile(x, pr, out), f"{name} {pr} {out}")
+
+
 def test_apply_threshold_matches_oracle():
     fov, _, _ = make_fov(23, 2, 200, 240, 30)
     for c in range(2):
