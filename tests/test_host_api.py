@@ -342,6 +342,14 @@ def test_lif_raw_reader_round_trip(tmp_path):
             MicroscopyImage.from_lif_path(path, "lapse")
         single = MicroscopyImage.from_lif_path(path, "overview")
         assert single.sizes == {"Y": 12, "X": 10} and single.intensities.dtype == np.uint8
+    # channel-interleaved storage (channel stride = one sample): the axes come back in stored order, C last
+    interleaved = rng.integers(0, 60000, (6, 7, 2), dtype=np.uint16)
+    inter_path = tmp_path / "interleaved.lif"
+    write_lif(inter_path, [("inter", interleaved, "YXC")])
+    got, sizes = lif_raw.read_lif_image(inter_path, "inter")
+    assert sizes == {"Y": 6, "X": 7, "C": 2} and np.array_equal(got, interleaved)
+    image = MicroscopyImage.from_lif_path(inter_path, "inter", channels=[DAPI, FITC])
+    assert np.array_equal(image.get_channel_intensities(FITC), interleaved[..., 1])
     nested = tmp_path / "nested.lif"
     write_lif(nested, [("a", plane8, "YX")], folder="Project")
     assert lif_raw.list_image_names(nested) == ["Project/a"]
