@@ -25,11 +25,21 @@ Pinning status
 * Raw-data golden checks (sha256, per-channel min/max/sum) and the provisional
   known answers of SURVEY.md section 8c for ``example-multichannel.nd2`` are checked in
   ``tests/test_golden.py`` against ``tests/golden/``.
-* Everything that is scikit-image's *own* Python (Otsu scan, clear_border,
-  relabel_sequential, regionprops) has no numeric test in the reference and no
-  importable implementation here: **parity unpinned** for those legs beyond the
-  reference's coarse assertions (disc areas, centroids within 2 px, circularity range),
-  which ``tests/test_oracle.py`` re-checks.
+* Independent implementations of the same definitions in OpenCV 4.13 pin further legs
+  (``tests/test_oracle_opencv.py``): integer-image Otsu, 8-connected labelling with area /
+  bbox / centroid, second-order central moments, the Gaussian's definition (nearest and
+  reflect borders), the box mean / std behind niblack and sauvola, clear_border (bool and
+  integer-fragment semantics) and relabel_sequential; ``outlines.extract_outlines_cellpose``
+  is a loop around the REAL ``cv2.findContours`` (``tests/test_outlines.py``).
+* What remains scikit-image's *own* Python with no importable implementation here
+  (isodata / yen / li / minimum / triangle scans, the float-image Otsu path, the
+  threshold_local / niblack / sauvola formulas, find_contours' case table and segment
+  joining, perimeter weights, 3-D regionprops formulas) is restated from the published
+  source: **parity unpinned** for those legs beyond the reference's coarse assertions (disc
+  areas, centroids within 2 px, circularity range, outline contract), scikit-image's own
+  ``find_contours`` docstring example and the committed golden vectors of the reference
+  fixture (``tests/golden/``), which ``tests/test_oracle.py``, ``tests/test_outlines.py`` and
+  ``tests/test_golden*.py`` re-check.
 """
 
 from . import exposure, filters, labeling, outlines, percentile, regionprops, threshold  # noqa: F401
