@@ -139,6 +139,74 @@ def dog2d(x, scale: float, low_sigma: float, high_sigma: float):
     return out, mm
 
 
+class TensorCoreGaussian:
+    """Handle of the tcgen05 / TMA Gaussian (``amt_tcg_*``): quantised weights + band tiles on the device."""
+
+    def __init__(self, sigma: float, device=None):
+        torch = torch_mod()
+        self.dev = require_cuda() if device is None else device
+        self.lib = _lib.load()
+        self.hw = gaussian_half_weights(sigma)
+        self.radius = len(self.hw) - 1
+        self.handle = C.c_void_p()
+        check(self.lib.amt_tcg_create(self.hw.ctypes.data, self.radius, self.dev.index or 0, C.byref(self.handle)),
+              "amt_tcg_create")
+        w = np.zeros(self.radius + 1, dtype=np.uint64)
+        s = C.c_int()
+        check(self.lib.amt_tcg_weights(self.handle, w.ctypes.data, C.byref(s)), "amt_tcg_weights")
+        self.int_weights, self.scale_bits = w, int(s.value)
+        self._torch = torch
+
+    def close(self):
+        if self.handle:
+            self.lib.amt_tcg_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def supported(self, h: int, w: int) -> bool:
+        return bool(self.lib.amt_tcg_supported(h, w, self.radius))
+
+    def axis0(self, x, skip_every: int = 0, skip_offset: int = 0):
+        """x: (n_img, H, W) uint16 bits -> (n_img, 5, H, W) uint8 digit planes of the axis-0 pass."""
+        torch = self._torch
+        n_img, h, w = x.shape
+        digits = torch.zeros((n_img, 5, h, w), dtype=torch.uint8, device=x.device)
+        check(self.lib.amt_tcg_axis0(self.handle, ptr(x), n_img, h, w, ptr(digits), skip_every, skip_offset, stream_ptr()),
+              "amt_tcg_axis0")
+        return digits
+
+    def axis1(self, digits, lo=None, scale: float = 1.0 / 65535.0, want_buckets: bool = False, skip_every: int = 0,
+              skip_offset: int = 0):
+        """digits -> (lo - G_hi float64 planes, min/max keys, bucket codes or None)."""
+        torch = self._torch
+        n_img, _, h, w = digits.shape
+        out = torch.zeros((n_img, h, w), dtype=torch.float64, device=digits.device)
+        mm = torch.empty((n_img, 2), dtype=torch.int64, device=digits.device)
+        buckets = torch.zeros((n_img, h, w), dtype=torch.int16, device=digits.device) if want_buckets else None
+        check(self.lib.amt_tcg_axis1(self.handle, ptr(digits), ptr(lo), scale, ptr(out), n_img, h, w, ptr(buckets), ptr(mm),
+                                     skip_every, skip_offset, stream_ptr()),
+              "amt_tcg_axis1")
+        return out, mm, buckets
+
+
+def gauss_lo2d(x, scale: float, sigma: float, skip_every: int = 0, skip_offset: int = 0):
+    """The narrow Gaussian (radius <= 4) of (n_img, H, W) uint16 planes, float64, scipy's order."""
+    torch = torch_mod()
+    n_img, h, w = x.shape
+    hw = gaussian_half_weights(sigma)
+    d_hw = torch.from_numpy(hw).to(x.device)
+    out = torch.zeros((n_img, h, w), dtype=torch.float64, device=x.device)
+    check(_lib.load().amt_gauss_lo2d(ptr(x), scale, ptr(out), n_img, h, w, ptr(d_hw), len(hw) - 1, skip_every, skip_offset,
+                                     stream_ptr()),
+          "amt_gauss_lo2d")
+    return out
+
+
 def gaussian_nd(x, scale: float, sigma, mode: int = 0):
     """All-axes Gaussian of one N-D array (scipy's axis order 0, 1, ...).  sigma: one value or one per
     axis; mode: 0 = scipy 'nearest', 1 = scipy 'reflect' (``AMT_EXTEND_*``)."""

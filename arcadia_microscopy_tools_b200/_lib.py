@@ -117,6 +117,14 @@ SIGNATURES: dict[str, tuple] = {
     "amt_dog2d": (_i, [_p, _i, _d, _p, _i64, _i64, _i64, _p, _i, _p, _i, _p, _p, _p, _p]),
     "amt_dog2d_axis0": (_i, [_p, _i, _d, _i64, _i64, _i64, _p, _i, _p, _i, _p, _p, _p]),
     "amt_dog2d_axis1": (_i, [_p, _p, _p, _i64, _i64, _i64, _p, _i, _p, _i, _p, _p]),
+    "amt_tcg_create": (_i, [_p, _i, _i, C.POINTER(_p)]),
+    "amt_tcg_destroy": (None, [_p]),
+    "amt_tcg_weights": (_i, [_p, _p, C.POINTER(_i)]),
+    "amt_tcg_supported": (_i, [_i64, _i64, _i]),
+    "amt_tcg_digit_bytes": (_sz, [_i64, _i64, _i64]),
+    "amt_tcg_axis0": (_i, [_p, _p, _i64, _i64, _i64, _p, _i, _i, _p]),
+    "amt_tcg_axis1": (_i, [_p, _p, _p, _d, _p, _i64, _i64, _i64, _p, _p, _i, _i, _p]),
+    "amt_gauss_lo2d": (_i, [_p, _d, _p, _i64, _i64, _i64, _p, _i, _i, _i, _p]),
     "amt_minmax_filter_axis": (_i, [_p, _i, _p, _p, _i64, _i64, _i64, _i, _i, _i, _p]),
     "amt_deinterleave_u16": (_i, [_p, _p, _i64, _i64, _i, _p]),
     "amt_sub_f64": (_i, [_p, _p, _p, _i64, _p]),

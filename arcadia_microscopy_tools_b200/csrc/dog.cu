@@ -182,7 +182,7 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
                  double* __restrict__ out_a, double* __restrict__ out_b, const int n, const int inner,
                  const double* __restrict__ hw_lo, const int r_lo, const double* __restrict__ hw_hi, const int r_hi,
                  const int nb, uint64_t* __restrict__ minmax, uint16_t* __restrict__ buckets, const int n_items,
-                 const int exact_every, const int exact_offset) {
+                 const int exact_every, const int exact_offset, const int plane_mul, const int plane_add) {
   constexpr int S = WARPS * R;  // rows per step
   constexpr int NT = WARPS * 32;
   constexpr int FRONT = RLO_MAX, BACK = R;
@@ -202,9 +202,10 @@ dog_strip_kernel(const InT* __restrict__ in, const double* __restrict__ in_lo, c
   // item = plane * (inner/32) + strip; one item per CTA unless the launch is persistent (round robin)
   const int strips = (inner + PV_TW - 1) / PV_TW;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-  const int plane_idx = item / strips;
+  const int plane_log = item / strips;
+  const int plane_idx = plane_log * plane_mul + plane_add;  // a launch may cover every plane_mul-th plane only
   const bool contract = FMA == 1 || (FMA == 2 && plane_idx % exact_every != exact_offset);  // CTA-uniform
-  const int x0 = (item - plane_idx * strips) * PV_TW;
+  const int x0 = (item - plane_log * strips) * PV_TW;
   const int64_t plane = (int64_t)plane_idx * n * inner;
   const InT* src = in + plane + x0;
   const int cols_valid = inner - x0 < PV_TW ? inner - x0 : PV_TW;  // a multiple of the load granule
@@ -447,6 +448,7 @@ static DogPlan dog_plan(int in_dtype, int64_t n_img, int64_t h, int64_t w, int r
 
 struct DogMix {
   int every, offset;  // every > 0: plane p is exact iff p % every == offset, the other planes are contracted
+  bool only;          // every > 0 and only: the launch covers the exact planes alone (the others belong to tcgauss.cu)
 };
 
 template <int R, int WARPS, int MIN_CTAS, typename InT, bool SECOND, int FMA>
@@ -455,13 +457,16 @@ static int launch_strip(const DogPlan& p, const InT* in, const double* in_lo, do
                         int r_hi, uint64_t* minmax, uint16_t* buckets, cudaStream_t st, DogMix mix) {
   auto kernel = dog_strip_kernel<R, WARPS, MIN_CTAS, InT, SECOND, FMA>;
   AMT_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  const bool subset = mix.only && mix.every > 0;
+  if (subset) planes /= mix.every;
   const int64_t items = planes * ((inner + PV_TW - 1) / PV_TW);
   // one CTA per strip by default (the hardware scheduler balances the tail better than a static
   // round robin); dog_persistent = 1 launches exactly the resident CTAs and lets them loop
   const int64_t resident = g_dog_persistent ? (int64_t)kNumSMs * p.ctas : items;
   dim3 grid((unsigned)(items < resident ? items : resident)), block(PV_TW, WARPS);
   kernel<<<grid, block, p.smem, st>>>(in, in_lo, scale, out_a, out_b, (int)n, (int)inner, hw_lo, r_lo, hw_hi, r_hi, p.nb,
-                                      minmax, buckets, (int)items, mix.every > 0 ? mix.every : 1, mix.offset);
+                                      minmax, buckets, (int)items, mix.every > 0 ? mix.every : 1, mix.offset,
+                                      subset ? mix.every : 1, subset ? mix.offset : 0);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
@@ -490,7 +495,7 @@ static int launch_variant(const DogPlan& p, const InT* in, const double* in_lo, 
   if (g_dog_fma)
     return launch_variant_fma<InT, SECOND, 1>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
                                               r_hi, minmax, buckets, st, mix);
-  if (mix.every > 0)
+  if (mix.every > 0 && !mix.only)
     return launch_variant_fma<InT, SECOND, 2>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
                                               r_hi, minmax, buckets, st, mix);
   return launch_variant_fma<InT, SECOND, 0>(p, in, in_lo, scale, out_a, out_b, planes, n, inner, hw_lo, r_lo, hw_hi,
@@ -519,22 +524,29 @@ static int dog_axis1(const DogPlan& p, const double* tmp_lo, const double* tmp_h
                                       minmax, buckets, st, mix);
 }
 
+// true iff dog2d would take the strip kernels for this problem (pointer alignment aside)
+bool dog2d_fast(int in_dtype, int64_t n_img, int64_t h, int64_t w, int r_lo, int r_hi) {
+  return dog_plan(in_dtype, n_img, h, w, r_lo, r_hi).fast;
+}
+
 // buckets (optional): n_img*h*w uint16 receiving bucket12() of every output sample; *buckets_written
 // tells the caller whether the strip kernels ran (the generic fallback does not produce them).
 int dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,
           const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, double* tmp_lo, double* tmp_hi,
           uint64_t* minmax, cudaStream_t st, uint16_t* buckets, bool* buckets_written, int exact_every,
-          int exact_offset) {
+          int exact_offset, bool only_exact) {
   if (buckets_written) *buckets_written = false;
   if (exact_every < 0 || (exact_every > 0 && (exact_offset < 0 || exact_offset >= exact_every))) return AMT_ERR_INVALID;
-  const DogMix mix{exact_every, exact_offset};
+  if (only_exact && (exact_every <= 0 || n_img % exact_every != 0)) return AMT_ERR_INVALID;
+  const DogMix mix{exact_every, exact_offset, only_exact};
   if (!in || !out || !tmp_lo || !tmp_hi || !hw_lo || !hw_hi) return AMT_ERR_INVALID;
   if (n_img <= 0 || h <= 0 || w <= 0 || r_lo < 0 || r_hi < 0) return AMT_ERR_INVALID;
   if (in_dtype != AMT_U16 && in_dtype != AMT_F64) return AMT_ERR_UNSUPPORTED;
-  if (minmax) AMT_TRY(minmax_init(minmax, n_img, st));
+  if (minmax && !only_exact) AMT_TRY(minmax_init(minmax, n_img, st));  // a subset launch leaves the others' keys alone
   DogPlan p = dog_plan(in_dtype, n_img, h, w, r_lo, r_hi);
   // the strip kernels use 16-byte accesses; odd pointers take the generic tile kernels for BOTH passes
   p.fast = p.fast && aligned16(in) && aligned16(out) && aligned16(tmp_lo) && aligned16(tmp_hi);
+  if (only_exact && !p.fast) return AMT_ERR_UNSUPPORTED;  // the generic tile kernels have no plane subset
   if (buckets && !(p.fast && aligned16(buckets))) buckets = nullptr;
   if (buckets_written) *buckets_written = buckets != nullptr;
   AMT_TRY(dog_axis0(p, in, in_dtype, in_scale, n_img, h, w, hw_lo, r_lo, hw_hi, r_hi, tmp_lo, tmp_hi, st, mix));
@@ -591,7 +603,7 @@ int amt_dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_
               uint64_t* minmax_keys, amt_stream_t stream) {
   return amt::dog2d(in, in_dtype, in_scale, out, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, tmp_lo, tmp_hi,
                     minmax_keys, amt::as_stream(stream), nullptr, nullptr, amt::g_dog_exact_every,
-                    amt::g_dog_exact_every > 0 ? amt::g_dog_exact_offset % amt::g_dog_exact_every : 0);
+                    amt::g_dog_exact_every > 0 ? amt::g_dog_exact_offset % amt::g_dog_exact_every : 0, false);
 }
 
 // The two passes separately (bench / profiling).  The layout of tmp_lo / tmp_hi between them is
@@ -605,7 +617,7 @@ int amt_dog2d_axis0(const void* in, int in_dtype, double in_scale, int64_t n_img
   const DogPlan p = dog_plan(in_dtype, n_img, h, w, r_lo, r_hi);
   if (p.fast && !(aligned16(in) && aligned16(tmp_lo) && aligned16(tmp_hi))) return AMT_ERR_INVALID;
   return dog_axis0(p, in, in_dtype, in_scale, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, tmp_lo, tmp_hi,
-                   as_stream(stream), DogMix{g_dog_exact_every, g_dog_exact_every > 0 ? g_dog_exact_offset % g_dog_exact_every : 0});
+                   as_stream(stream), DogMix{g_dog_exact_every, g_dog_exact_every > 0 ? g_dog_exact_offset % g_dog_exact_every : 0, false});
 }
 
 int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int64_t n_img, int64_t h, int64_t w,
@@ -617,7 +629,7 @@ int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int
   if (p.fast && !(aligned16(out) && aligned16(tmp_lo) && aligned16(tmp_hi))) return AMT_ERR_INVALID;
   if (minmax_keys) AMT_TRY(minmax_init(minmax_keys, n_img, as_stream(stream)));
   return dog_axis1(p, tmp_lo, tmp_hi, out, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, minmax_keys, nullptr,
-                   as_stream(stream), DogMix{g_dog_exact_every, g_dog_exact_every > 0 ? g_dog_exact_offset % g_dog_exact_every : 0});
+                   as_stream(stream), DogMix{g_dog_exact_every, g_dog_exact_every > 0 ? g_dog_exact_offset % g_dog_exact_every : 0, false});
 }
 
 }  // extern "C"

@@ -10,7 +10,9 @@ int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st);
 int dog2d(const void* in, int in_dtype, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,
           const double* hw_lo, int r_lo, const double* hw_hi, int r_hi, double* tmp_lo, double* tmp_hi,
           uint64_t* minmax, cudaStream_t st, uint16_t* buckets = nullptr, bool* buckets_written = nullptr,
-          int exact_every = 0, int exact_offset = 0);  // exact_every > 0: only planes p % every == offset keep scipy's order
+          int exact_every = 0, int exact_offset = 0,  // exact_every > 0: only planes p % every == offset keep scipy's order
+          bool only_exact = false);                   // ... and only those planes are computed at all (tcgauss.cu has the rest)
+bool dog2d_fast(int in_dtype, int64_t n_img, int64_t h, int64_t w, int r_lo, int r_hi);
 
 // order statistics of float64 planes whose bucket12() values were written next to them by dog2d
 int select_f64_bucketed(const double* data, const uint16_t* buckets, int64_t n_img, int64_t n, const int64_t* ranks_host,
@@ -42,7 +44,25 @@ int region_finalize(const uint64_t* acc, const int32_t* counts, int n_channels, 
 
 }  // namespace amt
 
+struct amt_tcg;
 namespace amt {
+namespace tc {
+struct PlaneSel {
+  int every, skip;  // every > 0: planes p with p % every == skip are left out
+  __host__ __device__ int phys(int q) const {
+    if (every <= 0) return q;
+    const int grp = q / (every - 1), c = q - grp * (every - 1);
+    return grp * every + c + (c >= skip ? 1 : 0);
+  }
+};
+bool tcg_shape_ok(int64_t h, int64_t w);
+int tcg_axis0(const amt_tcg* g, const uint16_t* in, int64_t n_img, int64_t h, int64_t w, uint8_t* digits, PlaneSel sel,
+              cudaStream_t st);
+int tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double in_scale, double* out, int64_t n_img,
+              int64_t h, int64_t w, uint16_t* buckets, uint64_t* minmax, PlaneSel sel, cudaStream_t st);
+int lo2d(const uint16_t* in, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w, const double* hw_lo, int r_lo,
+         PlaneSel sel, cudaStream_t st);
+}  // namespace tc
 size_t region_shape_scratch_bytes(int64_t n_img, int64_t h, int64_t w, int64_t max_labels);
 int region_shape(const int32_t* labels, const uint64_t* acc, int n_channels, const int32_t* counts, int64_t n_img,
                  int64_t h, int64_t w, int64_t max_labels, double* table, void* scratch, size_t scratch_bytes,

@@ -100,6 +100,39 @@ int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int
                     const double* half_w_lo, int r_lo, const double* half_w_hi, int r_hi,
                     uint64_t* minmax_keys, amt_stream_t stream);
 
+/* ------------------------------------------------------------------ tensor-core Gaussian (tcgen05 + TMA)
+ * ref: operations.py:91 — the sigma_high Gaussian of difference_of_gaussians for planes nothing discrete is
+ * derived from (every channel except the thresholded one): a 1-D pass is a banded Toeplitz product on
+ * tcgen05.mma kind::i8 with the weights rounded to 32 significant bits (base-256 digits) and exact integer
+ * accumulation, operands staged by TMA (csrc/tcgauss.cu).  Results equal scipy's to ~1e-10 of the [0, 1]
+ * scale (the reference tolerance for filtered planes is 1e-5); they are NOT bit-identical, so the
+ * thresholded channel keeps amt_dog2d.
+ *
+ * amt_tcg_create: half_w_host = weights[c-j], j = 0..radius (radius <= 64, i.e. sigma <= 16 at truncate 4).
+ * amt_tcg_weights: the integer weights W[j] (host array of radius+1) and S with w[j] ~ W[j] * 2^-S,
+ *   sum_j W == 2^S exactly (test hook: lets a CPU checker restate the integer pipeline bit for bit).
+ * amt_tcg_supported: 1 if (h, w, radius) can take this path (h, w >= 128, w % 16 == 0).
+ * amt_tcg_axis0: uint16 planes -> `digits`, five uint8 planes per image ([n_img][5][h][w]) holding
+ *   round(sum_t W[t] * x[y+t] / 2^(S-24)) (40 bits), rows clamped at the edges (mode='nearest').
+ * amt_tcg_axis1: digits -> out = lo - G_hi (lo = the narrow Gaussian, may be NULL: out = G_hi), G_hi in
+ *   units of in_scale * input; optional bucket12 codes (uint16 per sample) and min / max keys.
+ * amt_gauss_lo2d: the narrow Gaussian (radius <= 4) of uint16 planes in float64, scipy's order (bit-identical).
+ * skip_every > 0: planes p with p % skip_every == skip_offset are left untouched (the executor's
+ *   segmentation channel); n_img must then be a multiple of skip_every. */
+typedef struct amt_tcg amt_tcg;
+int amt_tcg_create(const double* half_w_host, int radius, int device, amt_tcg** out);
+void amt_tcg_destroy(amt_tcg* g);
+int amt_tcg_weights(const amt_tcg* g, uint64_t* w_host, int* scale_bits);
+int amt_tcg_supported(int64_t h, int64_t w, int radius);
+size_t amt_tcg_digit_bytes(int64_t n_img, int64_t h, int64_t w);
+int amt_tcg_axis0(const amt_tcg* g, const uint16_t* in, int64_t n_img, int64_t h, int64_t w, uint8_t* digits,
+                  int skip_every, int skip_offset, amt_stream_t stream);
+int amt_tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double in_scale, double* out,
+                  int64_t n_img, int64_t h, int64_t w, uint16_t* buckets, uint64_t* minmax_keys,
+                  int skip_every, int skip_offset, amt_stream_t stream);
+int amt_gauss_lo2d(const uint16_t* in, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,
+                   const double* half_w_lo, int r_lo, int skip_every, int skip_offset, amt_stream_t stream);
+
 /* Tuning knobs (process-wide; set before launching work; bench / profiling only — defaults are
  * the shipped configuration).  Keys: "dog_variant" 0 = 8 warps x 8 outputs per thread,
  * 1 = 4 warps x 16, 2 = 8 warps x 16; "dog_solo" 1 = one DoG CTA per SM (leaves half of the SM
