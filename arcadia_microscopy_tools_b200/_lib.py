@@ -19,9 +19,13 @@ AMT_ERR_CUDA = -2
 AMT_ERR_CAPACITY = -3
 AMT_ERR_UNSUPPORTED = -4
 
-AMT_U8, AMT_U16, AMT_I32, AMT_F64 = 0, 1, 2, 3
+AMT_U8, AMT_U16, AMT_I32, AMT_F64, AMT_I64 = 0, 1, 2, 3, 4
 AMT_MAX_RANKS = 8
 AMT_EXTEND_NEAREST, AMT_EXTEND_REFLECT = 0, 1  # amt_gaussian_axis_mode
+AMT_FILTER_TENSOR_CORE, AMT_FILTER_FMA = 0, 1  # amt_fov_config.plane_filter
+# per-FOV status bits of the executor (include/amt_b200.h)
+AMT_FOV_THR_CAPACITY, AMT_FOV_GIVEN_CAPACITY, AMT_FOV_GIVEN_VALUE_RANGE = 1, 2, 4
+AMT_FOV_THR_EMPTY, AMT_FOV_GIVEN_EMPTY, AMT_FOV_CONSTANT_PLANE, AMT_FOV_GIVEN_NEGATIVE = 8, 16, 32, 64
 AMT_MAP_SUBCLIP, AMT_MAP_RESCALE, AMT_MAP_FILL = 1, 2, 4
 AMT_ACC_BASE, AMT_ACC_PER_CHANNEL = 10, 4
 AMT_TABLE_BASE, AMT_TABLE_PER_CHANNEL = 16, 5
@@ -92,6 +96,8 @@ class FovConfig(C.Structure):
         ("pct_hi", C.c_double),
         ("out_lo", C.c_double),
         ("out_hi", C.c_double),
+        ("plane_filter", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -159,9 +165,10 @@ SIGNATURES: dict[str, tuple] = {
     "amt_outline_trace_write": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "amt_executor_create": (_i, [C.POINTER(FovConfig), C.POINTER(_d), _i, C.POINTER(_d), _i, C.POINTER(_p)]),
     "amt_executor_destroy": (None, [_p]),
+    "amt_executor_uses_tensor_cores": (_i, [_p]),
     "amt_executor_device_bytes": (_sz, [_p]),
-    "amt_executor_run_device": (_i, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "amt_executor_run_host": (_i, [_p, _p, _p, _i64, _p, _p, _p, _p, _p]),
+    "amt_executor_run_device": (_i, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "amt_executor_run_host": (_i, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),
     "amt_executor_sync": (_i, [_p]),
     "amt_executor_last_ms": (C.c_float, [_p]),
 }

@@ -34,11 +34,17 @@ class FovPipelineConfig:
     max_label_value: int = 65535
     quantify_given_mask: bool = True
     with_shape: bool = False  # also perimeter / area_convex columns (not part of workload W)
-    given_label_dtype: type = np.int32  # host label masks of run_host: np.int32 or np.uint16 (Cellpose's dtype)
+    # host label masks of run_host: np.int64 (what the reference hands SegmentationMask, ref: model.py:215,
+    # masks.py:138; copied as int64 and narrowed on the device), np.int32, or np.uint16 (Cellpose's own dtype)
+    given_label_dtype: type = np.int32
     # False: only the segmentation channel (whose plane decides the labels) keeps scipy's exact operation order; the
-    # other channels, which yield float planes only, use fused multiply-adds (equal to scipy's to ~1e-15 relative).
-    # True: every preprocessed plane is bit-identical to the reference's (about 12 % slower device-resident).
+    # other channels, which yield float planes only, take `plane_filter`.
+    # True: every preprocessed plane is bit-identical to the reference's.
     exact_all_channels: bool = False
+    # "tensor_core": the sigma_high Gaussian of the non-thresholded channels runs as integer Toeplitz products on
+    # tcgen05 (planes equal to scipy's to ~1e-10 of the [0, 1] scale; falls back to "fma" for shapes it does not take);
+    # "fma": float64 with fused multiply-adds (~1e-15).
+    plane_filter: str = "tensor_core"
     low_sigma: float = 0.6
     high_sigma: float = 16.0
     bg_percentile: float = 0.0
@@ -58,6 +64,43 @@ def table_columns(channel_names: list[str]) -> list[str]:
     return cols
 
 
+class FovCapacityError(RuntimeError):
+    """A field of view exceeded a capacity of the executor; ``.fovs`` maps FOV index -> status bits."""
+
+    def __init__(self, message: str, fovs: dict[int, int]) -> None:
+        super().__init__(message)
+        self.fovs = fovs
+
+
+_FATAL = (_lib.AMT_FOV_THR_CAPACITY | _lib.AMT_FOV_GIVEN_CAPACITY | _lib.AMT_FOV_GIVEN_VALUE_RANGE |
+          _lib.AMT_FOV_GIVEN_NEGATIVE)
+
+
+def describe_status(bits: int) -> list[str]:
+    names = {_lib.AMT_FOV_THR_CAPACITY: "threshold mask has more cells than max_labels",
+             _lib.AMT_FOV_GIVEN_CAPACITY: "given mask has more cells than max_labels",
+             _lib.AMT_FOV_GIVEN_VALUE_RANGE: "given mask holds a value above max_label_value",
+             _lib.AMT_FOV_THR_EMPTY: "no cells remain in the threshold mask after removing edge cells",
+             _lib.AMT_FOV_GIVEN_EMPTY: "no cells remain in the given mask after removing edge cells",
+             _lib.AMT_FOV_CONSTANT_PLANE: "the thresholded plane is constant",
+             _lib.AMT_FOV_GIVEN_NEGATIVE: "given mask holds a negative value"}
+    return [text for bit, text in names.items() if bits & bit]
+
+
+def raise_for_status(status, config: "FovPipelineConfig") -> None:
+    """Raise ``FovCapacityError`` if any FOV of a finished batch dropped data (capacity / value-range bits).
+    'No cells remain' and 'constant plane' are results, not errors: the reference raises them per image
+    (ref: masks.py:57-60) and a plate run must survive them (ref: model.py:276-288); they stay in ``status``."""
+    status = np.asarray(status)
+    bad = {int(i): int(status[i]) for i in np.flatnonzero(status & _FATAL)}
+    if bad:
+        first = next(iter(bad))
+        raise FovCapacityError(
+            f"{len(bad)} field(s) of view exceeded the executor's capacity (max_labels={config.max_labels}, "
+            f"max_label_value={config.max_label_value}); first: FOV {first}: " + "; ".join(describe_status(bad[first])),
+            bad)
+
+
 class FovBatchExecutor:
     """Owns one native executor (streams, scratch, staging) on one GPU."""
 
@@ -71,8 +114,10 @@ class FovBatchExecutor:
             seg_channel=config.seg_channel, chunk_fovs=config.chunk_fovs, max_labels=config.max_labels,
             max_label_value=config.max_label_value, quantify_given_mask=1 if config.quantify_given_mask else 0,
             with_shape=1 if config.with_shape else 0,
-            given_label_dtype=_lib.AMT_U16 if np.dtype(config.given_label_dtype) == np.uint16 else _lib.AMT_I32,
+            given_label_dtype={np.dtype(np.uint16): _lib.AMT_U16, np.dtype(np.int32): _lib.AMT_I32,
+                               np.dtype(np.int64): _lib.AMT_I64}[np.dtype(config.given_label_dtype)],
             exact_all_channels=1 if config.exact_all_channels else 0,
+            plane_filter={"tensor_core": _lib.AMT_FILTER_TENSOR_CORE, "fma": _lib.AMT_FILTER_FMA}[config.plane_filter],
             low_sigma=config.low_sigma, high_sigma=config.high_sigma,
             bg_percentile=config.bg_percentile, pct_lo=config.percentile_range[0], pct_hi=config.percentile_range[1],
             out_lo=config.out_range[0], out_hi=config.out_range[1],
@@ -107,6 +152,11 @@ class FovBatchExecutor:
         self.close()
 
     @property
+    def uses_tensor_cores(self) -> bool:
+        """True when the non-thresholded channels' wide Gaussian runs on tcgen05 (``plane_filter`` resolved)."""
+        return bool(self._lib.amt_executor_uses_tensor_cores(self._handle))
+
+    @property
     def device_bytes(self) -> int:
         return int(self._lib.amt_executor_device_bytes(self._handle))
 
@@ -121,6 +171,7 @@ class FovBatchExecutor:
             "tables_given": torch.empty((n_fov, self.n_cols, c.max_labels), dtype=torch.float64, device=dev),
             "counts_given": torch.empty(n_fov, dtype=torch.int32, device=dev),
             "thresholds": torch.empty(n_fov, dtype=torch.float64, device=dev),
+            "status": torch.zeros(n_fov, dtype=torch.int32, device=dev),
             "labels_thr": None, "labels_given": None, "preprocessed": None,
         }
         if labels:
@@ -143,7 +194,8 @@ class FovBatchExecutor:
             self._lib.amt_executor_run_device(
                 self._handle, p(fovs), p(given_labels), n_fov, p(outputs["tables_thr"]), p(outputs["counts_thr"]),
                 p(outputs["tables_given"]), p(outputs["counts_given"]), p(outputs["thresholds"]),
-                p(outputs["labels_thr"]), p(outputs["labels_given"]), p(outputs["preprocessed"])),
+                p(outputs["labels_thr"]), p(outputs["labels_given"]), p(outputs["preprocessed"]),
+                p(outputs.get("status"))),
             "amt_executor_run_device",
         )
         if not sync:
@@ -151,11 +203,22 @@ class FovBatchExecutor:
         check(self._lib.amt_executor_sync(self._handle), "amt_executor_sync")
         return float(self._lib.amt_executor_last_ms(self._handle))
 
+    def check_status(self, outputs: dict) -> None:
+        """After a synchronised ``run_device``: raise ``FovCapacityError`` if a FOV dropped data (one small D2H)."""
+        if outputs.get("status") is not None:
+            raise_for_status(_gpu.to_host(outputs["status"]), self.config)
+
     # ------------------------------------------------------------------ host-fed batch
-    def run_host(self, fovs: np.ndarray, given_labels: np.ndarray | None, out: dict | None = None) -> dict:
+    def run_host(self, fovs: np.ndarray, given_labels: np.ndarray | None, out: dict | None = None,
+                 on_error: str = "raise") -> dict:
         """fovs: host (n_fov, C, H, W) uint16 (pinned memory overlaps copies with compute);
-        given_labels: host (n_fov, H, W) of ``config.given_label_dtype`` (int32 or uint16) or None.
-        Returns host arrays."""
+        given_labels: host (n_fov, H, W) of ``config.given_label_dtype`` (int64, int32 or uint16) or None.
+        Returns host arrays; ``out["status"][i]`` holds the ``AMT_FOV_*`` bits of FOV i.
+
+        A field of view that overflows a capacity (more cells than ``max_labels``, a label value above
+        ``max_label_value``, a negative label) never disturbs the others of the batch.  ``on_error="raise"``
+        (default) raises ``FovCapacityError`` naming those FOVs once the whole batch is back (the reference
+        never drops cells silently); ``on_error="status"`` leaves the decision to the caller."""
         c = self.config
         n_fov = fovs.shape[0]
         assert fovs.dtype == np.uint16 and fovs.flags.c_contiguous
@@ -170,9 +233,11 @@ class FovBatchExecutor:
         check(
             self._lib.amt_executor_run_host(
                 self._handle, vp(fovs), vp(given_labels), n_fov, vp(out["tables_thr"]), vp(out["counts_thr"]),
-                vp(out["tables_given"]), vp(out["counts_given"]), vp(out["thresholds"])),
+                vp(out["tables_given"]), vp(out["counts_given"]), vp(out["thresholds"]), vp(out.get("status"))),
             "amt_executor_run_host",
         )
+        if on_error == "raise" and out.get("status") is not None:
+            raise_for_status(out["status"], c)
         return out
 
     def alloc_host_outputs(self, n_fov: int, pinned: bool = True) -> dict:
@@ -189,6 +254,7 @@ class FovBatchExecutor:
             "tables_given": host((n_fov, self.n_cols, c.max_labels), torch.float64),
             "counts_given": host((n_fov,), torch.int32),
             "thresholds": host((n_fov,), torch.float64),
+            "status": host((n_fov,), torch.int32),
         }
 
     # ------------------------------------------------------------------ table -> dict
@@ -196,6 +262,8 @@ class FovBatchExecutor:
         """One FOV's (cols, max_labels) table -> ``cell_properties``-style dict of columns."""
         cols = table_columns(channel_names)
         out: dict[str, np.ndarray] = {}
+        if count > table.shape[1]:
+            raise FovCapacityError(f"{count} cells but the table holds {table.shape[1]} (max_labels)", {})
         for i, name in enumerate(cols):
             col = np.ascontiguousarray(table[i, :count])
             if name == "label" or name.startswith("bbox-"):

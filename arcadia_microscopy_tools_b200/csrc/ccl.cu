@@ -543,14 +543,18 @@ ccl_final_kernel(int32_t* __restrict__ L, const int32_t* __restrict__ gid, const
 __global__ void __launch_bounds__(256)
 relabel_final_kernel(const int32_t* __restrict__ in, const int64_t in_stride, int32_t* __restrict__ L,
                      const int32_t* __restrict__ aux, const int64_t npx, const int32_t* __restrict__ rank,
-                     const int64_t nval, const int use_ccl, const int vec) {
+                     const int64_t nval, const int use_ccl, const int vec, int32_t* __restrict__ value_overflow) {
   const int64_t img = blockIdx.y;
   const int32_t* lab = in + img * in_stride;
   int32_t* Lp = L + img * npx;
   const int32_t* ap = aux + img * npx;
   const int32_t* rk = rank + img * nval;
   auto one = [&](int v, int root) -> int {
-    if (v <= 0 || v >= nval) return 0;
+    if (v >= nval) {  // outside the declared range: background here, reported to the caller
+      if (value_overflow != nullptr) value_overflow[img] = 1;
+      return 0;
+    }
+    if (v <= 0) return 0;
     if (use_ccl && __ldg(ap + root) == -1) return 0;
     return __ldg(rk + v);
   };
@@ -670,7 +674,7 @@ static int ccl_core(const void* in, int64_t in_stride, const double* thresholds,
 
 int label_launch(const void* in, int in_kind, int64_t in_stride, const double* thresholds, int64_t max_value,
                  int64_t n_img, int64_t h, int64_t w, int clear_border, int32_t* labels_out, int32_t* counts,
-                 void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                 void* scratch, size_t scratch_bytes, cudaStream_t st, int32_t* value_overflow) {
   if (!in || !labels_out || !counts || !scratch) return AMT_ERR_INVALID;
   if (n_img <= 0 || h <= 0 || w <= 0 || in_kind < 0 || in_kind > 2 || max_value < 0) return AMT_ERR_INVALID;
   if (in_kind == 1 && !thresholds) return AMT_ERR_INVALID;
@@ -706,7 +710,8 @@ int label_launch(const void* in, int in_kind, int64_t in_stride, const double* t
     scan_kernel<<<(unsigned)n_img, 1024, 0, st>>>(s.present, (int)nval, counts, 1);
     AMT_LAUNCH_CHECK();
     relabel_final_kernel<<<sgrid, 256, 0, st>>>((const int32_t*)in, in_stride, labels_out, s.gid, npx, s.present, nval,
-                                                clear_border, vec && (in_stride % 4 == 0) && (((uintptr_t)in) % 16 == 0));
+                                                clear_border, vec && (in_stride % 4 == 0) && (((uintptr_t)in) % 16 == 0),
+                                                value_overflow);
     AMT_LAUNCH_CHECK();
     return AMT_OK;
   }
@@ -739,7 +744,7 @@ int amt_label(const void* in, int in_kind, const double* thresholds, int64_t max
               int64_t w, int clear_border, int32_t* labels_out, int32_t* counts, void* scratch, size_t scratch_bytes,
               amt_stream_t stream) {
   return amt::label_launch(in, in_kind, h * w, thresholds, max_value, n_img, h, w, clear_border, labels_out, counts,
-                           scratch, scratch_bytes, amt::as_stream(stream));
+                           scratch, scratch_bytes, amt::as_stream(stream), nullptr);
 }
 
 }  // extern "C"

@@ -405,6 +405,8 @@ extern int g_stream_pad_kb;   // gauss.cu
 extern int g_exec_swap_prio;  // executor.cu
 extern int g_pass_ctas;       // core.cu
 extern int g_exec_buckets;    // executor.cu
+extern int g_exec_tc;         // executor.cu
+namespace tc { extern int g_tcg_debug; }  // tcgauss.cu
 
 constexpr size_t kSmemMax = 227 * 1024;
 constexpr size_t kSmemPerSM = 228 * 1024;
@@ -577,6 +579,10 @@ int amt_tune(const char* key, int value) {
     g_stream_ctas = value;
   } else if (is("exec_buckets")) {
     g_exec_buckets = value != 0;
+  } else if (is("tcg_debug")) {
+    tc::g_tcg_debug = value;
+  } else if (is("exec_tc")) {
+    g_exec_tc = value != 0;
   } else if (is("pass_ctas")) {
     if (value < 1 || value > 16) return AMT_ERR_INVALID;
     g_pass_ctas = value;

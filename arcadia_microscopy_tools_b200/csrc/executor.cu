@@ -37,6 +37,8 @@ struct amt_executor {
   double *hw_lo, *hw_hi;
   double *tmp_lo, *tmp_hi, *dog[2], *pre;
   uint64_t* mm[2];
+  amt_tcg* tcg;              // tensor-core Gaussian of the planes that are not thresholded (null: float64 everywhere)
+  uint8_t* digits;           // its 40-bit intermediate, five uint8 planes per image
   uint16_t* buckets[2];      // bucket12() of the DoG planes (written by the DoG's second pass)
   bool buckets_valid[2];
   double* stats;
@@ -55,6 +57,10 @@ struct amt_executor {
   uint16_t* in_slot[2];
   int32_t* given_slot[2];
   uint16_t* given16_slot[2];  // raw uint16 label masks (given_label_dtype == AMT_U16), widened on the device
+  int64_t* given64_slot[2];   // raw int64 label masks (given_label_dtype == AMT_I64), narrowed on the device
+  int32_t* flag_slot[2];      // per FOV of a chunk: [0, chunk) value > max_label_value seen, [chunk, 2 chunk) negative value seen
+  int32_t* status_slot[2];
+  int32_t* flags_dev;         // the same two flag arrays for the device-resident entry point
   double *tab_thr_slot[2], *tab_given_slot[2], *thr_slot[2];
   int32_t *cnt_thr_slot[2], *cnt_given_slot[2];
   bool host_slots;
@@ -75,6 +81,9 @@ int g_exec_swap_prio = 1;
 // amt_tune "exec_buckets": 1 (default) = the DoG's second pass also writes bucket12() of its output and the
 // percentile selection reads those 2-byte buckets instead of the 8-byte planes; 0 = plain amt_select_f64
 int g_exec_buckets = 1;
+// amt_tune "exec_tc": 0 switches the tensor-core path off in executors that have one (A/B timing in one process)
+int g_exec_tc = 1;
+int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st);  // gauss.cu
 
 static int dmalloc(amt_executor* ex, void** p, size_t bytes) {
   AMT_CUDA_TRY(cudaMalloc(p, bytes));
@@ -124,6 +133,25 @@ static int enqueue_dog(amt_executor* ex, const uint16_t* in, int g, cudaEvent_t 
   if (wait_input) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, wait_input, 0));
   if (ex->chunks_issued >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, ex->ev_dog_free[slot], 0));
   trace_mark(ex, ex->s_dog, "dog: begin");
+  if (ex->tcg != nullptr && g_exec_tc) {
+    // the thresholded channel: float64 in scipy's order (strip kernels over every C-th plane); the others: narrow
+    // Gaussian in float64 (into tmp_lo, whose planes of these channels the strip kernels do not touch), wide Gaussian
+    // on the tensor cores.  All three write disjoint planes of dog / buckets / mm.
+    const tc::PlaneSel sel{c.n_channels, c.seg_channel};
+    uint16_t* bk = g_exec_buckets ? ex->buckets[slot] : nullptr;
+    AMT_TRY(minmax_init(ex->mm[slot], planes, ex->s_dog));
+    AMT_TRY(dog2d(in, AMT_U16, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, ex->hw_lo, ex->r_lo, ex->hw_hi,
+                  ex->r_hi, ex->tmp_lo, ex->tmp_hi, ex->mm[slot], ex->s_dog, bk, &ex->buckets_valid[slot], c.n_channels,
+                  c.seg_channel, true));
+    trace_mark(ex, ex->s_dog, "dog: exact planes done");
+    AMT_TRY(tc::lo2d(in, 1.0 / 65535.0, ex->tmp_lo, planes, c.height, c.width, ex->hw_lo, ex->r_lo, sel, ex->s_dog));
+    AMT_TRY(tc::tcg_axis0(ex->tcg, in, planes, c.height, c.width, ex->digits, sel, ex->s_dog));
+    AMT_TRY(tc::tcg_axis1(ex->tcg, ex->digits, ex->tmp_lo, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, bk,
+                          ex->mm[slot], sel, ex->s_dog));
+    AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_done[slot], ex->s_dog));
+    trace_mark(ex, ex->s_dog, "dog: end");
+    return AMT_OK;
+  }
   AMT_TRY(dog2d(in, AMT_U16, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, ex->hw_lo, ex->r_lo, ex->hw_hi,
                 ex->r_hi, ex->tmp_lo, ex->tmp_hi, ex->mm[slot], ex->s_dog, g_exec_buckets ? ex->buckets[slot] : nullptr,
                 &ex->buckets_valid[slot],
@@ -135,10 +163,30 @@ static int enqueue_dog(amt_executor* ex, const uint16_t* in, int g, cudaEvent_t 
   return AMT_OK;
 }
 
+__global__ void fov_status_kernel(const int32_t* __restrict__ cnt_thr, const int32_t* __restrict__ cnt_given,
+                                  const int32_t* __restrict__ value_overflow, const int32_t* __restrict__ negative,
+                                  const amt_map_params* __restrict__ params, int n_channels, int seg_channel, int max_labels,
+                                  int n_fov, int32_t* __restrict__ status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_fov) return;
+  int s = 0;
+  if (cnt_thr[i] > max_labels) s |= AMT_FOV_THR_CAPACITY;
+  if (cnt_thr[i] == 0) s |= AMT_FOV_THR_EMPTY;
+  const amt_map_params& p = params[(int64_t)i * n_channels + seg_channel];
+  if (p.hist_first == p.hist_last) s |= AMT_FOV_CONSTANT_PLANE;
+  if (cnt_given != nullptr) {
+    if (cnt_given[i] > max_labels) s |= AMT_FOV_GIVEN_CAPACITY;
+    if (cnt_given[i] == 0) s |= AMT_FOV_GIVEN_EMPTY;
+    if (value_overflow[i]) s |= AMT_FOV_GIVEN_VALUE_RANGE;
+    if (negative[i]) s |= AMT_FOV_GIVEN_NEGATIVE;
+  }
+  status[i] = s;
+}
+
 // everything after the DoG, on s_compute
 static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* given, int g, double* tab_thr,
                          int32_t* cnt_thr, double* tab_given, int32_t* cnt_given, double* thr_out, int32_t* lab_thr_out,
-                         int32_t* lab_given_out, double* pre_out) {
+                         int32_t* lab_given_out, double* pre_out, int32_t* flags, int32_t* status) {
   const amt_fov_config& c = ex->cfg;
   const int C = c.n_channels;
   const int64_t H = c.height, W = c.width, HW = H * W;
@@ -179,7 +227,7 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
   trace_mark(ex, st, "  rest: regions(thr) done");
   if (c.quantify_given_mask && given) {
     AMT_TRY(label_launch(given, 2, HW, nullptr, c.max_label_value, g, H, W, 1, lab_given, cnt_given, ex->label_scratch,
-                         ex->label_bytes, st));
+                         ex->label_bytes, st, flags));
     trace_mark(ex, st, "  rest: label(given) done");
     AMT_TRY(region_reduce(lab_given, in, C, (int64_t)C * HW, HW, g, H, W, c.max_labels, ex->acc, st));
     AMT_TRY(region_finalize(ex->acc, cnt_given, C, g, c.max_labels, tab_given, st));
@@ -187,9 +235,32 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
       AMT_TRY(region_shape(lab_given, ex->acc, C, cnt_given, g, H, W, c.max_labels, tab_given, ex->shape_scratch,
                            ex->shape_bytes, st));
   }
+  if (status != nullptr) {
+    const bool with_given = c.quantify_given_mask && given;
+    fov_status_kernel<<<(unsigned)ceil_div(g, 128), 128, 0, st>>>(cnt_thr, with_given ? cnt_given : nullptr, flags,
+                                                                   flags + c.chunk_fovs, ex->params, C, c.seg_channel,
+                                                                   c.max_labels, g, status);
+    AMT_LAUNCH_CHECK();
+  }
   trace_mark(ex, st, "  rest: end");
   ex->chunks_issued += 1;
   return AMT_OK;
+}
+
+// int64 host masks (the reference's dtype): values beyond int32 saturate (and are then reported as out of range by
+// the labelling pass), negative values become background and raise the FOV's flag
+__global__ void narrow_i64_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n_per_fov, int64_t n_fov,
+                                  int32_t* __restrict__ negative) {
+  const int64_t n2 = n_per_fov / 2;  // pairs per FOV (n_per_fov is even)
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2 * n_fov; i += step) {
+    const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(in) + i);
+    int2 r;
+    r.x = v.x > 2147483647ll ? 2147483647 : (v.x < 0 ? 0 : (int)v.x);
+    r.y = v.y > 2147483647ll ? 2147483647 : (v.y < 0 ? 0 : (int)v.y);
+    if ((v.x | v.y) < 0) negative[i / n2] = 1;
+    reinterpret_cast<int2*>(out)[i] = r;
+  }
 }
 
 __global__ void widen_u16_kernel(const uint16_t* __restrict__ in, int32_t* __restrict__ out, int64_t n8) {
@@ -216,6 +287,10 @@ static int alloc_host_slots(amt_executor* ex) {
     AMT_TRY(dmalloc(ex, (void**)&ex->given_slot[s], (size_t)c.chunk_fovs * HW * sizeof(int32_t)));
     if (c.given_label_dtype == AMT_U16)
       AMT_TRY(dmalloc(ex, (void**)&ex->given16_slot[s], (size_t)c.chunk_fovs * HW * sizeof(uint16_t)));
+    if (c.given_label_dtype == AMT_I64)
+      AMT_TRY(dmalloc(ex, (void**)&ex->given64_slot[s], (size_t)c.chunk_fovs * HW * sizeof(int64_t)));
+    AMT_TRY(dmalloc(ex, (void**)&ex->flag_slot[s], (size_t)2 * c.chunk_fovs * sizeof(int32_t)));
+    AMT_TRY(dmalloc(ex, (void**)&ex->status_slot[s], (size_t)c.chunk_fovs * sizeof(int32_t)));
     AMT_TRY(dmalloc(ex, (void**)&ex->tab_thr_slot[s], tab));
     AMT_TRY(dmalloc(ex, (void**)&ex->tab_given_slot[s], tab));
     AMT_TRY(dmalloc(ex, (void**)&ex->thr_slot[s], (size_t)c.chunk_fovs * sizeof(double)));
@@ -237,7 +312,8 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
   if (cfg->n_channels < 1 || cfg->n_channels > 8 || cfg->height < 1 || cfg->width < 1 || cfg->chunk_fovs < 1 ||
       cfg->max_labels < 1 || cfg->seg_channel < 0 || cfg->seg_channel >= cfg->n_channels || cfg->max_label_value < 0)
     return AMT_ERR_INVALID;
-  if (cfg->given_label_dtype != 0 && cfg->given_label_dtype != AMT_I32 && cfg->given_label_dtype != AMT_U16)
+  if (cfg->given_label_dtype != 0 && cfg->given_label_dtype != AMT_I32 && cfg->given_label_dtype != AMT_U16 &&
+      cfg->given_label_dtype != AMT_I64)
     return AMT_ERR_INVALID;
   if (cfg->given_label_dtype == AMT_U16 && cfg->max_label_value > 65535) return AMT_ERR_INVALID;
   if (!(cfg->bg_percentile >= 0 && cfg->bg_percentile <= 100) ||
@@ -305,6 +381,16 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
     EX_TRY(dmalloc(ex, (void**)&ex->mm[s], (size_t)planes * 2 * sizeof(uint64_t)));
     EX_TRY(dmalloc(ex, (void**)&ex->buckets[s], (size_t)planes * HW * sizeof(uint16_t)));
   }
+  if (!cfg->exact_all_channels && cfg->plane_filter == AMT_FILTER_TENSOR_CORE && C >= 2 &&
+      amt_tcg_supported(cfg->height, cfg->width, r_hi) && cfg->height % 2 == 0 &&
+      dog2d_fast(AMT_U16, planes, cfg->height, cfg->width, r_lo, r_hi) && r_lo <= 4) {
+    const int ts = amt_tcg_create(half_w_hi_host, r_hi, cfg->device, &ex->tcg);
+    if (ts == AMT_OK) {
+      EX_TRY(dmalloc(ex, (void**)&ex->digits, amt_tcg_digit_bytes(planes, cfg->height, cfg->width)));
+    } else if (ts != AMT_ERR_UNSUPPORTED) {
+      return fail(ts);
+    }
+  }
   EX_TRY(dmalloc(ex, (void**)&ex->pre, plane_f64));
   EX_TRY(dmalloc(ex, (void**)&ex->stats, (size_t)planes * 6 * sizeof(double)));
   EX_TRY(dmalloc(ex, (void**)&ex->params, (size_t)planes * sizeof(amt_map_params)));
@@ -312,6 +398,7 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
   EX_TRY(dmalloc(ex, &ex->sel_scratch, ex->sel_bytes));
   EX_TRY(dmalloc(ex, (void**)&ex->hist256, (size_t)cfg->chunk_fovs * 256 * sizeof(uint32_t)));
   EX_TRY(dmalloc(ex, (void**)&ex->thr, (size_t)cfg->chunk_fovs * sizeof(double)));
+  EX_TRY(dmalloc(ex, (void**)&ex->flags_dev, (size_t)2 * cfg->chunk_fovs * sizeof(int32_t)));
   EX_TRY(dmalloc(ex, (void**)&ex->lab_thr, (size_t)cfg->chunk_fovs * HW * sizeof(int32_t)));
   EX_TRY(dmalloc(ex, (void**)&ex->lab_given, (size_t)cfg->chunk_fovs * HW * sizeof(int32_t)));
   ex->label_bytes = amt_label_scratch_bytes(cfg->chunk_fovs, cfg->height, cfg->width, cfg->max_label_value);
@@ -332,7 +419,8 @@ void amt_executor_destroy(amt_executor* ex) {
   if (!ex) return;
   cudaSetDevice(ex->cfg.device);
   cudaDeviceSynchronize();
-  void* bufs[] = {ex->hw_lo, ex->hw_hi, ex->tmp_lo, ex->tmp_hi, ex->dog[0], ex->dog[1], ex->pre, ex->mm[0], ex->mm[1],
+  if (ex->tcg) amt_tcg_destroy(ex->tcg);
+  void* bufs[] = {ex->flags_dev, ex->digits, ex->hw_lo, ex->hw_hi, ex->tmp_lo, ex->tmp_hi, ex->dog[0], ex->dog[1], ex->pre, ex->mm[0], ex->mm[1],
                   ex->buckets[0], ex->buckets[1],
                   ex->stats, ex->params,
                   ex->sel_scratch, ex->hist256, ex->thr, ex->lab_thr, ex->lab_given, ex->label_scratch, ex->acc,
@@ -340,7 +428,7 @@ void amt_executor_destroy(amt_executor* ex) {
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (int s = 0; s < 2; ++s) {
-    void* sb[] = {ex->in_slot[s], ex->given_slot[s], ex->given16_slot[s], ex->tab_thr_slot[s], ex->tab_given_slot[s], ex->thr_slot[s],
+    void* sb[] = {ex->given64_slot[s], ex->flag_slot[s], ex->status_slot[s], ex->in_slot[s], ex->given_slot[s], ex->given16_slot[s], ex->tab_thr_slot[s], ex->tab_given_slot[s], ex->thr_slot[s],
                   ex->cnt_thr_slot[s], ex->cnt_given_slot[s]};
     for (void* b : sb)
       if (b) cudaFree(b);
@@ -362,10 +450,12 @@ void amt_executor_destroy(amt_executor* ex) {
 }
 
 size_t amt_executor_device_bytes(const amt_executor* ex) { return ex ? ex->device_bytes : 0; }
+int amt_executor_uses_tensor_cores(const amt_executor* ex) { return ex && ex->tcg != nullptr ? 1 : 0; }
 
 int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_t* given_labels, int64_t n_fov,
                             double* tables_thr, int32_t* counts_thr, double* tables_given, int32_t* counts_given,
-                            double* thresholds, int32_t* labels_thr, int32_t* labels_given, double* preprocessed) {
+                            double* thresholds, int32_t* labels_thr, int32_t* labels_given, double* preprocessed,
+                            int32_t* status) {
   using namespace amt;
   if (!ex || !fovs || !tables_thr || !counts_thr || n_fov <= 0) return AMT_ERR_INVALID;
   const amt_fov_config& c = ex->cfg;
@@ -379,11 +469,13 @@ int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_
   for (int64_t f0 = 0; f0 < n_fov; f0 += c.chunk_fovs) {
     const int g = (int)((n_fov - f0 < c.chunk_fovs) ? n_fov - f0 : c.chunk_fovs);
     AMT_TRY(enqueue_dog(ex, fovs + f0 * C * HW, g, nullptr));
+    AMT_CUDA_TRY(cudaMemsetAsync(ex->flags_dev, 0, (size_t)2 * c.chunk_fovs * sizeof(int32_t), ex->s_compute));
     AMT_TRY(process_chunk(ex, fovs + f0 * C * HW, given_labels ? given_labels + f0 * HW : nullptr, g,
                           tables_thr + f0 * tab, counts_thr + f0, tables_given ? tables_given + f0 * tab : nullptr,
                           counts_given ? counts_given + f0 : nullptr, thresholds ? thresholds + f0 : nullptr,
                           labels_thr ? labels_thr + f0 * HW : nullptr, labels_given ? labels_given + f0 * HW : nullptr,
-                          preprocessed ? preprocessed + f0 * C * HW : nullptr));
+                          preprocessed ? preprocessed + f0 * C * HW : nullptr, ex->flags_dev,
+                          status ? status + f0 : nullptr));
   }
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_stop, ex->s_compute));
   trace_dump(ex);
@@ -392,14 +484,16 @@ int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_
 
 int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const void* given_labels_host, int64_t n_fov,
                           double* tables_thr_host, int32_t* counts_thr_host, double* tables_given_host,
-                          int32_t* counts_given_host, double* thresholds_host) {
+                          int32_t* counts_given_host, double* thresholds_host, int32_t* status_host) {
   using namespace amt;
   if (!ex || !fovs_host || !tables_thr_host || !counts_thr_host || n_fov <= 0) return AMT_ERR_INVALID;
   const amt_fov_config& c = ex->cfg;
   const bool given = c.quantify_given_mask && given_labels_host;
   const bool u16_labels = c.given_label_dtype == AMT_U16;
+  const bool i64_labels = c.given_label_dtype == AMT_I64;
   if (given && (!tables_given_host || !counts_given_host)) return AMT_ERR_INVALID;
   if (u16_labels && ((int64_t)c.height * c.width) % 8 != 0) return AMT_ERR_UNSUPPORTED;
+  if (i64_labels && ((int64_t)c.height * c.width) % 2 != 0) return AMT_ERR_UNSUPPORTED;
   AMT_CUDA_TRY(cudaSetDevice(c.device));
   AMT_TRY(alloc_host_slots(ex));
   const int C = c.n_channels;
@@ -415,7 +509,14 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const voi
     if (chunk >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_in, ex->ev_done[s], 0));
     AMT_CUDA_TRY(cudaMemcpyAsync(ex->in_slot[s], fovs_host + f0 * C * HW, (size_t)g * C * HW * sizeof(uint16_t),
                                  cudaMemcpyHostToDevice, ex->s_in));
-    if (given && u16_labels) {
+    AMT_CUDA_TRY(cudaMemsetAsync(ex->flag_slot[s], 0, (size_t)2 * c.chunk_fovs * sizeof(int32_t), ex->s_in));
+    if (given && i64_labels) {
+      AMT_CUDA_TRY(cudaMemcpyAsync(ex->given64_slot[s], (const int64_t*)given_labels_host + f0 * HW,
+                                   (size_t)g * HW * sizeof(int64_t), cudaMemcpyHostToDevice, ex->s_in));
+      narrow_i64_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given64_slot[s], ex->given_slot[s], HW, g,
+                                                           ex->flag_slot[s] + c.chunk_fovs);
+      AMT_LAUNCH_CHECK();
+    } else if (given && u16_labels) {
       AMT_CUDA_TRY(cudaMemcpyAsync(ex->given16_slot[s], (const uint16_t*)given_labels_host + f0 * HW,
                                    (size_t)g * HW * sizeof(uint16_t), cudaMemcpyHostToDevice, ex->s_in));
       widen_u16_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given16_slot[s], ex->given_slot[s], (int64_t)g * HW / 8);
@@ -431,7 +532,7 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const voi
     AMT_TRY(enqueue_dog(ex, ex->in_slot[s], g, ex->ev_in[s]));
     AMT_TRY(process_chunk(ex, ex->in_slot[s], given ? ex->given_slot[s] : nullptr, g, ex->tab_thr_slot[s],
                           ex->cnt_thr_slot[s], ex->tab_given_slot[s], ex->cnt_given_slot[s], ex->thr_slot[s], nullptr,
-                          nullptr, nullptr));
+                          nullptr, nullptr, ex->flag_slot[s], ex->status_slot[s]));
     AMT_CUDA_TRY(cudaEventRecord(ex->ev_done[s], ex->s_compute));
     AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_out, ex->ev_done[s], 0));
     AMT_CUDA_TRY(cudaMemcpyAsync(tables_thr_host + f0 * tab, ex->tab_thr_slot[s], (size_t)g * tab * sizeof(double),
@@ -446,6 +547,9 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const voi
     }
     if (thresholds_host)
       AMT_CUDA_TRY(cudaMemcpyAsync(thresholds_host + f0, ex->thr_slot[s], (size_t)g * sizeof(double),
+                                   cudaMemcpyDeviceToHost, ex->s_out));
+    if (status_host)
+      AMT_CUDA_TRY(cudaMemcpyAsync(status_host + f0, ex->status_slot[s], (size_t)g * sizeof(int32_t),
                                    cudaMemcpyDeviceToHost, ex->s_out));
     AMT_CUDA_TRY(cudaEventRecord(ex->ev_out[s], ex->s_out));
   }

@@ -35,7 +35,8 @@ int otsu_launch(const uint32_t* hist, int mode, const amt_map_params* params, in
 // in_stride: elements between consecutive input images
 int label_launch(const void* in, int in_kind, int64_t in_stride, const double* thresholds, int64_t max_value,
                  int64_t n_img, int64_t h, int64_t w, int clear_border, int32_t* labels_out, int32_t* counts,
-                 void* scratch, size_t scratch_bytes, cudaStream_t st);
+                 void* scratch, size_t scratch_bytes, cudaStream_t st,
+                 int32_t* value_overflow = nullptr);  // integer masks: [img] = 1 if a value > max_value was seen (zeroed by the caller)
 
 int region_reduce(const int32_t* labels, const uint16_t* channels, int n_channels, int64_t img_stride, int64_t chan_stride,
                   int64_t n_img, int64_t h, int64_t w, int64_t max_labels, uint64_t* acc, cudaStream_t st);

@@ -55,16 +55,24 @@ constexpr int GD = 5;            // digits of the pass-1 result (40 bits)
 constexpr int JMIN = 2;          // digit products with d + s < JMIN are dropped in pass 2
 constexpr int NACC2 = WD + GD - 1 - JMIN;  // accumulators of pass 2 (j = JMIN .. WD+GD-2)
 constexpr int P1_NB = 64;        // pass 1: bytes (UMMA N) per tile along the contiguous axis = 32 pixels
-constexpr int P1_STAGES = 4;
+constexpr int P1_STAGES = 8;
+constexpr int P1_GROUP = 4;      // x tiles per work unit: their 4 x 32 pixels leave as 128-byte rows through one staging tile
 constexpr int P2_NR = 32;        // pass 2: rows (UMMA N) per tile
-constexpr int P2_STAGES = 2;
+constexpr int P2_STAGES = 3;
 constexpr int EPI_WARPS = 8;
 constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
-constexpr uint32_t BAND_PANEL_BYTES = MT * 128;                  // one K panel (128 bytes of K) of one digit
-constexpr uint32_t BAND_BYTES = WD * 2 * BAND_PANEL_BYTES;       // 128 KB
+constexpr int MAX_STAGES = 8;
 constexpr uint32_t P1_STAGE_BYTES = KBAND * P1_NB;               // 16 KB
 constexpr uint32_t P2_PANEL_BYTES = P2_NR * 128;                 // 4 KB
-constexpr uint32_t P2_STAGE_BYTES = GD * 2 * P2_PANEL_BYTES;     // 40 KB
+constexpr uint32_t P2_DIG_BYTES = GD * 2 * P2_PANEL_BYTES;       // 40 KB of digit panels ...
+constexpr uint32_t P2_LO_BYTES = P2_NR * MT * 8;                 // ... and the 32 x 128 float64 tile of the narrow Gaussian
+constexpr uint32_t P2_STAGE_BYTES = P2_DIG_BYTES + P2_LO_BYTES;  // 72 KB
+constexpr uint32_t P1_OUT_BYTES = GD * MT * 128;                 // pass 1 staging: five 128 x 128-byte digit tiles
+// TMEM map (512 columns): the band matrix (A operand) lives in columns [0, 256): digit d, K step ks (32 inputs =
+// 8 columns of 4 bytes) at column d * 64 + ks * 8; the accumulators in [256, 512).
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TMEM_BAND_COLS_PER_DIGIT = KBAND / 4;  // 64
+constexpr uint32_t TMEM_ACC0 = 256;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -96,13 +104,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > (1u << 24)) __trap();
   }
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
@@ -110,8 +111,27 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// shared -> global tile store (bulk async group of the issuing thread); out-of-bounds parts of the box are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// true in exactly one lane of a converged warp.  Code that issues tcgen05.mma must branch on THIS (not on
+// lane == 0): ptxas then keeps the instruction's operands in uniform registers; under an ordinary divergent branch it
+// wraps every MMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (measured: 60-80 clk per MMA whatever its size).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -123,20 +143,23 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {  // the allocating warp
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], uint8 x uint8 -> int32, issued by one thread for the CTA
-__device__ __forceinline__ void mma_u8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem], uint8 x uint8 -> int32, issued by one thread for the CTA.  A (the band matrix,
+// the same for every tile) comes from tensor memory: with both operands in shared memory an M = 128 MMA re-reads
+// its 4 KB A block every time and runs at the shared-memory operand rate (measured ~73 B/clk: 84 clk for N = 64,
+// 70 clk for N = 32) instead of the math rate (N / 2 clk).
+__device__ __forceinline__ void mma_u8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // arrives on the mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -145,6 +168,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+          addr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (sm_100 format: version 1 in bits 46-47; offsets in 16-byte units)
 constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
@@ -159,197 +191,285 @@ __host__ __device__ constexpr uint32_t idesc_u8(int m, int n, bool b_mn_major) {
 }
 
 struct alignas(8) Barriers {
-  uint64_t band_full;
-  uint64_t full[4], empty[4];
-  uint64_t acc_full[2], acc_empty[2];
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES];
+  uint64_t acc_full, acc_empty;
+  uint64_t suffix[HALO + 2];   // pass 1: integer tail sums of the weights (clamped-edge taps)
+  double suffix_f[HALO + 2];   // pass 2: the same, as float64 * 2^-16
   uint32_t tmem_base;
   uint32_t pad;
 };
 
-struct Pass1Params {
-  const uint16_t* in;      // [planes][h][w]
-  uint8_t* digits;         // [planes][GD][h][w]
-  const uint64_t* suffix;  // suffix[j] = sum_{t >= j} W[t], j = 0 .. r + 1
-  int h, w, r, shift;      // G1q = (sum + 2^(shift-1)) >> shift
-  int n_sel;               // logical planes
-  int tiles_y, tiles_x;    // per plane
-  PlaneSel sel;
-};
-
-// ------------------------------------------------------------------ pass 1: uint16 image -> 40-bit digits, axis 0
-__global__ void __launch_bounds__(NTHREADS, 1)
-tcg_axis0_kernel(const __grid_constant__ CUtensorMap band_map, const __grid_constant__ CUtensorMap in_map,
-                 const Pass1Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* band_s = smem;
-  uint8_t* stage_s = smem + BAND_BYTES;
-  Barriers* bars = reinterpret_cast<Barriers*>(stage_s + P1_STAGES * P1_STAGE_BYTES);
+// One-time setup shared by both passes: barriers, tensor memory, the band matrix into tensor memory.
+// Band row m (all four digits, 256 bytes each) is written by the thread that owns TMEM lane m: epilogue warps with
+// warp % 4 == m / 32.  K element k of a row sits in column k / 4, byte k % 4.
+__device__ __forceinline__ uint32_t tcg_setup(Barriers* bars, const uint8_t* __restrict__ band, int n_stages,
+                                              int empty_count, const uint64_t* __restrict__ suffix,
+                                              const double* __restrict__ suffix_f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  const int64_t tiles_total = (int64_t)p.n_sel * p.tiles_y * p.tiles_x;
-  const int64_t per_cta = (tiles_total + gridDim.x - 1) / gridDim.x;
-  const int64_t t_begin = (int64_t)blockIdx.x * per_cta;
-  const int64_t t_end = t_begin + per_cta < tiles_total ? t_begin + per_cta : tiles_total;
-
   if (threadIdx.x == 0) {
-    mbar_init(&bars->band_full, 1);
-    for (int s = 0; s < P1_STAGES; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], 1);
+      mbar_init(&bars->empty[s], empty_count);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&bars->acc_full[b], 1);
-      mbar_init(&bars->acc_empty[b], EPI_WARPS);
-    }
+    mbar_init(&bars->acc_full, 1);
+    mbar_init(&bars->acc_empty, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+  for (int i = threadIdx.x; i < HALO + 2; i += NTHREADS) {
+    if (suffix != nullptr) bars->suffix[i] = suffix[i];
+    if (suffix_f != nullptr) bars->suffix_f[i] = suffix_f[i];
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  if (warp >= 2 && warp < 6) {
+    const int m = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+    for (int d = 0; d < WD; ++d) {
+      const uint4* src = reinterpret_cast<const uint4*>(band + ((size_t)d * MT + m) * KBAND);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint4 x = __ldg(src + c * 4 + k);
+          v[4 * k] = x.x, v[4 * k + 1] = x.y, v[4 * k + 2] = x.z, v[4 * k + 3] = x.w;
+        }
+        tmem_st16(lane_addr + d * TMEM_BAND_COLS_PER_DIGIT + c * 16, v);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return tmem;
+}
 
-  // tile t -> (logical plane, x tile, y tile), y fastest: consecutive tiles of a CTA share half their rows (L2)
-  auto decode = [&](int64_t t, int& q, int& tx, int& ty) {
-    ty = (int)(t % p.tiles_y);
-    const int64_t u = t / p.tiles_y;
-    tx = (int)(u % p.tiles_x);
-    q = (int)(u / p.tiles_x);
-  };
+// a CTA's contiguous range of tiles, walked without divisions: (plane, slow, fast) with `fast` innermost
+struct TileWalk {
+  int q, slow, fast, n_slow, n_fast;
+  __device__ void init(int64_t t, int n_slow_, int n_fast_) {
+    n_slow = n_slow_, n_fast = n_fast_;
+    fast = (int)(t % n_fast);
+    const int64_t u = t / n_fast;
+    slow = (int)(u % n_slow);
+    q = (int)(u / n_slow);
+  }
+  __device__ __forceinline__ void next() {
+    if (++fast == n_fast) {
+      fast = 0;
+      if (++slow == n_slow) slow = 0, ++q;
+    }
+  }
+};
+
+struct Pass1Params {
+  const uint16_t* in;      // [planes][h][w]
+  const uint8_t* band;     // [WD][128][256]
+  const uint64_t* suffix;  // suffix[j] = sum_{t >= j} W[t], j = 0 .. HALO + 1 (zero beyond the radius)
+  int h, w, r, shift;      // G1q = (sum + 2^(shift-1)) >> shift
+  int n_sel;               // logical planes
+  int tiles_y, groups_x;   // per plane: 128-row tiles, groups of P1_GROUP 32-pixel tiles
+  PlaneSel sel;
+  int dbg;                 // amt_tune "tcg_debug" (timing experiments): 1 = no MMAs, 2 = no epilogue arithmetic / stores, 4 = no TMEM loads, 8 = no stores
+};
+
+// ------------------------------------------------------------------ pass 1: uint16 image -> 40-bit digits, axis 0
+// Work unit = 128 rows x 128 pixels = P1_GROUP tiles of 32 pixels (the accumulators of one tile fill the 256 TMEM
+// columns next to the band).  The digits of a unit are collected in a shared-memory staging tile per digit plane
+// (128 rows x 128 bytes, 128-byte swizzle: conflict-free 16-byte writes) and leave by TMA store: whole 128-byte
+// lines.  (Written straight from the registers, each warp store touched 32 lines with 16 bytes each and the kernel
+// spent 3/4 of its time on those stores.)
+__global__ void __launch_bounds__(NTHREADS, 1)
+tcg_axis0_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                 const Pass1Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* stage_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* out_s = stage_s + P1_STAGES * P1_STAGE_BYTES;
+  Barriers* bars = reinterpret_cast<Barriers*>(out_s + P1_OUT_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int64_t units_total = (int64_t)p.n_sel * p.tiles_y * p.groups_x;
+  const int64_t per_cta = (units_total + gridDim.x - 1) / gridDim.x;
+  const int64_t u_begin = (int64_t)blockIdx.x * per_cta;
+  const int64_t u_end = u_begin + per_cta < units_total ? u_begin + per_cta : units_total;
+  const int n_units = u_end > u_begin ? (int)(u_end - u_begin) : 0;
+
+  const uint32_t tmem = tcg_setup(bars, p.band, P1_STAGES, 1, p.suffix, nullptr);
+  // unit -> (logical plane, x group, y tile), y fastest: consecutive units of a CTA share half their rows (L2)
+  TileWalk tw;
+  tw.init(u_begin, p.groups_x, p.tiles_y);
 
   if (warp == 0) {
-    if (lane == 0) {
-      prefetch_tmap(&band_map);
-      prefetch_tmap(&in_map);
-      mbar_expect_tx(&bars->band_full, BAND_BYTES);
-      for (int d = 0; d < WD; ++d)
-        for (int pn = 0; pn < 2; ++pn)
-          tma_load_2d(band_s + (d * 2 + pn) * BAND_PANEL_BYTES, &band_map, &bars->band_full, pn * 128, d * MT);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int64_t t = t_begin; t < t_end; ++t) {
-        int q, tx, ty;
-        decode(t, q, tx, ty);
+    prefetch_tmap(&in_map);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = 0; u < n_units; ++u, tw.next()) {
+      const int plane = p.sel.phys(tw.q);
+      for (int k = 0; k < P1_GROUP; ++k) {
         mbar_wait(&bars->empty[stage], phase ^ 1);
-        mbar_expect_tx(&bars->full[stage], P1_STAGE_BYTES);
-        tma_load_3d(stage_s + stage * P1_STAGE_BYTES, &in_map, &bars->full[stage], tx * P1_NB, ty * MT - HALO,
-                    p.sel.phys(q));
-        if (++stage == P1_STAGES) {
-          stage = 0;
-          phase ^= 1;
+        if (elect_one()) {
+          mbar_expect_tx(&bars->full[stage], P1_STAGE_BYTES);
+          tma_load_3d(stage_s + stage * P1_STAGE_BYTES, &in_map, &bars->full[stage], (tw.slow * P1_GROUP + k) * P1_NB,
+                      tw.fast * MT - HALO, plane);
         }
+        __syncwarp();
+        if (++stage == P1_STAGES) stage = 0, phase ^= 1;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_u8(MT, P1_NB, true);
-      mbar_wait(&bars->band_full, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int64_t it = 0;
-      for (int64_t t = t_begin; t < t_end; ++t, ++it) {
-        const int buf = (int)(it & 1);
-        const uint32_t accphase = (uint32_t)((it >> 1) & 1);
-        mbar_wait(&bars->acc_empty[buf], accphase ^ 1);
-        mbar_wait(&bars->full[stage], phase);
-        tc_fence_after();
-        const uint32_t b_base = smem_u32(stage_s + stage * P1_STAGE_BYTES);
-#pragma unroll
-        for (int d = 0; d < WD; ++d) {
-          const uint32_t d_tmem = tmem + buf * 256 + d * P1_NB;
+    // the whole warp walks the loop (uniform control flow and addresses); one elected lane issues
+    constexpr uint32_t idesc = idesc_u8(MT, P1_NB, true);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    const int n_tiles = n_units * P1_GROUP;
+    for (int it = 0; it < n_tiles; ++it) {
+      mbar_wait(&bars->acc_empty, (uint32_t)(it & 1) ^ 1);
+      mbar_wait(&bars->full[stage], phase);
+      tc_fence_after();
+      const uint32_t b_base = smem_u32(stage_s + stage * P1_STAGE_BYTES);
+      if (elect_one()) {
+        if (!(p.dbg & 1)) {
 #pragma unroll
           for (int ks = 0; ks < KBAND / 32; ++ks) {
-            const uint64_t a_desc =
-                smem_desc(smem_u32(band_s) + (d * 2 + ks / 4) * BAND_PANEL_BYTES + (ks % 4) * 32, 16, 1024, LAYOUT_SW128);
-            // MN-major, 64-byte swizzle: 8 K rows of 64 bytes per atom (512 bytes), 32 K rows per MMA
+            // B: MN-major, 64-byte swizzle: 8 K rows of 64 bytes per atom (512 bytes), 32 K rows per MMA
             const uint64_t b_desc = smem_desc(b_base + ks * 32 * P1_NB, P1_STAGE_BYTES, 512, LAYOUT_SW64);
-            mma_u8(d_tmem, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+            for (int d = 0; d < WD; ++d)
+              mma_u8_ts(tm + TMEM_ACC0 + d * P1_NB, tm + d * TMEM_BAND_COLS_PER_DIGIT + ks * 8, b_desc, idesc, ks > 0 ? 1u : 0u);
           }
         }
         mma_commit(&bars->empty[stage]);
-        mma_commit(&bars->acc_full[buf]);
-        if (++stage == P1_STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        mma_commit(&bars->acc_full);
       }
+      __syncwarp();
+      if (++stage == P1_STAGES) stage = 0, phase ^= 1;
     }
   } else {
     const int ew = warp - 2;
     const int quarter = warp & 3;        // TMEM lanes this warp may read
-    const int hcol = ew >> 2;            // which half of the tile's 64 byte columns
+    const int hcol = ew >> 2;            // which half of a tile's 64 byte columns
     const int m = quarter * 32 + lane;   // output row inside the tile
     const int64_t hw = (int64_t)p.h * p.w;
-    int64_t it = 0;
-    for (int64_t t = t_begin; t < t_end; ++t, ++it) {
-      int q, tx, ty;
-      decode(t, q, tx, ty);
-      const int buf = (int)(it & 1);
-      const uint32_t accphase = (uint32_t)((it >> 1) & 1);
-      mbar_wait(&bars->acc_full[buf], accphase);
-      tc_fence_after();
-      uint32_t v[WD][32];
-      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + hcol * 32;
-#pragma unroll
-      for (int d = 0; d < WD; ++d) {
-        tmem_ld16(taddr + d * P1_NB, *reinterpret_cast<uint32_t(*)[16]>(&v[d][0]));
-        tmem_ld16(taddr + d * P1_NB + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[d][16]));
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
-
-      const int plane = p.sel.phys(q);
+    const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + TMEM_ACC0 + hcol * 32;
+    const uint32_t half = 1u << (p.shift - 1);
+    uint8_t* my_row = out_s + m * 128;
+    int it = 0;
+    for (int u = 0; u < n_units; ++u, tw.next()) {
+      const int plane = p.sel.phys(tw.q);
+      const int ty = tw.fast, xg = tw.slow;
       const int y = ty * MT + m;
-      const int x0 = tx * (P1_NB / 2) + hcol * 16;  // first of this thread's 16 pixels
-      if (y < p.h && x0 < p.w) {
-        // clamped-edge taps: rows above 0 / below h-1 all read the edge row
-        uint64_t f_top = 0, f_bot = 0;
-        if (y < p.r) f_top = p.suffix[y + 1];
-        if (y >= p.h - p.r) f_bot = p.suffix[p.h - y];
-        uint16_t e_top[16], e_bot[16];
-        if (f_top | f_bot) {
-          const uint16_t* row0 = p.in + (int64_t)plane * hw + x0;
-          const uint16_t* row1 = row0 + (int64_t)(p.h - 1) * p.w;
-          *reinterpret_cast<uint4*>(&e_top[0]) = __ldg(reinterpret_cast<const uint4*>(row0));
-          *reinterpret_cast<uint4*>(&e_top[8]) = __ldg(reinterpret_cast<const uint4*>(row0) + 1);
-          *reinterpret_cast<uint4*>(&e_bot[0]) = __ldg(reinterpret_cast<const uint4*>(row1));
-          *reinterpret_cast<uint4*>(&e_bot[8]) = __ldg(reinterpret_cast<const uint4*>(row1) + 1);
+      const bool edge_unit = ty * MT < p.r || ty * MT + MT > p.h - p.r;  // warp-uniform
+      const uint64_t f_top = (edge_unit && y < p.r) ? bars->suffix[y + 1] : 0ull;
+      const uint64_t f_bot = (edge_unit && y < p.h && y >= p.h - p.r) ? bars->suffix[p.h - y] : 0ull;
+#pragma unroll 1
+      for (int k = 0; k < P1_GROUP; ++k, ++it) {
+        mbar_wait(&bars->acc_full, (uint32_t)(it & 1));
+        tc_fence_after();
+        uint32_t v[WD][32];
+        if (!(p.dbg & 4)) {
+#pragma unroll
+          for (int d = 0; d < WD; ++d) {
+            tmem_ld16(taddr + d * P1_NB, &v[d][0]);
+            tmem_ld16(taddr + d * P1_NB + 16, &v[d][16]);
+          }
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int d = 0; d < WD; ++d)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[d][i] = (uint32_t)(it + d + i);
         }
-        const uint64_t half = 1ull << (p.shift - 1);
-        uint32_t dig[GD][4];
-#pragma unroll
-        for (int g = 0; g < GD; ++g)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) dig[g][k] = 0;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->acc_empty);  // the MMAs of the next tile may overwrite the accumulators now
+        if (k == 0 && u > 0) {
+          // the staging tile is free once the previous unit's TMA stores have READ it
+          if (warp == 2 && lane == 0) tma_store_wait_read();
+          epi_barrier();
+        }
+        if (p.dbg & 2) continue;
+
+        const int x0 = (xg * P1_GROUP + k) * (P1_NB / 2) + hcol * 16;  // first of this thread's 16 pixels
+        // 53-bit sums, rounded to 40 bits: g = (sum_d 256^d (lo_d + 256 hi_d) + half) >> shift
+        uint32_t glo[16], ghi[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          uint64_t tot = 0;
-#pragma unroll
-          for (int d = 0; d < WD; ++d) tot += (uint64_t)(v[d][2 * i] + (v[d][2 * i + 1] << 8)) << (8 * d);
-          if (f_top | f_bot) tot += f_top * e_top[i] + f_bot * e_bot[i];
-          const uint64_t g40 = (tot + half) >> p.shift;
-          const uint32_t lo = (uint32_t)g40, hi = (uint32_t)(g40 >> 32);
-          const int sh = 8 * (i & 3);
-          dig[0][i >> 2] |= (lo & 0xffu) << sh;
-          dig[1][i >> 2] |= ((lo >> 8) & 0xffu) << sh;
-          dig[2][i >> 2] |= ((lo >> 16) & 0xffu) << sh;
-          dig[3][i >> 2] |= (lo >> 24) << sh;
-          dig[4][i >> 2] |= (hi & 0xffu) << sh;
+          const uint32_t a0 = v[0][2 * i + 1] * 256u + v[0][2 * i] + half;  // < 2^32: the parts are < 2^23
+          const uint32_t a1 = v[1][2 * i + 1] * 256u + v[1][2 * i];
+          const uint32_t a2 = v[2][2 * i + 1] * 256u + v[2][2 * i];
+          const uint32_t a3 = v[3][2 * i + 1] * 256u + v[3][2 * i];
+          const uint64_t t01 = (uint64_t)a1 * 256u + a0;
+          const uint64_t t23 = (uint64_t)a3 * 256u + a2;
+          uint64_t tot = (uint64_t)(uint32_t)t23 * 65536u + t01;
+          tot += (uint64_t)((uint32_t)(t23 >> 32) << 16) << 32;
+          glo[i] = (uint32_t)tot, ghi[i] = (uint32_t)(tot >> 32);
         }
-        uint8_t* dst = p.digits + ((int64_t)plane * GD) * hw + (int64_t)y * p.w + x0;
+        // clamped-edge taps (mode='nearest'): rows above 0 / below h-1 all read the edge row.  Only the first and
+        // the last units of a column of units get here.
+        if (edge_unit && (f_top | f_bot) != 0ull && x0 < p.w) {
+          const uint16_t* row0 = p.in + (int64_t)plane * hw + x0;
+          const uint16_t* row1 = row0 + (int64_t)(p.h - 1) * p.w;
+          uint32_t et[8], eb[8];
+          *reinterpret_cast<uint4*>(&et[0]) = __ldg(reinterpret_cast<const uint4*>(row0));
+          *reinterpret_cast<uint4*>(&et[4]) = __ldg(reinterpret_cast<const uint4*>(row0) + 1);
+          *reinterpret_cast<uint4*>(&eb[0]) = __ldg(reinterpret_cast<const uint4*>(row1));
+          *reinterpret_cast<uint4*>(&eb[4]) = __ldg(reinterpret_cast<const uint4*>(row1) + 1);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t e0 = (i & 1) ? (et[i >> 1] >> 16) : (et[i >> 1] & 0xffffu);
+            const uint32_t e1 = (i & 1) ? (eb[i >> 1] >> 16) : (eb[i >> 1] & 0xffffu);
+            const uint64_t tot = (((uint64_t)ghi[i] << 32) | glo[i]) + f_top * e0 + f_bot * e1;
+            glo[i] = (uint32_t)tot, ghi[i] = (uint32_t)(tot >> 32);
+          }
+        }
+        uint32_t dig[GD][4];
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+          uint32_t l[4], hb[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int i = 4 * g4 + kk;
+            l[kk] = __funnelshift_r(glo[i], ghi[i], p.shift);  // bits [shift, shift + 32)
+            hb[kk] = ghi[i] >> p.shift;                          // bits [shift + 32, shift + 40)
+          }
+          // 4 x 4 byte transpose: l[kk] holds digits 0..3 of pixel kk -> dig[d] holds digit d of pixels 0..3
+          const uint32_t x01 = __byte_perm(l[0], l[1], 0x5140), y01 = __byte_perm(l[0], l[1], 0x7362);
+          const uint32_t x23 = __byte_perm(l[2], l[3], 0x5140), y23 = __byte_perm(l[2], l[3], 0x7362);
+          dig[0][g4] = __byte_perm(x01, x23, 0x5410);
+          dig[1][g4] = __byte_perm(x01, x23, 0x7632);
+          dig[2][g4] = __byte_perm(y01, y23, 0x5410);
+          dig[3][g4] = __byte_perm(y01, y23, 0x7632);
+          dig[4][g4] = __byte_perm(__byte_perm(hb[0], hb[1], 0x0040), __byte_perm(hb[2], hb[3], 0x0040), 0x5410);
+        }
+        if ((p.dbg & 8) && (dig[0][0] ^ dig[1][1] ^ dig[2][2] ^ dig[3][3] ^ dig[4][0]) != 0x9e3779b9u) continue;  // timing: no stores
+        // 16 bytes per digit plane into the staging tile: chunk c of row m sits at chunk position c ^ (m & 7)
+        uint8_t* dst = my_row + (((k * 2 + hcol) ^ (m & 7)) << 4);
 #pragma unroll
         for (int g = 0; g < GD; ++g)
-          *reinterpret_cast<uint4*>(dst + g * hw) = make_uint4(dig[g][0], dig[g][1], dig[g][2], dig[g][3]);
+          *reinterpret_cast<uint4*>(dst + g * (MT * 128)) = make_uint4(dig[g][0], dig[g][1], dig[g][2], dig[g][3]);
+      }
+      if (p.dbg & (2 | 8)) continue;
+      fence_async_smem();  // this thread's staging writes become visible to the TMA engine
+      epi_barrier();
+      if (warp == 2 && lane == 0) {
+#pragma unroll
+        for (int g = 0; g < GD; ++g)
+          tma_store_3d(&out_map, out_s + g * (MT * 128), xg * (P1_GROUP * P1_NB / 2), ty * MT, plane * GD + g);
+        tma_store_commit();
       }
     }
+    if (warp == 2 && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 struct Pass2Params {
@@ -358,21 +478,21 @@ struct Pass2Params {
   double* out;             // lo - G_hi
   uint16_t* buckets;       // optional
   uint64_t* minmax;        // optional [planes][2]
+  const uint8_t* band;
   const double* suffix_f;  // (double)suffix[j] * 2^-16
   double scale;            // in_scale * 2^-(S+8)
   int h, w, r;
   int n_sel, tiles_y, tiles_x;
   PlaneSel sel;
+  int dbg;
 };
 
 // ------------------------------------------------------------------ pass 2: digits -> float64 DoG, axis 1
 __global__ void __launch_bounds__(NTHREADS, 1)
-tcg_axis1_kernel(const __grid_constant__ CUtensorMap band_map, const __grid_constant__ CUtensorMap dig_map,
+tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_constant__ CUtensorMap lo_map,
                  const Pass2Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* band_s = smem;
-  uint8_t* stage_s = smem + BAND_BYTES;
+  uint8_t* stage_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Barriers* bars = reinterpret_cast<Barriers*>(stage_s + P2_STAGES * P2_STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -380,100 +500,71 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap band_map, const __grid_cons
   const int64_t per_cta = (tiles_total + gridDim.x - 1) / gridDim.x;
   const int64_t t_begin = (int64_t)blockIdx.x * per_cta;
   const int64_t t_end = t_begin + per_cta < tiles_total ? t_begin + per_cta : tiles_total;
+  const int n_tiles = t_end > t_begin ? (int)(t_end - t_begin) : 0;
 
-  if (threadIdx.x == 0) {
-    mbar_init(&bars->band_full, 1);
-    for (int s = 0; s < P2_STAGES; ++s) {
-      mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&bars->acc_full[b], 1);
-      mbar_init(&bars->acc_empty[b], EPI_WARPS);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = bars->tmem_base;
-
+  // a stage is free again once the MMAs have read its digit panels AND the epilogue warps its narrow-Gaussian tile
+  const uint32_t tmem = tcg_setup(bars, p.band, P2_STAGES, 1 + EPI_WARPS, nullptr, p.suffix_f);
   // x fastest: consecutive tiles of a CTA share half their columns
-  auto decode = [&](int64_t t, int& q, int& tx, int& ty) {
-    tx = (int)(t % p.tiles_x);
-    const int64_t u = t / p.tiles_x;
-    ty = (int)(u % p.tiles_y);
-    q = (int)(u / p.tiles_y);
-  };
+  TileWalk tw;
+  tw.init(t_begin, p.tiles_y, p.tiles_x);
 
   if (warp == 0) {
-    if (lane == 0) {
-      prefetch_tmap(&band_map);
-      prefetch_tmap(&dig_map);
-      mbar_expect_tx(&bars->band_full, BAND_BYTES);
-      for (int d = 0; d < WD; ++d)
-        for (int pn = 0; pn < 2; ++pn)
-          tma_load_2d(band_s + (d * 2 + pn) * BAND_PANEL_BYTES, &band_map, &bars->band_full, pn * 128, d * MT);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int64_t t = t_begin; t < t_end; ++t) {
-        int q, tx, ty;
-        decode(t, q, tx, ty);
-        mbar_wait(&bars->empty[stage], phase ^ 1);
-        mbar_expect_tx(&bars->full[stage], P2_STAGE_BYTES);
-        const int plane = p.sel.phys(q);
+    prefetch_tmap(&dig_map);
+    prefetch_tmap(&lo_map);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < n_tiles; ++it, tw.next()) {
+      mbar_wait(&bars->empty[stage], phase ^ 1);
+      const int plane = p.sel.phys(tw.q);
+      if (elect_one()) {
+        uint8_t* dst = stage_s + stage * P2_STAGE_BYTES;
+        mbar_expect_tx(&bars->full[stage], p.lo != nullptr ? P2_STAGE_BYTES : P2_DIG_BYTES);
+#pragma unroll
         for (int s = 0; s < GD; ++s)
+#pragma unroll
           for (int pn = 0; pn < 2; ++pn)
-            tma_load_3d(stage_s + stage * P2_STAGE_BYTES + (s * 2 + pn) * P2_PANEL_BYTES, &dig_map, &bars->full[stage],
-                        tx * MT - HALO + pn * 128, ty * P2_NR, plane * GD + s);
-        if (++stage == P2_STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+            tma_load_3d(dst + (s * 2 + pn) * P2_PANEL_BYTES, &dig_map, &bars->full[stage], tw.fast * MT - HALO + pn * 128,
+                        tw.slow * P2_NR, plane * GD + s);
+        if (p.lo != nullptr) tma_load_3d(dst + P2_DIG_BYTES, &lo_map, &bars->full[stage], tw.fast * MT, tw.slow * P2_NR, plane);
       }
+      __syncwarp();
+      if (++stage == P2_STAGES) stage = 0, phase ^= 1;
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_u8(MT, P2_NR, false);
-      mbar_wait(&bars->band_full, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int64_t it = 0;
-      for (int64_t t = t_begin; t < t_end; ++t, ++it) {
-        const int buf = (int)(it & 1);
-        const uint32_t accphase = (uint32_t)((it >> 1) & 1);
-        mbar_wait(&bars->acc_empty[buf], accphase ^ 1);
-        mbar_wait(&bars->full[stage], phase);
-        tc_fence_after();
-        const uint32_t b_base = smem_u32(stage_s + stage * P2_STAGE_BYTES);
+    constexpr uint32_t idesc = idesc_u8(MT, P2_NR, false);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < n_tiles; ++it) {
+      mbar_wait(&bars->acc_empty, (uint32_t)(it & 1) ^ 1);
+      mbar_wait(&bars->full[stage], phase);
+      tc_fence_after();
+      const uint32_t b_base = smem_u32(stage_s + stage * P2_STAGE_BYTES);
+      if (elect_one()) {
+        if (!(p.dbg & 1)) {
+          // K step outermost, then weight digit, then sample digit: consecutive MMAs go to different accumulators
 #pragma unroll
-        for (int j = JMIN; j <= WD + GD - 2; ++j) {
-          const uint32_t d_tmem = tmem + buf * 256 + (j - JMIN) * P2_NR;
-          bool first = true;
+          for (int ks = 0; ks < KBAND / 32; ++ks) {
 #pragma unroll
-          for (int d = 0; d < WD; ++d) {
-            const int s = j - d;
-            if (s < 0 || s >= GD) continue;
+            for (int d = 0; d < WD; ++d) {
 #pragma unroll
-            for (int ks = 0; ks < KBAND / 32; ++ks) {
-              const uint64_t a_desc =
-                  smem_desc(smem_u32(band_s) + (d * 2 + ks / 4) * BAND_PANEL_BYTES + (ks % 4) * 32, 16, 1024, LAYOUT_SW128);
-              const uint64_t b_desc =
-                  smem_desc(b_base + (s * 2 + ks / 4) * P2_PANEL_BYTES + (ks % 4) * 32, 16, 1024, LAYOUT_SW128);
-              mma_u8(d_tmem, a_desc, b_desc, idesc, first ? 0u : 1u);
-              first = false;
+              for (int s = 0; s < GD; ++s) {
+                const int j = d + s;
+                if (j < JMIN) continue;
+                const int d_first = j - (GD - 1) > 0 ? j - (GD - 1) : 0;  // the first product that lands in accumulator j
+                const uint64_t b_desc =
+                    smem_desc(b_base + (s * 2 + ks / 4) * P2_PANEL_BYTES + (ks % 4) * 32, 16, 1024, LAYOUT_SW128);
+                mma_u8_ts(tm + TMEM_ACC0 + (j - JMIN) * P2_NR, tm + d * TMEM_BAND_COLS_PER_DIGIT + ks * 8, b_desc, idesc,
+                          (ks == 0 && d == d_first) ? 0u : 1u);
+              }
             }
           }
         }
         mma_commit(&bars->empty[stage]);
-        mma_commit(&bars->acc_full[buf]);
-        if (++stage == P2_STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        mma_commit(&bars->acc_full);
       }
+      __syncwarp();
+      if (++stage == P2_STAGES) stage = 0, phase ^= 1;
     }
   } else {
     const int ew = warp - 2;
@@ -481,75 +572,93 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap band_map, const __grid_cons
     const int hrow = ew >> 2;               // which 16 of the tile's 32 rows
     const int mx = quarter * 32 + lane;     // output column inside the tile
     const int64_t hw = (int64_t)p.h * p.w;
-    uint64_t kmin = ~0ull, kmax = 0ull;
-    int cur_plane = -1;
+    const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + TMEM_ACC0 + hrow * 16;
+    // No -0.0 can occur (lo >= +0, g >= +0, and x - x = +0), so float64 comparisons order the values as their keys do
+    double vmin = __longlong_as_double(0x7ff0000000000000ll), vmax = __longlong_as_double(0xfff0000000000000ll);
+    int cur_q = -1, plane = -1;
+    int stage = 0;
+    uint32_t phase = 0;
     auto flush = [&]() {
-      if (p.minmax != nullptr && cur_plane >= 0) {
-        const uint64_t a = warp_min_u64(kmin), b = warp_max_u64(kmax);
+      if (p.minmax != nullptr && plane >= 0) {
+        const uint64_t a = warp_min_u64(f64_to_key(vmin)), b = warp_max_u64(f64_to_key(vmax));
         if (lane == 0 && a <= b) {
-          atomicMin((unsigned long long*)&p.minmax[2 * cur_plane], (unsigned long long)a);
-          atomicMax((unsigned long long*)&p.minmax[2 * cur_plane + 1], (unsigned long long)b);
+          atomicMin((unsigned long long*)&p.minmax[2 * plane], (unsigned long long)a);
+          atomicMax((unsigned long long*)&p.minmax[2 * plane + 1], (unsigned long long)b);
         }
       }
-      kmin = ~0ull;
-      kmax = 0ull;
+      vmin = __longlong_as_double(0x7ff0000000000000ll), vmax = __longlong_as_double(0xfff0000000000000ll);
     };
-    int64_t it = 0;
-    for (int64_t t = t_begin; t < t_end; ++t, ++it) {
-      int q, tx, ty;
-      decode(t, q, tx, ty);
-      const int plane = p.sel.phys(q);
-      if (plane != cur_plane) {
+    for (int it = 0; it < n_tiles; ++it, tw.next()) {
+      if (tw.q != cur_q) {
         flush();
-        cur_plane = plane;
+        cur_q = tw.q, plane = p.sel.phys(tw.q);
       }
+      const int tx = tw.fast, ty = tw.slow;
       const int x = tx * MT + mx;
       const int y0 = ty * P2_NR + hrow * 16;
       const bool x_ok = x < p.w;
-      // the narrow operand (coalesced: lanes are consecutive x), in flight while the accumulators arrive
+      const int rows = p.h - y0 < 16 ? p.h - y0 : 16;  // valid rows of this thread's 16 (may be <= 0)
+      // the narrow operand: this thread's 16 samples of the stage's float64 tile (lanes are consecutive x: no bank
+      // conflicts), then the stage goes back to the producer
       double lo[16];
+      mbar_wait(&bars->full[stage], phase);
       if (p.lo != nullptr) {
-        const double* lp = p.lo + (int64_t)plane * hw + (int64_t)y0 * p.w + (x_ok ? x : p.w - 1);
+        const double* lt = reinterpret_cast<const double*>(stage_s + stage * P2_STAGE_BYTES + P2_DIG_BYTES) + (hrow * 16) * MT + mx;
 #pragma unroll
-        for (int n = 0; n < 16; ++n) lo[n] = (y0 + n < p.h) ? __ldg(lp + (int64_t)n * p.w) : 0.0;
+        for (int n = 0; n < 16; ++n) lo[n] = lt[n * MT];
+      } else {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) lo[n] = 0.0;
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->empty[stage]);
+      if (++stage == P2_STAGES) stage = 0, phase ^= 1;
       // clamped-edge taps: columns left of 0 / right of w-1 all read the edge column of the same row
-      double f_l = 0.0, f_r = 0.0;
-      if (x_ok && x < p.r) f_l = p.suffix_f[x + 1];
-      if (x_ok && x >= p.w - p.r) f_r = p.suffix_f[p.w - x];
       const bool edge_tile = tx * MT < p.r || tx * MT + MT > p.w - p.r;  // warp-uniform
-      double e_l = 0.0, e_r = 0.0;  // lane n < 16: the edge samples of row y0 + n (40-bit integers, exact in float64)
-      if (edge_tile && lane < 16 && y0 + lane < p.h) {
-        const uint8_t* dp = p.digits + ((int64_t)plane * GD) * hw + (int64_t)(y0 + lane) * p.w;
-        uint64_t a = 0, b = 0;
+      double f_l = 0.0, f_r = 0.0, e_l = 0.0, e_r = 0.0;
+      if (edge_tile) {
+        if (x_ok && x < p.r) f_l = bars->suffix_f[x + 1];
+        if (x_ok && x >= p.w - p.r) f_r = bars->suffix_f[p.w - x];
+        if (lane < rows) {  // lane n < 16: the edge samples of row y0 + n (40-bit integers, exact in float64)
+          const uint8_t* dp = p.digits + ((int64_t)plane * GD) * hw + (int64_t)(y0 + lane) * p.w;
+          uint64_t a = 0, b = 0;
 #pragma unroll
-        for (int s = 0; s < GD; ++s) {
-          a |= (uint64_t)dp[s * hw] << (8 * s);
-          b |= (uint64_t)dp[s * hw + p.w - 1] << (8 * s);
+          for (int s = 0; s < GD; ++s) {
+            a |= (uint64_t)dp[s * hw] << (8 * s);
+            b |= (uint64_t)dp[s * hw + p.w - 1] << (8 * s);
+          }
+          e_l = (double)a, e_r = (double)b;
         }
-        e_l = (double)a;
-        e_r = (double)b;
       }
 
-      const int buf = (int)(it & 1);
-      const uint32_t accphase = (uint32_t)((it >> 1) & 1);
-      mbar_wait(&bars->acc_full[buf], accphase);
+      mbar_wait(&bars->acc_full, (uint32_t)(it & 1));
       tc_fence_after();
       uint32_t v[NACC2][16];
-      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + hrow * 16;
+      if (!(p.dbg & 4)) {
 #pragma unroll
-      for (int a = 0; a < NACC2; ++a) tmem_ld16(taddr + a * P2_NR, v[a]);
-      tmem_ld_wait();
+        for (int a = 0; a < NACC2; ++a) tmem_ld16(taddr + a * P2_NR, v[a]);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int a = 0; a < NACC2; ++a)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[a][i] = (uint32_t)(it + a + i);
+      }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+      if (lane == 0) mbar_arrive(&bars->acc_empty);
+      if (p.dbg & 2) continue;
 
       double res[16];
 #pragma unroll
       for (int n = 0; n < 16; ++n) {
-        uint64_t tot = 0;
-#pragma unroll
-        for (int a = 0; a < NACC2; ++a) tot += (uint64_t)v[a][n] << (8 * a);
+        // sum_a acc_a * 256^a, a = 0..5, pairwise: every pair fits 34 bits, the total 61
+        static_assert(NACC2 == 6, "the combine below is written for six accumulators");
+        const uint64_t p01 = (uint64_t)v[1][n] * 256u + v[0][n];
+        const uint64_t p23 = (uint64_t)v[3][n] * 256u + v[2][n];
+        const uint64_t p45 = (uint64_t)v[5][n] * 256u + v[4][n];
+        uint64_t tot = (uint64_t)(uint32_t)p23 * 65536u + p01;
+        tot += ((uint64_t)((uint32_t)(p23 >> 32) << 16) + (uint32_t)p45) << 32;
         double g = (double)tot;
         if (edge_tile) {
           const double el = __shfl_sync(0xffffffffu, e_l, n), er = __shfl_sync(0xffffffffu, e_r, n);
@@ -558,17 +667,16 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap band_map, const __grid_cons
         g *= p.scale;
         res[n] = p.lo != nullptr ? lo[n] - g : g;
       }
-      if (x_ok) {
+      if (x_ok && rows > 0) {
         double* op = p.out + (int64_t)plane * hw + (int64_t)y0 * p.w + x;
         uint16_t* bp = p.buckets != nullptr ? p.buckets + (int64_t)plane * hw + (int64_t)y0 * p.w + x : nullptr;
 #pragma unroll
         for (int n = 0; n < 16; ++n) {
-          if (y0 + n < p.h) {
+          if (n < rows) {
             op[(int64_t)n * p.w] = res[n];
             if (bp != nullptr) bp[(int64_t)n * p.w] = (uint16_t)bucket12(res[n]);
-            const uint64_t key = f64_to_key(res[n]);
-            kmin = key < kmin ? key : kmin;
-            kmax = key > kmax ? key : kmax;
+            vmin = res[n] < vmin ? res[n] : vmin;
+            vmax = res[n] > vmax ? res[n] : vmax;
           }
         }
       }
@@ -577,14 +685,16 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap band_map, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ the narrow Gaussian (radius <= 4), float64
 // Exact scipy order (axis 0 first, then axis 1; acc = x0*w0; acc += (x-j + x+j) * wj for j = r..1).
 // A CTA of 128 threads walks a strip of LO_TW output columns down the plane in blocks of LO_TH rows:
 // thread t owns column x0 - 4 + t for the axis-0 pass (sliding window in registers, uint16 -> float64 on the
-// way in), the block's axis-0 results sit in shared memory, then thread t < LO_TW produces column x0 + t.
+// way in; the NEXT block's LO_TH samples are fetched as one batch of independent loads before this block is
+// computed, so the walk is not a chain of exposed L2 latencies), the block's axis-0 results sit in shared
+// memory, then thread t < LO_TW produces column x0 + t.
 constexpr int LO_R = 4, LO_NT = 128, LO_TW = LO_NT - 2 * LO_R, LO_TH = 32;
 
 __global__ void __launch_bounds__(LO_NT)
@@ -603,20 +713,28 @@ lo2d_kernel(const uint16_t* __restrict__ in, double* __restrict__ out, const dou
   double* dst = out + (int64_t)plane * h * w;
   __syncthreads();
   const double w0 = wsm[0], w1 = wsm[1], w2 = wsm[2], w3 = wsm[3], w4 = wsm[4];
-  // window[i] = sample y - 4 + i of the current row y
-  double win[2 * LO_R + 1];
-  auto fetch = [&](int y) {
+  auto raw_at = [&](int y) -> uint16_t {
     y = y < 0 ? 0 : (y > h - 1 ? h - 1 : y);
-    return dmul((double)__ldg(src + (int64_t)y * w), scale);
+    return __ldg(src + (int64_t)y * w);
   };
+  // win[i] = sample y - 4 + i of the current row y; cur[yy] = raw sample yb + yy + 4 (the one row yy shifts in)
+  double win[2 * LO_R + 1];
 #pragma unroll
-  for (int i = 0; i < 2 * LO_R; ++i) win[i + 1] = fetch(i - LO_R);
+  for (int i = 0; i < 2 * LO_R; ++i) win[i + 1] = dmul((double)raw_at(i - LO_R), scale);
+  uint16_t cur[LO_TH];
+#pragma unroll
+  for (int yy = 0; yy < LO_TH; ++yy) cur[yy] = raw_at(yy + LO_R);
   for (int yb = 0; yb < h; yb += LO_TH) {
-#pragma unroll 4
+    uint16_t nxt[LO_TH];
+    if (yb + LO_TH < h) {
+#pragma unroll
+      for (int yy = 0; yy < LO_TH; ++yy) nxt[yy] = raw_at(yb + LO_TH + yy + LO_R);
+    }
+#pragma unroll
     for (int yy = 0; yy < LO_TH; ++yy) {
 #pragma unroll
       for (int i = 0; i < 2 * LO_R; ++i) win[i] = win[i + 1];
-      win[2 * LO_R] = fetch(yb + yy + LO_R);
+      win[2 * LO_R] = dmul((double)cur[yy], scale);
       double acc = dmul(win[LO_R], w0);
       if (r >= 4) acc = dadd(acc, dmul(dadd(win[LO_R - 4], win[LO_R + 4]), w4));
       if (r >= 3) acc = dadd(acc, dmul(dadd(win[LO_R - 3], win[LO_R + 3]), w3));
@@ -627,9 +745,9 @@ lo2d_kernel(const uint16_t* __restrict__ in, double* __restrict__ out, const dou
     __syncthreads();
     const int x = x0 + t;
     if (t < LO_TW && x < w) {
-#pragma unroll 4
-      for (int yy = 0; yy < LO_TH; ++yy) {
-        if (yb + yy >= h) break;
+      const int rows = h - yb < LO_TH ? h - yb : LO_TH;
+#pragma unroll 8
+      for (int yy = 0; yy < rows; ++yy) {
         const double* vr = &vs[yy][t + LO_R];
         double acc = dmul(vr[0], w0);
         if (r >= 4) acc = dadd(acc, dmul(dadd(vr[-4], vr[4]), w4));
@@ -640,6 +758,8 @@ lo2d_kernel(const uint16_t* __restrict__ in, double* __restrict__ out, const dou
       }
     }
     __syncthreads();
+#pragma unroll
+    for (int yy = 0; yy < LO_TH; ++yy) cur[yy] = nxt[yy];
   }
 }
 
@@ -676,6 +796,21 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
   return r == CUDA_SUCCESS ? AMT_OK : AMT_ERR_CUDA;
 }
 
+// float64 tensor (inner, rows, planes) with a (box_inner x box_rows) box, no swizzle
+static int make_map_f64(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t planes, uint32_t box_inner,
+                        uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return AMT_ERR_UNSUPPORTED;
+  cuuint64_t dims[3] = {inner, rows, planes};
+  cuuint64_t strides[2] = {inner * 8, inner * rows * 8};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? AMT_OK : AMT_ERR_CUDA;
+}
+
 }  // namespace tc
 }  // namespace amt
 
@@ -683,16 +818,16 @@ struct amt_tcg {
   int device, r, S;
   std::vector<uint64_t>* W;  // W[t], t = 0..r (symmetric)
   uint8_t* band;             // device [WD][128][256]
-  uint64_t* suffix;          // device [r + 2]
-  double* suffix_f;          // device [r + 2]: suffix * 2^-16
-  CUtensorMap band_map;
+  uint64_t* suffix;          // device [HALO + 2]
+  double* suffix_f;          // device [HALO + 2]: suffix * 2^-16
 };
 
 namespace amt {
 namespace tc {
 
-constexpr size_t P1_SMEM = 1024 + BAND_BYTES + P1_STAGES * P1_STAGE_BYTES + sizeof(Barriers);
-constexpr size_t P2_SMEM = 1024 + BAND_BYTES + P2_STAGES * P2_STAGE_BYTES + sizeof(Barriers);
+int g_tcg_debug = 0;  // amt_tune "tcg_debug"
+constexpr size_t P1_SMEM = 1024 + P1_STAGES * P1_STAGE_BYTES + P1_OUT_BYTES + sizeof(Barriers);
+constexpr size_t P2_SMEM = 1024 + P2_STAGES * P2_STAGE_BYTES + sizeof(Barriers);
 
 bool tcg_shape_ok(int64_t h, int64_t w) { return h >= 128 && w >= 128 && w % 16 == 0 && h * w < (1ll << 31); }
 
@@ -717,20 +852,23 @@ int tcg_axis0(const amt_tcg* g, const uint16_t* in, int64_t n_img, int64_t h, in
   AMT_TRY(make_map(&in_map, in, (uint64_t)w * 2, (uint64_t)h, (uint64_t)n_img, P1_NB, KBAND, CU_TENSOR_MAP_SWIZZLE_64B));
   Pass1Params p{};
   p.in = in;
-  p.digits = digits;
+  p.band = g->band;
   p.suffix = g->suffix;
   p.h = (int)h;
   p.w = (int)w;
   p.r = g->r;
   p.shift = g->S - 24;
   p.n_sel = (int)n_sel;
+  CUtensorMap out_map;
+  AMT_TRY(make_map(&out_map, digits, (uint64_t)w, (uint64_t)h, (uint64_t)n_img * GD, 128, MT, CU_TENSOR_MAP_SWIZZLE_128B));
   p.tiles_y = (int)ceil_div(h, MT);
-  p.tiles_x = (int)ceil_div(w * 2, P1_NB);
+  p.groups_x = (int)ceil_div(w, P1_GROUP * P1_NB / 2);
   p.sel = sel;
-  const int64_t tiles = n_sel * p.tiles_y * p.tiles_x;
+  p.dbg = g_tcg_debug;
+  const int64_t units = n_sel * p.tiles_y * p.groups_x;
   AMT_CUDA_TRY(cudaFuncSetAttribute(tcg_axis0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P1_SMEM));
-  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  tcg_axis0_kernel<<<grid, NTHREADS, P1_SMEM, st>>>(g->band_map, in_map, p);
+  const int grid = (int)(units < kNumSMs ? units : kNumSMs);
+  tcg_axis0_kernel<<<grid, NTHREADS, P1_SMEM, st>>>(in_map, out_map, p);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
@@ -750,6 +888,7 @@ int tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double 
   p.out = out;
   p.buckets = buckets;
   p.minmax = minmax;
+  p.band = g->band;
   p.suffix_f = g->suffix_f;
   p.scale = std::ldexp(in_scale, -(g->S + 8));
   p.h = (int)h;
@@ -759,10 +898,16 @@ int tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double 
   p.tiles_y = (int)ceil_div(h, P2_NR);
   p.tiles_x = (int)ceil_div(w, MT);
   p.sel = sel;
+  p.dbg = g_tcg_debug;
   const int64_t tiles = n_sel * p.tiles_y * p.tiles_x;
   AMT_CUDA_TRY(cudaFuncSetAttribute(tcg_axis1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM));
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  tcg_axis1_kernel<<<grid, NTHREADS, P2_SMEM, st>>>(g->band_map, dig_map, p);
+  CUtensorMap lo_map = dig_map;  // unused when lo == nullptr
+  if (lo != nullptr) {
+    if ((uintptr_t)lo % 16) return AMT_ERR_UNSUPPORTED;
+    AMT_TRY(make_map_f64(&lo_map, lo, (uint64_t)w, (uint64_t)h, (uint64_t)n_img, MT, P2_NR));
+  }
+  tcg_axis1_kernel<<<grid, NTHREADS, P2_SMEM, st>>>(dig_map, lo_map, p);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
@@ -844,10 +989,10 @@ int amt_tcg_create(const double* half_w_host, int radius, int device, amt_tcg** 
         const int t = std::abs(k - HALO - m);
         if (t <= radius) band[((size_t)d * MT + m) * KBAND + k] = (uint8_t)((W[t] >> (8 * d)) & 0xff);
       }
-  std::vector<uint64_t> suffix(radius + 2, 0);
-  std::vector<double> suffix_f(radius + 2, 0.0);
+  std::vector<uint64_t> suffix(HALO + 2, 0);  // zero beyond the radius
+  std::vector<double> suffix_f(HALO + 2, 0.0);
   for (int j = radius; j >= 0; --j) suffix[j] = suffix[j + 1] + W[j];
-  for (int j = 0; j <= radius + 1; ++j) suffix_f[j] = std::ldexp((double)suffix[j], -16);
+  for (int j = 0; j <= HALO + 1; ++j) suffix_f[j] = std::ldexp((double)suffix[j], -16);
   auto fail = [&](int s) {
     amt_tcg_destroy(g);
     return s;
@@ -859,8 +1004,7 @@ int amt_tcg_create(const double* half_w_host, int radius, int device, amt_tcg** 
       cudaMemcpy(g->suffix, suffix.data(), suffix.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
       cudaMemcpy(g->suffix_f, suffix_f.data(), suffix_f.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess)
     return fail(AMT_ERR_CUDA);
-  const int ms = make_map(&g->band_map, g->band, KBAND, (uint64_t)WD * MT, 0, 128, MT, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (ms != AMT_OK) return fail(ms);
+  if (encode_fn() == nullptr) return fail(AMT_ERR_UNSUPPORTED);  // no cuTensorMapEncodeTiled in this driver
   *out = g;
   return AMT_OK;
 }

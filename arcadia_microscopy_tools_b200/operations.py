@@ -31,19 +31,40 @@ def _device_op(func):
     return func
 
 
-def _prepare(intensities, *, allow_bool: bool = False):
-    """-> (device tensor, numpy dtype of the logical input, was_numpy).  Integer dtypes other
-    than uint8/uint16 are promoted to float64 when that is exact (|v| < 2**53)."""
+def _img_as_float_wide(a: np.ndarray) -> np.ndarray:
+    """``skimage.util.img_as_float`` for the integer dtypes that have no kernel of their own (int8, int16, int32,
+    int64, uint32, uint64), as scikit-image's ``_convert`` does it: unsigned ``x * (1 / max)``; signed
+    ``(x + 0.5) * 2 / (max - min)``.  A dtype conversion at the host boundary (the array has to become float64
+    to be uploaded at all); uint8 / uint16 never come here, their scale is applied inside the kernels."""
+    info = np.iinfo(a.dtype)
+    if a.dtype.kind == "u":
+        return np.multiply(a, 1.0 / info.max, dtype=np.float64)
+    out = np.add(a, 0.5, dtype=np.float64)
+    out *= 2
+    out /= float(info.max) - float(info.min)
+    return out
+
+
+def _prepare(intensities, *, allow_bool: bool = False, as_float: bool = False):
+    """-> (device tensor, numpy dtype of the logical input, was_numpy).  The tensor is C-contiguous (the kernels
+    take a base pointer and plane strides: a cropped or sliced view is packed first).  Integer dtypes other than
+    uint8/uint16 are promoted to float64 — with ``img_as_float``'s scale and offset when ``as_float`` (the
+    Gaussian / DoG ops, which scikit-image feeds through ``img_as_float``), unscaled otherwise (exact while
+    |v| < 2**53)."""
     if _gpu.is_device_array(intensities):
         torch = _gpu.torch_mod()
         if intensities.dtype in (torch.int16, torch.uint16):
-            return intensities, np.dtype(np.uint16), False
+            return intensities.contiguous(), np.dtype(np.uint16), False
         if intensities.dtype == torch.float64:
-            return intensities, np.dtype(np.float64), False
+            return intensities.contiguous(), np.dtype(np.float64), False
+        if intensities.dtype == torch.bool and allow_bool:
+            return intensities.to(torch.float64).contiguous(), np.dtype(np.bool_), False
         raise TypeError(f"unsupported device dtype {intensities.dtype}")
     a = np.asarray(intensities)
     if a.dtype == np.uint16 or a.dtype == np.float64:
         return _gpu.to_device(a), a.dtype, True
+    if as_float and a.dtype.kind in "iu" and a.dtype != np.uint8:
+        return _gpu.to_device(_img_as_float_wide(a)), np.dtype(np.float64), True
     if a.dtype == np.uint8:
         return _gpu.to_device(a.astype(np.uint16)), a.dtype, True
     if a.dtype == np.bool_ and allow_bool:
@@ -58,6 +79,9 @@ def _prepare(intensities, *, allow_bool: bool = False):
 
 
 def _finish(out, was_numpy: bool):
+    # inside a device-resident Pipeline chain the result stays on the device whatever the first input was
+    if getattr(_gpu._tls, "keep_on_device", False):
+        return out
     return _gpu.to_host(out) if was_numpy else out
 
 
@@ -132,7 +156,7 @@ def subtract_background_dog(
         raise ValueError(f"low_sigma ({low_sigma}) must be smaller than high_sigma ({high_sigma})")
     if not _gpu.is_device_array(intensities) and np.asarray(intensities).size == 0:
         return np.zeros_like(np.asarray(intensities), dtype=float)
-    t, np_dtype, was_numpy = _prepare(intensities, allow_bool=True)
+    t, np_dtype, was_numpy = _prepare(intensities, allow_bool=True, as_float=True)
     scale = _gpu.input_scale(np_dtype)
     slice_ndim = t.ndim - 1 if _batched else t.ndim
     if slice_ndim == 2:
@@ -166,7 +190,7 @@ def gaussian_smooth(intensities, sigma: float = 1.0, *, _batched: bool = False):
         raise ValueError(f"sigma must be non-negative, got {sigma}")
     if not _gpu.is_device_array(intensities) and np.asarray(intensities).size == 0:
         return np.zeros_like(np.asarray(intensities), dtype=float)
-    t, np_dtype, was_numpy = _prepare(intensities, allow_bool=True)
+    t, np_dtype, was_numpy = _prepare(intensities, allow_bool=True, as_float=True)
     scale = _gpu.input_scale(np_dtype)
     torch = _gpu.torch_mod()
     parts = [t[i] for i in range(t.shape[0])] if _batched else [t]

@@ -102,9 +102,15 @@ class Pipeline:
     def _apply_on_device(self, intensities: np.ndarray, batched: bool):
         from . import _gpu
 
-        out: Any = _gpu.to_device(intensities)
-        for operation in self.operations:
-            out = operation.func(out, *operation.args, **operation.kwargs, _batched=batched)
+        # the first operation uploads the NumPy array itself (its own dtype rules: uint8 keeps its 1/255 scale, wide
+        # integers and bool are normalised); every intermediate then stays on the device
+        out: Any = intensities
+        _gpu._tls.keep_on_device = True
+        try:
+            for operation in self.operations:
+                out = operation.func(out, *operation.args, **operation.kwargs, _batched=batched)
+        finally:
+            _gpu._tls.keep_on_device = False
         return _gpu.to_host(out) if _gpu.is_device_array(out) else out
 
     # ------------------------------------------------------------------ call

@@ -42,7 +42,8 @@ typedef enum amt_dtype {
   AMT_U8 = 0,  /* also bool masks (0/1) */
   AMT_U16 = 1,
   AMT_I32 = 2,
-  AMT_F64 = 3
+  AMT_F64 = 3,
+  AMT_I64 = 4  /* host label masks of amt_executor_run_host only (the reference's mask dtype, masks.py:138) */
 } amt_dtype;
 
 int amt_version(void);
@@ -366,40 +367,67 @@ typedef struct amt_fov_config {
   int32_t max_label_value; /* largest value allowed in a given label mask */
   int32_t quantify_given_mask; /* 1: also clear_border + relabel + quantify the given mask */
   int32_t with_shape;          /* 1: also fill perimeter / area_convex (amt_region_shape) */
-  int32_t given_label_dtype;   /* amt_executor_run_host only: AMT_I32 (0 = default) or AMT_U16 host label
-                                  masks (Cellpose's own mask dtype below 65536 cells; halves their PCIe bytes) */
+  int32_t given_label_dtype;   /* amt_executor_run_host only: dtype of the host label masks.  AMT_I32 (0 = default),
+                                  AMT_I64 (what the reference hands SegmentationMask: model.py:215, masks.py:138;
+                                  copied as int64 and narrowed on the device) or AMT_U16 (Cellpose's own mask dtype
+                                  below 65536 cells; a quarter of the int64 PCIe bytes) */
   int32_t exact_all_channels;  /* 0 (default): scipy's exact operation order for the segmentation channel, whose
                                   plane decides the labels; the other channels, which only yield float planes,
-                                  run the Gaussians with fused multiply-adds (planes equal to scipy's to ~1e-15
-                                  relative, 1/3 fewer FP64 instructions).  1: exact order for every channel
+                                  take the faster filter named by plane_filter.  1: exact order for every channel
                                   (every preprocessed plane bit-identical to the reference's) */
   double low_sigma, high_sigma;  /* subtract_background_dog */
   double bg_percentile;
   double pct_lo, pct_hi;         /* rescale_by_percentile percentile_range */
   double out_lo, out_hi;         /* rescale_by_percentile out_range */
+  int32_t plane_filter;          /* how the channels that are NOT thresholded get their sigma_high Gaussian when
+                                    exact_all_channels == 0: AMT_FILTER_TENSOR_CORE (0, default) = tcgen05 integer
+                                    Toeplitz passes (amt_tcg_*; planes equal to scipy's to ~1e-10 of the [0, 1] scale)
+                                    whenever amt_tcg_supported(height, width, radius) and n_channels >= 2, else the
+                                    next mode; AMT_FILTER_FMA (1) = float64 with fused multiply-adds (~1e-15) */
+  int32_t reserved0;
 } amt_fov_config;
+#define AMT_FILTER_TENSOR_CORE 0
+#define AMT_FILTER_FMA 1
 
 /* half_w_*_host: NumPy-computed half kernels (radius+1 doubles each). */
 int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host, int r_lo,
                         const double* half_w_hi_host, int r_hi, amt_executor** out);
 void amt_executor_destroy(amt_executor* ex);
 size_t amt_executor_device_bytes(const amt_executor* ex);
+/* 1 if this executor filters the non-thresholded channels on the tensor cores (plane_filter resolved at creation). */
+int amt_executor_uses_tensor_cores(const amt_executor* ex);
+
+/* Per-FOV status bits (status[i] == 0: FOV i is complete and exact).  A field of view that trips one of these
+ * does not disturb the others of the batch (the reference maps its per-image loop the same way:
+ * model.py:276-288); counts_* always hold the TRUE number of cells, tables hold min(count, max_labels) columns. */
+#define AMT_FOV_THR_CAPACITY 1       /* threshold mask: more cells than max_labels, table truncated to the first max_labels */
+#define AMT_FOV_GIVEN_CAPACITY 2     /* given mask: idem */
+#define AMT_FOV_GIVEN_VALUE_RANGE 4  /* given mask holds a value > max_label_value (such pixels count as background) */
+#define AMT_FOV_THR_EMPTY 8          /* no cell left in the threshold mask after removing edge cells: the reference's
+                                        _process_mask raises ValueError here (masks.py:57-60) */
+#define AMT_FOV_GIVEN_EMPTY 16       /* idem for the given mask */
+#define AMT_FOV_CONSTANT_PLANE 32    /* the thresholded plane is constant: apply_threshold returns all-False
+                                        (operations.py:199-202) */
+#define AMT_FOV_GIVEN_NEGATIVE 64    /* int64 host mask with a negative value (SegmentationMask raises, masks.py:173-176);
+                                        such pixels count as background */
 
 /* Device-resident batch.  fovs: n_fov*C*H*W uint16; given_labels: n_fov*H*W int32 or NULL.
  * Outputs (device): tables_thr / tables_given: n_fov*AMT_TABLE_COLS(C)*max_labels float64;
  * counts_thr / counts_given: n_fov int32; thresholds: n_fov float64; labels_thr /
  * labels_given (optional, may be NULL): n_fov*H*W int32; preprocessed (optional):
- * n_fov*C*H*W float64.  Asynchronous on the executor's streams; amt_executor_sync waits. */
+ * n_fov*C*H*W float64; status (optional): n_fov int32 of AMT_FOV_* bits.
+ * Asynchronous on the executor's streams; amt_executor_sync waits. */
 int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_t* given_labels,
                             int64_t n_fov, double* tables_thr, int32_t* counts_thr,
                             double* tables_given, int32_t* counts_given, double* thresholds,
-                            int32_t* labels_thr, int32_t* labels_given, double* preprocessed);
+                            int32_t* labels_thr, int32_t* labels_given, double* preprocessed, int32_t* status);
 /* Host-fed batch: inputs and outputs are HOST pointers (pinned memory recommended; pageable
  * works but serialises).  Copies are double-buffered against compute on separate streams.
  * Synchronous: returns when every output byte is on the host. */
 int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const void* given_labels_host,
                           int64_t n_fov, double* tables_thr_host, int32_t* counts_thr_host,
-                          double* tables_given_host, int32_t* counts_given_host, double* thresholds_host);
+                          double* tables_given_host, int32_t* counts_given_host, double* thresholds_host,
+                          int32_t* status_host);
 int amt_executor_sync(amt_executor* ex);
 /* CUDA-event time (ms) of the last run_device / run_host call's device work. */
 float amt_executor_last_ms(amt_executor* ex);

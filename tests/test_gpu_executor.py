@@ -62,11 +62,17 @@ def check_table(ex, table, count, want, n_ch, ctx):
 # Tolerance of the preprocessed float planes of the channels that are NOT thresholded, in the executor's default
 # mode (fused multiply-adds there): 1e-12 of the plane's [0, 1] scale; the north star allows 1e-5 relative.
 CONTRACTED_PLANE_ATOL = 1e-12
+# ... and when their sigma = 16 Gaussian runs on the tensor cores (the default where the shape allows it: integer
+# Toeplitz products with 32-bit weights, csrc/tcgauss.cu): the Gaussian itself is within 2e-10 of scipy's on the
+# [0, 1] input scale (tests/test_gpu_tcgauss.py); the percentile rescale divides by p99 - p1 of the DoG plane
+# (~0.03 for these images), hence 1e-8 on the rescaled plane.  Measured: ~1e-10.
+TENSOR_CORE_PLANE_ATOL = 1e-8
 
 
-@pytest.mark.parametrize("exact_all", [False, True])
+@pytest.mark.parametrize("mode", ["tensor_core", "fma", "exact"])
 @pytest.mark.parametrize("shape,C,seg,bg", [((256, 256), 4, 1, 0.0), ((192, 320), 2, 0, 25.0), ((130, 100), 3, 2, 90.0)])
-def test_executor_matches_oracle(shape, C, seg, bg, exact_all):
+def test_executor_matches_oracle(shape, C, seg, bg, mode):
+    exact_all = mode == "exact"
     n_fov = 5
     fovs, givens = [], []
     for i in range(n_fov):
@@ -74,8 +80,12 @@ def test_executor_matches_oracle(shape, C, seg, bg, exact_all):
         fovs.append(f), givens.append(g)
     fovs, givens = np.stack(fovs), np.stack(givens)
     cfg = FovPipelineConfig(n_channels=C, height=shape[0], width=shape[1], seg_channel=seg, chunk_fovs=2, max_labels=512,
-                            max_label_value=int(givens.max()), bg_percentile=bg, exact_all_channels=exact_all)
+                            max_label_value=int(givens.max()), bg_percentile=bg, exact_all_channels=exact_all,
+                            plane_filter="fma" if mode == "fma" else "tensor_core")
     with FovBatchExecutor(cfg) as ex:
+        # the tensor-core path takes planes of at least 128 x 128 with a width that is a multiple of 16
+        tc = mode == "tensor_core" and shape[0] >= 128 and shape[1] >= 128 and shape[1] % 16 == 0
+        assert ex.uses_tensor_cores == tc
         out = ex.alloc_outputs(n_fov, labels=True, preprocessed=True)
         ms = ex.run_device(_gpu.to_device(fovs), _gpu.to_device(givens), out)
         assert ms > 0
@@ -98,7 +108,8 @@ def test_executor_matches_oracle(shape, C, seg, bg, exact_all):
         if exact_all:
             assert np.array_equal(host["preprocessed"][i], want["pre"]), f"preprocessed planes differ (fov {i})"
         else:
-            assert np.max(np.abs(host["preprocessed"][i] - want["pre"])) <= CONTRACTED_PLANE_ATOL, f"fov {i}"
+            err = np.max(np.abs(host["preprocessed"][i] - want["pre"]))
+            assert err <= (TENSOR_CORE_PLANE_ATOL if tc else CONTRACTED_PLANE_ATOL), f"fov {i}: {err:.3e}"
         assert np.array_equal(host["labels_thr"][i], want["labels_thr"]), f"threshold labels differ (fov {i})"
         assert np.array_equal(host["labels_given"][i], want["labels_given"]), f"given labels differ (fov {i})"
         assert host["counts_thr"][i] == want["labels_thr"].max() and host["counts_given"][i] == want["labels_given"].max()
@@ -186,8 +197,9 @@ def test_executor_full_size_properties():
             assert np.array_equal(strict[f"tables_{which}"][i][:, :kk], host[f"tables_{which}"][i][:, :kk], equal_nan=True)
 
 
-def test_run_host_uint16_label_masks_match_int32():
-    """Host label masks may travel as uint16 (Cellpose's mask dtype): same tables, half the PCIe bytes."""
+def test_run_host_label_mask_dtypes_match():
+    """Host label masks may travel as int64 (the reference's dtype at this boundary, ref: masks.py:138), int32 or
+    uint16 (Cellpose's mask dtype): same tables; a dtype other than the configured one is a TypeError."""
     n_fov, C, shape = 3, 2, (128, 160)
     fovs, givens = [], []
     for i in range(n_fov):
@@ -195,17 +207,67 @@ def test_run_host_uint16_label_masks_match_int32():
         fovs.append(f), givens.append(g)
     fovs, givens = np.stack(fovs), np.stack(givens).astype(np.int32)
     outs = []
-    for dt in (np.int32, np.uint16):
+    for dt in (np.int32, np.uint16, np.int64):
         cfg = FovPipelineConfig(n_channels=C, height=shape[0], width=shape[1], seg_channel=1, chunk_fovs=2, max_labels=256,
                                 max_label_value=int(givens.max()), given_label_dtype=dt)
         with FovBatchExecutor(cfg) as ex:
             outs.append(ex.run_host(fovs, givens.astype(dt)))
             with pytest.raises(TypeError):
-                ex.run_host(fovs, givens.astype(np.int64))
-    assert np.array_equal(outs[0]["counts_given"], outs[1]["counts_given"]) and outs[0]["counts_given"].min() > 0
-    for i in range(n_fov):
-        cnt = int(outs[0]["counts_given"][i])
-        assert np.array_equal(outs[0]["tables_given"][i][:, :cnt], outs[1]["tables_given"][i][:, :cnt], equal_nan=True)
+                ex.run_host(fovs, givens.astype(np.int16))
+    assert outs[0]["counts_given"].min() > 0
+    for other in outs[1:]:
+        assert np.array_equal(outs[0]["counts_given"], other["counts_given"])
+        assert not other["status"].any()
+        for i in range(n_fov):
+            cnt = int(outs[0]["counts_given"][i])
+            assert np.array_equal(outs[0]["tables_given"][i][:, :cnt], other["tables_given"][i][:, :cnt], equal_nan=True)
+
+
+def test_status_isolates_a_field_of_view_that_overflows():
+    """SURVEY 5 / ref: model.py:276-288: a bad field of view must not poison its batch.  FOV 1 is speckle whose
+    threshold mask has more components than max_labels; FOV 2's given mask holds a value above max_label_value and
+    a negative one; FOV 3 is constant.  FOVs 0 and 4 come back exactly as when processed alone."""
+    from arcadia_microscopy_tools_b200 import _lib
+    from arcadia_microscopy_tools_b200.batch import FovCapacityError
+
+    C, shape, cells = 2, (128, 160), 20
+    rng = np.random.default_rng(5)
+    fovs, givens = [], []
+    for i in range(5):
+        f, g, _ = make_fov(4000 + i, C, shape[0], shape[1], cells)
+        fovs.append(f), givens.append(g.astype(np.int64))
+    fovs, givens = np.stack(fovs), np.stack(givens)
+    fovs[1, 0] = np.where(rng.random(shape) < 0.08, 40000, 300).astype(np.uint16)  # isolated bright pixels
+    givens[2, 40, 40] = 70000
+    givens[2, 41, 41] = -3
+    fovs[3] = 500
+    cfg = FovPipelineConfig(n_channels=C, height=shape[0], width=shape[1], seg_channel=0, chunk_fovs=2, max_labels=64,
+                            max_label_value=cells + 5, given_label_dtype=np.int64)
+    with FovBatchExecutor(cfg) as ex:
+        with pytest.raises(FovCapacityError) as err:
+            ex.run_host(fovs, givens)
+        assert set(err.value.fovs) == {1, 2}
+        out = ex.run_host(fovs, givens, on_error="status")
+        st = out["status"]
+        assert st[1] & _lib.AMT_FOV_THR_CAPACITY and out["counts_thr"][1] > cfg.max_labels
+        assert st[2] & _lib.AMT_FOV_GIVEN_VALUE_RANGE and st[2] & _lib.AMT_FOV_GIVEN_NEGATIVE
+        assert st[3] & _lib.AMT_FOV_CONSTANT_PLANE and st[3] & _lib.AMT_FOV_THR_EMPTY and out["counts_thr"][3] == 0
+        assert st[0] == 0 and st[4] == 0
+        with pytest.raises(FovCapacityError):
+            ex.table_to_properties(out["tables_thr"][1], int(out["counts_thr"][1]), NAMES[:C])
+        for i in (0, 4):
+            alone = ex.run_host(fovs[i : i + 1], givens[i : i + 1])
+            for which in ("thr", "given"):
+                k = int(alone[f"counts_{which}"][0])
+                assert k == out[f"counts_{which}"][i] and k > 0
+                assert np.array_equal(alone[f"tables_{which}"][0][:, :k], out[f"tables_{which}"][i][:, :k], equal_nan=True)
+        # the device-resident entry point reports the same bits
+        dev_out = ex.alloc_outputs(5)
+        ex.run_device(_gpu.to_device(fovs), _gpu.to_device(np.clip(givens, 0, 2**31 - 1).astype(np.int32)), dev_out)
+        dst = _gpu.to_host(dev_out["status"])
+        assert dst[1] == st[1] and dst[3] == st[3] and dst[2] == _lib.AMT_FOV_GIVEN_VALUE_RANGE and not dst[0] and not dst[4]
+        with pytest.raises(FovCapacityError):
+            ex.check_status(dev_out)
 
 
 def test_run_host_from_library_pinned_staging():

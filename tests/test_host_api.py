@@ -209,7 +209,7 @@ def test_shared_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert lib.amt_version() >= 100
     assert lib.amt_strerror(_lib.AMT_ERR_CAPACITY) == b"capacity exceeded"
-    assert ctypes.sizeof(_lib.MapParams) == 64 and ctypes.sizeof(_lib.FovConfig) == 104
+    assert ctypes.sizeof(_lib.MapParams) == 64 and ctypes.sizeof(_lib.FovConfig) == 112
 
 
 def test_compute_entry_points_fail_loudly_without_a_gpu():
