@@ -356,12 +356,12 @@ def otsu_threshold(x2d, mm=None):
     return thr, mm
 
 
-def plane_histograms(x2d, mm=None):
+def plane_histograms(x2d, mm=None, nbins: int = 256):
     """The histogram skimage's histogram-based thresholds start from, per plane, on the device:
-    float64 planes -> 256 uniform bins over [min, max] (np.histogram semantics, ``amt_hist256_f64``),
-    uint16 planes -> exact per-value counts (``amt_hist_u16``).  Returns ``[(counts int64, centers)]``
-    on the host: the scalar scans over these <= 65536 bins are the host-side plan step (NumPy, in
-    skimage's own dtypes); every per-pixel pass stays on the GPU."""
+    float64 planes -> ``nbins`` uniform bins over [min, max] (np.histogram semantics: ``amt_hist256_f64`` for the
+    default 256, ``amt_hist_f64`` otherwise), uint16 planes -> exact per-value counts (``amt_hist_u16``; skimage
+    ignores nbins for integer images).  Returns ``[(counts int64, centers)]`` on the host: the scalar scans over
+    these bins are the host-side plan step (NumPy, in skimage's own dtypes); every per-pixel pass stays on the GPU."""
     torch = torch_mod()
     lib = _lib.load()
     n_img, n = x2d.shape
@@ -369,15 +369,22 @@ def plane_histograms(x2d, mm=None):
         mm = minmax_keys(x2d)
     out = []
     if dtype_code(x2d) == AMT_F64:
-        hist = torch.empty((n_img, 256), dtype=torch.int32, device=x2d.device)
-        check(lib.amt_hist256_f64(ptr(x2d), n_img, n, ptr(mm), ptr(hist), stream_ptr()), "amt_hist256_f64")
-        h = to_host(hist).astype(np.int64)
         mnmx = minmax_values(mm, True)
+        all_edges = []
         for i in range(n_img):
             first, last = float(mnmx[i, 0]), float(mnmx[i, 1])
             if first == last:
                 first, last = first - 0.5, last + 0.5
-            edges = np.linspace(first, last, 257, endpoint=True, dtype=np.float64)
+            all_edges.append(np.linspace(first, last, nbins + 1, endpoint=True, dtype=np.float64))
+        hist = torch.empty((n_img, nbins), dtype=torch.int32, device=x2d.device)
+        if nbins == 256:
+            check(lib.amt_hist256_f64(ptr(x2d), n_img, n, ptr(mm), ptr(hist), stream_ptr()), "amt_hist256_f64")
+        else:
+            d_edges = torch.from_numpy(np.stack(all_edges)).to(x2d.device)
+            check(lib.amt_hist_f64(ptr(x2d), n_img, n, ptr(d_edges), nbins, ptr(hist), stream_ptr()), "amt_hist_f64")
+        h = to_host(hist).astype(np.int64)
+        for i in range(n_img):
+            edges = all_edges[i]
             out.append((h[i], (edges[:-1] + edges[1:]) / 2.0))
     else:
         hist = torch.empty((n_img, 65536), dtype=torch.int32, device=x2d.device)
@@ -388,6 +395,19 @@ def plane_histograms(x2d, mm=None):
             lo, hi = int(mnmx[i, 0]), int(mnmx[i, 1])
             out.append((h[i, lo : hi + 1], np.arange(lo, hi + 1)))
     return out
+
+
+def plane_sums_f64(x2d) -> np.ndarray:
+    """``np.sum`` of every contiguous float64 plane in NumPy's pairwise order, bit for bit (``amt_pairwise_sum_f64``)."""
+    torch = torch_mod()
+    lib = _lib.load()
+    n_img, n = x2d.shape
+    x2d = x2d.contiguous()
+    nbytes = lib.amt_pairwise_sum_scratch_bytes(n_img, n)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x2d.device)
+    out = torch.empty(n_img, dtype=torch.float64, device=x2d.device)
+    check(lib.amt_pairwise_sum_f64(ptr(x2d), n_img, n, ptr(out), ptr(scratch), nbytes, stream_ptr()), "amt_pairwise_sum_f64")
+    return to_host(out)
 
 
 def plane_sums_u16(x2d) -> np.ndarray:

@@ -23,6 +23,8 @@ AMT_U8, AMT_U16, AMT_I32, AMT_F64, AMT_I64 = 0, 1, 2, 3, 4
 AMT_MAX_RANKS = 8
 AMT_EXTEND_NEAREST, AMT_EXTEND_REFLECT = 0, 1  # amt_gaussian_axis_mode
 AMT_FILTER_TENSOR_CORE, AMT_FILTER_FMA = 0, 1  # amt_fov_config.plane_filter
+STAGE_NAMES = ("dog_exact", "dog_lo", "dog_tc_axis0", "dog_tc_axis1", "select", "map", "label_thr", "regions_thr",
+               "label_given", "regions_given")  # AMT_STAGE_*
 # per-FOV status bits of the executor (include/amt_b200.h)
 AMT_FOV_THR_CAPACITY, AMT_FOV_GIVEN_CAPACITY, AMT_FOV_GIVEN_VALUE_RANGE = 1, 2, 4
 AMT_FOV_THR_EMPTY, AMT_FOV_GIVEN_EMPTY, AMT_FOV_CONSTANT_PLANE, AMT_FOV_GIVEN_NEGATIVE = 8, 16, 32, 64
@@ -164,8 +166,13 @@ SIGNATURES: dict[str, tuple] = {
     "amt_outline_trace_find": (_i, [_p, _i64, _i64, _i64, _p, _p]),
     "amt_outline_trace_write": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "amt_executor_create": (_i, [C.POINTER(FovConfig), C.POINTER(_d), _i, C.POINTER(_d), _i, C.POINTER(_p)]),
+    "amt_hist_f64": (_i, [_p, _i64, _i64, _p, _i, _p, _p]),
+    "amt_pairwise_sum_scratch_bytes": (_sz, [_i64, _i64]),
+    "amt_pairwise_sum_f64": (_i, [_p, _i64, _i64, _p, _p, _sz, _p]),
     "amt_executor_destroy": (None, [_p]),
     "amt_executor_uses_tensor_cores": (_i, [_p]),
+    "amt_executor_set_profiling": (_i, [_p, _i]),
+    "amt_executor_stage_ms": (_i, [_p, _p, C.POINTER(_i64)]),
     "amt_executor_device_bytes": (_sz, [_p]),
     "amt_executor_run_device": (_i, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "amt_executor_run_host": (_i, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),

@@ -203,6 +203,17 @@ class FovBatchExecutor:
         check(self._lib.amt_executor_sync(self._handle), "amt_executor_sync")
         return float(self._lib.amt_executor_last_ms(self._handle))
 
+    def set_profiling(self, enable: bool) -> None:
+        """Per-stage CUDA-event timing of the runs that follow (``stage_ms``); zeroes the counters."""
+        check(self._lib.amt_executor_set_profiling(self._handle, 1 if enable else 0), "amt_executor_set_profiling")
+
+    def stage_ms(self) -> tuple[dict[str, float], int]:
+        """(milliseconds per stage summed over the profiled chunks, number of chunks)."""
+        ms = (C.c_double * len(_lib.STAGE_NAMES))()
+        n = C.c_int64(0)
+        check(self._lib.amt_executor_stage_ms(self._handle, ms, C.byref(n)), "amt_executor_stage_ms")
+        return {name: float(ms[i]) for i, name in enumerate(_lib.STAGE_NAMES)}, int(n.value)
+
     def check_status(self, outputs: dict) -> None:
         """After a synchronised ``run_device``: raise ``FovCapacityError`` if a FOV dropped data (one small D2H)."""
         if outputs.get("status") is not None:
@@ -272,3 +283,51 @@ class FovBatchExecutor:
                 col = col.astype(np.uint64)
             out[name] = col
         return out
+
+
+# ---------------------------------------------------------------------------------------------- plates
+def fov_record(out: dict, j: int, n_cols_used: int | None = None) -> dict:
+    """One FOV's results cut out of a batch's host outputs: counts, threshold, status and the table columns that
+    are filled (``min(count, max_labels)`` cells) — what crosses ranks when a plate is gathered."""
+    rec = {"threshold": float(out["thresholds"][j]), "status": int(out["status"][j]) if "status" in out else 0}
+    for which in ("thr", "given"):
+        cnt = int(out[f"counts_{which}"][j])
+        tab = out[f"tables_{which}"][j]
+        rec[f"count_{which}"] = cnt
+        rec[f"table_{which}"] = np.array(tab[:, : min(cnt, tab.shape[1])], copy=True)
+    return rec
+
+
+def run_plate(fov_source, n_fov: int, config: FovPipelineConfig, dist=None, device: int | None = None,
+              batch_fovs: int = 32, process_batch=None, dst: int = 0):
+    """A whole plate (BASELINE config 5: wells x FOVs), sharded by field of view across the ranks of an initialised
+    ``torch.distributed`` group: FOV i belongs to rank ``i mod world`` (the reference's analogue is
+    the per-axis fan-out of ``pipeline.py:139-149``).  No data-path collective: every rank feeds its own FOVs
+    through its own executor (``run_host`` in batches of ``batch_fovs``), then the per-FOV records
+    (``fov_record``) are gathered on ``dst`` in FOV order.  Returns the list on ``dst``, None elsewhere.
+
+    ``fov_source(i) -> (fov uint16 (C, H, W), given labels (H, W) of config.given_label_dtype or None)``.
+    ``process_batch(fovs, givens) -> host output dict`` replaces the executor (CPU tests of the sharding logic)."""
+    from .sharding import gather_fov_results, shard_indices
+
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    mine = shard_indices(n_fov, rank, world)
+    executor = None
+    if process_batch is None:
+        executor = FovBatchExecutor(config, device=device)
+        process_batch = lambda f, g: executor.run_host(f, g, on_error="status")  # noqa: E731
+    local: dict[int, dict] = {}
+    try:
+        for b0 in range(0, len(mine), batch_fovs):
+            idx = mine[b0 : b0 + batch_fovs]
+            items = [fov_source(int(i)) for i in idx]
+            fovs = np.ascontiguousarray(np.stack([it[0] for it in items]))
+            givens = None if items[0][1] is None else np.ascontiguousarray(np.stack([it[1] for it in items]))
+            out = process_batch(fovs, givens)
+            for j, i in enumerate(idx):
+                local[int(i)] = fov_record(out, j) | {"rank": rank}
+    finally:
+        if executor is not None:
+            executor.close()
+    return gather_fov_results(local, n_fov, dist, dst=dst)

@@ -406,6 +406,8 @@ extern int g_exec_swap_prio;  // executor.cu
 extern int g_pass_ctas;       // core.cu
 extern int g_exec_buckets;    // executor.cu
 extern int g_exec_tc;         // executor.cu
+extern int g_exec_copy_only;  // executor.cu
+static int g_dog_only_exact = 0;  // amt_tune: the stand-alone axis0 / axis1 entry points cover the exact planes only
 namespace tc { extern int g_tcg_debug; }  // tcgauss.cu
 
 constexpr size_t kSmemMax = 227 * 1024;
@@ -581,6 +583,10 @@ int amt_tune(const char* key, int value) {
     g_exec_buckets = value != 0;
   } else if (is("tcg_debug")) {
     tc::g_tcg_debug = value;
+  } else if (is("exec_copy_only")) {
+    g_exec_copy_only = value != 0;
+  } else if (is("dog_only_exact")) {
+    g_dog_only_exact = value != 0;
   } else if (is("exec_tc")) {
     g_exec_tc = value != 0;
   } else if (is("pass_ctas")) {
@@ -623,7 +629,8 @@ int amt_dog2d_axis0(const void* in, int in_dtype, double in_scale, int64_t n_img
   const DogPlan p = dog_plan(in_dtype, n_img, h, w, r_lo, r_hi);
   if (p.fast && !(aligned16(in) && aligned16(tmp_lo) && aligned16(tmp_hi))) return AMT_ERR_INVALID;
   return dog_axis0(p, in, in_dtype, in_scale, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, tmp_lo, tmp_hi,
-                   as_stream(stream), DogMix{g_dog_exact_every, g_dog_exact_every > 0 ? g_dog_exact_offset % g_dog_exact_every : 0, false});
+                   as_stream(stream), DogMix{g_dog_exact_every, g_dog_exact_every > 0 ? g_dog_exact_offset % g_dog_exact_every : 0,
+                          g_dog_only_exact && g_dog_exact_every > 0 && n_img % g_dog_exact_every == 0});
 }
 
 int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int64_t n_img, int64_t h, int64_t w,
@@ -635,7 +642,8 @@ int amt_dog2d_axis1(const double* tmp_lo, const double* tmp_hi, double* out, int
   if (p.fast && !(aligned16(out) && aligned16(tmp_lo) && aligned16(tmp_hi))) return AMT_ERR_INVALID;
   if (minmax_keys) AMT_TRY(minmax_init(minmax_keys, n_img, as_stream(stream)));
   return dog_axis1(p, tmp_lo, tmp_hi, out, n_img, h, w, half_w_lo, r_lo, half_w_hi, r_hi, minmax_keys, nullptr,
-                   as_stream(stream), DogMix{g_dog_exact_every, g_dog_exact_every > 0 ? g_dog_exact_offset % g_dog_exact_every : 0, false});
+                   as_stream(stream), DogMix{g_dog_exact_every, g_dog_exact_every > 0 ? g_dog_exact_offset % g_dog_exact_every : 0,
+                          g_dog_only_exact && g_dog_exact_every > 0 && n_img % g_dog_exact_every == 0});
 }
 
 }  // extern "C"

@@ -71,6 +71,12 @@ struct amt_executor {
   bool trace;
   std::vector<cudaEvent_t>* trace_events;
   std::vector<const char*>* trace_names;
+  // amt_executor_set_profiling: an event after every stage; per-stage device milliseconds of the last run
+  bool profile;
+  std::vector<int>* trace_stage;   // stage id each event closes (-1: a "begin" mark), same order as trace_events
+  std::vector<int>* trace_stream;  // 0 = s_dog, 1 = s_compute
+  double stage_ms[AMT_N_STAGES];
+  int64_t profiled_chunks;
 };
 
 namespace amt {
@@ -83,6 +89,9 @@ int g_exec_swap_prio = 1;
 int g_exec_buckets = 1;
 // amt_tune "exec_tc": 0 switches the tensor-core path off in executors that have one (A/B timing in one process)
 int g_exec_tc = 1;
+// amt_tune "exec_copy_only": 1 = amt_executor_run_host performs every H2D / D2H copy of a batch with the same staging,
+// streams and events but launches no kernel: the copy-only ceiling the host-fed path is measured against
+int g_exec_copy_only = 0;
 int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st);  // gauss.cu
 
 static int dmalloc(amt_executor* ex, void** p, size_t bytes) {
@@ -91,26 +100,46 @@ static int dmalloc(amt_executor* ex, void** p, size_t bytes) {
   return AMT_OK;
 }
 
-static void trace_mark(amt_executor* ex, cudaStream_t st, const char* name) {
-  if (!ex->trace) return;
+// stage: the AMT_STAGE_* id whose work this mark closes, or -1 for a mark that only opens a stream's timeline
+static void trace_mark(amt_executor* ex, cudaStream_t st, const char* name, int stage = -1) {
+  if (!ex->trace && !ex->profile) return;
   cudaEvent_t e;
   if (cudaEventCreate(&e) != cudaSuccess) return;
   cudaEventRecord(e, st);
   ex->trace_events->push_back(e);
   ex->trace_names->push_back(name);
+  ex->trace_stage->push_back(stage);
+  ex->trace_stream->push_back(st == ex->s_dog ? 0 : 1);
 }
 
 static void trace_dump(amt_executor* ex) {
-  if (!ex->trace) return;
+  if (!ex->trace && !ex->profile) return;
   cudaDeviceSynchronize();
+  if (ex->profile) {
+    // a stage lasts from the previous mark on ITS stream to its own mark
+    int last[2] = {-1, -1};
+    for (size_t i = 0; i < ex->trace_events->size(); ++i) {
+      const int sid = (*ex->trace_stream)[i], stage = (*ex->trace_stage)[i];
+      if (stage >= 0 && last[sid] >= 0) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, (*ex->trace_events)[last[sid]], (*ex->trace_events)[i]) == cudaSuccess)
+          ex->stage_ms[stage] += ms;
+      }
+      last[sid] = (int)i;
+    }
+  }
   for (size_t i = 0; i < ex->trace_events->size(); ++i) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ex->ev_start, (*ex->trace_events)[i]);
-    std::fprintf(stderr, "amt-trace %9.3f ms  %s\n", ms, (*ex->trace_names)[i]);
+    if (ex->trace) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ex->ev_start, (*ex->trace_events)[i]);
+      std::fprintf(stderr, "amt-trace %9.3f ms  %s\n", ms, (*ex->trace_names)[i]);
+    }
     cudaEventDestroy((*ex->trace_events)[i]);
   }
   ex->trace_events->clear();
   ex->trace_names->clear();
+  ex->trace_stage->clear();
+  ex->trace_stream->clear();
 }
 
 static void rank_pair(int64_t n, double q, int64_t* lo, int64_t* hi, double* gamma) {
@@ -143,13 +172,15 @@ static int enqueue_dog(amt_executor* ex, const uint16_t* in, int g, cudaEvent_t 
     AMT_TRY(dog2d(in, AMT_U16, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, ex->hw_lo, ex->r_lo, ex->hw_hi,
                   ex->r_hi, ex->tmp_lo, ex->tmp_hi, ex->mm[slot], ex->s_dog, bk, &ex->buckets_valid[slot], c.n_channels,
                   c.seg_channel, true));
-    trace_mark(ex, ex->s_dog, "dog: exact planes done");
+    trace_mark(ex, ex->s_dog, "dog: exact planes done", AMT_STAGE_DOG_EXACT);
     AMT_TRY(tc::lo2d(in, 1.0 / 65535.0, ex->tmp_lo, planes, c.height, c.width, ex->hw_lo, ex->r_lo, sel, ex->s_dog));
+    trace_mark(ex, ex->s_dog, "dog: narrow Gaussian done", AMT_STAGE_DOG_LO);
     AMT_TRY(tc::tcg_axis0(ex->tcg, in, planes, c.height, c.width, ex->digits, sel, ex->s_dog));
+    trace_mark(ex, ex->s_dog, "dog: tensor-core axis 0 done", AMT_STAGE_DOG_TC0);
     AMT_TRY(tc::tcg_axis1(ex->tcg, ex->digits, ex->tmp_lo, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, bk,
                           ex->mm[slot], sel, ex->s_dog));
     AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_done[slot], ex->s_dog));
-    trace_mark(ex, ex->s_dog, "dog: end");
+    trace_mark(ex, ex->s_dog, "dog: end", AMT_STAGE_DOG_TC1);
     return AMT_OK;
   }
   AMT_TRY(dog2d(in, AMT_U16, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, ex->hw_lo, ex->r_lo, ex->hw_hi,
@@ -159,7 +190,7 @@ static int enqueue_dog(amt_executor* ex, const uint16_t* in, int g, cudaEvent_t 
                 // channels yield float planes only and take the contracted filter unless the caller asks otherwise
                 (c.exact_all_channels || c.n_channels < 2) ? 0 : c.n_channels, c.seg_channel));
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_done[slot], ex->s_dog));
-  trace_mark(ex, ex->s_dog, "dog: end");
+  trace_mark(ex, ex->s_dog, "dog: end", AMT_STAGE_DOG_EXACT);
   return AMT_OK;
 }
 
@@ -208,27 +239,27 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
                                 ex->sel_bytes, st));
   else
     AMT_TRY(amt_select_f64(dog, planes, HW, ex->ranks, 6, mm, ex->stats, ex->sel_scratch, ex->sel_bytes, st));
-  trace_mark(ex, st, "  rest: select done");
+  trace_mark(ex, st, "  rest: select done", AMT_STAGE_SELECT);
   AMT_TRY(plan_dog_rescale(ex->stats, mm, planes, ex->g_bg, ex->g_lo, ex->g_hi, c.out_lo, c.out_hi, ex->params, st));
   AMT_CUDA_TRY(cudaMemsetAsync(ex->hist256, 0, (size_t)g * 256 * sizeof(uint32_t), st));
   AMT_TRY(map_launch(dog, AMT_F64, pre, planes, HW, ex->params, ex->hist256, C, c.seg_channel, st));
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_free[slot], st));
-  trace_mark(ex, st, "  rest: map done");
+  trace_mark(ex, st, "  rest: map done", AMT_STAGE_MAP);
   // stage B: Otsu -> threshold + CCL + clear_border
   AMT_TRY(otsu_launch(ex->hist256, 0, ex->params, C, c.seg_channel, nullptr, g, thr, nullptr, 0, st));
   AMT_TRY(label_launch(pre + (int64_t)c.seg_channel * HW, 1, (int64_t)C * HW, thr, 0, g, H, W, 1, lab_thr, cnt_thr,
                        ex->label_scratch, ex->label_bytes, st));
-  trace_mark(ex, st, "  rest: otsu+label(thr) done");
+  trace_mark(ex, st, "  rest: otsu+label(thr) done", AMT_STAGE_LABEL_THR);
   // stage C: per-cell tables over the raw channels
   AMT_TRY(region_reduce(lab_thr, in, C, (int64_t)C * HW, HW, g, H, W, c.max_labels, ex->acc, st));
   AMT_TRY(region_finalize(ex->acc, cnt_thr, C, g, c.max_labels, tab_thr, st));
   if (c.with_shape)
     AMT_TRY(region_shape(lab_thr, ex->acc, C, cnt_thr, g, H, W, c.max_labels, tab_thr, ex->shape_scratch, ex->shape_bytes, st));
-  trace_mark(ex, st, "  rest: regions(thr) done");
+  trace_mark(ex, st, "  rest: regions(thr) done", AMT_STAGE_REGIONS_THR);
   if (c.quantify_given_mask && given) {
     AMT_TRY(label_launch(given, 2, HW, nullptr, c.max_label_value, g, H, W, 1, lab_given, cnt_given, ex->label_scratch,
                          ex->label_bytes, st, flags));
-    trace_mark(ex, st, "  rest: label(given) done");
+    trace_mark(ex, st, "  rest: label(given) done", AMT_STAGE_LABEL_GIVEN);
     AMT_TRY(region_reduce(lab_given, in, C, (int64_t)C * HW, HW, g, H, W, c.max_labels, ex->acc, st));
     AMT_TRY(region_finalize(ex->acc, cnt_given, C, g, c.max_labels, tab_given, st));
     if (c.with_shape)
@@ -242,7 +273,8 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
                                                                    c.max_labels, g, status);
     AMT_LAUNCH_CHECK();
   }
-  trace_mark(ex, st, "  rest: end");
+  trace_mark(ex, st, "  rest: end", AMT_STAGE_REGIONS_GIVEN);
+  if (ex->profile) ex->profiled_chunks += 1;
   ex->chunks_issued += 1;
   return AMT_OK;
 }
@@ -329,6 +361,8 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
   ex->trace = std::getenv("AMT_TRACE") != nullptr;
   ex->trace_events = new std::vector<cudaEvent_t>();
   ex->trace_names = new std::vector<const char*>();
+  ex->trace_stage = new std::vector<int>();
+  ex->trace_stream = new std::vector<int>();
   const int C = cfg->n_channels;
   const int64_t HW = (int64_t)cfg->height * cfg->width;
   const int64_t planes = (int64_t)cfg->chunk_fovs * C;
@@ -446,11 +480,28 @@ void amt_executor_destroy(amt_executor* ex) {
   if (ex->s_out) cudaStreamDestroy(ex->s_out);
   delete ex->trace_events;
   delete ex->trace_names;
+  delete ex->trace_stage;
+  delete ex->trace_stream;
   delete ex;
 }
 
 size_t amt_executor_device_bytes(const amt_executor* ex) { return ex ? ex->device_bytes : 0; }
 int amt_executor_uses_tensor_cores(const amt_executor* ex) { return ex && ex->tcg != nullptr ? 1 : 0; }
+
+int amt_executor_set_profiling(amt_executor* ex, int enable) {
+  if (!ex) return AMT_ERR_INVALID;
+  ex->profile = enable != 0;
+  for (int i = 0; i < AMT_N_STAGES; ++i) ex->stage_ms[i] = 0.0;
+  ex->profiled_chunks = 0;
+  return AMT_OK;
+}
+
+int amt_executor_stage_ms(const amt_executor* ex, double* stage_ms, int64_t* n_chunks) {
+  if (!ex || !stage_ms) return AMT_ERR_INVALID;
+  for (int i = 0; i < AMT_N_STAGES; ++i) stage_ms[i] = ex->stage_ms[i];
+  if (n_chunks) *n_chunks = ex->profiled_chunks;
+  return AMT_OK;
+}
 
 int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_t* given_labels, int64_t n_fov,
                             double* tables_thr, int32_t* counts_thr, double* tables_given, int32_t* counts_given,
@@ -529,10 +580,12 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const voi
     // output slot s is free once its previous D2H has finished
     AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_compute, ex->ev_in[s], 0));
     if (chunk >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_compute, ex->ev_out[s], 0));
-    AMT_TRY(enqueue_dog(ex, ex->in_slot[s], g, ex->ev_in[s]));
-    AMT_TRY(process_chunk(ex, ex->in_slot[s], given ? ex->given_slot[s] : nullptr, g, ex->tab_thr_slot[s],
-                          ex->cnt_thr_slot[s], ex->tab_given_slot[s], ex->cnt_given_slot[s], ex->thr_slot[s], nullptr,
-                          nullptr, nullptr, ex->flag_slot[s], ex->status_slot[s]));
+    if (!g_exec_copy_only) {
+      AMT_TRY(enqueue_dog(ex, ex->in_slot[s], g, ex->ev_in[s]));
+      AMT_TRY(process_chunk(ex, ex->in_slot[s], given ? ex->given_slot[s] : nullptr, g, ex->tab_thr_slot[s],
+                            ex->cnt_thr_slot[s], ex->tab_given_slot[s], ex->cnt_given_slot[s], ex->thr_slot[s], nullptr,
+                            nullptr, nullptr, ex->flag_slot[s], ex->status_slot[s]));
+    }
     AMT_CUDA_TRY(cudaEventRecord(ex->ev_done[s], ex->s_compute));
     AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_out, ex->ev_done[s], 0));
     AMT_CUDA_TRY(cudaMemcpyAsync(tables_thr_host + f0 * tab, ex->tab_thr_slot[s], (size_t)g * tab * sizeof(double),

@@ -673,8 +673,13 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
 #pragma unroll
         for (int n = 0; n < 16; ++n) {
           if (n < rows) {
-            op[(int64_t)n * p.w] = res[n];
-            if (bp != nullptr) bp[(int64_t)n * p.w] = (uint16_t)bucket12(res[n]);
+            if (p.dbg & 64) {  // timing experiment: streaming (evict-first) stores
+              __stcs(op + (int64_t)n * p.w, res[n]);
+              if (bp != nullptr) __stcs(bp + (int64_t)n * p.w, (unsigned short)bucket12(res[n]));
+            } else {
+              op[(int64_t)n * p.w] = res[n];
+              if (bp != nullptr) bp[(int64_t)n * p.w] = (uint16_t)bucket12(res[n]);
+            }
             vmin = res[n] < vmin ? res[n] : vmin;
             vmax = res[n] > vmax ? res[n] : vmax;
           }

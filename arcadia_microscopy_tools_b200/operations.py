@@ -387,9 +387,9 @@ def _check_threshold_kwargs(method: str, kwargs: dict):
     for name in kwargs:
         if name not in _THRESHOLD_KWARGS[method]:
             raise TypeError(f"threshold_{method}() got an unexpected keyword argument '{name}'")
-    if kwargs.get("nbins", 256) != 256:
-        raise NotImplementedError("nbins other than 256 (scikit-image's default) is not built on the B200 path; "
-                                  "integer images ignore nbins anyway")
+    nbins = kwargs.get("nbins", 256)
+    if not (isinstance(nbins, (int, np.integer)) and 2 <= nbins <= 1 << 20):
+        raise ValueError(f"nbins must be an integer between 2 and 2**20, got {nbins!r}")
 
 
 def _otsu_from_histogram(counts: np.ndarray, centers: np.ndarray):
@@ -428,12 +428,22 @@ def _apply_histogram_threshold(intensities, method: str, batched: bool, kwargs: 
     t, np_dtype, was_numpy = _prepare(intensities)
     planes = _slices(t, batched)
     integer_image = np_dtype.kind in "iu" and planes.dtype != _gpu.torch_mod().float64
-    if method in ("mean", "li") and not integer_image:
+    if method == "li" and not integer_image:
         raise NotImplementedError(
-            f"method '{method}' is implemented for uint8 / uint16 images only (scikit-image sums the float "
-            "pixels themselves there, in NumPy's pairwise order, which is not reproduced on the GPU)")
-    hists = _gpu.plane_histograms(planes)
+            "method 'li' is implemented for uint8 / uint16 images only (on float images scikit-image iterates over "
+            "means of the thresholded pixels themselves and takes its tolerance from the sorted unique values; "
+            "neither is built on the GPU)")
     thr = np.empty(planes.shape[0], dtype=np.float64)
+    if method == "mean" and not integer_image:
+        # np.mean(image): NumPy's pairwise float64 sum, reproduced bit for bit on the device, / n
+        limits = _gpu.minmax_values(_gpu.minmax_keys(planes), True)
+        sums = _gpu.plane_sums_f64(planes)
+        for i in range(planes.shape[0]):
+            thr[i] = limits[i, 0] if limits[i, 0] == limits[i, 1] else float(np.float64(sums[i]) / np.float64(planes.shape[1]))
+        d_thr = _gpu.torch_mod().from_numpy(thr).to(planes.device)
+        mask = _gpu.threshold_gt(planes, d_thr).reshape(t.shape).view(_gpu.torch_mod().bool)
+        return _finish(mask, was_numpy)
+    hists = _gpu.plane_histograms(planes, nbins=int(kwargs.get("nbins", 256)))
     for i, (counts, centers) in enumerate(hists):
         centers = centers + offset if offset else centers
         if len(centers) == 1 or counts.sum() == counts.max():  # constant plane: nothing is above it
@@ -457,7 +467,7 @@ def _apply_histogram_threshold(intensities, method: str, batched: bool, kwargs: 
         thr = np.floor(thr) - offset
     d_thr = _gpu.torch_mod().from_numpy(thr).to(planes.device)
     mask = _gpu.threshold_gt(planes, d_thr).reshape(t.shape).view(_gpu.torch_mod().bool)
-    return _gpu.to_host(mask) if was_numpy else mask
+    return _finish(mask, was_numpy)
 
 
 def _window_per_axis(size, ndim: int, what: str) -> tuple[int, ...]:
@@ -529,7 +539,7 @@ def _apply_local_threshold(intensities, method: str, batched: bool, kwargs: dict
     for i in np.flatnonzero(limits[:, 0] == limits[:, 1]):
         mask[int(i)].zero_()
     mask = mask.reshape(t.shape).view(torch.bool)
-    return _gpu.to_host(mask) if was_numpy else mask
+    return _finish(mask, was_numpy)
 
 
 @_device_op
@@ -545,7 +555,7 @@ def apply_threshold(
     Empty or constant input -> all False (checked before the method name, as in the
     reference).  All ten methods of the reference run on the B200 path: ``otsu``, ``li``, ``yen``,
     ``isodata``, ``mean``, ``minimum``, ``triangle`` from skimage's histogram (exact per-value counts for
-    integer images, 256 uniform bins for float images; ``li`` and ``mean`` for integer images only), and
+    integer images, ``nbins`` uniform bins for float images; ``li`` for integer images only), and
     the local-window methods ``local`` (Gaussian), ``niblack``, ``sauvola`` (integer images).
     """
     if not _gpu.is_device_array(intensities) and np.asarray(intensities).size == 0:
@@ -564,11 +574,14 @@ def apply_threshold(
     if method_lower in _LOCAL_THRESHOLD_METHODS:
         return _apply_local_threshold(intensities, method_lower, _batched, kwargs)
     intensities, offset = _shift_wide_integers(intensities)
-    if method_lower != "otsu" or offset:
+    float_nbins = kwargs.get("nbins", 256) != 256 and not (
+        _gpu.is_device_array(intensities) and _gpu.dtype_code(intensities) == _lib.AMT_U16
+        or not _gpu.is_device_array(intensities) and np.asarray(intensities).dtype.kind in "iub")
+    if method_lower != "otsu" or offset or float_nbins:
         return _apply_histogram_threshold(intensities, method_lower, _batched, kwargs, offset)
     t, _, was_numpy = _prepare(intensities)
     planes = _slices(t, _batched)
     # a constant plane gets threshold == its value, so nothing is above it (all False)
     thr, _ = _gpu.otsu_threshold(planes)
     mask = _gpu.threshold_gt(planes, thr).reshape(t.shape).view(_gpu.torch_mod().bool)
-    return _gpu.to_host(mask) if was_numpy else mask
+    return _finish(mask, was_numpy)

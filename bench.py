@@ -173,24 +173,32 @@ def build_device_batch(n_fov: int, n_unique: int, device, seed0: int = 20260000)
 
 
 # ------------------------------------------------------------------------------------ CPU side
-def oracle_fov(args) -> int:
-    """Workload W for one FOV through the oracle (the reference's call chain on SciPy/NumPy)."""
+NAMES = ["brightfield", "dapi", "fitc", "tritc"]
+MORPH = ["label", "area", "bbox", "centroid", "axis_major_length", "axis_minor_length", "eccentricity", "orientation"]
+INTEN = ["intensity_sum", "intensity_mean", "intensity_max", "intensity_min", "intensity_std"]
+
+
+def oracle_fov_full(args) -> dict:
+    """Workload W for one FOV through the oracle (the reference's call chain on SciPy/NumPy); keeps every result."""
     fov, given = args
     import oracle
 
-    names = ["brightfield", "dapi", "fitc", "tritc"]
-    morph = ["label", "area", "bbox", "centroid", "axis_major_length", "axis_minor_length", "eccentricity", "orientation"]
-    inten = ["intensity_mean", "intensity_max", "intensity_min", "intensity_std"]
     pre = [oracle.rescale_by_percentile(oracle.subtract_background_dog(fov[c], 0.6, 16.0, 0), (1, 99), (0, 1))
            for c in range(fov.shape[0])]
+    thr = oracle.threshold.threshold_otsu(pre[SEG_CHANNEL])
     mask = oracle.apply_threshold(pre[SEG_CHANNEL])
-    chans = {n: fov[i] for i, n in enumerate(names[: fov.shape[0]])}
-    total = 0
-    for m in (mask, given.astype(np.int64)):
+    chans = {n: fov[i] for i, n in enumerate(NAMES[: fov.shape[0]])}
+    res = {"pre": np.stack(pre), "threshold": float(thr)}
+    for key, m in (("thr", mask), ("given", given.astype(np.int64))):
         labels = oracle.process_mask(m, True)
-        props = oracle.cell_properties(labels, chans, morph, inten)
-        total += len(props["label"])
-    return total
+        res["labels_" + key] = labels
+        res["props_" + key] = oracle.cell_properties(labels, chans, MORPH, INTEN)
+    return res
+
+
+def oracle_fov(args) -> int:
+    res = oracle_fov_full(args)
+    return len(res["props_thr"]["label"]) + len(res["props_given"]["label"])
 
 
 def host_fov(seed: int):
@@ -200,28 +208,72 @@ def host_fov(seed: int):
     return fov, given
 
 
-def cpu_baseline_single(n_fovs: int = 3) -> dict:
+def cpu_baseline_single(n_fovs: int = 3) -> tuple[dict, list, list]:
+    """The oracle on one host core over a bounded sample; returns (cpu_baseline entry, inputs, oracle results) —
+    the results are what `parity_check` compares the GPU path with."""
     batch = [host_fov(20260000 + i) for i in range(n_fovs)]
     t0 = time.perf_counter()
-    for item in batch:
-        oracle_fov(item)
+    results = [oracle_fov_full(item) for item in batch]
     dt = time.perf_counter() - t0
-    return {"value": n_fovs * C * H * W / dt / 1e6, "unit": "Mpix/s", "cores": 1, "kind": "port", "seconds": dt,
-            "sample": f"{n_fovs} FOVs of {C}x{H}x{W} uint16 + their label masks, full workload W, single thread (oracle: "
-                      "reference call chain on scipy/numpy; scikit-image itself is not installable here)"}
+    entry = {"value": n_fovs * C * H * W / dt / 1e6, "unit": "Mpix/s", "cores": 1, "kind": "port", "seconds": dt,
+             "sample": f"{n_fovs} FOVs of {C}x{H}x{W} uint16 + their label masks, full workload W, single thread (oracle: "
+                       "reference call chain on scipy/numpy; scikit-image itself is not installable here)"}
+    return entry, batch, results
 
 
-def ncu_traffic(dom: str, planes: int) -> tuple[float | None, str | None]:
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_ncu_full_dog_strip.json, same 32-plane launch as the live timing)."""
-    path = ROOT / "profiles" / "r01_ncu_full_dog_strip.json"
-    if not path.exists() or planes != 32:
-        return None, None
-    want = "unsigned short" if dom == "axis0" else "double, 1"
-    for k in json.loads(path.read_text())["kernels"]:
-        if want in k["kernel"] and "dram_bytes" in k:
-            return float(k["dram_bytes"]), f"profiles/{path.name} ({k['kernel']})"
-    return None, None
+PLANE_ATOL_TENSOR_CORE = 1e-8  # tests/test_gpu_executor.py: TENSOR_CORE_PLANE_ATOL
+
+
+def parity_check(ex, batch, results, names) -> dict:
+    """The same seeded full-size FOVs the CPU baseline just ran, through the product (host-fed C-ABI call with the
+    reference's int64 masks for the tables, device-resident call for labels and planes), against the oracle's
+    results: thresholds, labels, counts and integer columns bit for bit, float columns to rtol 1e-5, the
+    thresholded channel's plane bit for bit, the other planes to PLANE_ATOL_TENSOR_CORE."""
+    from arcadia_microscopy_tools_b200 import _gpu
+
+    fovs = np.stack([b[0] for b in batch])
+    givens = np.stack([b[1] for b in batch]).astype(np.int64)
+    host = ex.run_host(fovs, givens)
+    dev_out = ex.alloc_outputs(len(batch), labels=True, preprocessed=True)
+    ex.run_device(_gpu.to_device(fovs), _gpu.to_device(givens.astype(np.int32)), dev_out)
+    dev = {k: _gpu.to_host(v) for k, v in dev_out.items() if v is not None}
+    report = {"fovs": len(batch), "ok": True, "max_plane_abs_err_other_channels": 0.0, "failures": []}
+
+    def fail(msg):
+        report["ok"] = False
+        if len(report["failures"]) < 8:
+            report["failures"].append(msg)
+
+    for i, want in enumerate(results):
+        if host["thresholds"][i] != want["threshold"] or dev["thresholds"][i] != want["threshold"]:
+            fail(f"fov {i}: threshold {host['thresholds'][i]!r} != {want['threshold']!r}")
+        if not np.array_equal(dev["preprocessed"][i, SEG_CHANNEL], want["pre"][SEG_CHANNEL]):
+            fail(f"fov {i}: thresholded channel's plane is not bit-identical")
+        err = float(np.max(np.abs(dev["preprocessed"][i] - want["pre"])))
+        report["max_plane_abs_err_other_channels"] = max(report["max_plane_abs_err_other_channels"], err)
+        if err > PLANE_ATOL_TENSOR_CORE:
+            fail(f"fov {i}: plane error {err:.3e}")
+        for which in ("thr", "given"):
+            if not np.array_equal(dev[f"labels_{which}"][i], want[f"labels_{which}"]):
+                fail(f"fov {i}: labels_{which} differ")
+            props = want[f"props_{which}"]
+            k = len(props["label"])
+            if int(host[f"counts_{which}"][i]) != k or int(dev[f"counts_{which}"][i]) != k:
+                fail(f"fov {i}: count_{which} {int(host[f'counts_{which}'][i])} != {k}")
+                continue
+            got = ex.table_to_properties(host[f"tables_{which}"][i], k, names)
+            if not np.array_equal(host[f"tables_{which}"][i][:, :k], dev[f"tables_{which}"][i][:, :k], equal_nan=True):
+                fail(f"fov {i}: host-fed and device-resident tables_{which} differ")
+            for key, w in props.items():
+                g = got[key]
+                if key in ("label", "area") or key.startswith(("bbox", "intensity_sum", "intensity_max", "intensity_min")):
+                    if not np.array_equal(g.astype(np.float64), w.astype(np.float64)):
+                        fail(f"fov {i} {which}: integer column {key} differs")
+                elif key not in ("orientation", "eccentricity"):  # round-off determined for near-symmetric specks (SURVEY 8a-11)
+                    atol = 1e-9 * max(1.0, float(np.abs(w).max()))
+                    if not np.allclose(g, w, rtol=1e-5, atol=atol):
+                        fail(f"fov {i} {which}: float column {key} differs")
+    return report
 
 
 def run_reference(args) -> None:
@@ -259,10 +311,22 @@ def run_reference(args) -> None:
 
 
 # ------------------------------------------------------------------------------------ GPU side
-def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int, exact_every: int = 0, exact_offset: int = 0) -> dict:
-    """Per-kernel CUDA-event timings of the two Gaussian passes and the FP64 probe.  exact_every > 0: the launch
-    the executor makes by default (plane p keeps scipy's operation order iff p % exact_every == exact_offset, the
-    other planes use fused multiply-adds); 0: every plane in scipy's order."""
+def ncu_traffic(kernel_substr: str) -> tuple[float | None, str | None]:
+    """DRAM bytes per launch of the named kernel from the committed `ncu --set full` capture of this round
+    (profiles/r02_ncu_dog_kernels.json: the same 32-plane chunk, 24 planes on the tensor cores, 8 exact)."""
+    path = ROOT / "profiles" / "r02_ncu_dog_kernels.json"
+    if not path.exists():
+        return None, None
+    for k in json.loads(path.read_text())["kernels"]:
+        if kernel_substr in k["kernel"] and "dram_bytes" in k:
+            return float(k["dram_bytes"]), f"profiles/{path.name} ({k['kernel'][:60]})"
+    return None, None
+
+
+def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int, tcg) -> dict:
+    """CUDA-event timings of the DoG kernels of one executor chunk, each timed alone: the float64 strip kernels on
+    the thresholded channel's planes (8 of 32), and — when the executor runs the other channels on the tensor
+    cores — the narrow Gaussian and the two tcgen05 passes on the other 24; plus the FP64 issue-rate probe."""
     import ctypes as CT
 
     import torch
@@ -281,22 +345,24 @@ def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int, exact_every: i
     mm = torch.empty((planes, 2), dtype=torch.int64, device=dev)
     probe_scratch = torch.empty(148 * 8 * 256, dtype=torch.float64, device=dev)
     st = gpu.stream_ptr()
+    p = gpu.ptr
+    scale = 1.0 / 65535.0
 
     def v_pass():
-        L.check(lib.amt_dog2d_axis0(gpu.ptr(fovs), L.AMT_U16, 1.0 / 65535.0, planes, H, W, gpu.ptr(d_lo), len(hw_lo) - 1,
-                                    gpu.ptr(d_hi), len(hw_hi) - 1, gpu.ptr(tmp_lo), gpu.ptr(tmp_hi), st))
+        L.check(lib.amt_dog2d_axis0(p(fovs), L.AMT_U16, scale, planes, H, W, p(d_lo), len(hw_lo) - 1, p(d_hi), len(hw_hi) - 1,
+                                    p(tmp_lo), p(tmp_hi), st))
 
     def h_pass():
-        L.check(lib.amt_dog2d_axis1(gpu.ptr(tmp_lo), gpu.ptr(tmp_hi), gpu.ptr(out), planes, H, W, gpu.ptr(d_lo),
-                                    len(hw_lo) - 1, gpu.ptr(d_hi), len(hw_hi) - 1, gpu.ptr(mm), st))
+        L.check(lib.amt_dog2d_axis1(p(tmp_lo), p(tmp_hi), p(out), planes, H, W, p(d_lo), len(hw_lo) - 1, p(d_hi),
+                                    len(hw_hi) - 1, p(mm), st))
 
     dp = CT.c_uint64(0)
 
     def probe():
-        L.check(lib.amt_fp64_probe(4096, gpu.ptr(probe_scratch), CT.byref(dp), st))
+        L.check(lib.amt_fp64_probe(4096, p(probe_scratch), CT.byref(dp), st))
 
     def timed(fn) -> float:
-        for _ in range(max(warmup, 3)):
+        for _ in range(max(warmup, 1) if steps == 1 else max(warmup, 3)):
             fn()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -307,25 +373,42 @@ def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int, exact_every: i
         torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1) / steps
 
-    L.check(lib.amt_tune(b"dog_exact_every", exact_every), "amt_tune")
-    L.check(lib.amt_tune(b"dog_exact_offset", exact_offset), "amt_tune")
+    r_lo, r_hi = len(hw_lo) - 1, len(hw_hi) - 1
+    px_plane = H * W
+    res = {"planes": planes}
+    mixed = tcg is not None
+    exact_planes = planes // C if mixed else planes
+    if mixed:
+        for key, val in ((b"dog_exact_every", C), (b"dog_exact_offset", SEG_CHANNEL), (b"dog_only_exact", 1)):
+            L.check(lib.amt_tune(key, val), "amt_tune")
     try:
         ms_v, ms_h = timed(v_pass), timed(h_pass)
     finally:
-        L.check(lib.amt_tune(b"dog_exact_every", 0), "amt_tune")
-        L.check(lib.amt_tune(b"dog_exact_offset", 0), "amt_tune")
+        for key in (b"dog_exact_every", b"dog_exact_offset", b"dog_only_exact"):
+            L.check(lib.amt_tune(key, 0), "amt_tune")
+    dp_axis = (1 + 3 * r_lo) + (1 + 3 * r_hi) + 1  # DADD + DMUL + DADD per tap pair, both filters, + the conversion / subtraction
+    res["strip_axis0"] = {"ms": ms_v, "planes": exact_planes, "bytes": exact_planes * px_plane * (2 + 16),
+                          "dp_instr": exact_planes * px_plane * dp_axis, "kernel": "dog_strip_kernel<..., uint16, axis 0>"}
+    res["strip_axis1"] = {"ms": ms_h, "planes": exact_planes, "bytes": exact_planes * px_plane * (16 + 8 + 2),
+                          "dp_instr": exact_planes * px_plane * dp_axis, "kernel": "dog_strip_kernel<..., double, axis 1>"}
+    if mixed:
+        tc_planes = planes - exact_planes
+        digits = torch.empty((planes, 5, H, W), dtype=torch.uint8, device=dev)
+        buckets = torch.empty((planes, H, W), dtype=torch.int16, device=dev)
+        ms_lo = timed(lambda: L.check(lib.amt_gauss_lo2d(p(fovs), scale, p(tmp_lo), planes, H, W, p(d_lo), r_lo, C, SEG_CHANNEL, st)))
+        ms_a0 = timed(lambda: L.check(lib.amt_tcg_axis0(tcg.handle, p(fovs), planes, H, W, p(digits), C, SEG_CHANNEL, st)))
+        ms_a1 = timed(lambda: L.check(lib.amt_tcg_axis1(tcg.handle, p(digits), p(tmp_lo), scale, p(out), planes, H, W, p(buckets),
+                                                       p(mm), C, SEG_CHANNEL, st)))
+        # int8 multiply-adds per sample: 4 weight digits x 2 sample bytes x K = 256 (axis 0), 17 digit products x 256 (axis 1)
+        res["lo2d"] = {"ms": ms_lo, "planes": tc_planes, "bytes": tc_planes * px_plane * (2 + 8), "kernel": "lo2d_kernel"}
+        res["tcg_axis0"] = {"ms": ms_a0, "planes": tc_planes, "bytes": tc_planes * px_plane * (2 + 5),
+                            "macs": tc_planes * px_plane * 8 * 256, "kernel": "tcg_axis0_kernel"}
+        res["tcg_axis1"] = {"ms": ms_a1, "planes": tc_planes, "bytes": tc_planes * px_plane * (5 + 8 + 8 + 2),
+                            "macs": tc_planes * px_plane * 17 * 256, "kernel": "tcg_axis1_kernel"}
     ms_p = timed(probe)
-    px = planes * H * W
-    r_lo, r_hi = len(hw_lo) - 1, len(hw_hi) - 1
-    exact_share = 1.0 / exact_every if exact_every > 0 else 1.0
-    # DP instructions per sample and axis: DADD + DMUL + DADD per tap pair in scipy's order, DADD + DFMA contracted
-    dp_per_px_axis = exact_share * ((1 + 3 * r_lo) + (1 + 3 * r_hi)) + (1.0 - exact_share) * ((1 + 2 * r_lo) + (1 + 2 * r_hi))
-    return {
-        "planes": planes, "ms_axis0": ms_v, "ms_axis1": ms_h, "ms_probe": ms_p,
-        "fp64_peak_tinstr_s": dp.value / (ms_p * 1e-3) / 1e12,
-        "axis0": {"bytes": px * (2 + 16), "dp_instr": px * (dp_per_px_axis + 1)},
-        "axis1": {"bytes": px * (16 + 8), "dp_instr": px * (dp_per_px_axis + 1)},
-    }
+    res["ms_probe"] = ms_p
+    res["fp64_peak_tinstr_s"] = dp.value / (ms_p * 1e-3) / 1e12
+    return res
 
 
 def bind_near_gpu(local: int) -> list[int]:
@@ -349,12 +432,25 @@ def bind_near_gpu(local: int) -> list[int]:
     return []
 
 
+def host_mem_available_gb() -> float:
+    try:
+        for line in Path("/proc/meminfo").read_text().splitlines():
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 64.0
+
+
 def run_b200(args) -> None:
+    import dataclasses
+
     import torch
     import torch.distributed as dist
 
     from arcadia_microscopy_tools_b200 import _gpu, _lib
-    from arcadia_microscopy_tools_b200.batch import FovBatchExecutor, FovPipelineConfig
+    from arcadia_microscopy_tools_b200.batch import FovBatchExecutor, FovPipelineConfig, fov_record
+    from arcadia_microscopy_tools_b200.sharding import gather_fov_results
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -372,13 +468,21 @@ def run_b200(args) -> None:
         if world > 1:
             dist.barrier()
 
+    def max_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
     n_fov = args.fovs
     fovs, given, max_label = build_device_batch(n_fov, args.unique, dev, seed0=20260000 + 1000 * rank)
+    # the host-fed leg hands the executor the reference's own mask dtype: int64 (ref: model.py:215, masks.py:138)
     cfg = FovPipelineConfig(n_channels=C, height=H, width=W, seg_channel=SEG_CHANNEL, chunk_fovs=args.chunk,
-                            max_labels=4096, max_label_value=max_label, given_label_dtype=np.uint16,
-                            exact_all_channels=args.exact_all_channels)
+                            max_labels=4096, max_label_value=max_label, given_label_dtype=np.int64,
+                            exact_all_channels=args.exact_all_channels, plane_filter=args.plane_filter)
     ex = FovBatchExecutor(cfg, device=local)
     out = ex.alloc_outputs(n_fov)
+    tensor_cores = ex.uses_tensor_cores
 
     # ---- device-resident timed region: W warm-up steps, then exactly K timed steps
     for _ in range(args.warmup):
@@ -394,59 +498,76 @@ def run_b200(args) -> None:
         wall = time.perf_counter() - t0
     barrier()
     launches = int(lib.amt_launch_count() - launches0)
-    dev_s = sum(step_ms) / 1e3
-    t = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_s, wall = float(t[0]), float(t[1])
+    dev_s, wall = max_ranks(sum(step_ms) / 1e3), max_ranks(wall)
     counts = _gpu.to_host(out["counts_thr"]), _gpu.to_host(out["counts_given"])
+    status_any = int(_gpu.to_host(out["status"]).any())
 
-    # ---- end to end through the host-fed C-ABI call (pinned host buffers)
+    # ---- per-stage device time of one more (untimed) pass: CUDA events after every stage of both streams
+    ex.set_profiling(True)
+    ex.run_device(fovs, given, out, sync=True)
+    stage_ms, stage_chunks = ex.stage_ms()
+    ex.set_profiling(False)
+
+    # ---- end to end through the host-fed C-ABI call (pinned host buffers): H2D of every FOV and label mask and D2H of
+    # the tables inside the timed region.  Headline: int64 masks (the reference's dtype at this boundary); beside it the
+    # same with uint16 masks (Cellpose's own dtype), and the copy-only ceiling (same buffers, staging, streams; no kernels)
     e2e = None
     if not args.no_e2e:
-        # pinned host staging is per rank: halve it on multi-GPU runs so that 8 ranks stay well inside host RAM
-        n_e2e = min(n_fov, args.e2e_fovs if world == 1 else min(args.e2e_fovs, 128))
-        # label masks travel as uint16 (Cellpose's own mask dtype below 65536 cells): 8.4 instead of 16.8 MB per FOV
-        if args.host_alloc == "torch":
-            h_fovs = torch.empty((n_e2e, C, H, W), dtype=torch.int16, pin_memory=True)
-            h_given = torch.empty((n_e2e, H, W), dtype=torch.int16, pin_memory=True)
-            h_fovs.copy_(fovs[:n_e2e])
-            h_given.copy_(given[:n_e2e].to(torch.int16))
-            np_fovs = h_fovs.numpy().view(np.uint16)
-            np_given = h_given.numpy().view(np.uint16)
-        else:  # the library's own pinned staging (amt_host_alloc), optionally write-combined
-            pin_fovs = _gpu.PinnedBuffer((n_e2e, C, H, W), np.uint16, write_combined=args.host_alloc == "wc")
-            pin_given = _gpu.PinnedBuffer((n_e2e, H, W), np.uint16, write_combined=args.host_alloc == "wc")
-            np_fovs, np_given = pin_fovs.array, pin_given.array
-            np_fovs[...] = fovs[:n_e2e].cpu().numpy().view(np.uint16)
-            np_given[...] = given[:n_e2e].to(torch.int16).cpu().numpy().view(np.uint16)
+        # pinned staging per rank: FOVs + int64 masks = 67 MB per FOV; keep all ranks together inside half of the host's RAM
+        budget_gb = 0.5 * host_mem_available_gb() / max(world, 1)
+        n_e2e = int(min(n_fov, args.e2e_fovs, max(8, budget_gb * 1e9 // (C * H * W * 2 + H * W * 10))))
+        h_fovs = torch.empty((n_e2e, C, H, W), dtype=torch.int16, pin_memory=True)
+        h_given64 = torch.empty((n_e2e, H, W), dtype=torch.int64, pin_memory=True)
+        h_given16 = torch.empty((n_e2e, H, W), dtype=torch.int16, pin_memory=True)
+        h_fovs.copy_(fovs[:n_e2e])
+        h_given64.copy_(given[:n_e2e].to(torch.int64))
+        h_given16.copy_(given[:n_e2e].to(torch.int16))
+        np_fovs = h_fovs.numpy().view(np.uint16)
         h_out = ex.alloc_host_outputs(n_e2e)
-        for _ in range(min(args.warmup, 2)):
-            ex.run_host(np_fovs, np_given, h_out)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            ex.run_host(np_fovs, np_given, h_out)
-        e2e_s = time.perf_counter() - t0
-        barrier()
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te[0])
+
+        def timed_host(executor, masks) -> float:
+            for _ in range(min(args.warmup, 2)):
+                executor.run_host(np_fovs, masks, h_out)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                executor.run_host(np_fovs, masks, h_out)
+            dt = time.perf_counter() - t0
+            barrier()
+            return max_ranks(dt)
+
+        s64 = timed_host(ex, h_given64.numpy())
         assert np.array_equal(h_out["counts_thr"], counts[0][:n_e2e]) and np.array_equal(h_out["counts_given"], counts[1][:n_e2e])
+        _lib.check(lib.amt_tune(b"exec_copy_only", 1), "amt_tune")
+        try:
+            c64 = timed_host(ex, h_given64.numpy())
+        finally:
+            _lib.check(lib.amt_tune(b"exec_copy_only", 0), "amt_tune")
+        with FovBatchExecutor(dataclasses.replace(cfg, given_label_dtype=np.uint16), device=local) as ex16:
+            s16 = timed_host(ex16, h_given16.numpy().view(np.uint16))
+            assert np.array_equal(h_out["counts_given"], counts[1][:n_e2e])
         d2h = sum(int(h_out[k].nbytes) for k in h_out)
-        e2e = {"value": world * args.steps * n_e2e * C * H * W / e2e_s / 1e6, "unit": "Mpix/s",
-               "h2d_bytes_per_step": int(np_fovs.nbytes + np_given.nbytes), "d2h_bytes_per_step": d2h,
-               "fov_per_s": world * args.steps * n_e2e / e2e_s, "fovs_per_step": n_e2e, "timing": "wall clock around the synchronous C-ABI call",
-               "rank0_cpu_affinity": f"{len(cpus)} CPUs local to the GPU (NVML)" if cpus else "unchanged",
-               "host_buffers": {"torch": "torch pinned tensors", "pinned": "amt_host_alloc", "wc": "amt_host_alloc, write-combined"}[args.host_alloc]}
+        h2d64 = int(np_fovs.nbytes + h_given64.numpy().nbytes)
+        h2d16 = int(np_fovs.nbytes + h_given16.numpy().nbytes)
+        samples = world * args.steps * n_e2e * C * H * W
+        e2e = {"value": samples / s64 / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d64, "d2h_bytes_per_step": d2h,
+               "fov_per_s": world * args.steps * n_e2e / s64, "fovs_per_step": n_e2e,
+               "label_mask_dtype": "int64 (the reference's dtype at this boundary: model.py:215, masks.py:138), narrowed on the device",
+               "h2d_gbs": world * args.steps * h2d64 / s64 / 1e9,
+               "copy_only": {"seconds_per_step": c64 / args.steps, "h2d_ceiling_gbs": world * args.steps * h2d64 / c64 / 1e9,
+                             "note": "amt_tune('exec_copy_only'): the same call, buffers, staging slots, streams and events with "
+                                     "no kernel launched; all ranks concurrently"},
+               "frac_of_copy_ceiling": c64 / s64,
+               "uint16_masks": {"value": samples / s16 / 1e6, "fov_per_s": world * args.steps * n_e2e / s16,
+                                "h2d_bytes_per_step": h2d16,
+                                "note": "Cellpose's own mask dtype (below 65536 cells): 42 instead of 67 MB per FOV over PCIe"},
+               "timing": "wall clock around the synchronous C-ABI call, max over ranks",
+               "rank0_cpu_affinity": f"{len(cpus)} CPUs local to the GPU (NVML)" if cpus else "unchanged"}
+        del h_fovs, h_given64, h_given16
 
-    # ---- the same device-resident pass with the DoG's multiply-adds contracted (amt_tune "dog_fma"): what scipy's
-    # exact operation order costs.  Not the reported value: the default path stays bit-identical to the reference.
-    contracted = strict = None
-    if not args.no_contracted:
-        import dataclasses
-
+    # ---- the same device-resident pass in the other arithmetic modes (never the reported value)
+    modes = {}
+    if not args.no_modes:
         keep = {k: out[k].clone() for k in ("tables_thr", "counts_thr", "thresholds")}
 
         def same_as_default() -> bool:
@@ -458,96 +579,135 @@ def run_b200(args) -> None:
             barrier()
             ms = [executor.run_device(fovs, given, out, sync=True) for _ in range(args.steps)]
             barrier()
-            t_pass = torch.tensor([sum(ms) / 1e3], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(t_pass, op=dist.ReduceOp.MAX)
-            return float(t_pass[0])
+            return max_ranks(sum(ms) / 1e3)
 
-        _lib.check(lib.amt_tune(b"dog_fma", 1), "amt_tune")
-        try:
-            c_s = timed_pass(ex)
-        finally:
-            _lib.check(lib.amt_tune(b"dog_fma", 0), "amt_tune")
-        contracted = {"value": world * args.steps * n_fov * C * H * W / c_s / 1e6, "unit": "Mpix/s",
-                      "ms_per_step": 1e3 * c_s / args.steps,
-                      "thresholds_counts_and_tables_bit_identical_to_default": same_as_default(),
-                      "note": "opt-in amt_tune('dog_fma', 1): fused multiply-adds for EVERY channel, the segmentation channel "
-                              "included (its plane then differs from scipy's in the last bits); NOT the reported value"}
-        if not cfg.exact_all_channels:
-            # the strict configuration: scipy's exact operation order for every channel (all float planes bit-identical)
-            with FovBatchExecutor(dataclasses.replace(cfg, exact_all_channels=True), device=local) as ex_strict:
-                s_s = timed_pass(ex_strict)
-            strict = {"value": world * args.steps * n_fov * C * H * W / s_s / 1e6, "unit": "Mpix/s",
-                      "ms_per_step": 1e3 * s_s / args.steps,
-                      "thresholds_counts_and_tables_bit_identical_to_default": same_as_default(),
-                      "note": "FovPipelineConfig(exact_all_channels=True): the float planes of the channels that are not "
-                              "thresholded are bit-identical to scipy's too (default: equal to ~1e-15 relative)"}
+        variants = {"fma": dict(plane_filter="fma", exact_all_channels=False),
+                    "exact_all_channels": dict(exact_all_channels=True),
+                    "tensor_core": dict(plane_filter="tensor_core", exact_all_channels=False)}
+        for name, kw in variants.items():
+            vcfg = dataclasses.replace(cfg, **kw)
+            if (vcfg.plane_filter, vcfg.exact_all_channels) == (cfg.plane_filter, cfg.exact_all_channels):
+                continue
+            with FovBatchExecutor(vcfg, device=local) as ex_v:
+                s_v = timed_pass(ex_v)
+                modes[name] = {"value": world * args.steps * n_fov * C * H * W / s_v / 1e6, "unit": "Mpix/s",
+                               "ms_per_step": 1e3 * s_v / args.steps, "uses_tensor_cores": ex_v.uses_tensor_cores,
+                               "thresholds_counts_and_tables_bit_identical_to_default": same_as_default()}
+        ex.run_device(fovs, given, out, sync=True)  # leave the default mode's results in `out`
         del keep
 
-    # ---- per-kernel roofline (rank 0) and CPU baseline (rank 0, N=1)
+    # ---- the plate view of this run (config 5's sharding): global FOV i lives on rank i mod world as its local FOV
+    # i div world; per-FOV records are gathered on rank 0 in FOV order, outside every timed region
+    plate = None
+    if world > 1 or args.plate_check:
+        host_out = {k: _gpu.to_host(v) for k, v in out.items() if v is not None and k in
+                    ("tables_thr", "counts_thr", "tables_given", "counts_given", "thresholds", "status")}
+        full = set(range(min(2, n_fov)))  # whole tables for the first FOVs of every rank, counts for all
+        local_records = {}
+        for j in range(n_fov):
+            rec = fov_record(host_out, j) if j in full else {
+                "count_thr": int(host_out["counts_thr"][j]), "count_given": int(host_out["counts_given"][j]),
+                "threshold": float(host_out["thresholds"][j]), "status": int(host_out["status"][j])}
+            local_records[j * world + rank] = rec | {"rank": rank, "local_index": j}
+        merged = gather_fov_results(local_records, n_fov * world, dist if world > 1 else None)
+        if rank == 0:
+            assert merged is not None and len(merged) == n_fov * world
+            for i, rec in enumerate(merged):
+                assert rec["rank"] == i % world and rec["local_index"] == i // world, ("plate order", i, rec["rank"])
+                if rec["rank"] == 0:
+                    assert rec["count_thr"] == int(host_out["counts_thr"][i // world])
+                if "table_thr" in rec:
+                    assert rec["table_thr"].shape[1] == min(rec["count_thr"], cfg.max_labels)
+            plate = {"fovs_gathered": len(merged), "order": "FOV i from rank i mod world, local index i div world: verified",
+                     "cells_threshold_mask": int(sum(r["count_thr"] for r in merged)),
+                     "cells_given_mask": int(sum(r["count_given"] for r in merged)),
+                     "fovs_with_status": int(sum(1 for r in merged if r["status"]))}
+        del host_out
+
+    # ---- per-kernel roofline (rank 0) and CPU baseline + full-size parity (rank 0, N=1)
     line = None
     if rank == 0:
         peaks = measured_peaks()
         hw = (_gpu.gaussian_half_weights(cfg.low_sigma), _gpu.gaussian_half_weights(cfg.high_sigma))
-        mixed = not cfg.exact_all_channels and C > 1
-        k = time_kernels(lib, _gpu, fovs, hw, steps=max(args.steps, 5), warmup=args.warmup,
-                         exact_every=C if mixed else 0, exact_offset=SEG_CHANNEL if mixed else 0)
-        k_exact = time_kernels(lib, _gpu, fovs, hw, steps=max(args.steps, 5), warmup=args.warmup) if mixed else k
-        dom = "axis1" if k["ms_axis1"] >= k["ms_axis0"] else "axis0"
-        dom_ms = k["ms_" + dom]
+        tcg = _gpu.TensorCoreGaussian(cfg.high_sigma) if tensor_cores else None
+        k = time_kernels(lib, _gpu, fovs, hw, steps=max(args.steps, 5), warmup=args.warmup, tcg=tcg)
+        kernel_keys = [key for key in ("strip_axis0", "strip_axis1", "lo2d", "tcg_axis0", "tcg_axis1") if key in k]
+        dom = max(kernel_keys, key=lambda key: k[key]["ms"])
+        dom_ms = k[dom]["ms"]
         achieved = k[dom]["bytes"] / (dom_ms * 1e-3) / 1e9
-        fp64_ach = k[dom]["dp_instr"] / (dom_ms * 1e-3) / 1e12
-        traffic, traffic_src = ncu_traffic(dom, k["planes"])
-        dp_per_sample_axis = k[dom]["dp_instr"] / (k["planes"] * H * W) - 1
+        traffic, traffic_src = ncu_traffic(k[dom]["kernel"].split("<")[0])
         ms_per_step = 1e3 * dev_s / args.steps
         value = world * args.steps * n_fov * C * H * W / dev_s / 1e6
+        px_step = n_fov * H * W  # FOV-pixels of the profiled pass
+        pre_ms = sum(stage_ms[s] for s in ("dog_exact", "dog_lo", "dog_tc_axis0", "dog_tc_axis1", "select", "map"))
+        seg_ms = stage_ms["label_thr"]
+        quant_ms = stage_ms["regions_thr"] + stage_ms["label_given"] + stage_ms["regions_given"]
+
+        def stage_roof(ms: float, bytes_per_fov_pixel: int) -> dict:
+            gbs = px_step * bytes_per_fov_pixel / (ms * 1e-3) / 1e9 if ms > 0 else None
+            return {"ms_per_8_fov_chunk": ms / max(stage_chunks, 1) * (8 / args.chunk), "algorithmic_bytes_per_fov_pixel": bytes_per_fov_pixel,
+                    "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"] if gbs else None}
+
+        chunk_ms = ms_per_step / (n_fov / args.chunk)
+        budget_ms = args.chunk * ALGO_BYTES_PER_FOV_PIXEL * H * W / (0.6 * peaks["hbm_gbs"] * 1e9) * 1e3
         line = {
             "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"config2: {n_fov} FOVs/GPU x {C}x{H}x{W} uint16 + ~{N_CELLS}-cell int32 label mask per FOV; "
+            "config": {"workload": f"config2: {n_fov} FOVs/GPU x {C}x{H}x{W} uint16 + ~{N_CELLS}-cell label mask per FOV; "
                                    "W = DoG(0.6,16)+pct rescale on 4 channels, Otsu+CCL+clear_border on ch1, per-cell tables "
                                    "for the threshold mask and the given mask",
                        "arithmetic": ("float64, scipy's exact operation order for every channel" if cfg.exact_all_channels else
-                                      "float64; scipy's exact operation order for the segmentation channel (labels, counts, tables "
-                                      "bit-exact by construction), fused multiply-adds for the other channels' float planes "
-                                      "(equal to scipy's to ~1e-15 relative; tolerance 1e-5)"),
+                                      "thresholded channel: float64 in scipy's exact operation order (labels, counts, tables bit-exact "
+                                      "by construction); other channels' sigma=16 Gaussian: " +
+                                      ("exact integer Toeplitz products on tcgen05 (uint8 x uint8 -> int32, weights rounded to 32 bits; "
+                                       "planes within 1e-8 of scipy's on the [0, 1] scale, tolerance 1e-5)" if tensor_cores else
+                                       "float64 with fused multiply-adds (~1e-15)")),
                        "fovs_per_gpu": n_fov, "unique_cell_layouts": args.unique, "chunk_fovs": args.chunk,
+                       "uses_tensor_cores": tensor_cores,
                        "l2_policy": f"inputs {fovs.numel() * 2 / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
                        "sharding": "FOV-independent, one process per GPU, no collective on the data path"},
             "fov_per_s": world * args.steps * n_fov / dev_s,
             "hbm_algorithmic": {"bytes_per_fov": ALGO_BYTES_PER_FOV_PIXEL * H * W,
                                 "achieved_gbs": world * args.steps * n_fov * ALGO_BYTES_PER_FOV_PIXEL * H * W / dev_s / 1e9,
                                 "frac_of_peak_per_gpu": args.steps * n_fov * ALGO_BYTES_PER_FOV_PIXEL * H * W / dev_s / 1e9 / peaks["hbm_gbs"]},
+            "chunk": {"fovs": args.chunk, "ms": chunk_ms, "ms_budget_for_60pct_of_hbm": budget_ms, "distance_to_budget": chunk_ms / budget_ms},
+            "stages": {"W_pre": stage_roof(pre_ms, 4 * 34), "W_seg": stage_roof(seg_ms, 20), "W_quant": stage_roof(quant_ms, 2 * (4 + 2 * C)),
+                       "stage_ms_per_chunk": {s: v / max(stage_chunks, 1) for s, v in stage_ms.items()},
+                       "note": "CUDA events after every stage of one untimed pass; the DoG stages run on their own stream one chunk "
+                               "ahead of the others, so the stage sum exceeds the chunk time"},
             "wall_ms_per_step": 1e3 * wall / args.steps,
             "gpu_launches": launches,
             "cells_per_fov": {"threshold_mask": float(counts[0].mean()), "given_mask": float(counts[1].mean())},
+            "fovs_with_status_bits": status_any,
             "clocks": clocks.summary(),
             "e2e": e2e,
-            "exact_all_channels_mode": strict,
-            "contracted_mode": contracted,
-            "roofline": {"kernel": f"dog_strip_kernel ({dom} pass of the DoG: sigma 0.6 and 16 filters of {k['planes']} planes)",
+            "other_modes": modes,
+            "plate": plate,
+            "roofline": {"kernel": f"{k[dom]['kernel']} ({k[dom]['planes']} planes of {H}x{W}, timed alone)",
                          "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
-                         "algorithmic_bytes_per_launch": k[dom]["bytes"], "peak_source": peaks["source"],
-                         "ms_per_launch": dom_ms,
-                         "note": "this kernel is FP64-pipe-bound by construction (193 DP instr per sample and axis at sigma=16 in "
-                                 "scipy's exact operation order, 129 contracted; the default launch keeps the exact order for "
-                                 "the segmentation channel's planes only); see roofline_fp64"},
-            "roofline_fp64": {"bound": "fp64_pipe", "achieved": fp64_ach, "peak": k["fp64_peak_tinstr_s"],
-                              "unit": "T DP-instr/s", "frac": fp64_ach / k["fp64_peak_tinstr_s"],
-                              "peak_source": "amt_fp64_probe (DMUL+DADD chains) timed in this run"},
-            "kernels_ms": {"dog_axis0": k["ms_axis0"], "dog_axis1": k["ms_axis1"], "planes": k["planes"],
-                           "exact_planes": k["planes"] // C if mixed else k["planes"],
-                           "all_planes_exact": {"dog_axis0": k_exact["ms_axis0"], "dog_axis1": k_exact["ms_axis1"]}},
-            # what binds the whole path: the float64 Gaussians need 2 * (taps of both filters) + 1 DP instructions per input
-            # sample (401 in scipy's order, 269 contracted); at the measured DP issue rate that caps one GPU at this many FOV/s
-            "path_fp64_ceiling": {"dp_instr_per_sample": 2 * dp_per_sample_axis + 1,
-                                  "fov_per_s_per_gpu": k["fp64_peak_tinstr_s"] * 1e12 / (C * H * W * (2 * dp_per_sample_axis + 1)),
-                                  "frac": (args.steps * n_fov / dev_s) / (k["fp64_peak_tinstr_s"] * 1e12 / (C * H * W * (2 * dp_per_sample_axis + 1)))},
+                         "algorithmic_bytes_per_launch": k[dom]["bytes"], "peak_source": peaks["source"], "ms_per_launch": dom_ms},
+            "kernels": {key: {kk: vv for kk, vv in k[key].items()} | {"gbs": k[key]["bytes"] / (k[key]["ms"] * 1e-3) / 1e9}
+                        for key in kernel_keys},
         }
+        if "tcg_axis1" in k:
+            nominal_i8 = 4500.0  # T int8 multiply-adds... dense int8 peak of B200: 4.5 Pop/s = 2.25 P multiply-adds per second
+            for key in ("tcg_axis0", "tcg_axis1"):
+                line["kernels"][key]["tmacs"] = k[key]["macs"] / (k[key]["ms"] * 1e-3) / 1e12
+                line["kernels"][key]["frac_of_nominal_int8_peak"] = 2 * line["kernels"][key]["tmacs"] / nominal_i8
+        for key in ("strip_axis0", "strip_axis1"):
+            ach = k[key]["dp_instr"] / (k[key]["ms"] * 1e-3) / 1e12
+            line["kernels"][key]["fp64_tinstr_s"] = ach
+            line["kernels"][key]["frac_of_fp64_issue_peak"] = ach / k["fp64_peak_tinstr_s"]
+        line["roofline_fp64"] = {"bound": "fp64_pipe", "kernel": k["strip_axis1"]["kernel"],
+                                 "achieved": line["kernels"]["strip_axis1"]["fp64_tinstr_s"], "peak": k["fp64_peak_tinstr_s"],
+                                 "unit": "T DP-instr/s", "frac": line["kernels"]["strip_axis1"]["frac_of_fp64_issue_peak"],
+                                 "peak_source": "amt_fp64_probe (DMUL+DADD chains) timed in this run"}
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_single()
+            cpu, batch, results = cpu_baseline_single()
+            line["cpu_baseline"] = cpu
+            line["parity_checked"] = parity_check(ex, batch, results, [n.upper() for n in NAMES])
     ex.close()
     if world > 1:
         dist.barrier()
@@ -594,13 +754,14 @@ def main() -> None:
     ap.add_argument("--chunk", type=int, default=8, help="FOVs per launch wave")
     ap.add_argument("--e2e-fovs", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--host-alloc", default="torch", choices=["torch", "pinned", "wc"],
-                    help="pinned host input buffers of the e2e leg: torch's allocator, amt_host_alloc, or amt_host_alloc write-combined")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-contracted", action="store_true",
-                    help="skip the two comparison passes (every channel contracted / every channel in scipy's exact order)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline and the full-size parity check (N=1)")
+    ap.add_argument("--no-modes", action="store_true",
+                    help="skip the comparison passes in the other arithmetic modes (fma / exact_all_channels)")
+    ap.add_argument("--plane-filter", default="tensor_core", choices=["tensor_core", "fma"],
+                    help="filter of the channels that are not thresholded (FovPipelineConfig.plane_filter)")
     ap.add_argument("--exact-all-channels", action="store_true",
                     help="measure FovPipelineConfig(exact_all_channels=True) as the reported configuration")
+    ap.add_argument("--plate-check", action="store_true", help="also run the plate gather at N=1")
     args = ap.parse_args()
     capture_stdout()
     if args.impl == "reference":

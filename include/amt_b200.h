@@ -242,6 +242,16 @@ int amt_plan_dog_rescale(const double* order_stats /* n_img*6 */, const uint64_t
 int amt_hist256_f64(const double* data, int64_t n_img, int64_t n, const uint64_t* minmax_keys,
                     uint32_t* hist256, amt_stream_t stream);
 int amt_hist_u16(const uint16_t* data, int64_t n_img, int64_t n, uint32_t* hist65536, amt_stream_t stream);
+/* np.histogram(plane, nbins, range=(min, max)) of float64 planes for ANY nbins (threshold_*'s `nbins` argument,
+ * operations.py:214 forwards it): edges = n_img * (nbins + 1) doubles, np.linspace(min, max, nbins + 1) computed
+ * by the host; uniform-formula candidate corrected against the edges exactly as NumPy does. */
+int amt_hist_f64(const double* data, int64_t n_img, int64_t n, const double* edges, int nbins, uint32_t* hist,
+                 amt_stream_t stream);
+/* np.sum of every contiguous float64 plane in NumPy's PAIRWISE order (bit-identical; np.mean = sum / n):
+ * threshold_mean on float images (operations.py:191).  scratch: amt_pairwise_sum_scratch_bytes. */
+size_t amt_pairwise_sum_scratch_bytes(int64_t n_img, int64_t n);
+int amt_pairwise_sum_f64(const double* data, int64_t n_img, int64_t n, double* sums, void* scratch, size_t scratch_bytes,
+                         amt_stream_t stream);
 /* mode 0: float histogram, 256 bins, range from params[i].hist_first/last;
  * mode 1: float histogram, 256 bins, range from minmax_keys;
  * mode 2: uint16 exact histogram (65536 bins), range from minmax_keys. */
@@ -396,6 +406,25 @@ void amt_executor_destroy(amt_executor* ex);
 size_t amt_executor_device_bytes(const amt_executor* ex);
 /* 1 if this executor filters the non-thresholded channels on the tensor cores (plane_filter resolved at creation). */
 int amt_executor_uses_tensor_cores(const amt_executor* ex);
+
+/* Per-stage device time (CUDA events after every stage of both executor streams; adds a few microseconds per
+ * chunk, off by default).  amt_executor_set_profiling(ex, 1) zeroes the counters; every amt_executor_run_device call
+ * that follows adds its chunks; amt_executor_stage_ms copies the sums (milliseconds, AMT_N_STAGES entries) and
+ * the number of chunks they cover.  The DoG stages run on their own stream one chunk ahead of the others, so the
+ * sum over stages exceeds the wall time of a run. */
+#define AMT_STAGE_DOG_EXACT 0     /* float64 DoG in scipy's order (the thresholded channel, or every plane) */
+#define AMT_STAGE_DOG_LO 1        /* narrow Gaussian of the tensor-core planes */
+#define AMT_STAGE_DOG_TC0 2       /* tensor-core wide Gaussian, axis 0 */
+#define AMT_STAGE_DOG_TC1 3       /* tensor-core wide Gaussian, axis 1, + subtraction, buckets, min / max */
+#define AMT_STAGE_SELECT 4        /* order statistics (percentiles) */
+#define AMT_STAGE_MAP 5           /* plan + subtract / clip / rescale map + 256-bin histogram */
+#define AMT_STAGE_LABEL_THR 6     /* Otsu scan + threshold + CCL + clear_border + numbering */
+#define AMT_STAGE_REGIONS_THR 7   /* per-cell tables of the threshold mask */
+#define AMT_STAGE_LABEL_GIVEN 8   /* clear_border + relabel_sequential of the given mask */
+#define AMT_STAGE_REGIONS_GIVEN 9 /* per-cell tables of the given mask (+ status) */
+#define AMT_N_STAGES 10
+int amt_executor_set_profiling(amt_executor* ex, int enable);
+int amt_executor_stage_ms(const amt_executor* ex, double* stage_ms, int64_t* n_chunks);
 
 /* Per-FOV status bits (status[i] == 0: FOV i is complete and exact).  A field of view that trips one of these
  * does not disturb the others of the batch (the reference maps its per-image loop the same way:

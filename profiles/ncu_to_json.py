@@ -16,6 +16,7 @@ KEYS = {
     "dram__bytes_read.sum": "dram_read",
     "dram__bytes_write.sum": "dram_write",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_active_pct",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_active_pct",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
     "smsp__inst_executed.sum": "warp_instructions",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",

@@ -344,10 +344,25 @@ def test_li_minimum_triangle_match_oracle(method):
         assert np.array_equal(operations.apply_threshold(u16[0], "li", **kw), oracle.apply_threshold(u16[0].copy(), "li", **kw))
         with pytest.raises(NotImplementedError, match="uint8 / uint16 images only"):
             operations.apply_threshold(base[0] / 65535.0, "li")
+        # 'mean' on float64 planes: NumPy's pairwise sum reproduced bit for bit on the device
+        for shape2 in ((150, 130), (97, 257), (1, 5), (640, 1000)):
+            f = rng.random(shape2) * 3.0 - 1.0
+            assert np.array_equal(operations.apply_threshold(f, "mean"), f > np.mean(f)), shape2
+            assert np.array_equal(_gpu.plane_sums_f64(_gpu.to_device(f.reshape(1, -1))), np.array([np.sum(f)])), shape2
+        chain = operations.apply_threshold(operations.rescale_by_percentile(u16[0], (1, 99)), "mean")
+        assert np.array_equal(chain, oracle.apply_threshold(oracle.rescale_by_percentile(u16[0], (1, 99)), "mean"))
     else:
         f = base / 65535.0
         for i in range(3):
             assert np.array_equal(operations.apply_threshold(f[i], method), oracle.apply_threshold(f[i], method)), (method, i)
+        # nbins (operations.py:214 forwards it): the device histogram for any bin count equals np.histogram's
+        for nbins in (16, 100, 1000):
+            (counts, centers), = _gpu.plane_histograms(_gpu.to_device(f[0].reshape(1, -1)), nbins=nbins)
+            want_counts, edges = np.histogram(f[0].ravel(), bins=nbins)
+            assert np.array_equal(counts, want_counts) and np.array_equal(centers, (edges[:-1] + edges[1:]) / 2)
+            assert np.array_equal(operations.apply_threshold(f[0], method, nbins=nbins),
+                                  oracle.apply_threshold(f[0], method, nbins=nbins)), (method, nbins)
+        assert np.array_equal(operations.apply_threshold(f[0], "otsu", nbins=64), oracle.apply_threshold(f[0], "otsu", nbins=64))
     u8 = (base[0] / 8).clip(0, 255).astype(np.uint8)
     assert np.array_equal(operations.apply_threshold(u8, method), oracle.apply_threshold(u8.copy(), method))
     assert not operations.apply_threshold(np.full((32, 32), 7, dtype=np.uint16), method).any()

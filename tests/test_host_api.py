@@ -300,8 +300,9 @@ def test_three_bin_mean_is_scipys_uniform_filter_bit_for_bit():
 def test_threshold_keyword_arguments_are_checked():
     with pytest.raises(TypeError, match="unexpected keyword argument 'window_size'"):
         operations._check_threshold_kwargs("otsu", {"window_size": 5})
-    with pytest.raises(NotImplementedError, match="nbins"):
-        operations._check_threshold_kwargs("yen", {"nbins": 64})
+    operations._check_threshold_kwargs("yen", {"nbins": 64})
+    with pytest.raises(ValueError, match="nbins"):
+        operations._check_threshold_kwargs("yen", {"nbins": 1})
     operations._check_threshold_kwargs("li", {"tolerance": 0.25, "initial_guess": 300.0})
     wide = np.array([[-70000, 3], [5, 9]], dtype=np.int64)
     with pytest.raises(NotImplementedError, match="65536 bins"):
@@ -362,3 +363,48 @@ def test_lif_raw_reader_round_trip(tmp_path):
     truncated.write_bytes((tmp_path / "synthetic_v2.lif").read_bytes()[:-100])
     with pytest.raises(ValueError):
         lif_raw.read_lif_image(truncated, "lapse")
+
+
+def test_histogram_scans_against_independent_constructions():
+    """The host scans of the product checked against something that is NOT their twin in oracle/: OpenCV's Otsu and
+    Triangle on uint8 images, and brute-force evaluations of the published criteria on small histograms
+    (isodata: the threshold t with t == (mean_below + mean_above) / 2; yen: argmax of the entropic criterion written
+    out term by term; minimum: the valley between the two surviving peaks of a hand-built bimodal histogram)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(99)
+    for trial in range(6):
+        img = np.clip(np.where(rng.random((96, 96)) < 0.35, rng.normal(170, 18, (96, 96)), rng.normal(60, 25 + 3 * trial, (96, 96))), 0, 255).astype(np.uint8)
+        lo, hi = int(img.min()), int(img.max())
+        counts = np.bincount(img.ravel(), minlength=256)[lo : hi + 1]
+        centers = np.arange(lo, hi + 1)
+        t_cv, _ = cv2.threshold(img, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
+        assert np.array_equal(img > operations._otsu_from_histogram(counts, centers), img > t_cv)
+        t_tri, _ = cv2.threshold(img, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_TRIANGLE)
+        assert abs(float(operations._triangle_from_histogram(counts, centers)) - t_tri) <= 1  # OpenCV's end convention differs by one level
+        # isodata, brute force over every candidate threshold: the lowest t with t >= (m_below + m_above) / 2 midpoint rule
+        c = counts.astype(np.float64)
+        best = None
+        for k in range(len(centers) - 1):
+            w_lo, w_hi = c[: k + 1].sum(), c[k + 1 :].sum()
+            if w_lo == 0 or w_hi == 0:
+                continue
+            m_lo = (c[: k + 1] * centers[: k + 1]).sum() / w_lo
+            m_hi = (c[k + 1 :] * centers[k + 1 :]).sum() / w_hi
+            if centers[k] >= (m_lo + m_hi) / 2.0 - 1.0:  # bin width 1: the first centre within one bin of the midpoint
+                best = centers[k]
+                break
+        got = operations._isodata_from_histogram(counts, centers)
+        assert best is not None and abs(float(got) - float(best)) <= 1.0
+        # yen, term by term
+        pmf = c / c.sum()
+        crit = []
+        for k in range(len(centers) - 1):
+            p1 = pmf[: k + 1].sum()
+            crit.append(-np.log((pmf[: k + 1] ** 2).sum() * (pmf[k + 1 :] ** 2).sum()) + 2 * np.log(p1 * (1 - p1)))
+        assert operations._yen_from_histogram(counts, centers) == centers[int(np.argmax(crit))]
+    # minimum: two clean triangular peaks at 20 and 70 with a flat valley bottom at 40..45 -> the first lowest bin
+    hist = np.zeros(100, dtype=np.int64)
+    for k in range(100):
+        hist[k] = max(0, 50 - 5 * abs(k - 20)) + max(0, 80 - 4 * abs(k - 70))
+    t = operations._minimum_from_histogram(hist, np.arange(100))
+    assert 30 <= t <= 50 and hist[int(t)] == hist[30:51].min()
