@@ -23,6 +23,7 @@ AMT_U8, AMT_U16, AMT_I32, AMT_F64, AMT_I64 = 0, 1, 2, 3, 4
 AMT_MAX_RANKS = 8
 AMT_EXTEND_NEAREST, AMT_EXTEND_REFLECT = 0, 1  # amt_gaussian_axis_mode
 AMT_FILTER_TENSOR_CORE, AMT_FILTER_FMA = 0, 1  # amt_fov_config.plane_filter
+AMT_SEG_DECISION_EXACT, AMT_SEG_FLOAT64 = 0, 1  # amt_fov_config.seg_plane_filter
 STAGE_NAMES = ("dog_exact", "dog_lo", "dog_tc_axis0", "dog_tc_axis1", "select", "map", "label_thr", "regions_thr",
                "label_given", "regions_given")  # AMT_STAGE_*
 # per-FOV status bits of the executor (include/amt_b200.h)
@@ -99,7 +100,7 @@ class FovConfig(C.Structure):
         ("out_lo", C.c_double),
         ("out_hi", C.c_double),
         ("plane_filter", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("seg_plane_filter", C.c_int32),
     ]
 
 
@@ -171,6 +172,9 @@ SIGNATURES: dict[str, tuple] = {
     "amt_pairwise_sum_f64": (_i, [_p, _i64, _i64, _p, _p, _sz, _p]),
     "amt_executor_destroy": (None, [_p]),
     "amt_executor_uses_tensor_cores": (_i, [_p]),
+    "amt_executor_decision_exact": (_i, [_p]),
+    "amt_executor_retry_count": (_i64, [_p]),
+    "amt_tcg_error_bound": (_d, [_p]),
     "amt_executor_set_profiling": (_i, [_p, _i]),
     "amt_executor_stage_ms": (_i, [_p, _p, C.POINTER(_i64)]),
     "amt_executor_device_bytes": (_sz, [_p]),

@@ -45,6 +45,11 @@ class FovPipelineConfig:
     # tcgen05 (planes equal to scipy's to ~1e-10 of the [0, 1] scale; falls back to "fma" for shapes it does not take);
     # "fma": float64 with fused multiply-adds (~1e-15).
     plane_filter: str = "tensor_core"
+    # The thresholded channel when the tensor-core path is on.  "decision_exact" (default): tensor-core filter too;
+    # every decision derived from its plane is taken on exactly re-evaluated samples wherever the filter's proven error
+    # bound could change it, so thresholds, labels, counts and tables stay bit-identical to the reference's (its float
+    # plane is within the bound).  "float64": scipy's exact operation order for that channel (plane bit-identical too).
+    seg_plane_filter: str = "decision_exact"
     low_sigma: float = 0.6
     high_sigma: float = 16.0
     bg_percentile: float = 0.0
@@ -118,6 +123,7 @@ class FovBatchExecutor:
                                np.dtype(np.int64): _lib.AMT_I64}[np.dtype(config.given_label_dtype)],
             exact_all_channels=1 if config.exact_all_channels else 0,
             plane_filter={"tensor_core": _lib.AMT_FILTER_TENSOR_CORE, "fma": _lib.AMT_FILTER_FMA}[config.plane_filter],
+            seg_plane_filter={"decision_exact": _lib.AMT_SEG_DECISION_EXACT, "float64": _lib.AMT_SEG_FLOAT64}[config.seg_plane_filter],
             low_sigma=config.low_sigma, high_sigma=config.high_sigma,
             bg_percentile=config.bg_percentile, pct_lo=config.percentile_range[0], pct_hi=config.percentile_range[1],
             out_lo=config.out_range[0], out_hi=config.out_range[1],
@@ -155,6 +161,16 @@ class FovBatchExecutor:
     def uses_tensor_cores(self) -> bool:
         """True when the non-thresholded channels' wide Gaussian runs on tcgen05 (``plane_filter`` resolved)."""
         return bool(self._lib.amt_executor_uses_tensor_cores(self._handle))
+
+    @property
+    def decision_exact(self) -> bool:
+        """True when the thresholded channel runs in decision-exact mode (``seg_plane_filter`` resolved)."""
+        return bool(self._lib.amt_executor_decision_exact(self._handle))
+
+    @property
+    def retry_count(self) -> int:
+        """Fields of view recomputed in float64 because a candidate list of the decision-exact mode overflowed."""
+        return int(self._lib.amt_executor_retry_count(self._handle))
 
     @property
     def device_bytes(self) -> int:

@@ -38,6 +38,31 @@ struct amt_executor {
   double *tmp_lo, *tmp_hi, *dog[2], *pre;
   uint64_t* mm[2];
   amt_tcg* tcg;              // tensor-core Gaussian of the planes that are not thresholded (null: float64 everywhere)
+  // decision-exact thresholded channel (decide.cu): every plane takes the tensor-core filter; the samples a decision
+  // hinges on are re-evaluated in scipy's exact order
+  bool dx;                   // mode resolved at creation
+  bool force_exact;          // set while a field of view whose candidate lists overflowed is recomputed in float64
+  double dx_eps;             // |D' - D| <= dx_eps (amt_tcg_error_bound)
+  int64_t* dx_ranks;         // device copy of the six percentile ranks
+  uint32_t* dx_rank_u32;     // below / count / idx of the order-statistic windows
+  double* dx_rank_val;
+  uint32_t* dx_bin_count;    // per FOV of a chunk
+  uint32_t* dx_bin_idx;
+  double* dx_bin_val;
+  int32_t* retry_dev;        // per FOV of the current run_device batch (grown on demand)
+  int64_t retry_cap;
+  int32_t* retry_slot[2];    // host-fed path: per FOV of a chunk
+  int32_t* retry_host;       // pinned, per FOV of a run_host batch (grown on demand)
+  int64_t retry_host_cap;
+  int64_t retries;           // fields of view recomputed in float64 since creation
+  struct {
+    bool pending;
+    const uint16_t* fovs;
+    const int32_t* given;
+    int64_t n_fov;
+    double *tables_thr, *tables_given, *thresholds, *preprocessed;
+    int32_t *counts_thr, *counts_given, *labels_thr, *labels_given, *status;
+  } last;
   uint8_t* digits;           // its 40-bit intermediate, five uint8 planes per image
   uint16_t* buckets[2];      // bucket12() of the DoG planes (written by the DoG's second pass)
   bool buckets_valid[2];
@@ -89,6 +114,9 @@ int g_exec_swap_prio = 1;
 int g_exec_buckets = 1;
 // amt_tune "exec_tc": 0 switches the tensor-core path off in executors that have one (A/B timing in one process)
 int g_exec_tc = 1;
+// decision-exact mode: capacities of the candidate lists per plane and window / per plane (overflow = float64 retry)
+constexpr int kDxRankCap = 1024;
+constexpr int kDxBinCap = 16384;
 // amt_tune "exec_copy_only": 1 = amt_executor_run_host performs every H2D / D2H copy of a batch with the same staging,
 // streams and events but launches no kernel: the copy-only ceiling the host-fed path is measured against
 int g_exec_copy_only = 0;
@@ -162,6 +190,22 @@ static int enqueue_dog(amt_executor* ex, const uint16_t* in, int g, cudaEvent_t 
   if (wait_input) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, wait_input, 0));
   if (ex->chunks_issued >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, ex->ev_dog_free[slot], 0));
   trace_mark(ex, ex->s_dog, "dog: begin");
+  if (ex->tcg != nullptr && g_exec_tc && ex->dx && !ex->force_exact) {
+    // decision-exact mode: every plane on the tensor cores; process_chunk re-evaluates the deciding samples exactly
+    const tc::PlaneSel all{0, 0};
+    uint16_t* bk = g_exec_buckets ? ex->buckets[slot] : nullptr;
+    ex->buckets_valid[slot] = bk != nullptr;
+    AMT_TRY(minmax_init(ex->mm[slot], planes, ex->s_dog));
+    AMT_TRY(tc::lo2d(in, 1.0 / 65535.0, ex->tmp_lo, planes, c.height, c.width, ex->hw_lo, ex->r_lo, all, ex->s_dog));
+    trace_mark(ex, ex->s_dog, "dog: narrow Gaussian done", AMT_STAGE_DOG_LO);
+    AMT_TRY(tc::tcg_axis0(ex->tcg, in, planes, c.height, c.width, ex->digits, all, ex->s_dog));
+    trace_mark(ex, ex->s_dog, "dog: tensor-core axis 0 done", AMT_STAGE_DOG_TC0);
+    AMT_TRY(tc::tcg_axis1(ex->tcg, ex->digits, ex->tmp_lo, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, bk,
+                          ex->mm[slot], all, ex->s_dog));
+    AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_done[slot], ex->s_dog));
+    trace_mark(ex, ex->s_dog, "dog: end", AMT_STAGE_DOG_TC1);
+    return AMT_OK;
+  }
   if (ex->tcg != nullptr && g_exec_tc) {
     // the thresholded channel: float64 in scipy's order (strip kernels over every C-th plane); the others: narrow
     // Gaussian in float64 (into tmp_lo, whose planes of these channels the strip kernels do not touch), wide Gaussian
@@ -197,9 +241,12 @@ static int enqueue_dog(amt_executor* ex, const uint16_t* in, int g, cudaEvent_t 
 __global__ void fov_status_kernel(const int32_t* __restrict__ cnt_thr, const int32_t* __restrict__ cnt_given,
                                   const int32_t* __restrict__ value_overflow, const int32_t* __restrict__ negative,
                                   const amt_map_params* __restrict__ params, int n_channels, int seg_channel, int max_labels,
-                                  int n_fov, int32_t* __restrict__ status) {
+                                  int n_fov, int32_t* __restrict__ status, const int32_t* __restrict__ retry_flags,
+                                  int32_t* __restrict__ retry_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_fov) return;
+  if (retry_out != nullptr) retry_out[i] = retry_flags[i];
+  if (status == nullptr) return;
   int s = 0;
   if (cnt_thr[i] > max_labels) s |= AMT_FOV_THR_CAPACITY;
   if (cnt_thr[i] == 0) s |= AMT_FOV_THR_EMPTY;
@@ -217,7 +264,7 @@ __global__ void fov_status_kernel(const int32_t* __restrict__ cnt_thr, const int
 // everything after the DoG, on s_compute
 static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* given, int g, double* tab_thr,
                          int32_t* cnt_thr, double* tab_given, int32_t* cnt_given, double* thr_out, int32_t* lab_thr_out,
-                         int32_t* lab_given_out, double* pre_out, int32_t* flags, int32_t* status) {
+                         int32_t* lab_given_out, double* pre_out, int32_t* flags, int32_t* status, int32_t* retry_out) {
   const amt_fov_config& c = ex->cfg;
   const int C = c.n_channels;
   const int64_t H = c.height, W = c.width, HW = H * W;
@@ -239,10 +286,33 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
                                 ex->sel_bytes, st));
   else
     AMT_TRY(amt_select_f64(dog, planes, HW, ex->ranks, 6, mm, ex->stats, ex->sel_scratch, ex->sel_bytes, st));
+  const bool dx = ex->tcg != nullptr && g_exec_tc && ex->dx && !ex->force_exact;
+  int32_t* retry_flags = flags + 2 * c.chunk_fovs;
+  if (dx) {
+    // the thresholded planes' order statistics and min / max become exact (decide.cu)
+    const int64_t seg = c.seg_channel;
+    AMT_TRY(dx::rank_exact(in + seg * HW, (int64_t)C * HW, dog + seg * HW,
+                           ex->buckets_valid[slot] ? ex->buckets[slot] + seg * HW : nullptr, (int64_t)C * HW, g, (int)H, (int)W,
+                           1.0 / 65535.0,
+                           ex->hw_hi, ex->r_hi, ex->hw_lo, ex->r_lo, ex->dx_eps, ex->dx_ranks, ex->stats + seg * 6,
+                           (int64_t)C * 6, mm + seg * 2, (int64_t)C * 2, ex->dx_rank_u32, ex->dx_rank_val, kDxRankCap,
+                           retry_flags, st));
+  }
   trace_mark(ex, st, "  rest: select done", AMT_STAGE_SELECT);
   AMT_TRY(plan_dog_rescale(ex->stats, mm, planes, ex->g_bg, ex->g_lo, ex->g_hi, c.out_lo, c.out_hi, ex->params, st));
   AMT_CUDA_TRY(cudaMemsetAsync(ex->hist256, 0, (size_t)g * 256 * sizeof(uint32_t), st));
-  AMT_TRY(map_launch(dog, AMT_F64, pre, planes, HW, ex->params, ex->hist256, C, c.seg_channel, st));
+  if (dx) {
+    AMT_CUDA_TRY(cudaMemsetAsync(ex->dx_bin_count, 0, (size_t)g * sizeof(uint32_t), st));
+    AMT_TRY(map_launch(dog, AMT_F64, pre, planes, HW, ex->params, ex->hist256, C, c.seg_channel, st, ex->dx_eps,
+                       ex->dx_bin_count, ex->dx_bin_idx, kDxBinCap));
+    // the samples next to a histogram edge or a bin centre: exact value, exact bin
+    AMT_TRY(dx::exact_eval(in + (int64_t)c.seg_channel * HW, (int64_t)C * HW, (int)H, (int)W, 1.0 / 65535.0, ex->hw_hi, ex->r_hi,
+                           ex->hw_lo, ex->r_lo, ex->dx_bin_count, ex->dx_bin_idx, ex->dx_bin_val, g, kDxBinCap, st));
+    AMT_TRY(dx_patch(ex->dx_bin_count, ex->dx_bin_idx, ex->dx_bin_val, kDxBinCap, ex->params, C, c.seg_channel, g, pre, HW,
+                     ex->hist256, retry_flags, st));
+  } else {
+    AMT_TRY(map_launch(dog, AMT_F64, pre, planes, HW, ex->params, ex->hist256, C, c.seg_channel, st));
+  }
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_free[slot], st));
   trace_mark(ex, st, "  rest: map done", AMT_STAGE_MAP);
   // stage B: Otsu -> threshold + CCL + clear_border
@@ -266,11 +336,12 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
       AMT_TRY(region_shape(lab_given, ex->acc, C, cnt_given, g, H, W, c.max_labels, tab_given, ex->shape_scratch,
                            ex->shape_bytes, st));
   }
-  if (status != nullptr) {
+  if (status != nullptr || (dx && retry_out != nullptr)) {
     const bool with_given = c.quantify_given_mask && given;
     fov_status_kernel<<<(unsigned)ceil_div(g, 128), 128, 0, st>>>(cnt_thr, with_given ? cnt_given : nullptr, flags,
                                                                    flags + c.chunk_fovs, ex->params, C, c.seg_channel,
-                                                                   c.max_labels, g, status);
+                                                                   c.max_labels, g, status, retry_flags,
+                                                                   dx ? retry_out : nullptr);
     AMT_LAUNCH_CHECK();
   }
   trace_mark(ex, st, "  rest: end", AMT_STAGE_REGIONS_GIVEN);
@@ -321,7 +392,8 @@ static int alloc_host_slots(amt_executor* ex) {
       AMT_TRY(dmalloc(ex, (void**)&ex->given16_slot[s], (size_t)c.chunk_fovs * HW * sizeof(uint16_t)));
     if (c.given_label_dtype == AMT_I64)
       AMT_TRY(dmalloc(ex, (void**)&ex->given64_slot[s], (size_t)c.chunk_fovs * HW * sizeof(int64_t)));
-    AMT_TRY(dmalloc(ex, (void**)&ex->flag_slot[s], (size_t)2 * c.chunk_fovs * sizeof(int32_t)));
+    AMT_TRY(dmalloc(ex, (void**)&ex->flag_slot[s], (size_t)3 * c.chunk_fovs * sizeof(int32_t)));
+    AMT_TRY(dmalloc(ex, (void**)&ex->retry_slot[s], (size_t)c.chunk_fovs * sizeof(int32_t)));
     AMT_TRY(dmalloc(ex, (void**)&ex->status_slot[s], (size_t)c.chunk_fovs * sizeof(int32_t)));
     AMT_TRY(dmalloc(ex, (void**)&ex->tab_thr_slot[s], tab));
     AMT_TRY(dmalloc(ex, (void**)&ex->tab_given_slot[s], tab));
@@ -421,6 +493,18 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
     const int ts = amt_tcg_create(half_w_hi_host, r_hi, cfg->device, &ex->tcg);
     if (ts == AMT_OK) {
       EX_TRY(dmalloc(ex, (void**)&ex->digits, amt_tcg_digit_bytes(planes, cfg->height, cfg->width)));
+      if (cfg->seg_plane_filter == AMT_SEG_DECISION_EXACT) {
+        ex->dx = true;
+        ex->dx_eps = amt_tcg_error_bound(ex->tcg);
+        EX_TRY(dmalloc(ex, (void**)&ex->dx_ranks, 6 * sizeof(int64_t)));
+        EX_CUDA(cudaMemcpy(ex->dx_ranks, ex->ranks, 6 * sizeof(int64_t), cudaMemcpyHostToDevice));
+        const size_t lists = (size_t)cfg->chunk_fovs * 8;
+        EX_TRY(dmalloc(ex, (void**)&ex->dx_rank_u32, (lists * 2 + lists * kDxRankCap) * sizeof(uint32_t)));
+        EX_TRY(dmalloc(ex, (void**)&ex->dx_rank_val, lists * kDxRankCap * sizeof(double)));
+        EX_TRY(dmalloc(ex, (void**)&ex->dx_bin_count, (size_t)cfg->chunk_fovs * sizeof(uint32_t)));
+        EX_TRY(dmalloc(ex, (void**)&ex->dx_bin_idx, (size_t)cfg->chunk_fovs * kDxBinCap * sizeof(uint32_t)));
+        EX_TRY(dmalloc(ex, (void**)&ex->dx_bin_val, (size_t)cfg->chunk_fovs * kDxBinCap * sizeof(double)));
+      }
     } else if (ts != AMT_ERR_UNSUPPORTED) {
       return fail(ts);
     }
@@ -432,7 +516,7 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
   EX_TRY(dmalloc(ex, &ex->sel_scratch, ex->sel_bytes));
   EX_TRY(dmalloc(ex, (void**)&ex->hist256, (size_t)cfg->chunk_fovs * 256 * sizeof(uint32_t)));
   EX_TRY(dmalloc(ex, (void**)&ex->thr, (size_t)cfg->chunk_fovs * sizeof(double)));
-  EX_TRY(dmalloc(ex, (void**)&ex->flags_dev, (size_t)2 * cfg->chunk_fovs * sizeof(int32_t)));
+  EX_TRY(dmalloc(ex, (void**)&ex->flags_dev, (size_t)3 * cfg->chunk_fovs * sizeof(int32_t)));
   EX_TRY(dmalloc(ex, (void**)&ex->lab_thr, (size_t)cfg->chunk_fovs * HW * sizeof(int32_t)));
   EX_TRY(dmalloc(ex, (void**)&ex->lab_given, (size_t)cfg->chunk_fovs * HW * sizeof(int32_t)));
   ex->label_bytes = amt_label_scratch_bytes(cfg->chunk_fovs, cfg->height, cfg->width, cfg->max_label_value);
@@ -454,7 +538,9 @@ void amt_executor_destroy(amt_executor* ex) {
   cudaSetDevice(ex->cfg.device);
   cudaDeviceSynchronize();
   if (ex->tcg) amt_tcg_destroy(ex->tcg);
-  void* bufs[] = {ex->flags_dev, ex->digits, ex->hw_lo, ex->hw_hi, ex->tmp_lo, ex->tmp_hi, ex->dog[0], ex->dog[1], ex->pre, ex->mm[0], ex->mm[1],
+  if (ex->retry_host) cudaFreeHost(ex->retry_host);
+  void* bufs[] = {ex->dx_ranks, ex->dx_rank_u32, ex->dx_rank_val, ex->dx_bin_count, ex->dx_bin_idx, ex->dx_bin_val, ex->retry_dev,
+                  ex->flags_dev, ex->digits, ex->hw_lo, ex->hw_hi, ex->tmp_lo, ex->tmp_hi, ex->dog[0], ex->dog[1], ex->pre, ex->mm[0], ex->mm[1],
                   ex->buckets[0], ex->buckets[1],
                   ex->stats, ex->params,
                   ex->sel_scratch, ex->hist256, ex->thr, ex->lab_thr, ex->lab_given, ex->label_scratch, ex->acc,
@@ -462,7 +548,7 @@ void amt_executor_destroy(amt_executor* ex) {
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (int s = 0; s < 2; ++s) {
-    void* sb[] = {ex->given64_slot[s], ex->flag_slot[s], ex->status_slot[s], ex->in_slot[s], ex->given_slot[s], ex->given16_slot[s], ex->tab_thr_slot[s], ex->tab_given_slot[s], ex->thr_slot[s],
+    void* sb[] = {ex->retry_slot[s], ex->given64_slot[s], ex->flag_slot[s], ex->status_slot[s], ex->in_slot[s], ex->given_slot[s], ex->given16_slot[s], ex->tab_thr_slot[s], ex->tab_given_slot[s], ex->thr_slot[s],
                   ex->cnt_thr_slot[s], ex->cnt_given_slot[s]};
     for (void* b : sb)
       if (b) cudaFree(b);
@@ -503,6 +589,51 @@ int amt_executor_stage_ms(const amt_executor* ex, double* stage_ms, int64_t* n_c
   return AMT_OK;
 }
 
+// Decision-exact mode, device-resident batch: fields of view whose candidate lists overflowed (retry flag) are
+// recomputed one by one with the float64 strip kernels, into the same output slots.  Runs inside amt_executor_sync.
+static int retry_device(amt_executor* ex) {
+  using namespace amt;
+  if (!ex->last.pending) return AMT_OK;
+  ex->last.pending = false;
+  const amt_fov_config& c = ex->cfg;
+  const int64_t n_fov = ex->last.n_fov;
+  std::vector<int32_t> flags((size_t)n_fov);
+  AMT_CUDA_TRY(cudaMemcpy(flags.data(), ex->retry_dev, (size_t)n_fov * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  const int C = c.n_channels;
+  const int64_t HW = (int64_t)c.height * c.width;
+  const int64_t tab = (int64_t)AMT_TABLE_COLS(C) * c.max_labels;
+  bool any = false;
+  ex->force_exact = true;
+  int rc = AMT_OK;
+  for (int64_t i = 0; i < n_fov && rc == AMT_OK; ++i) {
+    if (!flags[(size_t)i]) continue;
+    any = true;
+    ex->retries += 1;
+    rc = enqueue_dog(ex, ex->last.fovs + i * C * HW, 1, nullptr);
+    if (rc != AMT_OK) break;
+    if (cudaMemsetAsync(ex->flags_dev, 0, (size_t)3 * c.chunk_fovs * sizeof(int32_t), ex->s_compute) != cudaSuccess) {
+      rc = AMT_ERR_CUDA;
+      break;
+    }
+    rc = process_chunk(ex, ex->last.fovs + i * C * HW, ex->last.given ? ex->last.given + i * HW : nullptr, 1,
+                       ex->last.tables_thr + i * tab, ex->last.counts_thr + i,
+                       ex->last.tables_given ? ex->last.tables_given + i * tab : nullptr,
+                       ex->last.counts_given ? ex->last.counts_given + i : nullptr,
+                       ex->last.thresholds ? ex->last.thresholds + i : nullptr,
+                       ex->last.labels_thr ? ex->last.labels_thr + i * HW : nullptr,
+                       ex->last.labels_given ? ex->last.labels_given + i * HW : nullptr,
+                       ex->last.preprocessed ? ex->last.preprocessed + i * C * HW : nullptr, ex->flags_dev,
+                       ex->last.status ? ex->last.status + i : nullptr, nullptr);
+  }
+  ex->force_exact = false;
+  if (rc != AMT_OK) return rc;
+  if (any) {
+    AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_dog));
+    AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_compute));
+  }
+  return AMT_OK;
+}
+
 int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_t* given_labels, int64_t n_fov,
                             double* tables_thr, int32_t* counts_thr, double* tables_given, int32_t* counts_given,
                             double* thresholds, int32_t* labels_thr, int32_t* labels_given, double* preprocessed,
@@ -512,24 +643,107 @@ int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_
   const amt_fov_config& c = ex->cfg;
   if (c.quantify_given_mask && given_labels && (!tables_given || !counts_given)) return AMT_ERR_INVALID;
   AMT_CUDA_TRY(cudaSetDevice(c.device));
+  if (ex->last.pending) AMT_TRY(amt_executor_sync(ex));  // a batch whose retry check has not run yet
   const int C = c.n_channels;
   const int64_t HW = (int64_t)c.height * c.width;
   const int64_t tab = (int64_t)AMT_TABLE_COLS(C) * c.max_labels;
+  const bool dx = ex->tcg != nullptr && g_exec_tc && ex->dx;
+  if (dx && n_fov > ex->retry_cap) {
+    if (ex->retry_dev) cudaFree(ex->retry_dev);
+    ex->retry_dev = nullptr;
+    AMT_CUDA_TRY(cudaMalloc((void**)&ex->retry_dev, (size_t)n_fov * sizeof(int32_t)));
+    ex->retry_cap = n_fov;
+  }
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_start, ex->s_compute));
   AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, ex->ev_start, 0));
   for (int64_t f0 = 0; f0 < n_fov; f0 += c.chunk_fovs) {
     const int g = (int)((n_fov - f0 < c.chunk_fovs) ? n_fov - f0 : c.chunk_fovs);
     AMT_TRY(enqueue_dog(ex, fovs + f0 * C * HW, g, nullptr));
-    AMT_CUDA_TRY(cudaMemsetAsync(ex->flags_dev, 0, (size_t)2 * c.chunk_fovs * sizeof(int32_t), ex->s_compute));
+    AMT_CUDA_TRY(cudaMemsetAsync(ex->flags_dev, 0, (size_t)3 * c.chunk_fovs * sizeof(int32_t), ex->s_compute));
     AMT_TRY(process_chunk(ex, fovs + f0 * C * HW, given_labels ? given_labels + f0 * HW : nullptr, g,
                           tables_thr + f0 * tab, counts_thr + f0, tables_given ? tables_given + f0 * tab : nullptr,
                           counts_given ? counts_given + f0 : nullptr, thresholds ? thresholds + f0 : nullptr,
                           labels_thr ? labels_thr + f0 * HW : nullptr, labels_given ? labels_given + f0 * HW : nullptr,
                           preprocessed ? preprocessed + f0 * C * HW : nullptr, ex->flags_dev,
-                          status ? status + f0 : nullptr));
+                          status ? status + f0 : nullptr, dx ? ex->retry_dev + f0 : nullptr));
   }
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_stop, ex->s_compute));
+  if (dx) {
+    ex->last.pending = true;
+    ex->last.fovs = fovs, ex->last.given = given_labels, ex->last.n_fov = n_fov;
+    ex->last.tables_thr = tables_thr, ex->last.tables_given = tables_given, ex->last.thresholds = thresholds;
+    ex->last.preprocessed = preprocessed, ex->last.counts_thr = counts_thr, ex->last.counts_given = counts_given;
+    ex->last.labels_thr = labels_thr, ex->last.labels_given = labels_given, ex->last.status = status;
+  }
   trace_dump(ex);
+  return AMT_OK;
+}
+
+// H2D of one chunk of a host-fed batch into staging slot s (on s_in), label masks converted on the device
+static int upload_chunk(amt_executor* ex, int s, const uint16_t* fovs_host, const void* given_labels_host, int64_t f0, int g) {
+  using namespace amt;
+  const amt_fov_config& c = ex->cfg;
+  const int C = c.n_channels;
+  const int64_t HW = (int64_t)c.height * c.width;
+  const bool given = c.quantify_given_mask && given_labels_host;
+  AMT_CUDA_TRY(cudaMemcpyAsync(ex->in_slot[s], fovs_host + f0 * C * HW, (size_t)g * C * HW * sizeof(uint16_t),
+                               cudaMemcpyHostToDevice, ex->s_in));
+  AMT_CUDA_TRY(cudaMemsetAsync(ex->flag_slot[s], 0, (size_t)3 * c.chunk_fovs * sizeof(int32_t), ex->s_in));
+  if (given && c.given_label_dtype == AMT_I64) {
+    AMT_CUDA_TRY(cudaMemcpyAsync(ex->given64_slot[s], (const int64_t*)given_labels_host + f0 * HW,
+                                 (size_t)g * HW * sizeof(int64_t), cudaMemcpyHostToDevice, ex->s_in));
+    narrow_i64_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given64_slot[s], ex->given_slot[s], HW, g,
+                                                         ex->flag_slot[s] + c.chunk_fovs);
+    AMT_LAUNCH_CHECK();
+  } else if (given && c.given_label_dtype == AMT_U16) {
+    AMT_CUDA_TRY(cudaMemcpyAsync(ex->given16_slot[s], (const uint16_t*)given_labels_host + f0 * HW,
+                                 (size_t)g * HW * sizeof(uint16_t), cudaMemcpyHostToDevice, ex->s_in));
+    widen_u16_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given16_slot[s], ex->given_slot[s], (int64_t)g * HW / 8);
+    AMT_LAUNCH_CHECK();
+  } else if (given) {
+    AMT_CUDA_TRY(cudaMemcpyAsync(ex->given_slot[s], (const int32_t*)given_labels_host + f0 * HW,
+                                 (size_t)g * HW * sizeof(int32_t), cudaMemcpyHostToDevice, ex->s_in));
+  }
+  AMT_CUDA_TRY(cudaEventRecord(ex->ev_in[s], ex->s_in));
+  return AMT_OK;
+}
+
+// D2H of one chunk's results from staging slot s (on s_out, after ev_done[s])
+static int download_chunk(amt_executor* ex, int s, int64_t f0, int g, bool given, double* tables_thr_host,
+                          int32_t* counts_thr_host, double* tables_given_host, int32_t* counts_given_host,
+                          double* thresholds_host, int32_t* status_host, bool with_retry) {
+  using namespace amt;
+  const amt_fov_config& c = ex->cfg;
+  const int64_t tab = (int64_t)AMT_TABLE_COLS(c.n_channels) * c.max_labels;
+  AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_out, ex->ev_done[s], 0));
+  AMT_CUDA_TRY(cudaMemcpyAsync(tables_thr_host + f0 * tab, ex->tab_thr_slot[s], (size_t)g * tab * sizeof(double),
+                               cudaMemcpyDeviceToHost, ex->s_out));
+  AMT_CUDA_TRY(cudaMemcpyAsync(counts_thr_host + f0, ex->cnt_thr_slot[s], (size_t)g * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, ex->s_out));
+  if (given) {
+    AMT_CUDA_TRY(cudaMemcpyAsync(tables_given_host + f0 * tab, ex->tab_given_slot[s], (size_t)g * tab * sizeof(double),
+                                 cudaMemcpyDeviceToHost, ex->s_out));
+    AMT_CUDA_TRY(cudaMemcpyAsync(counts_given_host + f0, ex->cnt_given_slot[s], (size_t)g * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, ex->s_out));
+  }
+  if (thresholds_host)
+    AMT_CUDA_TRY(cudaMemcpyAsync(thresholds_host + f0, ex->thr_slot[s], (size_t)g * sizeof(double), cudaMemcpyDeviceToHost,
+                                 ex->s_out));
+  if (status_host)
+    AMT_CUDA_TRY(cudaMemcpyAsync(status_host + f0, ex->status_slot[s], (size_t)g * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 ex->s_out));
+  if (with_retry)
+    AMT_CUDA_TRY(cudaMemcpyAsync(ex->retry_host + f0, ex->retry_slot[s], (size_t)g * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 ex->s_out));
+  AMT_CUDA_TRY(cudaEventRecord(ex->ev_out[s], ex->s_out));
+  return AMT_OK;
+}
+
+static int sync_all(amt_executor* ex) {
+  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_in));
+  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_dog));
+  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_compute));
+  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_out));
   return AMT_OK;
 }
 
@@ -540,43 +754,26 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const voi
   if (!ex || !fovs_host || !tables_thr_host || !counts_thr_host || n_fov <= 0) return AMT_ERR_INVALID;
   const amt_fov_config& c = ex->cfg;
   const bool given = c.quantify_given_mask && given_labels_host;
-  const bool u16_labels = c.given_label_dtype == AMT_U16;
-  const bool i64_labels = c.given_label_dtype == AMT_I64;
   if (given && (!tables_given_host || !counts_given_host)) return AMT_ERR_INVALID;
-  if (u16_labels && ((int64_t)c.height * c.width) % 8 != 0) return AMT_ERR_UNSUPPORTED;
-  if (i64_labels && ((int64_t)c.height * c.width) % 2 != 0) return AMT_ERR_UNSUPPORTED;
+  if (c.given_label_dtype == AMT_U16 && ((int64_t)c.height * c.width) % 8 != 0) return AMT_ERR_UNSUPPORTED;
+  if (c.given_label_dtype == AMT_I64 && ((int64_t)c.height * c.width) % 2 != 0) return AMT_ERR_UNSUPPORTED;
   AMT_CUDA_TRY(cudaSetDevice(c.device));
+  if (ex->last.pending) AMT_TRY(amt_executor_sync(ex));
   AMT_TRY(alloc_host_slots(ex));
-  const int C = c.n_channels;
-  const int64_t HW = (int64_t)c.height * c.width;
-  const int64_t tab = (int64_t)AMT_TABLE_COLS(C) * c.max_labels;
+  const bool dx = ex->tcg != nullptr && g_exec_tc && ex->dx && !g_exec_copy_only;
+  if (dx && n_fov > ex->retry_host_cap) {
+    if (ex->retry_host) cudaFreeHost(ex->retry_host);
+    ex->retry_host = nullptr;
+    AMT_CUDA_TRY(cudaMallocHost((void**)&ex->retry_host, (size_t)n_fov * sizeof(int32_t)));
+    ex->retry_host_cap = n_fov;
+  }
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_start, ex->s_compute));
   AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_dog, ex->ev_start, 0));
-  int64_t chunk = 0;
-  for (int64_t f0 = 0; f0 < n_fov; f0 += c.chunk_fovs, ++chunk) {
-    const int g = (int)((n_fov - f0 < c.chunk_fovs) ? n_fov - f0 : c.chunk_fovs);
+  auto issue = [&](int64_t chunk, int64_t f0, int g) -> int {
     const int s = (int)(chunk & 1);
     // input slot s is free once the compute that last read it has finished
     if (chunk >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_in, ex->ev_done[s], 0));
-    AMT_CUDA_TRY(cudaMemcpyAsync(ex->in_slot[s], fovs_host + f0 * C * HW, (size_t)g * C * HW * sizeof(uint16_t),
-                                 cudaMemcpyHostToDevice, ex->s_in));
-    AMT_CUDA_TRY(cudaMemsetAsync(ex->flag_slot[s], 0, (size_t)2 * c.chunk_fovs * sizeof(int32_t), ex->s_in));
-    if (given && i64_labels) {
-      AMT_CUDA_TRY(cudaMemcpyAsync(ex->given64_slot[s], (const int64_t*)given_labels_host + f0 * HW,
-                                   (size_t)g * HW * sizeof(int64_t), cudaMemcpyHostToDevice, ex->s_in));
-      narrow_i64_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given64_slot[s], ex->given_slot[s], HW, g,
-                                                           ex->flag_slot[s] + c.chunk_fovs);
-      AMT_LAUNCH_CHECK();
-    } else if (given && u16_labels) {
-      AMT_CUDA_TRY(cudaMemcpyAsync(ex->given16_slot[s], (const uint16_t*)given_labels_host + f0 * HW,
-                                   (size_t)g * HW * sizeof(uint16_t), cudaMemcpyHostToDevice, ex->s_in));
-      widen_u16_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given16_slot[s], ex->given_slot[s], (int64_t)g * HW / 8);
-      AMT_LAUNCH_CHECK();
-    } else if (given) {
-      AMT_CUDA_TRY(cudaMemcpyAsync(ex->given_slot[s], (const int32_t*)given_labels_host + f0 * HW,
-                                   (size_t)g * HW * sizeof(int32_t), cudaMemcpyHostToDevice, ex->s_in));
-    }
-    AMT_CUDA_TRY(cudaEventRecord(ex->ev_in[s], ex->s_in));
+    AMT_TRY(upload_chunk(ex, s, fovs_host, given_labels_host, f0, g));
     // output slot s is free once its previous D2H has finished
     AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_compute, ex->ev_in[s], 0));
     if (chunk >= 2) AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_compute, ex->ev_out[s], 0));
@@ -584,33 +781,33 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const voi
       AMT_TRY(enqueue_dog(ex, ex->in_slot[s], g, ex->ev_in[s]));
       AMT_TRY(process_chunk(ex, ex->in_slot[s], given ? ex->given_slot[s] : nullptr, g, ex->tab_thr_slot[s],
                             ex->cnt_thr_slot[s], ex->tab_given_slot[s], ex->cnt_given_slot[s], ex->thr_slot[s], nullptr,
-                            nullptr, nullptr, ex->flag_slot[s], ex->status_slot[s]));
+                            nullptr, nullptr, ex->flag_slot[s], ex->status_slot[s], ex->retry_slot[s]));
     }
     AMT_CUDA_TRY(cudaEventRecord(ex->ev_done[s], ex->s_compute));
-    AMT_CUDA_TRY(cudaStreamWaitEvent(ex->s_out, ex->ev_done[s], 0));
-    AMT_CUDA_TRY(cudaMemcpyAsync(tables_thr_host + f0 * tab, ex->tab_thr_slot[s], (size_t)g * tab * sizeof(double),
-                                 cudaMemcpyDeviceToHost, ex->s_out));
-    AMT_CUDA_TRY(cudaMemcpyAsync(counts_thr_host + f0, ex->cnt_thr_slot[s], (size_t)g * sizeof(int32_t),
-                                 cudaMemcpyDeviceToHost, ex->s_out));
-    if (given) {
-      AMT_CUDA_TRY(cudaMemcpyAsync(tables_given_host + f0 * tab, ex->tab_given_slot[s], (size_t)g * tab * sizeof(double),
-                                   cudaMemcpyDeviceToHost, ex->s_out));
-      AMT_CUDA_TRY(cudaMemcpyAsync(counts_given_host + f0, ex->cnt_given_slot[s], (size_t)g * sizeof(int32_t),
-                                   cudaMemcpyDeviceToHost, ex->s_out));
-    }
-    if (thresholds_host)
-      AMT_CUDA_TRY(cudaMemcpyAsync(thresholds_host + f0, ex->thr_slot[s], (size_t)g * sizeof(double),
-                                   cudaMemcpyDeviceToHost, ex->s_out));
-    if (status_host)
-      AMT_CUDA_TRY(cudaMemcpyAsync(status_host + f0, ex->status_slot[s], (size_t)g * sizeof(int32_t),
-                                   cudaMemcpyDeviceToHost, ex->s_out));
-    AMT_CUDA_TRY(cudaEventRecord(ex->ev_out[s], ex->s_out));
+    return download_chunk(ex, s, f0, g, given, tables_thr_host, counts_thr_host, tables_given_host, counts_given_host,
+                          thresholds_host, status_host, dx && !ex->force_exact);
+  };
+  int64_t chunk = 0;
+  for (int64_t f0 = 0; f0 < n_fov; f0 += c.chunk_fovs, ++chunk) {
+    const int g = (int)((n_fov - f0 < c.chunk_fovs) ? n_fov - f0 : c.chunk_fovs);
+    AMT_TRY(issue(chunk, f0, g));
   }
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_stop, ex->s_compute));
-  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_in));
-  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_dog));
-  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_compute));
-  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_out));
+  AMT_TRY(sync_all(ex));
+  if (dx) {
+    // fields of view whose candidate lists overflowed: once more, one by one, with the float64 strip kernels
+    ex->force_exact = true;
+    int rc = AMT_OK;
+    for (int64_t i = 0; i < n_fov && rc == AMT_OK; ++i) {
+      if (!ex->retry_host[i]) continue;
+      ex->retries += 1;
+      rc = issue(chunk, i, 1);  // every stream is idle: the slot-reuse waits are satisfied at once
+      if (rc == AMT_OK) rc = sync_all(ex);
+      ++chunk;
+    }
+    ex->force_exact = false;
+    AMT_TRY(rc);
+  }
   return AMT_OK;
 }
 
@@ -618,12 +815,12 @@ int amt_executor_sync(amt_executor* ex) {
   using namespace amt;
   if (!ex) return AMT_ERR_INVALID;
   AMT_CUDA_TRY(cudaSetDevice(ex->cfg.device));
-  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_in));
-  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_dog));
-  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_compute));
-  AMT_CUDA_TRY(cudaStreamSynchronize(ex->s_out));
-  return AMT_OK;
+  AMT_TRY(sync_all(ex));
+  return retry_device(ex);
 }
+
+int64_t amt_executor_retry_count(const amt_executor* ex) { return ex ? ex->retries : -1; }
+int amt_executor_decision_exact(const amt_executor* ex) { return ex && ex->dx ? 1 : 0; }
 
 float amt_executor_last_ms(amt_executor* ex) {
   if (!ex) return -1.0f;

@@ -22,7 +22,26 @@ int select_f64_bucketed(const double* data, const uint16_t* buckets, int64_t n_i
 // hist256 (optional): plane i gets a histogram iff i % hist_every == hist_offset, stored at
 // hist256[(i / hist_every) * 256].
 int map_launch(const void* in, int in_dtype, double* out, int64_t n_img, int64_t n, const amt_map_params* params,
-               uint32_t* hist256, int hist_every, int hist_offset, cudaStream_t st);
+               uint32_t* hist256, int hist_every, int hist_offset, cudaStream_t st,
+               // decision-exact mode (decide.cu): samples of the histogram planes within the propagated cand_eps of a bin
+               // edge / centre are listed (cand_count[hist plane], cand_idx[hist plane * cand_cap + k])
+               double cand_eps = 0.0, uint32_t* cand_count = nullptr, uint32_t* cand_idx = nullptr, int cand_cap = 0);
+int dx_patch(const uint32_t* cand_count, const uint32_t* cand_idx, const double* exact_in, int cap, const amt_map_params* params,
+             int hist_every, int hist_offset, int64_t n_hist, double* out, int64_t n, uint32_t* hist256, int32_t* retry,
+             cudaStream_t st);
+namespace dx {
+// exact order statistics (6 percentile ranks + min + max) of n_img planes whose approximate plane `dog` is within eps
+// of the exact difference of Gaussians of `in`; stats / mm are read (approximate) and overwritten (exact)
+int rank_exact(const uint16_t* in, int64_t in_img_stride, const double* dog, const uint16_t* buckets /* or null */,
+               int64_t dog_img_stride, int64_t n_img, int h, int w, double scale, const double* hw_hi, int r_hi,
+               const double* hw_lo, int r_lo, double eps,
+               const int64_t* ranks_dev, double* stats, int64_t stats_stride, uint64_t* mm, int64_t mm_stride,
+               uint32_t* scratch_u32, double* scratch_val, int cap, int32_t* retry, cudaStream_t st);
+// exact difference of Gaussians of the listed pixels: list l = image l, count[l] entries (capped at cap)
+int exact_eval(const uint16_t* in, int64_t in_img_stride, int h, int w, double scale, const double* hw_hi, int r_hi,
+               const double* hw_lo, int r_lo, const uint32_t* count, const uint32_t* idx, double* val, int n_lists, int cap,
+               cudaStream_t st);
+}  // namespace dx
 
 int plan_dog_rescale(const double* stats, const uint64_t* mm, int64_t n_img, double g_bg, double g_lo, double g_hi,
                      double o1, double o2, amt_map_params* params, cudaStream_t st);

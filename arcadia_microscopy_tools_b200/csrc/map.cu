@@ -233,7 +233,8 @@ __device__ __forceinline__ void st_stream(double* p, double a, double b) {
 template <typename InT, bool HIST, bool VEC>
 __global__ void __launch_bounds__(256)
 map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, const amt_map_params* __restrict__ params,
-           uint32_t* __restrict__ hist256, int hist_every, int hist_offset) {
+           uint32_t* __restrict__ hist256, int hist_every, int hist_offset, const double cand_eps,
+           uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx, const int cand_cap) {
   __shared__ uint32_t s_hist[HIST ? 8 * 256 : 1];
   __shared__ double s_edges[HIST ? 257 : 1];
   // HIST launch: grid.y runs over the histogram planes only (img = y * hist_every + hist_offset).
@@ -256,6 +257,21 @@ map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, cons
   const DivConst hden = make_div_const(HIST ? hr.denom : 1.0);
   const DivConst den = make_div_const(dsub(p.p2, p.p1));
   const double gain = dsub(p.o2, p.o1);
+  // Decision-exact mode (decide.cu): the input plane is within cand_eps of the exact one, hence the output within
+  // tol of the exact output; a sample closer than that to a bin edge or to its bin's centre (the Otsu threshold is
+  // a centre) is listed for exact re-evaluation.  The outer edges decide nothing (every exact value lies inside
+  // [first, last] too); a constant output plane (FILL, p1 == p2) decides nothing at all.
+  const bool collect = HIST && cand_count != nullptr && map_mode(p) == 3;
+  const double tol = collect ? cand_eps * fabs(gain) / dsub(p.p2, p.p1) * 1.000001 + 1e-15 : -1.0;
+  const int64_t img_h = HIST ? (int64_t)blockIdx.y : 0;
+  auto consider = [&](double x, int bin, int64_t index) {
+    const double lo_e = s_edges[bin], hi_e = s_edges[bin + 1];
+    const double centre = dmul(dadd(lo_e, hi_e), 0.5);
+    if ((bin > 0 && x - lo_e <= tol) || (bin < 255 && hi_e - x <= tol) || fabs(x - centre) <= tol) {
+      const uint32_t pos = atomicAdd(&cand_count[img_h], 1u);
+      if (pos < (uint32_t)cand_cap) cand_idx[img_h * cand_cap + pos] = (uint32_t)index;
+    }
+  };
   auto run = [&](auto mode_tag) {
     constexpr int MODE = decltype(mode_tag)::value;
     if (VEC) {
@@ -289,7 +305,11 @@ map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, cons
         if (HIST && do_hist) {
 #pragma unroll
           for (int e = 0; e < 8; ++e)
-            if (e < 4 || second) atomicAdd(&wh[hist_bin_table(hr, hden, s_edges, v[e])], 1u);
+            if (e < 4 || second) {
+              const int bin = hist_bin_table(hr, hden, s_edges, v[e]);
+              atomicAdd(&wh[bin], 1u);
+              if (collect) consider(v[e], bin, 4 * (e < 4 ? q : q2) + (e & 3));
+            }
         }
       }
     } else {
@@ -297,7 +317,11 @@ map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, cons
       for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += step) {
         const double y = map_value_mode<MODE>(map_load<InT>(src + i), p, den, gain);
         dst[i] = y;
-        if (HIST && do_hist) atomicAdd(&wh[hist_bin_table(hr, hden, s_edges, y)], 1u);
+        if (HIST && do_hist) {
+          const int bin = hist_bin_table(hr, hden, s_edges, y);
+          atomicAdd(&wh[bin], 1u);
+          if (collect) consider(y, bin, i);
+        }
       }
     }
   };
@@ -338,6 +362,35 @@ hist256_kernel(const double* __restrict__ data, int64_t n, const uint64_t* __res
 #pragma unroll
   for (int wv = 0; wv < 8; ++wv) c += s_hist[wv * 256 + threadIdx.x];
   if (c) atomicAdd(&hist256[img * 256 + threadIdx.x], c);
+}
+
+// Decision-exact mode: the listed samples of the histogram planes get their exact value (the exact difference of
+// Gaussians through the plane's map) and their histogram count moves to the exact value's bin.
+__global__ void __launch_bounds__(256)
+dx_patch_kernel(const uint32_t* __restrict__ cand_count, const uint32_t* __restrict__ cand_idx, const double* __restrict__ exact_in,
+                int cap, const amt_map_params* __restrict__ params, int hist_every, int hist_offset, double* __restrict__ out,
+                int64_t n, uint32_t* __restrict__ hist256, int32_t* __restrict__ retry) {
+  const int64_t img_h = blockIdx.y;
+  const int64_t img = img_h * hist_every + hist_offset;
+  const uint32_t c = cand_count[img_h];
+  if (c > (uint32_t)cap) {  // list overflow: this image is recomputed in float64
+    if (blockIdx.x == 0 && threadIdx.x == 0) retry[img_h] = 1;
+    return;
+  }
+  const amt_map_params p = params[img];
+  const HistRange hr = make_hist_range(p.hist_first, p.hist_last);
+  double* dst = out + img * n;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < c; k += gridDim.x * blockDim.x) {
+    const uint32_t pix = cand_idx[img_h * cap + k];
+    const double approx = dst[pix];
+    const double exact = map_value(exact_in[img_h * cap + k], p);
+    dst[pix] = exact;
+    const int b0 = hist_bin(hr, approx), b1 = hist_bin(hr, exact);
+    if (b0 != b1) {
+      atomicSub(&hist256[img_h * 256 + b0], 1u);
+      atomicAdd(&hist256[img_h * 256 + b1], 1u);
+    }
+  }
 }
 
 __global__ void plan_dog_rescale_kernel(const double* __restrict__ stats, const uint64_t* __restrict__ mm, int64_t n_img,
@@ -551,7 +604,8 @@ static unsigned stream_blocks(int64_t n, int64_t n_img, int per_thread) {
 }
 
 int map_launch(const void* in, int in_dtype, double* out, int64_t n_img, int64_t n, const amt_map_params* params,
-               uint32_t* hist256, int hist_every, int hist_offset, cudaStream_t st) {
+               uint32_t* hist256, int hist_every, int hist_offset, cudaStream_t st, double cand_eps, uint32_t* cand_count,
+               uint32_t* cand_idx, int cand_cap) {
   if (!in || !out || !params || n_img <= 0 || n <= 0 || n_img > 65535 || hist_every < 1) return AMT_ERR_INVALID;
   const bool vec = (n % 4 == 0) && (((uintptr_t)in) % 16 == 0) && (((uintptr_t)out) % 16 == 0);
   // planes with a histogram go through the HIST instantiation (66 registers, 10 KB of shared memory), all
@@ -565,11 +619,12 @@ int map_launch(const void* in, int in_dtype, double* out, int64_t n_img, int64_t
   do {                                                                                                            \
     if (plain_needed) {                                                                                           \
       map_kernel<T, false, V><<<grid, 256, 0, st>>>((const T*)in, out, n, params, nullptr, hist256 ? hist_every : 0, \
-                                                    hist_offset);                                                 \
+                                                    hist_offset, 0.0, nullptr, nullptr, 0);                       \
       count_launch();                                                                                             \
     }                                                                                                             \
     if (n_hist > 0)                                                                                               \
-      map_kernel<T, true, V><<<hgrid, 256, 0, st>>>((const T*)in, out, n, params, hist256, hist_every, hist_offset); \
+      map_kernel<T, true, V><<<hgrid, 256, 0, st>>>((const T*)in, out, n, params, hist256, hist_every, hist_offset, \
+                                                    cand_eps, cand_count, cand_idx, cand_cap);                    \
   } while (0)
   if (in_dtype == AMT_F64) {
     if (vec) AMT_MAP_LAUNCH(double, true); else AMT_MAP_LAUNCH(double, false);
@@ -589,6 +644,15 @@ int map_launch(const void* in, int in_dtype, double* out, int64_t n_img, int64_t
       return AMT_ERR_CUDA;
     }
   }
+  return AMT_OK;
+}
+
+int dx_patch(const uint32_t* cand_count, const uint32_t* cand_idx, const double* exact_in, int cap, const amt_map_params* params,
+             int hist_every, int hist_offset, int64_t n_hist, double* out, int64_t n, uint32_t* hist256, int32_t* retry,
+             cudaStream_t st) {
+  dx_patch_kernel<<<dim3(4, (unsigned)n_hist), 256, 0, st>>>(cand_count, cand_idx, exact_in, cap, params, hist_every, hist_offset,
+                                                           out, n, hist256, retry);
+  AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
 
@@ -624,7 +688,7 @@ extern "C" {
 
 int amt_map(const void* in, int in_dtype, double* out, int64_t n_img, int64_t n, const amt_map_params* params,
             uint32_t* hist256, amt_stream_t stream) {
-  return amt::map_launch(in, in_dtype, out, n_img, n, params, hist256, 1, 0, amt::as_stream(stream));
+  return amt::map_launch(in, in_dtype, out, n_img, n, params, hist256, 1, 0, amt::as_stream(stream), 0.0, nullptr, nullptr, 0);
 }
 
 int amt_plan_dog_rescale(const double* order_stats, const uint64_t* minmax_keys, int64_t n_img, double g_bg,

@@ -825,6 +825,7 @@ struct amt_tcg {
   uint8_t* band;             // device [WD][128][256]
   uint64_t* suffix;          // device [HALO + 2]
   double* suffix_f;          // device [HALO + 2]: suffix * 2^-16
+  double weight_l1_error;    // sum over the taps of |W[t] * 2^-S - w[t]|
 };
 
 namespace amt {
@@ -987,6 +988,8 @@ int amt_tcg_create(const double* half_w_host, int radius, int device, amt_tcg** 
   g->r = radius;
   g->S = S;
   g->W = new std::vector<uint64_t>(W);
+  for (int t = 0; t <= radius; ++t)
+    g->weight_l1_error += (t == 0 ? 1.0 : 2.0) * std::fabs(std::ldexp((double)W[t], -S) - half_w_host[t]);
   std::vector<uint8_t> band((size_t)WD * MT * KBAND, 0);
   for (int d = 0; d < WD; ++d)
     for (int m = 0; m < MT; ++m)
@@ -1029,6 +1032,18 @@ int amt_tcg_weights(const amt_tcg* g, uint64_t* w_host, int* scale_bits) {
   for (int t = 0; t <= g->r; ++t) w_host[t] = (*g->W)[t];
   *scale_bits = g->S;
   return AMT_OK;
+}
+
+/* |G' - G| <= this, on the [0, 1] scale of img_as_float, for every sample of every image: G' = the two tensor-core
+ * passes, G = the float64 Gaussian in scipy's operation order.  Terms (X = 1 bounds the scaled samples):
+ *   weights rounded to integers, both passes        2 * sum_t |W[t] 2^-S - w[t]|
+ *   pass-1 result rounded to 40 bits                 2^-41 (half a unit of 2^-24 / 65535 per sample, times weights summing to 1)
+ *   digit products dropped in pass 2 (d + s < 2)     2^-45
+ *   float64 roundings of scipy's 2 x (2 r + 2) operations and of the final conversion / scaling: < 1e-13
+ * plus a 1 % margin. */
+double amt_tcg_error_bound(const amt_tcg* g) {
+  if (!g) return -1.0;
+  return 1.01 * (2.0 * g->weight_l1_error + std::ldexp(1.0, -41) + std::ldexp(1.0, -45) + 1e-13);
 }
 
 int amt_tcg_supported(int64_t h, int64_t w, int radius) {

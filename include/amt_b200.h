@@ -125,6 +125,9 @@ int amt_tcg_create(const double* half_w_host, int radius, int device, amt_tcg** 
 void amt_tcg_destroy(amt_tcg* g);
 int amt_tcg_weights(const amt_tcg* g, uint64_t* w_host, int* scale_bits);
 int amt_tcg_supported(int64_t h, int64_t w, int radius);
+/* Proven bound on |tensor-core Gaussian - float64 Gaussian in scipy's order| per sample, [0, 1] input scale
+ * (see csrc/tcgauss.cu); what the decision-exact mode of the executor widens its comparisons by. */
+double amt_tcg_error_bound(const amt_tcg* g);
 size_t amt_tcg_digit_bytes(int64_t n_img, int64_t h, int64_t w);
 int amt_tcg_axis0(const amt_tcg* g, const uint16_t* in, int64_t n_img, int64_t h, int64_t w, uint8_t* digits,
                   int skip_every, int skip_offset, amt_stream_t stream);
@@ -394,10 +397,19 @@ typedef struct amt_fov_config {
                                     Toeplitz passes (amt_tcg_*; planes equal to scipy's to ~1e-10 of the [0, 1] scale)
                                     whenever amt_tcg_supported(height, width, radius) and n_channels >= 2, else the
                                     next mode; AMT_FILTER_FMA (1) = float64 with fused multiply-adds (~1e-15) */
-  int32_t reserved0;
+  int32_t seg_plane_filter;      /* the thresholded channel when the tensor-core path is on: AMT_SEG_DECISION_EXACT
+                                    (0, default) = tensor-core filter too; every decision derived from its plane
+                                    (order statistics, histogram bins, the mask) is taken on exactly re-evaluated
+                                    samples wherever the filter's proven error bound could change it (csrc/decide.cu),
+                                    so thresholds, labels, counts and tables stay bit-identical to the reference's;
+                                    its float plane is then within the bound like the other channels'.
+                                    AMT_SEG_FLOAT64 (1) = the float64 strip kernels in scipy's order for that channel
+                                    (its plane bit-identical as well) */
 } amt_fov_config;
 #define AMT_FILTER_TENSOR_CORE 0
 #define AMT_FILTER_FMA 1
+#define AMT_SEG_DECISION_EXACT 0
+#define AMT_SEG_FLOAT64 1
 
 /* half_w_*_host: NumPy-computed half kernels (radius+1 doubles each). */
 int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host, int r_lo,
@@ -406,6 +418,11 @@ void amt_executor_destroy(amt_executor* ex);
 size_t amt_executor_device_bytes(const amt_executor* ex);
 /* 1 if this executor filters the non-thresholded channels on the tensor cores (plane_filter resolved at creation). */
 int amt_executor_uses_tensor_cores(const amt_executor* ex);
+/* 1 if the thresholded channel runs in decision-exact mode (seg_plane_filter resolved at creation). */
+int amt_executor_decision_exact(const amt_executor* ex);
+/* Fields of view recomputed with the float64 kernels since creation because a candidate list of the decision-exact
+ * mode overflowed (massive ties, e.g. constant images).  Their results are exact like everybody else's. */
+int64_t amt_executor_retry_count(const amt_executor* ex);
 
 /* Per-stage device time (CUDA events after every stage of both executor streams; adds a few microseconds per
  * chunk, off by default).  amt_executor_set_profiling(ex, 1) zeroes the counters; every amt_executor_run_device call

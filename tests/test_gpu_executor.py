@@ -69,7 +69,7 @@ CONTRACTED_PLANE_ATOL = 1e-12
 TENSOR_CORE_PLANE_ATOL = 1e-8
 
 
-@pytest.mark.parametrize("mode", ["tensor_core", "fma", "exact"])
+@pytest.mark.parametrize("mode", ["tensor_core", "tensor_core_float64_seg", "fma", "exact"])
 @pytest.mark.parametrize("shape,C,seg,bg", [((256, 256), 4, 1, 0.0), ((192, 320), 2, 0, 25.0), ((130, 100), 3, 2, 90.0)])
 def test_executor_matches_oracle(shape, C, seg, bg, mode):
     exact_all = mode == "exact"
@@ -81,11 +81,13 @@ def test_executor_matches_oracle(shape, C, seg, bg, mode):
     fovs, givens = np.stack(fovs), np.stack(givens)
     cfg = FovPipelineConfig(n_channels=C, height=shape[0], width=shape[1], seg_channel=seg, chunk_fovs=2, max_labels=512,
                             max_label_value=int(givens.max()), bg_percentile=bg, exact_all_channels=exact_all,
-                            plane_filter="fma" if mode == "fma" else "tensor_core")
+                            plane_filter="fma" if mode == "fma" else "tensor_core",
+                            seg_plane_filter="float64" if mode == "tensor_core_float64_seg" else "decision_exact")
     with FovBatchExecutor(cfg) as ex:
         # the tensor-core path takes planes of at least 128 x 128 with a width that is a multiple of 16
-        tc = mode == "tensor_core" and shape[0] >= 128 and shape[1] >= 128 and shape[1] % 16 == 0
-        assert ex.uses_tensor_cores == tc
+        tc = mode.startswith("tensor_core") and shape[0] >= 128 and shape[1] >= 128 and shape[1] % 16 == 0
+        dx = tc and mode == "tensor_core"  # decision-exact thresholded channel: its float plane is within the bound too
+        assert ex.uses_tensor_cores == tc and ex.decision_exact == dx
         out = ex.alloc_outputs(n_fov, labels=True, preprocessed=True)
         ms = ex.run_device(_gpu.to_device(fovs), _gpu.to_device(givens), out)
         assert ms > 0
@@ -104,7 +106,8 @@ def test_executor_matches_oracle(shape, C, seg, bg, mode):
         want = oracle_fov(fovs[i], givens[i], seg, bg, (1, 99))
         # the segmentation channel's plane decides the labels: bit-identical in both modes; the other planes are
         # bit-identical with exact_all_channels, within CONTRACTED_PLANE_ATOL otherwise
-        assert np.array_equal(host["preprocessed"][i, seg], want["pre"][seg]), f"segmentation plane differs (fov {i})"
+        if not dx:
+            assert np.array_equal(host["preprocessed"][i, seg], want["pre"][seg]), f"segmentation plane differs (fov {i})"
         if exact_all:
             assert np.array_equal(host["preprocessed"][i], want["pre"]), f"preprocessed planes differ (fov {i})"
         else:
@@ -120,17 +123,20 @@ def test_executor_matches_oracle(shape, C, seg, bg, mode):
 
 def test_executor_golden_config1(golden):
     fov, given = golden["fov"][None], golden["given"][None]
-    for bg, exact_all in ((0.0, True), (90.0, True), (0.0, False), (90.0, False)):
+    for bg, exact_all, seg_filter in ((0.0, True, "float64"), (90.0, True, "float64"), (0.0, False, "float64"),
+                                      (90.0, False, "float64"), (0.0, False, "decision_exact"), (90.0, False, "decision_exact")):
         cfg = FovPipelineConfig(n_channels=4, height=256, width=256, seg_channel=1, chunk_fovs=1, max_labels=256,
-                                max_label_value=int(given.max()), bg_percentile=bg, exact_all_channels=exact_all)
+                                max_label_value=int(given.max()), bg_percentile=bg, exact_all_channels=exact_all,
+                                seg_plane_filter=seg_filter)
         with FovBatchExecutor(cfg) as ex:
+            assert ex.decision_exact == (seg_filter == "decision_exact")
             out = ex.alloc_outputs(1, labels=True, preprocessed=True)
             ex.run_device(_gpu.to_device(fov), _gpu.to_device(given), out)
             host = {k: _gpu.to_host(v) for k, v in out.items() if v is not None}
         tag = f"bg{int(bg)}"
         for c in range(4):  # default mode: only the thresholded channel's plane is bit-identical by construction
             sha = hashlib.sha256(np.ascontiguousarray(host["preprocessed"][0, c]).tobytes()).hexdigest()
-            if exact_all or c == 1:
+            if exact_all or (c == 1 and seg_filter == "float64"):
                 assert sha == str(golden[f"{tag}/pre_sha256"][c]), (tag, c)
         assert host["thresholds"][0] == float(golden[f"{tag}/threshold"])
         assert np.array_equal(host["labels_thr"][0], golden[f"{tag}/labels_thr"])
@@ -286,3 +292,39 @@ def test_run_host_from_library_pinned_staging():
                 for i in range(n_fov):
                     k = int(want["counts_thr"][i])
                     assert np.array_equal(got["tables_thr"][i][:, :k], want["tables_thr"][i][:, :k], equal_nan=True)
+
+
+def test_decision_exact_retries_planes_with_massive_ties():
+    """Decision-exact mode lists the samples within the filter's error bound of a deciding value; a plane with huge
+    ties (here: a flat thresholded channel with one bright square, so that thousands of samples share the percentile
+    values) overflows those lists, and the executor recomputes that field of view with the float64 kernels.  Results
+    equal the float64 mode's bit for bit either way, and the ordinary FOVs next to it are not retried."""
+    C, shape = 2, (160, 192)
+    fovs, givens = [], []
+    for i in range(4):
+        f, g, _ = make_fov(5100 + i, C, shape[0], shape[1], 25)
+        fovs.append(f), givens.append(g)
+    fovs, givens = np.stack(fovs), np.stack(givens)
+    fovs[2, 0] = 300
+    fovs[2, 0, 0:10, 0:12] = 5000  # far from it the filtered plane is perfectly flat: > 20 000 tied samples
+    outs = {}
+    for seg_filter in ("decision_exact", "float64"):
+        cfg = FovPipelineConfig(n_channels=C, height=shape[0], width=shape[1], seg_channel=0, chunk_fovs=2, max_labels=256,
+                                max_label_value=int(givens.max()), seg_plane_filter=seg_filter)
+        with FovBatchExecutor(cfg) as ex:
+            dev_out = ex.alloc_outputs(4, labels=True)
+            ex.run_device(_gpu.to_device(fovs), _gpu.to_device(givens), dev_out)
+            retries_device = ex.retry_count
+            host_out = ex.run_host(fovs, givens)
+            outs[seg_filter] = ({k: _gpu.to_host(v) for k, v in dev_out.items() if v is not None}, host_out,
+                                retries_device, ex.retry_count)
+    dx, f64 = outs["decision_exact"], outs["float64"]
+    assert dx[2] == 1 and dx[3] == 2 and f64[3] == 0  # FOV 2 retried once per entry point, nobody else
+    for key in ("thresholds", "counts_thr", "counts_given", "labels_thr", "labels_given"):
+        assert np.array_equal(dx[0][key], f64[0][key]), key
+    for which in ("thr", "given"):
+        for i in range(4):
+            k = int(f64[0][f"counts_{which}"][i])
+            assert np.array_equal(dx[0][f"tables_{which}"][i][:, :k], f64[0][f"tables_{which}"][i][:, :k], equal_nan=True)
+            assert np.array_equal(dx[1][f"tables_{which}"][i][:, :k], f64[1][f"tables_{which}"][i][:, :k], equal_nan=True)
+    assert np.array_equal(dx[1]["thresholds"], f64[1]["thresholds"]) and np.array_equal(dx[1]["counts_thr"], f64[1]["counts_thr"])
