@@ -24,15 +24,22 @@ _MAGIC = 0x0ABECEDA
 
 
 def _read_chunk(buf, offset: int):
-    """Payload of the chunk at ``offset`` (a zero-copy slice of ``buf``: bytes or a memoryview)."""
+    """Payload of the chunk at ``offset`` (a zero-copy slice of ``buf``: bytes or a memoryview).  Offsets and
+    lengths come from the file: they are checked against its size before anything is sliced."""
+    if not (0 <= offset <= len(buf) - 16):
+        raise ValueError(f"ND2 chunk offset {offset} lies outside the file ({len(buf)} bytes)")
     magic, name_len, data_len = struct.unpack_from("<IIQ", buf, offset)
     if magic != _MAGIC:
         raise ValueError(f"not an ND2 chunk at offset {offset} (magic {magic:#x})")
     start = offset + 16 + name_len
+    if start + data_len > len(buf):
+        raise ValueError(f"ND2 chunk at offset {offset} claims {data_len} bytes beyond the end of the file")
     return buf[start : start + data_len]
 
 
 def _chunk_map(buf) -> dict[bytes, tuple[int, int]]:
+    if len(buf) < 40:
+        raise ValueError("file too short to be an ND2 container")
     (map_offset,) = struct.unpack_from("<Q", buf, len(buf) - 8)
     payload = bytes(_read_chunk(buf, map_offset))
     out: dict[bytes, tuple[int, int]] = {}
@@ -44,6 +51,8 @@ def _chunk_map(buf) -> dict[bytes, tuple[int, int]]:
         name = payload[pos : end + 1]
         if name.startswith(b"ND2 CHUNK MAP SIGNATURE"):
             break
+        if end + 17 > len(payload):
+            raise ValueError("truncated ND2 chunk map")
         off, length = struct.unpack_from("<QQ", payload, end + 1)
         out[name] = (off, length)
         pos = end + 1 + 16
@@ -62,11 +71,9 @@ def _lite_variant_uint(payload, key: str) -> int:
     return int(val)
 
 
-def read_nd2_frames(path: str | Path) -> np.ndarray:
-    """Return the pixel data as ``(n_frames, C, Y, X)`` uint16, C-contiguous."""
-    buf = Path(path).read_bytes()
-    cmap = _chunk_map(buf)
-    attrs = _read_chunk(buf, cmap[b"ImageAttributesLV!"][0])
+def _frame_geometry(attrs) -> tuple[int, int, int, int, int]:
+    """(height, width, components, sequence count, row pitch in bytes).  ND2 writers pad rows to a multiple of four
+    bytes (``uiWidthBytes``); files without the entry are tightly packed."""
     width = _lite_variant_uint(attrs, "uiWidth")
     height = _lite_variant_uint(attrs, "uiHeight")
     comps = _lite_variant_uint(attrs, "uiComp")
@@ -74,13 +81,29 @@ def read_nd2_frames(path: str | Path) -> np.ndarray:
     nseq = _lite_variant_uint(attrs, "uiSequenceCount")
     if bpc != 16:
         raise ValueError(f"only 16-bit ND2 frames are supported, got {bpc} bits")
+    try:
+        pitch = _lite_variant_uint(attrs, "uiWidthBytes")
+    except KeyError:
+        pitch = width * comps * 2
+    if pitch < width * comps * 2 or pitch % 2:
+        raise ValueError(f"ND2 row pitch {pitch} does not fit {width} x {comps} 16-bit samples")
+    return height, width, comps, nseq, pitch
+
+
+def read_nd2_frames(path: str | Path) -> np.ndarray:
+    """Return the pixel data as ``(n_frames, C, Y, X)`` uint16, C-contiguous."""
+    buf = Path(path).read_bytes()
+    cmap = _chunk_map(buf)
+    attrs = _read_chunk(buf, cmap[b"ImageAttributesLV!"][0])
+    height, width, comps, nseq, pitch = _frame_geometry(attrs)
     frames = np.empty((nseq, comps, height, width), dtype=np.uint16)
-    n_samples = height * width * comps
     for i in range(nseq):
         off, _ = cmap[f"ImageDataSeq|{i}!".encode()]
         data = _read_chunk(buf, off)
-        px = np.frombuffer(data, dtype="<u2", count=n_samples, offset=8)
-        frames[i] = px.reshape(height, width, comps).transpose(2, 0, 1)
+        if len(data) < 8 + height * pitch:
+            raise ValueError(f"ND2 frame {i} holds {len(data)} bytes, expected {8 + height * pitch}")
+        rows = np.frombuffer(data, dtype="<u2", count=height * (pitch // 2), offset=8).reshape(height, pitch // 2)
+        frames[i] = rows[:, : width * comps].reshape(height, width, comps).transpose(2, 0, 1)
     return frames
 
 
@@ -95,16 +118,15 @@ def nd2_frame_layout(path: str | Path) -> tuple[np.memmap, list[int], tuple[int,
     buf = memoryview(mm)  # struct.unpack_from and slicing without copying the file
     cmap = _chunk_map(buf)
     attrs = _read_chunk(buf, cmap[b"ImageAttributesLV!"][0])
-    width = _lite_variant_uint(attrs, "uiWidth")
-    height = _lite_variant_uint(attrs, "uiHeight")
-    comps = _lite_variant_uint(attrs, "uiComp")
-    bpc = _lite_variant_uint(attrs, "uiBpcInMemory")
-    nseq = _lite_variant_uint(attrs, "uiSequenceCount")
-    if bpc != 16:
-        raise ValueError(f"only 16-bit ND2 frames are supported, got {bpc} bits")
+    height, width, comps, nseq, pitch = _frame_geometry(attrs)
+    if pitch != width * comps * 2:
+        raise ValueError(f"ND2 rows are padded (pitch {pitch} bytes for {width * comps * 2}): use read_nd2_frames")
     offsets = []
     for i in range(nseq):
         off, _ = cmap[f"ImageDataSeq|{i}!".encode()]
+        payload = _read_chunk(buf, off)  # bounds-checked
+        if len(payload) < 8 + height * pitch:
+            raise ValueError(f"ND2 frame {i} holds {len(payload)} bytes, expected {8 + height * pitch}")
         _, name_len, _ = struct.unpack_from("<IIQ", buf, off)
         offsets.append(off + 16 + name_len + 8)  # chunk header, name, float64 timestamp
     return mm, offsets, (height, width, comps)
@@ -118,7 +140,12 @@ def read_nd2_to_device(path: str | Path, device=None):
 
     torch = _gpu.torch_mod()
     dev = _gpu.require_cuda() if device is None else device
-    mm, offsets, (height, width, comps) = nd2_frame_layout(path)
+    try:
+        mm, offsets, (height, width, comps) = nd2_frame_layout(path)
+    except ValueError as err:
+        if "padded" not in str(err):
+            raise
+        return _gpu.to_device(read_nd2_frames(path), dev)  # padded rows: the strided host reader, then one upload
     n_pix = height * width
     nbytes = n_pix * comps * 2
     staging = torch.empty((len(offsets), n_pix, comps), dtype=torch.int16, pin_memory=True)

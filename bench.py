@@ -325,10 +325,11 @@ def ncu_traffic(kernel_substr: str) -> tuple[float | None, str | None]:
     return None, None
 
 
-def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int, tcg) -> dict:
-    """CUDA-event timings of the DoG kernels of one executor chunk, each timed alone: the float64 strip kernels on
-    the thresholded channel's planes (8 of 32), and — when the executor runs the other channels on the tensor
-    cores — the narrow Gaussian and the two tcgen05 passes on the other 24; plus the FP64 issue-rate probe."""
+def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int, tcg, decision_exact: bool = False) -> dict:
+    """CUDA-event timings of the DoG kernels of one executor chunk, each timed alone.  Decision-exact mode (the
+    default): the narrow Gaussian and the two tcgen05 passes on all 32 planes; the float64 strip kernels (which then
+    only serve the retry path) on the thresholded channel's 8 planes for comparison.  seg_plane_filter="float64": the
+    strip kernels on those 8 planes and the tensor-core kernels on the other 24.  Plus the FP64 issue-rate probe."""
     import ctypes as CT
 
     import torch
@@ -394,13 +395,14 @@ def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int, tcg) -> dict:
     res["strip_axis1"] = {"ms": ms_h, "planes": exact_planes, "bytes": exact_planes * px_plane * (16 + 8 + 2),
                           "dp_instr": exact_planes * px_plane * dp_axis, "kernel": "dog_strip_kernel<..., double, axis 1>"}
     if mixed:
-        tc_planes = planes - exact_planes
+        tc_planes = planes if decision_exact else planes - exact_planes
+        every, off = (0, 0) if decision_exact else (C, SEG_CHANNEL)
         digits = torch.empty((planes, 5, H, W), dtype=torch.uint8, device=dev)
         buckets = torch.empty((planes, H, W), dtype=torch.int16, device=dev)
-        ms_lo = timed(lambda: L.check(lib.amt_gauss_lo2d(p(fovs), scale, p(tmp_lo), planes, H, W, p(d_lo), r_lo, C, SEG_CHANNEL, st)))
-        ms_a0 = timed(lambda: L.check(lib.amt_tcg_axis0(tcg.handle, p(fovs), planes, H, W, p(digits), C, SEG_CHANNEL, st)))
+        ms_lo = timed(lambda: L.check(lib.amt_gauss_lo2d(p(fovs), scale, p(tmp_lo), planes, H, W, p(d_lo), r_lo, every, off, st)))
+        ms_a0 = timed(lambda: L.check(lib.amt_tcg_axis0(tcg.handle, p(fovs), planes, H, W, p(digits), every, off, st)))
         ms_a1 = timed(lambda: L.check(lib.amt_tcg_axis1(tcg.handle, p(digits), p(tmp_lo), scale, p(out), planes, H, W, p(buckets),
-                                                       p(mm), C, SEG_CHANNEL, st)))
+                                                       p(mm), every, off, st)))
         # int8 multiply-adds per sample: 4 weight digits x 2 sample bytes x K = 256 (axis 0), 17 digit products x 256 (axis 1)
         res["lo2d"] = {"ms": ms_lo, "planes": tc_planes, "bytes": tc_planes * px_plane * (2 + 8), "kernel": "lo2d_kernel"}
         res["tcg_axis0"] = {"ms": ms_a0, "planes": tc_planes, "bytes": tc_planes * px_plane * (2 + 5),
@@ -481,10 +483,12 @@ def run_b200(args) -> None:
     # the host-fed leg hands the executor the reference's own mask dtype: int64 (ref: model.py:215, masks.py:138)
     cfg = FovPipelineConfig(n_channels=C, height=H, width=W, seg_channel=SEG_CHANNEL, chunk_fovs=args.chunk,
                             max_labels=4096, max_label_value=max_label, given_label_dtype=np.int64,
-                            exact_all_channels=args.exact_all_channels, plane_filter=args.plane_filter)
+                            exact_all_channels=args.exact_all_channels, plane_filter=args.plane_filter,
+                            seg_plane_filter=args.seg_plane_filter)
     ex = FovBatchExecutor(cfg, device=local)
     out = ex.alloc_outputs(n_fov)
     tensor_cores = ex.uses_tensor_cores
+    decision_exact = ex.decision_exact
 
     # ---- device-resident timed region: W warm-up steps, then exactly K timed steps
     for _ in range(args.warmup):
@@ -583,17 +587,19 @@ def run_b200(args) -> None:
             barrier()
             return max_ranks(sum(ms) / 1e3)
 
-        variants = {"fma": dict(plane_filter="fma", exact_all_channels=False),
+        variants = {"float64_thresholded_channel": dict(plane_filter="tensor_core", seg_plane_filter="float64", exact_all_channels=False),
+                    "fma": dict(plane_filter="fma", exact_all_channels=False),
                     "exact_all_channels": dict(exact_all_channels=True),
-                    "tensor_core": dict(plane_filter="tensor_core", exact_all_channels=False)}
+                    "decision_exact": dict(plane_filter="tensor_core", seg_plane_filter="decision_exact", exact_all_channels=False)}
         for name, kw in variants.items():
             vcfg = dataclasses.replace(cfg, **kw)
-            if (vcfg.plane_filter, vcfg.exact_all_channels) == (cfg.plane_filter, cfg.exact_all_channels):
+            if (vcfg.plane_filter, vcfg.exact_all_channels, vcfg.seg_plane_filter) == (cfg.plane_filter, cfg.exact_all_channels, cfg.seg_plane_filter):
                 continue
             with FovBatchExecutor(vcfg, device=local) as ex_v:
                 s_v = timed_pass(ex_v)
                 modes[name] = {"value": world * args.steps * n_fov * C * H * W / s_v / 1e6, "unit": "Mpix/s",
                                "ms_per_step": 1e3 * s_v / args.steps, "uses_tensor_cores": ex_v.uses_tensor_cores,
+                               "decision_exact": ex_v.decision_exact,
                                "thresholds_counts_and_tables_bit_identical_to_default": same_as_default()}
         ex.run_device(fovs, given, out, sync=True)  # leave the default mode's results in `out`
         del keep
@@ -632,9 +638,11 @@ def run_b200(args) -> None:
         peaks = measured_peaks()
         hw = (_gpu.gaussian_half_weights(cfg.low_sigma), _gpu.gaussian_half_weights(cfg.high_sigma))
         tcg = _gpu.TensorCoreGaussian(cfg.high_sigma) if tensor_cores else None
-        k = time_kernels(lib, _gpu, fovs, hw, steps=max(args.steps, 5), warmup=args.warmup, tcg=tcg)
+        k = time_kernels(lib, _gpu, fovs, hw, steps=max(args.steps, 5), warmup=args.warmup, tcg=tcg, decision_exact=decision_exact)
         kernel_keys = [key for key in ("strip_axis0", "strip_axis1", "lo2d", "tcg_axis0", "tcg_axis1") if key in k]
-        dom = max(kernel_keys, key=lambda key: k[key]["ms"])
+        # in decision-exact mode the strip kernels are not on the path (they serve the rare float64 retry only)
+        on_path = [key for key in kernel_keys if not (decision_exact and key.startswith("strip"))]
+        dom = max(on_path, key=lambda key: k[key]["ms"])
         dom_ms = k[dom]["ms"]
         achieved = k[dom]["bytes"] / (dom_ms * 1e-3) / 1e9
         traffic, traffic_src = ncu_traffic(k[dom]["kernel"].split("<")[0])
@@ -660,13 +668,20 @@ def run_b200(args) -> None:
                                    "W = DoG(0.6,16)+pct rescale on 4 channels, Otsu+CCL+clear_border on ch1, per-cell tables "
                                    "for the threshold mask and the given mask",
                        "arithmetic": ("float64, scipy's exact operation order for every channel" if cfg.exact_all_channels else
-                                      "thresholded channel: float64 in scipy's exact operation order (labels, counts, tables bit-exact "
-                                      "by construction); other channels' sigma=16 Gaussian: " +
-                                      ("exact integer Toeplitz products on tcgen05 (uint8 x uint8 -> int32, weights rounded to 32 bits; "
-                                       "planes within 1e-8 of scipy's on the [0, 1] scale, tolerance 1e-5)" if tensor_cores else
-                                       "float64 with fused multiply-adds (~1e-15)")),
+                                      ("every channel's sigma=16 Gaussian as exact integer Toeplitz products on tcgen05 (uint8 x uint8 -> "
+                                       "int32, weights rounded to 32 bits; planes within 1e-8 of scipy's on the [0, 1] scale, tolerance "
+                                       "1e-5); thresholded channel decision-exact: every sample within the filter's proven error bound of "
+                                       "a percentile, a histogram edge or the threshold is re-evaluated in scipy's exact float64 order, so "
+                                       "thresholds, labels, counts and tables are bit-identical to the reference's by construction"
+                                       if decision_exact else
+                                       "thresholded channel: float64 in scipy's exact operation order (labels, counts, tables bit-exact "
+                                       "by construction); other channels' sigma=16 Gaussian: " +
+                                       ("exact integer Toeplitz products on tcgen05 (planes within 1e-8 of scipy's, tolerance 1e-5)"
+                                        if tensor_cores else "float64 with fused multiply-adds (~1e-15)"))),
                        "fovs_per_gpu": n_fov, "unique_cell_layouts": args.unique, "chunk_fovs": args.chunk,
-                       "uses_tensor_cores": tensor_cores,
+                       "uses_tensor_cores": tensor_cores, "decision_exact": decision_exact,
+                       "exact_planes": 0 if decision_exact else (n_fov if not cfg.exact_all_channels else n_fov * C),
+                       "float64_retries": ex.retry_count,
                        "l2_policy": f"inputs {fovs.numel() * 2 / 1e9:.1f} GB per step >> 126 MB L2 (no flush needed)",
                        "sharding": "FOV-independent, one process per GPU, no collective on the data path"},
             "fov_per_s": world * args.steps * n_fov / dev_s,
@@ -761,6 +776,8 @@ def main() -> None:
                     help="skip the comparison passes in the other arithmetic modes (fma / exact_all_channels)")
     ap.add_argument("--plane-filter", default="tensor_core", choices=["tensor_core", "fma"],
                     help="filter of the channels that are not thresholded (FovPipelineConfig.plane_filter)")
+    ap.add_argument("--seg-plane-filter", default="decision_exact", choices=["decision_exact", "float64"],
+                    help="the thresholded channel (FovPipelineConfig.seg_plane_filter)")
     ap.add_argument("--exact-all-channels", action="store_true",
                     help="measure FovPipelineConfig(exact_all_channels=True) as the reported configuration")
     ap.add_argument("--plate-check", action="store_true", help="also run the plate gather at N=1")

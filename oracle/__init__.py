@@ -46,6 +46,7 @@ from . import exposure, filters, labeling, outlines, percentile, regionprops, th
 from .ops import (  # noqa: F401
     apply_threshold,
     cell_properties,
+    crop_to_center,
     process_mask,
     rescale_by_percentile,
     subtract_background_dog,

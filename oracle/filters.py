@@ -29,6 +29,14 @@ def img_as_float(image: np.ndarray) -> np.ndarray:
         return image.astype(np.float64)
     if image.dtype in _UINT_MAX:
         return np.multiply(image, 1.0 / _UINT_MAX[image.dtype], dtype=np.float64)
+    if image.dtype.kind == "u":  # skimage.util.dtype._convert, unsigned -> float: multiply by 1 / imax
+        return np.multiply(image, 1.0 / np.iinfo(image.dtype).max, dtype=np.float64)
+    if image.dtype.kind == "i":  # signed -> float: (x + 0.5) * 2 / (imax - imin), in float64, in this order
+        info = np.iinfo(image.dtype)
+        out = np.add(image, 0.5, dtype=np.float64)
+        out *= 2
+        out /= int(info.max) - int(info.min)
+        return out
     raise TypeError(f"oracle.img_as_float: dtype {image.dtype} is outside the hot path")
 
 

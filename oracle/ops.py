@@ -54,6 +54,16 @@ def subtract_background_dog(intensities, low_sigma=0.6, high_sigma=16.0, percent
     return np.clip(dog - background_level, 0, None)
 
 
+def crop_to_center(intensities, output_shape):
+    """ref: operations.py:100-132: centred slice of the last two axes, clamped to the image size (a view)."""
+    height, width = intensities.shape[-2:]
+    crop_height = min(height, output_shape[0])
+    crop_width = min(width, output_shape[1])
+    top = (height - crop_height) // 2
+    left = (width - crop_width) // 2
+    return intensities[..., top : top + crop_height, left : left + crop_width]
+
+
 def apply_threshold(intensities, method="otsu", **kwargs):
     """ref: operations.py:135-216 (all ten methods)."""
     if intensities.size == 0:

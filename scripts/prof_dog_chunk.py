@@ -17,5 +17,5 @@ lib = _lib.load()
 fovs, given, max_label = bench.build_device_batch(8, 2, dev)
 hw = (_gpu.gaussian_half_weights(0.6), _gpu.gaussian_half_weights(16.0))
 tcg = _gpu.TensorCoreGaussian(16.0)
-k = bench.time_kernels(lib, _gpu, fovs, hw, steps=1, warmup=1, tcg=tcg)
+k = bench.time_kernels(lib, _gpu, fovs, hw, steps=1, warmup=1, tcg=tcg, decision_exact=True)
 print({key: round(v["ms"], 4) for key, v in k.items() if isinstance(v, dict)})

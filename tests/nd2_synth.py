@@ -21,9 +21,11 @@ def _lv_u32(key: str, value: int) -> bytes:
     return bytes([2, len(key) + 1]) + name + struct.pack("<I", value)
 
 
-def write_nd2(path: Path, frames: np.ndarray) -> None:
-    """frames: (n_frames, C, Y, X) uint16."""
+def write_nd2(path: Path, frames: np.ndarray, row_align: int = 1) -> None:
+    """frames: (n_frames, C, Y, X) uint16.  row_align > 1 pads every row to a multiple of that many bytes
+    (real ND2 writers use 4), recorded in uiWidthBytes."""
     n, c, h, w = frames.shape
+    pitch = -(-(w * c * 2) // row_align) * row_align
     blob = bytearray()
     table: list[tuple[bytes, int, int]] = []
 
@@ -32,12 +34,14 @@ def write_nd2(path: Path, frames: np.ndarray) -> None:
         blob.extend(_chunk(name, payload))
 
     add(b"ND2 FILE SIGNATURE CHUNK NAME01!", b"Ver3.0" + b"\x00" * 58)
-    attrs = b"".join(_lv_u32(k, v) for k, v in [("uiWidth", w), ("uiWidthBytes", w * c * 2), ("uiHeight", h), ("uiComp", c),
+    attrs = b"".join(_lv_u32(k, v) for k, v in [("uiWidth", w), ("uiWidthBytes", pitch), ("uiHeight", h), ("uiComp", c),
                                                 ("uiBpcInMemory", 16), ("uiBpcSignificant", 16), ("uiSequenceCount", n)])
     add(b"ImageAttributesLV!", attrs)
     for i in range(n):
         yxc = np.ascontiguousarray(frames[i].transpose(1, 2, 0)).astype("<u2")
-        add(f"ImageDataSeq|{i}!".encode(), struct.pack("<d", 0.25 * i) + yxc.tobytes())
+        rows = np.zeros((h, pitch), dtype=np.uint8)
+        rows[:, : w * c * 2] = yxc.reshape(h, w * c).view(np.uint8)
+        add(f"ImageDataSeq|{i}!".encode(), struct.pack("<d", 0.25 * i) + rows.tobytes())
     map_offset = len(blob)
     payload = b"".join(name + struct.pack("<QQ", off, ln) for name, off, ln in table)
     payload += b"ND2 CHUNK MAP SIGNATURE 0000001!" + struct.pack("<Q", map_offset)

@@ -328,3 +328,31 @@ def test_decision_exact_retries_planes_with_massive_ties():
             assert np.array_equal(dx[0][f"tables_{which}"][i][:, :k], f64[0][f"tables_{which}"][i][:, :k], equal_nan=True)
             assert np.array_equal(dx[1][f"tables_{which}"][i][:, :k], f64[1][f"tables_{which}"][i][:, :k], equal_nan=True)
     assert np.array_equal(dx[1]["thresholds"], f64[1]["thresholds"]) and np.array_equal(dx[1]["counts_thr"], f64[1]["counts_thr"])
+
+
+def test_nd2_file_to_pinned_staging_to_executor(tmp_path):
+    """SURVEY 8f-3, end to end: raw ND2 frames -> pinned staging (one memcpy per frame) -> one H2D copy ->
+    de-interleave kernel -> the executor's device-resident entry point; the same tables as the host reader's planar
+    array through the host-fed entry point."""
+    from nd2_synth import write_nd2
+
+    from arcadia_microscopy_tools_b200 import nd2_raw
+
+    C, shape = 4, (128, 160)
+    frames = np.stack([make_fov(6100 + i, C, shape[0], shape[1], 25)[0] for i in range(3)])
+    path = tmp_path / "plate.nd2"
+    write_nd2(path, frames)
+    cfg = FovPipelineConfig(n_channels=C, height=shape[0], width=shape[1], seg_channel=1, chunk_fovs=2, max_labels=256,
+                            quantify_given_mask=False)
+    with FovBatchExecutor(cfg) as ex:
+        dev_frames = nd2_raw.read_nd2_to_device(path)
+        assert tuple(dev_frames.shape) == (3, C, *shape)
+        out = ex.alloc_outputs(3)
+        ex.run_device(dev_frames, None, out)
+        got = {k: _gpu.to_host(v) for k, v in out.items() if v is not None}
+        want = ex.run_host(nd2_raw.read_nd2_frames(path), None)
+    assert np.array_equal(got["counts_thr"], want["counts_thr"]) and got["counts_thr"].min() > 0
+    assert np.array_equal(got["thresholds"], want["thresholds"])
+    for i in range(3):
+        k = int(want["counts_thr"][i])
+        assert np.array_equal(got["tables_thr"][i][:, :k], want["tables_thr"][i][:, :k], equal_nan=True)

@@ -516,3 +516,34 @@ def test_bucketed_selection_matches_sorted_order():
     got = out.cpu().numpy()
     want = np.sort(data, axis=1)[:, ranks]
     assert np.array_equal(got, want), [(list(planes)[i], got[i], want[i]) for i in range(len(planes)) if not np.array_equal(got[i], want[i])][:2]
+
+
+def test_device_chain_after_crop_and_narrow_dtypes():
+    """A device-resident Pipeline hands each operation the previous one's tensor: a centred crop is a strided view
+    (it must be packed before a kernel sees it), and a uint8 / int32 / bool first input keeps its own dtype rules
+    (img_as_float's 1/255 for uint8, (2x + 1) / (max - min) for signed integers)."""
+    rng = np.random.default_rng(321)
+    img = rng.integers(100, 5000, size=(3, 150, 170)).astype(np.uint16)
+    crop = ImageOperation(operations.crop_to_center, (96, 112))
+    dog = ImageOperation(operations.subtract_background_dog, low_sigma=0.6, high_sigma=4.0, percentile=5)
+    rescale = ImageOperation(operations.rescale_by_percentile, percentile_range=(1, 99))
+
+    def want_for(plane):
+        c = oracle.crop_to_center(plane, (96, 112))
+        return oracle.rescale_by_percentile(oracle.subtract_background_dog(c, 0.6, 4.0, 5), (1, 99))
+
+    got = Pipeline([crop, dog, rescale])(img[0])
+    _bits_equal(got, want_for(img[0]), "crop -> dog -> rescale")
+    got = Pipeline([crop, dog, rescale], parallel=True)(img)
+    for i in range(3):
+        _bits_equal(got[i], want_for(img[i]), f"parallel crop chain, slice {i}")
+    dev = operations.crop_to_center(_gpu.to_device(img[1]), (96, 112))
+    assert not dev.is_contiguous()
+    _bits_equal(_gpu.to_host(operations.subtract_background_dog(dev, 0.6, 4.0, 5)),
+                oracle.subtract_background_dog(oracle.crop_to_center(img[1], (96, 112)), 0.6, 4.0, 5), "sliced device input")
+    u8 = (img[0] >> 5).astype(np.uint8)
+    _bits_equal(Pipeline([dog, rescale])(u8), oracle.rescale_by_percentile(oracle.subtract_background_dog(u8, 0.6, 4.0, 5), (1, 99)),
+                "uint8 device chain")
+    i32 = img[0].astype(np.int32) - 2000
+    _bits_equal(operations.subtract_background_dog(i32, 0.6, 4.0, 5), oracle.subtract_background_dog(i32, 0.6, 4.0, 5), "int32 DoG")
+    _bits_equal(operations.gaussian_smooth(img[0].astype(np.uint32), 2.0), filters.gaussian(img[0].astype(np.uint32), 2.0), "uint32 gaussian")

@@ -408,3 +408,30 @@ def test_histogram_scans_against_independent_constructions():
         hist[k] = max(0, 50 - 5 * abs(k - 20)) + max(0, 80 - 4 * abs(k - 70))
     t = operations._minimum_from_histogram(hist, np.arange(100))
     assert 30 <= t <= 50 and hist[int(t)] == hist[30:51].min()
+
+
+def test_nd2_reader_honours_row_pitch_and_rejects_bad_offsets(tmp_path):
+    """ND2 rows are padded to four bytes (uiWidthBytes): an odd width x components must not shear the image; chunk
+    offsets and lengths read from the file are bounds-checked before use."""
+    from nd2_synth import write_nd2
+
+    from arcadia_microscopy_tools_b200 import nd2_raw
+
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 65536, size=(2, 3, 5, 7)).astype(np.uint16)  # 7 * 3 * 2 = 42 bytes per row -> pitch 44
+    path = tmp_path / "padded.nd2"
+    write_nd2(path, frames, row_align=4)
+    assert np.array_equal(nd2_raw.read_nd2_frames(path), frames)
+    with pytest.raises(ValueError, match="padded"):
+        nd2_raw.nd2_frame_layout(path)
+    tight = tmp_path / "tight.nd2"
+    write_nd2(tight, frames)
+    assert np.array_equal(nd2_raw.read_nd2_frames(tight), frames)
+    blob = bytearray(tight.read_bytes())
+    bad = tmp_path / "bad.nd2"
+    bad.write_bytes(bytes(blob[:-8]) + (10**12).to_bytes(8, "little"))  # chunk-map offset far beyond the file
+    with pytest.raises(ValueError, match="outside the file"):
+        nd2_raw.read_nd2_frames(bad)
+    bad.write_bytes(bytes(blob[: len(blob) // 2]))  # truncated
+    with pytest.raises(ValueError):
+        nd2_raw.read_nd2_frames(bad)
