@@ -578,6 +578,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
     int cur_q = -1, plane = -1;
     int stage = 0;
     uint32_t phase = 0;
+    const bool has_lo = p.lo != nullptr;
     auto flush = [&]() {
       if (p.minmax != nullptr && plane >= 0) {
         const uint64_t a = warp_min_u64(f64_to_key(vmin)), b = warp_max_u64(f64_to_key(vmax));
@@ -602,7 +603,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       // conflicts), then the stage goes back to the producer
       double lo[16];
       mbar_wait(&bars->full[stage], phase);
-      if (p.lo != nullptr) {
+      if (has_lo) {
         const double* lt = reinterpret_cast<const double*>(stage_s + stage * P2_STAGE_BYTES + P2_DIG_BYTES) + (hrow * 16) * MT + mx;
 #pragma unroll
         for (int n = 0; n < 16; ++n) lo[n] = lt[n * MT];
@@ -649,6 +650,9 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       if (lane == 0) mbar_arrive(&bars->acc_empty);
       if (p.dbg & 2) continue;
 
+      // Branch-free passes over the thread's 16 samples (a per-sample `if` would put every sample in its own basic
+      // block and serialise sixteen independent latency chains): integer combine + ONE conversion each, then the
+      // rare edge term for all of them, then scale and subtract.
       double res[16];
 #pragma unroll
       for (int n = 0; n < 16; ++n) {
@@ -659,29 +663,47 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
         const uint64_t p45 = (uint64_t)v[5][n] * 256u + v[4][n];
         uint64_t tot = (uint64_t)(uint32_t)p23 * 65536u + p01;
         tot += ((uint64_t)((uint32_t)(p23 >> 32) << 16) + (uint32_t)p45) << 32;
-        double g = (double)tot;
-        if (edge_tile) {
+        res[n] = (double)tot;
+      }
+      if (edge_tile) {  // warp-uniform
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
           const double el = __shfl_sync(0xffffffffu, e_l, n), er = __shfl_sync(0xffffffffu, e_r, n);
-          g += f_l * el + f_r * er;
+          res[n] += f_l * el + f_r * er;
         }
-        g *= p.scale;
-        res[n] = p.lo != nullptr ? lo[n] - g : g;
+      }
+      const double scale = p.scale;
+      if (has_lo) {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) res[n] = lo[n] - res[n] * scale;
+      } else {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) res[n] = res[n] * scale;
       }
       if (x_ok && rows > 0) {
         double* op = p.out + (int64_t)plane * hw + (int64_t)y0 * p.w + x;
         uint16_t* bp = p.buckets != nullptr ? p.buckets + (int64_t)plane * hw + (int64_t)y0 * p.w + x : nullptr;
+        if (rows == 16) {  // the whole run lies inside the plane: no per-row tests
 #pragma unroll
-        for (int n = 0; n < 16; ++n) {
-          if (n < rows) {
-            if (p.dbg & 64) {  // timing experiment: streaming (evict-first) stores
-              __stcs(op + (int64_t)n * p.w, res[n]);
-              if (bp != nullptr) __stcs(bp + (int64_t)n * p.w, (unsigned short)bucket12(res[n]));
-            } else {
-              op[(int64_t)n * p.w] = res[n];
-              if (bp != nullptr) bp[(int64_t)n * p.w] = (uint16_t)bucket12(res[n]);
-            }
+          for (int n = 0; n < 16; ++n) op[(int64_t)n * p.w] = res[n];
+          if (bp != nullptr) {
+#pragma unroll
+            for (int n = 0; n < 16; ++n) bp[(int64_t)n * p.w] = (uint16_t)bucket12(res[n]);
+          }
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
             vmin = res[n] < vmin ? res[n] : vmin;
             vmax = res[n] > vmax ? res[n] : vmax;
+          }
+        } else {
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            if (n < rows) {
+              op[(int64_t)n * p.w] = res[n];
+              if (bp != nullptr) bp[(int64_t)n * p.w] = (uint16_t)bucket12(res[n]);
+              vmin = res[n] < vmin ? res[n] : vmin;
+              vmax = res[n] > vmax ? res[n] : vmax;
+            }
           }
         }
       }

@@ -55,7 +55,8 @@ def test_axis0_digits_bit_exact(shape, kind):
 
 
 @pytest.mark.parametrize("shape,kind", [((256, 256), "noise"), ((384, 272), "blob"), ((130, 144), "dim"),
-                                        ((512, 1024), "blob")])
+                                        ((512, 1024), "blob"), ((128, 128), "noise"), ((250, 400), "blob"),
+                                        ((1100, 144), "dim")])
 def test_axis1_bit_exact_and_close_to_scipy(shape, kind):
     tcg = _gpu.TensorCoreGaussian(16.0)
     imgs = np.stack([_image(9 + i, shape, kind) for i in range(2)])
