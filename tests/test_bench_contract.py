@@ -1,5 +1,5 @@
 """The JSON line ``bench.py`` prints is a contract with the driver; the committed lines of the last measurement
-pass (``profiles/r01_bench_*.json``) must carry every key it names, with consistent values."""
+pass (``profiles/r02_bench_*.json``) must carry every key it names, with consistent values."""
 
 from __future__ import annotations
 
@@ -20,7 +20,7 @@ def _line(name: str) -> dict:
     return json.loads(path.read_text())
 
 
-@pytest.mark.parametrize("name,n_gpus", [("r01_bench_default_n1.json", 1), ("r01_bench_n8.json", 8)])
+@pytest.mark.parametrize("name,n_gpus", [("r02_bench_n1.json", 1), ("r02_bench_n2.json", 2), ("r02_bench_n8.json", 8)])
 def test_b200_line_has_the_contract_keys(name, n_gpus):
     d = _line(name)
     assert BASE_KEYS | {"gpu_launches", "clocks", "roofline"} <= set(d)
@@ -31,25 +31,38 @@ def test_b200_line_has_the_contract_keys(name, n_gpus):
     # value = samples per second of the timed steps (256 FOVs of 4 x 2048 x 2048 per GPU and step)
     samples = n_gpus * d["steps"] * d["config"]["fovs_per_gpu"] * 4 * 2048 * 2048
     assert d["value"] == pytest.approx(samples / (d["ms_per_step"] * d["steps"] * 1e-3) / 1e6, rel=1e-6)
+    assert d["config"]["uses_tensor_cores"] is True and d["config"]["decision_exact"] is True and d["config"]["exact_planes"] == 0
     e2e = d["e2e"]
-    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e2e)
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "copy_only", "frac_of_copy_ceiling", "uint16_masks"} <= set(e2e)
     assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and 0 < e2e["value"] < d["value"]
+    assert e2e["fovs_per_step"] == 256  # the same batch at every N
+    # int64 label masks: 4 x 2 bytes of pixels + 8 bytes of label per FOV-pixel
+    assert e2e["h2d_bytes_per_step"] == e2e["fovs_per_step"] * 2048 * 2048 * (4 * 2 + 8)
+    assert 0.5 < e2e["frac_of_copy_ceiling"] <= 1.05 and e2e["uint16_masks"]["value"] > e2e["value"]
     clocks = d["clocks"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(clocks) and clocks["samples"] >= 10
     assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks["reasons"])
     roof = d["roofline"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(roof) and roof["bound"] in ("hbm", "tensor")
     assert roof["frac"] == pytest.approx(roof["achieved"] / roof["peak"], rel=1e-9) and 0 < roof["frac"] < 1
+    assert "tcg_axis1" in roof["kernel"] and roof["traffic"] == pytest.approx(roof["algorithmic_bytes_per_launch"], rel=0.1)
+    stages = d["stages"]
+    assert {"W_pre", "W_seg", "W_quant", "stage_ms_per_chunk"} <= set(stages)
+    assert d["chunk"]["ms"] > 0 and d["chunk"]["ms_budget_for_60pct_of_hbm"] == pytest.approx(1.5357, rel=1e-3)
+    for mode in d["other_modes"].values():  # every arithmetic mode decides the same labels as the default one
+        assert mode["thresholds_counts_and_tables_bit_identical_to_default"] is True
     if n_gpus == 1:
         cpu = d["cpu_baseline"]
         assert {"value", "unit", "cores", "kind", "sample"} <= set(cpu) and cpu["kind"] in ("reference", "port")
-        # the strict and the fully contracted passes decide the same labels as the default one
-        for key in ("exact_all_channels_mode", "contracted_mode"):
-            assert d[key]["thresholds_counts_and_tables_bit_identical_to_default"] is True
+        assert d["parity_checked"]["ok"] is True and d["parity_checked"]["fovs"] == 3
+        assert d["parity_checked"]["max_plane_abs_err_other_channels"] <= 1e-8
+    else:
+        plate = d["plate"]
+        assert plate["fovs_gathered"] == n_gpus * 256 and "verified" in plate["order"] and plate["fovs_with_status"] == 0
 
 
 def test_reference_arm_line():
-    d = _line("r01_bench_reference_arm.json")
+    d = _line("r02_bench_reference_arm.json")
     assert BASE_KEYS | {"impl", "cpu_baseline"} <= set(d) and d["impl"] == "reference"
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
