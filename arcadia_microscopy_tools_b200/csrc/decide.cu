@@ -23,19 +23,25 @@
 namespace amt {
 namespace dx {
 
-// D(y, x) of one plane in scipy's exact operation order, computed by one warp; every lane returns the value.
-// The axis-0 filters of the 2 r_hi + 1 columns the axis-1 pass of this one sample needs run 32 columns at a time:
-// the warp first stages the (2 r_hi + 1) rows x 32 columns of raw samples it needs in shared memory (row loads
-// of 64 bytes, all independent: one round trip to L2 instead of one per tap), then every lane walks its column in
-// the strip kernels' order (dog.cu: centre tap first, then the tap pairs from the outside in).  The narrow filter's
-// columns and rows are a subset of the wide filter's.
-// tile: (2 r_hi + 1) x 32 uint16; g: (2 r_hi + 1) + (2 r_lo + 1) doubles; both private to the warp.
-__device__ double exact_dog_warp(const uint16_t* __restrict__ plane, int h, int w, int y, int x, double scale,
-                                 const double* __restrict__ whi, int r_hi, const double* __restrict__ wlo, int r_lo,
-                                 uint16_t* __restrict__ tile, double* __restrict__ g) {
-  const int lane = threadIdx.x & 31;
+// D(y, x) of one plane in scipy's exact operation order, computed by one CTA of EVAL_WARPS warps; every thread
+// returns the value.  The axis-0 filters of the 2 r_hi + 1 columns the axis-1 pass of this one sample needs run 32
+// columns per warp, all warps at once: a warp first stages the (2 r_hi + 1) rows x 32 columns of raw samples it
+// needs in shared memory (row loads of 64 bytes, all independent: one round trip to L2 instead of one per tap),
+// then every lane walks its column in the strip kernels' order (dog.cu: centre tap first, then the tap pairs from
+// the outside in).  The narrow filter's columns and rows are a subset of the wide filter's.
+// tile: EVAL_WARPS x (2 r_hi + 1) x 32 uint16; g: (2 r_hi + 1) + (2 r_lo + 1) doubles; both shared by the CTA.
+constexpr int MAX_R_HI = 64, MAX_R_LO = 4;
+constexpr int G_DOUBLES = (2 * MAX_R_HI + 1) + (2 * MAX_R_LO + 1) + 1;
+constexpr int TILE_U16 = (2 * MAX_R_HI + 1) * 32;
+constexpr int EVAL_WARPS = 5;  // ceil((2 * 64 + 1) / 32) column groups
+
+__device__ double exact_dog_cta(const uint16_t* __restrict__ plane, int h, int w, int y, int x, double scale,
+                                const double* __restrict__ whi, int r_hi, const double* __restrict__ wlo, int r_lo,
+                                uint16_t* __restrict__ tiles, double* __restrict__ g) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_hi = 2 * r_hi + 1;
-  for (int c0 = 0; c0 < n_hi; c0 += 32) {
+  uint16_t* tile = tiles + warp * TILE_U16;
+  for (int c0 = warp * 32; c0 < n_hi; c0 += EVAL_WARPS * 32) {
     // column c0 + lane of the window = image column clamp(x - r_hi + c0 + lane) (mode='nearest')
     int xc = x - r_hi + c0 + lane;
     xc = xc < 0 ? 0 : (xc > w - 1 ? w - 1 : xc);
@@ -65,22 +71,18 @@ __device__ double exact_dog_warp(const uint16_t* __restrict__ plane, int h, int 
     }
     __syncwarp();
   }
-  // axis 1 at column x (every lane redundantly: shared-memory broadcasts)
+  __syncthreads();
+  // axis 1 at column x (every thread redundantly: shared-memory broadcasts)
   double hi = dmul(g[r_hi], whi[0]);
   for (int j = r_hi; j >= 1; --j) hi = dadd(hi, dmul(dadd(g[r_hi - j], g[r_hi + j]), whi[j]));
   const double* gl = g + n_hi;
   double lo = dmul(gl[r_lo], wlo[0]);
   for (int j = r_lo; j >= 1; --j) lo = dadd(lo, dmul(dadd(gl[r_lo - j], gl[r_lo + j]), wlo[j]));
-  __syncwarp();
+  __syncthreads();
   return dsub(lo, hi);
 }
 
-constexpr int MAX_R_HI = 64, MAX_R_LO = 4;
-constexpr int G_DOUBLES = (2 * MAX_R_HI + 1) + (2 * MAX_R_LO + 1) + 1;
-constexpr int TILE_U16 = (2 * MAX_R_HI + 1) * 32;
-constexpr int EVAL_WARPS = 4;
-
-// one warp per candidate.  Candidates sit in `n_lists` lists of capacity `cap`: list l belongs to image l / lists_per_img,
+// one CTA per candidate.  Candidates sit in `n_lists` lists of capacity `cap`: list l belongs to image l / lists_per_img,
 // holds min(count[l], cap) pixel indices in idx[l * cap ..], and receives the exact values in val[l * cap ..].
 __global__ void __launch_bounds__(EVAL_WARPS * 32)
 exact_eval_kernel(const uint16_t* __restrict__ in, int64_t img_stride, int h, int w, double scale,
@@ -88,27 +90,26 @@ exact_eval_kernel(const uint16_t* __restrict__ in, int64_t img_stride, int h, in
                   const uint32_t* __restrict__ count, const uint32_t* __restrict__ idx, double* __restrict__ val,
                   int n_lists, int lists_per_img, int cap) {
   __shared__ double s_whi[MAX_R_HI + 1], s_wlo[MAX_R_LO + 1];
-  __shared__ double s_g[EVAL_WARPS][G_DOUBLES];
-  __shared__ uint16_t s_tile[EVAL_WARPS][TILE_U16];
+  __shared__ double s_g[G_DOUBLES];
+  __shared__ uint16_t s_tile[EVAL_WARPS * TILE_U16];
   for (int i = threadIdx.x; i <= r_hi; i += blockDim.x) s_whi[i] = hw_hi[i];
   for (int i = threadIdx.x; i <= r_lo; i += blockDim.x) s_wlo[i] = hw_lo[i];
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // the lists are short and uneven: walk them as one concatenated sequence so that the warps share the work evenly
+  // the lists are short and uneven: walk them as one concatenated sequence so that the CTAs share the work evenly
   int64_t base = 0;
-  const int64_t gw = (int64_t)blockIdx.x * EVAL_WARPS + warp, n_warps = (int64_t)gridDim.x * EVAL_WARPS;
+  const int64_t gb = blockIdx.x, n_blocks = gridDim.x;
   for (int l = 0; l < n_lists; ++l) {
     const uint32_t cl = count[l];
     const int c = (int)(cl < (uint32_t)cap ? cl : (uint32_t)cap);
-    // candidate k of list l has global number base + k; this warp takes those congruent to gw
-    int64_t k0 = (gw - base) % n_warps;
-    if (k0 < 0) k0 += n_warps;
-    for (int64_t k = k0; k < c; k += n_warps) {
+    // candidate k of list l has global number base + k; this CTA takes those congruent to its index
+    int64_t k0 = (gb - base) % n_blocks;
+    if (k0 < 0) k0 += n_blocks;
+    for (int64_t k = k0; k < c; k += n_blocks) {  // block-uniform
       const uint32_t pix = idx[(int64_t)l * cap + k];
       const int y = (int)(pix / (uint32_t)w), x = (int)(pix - (uint32_t)y * (uint32_t)w);
       const uint16_t* plane = in + (int64_t)(l / lists_per_img) * img_stride;
-      const double d = exact_dog_warp(plane, h, w, y, x, scale, s_whi, r_hi, s_wlo, r_lo, s_tile[warp], s_g[warp]);
-      if (lane == 0) val[(int64_t)l * cap + k] = d;
+      const double d = exact_dog_cta(plane, h, w, y, x, scale, s_whi, r_hi, s_wlo, r_lo, s_tile, s_g);
+      if (threadIdx.x == 0) val[(int64_t)l * cap + k] = d;
     }
     base += c;
   }
