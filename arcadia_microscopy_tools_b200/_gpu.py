@@ -410,6 +410,62 @@ def plane_sums_f64(x2d) -> np.ndarray:
     return to_host(out)
 
 
+def li_threshold_f64(plane, lo: float, tolerance=None, initial_guess=None) -> float:
+    """``ski.filters.threshold_li`` of one finite, non-constant float64 plane (flattened, on the device): scikit-image's
+    iteration on ``image - image.min()`` with both class means taken over the PIXELS in NumPy's pairwise order
+    (``amt_li_shift_f64`` / ``amt_li_min_gap_f64`` / ``amt_li_split_f64`` + ``amt_pairwise_sum_f64``); the scalar
+    recurrence runs here in NumPy float64 scalars, as it does in scikit-image."""
+    torch = torch_mod()
+    lib = _lib.load()
+    n = int(plane.numel())
+    plane = plane.contiguous().reshape(-1)
+    shifted = torch.empty(n, dtype=torch.float64, device=plane.device)
+    check(lib.amt_li_shift_f64(ptr(plane), n, float(lo), ptr(shifted), stream_ptr()), "amt_li_shift_f64")
+    if not tolerance:
+        nbytes = lib.amt_li_min_gap_scratch_bytes(n)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=plane.device)
+        gap = torch.empty(1, dtype=torch.float64, device=plane.device)
+        check(lib.amt_li_min_gap_f64(ptr(shifted), n, ptr(gap), ptr(scratch), nbytes, stream_ptr()), "amt_li_min_gap_f64")
+        tolerance = np.float64(to_host(gap)[0]) / 2
+        del scratch
+    if initial_guess is None:
+        t_next = np.float64(plane_sums_f64(shifted.reshape(1, n))[0]) / n  # np.mean
+    elif np.isscalar(initial_guess):
+        t_next = initial_guess - float(lo)
+        top = float(minmax_values(minmax_keys(shifted.reshape(1, n)), True)[0, 1])
+        if not 0 < t_next < top:
+            raise ValueError("The initial guess for threshold_li must be within the range of the image.")
+    elif callable(initial_guess):
+        raise NotImplementedError("threshold_li on a float image: a callable initial_guess would run on the host copy of the "
+                                  "image; pass its value instead")
+    else:
+        raise TypeError("Incorrect type for `initial_guess`")
+    above = torch.empty(n, dtype=torch.float64, device=plane.device)
+    rest = torch.empty(n, dtype=torch.float64, device=plane.device)
+    totals = torch.empty(2, dtype=torch.int64, device=plane.device)
+    nbytes = lib.amt_li_split_scratch_bytes(n)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=plane.device)
+
+    def mean_of(part, count):  # np.mean of the compacted array: pairwise sum / count (nan for an empty one, as NumPy)
+        if count == 0:
+            return np.float64(np.nan)
+        return np.float64(plane_sums_f64(part[:count].reshape(1, count))[0]) / count
+
+    t_curr = -2 * tolerance
+    with np.errstate(all="ignore"):
+        while abs(t_next - t_curr) > tolerance:
+            t_curr = t_next
+            check(lib.amt_li_split_f64(ptr(shifted), n, float(t_curr), ptr(above), ptr(rest), ptr(totals), ptr(scratch), nbytes,
+                                       stream_ptr()), "amt_li_split_f64")
+            n_above, n_rest = (int(v) for v in to_host(totals))
+            mean_fore = mean_of(above, n_above)
+            mean_back = mean_of(rest, n_rest)
+            if mean_back == 0.0:
+                break
+            t_next = (mean_back - mean_fore) / (np.log(mean_back) - np.log(mean_fore))
+    return float(t_next + np.float64(lo))
+
+
 def plane_sums_u16(x2d) -> np.ndarray:
     """Exact integer sum of every uint16 plane (from the device histogram) -> int64 per plane."""
     return np.array([int((c * v).sum()) for c, v in plane_histograms(x2d)], dtype=np.int64)
@@ -521,6 +577,25 @@ def window_threshold_u16(x3d, window: tuple[int, int], kind: int, k: float, r: f
         _lib.load().amt_window_threshold_u16(ptr(x3d), n_img, h, w, int(window[0]), int(window[1]), kind, float(k),
                                              float(r), ptr(mask), ptr(thr), stream_ptr()),
         "amt_window_threshold_u16",
+    )
+    return mask, thr
+
+
+def window_threshold_f64(x3d, window: tuple[int, int], kind: int, k: float, r: float, want_thresholds: bool = False):
+    """niblack (kind 0) / sauvola (kind 1) of (n_img, H, W) float64 planes, scikit-image's float route operation by
+    operation -> uint8 mask (and the float64 threshold image when asked for)."""
+    torch = torch_mod()
+    lib = _lib.load()
+    n_img, h, w = x3d.shape
+    x3d = x3d.contiguous()
+    mask = torch.empty((n_img, h, w), dtype=torch.uint8, device=x3d.device)
+    thr = torch.empty((n_img, h, w), dtype=torch.float64, device=x3d.device) if want_thresholds else None
+    nbytes = lib.amt_window_threshold_f64_scratch_bytes(n_img, h, w, int(window[0]), int(window[1]))
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x3d.device)
+    check(
+        lib.amt_window_threshold_f64(ptr(x3d), n_img, h, w, int(window[0]), int(window[1]), kind, float(k), float(r),
+                                     ptr(mask), ptr(thr), ptr(scratch), nbytes, stream_ptr()),
+        "amt_window_threshold_f64",
     )
     return mask, thr
 

@@ -167,6 +167,13 @@ SIGNATURES: dict[str, tuple] = {
     "amt_outline_trace_find": (_i, [_p, _i64, _i64, _i64, _p, _p]),
     "amt_outline_trace_write": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "amt_executor_create": (_i, [C.POINTER(FovConfig), C.POINTER(_d), _i, C.POINTER(_d), _i, C.POINTER(_p)]),
+    "amt_window_threshold_f64_scratch_bytes": (_sz, [_i64, _i64, _i64, _i, _i]),
+    "amt_window_threshold_f64": (_i, [_p, _i64, _i64, _i64, _i, _i, _i, _d, _d, _p, _p, _p, _sz, _p]),
+    "amt_li_shift_f64": (_i, [_p, _i64, _d, _p, _p]),
+    "amt_li_min_gap_scratch_bytes": (_sz, [_i64]),
+    "amt_li_min_gap_f64": (_i, [_p, _i64, _p, _p, _sz, _p]),
+    "amt_li_split_scratch_bytes": (_sz, [_i64]),
+    "amt_li_split_f64": (_i, [_p, _i64, _d, _p, _p, _p, _p, _sz, _p]),
     "amt_hist_f64": (_i, [_p, _i64, _i64, _p, _i, _p, _p]),
     "amt_pairwise_sum_scratch_bytes": (_sz, [_i64, _i64]),
     "amt_pairwise_sum_f64": (_i, [_p, _i64, _i64, _p, _p, _sz, _p]),

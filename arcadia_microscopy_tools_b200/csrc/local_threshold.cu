@@ -93,9 +93,132 @@ threshold_gt_image_kernel(const T* __restrict__ data, const double* __restrict__
     mask[i] = (double)data[i] > dsub(thr[i], offset) ? 1 : 0;
 }
 
+// ---------------------------------------------------------------- float64 images: skimage's float route
+// ref: operations.py:194-195 -> [3p] skimage.filters.thresholding._mean_std on a float image: np.pad(mode='reflect')
+// by (k//2 + 1, k//2), integral images of the padded plane and of its square as SEQUENTIAL float64 cumulative sums
+// along axis 0 then axis 1 (np.cumsum), window sums as ((I00 - I01) - I10) + I11 (_correlate_sparse's order), then
+// m = sum / size, g2 = sumsq / size, s = sqrt(max(g2 - m*m, 0)).  Float addition does not reassociate, so the sums are
+// formed in exactly that order: one thread per column for axis 0, one thread per row (through transposing
+// shared-memory tiles) for axis 1.
+__device__ __forceinline__ int reflect_index(int i, int n) {  // np.pad 'reflect' (no repeated edge); |overshoot| < n
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+__global__ void __launch_bounds__(256)
+pad_square_kernel(const double* __restrict__ in, int h, int w, int ph, int pw, int oy, int ox, double* __restrict__ p,
+                  double* __restrict__ q) {
+  const int64_t img = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= pw) return;
+  const double v = in[img * (int64_t)h * w + (int64_t)reflect_index(y - oy, h) * w + reflect_index(x - ox, w)];
+  const int64_t o = img * (int64_t)ph * pw + (int64_t)y * pw + x;
+  p[o] = v;
+  q[o] = dmul(v, v);
+}
+
+__global__ void __launch_bounds__(128)
+cumsum_axis0_kernel(double* __restrict__ a, double* __restrict__ b, int ph, int pw) {
+  const int64_t img = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= pw) return;
+  double* pa = a + img * (int64_t)ph * pw + x;
+  double* pb = b + img * (int64_t)ph * pw + x;
+  double sa = pa[0], sb = pb[0];
+  for (int y = 1; y < ph; ++y) {
+    sa = dadd(sa, pa[(int64_t)y * pw]);
+    sb = dadd(sb, pb[(int64_t)y * pw]);
+    pa[(int64_t)y * pw] = sa;
+    pb[(int64_t)y * pw] = sb;
+  }
+}
+
+// 32 rows per CTA; the row is walked left to right in 32-column tiles that pass through shared memory so that the
+// global accesses are row-contiguous while every thread owns one row's running sum
+__global__ void __launch_bounds__(32)
+cumsum_axis1_kernel(double* __restrict__ a, int ph, int pw) {
+  __shared__ double tile[32][33];
+  const int64_t img = blockIdx.y;
+  const int y0 = blockIdx.x * 32, lane = threadIdx.x;
+  double* base = a + img * (int64_t)ph * pw;
+  double run = 0.0;
+  bool first = true;
+  for (int x0 = 0; x0 < pw; x0 += 32) {
+    for (int r = 0; r < 32; ++r)
+      if (y0 + r < ph && x0 + lane < pw) tile[r][lane] = base[(int64_t)(y0 + r) * pw + x0 + lane];
+    __syncwarp();
+    if (y0 + lane < ph) {
+      for (int c = 0; c < 32 && x0 + c < pw; ++c) {
+        run = first ? tile[lane][c] : dadd(run, tile[lane][c]);
+        first = false;
+        tile[lane][c] = run;
+      }
+    }
+    __syncwarp();
+    for (int r = 0; r < 32; ++r)
+      if (y0 + r < ph && x0 + lane < pw) base[(int64_t)(y0 + r) * pw + x0 + lane] = tile[r][lane];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+window_threshold_f64_kernel(const double* __restrict__ in, const double* __restrict__ ip, const double* __restrict__ iq, int h,
+                            int w, int pw, int ph, int k0, int k1, int kind, double kk, double r, uint8_t* __restrict__ mask,
+                            double* __restrict__ thresholds) {
+  const int64_t img = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const double* P = ip + img * (int64_t)ph * pw;
+  const double* Q = iq + img * (int64_t)ph * pw;
+  const int64_t i00 = (int64_t)y * pw + x, i01 = i00 + k1, i10 = i00 + (int64_t)k0 * pw, i11 = i10 + k1;
+  const double total = (double)(k0 * k1);
+  const double m = ddiv(dadd(dsub(dsub(P[i00], P[i01]), P[i10]), P[i11]), total);
+  const double g2 = ddiv(dadd(dsub(dsub(Q[i00], Q[i01]), Q[i10]), Q[i11]), total);
+  double var = dsub(g2, dmul(m, m));
+  var = var < 0.0 ? 0.0 : var;  // np.clip(., 0, None); NaN propagates as in NumPy
+  const double sd = __dsqrt_rn(var);
+  const double t = kind == 0 ? dsub(m, dmul(kk, sd)) : dmul(m, dadd(1.0, dmul(kk, dsub(ddiv(sd, r), 1.0))));
+  const int64_t o = img * (int64_t)h * w + (int64_t)y * w + x;
+  mask[o] = in[o] > t ? 1 : 0;
+  if (thresholds != nullptr) thresholds[o] = t;
+}
+
 }  // namespace amt
 
 extern "C" {
+
+size_t amt_window_threshold_f64_scratch_bytes(int64_t n_img, int64_t h, int64_t w, int window_h, int window_w) {
+  if (n_img <= 0 || h <= 0 || w <= 0 || window_h < 1 || window_w < 1) return 0;
+  return (size_t)2 * n_img * (h + window_h) * (w + window_w) * sizeof(double);
+}
+
+int amt_window_threshold_f64(const double* data, int64_t n_img, int64_t h, int64_t w, int window_h, int window_w, int kind,
+                             double k, double r, uint8_t* mask, double* thresholds, void* scratch, size_t scratch_bytes,
+                             amt_stream_t stream) {
+  using namespace amt;
+  if (!data || !mask || !scratch || n_img <= 0 || h <= 0 || w <= 0) return AMT_ERR_INVALID;
+  if (window_h < 1 || window_w < 1 || window_h % 2 == 0 || window_w % 2 == 0 || (kind != 0 && kind != 1)) return AMT_ERR_INVALID;
+  // np.pad would reflect more than once beyond these; n_img and the padded height ride on grid.z / grid.y
+  if (window_h / 2 + 1 >= h || window_w / 2 + 1 >= w || n_img > 65535 || h + window_h > 65535 || (h + window_h) * (w + window_w) >= (1ll << 31))
+    return AMT_ERR_UNSUPPORTED;
+  if (scratch_bytes < amt_window_threshold_f64_scratch_bytes(n_img, h, w, window_h, window_w)) return AMT_ERR_CAPACITY;
+  const int ph = (int)h + window_h, pw = (int)w + window_w;
+  double* p = (double*)scratch;
+  double* q = p + (size_t)n_img * ph * pw;
+  cudaStream_t st = as_stream(stream);
+  pad_square_kernel<<<dim3((unsigned)ceil_div(pw, 256), (unsigned)ph, (unsigned)n_img), 256, 0, st>>>(
+      data, (int)h, (int)w, ph, pw, window_h / 2 + 1, window_w / 2 + 1, p, q);
+  AMT_LAUNCH_CHECK();
+  cumsum_axis0_kernel<<<dim3((unsigned)ceil_div(pw, 128), (unsigned)n_img), 128, 0, st>>>(p, q, ph, pw);
+  AMT_LAUNCH_CHECK();
+  cumsum_axis1_kernel<<<dim3((unsigned)ceil_div(ph, 32), (unsigned)(2 * n_img)), 32, 0, st>>>(p, ph, pw);  // q follows p
+  AMT_LAUNCH_CHECK();
+  window_threshold_f64_kernel<<<dim3((unsigned)ceil_div(w, 256), (unsigned)h, (unsigned)n_img), 256, 0, st>>>(
+      data, p, q, (int)h, (int)w, pw, ph, window_h, window_w, kind, k, r, mask, thresholds);
+  AMT_LAUNCH_CHECK();
+  return AMT_OK;
+}
 
 int amt_window_threshold_u16(const uint16_t* data, int64_t n_img, int64_t h, int64_t w, int window_h, int window_w,
                              int kind, double k, double r, uint8_t* mask, double* thresholds, amt_stream_t stream) {

@@ -428,12 +428,21 @@ def _apply_histogram_threshold(intensities, method: str, batched: bool, kwargs: 
     t, np_dtype, was_numpy = _prepare(intensities)
     planes = _slices(t, batched)
     integer_image = np_dtype.kind in "iu" and planes.dtype != _gpu.torch_mod().float64
-    if method == "li" and not integer_image:
-        raise NotImplementedError(
-            "method 'li' is implemented for uint8 / uint16 images only (on float images scikit-image iterates over "
-            "means of the thresholded pixels themselves and takes its tolerance from the sorted unique values; "
-            "neither is built on the GPU)")
     thr = np.empty(planes.shape[0], dtype=np.float64)
+    if method == "li" and not integer_image:
+        # float image: scikit-image iterates over means of the thresholded PIXELS and takes its tolerance from the
+        # sorted unique values; both are device passes (csrc/li.cu), the scalar recurrence is NumPy's
+        limits = _gpu.minmax_values(_gpu.minmax_keys(planes), True)
+        if not np.all(np.isfinite(limits)):
+            raise NotImplementedError("method 'li' on a float image holding NaN or infinite values is not built")
+        for i in range(planes.shape[0]):
+            if limits[i, 0] == limits[i, 1]:
+                thr[i] = limits[i, 0]
+            else:
+                thr[i] = _gpu.li_threshold_f64(planes[i], limits[i, 0], kwargs.get("tolerance"), kwargs.get("initial_guess"))
+        d_thr = _gpu.torch_mod().from_numpy(thr).to(planes.device)
+        mask = _gpu.threshold_gt(planes, d_thr).reshape(t.shape).view(_gpu.torch_mod().bool)
+        return _finish(mask, was_numpy)
     if method == "mean" and not integer_image:
         # np.mean(image): NumPy's pairwise float64 sum, reproduced bit for bit on the device, / n
         limits = _gpu.minmax_values(_gpu.minmax_keys(planes), True)
@@ -482,9 +491,9 @@ def _apply_local_threshold(intensities, method: str, batched: bool, kwargs: dict
     (ref: ``operations.py:193-195`` -> ``ski.filters.threshold_local / _niblack / _sauvola`` [3p]).
 
     niblack, sauvola: box mean m and standard deviation s over ``window_size`` (odd), ``m - k*s`` and
-    ``m*(1 + k*(s/r - 1))``; uint8 / uint16 images only (scikit-image's float64 integral images are exact
-    integer arithmetic there, so the result is bit-identical; a float image would need its summation
-    order).  local: Gaussian-weighted mean (threshold_local's default method, the only one reachable
+    ``m*(1 + k*(s/r - 1))``.  uint8 / uint16 images: exact integer window sums (scikit-image's float64 integral
+    images are exact integer arithmetic there, so the result is bit-identical); float64 images: the float64
+    integral images themselves, summed in ``np.cumsum``'s order (``amt_window_threshold_f64``).  local: Gaussian-weighted mean (threshold_local's default method, the only one reachable
     through the reference's signature, whose own ``method`` parameter takes the name; sigma =
     (block_size-1)/6 unless ``param`` is given, ``mode`` 'reflect' or 'nearest') minus ``offset``."""
     torch = _gpu.torch_mod()
@@ -512,15 +521,25 @@ def _apply_local_threshold(intensities, method: str, batched: bool, kwargs: dict
             masks.append(_gpu.threshold_gt_image(planes[i], smooth, float(kwargs.get("offset", 0))))
         mask = torch.stack(masks)
     else:
-        if not integer_image:
-            raise NotImplementedError(
-                f"method '{method}' is implemented for uint8 / uint16 images only (scikit-image's integral images "
-                "are exact there; a float image would need its float64 summation order reproduced)")
         window = _window_per_axis(kwargs.get("window_size", 15), 2, "window_size")
         if any(v % 2 == 0 for v in window):
             raise ValueError(
                 "Window size for `threshold_sauvola` or `threshold_niblack` must not be even on any dimension. "
                 f"Got {window}")
+        if not integer_image:
+            # float image: scikit-image's float64 integral images, summed in np.cumsum's order on the device
+            if window[0] // 2 + 1 >= h or window[1] // 2 + 1 >= w:
+                raise NotImplementedError(f"window_size {window} on a {h}x{w} image: windows smaller than twice the image are built")
+            k = kwargs.get("k", 0.2)
+            r = kwargs.get("r")
+            if r is None:  # dtype_limits(float image, clip_negative=False) = (-1, 1)
+                r = 1.0
+            mask, _ = _gpu.window_threshold_f64(planes, window, 1 if method == "sauvola" else 0, k, r)
+            limits = _gpu.minmax_values(mm, True)
+            for i in np.flatnonzero(limits[:, 0] == limits[:, 1]):
+                mask[int(i)].zero_()
+            mask = mask.reshape(t.shape).view(torch.bool)
+            return _finish(mask, was_numpy)
         if max(window) > 127 or window[0] // 2 >= max(h, 2) or window[1] // 2 >= max(w, 2):
             raise NotImplementedError(f"window_size {window} on a {h}x{w} image: windows up to 127 and smaller than "
                                       "twice the image are built")
@@ -555,8 +574,8 @@ def apply_threshold(
     Empty or constant input -> all False (checked before the method name, as in the
     reference).  All ten methods of the reference run on the B200 path: ``otsu``, ``li``, ``yen``,
     ``isodata``, ``mean``, ``minimum``, ``triangle`` from skimage's histogram (exact per-value counts for
-    integer images, ``nbins`` uniform bins for float images; ``li`` for integer images only), and
-    the local-window methods ``local`` (Gaussian), ``niblack``, ``sauvola`` (integer images).
+    integer images, ``nbins`` uniform bins for float images; ``li`` on a float image from the pixels themselves), and
+    the local-window methods ``local`` (Gaussian), ``niblack``, ``sauvola``.
     """
     if not _gpu.is_device_array(intensities) and np.asarray(intensities).size == 0:
         return np.zeros_like(np.asarray(intensities), dtype=bool)

@@ -272,6 +272,26 @@ int amt_threshold_gt(const void* data, int in_dtype, int64_t n_img, int64_t n, c
  * amt_threshold_gt_image: mask[i] = data[i] > thresholds[i] - offset (threshold_local's comparison). */
 int amt_window_threshold_u16(const uint16_t* data, int64_t n_img, int64_t h, int64_t w, int window_h, int window_w,
                              int kind, double k, double r, uint8_t* mask, double* thresholds, amt_stream_t stream);
+/* The same two methods on float64 images: scikit-image's float route (np.pad 'reflect', float64 integral images built
+ * with np.cumsum's sequential additions along axis 0 then 1, window sums in _correlate_sparse's order), reproduced
+ * operation by operation.  scratch: amt_window_threshold_f64_scratch_bytes (two padded planes per image). */
+size_t amt_window_threshold_f64_scratch_bytes(int64_t n_img, int64_t h, int64_t w, int window_h, int window_w);
+int amt_window_threshold_f64(const double* data, int64_t n_img, int64_t h, int64_t w, int window_h, int window_w,
+                             int kind, double k, double r, uint8_t* mask, double* thresholds, void* scratch,
+                             size_t scratch_bytes, amt_stream_t stream);
+/* threshold_li on float64 images (ref: operations.py:186 -> [3p] ski.filters.threshold_li, the non-integer branch):
+ * the per-pixel pieces of scikit-image's iteration on image - min; the scalar recurrence stays with the caller.
+ *  amt_li_shift_f64:    out[i] = data[i] - lo (rounded per element);
+ *  amt_li_min_gap_f64:  *gap (device) = min(np.diff(np.unique(data))), +inf when all values are equal; the plane must hold
+ *                       finite values; scratch: amt_li_min_gap_scratch_bytes (a padded copy that is sorted);
+ *  amt_li_split_f64:    above = data[data > t], rest = data[~(data > t)], both in raster order (NumPy's boolean-mask
+ *                       indexing); totals (device) = {len(above), len(rest)}; above / rest hold n doubles each. */
+int amt_li_shift_f64(const double* data, int64_t n, double lo, double* out, amt_stream_t stream);
+size_t amt_li_min_gap_scratch_bytes(int64_t n);
+int amt_li_min_gap_f64(const double* data, int64_t n, double* gap, void* scratch, size_t scratch_bytes, amt_stream_t stream);
+size_t amt_li_split_scratch_bytes(int64_t n);
+int amt_li_split_f64(const double* data, int64_t n, double t, double* above, double* rest, int64_t* totals, void* scratch,
+                     size_t scratch_bytes, amt_stream_t stream);
 int amt_threshold_gt_image(const void* data, int in_dtype, int64_t n, const double* thresholds, double offset,
                            uint8_t* mask, amt_stream_t stream);
 

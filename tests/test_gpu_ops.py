@@ -342,8 +342,17 @@ def test_li_minimum_triangle_match_oracle(method):
     if method == "li":
         kw = dict(tolerance=0.1, initial_guess=float(u16[0].mean()) * 1.4)
         assert np.array_equal(operations.apply_threshold(u16[0], "li", **kw), oracle.apply_threshold(u16[0].copy(), "li", **kw))
-        with pytest.raises(NotImplementedError, match="uint8 / uint16 images only"):
-            operations.apply_threshold(base[0] / 65535.0, "li")
+        # float images: scikit-image iterates over the pixels; shapes off every block / tile boundary
+        f = base / 65535.0
+        for img in (f[0], f[1, :97, :61], f[2, :33, :64] - 0.2, np.round(f[0], 2)):
+            want = oracle.apply_threshold(img.copy(), "li")
+            assert 0 < want.sum() < want.size and np.array_equal(operations.apply_threshold(img, "li"), want), img.shape
+        kw = dict(tolerance=1e-4, initial_guess=float(f[0].mean()) * 1.3)
+        assert np.array_equal(operations.apply_threshold(f[0], "li", **kw), oracle.apply_threshold(f[0].copy(), "li", **kw))
+        chain = operations.rescale_by_percentile(u16[0], (1, 99))  # the realistic chain the verdict names
+        assert np.array_equal(operations.apply_threshold(chain, "li"), oracle.apply_threshold(chain.copy(), "li"))
+        with pytest.raises(ValueError, match="initial guess"):
+            operations.apply_threshold(f[0], "li", initial_guess=5.0)
         # 'mean' on float64 planes: NumPy's pairwise sum reproduced bit for bit on the device
         for shape2 in ((150, 130), (97, 257), (1, 5), (640, 1000)):
             f = rng.random(shape2) * 3.0 - 1.0
@@ -368,6 +377,43 @@ def test_li_minimum_triangle_match_oracle(method):
     assert not operations.apply_threshold(np.full((32, 32), 7, dtype=np.uint16), method).any()
     with pytest.raises(TypeError, match="unexpected keyword argument"):
         operations.apply_threshold(u16[0], method, window_size=15)
+
+
+def test_li_float_building_blocks_against_numpy():
+    """csrc/li.cu piece by piece: min(diff(unique(.))) through the device sort, and the stable split (= NumPy's
+    boolean-mask indexing, order kept) whose pairwise sums equal np.sum of the compacted arrays bit for bit."""
+    import ctypes as C
+
+    import torch
+
+    from arcadia_microscopy_tools_b200 import _lib as L
+
+    lib = L.load()
+    rng = np.random.default_rng(321)
+    for n in (1, 2, 1000, 2048, 2049, 5000, 70001, 300000):
+        x = rng.gamma(2.0, 0.1, n)
+        x[rng.integers(0, n, n // 3)] = x[0]  # duplicates
+        d = torch.from_numpy(x).cuda()
+        nbytes = lib.amt_li_min_gap_scratch_bytes(n)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        gap = torch.empty(1, dtype=torch.float64, device="cuda")
+        L.check(lib.amt_li_min_gap_f64(d.data_ptr(), n, gap.data_ptr(), scratch.data_ptr(), nbytes, None))
+        uniq = np.unique(x)
+        want = np.min(np.diff(uniq)) if uniq.size > 1 else np.inf
+        assert gap.item() == want, (n, gap.item(), want)
+        sorted_copy = scratch[: 8 * n].view(torch.float64).cpu().numpy()
+        assert np.array_equal(sorted_copy, np.sort(x)), n
+        t = float(np.median(x))
+        above, rest = torch.empty_like(d), torch.empty_like(d)
+        totals = torch.empty(2, dtype=torch.int64, device="cuda")
+        nb2 = lib.amt_li_split_scratch_bytes(n)
+        scratch2 = torch.empty(nb2, dtype=torch.uint8, device="cuda")
+        L.check(lib.amt_li_split_f64(d.data_ptr(), n, C.c_double(t), above.data_ptr(), rest.data_ptr(), totals.data_ptr(),
+                                     scratch2.data_ptr(), nb2, None))
+        na, nr = totals.tolist()
+        assert np.array_equal(above[:na].cpu().numpy(), x[x > t]) and np.array_equal(rest[:nr].cpu().numpy(), x[~(x > t)]), n
+        if na:
+            assert _gpu.plane_sums_f64(above[:na].reshape(1, na))[0] == np.sum(x[x > t])
 
 
 @pytest.mark.parametrize("method", ["otsu", "li", "yen", "isodata", "mean", "minimum", "triangle"])
@@ -416,10 +462,48 @@ def test_window_thresholds_match_oracle(method):
     assert not operations.apply_threshold(np.full((40, 40), 900, np.uint16), method).any()
     with pytest.raises(ValueError, match="must not be even"):
         operations.apply_threshold(u16[0], method, window_size=14)
-    with pytest.raises(NotImplementedError, match="uint8 / uint16 images only"):
-        operations.apply_threshold(u16[0] / 65535.0, method)
     with pytest.raises(NotImplementedError, match="2\\*\\*53"):
         operations.apply_threshold(np.full((2048, 2048), 65535, np.uint16) - (np.arange(2048) % 2).astype(np.uint16), method)
+
+
+@pytest.mark.parametrize("method", ["niblack", "sauvola"])
+def test_window_thresholds_of_float_images_match_oracle(method):
+    """a preprocessed plane is float64.  scikit-image's float route (np.pad 'reflect', float64 integral
+    images by sequential np.cumsum along axis 0 then 1, four-corner sums in _correlate_sparse's order) is reproduced
+    addition by addition: threshold images and masks equal the oracle's bit for bit."""
+    import torch
+
+    rng = np.random.default_rng(93)
+    shape = (3, 101, 77)
+    fg = rng.random(shape) < 0.3
+    f64 = np.where(fg, rng.normal(0.4, 0.05, shape), rng.gamma(2.0, 0.02, shape))
+    f64[1, :40, :30] = 1.0  # flat patch: g2 - m*m rounds to either side of zero and is clipped
+    f64[2] -= 0.3  # negative values
+    func = oracle.threshold.threshold_niblack if method == "niblack" else oracle.threshold.threshold_sauvola
+    for kw in ({}, {"window_size": 3}, {"window_size": (5, 31), "k": 0.35}, {"window_size": 151, "k": -0.1}):
+        win = kw.get("window_size", 15)
+        if win == 151:
+            planes = np.ascontiguousarray(np.tile(f64, (1, 2, 3)))  # a window above the integer path's 127 limit
+        else:
+            planes = f64
+        for i in range(3):
+            want = oracle.apply_threshold(planes[i].copy(), method, **kw)
+            got = operations.apply_threshold(planes[i], method, **kw)
+            assert got.dtype == np.bool_ and np.array_equal(got, want), (method, kw, i, int((got != want).sum()))
+        got = operations.apply_threshold(planes, method, _batched=True, **kw)
+        assert all(np.array_equal(got[i], oracle.apply_threshold(planes[i].copy(), method, **kw)) for i in range(3))
+    d = torch.from_numpy(f64).cuda()
+    _, thr = _gpu.window_threshold_f64(d, (15, 9), 1 if method == "sauvola" else 0, 0.2, 1.0, want_thresholds=True)
+    for i in range(3):
+        kw = {"r": 1.0} if method == "sauvola" else {}
+        _bits_equal(thr[i].cpu().numpy(), func(f64[i].copy(), window_size=(15, 9), k=0.2, **kw), f"{method} float threshold image {i}")
+    # the realistic chain: a rescaled DoG plane
+    fov = make_fov(17, 2, 256, 320, n_cells=60)[0]
+    pre = operations.rescale_by_percentile(operations.subtract_background_dog(fov[1]), (1, 99))
+    assert np.array_equal(operations.apply_threshold(pre, method, window_size=25), oracle.apply_threshold(pre.copy(), method, window_size=25))
+    assert not operations.apply_threshold(np.full((40, 40), 0.25), method).any()
+    with pytest.raises(ValueError, match="must not be even"):
+        operations.apply_threshold(f64[0], method, window_size=14)
 
 
 def test_threshold_local_matches_oracle():
