@@ -600,19 +600,11 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       const bool x_ok = x < p.w;
       const int rows = p.h - y0 < 16 ? p.h - y0 : 16;  // valid rows of this thread's 16 (may be <= 0)
       // the narrow operand: this thread's 16 samples of the stage's float64 tile (lanes are consecutive x: no bank
-      // conflicts), then the stage goes back to the producer
-      double lo[16];
+      // conflicts) are read where they are used (holding them in registers across the accumulator loads spilled);
+      // the stage goes back to the producer after that
       mbar_wait(&bars->full[stage], phase);
-      if (has_lo) {
-        const double* lt = reinterpret_cast<const double*>(stage_s + stage * P2_STAGE_BYTES + P2_DIG_BYTES) + (hrow * 16) * MT + mx;
-#pragma unroll
-        for (int n = 0; n < 16; ++n) lo[n] = lt[n * MT];
-      } else {
-#pragma unroll
-        for (int n = 0; n < 16; ++n) lo[n] = 0.0;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->empty[stage]);
+      const double* lt = reinterpret_cast<const double*>(stage_s + stage * P2_STAGE_BYTES + P2_DIG_BYTES) + (hrow * 16) * MT + mx;
+      uint64_t* const stage_empty = &bars->empty[stage];
       if (++stage == P2_STAGES) stage = 0, phase ^= 1;
       // clamped-edge taps: columns left of 0 / right of w-1 all read the edge column of the same row
       const bool edge_tile = tx * MT < p.r || tx * MT + MT > p.w - p.r;  // warp-uniform
@@ -648,7 +640,11 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty);
-      if (p.dbg & 2) continue;
+      if (p.dbg & 2) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(stage_empty);
+        continue;
+      }
 
       // Branch-free passes over the thread's 16 samples (a per-sample `if` would put every sample in its own basic
       // block and serialise sixteen independent latency chains): integer combine + ONE conversion each, then the
@@ -675,11 +671,13 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       const double scale = p.scale;
       if (has_lo) {
 #pragma unroll
-        for (int n = 0; n < 16; ++n) res[n] = lo[n] - res[n] * scale;
+        for (int n = 0; n < 16; ++n) res[n] = lt[n * MT] - res[n] * scale;
       } else {
 #pragma unroll
         for (int n = 0; n < 16; ++n) res[n] = res[n] * scale;
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stage_empty);
       if (x_ok && rows > 0) {
         double* op = p.out + (int64_t)plane * hw + (int64_t)y0 * p.w + x;
         uint16_t* bp = p.buckets != nullptr ? p.buckets + (int64_t)plane * hw + (int64_t)y0 * p.w + x : nullptr;
