@@ -167,6 +167,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* v) {
       : "r"(addr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(addr)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t addr, uint32_t* v) {
+  static_assert(N == 8 || N == 16, "8 or 16 columns");
+  if (N == 16) tmem_ld16(addr, v); else tmem_ld8(addr, v);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* v) {
   asm volatile(
@@ -204,7 +215,7 @@ struct alignas(8) Barriers {
 // warp % 4 == m / 32.  K element k of a row sits in column k / 4, byte k % 4.
 __device__ __forceinline__ uint32_t tcg_setup(Barriers* bars, const uint8_t* __restrict__ band, int n_stages,
                                               int empty_count, const uint64_t* __restrict__ suffix,
-                                              const double* __restrict__ suffix_f) {
+                                              const double* __restrict__ suffix_f, int epi_warps = EPI_WARPS) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
@@ -212,11 +223,11 @@ __device__ __forceinline__ uint32_t tcg_setup(Barriers* bars, const uint8_t* __r
       mbar_init(&bars->empty[s], empty_count);
     }
     mbar_init(&bars->acc_full, 1);
-    mbar_init(&bars->acc_empty, EPI_WARPS);
+    mbar_init(&bars->acc_empty, epi_warps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < HALO + 2; i += NTHREADS) {
+  for (int i = threadIdx.x; i < HALO + 2; i += blockDim.x) {
     if (suffix != nullptr) bars->suffix[i] = suffix[i];
     if (suffix_f != nullptr) bars->suffix_f[i] = suffix_f[i];
   }
@@ -488,7 +499,10 @@ struct Pass2Params {
 };
 
 // ------------------------------------------------------------------ pass 2: digits -> float64 DoG, axis 1
-__global__ void __launch_bounds__(NTHREADS, 1)
+// EW epilogue warps (8 or 16): TMEM lane quarter = warp % 4, the tile's 32 rows are shared out over the EW / 4 warps of
+// a quarter (RPT rows per thread).
+template <int EW>
+__global__ void __launch_bounds__((2 + EW) * 32, 1)
 tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_constant__ CUtensorMap lo_map,
                  const Pass2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -503,7 +517,8 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
   const int n_tiles = t_end > t_begin ? (int)(t_end - t_begin) : 0;
 
   // a stage is free again once the MMAs have read its digit panels AND the epilogue warps its narrow-Gaussian tile
-  const uint32_t tmem = tcg_setup(bars, p.band, P2_STAGES, 1 + EPI_WARPS, nullptr, p.suffix_f);
+  constexpr int RPT = P2_NR / (EW / 4);  // rows per epilogue thread
+  const uint32_t tmem = tcg_setup(bars, p.band, P2_STAGES, 1 + EW, nullptr, p.suffix_f, EW);
   // x fastest: consecutive tiles of a CTA share half their columns
   TileWalk tw;
   tw.init(t_begin, p.tiles_y, p.tiles_x);
@@ -569,10 +584,10 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
   } else {
     const int ew = warp - 2;
     const int quarter = warp & 3;
-    const int hrow = ew >> 2;               // which 16 of the tile's 32 rows
+    const int hrow = ew >> 2;               // which RPT of the tile's 32 rows
     const int mx = quarter * 32 + lane;     // output column inside the tile
     const int64_t hw = (int64_t)p.h * p.w;
-    const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + TMEM_ACC0 + hrow * 16;
+    const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + TMEM_ACC0 + hrow * RPT;
     // No -0.0 can occur (lo >= +0, g >= +0, and x - x = +0), so float64 comparisons order the values as their keys do
     double vmin = __longlong_as_double(0x7ff0000000000000ll), vmax = __longlong_as_double(0xfff0000000000000ll);
     int cur_q = -1, plane = -1;
@@ -596,14 +611,14 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       }
       const int tx = tw.fast, ty = tw.slow;
       const int x = tx * MT + mx;
-      const int y0 = ty * P2_NR + hrow * 16;
+      const int y0 = ty * P2_NR + hrow * RPT;
       const bool x_ok = x < p.w;
-      const int rows = p.h - y0 < 16 ? p.h - y0 : 16;  // valid rows of this thread's 16 (may be <= 0)
+      const int rows = p.h - y0 < RPT ? p.h - y0 : RPT;  // valid rows of this thread's RPT (may be <= 0)
       // the narrow operand: this thread's 16 samples of the stage's float64 tile (lanes are consecutive x: no bank
       // conflicts) are read where they are used (holding them in registers across the accumulator loads spilled);
       // the stage goes back to the producer after that
       mbar_wait(&bars->full[stage], phase);
-      const double* lt = reinterpret_cast<const double*>(stage_s + stage * P2_STAGE_BYTES + P2_DIG_BYTES) + (hrow * 16) * MT + mx;
+      const double* lt = reinterpret_cast<const double*>(stage_s + stage * P2_STAGE_BYTES + P2_DIG_BYTES) + (hrow * RPT) * MT + mx;
       uint64_t* const stage_empty = &bars->empty[stage];
       if (++stage == P2_STAGES) stage = 0, phase ^= 1;
       // clamped-edge taps: columns left of 0 / right of w-1 all read the edge column of the same row
@@ -626,16 +641,16 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
 
       mbar_wait(&bars->acc_full, (uint32_t)(it & 1));
       tc_fence_after();
-      uint32_t v[NACC2][16];
+      uint32_t v[NACC2][RPT];
       if (!(p.dbg & 4)) {
 #pragma unroll
-        for (int a = 0; a < NACC2; ++a) tmem_ld16(taddr + a * P2_NR, v[a]);
+        for (int a = 0; a < NACC2; ++a) tmem_ldn<RPT>(taddr + a * P2_NR, v[a]);
         tmem_ld_wait();
       } else {
 #pragma unroll
         for (int a = 0; a < NACC2; ++a)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[a][i] = (uint32_t)(it + a + i);
+          for (int i = 0; i < RPT; ++i) v[a][i] = (uint32_t)(it + a + i);
       }
       tc_fence_before();
       __syncwarp();
@@ -649,9 +664,9 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       // Branch-free passes over the thread's 16 samples (a per-sample `if` would put every sample in its own basic
       // block and serialise sixteen independent latency chains): integer combine + ONE conversion each, then the
       // rare edge term for all of them, then scale and subtract.
-      double res[16];
+      double res[RPT];
 #pragma unroll
-      for (int n = 0; n < 16; ++n) {
+      for (int n = 0; n < RPT; ++n) {
         // sum_a acc_a * 256^a, a = 0..5, pairwise: every pair fits 34 bits, the total 61
         static_assert(NACC2 == 6, "the combine below is written for six accumulators");
         const uint64_t p01 = (uint64_t)v[1][n] * 256u + v[0][n];
@@ -663,7 +678,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       }
       if (edge_tile) {  // warp-uniform
 #pragma unroll
-        for (int n = 0; n < 16; ++n) {
+        for (int n = 0; n < RPT; ++n) {
           const double el = __shfl_sync(0xffffffffu, e_l, n), er = __shfl_sync(0xffffffffu, e_r, n);
           res[n] += f_l * el + f_r * er;
         }
@@ -671,31 +686,31 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       const double scale = p.scale;
       if (has_lo) {
 #pragma unroll
-        for (int n = 0; n < 16; ++n) res[n] = lt[n * MT] - res[n] * scale;
+        for (int n = 0; n < RPT; ++n) res[n] = lt[n * MT] - res[n] * scale;
       } else {
 #pragma unroll
-        for (int n = 0; n < 16; ++n) res[n] = res[n] * scale;
+        for (int n = 0; n < RPT; ++n) res[n] = res[n] * scale;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(stage_empty);
       if (x_ok && rows > 0) {
         double* op = p.out + (int64_t)plane * hw + (int64_t)y0 * p.w + x;
         uint16_t* bp = p.buckets != nullptr ? p.buckets + (int64_t)plane * hw + (int64_t)y0 * p.w + x : nullptr;
-        if (rows == 16) {  // the whole run lies inside the plane: no per-row tests
+        if (rows == RPT) {  // the whole run lies inside the plane: no per-row tests
 #pragma unroll
-          for (int n = 0; n < 16; ++n) op[(int64_t)n * p.w] = res[n];
+          for (int n = 0; n < RPT; ++n) op[(int64_t)n * p.w] = res[n];
           if (bp != nullptr) {
 #pragma unroll
-            for (int n = 0; n < 16; ++n) bp[(int64_t)n * p.w] = (uint16_t)bucket12(res[n]);
+            for (int n = 0; n < RPT; ++n) bp[(int64_t)n * p.w] = (uint16_t)bucket12(res[n]);
           }
 #pragma unroll
-          for (int n = 0; n < 16; ++n) {
+          for (int n = 0; n < RPT; ++n) {
             vmin = res[n] < vmin ? res[n] : vmin;
             vmax = res[n] > vmax ? res[n] : vmax;
           }
         } else {
 #pragma unroll
-          for (int n = 0; n < 16; ++n) {
+          for (int n = 0; n < RPT; ++n) {
             if (n < rows) {
               op[(int64_t)n * p.w] = res[n];
               if (bp != nullptr) bp[(int64_t)n * p.w] = (uint16_t)bucket12(res[n]);
@@ -939,14 +954,19 @@ int tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double 
   p.sel = sel;
   p.dbg = g_tcg_debug;
   const int64_t tiles = n_sel * p.tiles_y * p.tiles_x;
-  AMT_CUDA_TRY(cudaFuncSetAttribute(tcg_axis1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM));
+  const bool wide = (g_tcg_debug & 0x400) != 0;  // experiment: 16 epilogue warps
+  AMT_CUDA_TRY(cudaFuncSetAttribute(tcg_axis1_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM));
+  AMT_CUDA_TRY(cudaFuncSetAttribute(tcg_axis1_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM));
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
   CUtensorMap lo_map = dig_map;  // unused when lo == nullptr
   if (lo != nullptr) {
     if ((uintptr_t)lo % 16) return AMT_ERR_UNSUPPORTED;
     AMT_TRY(make_map_f64(&lo_map, lo, (uint64_t)w, (uint64_t)h, (uint64_t)n_img, MT, P2_NR));
   }
-  tcg_axis1_kernel<<<grid, NTHREADS, P2_SMEM, st>>>(dig_map, lo_map, p);
+  if (wide)
+    tcg_axis1_kernel<16><<<grid, (2 + 16) * 32, P2_SMEM, st>>>(dig_map, lo_map, p);
+  else
+    tcg_axis1_kernel<8><<<grid, (2 + 8) * 32, P2_SMEM, st>>>(dig_map, lo_map, p);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
