@@ -193,6 +193,22 @@ class TensorCoreGaussian:
               "amt_tcg_axis1")
         return out, mm, buckets
 
+    def axis1_dog(self, digits, raw, sigma_lo: float, scale: float = 1.0 / 65535.0, want_buckets: bool = False,
+                  skip_every: int = 0, skip_offset: int = 0):
+        """digits + the raw uint16 planes -> (G_lo(raw) - G_hi float64 planes, min/max keys, bucket codes or None): the
+        narrow Gaussian computed inside the tensor-core kernel (``amt_tcg_axis1_dog``, the executor's path)."""
+        torch = self._torch
+        n_img, _, h, w = digits.shape
+        hw = gaussian_half_weights(sigma_lo)
+        d_hw = torch.from_numpy(hw).to(digits.device)
+        out = torch.zeros((n_img, h, w), dtype=torch.float64, device=digits.device)
+        mm = torch.empty((n_img, 2), dtype=torch.int64, device=digits.device)
+        buckets = torch.zeros((n_img, h, w), dtype=torch.int16, device=digits.device) if want_buckets else None
+        check(self.lib.amt_tcg_axis1_dog(self.handle, ptr(digits), ptr(raw), ptr(d_hw), len(hw) - 1, scale, ptr(out), n_img, h,
+                                         w, ptr(buckets), ptr(mm), skip_every, skip_offset, stream_ptr()),
+              "amt_tcg_axis1_dog")
+        return out, mm, buckets
+
 
 def gauss_lo2d(x, scale: float, sigma: float, skip_every: int = 0, skip_offset: int = 0):
     """The narrow Gaussian (radius <= 4) of (n_img, H, W) uint16 planes, float64, scipy's order."""

@@ -133,6 +133,7 @@ SIGNATURES: dict[str, tuple] = {
     "amt_tcg_digit_bytes": (_sz, [_i64, _i64, _i64]),
     "amt_tcg_axis0": (_i, [_p, _p, _i64, _i64, _i64, _p, _i, _i, _p]),
     "amt_tcg_axis1": (_i, [_p, _p, _p, _d, _p, _i64, _i64, _i64, _p, _p, _i, _i, _p]),
+    "amt_tcg_axis1_dog": (_i, [_p, _p, _p, _p, _i, _d, _p, _i64, _i64, _i64, _p, _p, _i, _i, _p]),
     "amt_gauss_lo2d": (_i, [_p, _d, _p, _i64, _i64, _i64, _p, _i, _i, _i, _p]),
     "amt_minmax_filter_axis": (_i, [_p, _i, _p, _p, _i64, _i64, _i64, _i, _i, _i, _p]),
     "amt_deinterleave_u16": (_i, [_p, _p, _i64, _i64, _i, _p]),

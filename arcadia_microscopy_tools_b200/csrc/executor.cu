@@ -114,6 +114,11 @@ int g_exec_swap_prio = 1;
 int g_exec_buckets = 1;
 // amt_tune "exec_tc": 0 switches the tensor-core path off in executors that have one (A/B timing in one process)
 int g_exec_tc = 1;
+// amt_tune "exec_fused_lo": 1 = the narrow Gaussian inside pass 2 (amt_tcg_axis1_dog: 16 B/px less traffic, bit-identical).
+// Off by default: measured SLOWER on B200 (1.11 ms against 0.65 + 0.28 ms per 32 planes): the ~450 extra instructions per
+// epilogue warp and tile run at the same ~7 clk per instruction as the rest of that latency-bound epilogue (2 warps
+// per scheduler at 168 registers), see profiles/r02_tcgauss_experiments.md.
+int g_exec_fused_lo = 0;
 // decision-exact mode: capacities of the candidate lists per plane and window / per plane (overflow = float64 retry)
 constexpr int kDxRankCap = 1024;
 constexpr int kDxBinCap = 16384;
@@ -196,12 +201,15 @@ static int enqueue_dog(amt_executor* ex, const uint16_t* in, int g, cudaEvent_t 
     uint16_t* bk = g_exec_buckets ? ex->buckets[slot] : nullptr;
     ex->buckets_valid[slot] = bk != nullptr;
     AMT_TRY(minmax_init(ex->mm[slot], planes, ex->s_dog));
-    AMT_TRY(tc::lo2d(in, 1.0 / 65535.0, ex->tmp_lo, planes, c.height, c.width, ex->hw_lo, ex->r_lo, all, ex->s_dog));
-    trace_mark(ex, ex->s_dog, "dog: narrow Gaussian done", AMT_STAGE_DOG_LO);
+    const bool fused = g_exec_fused_lo && ex->r_lo <= 4;  // the narrow Gaussian inside pass 2 (no kernel, no plane of its own)
+    if (!fused) {
+      AMT_TRY(tc::lo2d(in, 1.0 / 65535.0, ex->tmp_lo, planes, c.height, c.width, ex->hw_lo, ex->r_lo, all, ex->s_dog));
+      trace_mark(ex, ex->s_dog, "dog: narrow Gaussian done", AMT_STAGE_DOG_LO);
+    }
     AMT_TRY(tc::tcg_axis0(ex->tcg, in, planes, c.height, c.width, ex->digits, all, ex->s_dog));
     trace_mark(ex, ex->s_dog, "dog: tensor-core axis 0 done", AMT_STAGE_DOG_TC0);
     AMT_TRY(tc::tcg_axis1(ex->tcg, ex->digits, ex->tmp_lo, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, bk,
-                          ex->mm[slot], all, ex->s_dog));
+                          ex->mm[slot], all, ex->s_dog, fused ? in : nullptr, ex->hw_lo, ex->r_lo));
     AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_done[slot], ex->s_dog));
     trace_mark(ex, ex->s_dog, "dog: end", AMT_STAGE_DOG_TC1);
     return AMT_OK;
@@ -217,12 +225,15 @@ static int enqueue_dog(amt_executor* ex, const uint16_t* in, int g, cudaEvent_t 
                   ex->r_hi, ex->tmp_lo, ex->tmp_hi, ex->mm[slot], ex->s_dog, bk, &ex->buckets_valid[slot], c.n_channels,
                   c.seg_channel, true));
     trace_mark(ex, ex->s_dog, "dog: exact planes done", AMT_STAGE_DOG_EXACT);
-    AMT_TRY(tc::lo2d(in, 1.0 / 65535.0, ex->tmp_lo, planes, c.height, c.width, ex->hw_lo, ex->r_lo, sel, ex->s_dog));
-    trace_mark(ex, ex->s_dog, "dog: narrow Gaussian done", AMT_STAGE_DOG_LO);
+    const bool fused = g_exec_fused_lo && ex->r_lo <= 4;
+    if (!fused) {
+      AMT_TRY(tc::lo2d(in, 1.0 / 65535.0, ex->tmp_lo, planes, c.height, c.width, ex->hw_lo, ex->r_lo, sel, ex->s_dog));
+      trace_mark(ex, ex->s_dog, "dog: narrow Gaussian done", AMT_STAGE_DOG_LO);
+    }
     AMT_TRY(tc::tcg_axis0(ex->tcg, in, planes, c.height, c.width, ex->digits, sel, ex->s_dog));
     trace_mark(ex, ex->s_dog, "dog: tensor-core axis 0 done", AMT_STAGE_DOG_TC0);
     AMT_TRY(tc::tcg_axis1(ex->tcg, ex->digits, ex->tmp_lo, 1.0 / 65535.0, ex->dog[slot], planes, c.height, c.width, bk,
-                          ex->mm[slot], sel, ex->s_dog));
+                          ex->mm[slot], sel, ex->s_dog, fused ? in : nullptr, ex->hw_lo, ex->r_lo));
     AMT_CUDA_TRY(cudaEventRecord(ex->ev_dog_done[slot], ex->s_dog));
     trace_mark(ex, ex->s_dog, "dog: end", AMT_STAGE_DOG_TC1);
     return AMT_OK;

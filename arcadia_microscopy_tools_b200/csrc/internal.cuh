@@ -79,7 +79,8 @@ bool tcg_shape_ok(int64_t h, int64_t w);
 int tcg_axis0(const amt_tcg* g, const uint16_t* in, int64_t n_img, int64_t h, int64_t w, uint8_t* digits, PlaneSel sel,
               cudaStream_t st);
 int tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double in_scale, double* out, int64_t n_img,
-              int64_t h, int64_t w, uint16_t* buckets, uint64_t* minmax, PlaneSel sel, cudaStream_t st);
+              int64_t h, int64_t w, uint16_t* buckets, uint64_t* minmax, PlaneSel sel, cudaStream_t st,
+              const uint16_t* raw = nullptr, const double* hw_lo = nullptr, int r_lo = 0);
 int lo2d(const uint16_t* in, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w, const double* hw_lo, int r_lo,
          PlaneSel sel, cudaStream_t st);
 }  // namespace tc

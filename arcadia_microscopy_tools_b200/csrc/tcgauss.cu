@@ -67,6 +67,16 @@ constexpr uint32_t P2_PANEL_BYTES = P2_NR * 128;                 // 4 KB
 constexpr uint32_t P2_DIG_BYTES = GD * 2 * P2_PANEL_BYTES;       // 40 KB of digit panels ...
 constexpr uint32_t P2_LO_BYTES = P2_NR * MT * 8;                 // ... and the 32 x 128 float64 tile of the narrow Gaussian
 constexpr uint32_t P2_STAGE_BYTES = P2_DIG_BYTES + P2_LO_BYTES;  // 72 KB
+// pass 2 with the narrow Gaussian fused in: the stage carries a raw uint16 tile (tile + a halo of LO_HALO samples on
+// every side) instead of the float64 tile, and two buffers of axis-0 results sit behind the stages
+constexpr int LO_HALO = 4;                                        // largest radius of the narrow Gaussian
+constexpr int P2F_RAW_HX = 8;                                     // x halo of the raw tile: TMA wants the box to start on a 16-byte boundary (8 uint16)
+constexpr int P2F_RAW_W = MT + 2 * P2F_RAW_HX;                    // 144 samples = 288 bytes
+constexpr int P2F_RAW_H = P2_NR + 2 * LO_HALO;                    // 40 rows
+constexpr uint32_t P2F_RAW_BYTES = P2F_RAW_W * P2F_RAW_H * 2;     // 11520
+constexpr uint32_t P2F_STAGE_BYTES = ((P2_DIG_BYTES + P2F_RAW_BYTES + 1023) / 1024) * 1024;  // 52 KB (panels stay 1 KB aligned)
+constexpr int P2F_V_W = MT + 2 * LO_HALO;                         // axis-0 results of a tile: 136 columns (tile + LO_HALO each side)
+constexpr uint32_t P2F_V_BYTES = P2_NR * P2F_V_W * 8;             // ... x 32 rows, float64
 constexpr uint32_t P1_OUT_BYTES = GD * MT * 128;                 // pass 1 staging: five 128 x 128-byte digit tiles
 // TMEM map (512 columns): the band matrix (A operand) lives in columns [0, 256): digit d, K step ks (32 inputs =
 // 8 columns of 4 bytes) at column d * 64 + ks * 8; the accumulators in [256, 512).
@@ -496,18 +506,57 @@ struct Pass2Params {
   int n_sel, tiles_y, tiles_x;
   PlaneSel sel;
   int dbg;
+  // fused narrow Gaussian (RT > 0): half weights hw_lo[0..r_lo] (device), the raw samples' scale
+  const double* hw_lo;
+  int r_lo;
+  double in_scale;
 };
+
+// N consecutive axis-0 results of the narrow Gaussian down one column of a raw tile, in scipy's order (lo2d_kernel's
+// arithmetic, operation by operation): acc = x0*w0; acc += (x-j + x+j) * wj for j = RT .. 1.  rt_col = the column in the
+// raw tile, whose row 0 is global row gy0; rows outside the plane read the edge row (mode='nearest') when yedge.
+template <int RT, int N>
+__device__ __forceinline__ void lo_axis0_run(const uint16_t* __restrict__ rt_col, const int y_first, const int gy0, const int h,
+                                             const bool yedge, const double scale, const double (&wt)[RT + 1],
+                                             double* __restrict__ vdst) {
+  auto sample = [&](int y) -> double {
+    if (yedge) y = y < 0 ? 0 : (y > h - 1 ? h - 1 : y);
+    return dmul((double)rt_col[(y - gy0) * P2F_RAW_W], scale);
+  };
+  double win[2 * RT + 1];
+#pragma unroll
+  for (int i = 0; i < 2 * RT; ++i) win[i + 1] = sample(y_first - RT + i);
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+#pragma unroll
+    for (int i = 0; i < 2 * RT; ++i) win[i] = win[i + 1];
+    win[2 * RT] = sample(y_first + n + RT);
+    double acc = dmul(win[RT], wt[0]);
+#pragma unroll
+    for (int j = RT; j >= 1; --j) acc = dadd(acc, dmul(dadd(win[RT - j], win[RT + j]), wt[j]));
+    vdst[n * P2F_V_W] = acc;
+  }
+}
 
 // ------------------------------------------------------------------ pass 2: digits -> float64 DoG, axis 1
 // EW epilogue warps (8 or 16): TMEM lane quarter = warp % 4, the tile's 32 rows are shared out over the EW / 4 warps of
 // a quarter (RPT rows per thread).
-template <int EW>
+// RT = 0: the narrow Gaussian comes from memory (lo_map: a float64 tile per stage) or not at all.
+// RT > 0: FUSED.  lo_map describes the raw uint16 planes; a stage carries the tile's raw samples with a halo, the
+// epilogue warps filter them along axis 0 (each thread its own column and rows, a few threads the halo columns) into a
+// double-buffered shared-memory tile while the tile's MMAs run, then along axis 1 where the result is used: the
+// narrow Gaussian never exists in HBM (- 8 B/px written by a kernel of its own, - 8 B/px read here, + 2 B/px).
+template <int EW, int RT>
 __global__ void __launch_bounds__((2 + EW) * 32, 1)
 tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_constant__ CUtensorMap lo_map,
                  const Pass2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* stage_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  Barriers* bars = reinterpret_cast<Barriers*>(stage_s + P2_STAGES * P2_STAGE_BYTES);
+  constexpr bool FUSED = RT > 0;
+  constexpr uint32_t STAGE_BYTES = FUSED ? P2F_STAGE_BYTES : P2_STAGE_BYTES;
+  constexpr uint32_t LO_TX_BYTES = FUSED ? P2F_RAW_BYTES : P2_LO_BYTES;
+  double* const vbuf = reinterpret_cast<double*>(stage_s + P2_STAGES * STAGE_BYTES);  // FUSED: two axis-0 result tiles
+  Barriers* bars = reinterpret_cast<Barriers*>(stage_s + P2_STAGES * STAGE_BYTES + (FUSED ? 2 * P2F_V_BYTES : 0));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int64_t tiles_total = (int64_t)p.n_sel * p.tiles_y * p.tiles_x;
@@ -532,15 +581,19 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       mbar_wait(&bars->empty[stage], phase ^ 1);
       const int plane = p.sel.phys(tw.q);
       if (elect_one()) {
-        uint8_t* dst = stage_s + stage * P2_STAGE_BYTES;
-        mbar_expect_tx(&bars->full[stage], p.lo != nullptr ? P2_STAGE_BYTES : P2_DIG_BYTES);
+        uint8_t* dst = stage_s + stage * STAGE_BYTES;
+        const bool load_lo = FUSED ? !(p.dbg & 16) : p.lo != nullptr;
+        mbar_expect_tx(&bars->full[stage], load_lo ? P2_DIG_BYTES + LO_TX_BYTES : P2_DIG_BYTES);
 #pragma unroll
         for (int s = 0; s < GD; ++s)
 #pragma unroll
           for (int pn = 0; pn < 2; ++pn)
             tma_load_3d(dst + (s * 2 + pn) * P2_PANEL_BYTES, &dig_map, &bars->full[stage], tw.fast * MT - HALO + pn * 128,
                         tw.slow * P2_NR, plane * GD + s);
-        if (p.lo != nullptr) tma_load_3d(dst + P2_DIG_BYTES, &lo_map, &bars->full[stage], tw.fast * MT, tw.slow * P2_NR, plane);
+        if (FUSED && load_lo)
+          tma_load_3d(dst + P2_DIG_BYTES, &lo_map, &bars->full[stage], tw.fast * MT - P2F_RAW_HX, tw.slow * P2_NR - LO_HALO, plane);
+        else if (!FUSED && load_lo)
+          tma_load_3d(dst + P2_DIG_BYTES, &lo_map, &bars->full[stage], tw.fast * MT, tw.slow * P2_NR, plane);
       }
       __syncwarp();
       if (++stage == P2_STAGES) stage = 0, phase ^= 1;
@@ -554,7 +607,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       mbar_wait(&bars->acc_empty, (uint32_t)(it & 1) ^ 1);
       mbar_wait(&bars->full[stage], phase);
       tc_fence_after();
-      const uint32_t b_base = smem_u32(stage_s + stage * P2_STAGE_BYTES);
+      const uint32_t b_base = smem_u32(stage_s + stage * STAGE_BYTES);
       if (elect_one()) {
         if (!(p.dbg & 1)) {
           // K step outermost, then weight digit, then sample digit: consecutive MMAs go to different accumulators
@@ -593,7 +646,10 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
     int cur_q = -1, plane = -1;
     int stage = 0;
     uint32_t phase = 0;
-    const bool has_lo = p.lo != nullptr;
+    const bool has_lo = FUSED || p.lo != nullptr;
+    double wt[RT + 1];
+#pragma unroll
+    for (int j = 0; j <= RT; ++j) wt[j] = (FUSED && j <= p.r_lo) ? __ldg(p.hw_lo + j) : 0.0;
     auto flush = [&]() {
       if (p.minmax != nullptr && plane >= 0) {
         const uint64_t a = warp_min_u64(f64_to_key(vmin)), b = warp_max_u64(f64_to_key(vmax));
@@ -618,8 +674,29 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       // conflicts) are read where they are used (holding them in registers across the accumulator loads spilled);
       // the stage goes back to the producer after that
       mbar_wait(&bars->full[stage], phase);
-      const double* lt = reinterpret_cast<const double*>(stage_s + stage * P2_STAGE_BYTES + P2_DIG_BYTES) + (hrow * RPT) * MT + mx;
+      const double* lt = reinterpret_cast<const double*>(stage_s + stage * STAGE_BYTES + P2_DIG_BYTES) + (hrow * RPT) * MT + mx;
       uint64_t* const stage_empty = &bars->empty[stage];
+      const double* vrow = nullptr;  // FUSED: this thread's first axis-0 result (row hrow * RPT, its own column)
+      if (FUSED) {
+        // axis 0 of the narrow Gaussian, while this tile's MMAs run.  Raw-tile / result-tile column c <-> global column
+        // tile x0 - 8 + c (result tile: x0 - 4 + c), raw-tile row k <-> global row gy0 + k.
+        const uint16_t* rt = reinterpret_cast<const uint16_t*>(stage_s + stage * STAGE_BYTES + P2_DIG_BYTES);
+        double* vb = vbuf + (size_t)(it & 1) * (P2F_V_BYTES / 8);
+        const int gy0 = ty * P2_NR - LO_HALO;
+        const bool yedge = gy0 + LO_HALO - RT < 0 || gy0 + LO_HALO + P2_NR + RT > p.h;  // warp-uniform
+        if (!(p.dbg & 32))
+        lo_axis0_run<RT, RPT>(rt + mx + P2F_RAW_HX, y0, gy0, p.h, yedge, p.in_scale, wt, vb + (hrow * RPT) * P2F_V_W + mx + LO_HALO);
+        // the halo columns left and right of the tile: 2 * RT columns x 32 rows, one value per thread and round
+        for (int v = ew * 32 + lane; v < 2 * RT * P2_NR && !(p.dbg & 32); v += EW * 32) {
+          const int hc = v >> 5, row = v & 31;
+          const int c = hc < RT ? hc - RT : MT + (hc - RT);  // column relative to the tile's first
+          lo_axis0_run<RT, 1>(rt + c + P2F_RAW_HX, ty * P2_NR + row, gy0, p.h, yedge, p.in_scale, wt, vb + row * P2F_V_W + c + LO_HALO);
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(EW * 32) : "memory");  // every column of this tile's axis-0 results is in place
+        vrow = vb + (hrow * RPT) * P2F_V_W + mx + LO_HALO;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(stage_empty);  // the raw tile is used up; the digit panels go back with the MMAs' commit
+      }
       if (++stage == P2_STAGES) stage = 0, phase ^= 1;
       // clamped-edge taps: columns left of 0 / right of w-1 all read the edge column of the same row
       const bool edge_tile = tx * MT < p.r || tx * MT + MT > p.w - p.r;  // warp-uniform
@@ -657,7 +734,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       if (lane == 0) mbar_arrive(&bars->acc_empty);
       if (p.dbg & 2) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(stage_empty);
+        if (!FUSED && lane == 0) mbar_arrive(stage_empty);
         continue;
       }
 
@@ -684,15 +761,42 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
         }
       }
       const double scale = p.scale;
-      if (has_lo) {
+      if (FUSED) {
+        // axis 1 of the narrow Gaussian from the shared-memory tile (columns beyond the plane read the edge column)
+        const bool xedge = tx * MT - RT < 0 || tx * MT + MT + RT > p.w;  // warp-uniform
+        int ol[RT + 1], orr[RT + 1];  // column offsets of the tap pairs relative to this thread's column
+#pragma unroll
+        for (int j = 1; j <= RT; ++j) {
+          ol[j] = -j, orr[j] = j;
+          if (xedge) {
+            const int xl = x - j < 0 ? 0 : (x - j > p.w - 1 ? p.w - 1 : x - j);
+            const int xr = x + j > p.w - 1 ? p.w - 1 : x + j;
+            ol[j] = xl - x, orr[j] = xr - x;
+          }
+        }
+        if (xedge && x > p.w - 1) {  // a column right of the plane (not stored): keep the reads inside the tile
+#pragma unroll
+          for (int j = 1; j <= RT; ++j) ol[j] = 0, orr[j] = 0;
+        }
+#pragma unroll
+        for (int n = 0; n < RPT; ++n) {
+          const double* vr = vrow + n * P2F_V_W;
+          double acc = dmul(vr[0], wt[0]);
+#pragma unroll
+          for (int j = RT; j >= 1; --j) acc = dadd(acc, dmul(dadd(vr[ol[j]], vr[orr[j]]), wt[j]));
+          res[n] = acc - res[n] * scale;
+        }
+      } else if (has_lo) {
 #pragma unroll
         for (int n = 0; n < RPT; ++n) res[n] = lt[n * MT] - res[n] * scale;
       } else {
 #pragma unroll
         for (int n = 0; n < RPT; ++n) res[n] = res[n] * scale;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(stage_empty);
+      if (!FUSED) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(stage_empty);
+      }
       if (x_ok && rows > 0) {
         double* op = p.out + (int64_t)plane * hw + (int64_t)y0 * p.w + x;
         uint16_t* bp = p.buckets != nullptr ? p.buckets + (int64_t)plane * hw + (int64_t)y0 * p.w + x : nullptr;
@@ -849,6 +953,21 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
   return r == CUDA_SUCCESS ? AMT_OK : AMT_ERR_CUDA;
 }
 
+// uint16 tensor (inner, rows, planes) with a (box_inner x box_rows) box, no swizzle, out-of-bounds samples read as zero
+static int make_map_u16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t planes, uint32_t box_inner,
+                        uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return AMT_ERR_UNSUPPORTED;
+  cuuint64_t dims[3] = {inner, rows, planes};
+  cuuint64_t strides[2] = {inner * 2, inner * rows * 2};
+  cuuint32_t box[3] = {box_inner, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? AMT_OK : AMT_ERR_CUDA;
+}
+
 // float64 tensor (inner, rows, planes) with a (box_inner x box_rows) box, no swizzle
 static int make_map_f64(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t planes, uint32_t box_inner,
                         uint32_t box_rows) {
@@ -882,6 +1001,8 @@ namespace tc {
 int g_tcg_debug = 0;  // amt_tune "tcg_debug"
 constexpr size_t P1_SMEM = 1024 + P1_STAGES * P1_STAGE_BYTES + P1_OUT_BYTES + sizeof(Barriers);
 constexpr size_t P2_SMEM = 1024 + P2_STAGES * P2_STAGE_BYTES + sizeof(Barriers);
+constexpr size_t P2F_SMEM = 1024 + P2_STAGES * P2F_STAGE_BYTES + 2 * P2F_V_BYTES + sizeof(Barriers);
+static_assert(P2F_SMEM <= 227 * 1024, "fused pass 2 exceeds the shared memory of an SM");
 
 bool tcg_shape_ok(int64_t h, int64_t w) { return h >= 128 && w >= 128 && w % 16 == 0 && h * w < (1ll << 31); }
 
@@ -927,10 +1048,23 @@ int tcg_axis0(const amt_tcg* g, const uint16_t* in, int64_t n_img, int64_t h, in
   return AMT_OK;
 }
 
+template <int EW, int RT>
+static int launch_axis1(int grid, size_t smem, const CUtensorMap& dig_map, const CUtensorMap& lo_map, const Pass2Params& p,
+                        cudaStream_t st) {
+  AMT_CUDA_TRY(cudaFuncSetAttribute(tcg_axis1_kernel<EW, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tcg_axis1_kernel<EW, RT><<<grid, (2 + EW) * 32, smem, st>>>(dig_map, lo_map, p);
+  AMT_LAUNCH_CHECK();
+  return AMT_OK;
+}
+
+// raw != nullptr: the narrow Gaussian (half weights hw_lo[0..r_lo] on the device, r_lo <= 4) is computed inside the kernel
+// from the raw uint16 planes and `lo` is ignored; otherwise `lo` (may be null) is the narrow Gaussian in memory.
 int tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double in_scale, double* out, int64_t n_img,
-              int64_t h, int64_t w, uint16_t* buckets, uint64_t* minmax, PlaneSel sel, cudaStream_t st) {
+              int64_t h, int64_t w, uint16_t* buckets, uint64_t* minmax, PlaneSel sel, cudaStream_t st, const uint16_t* raw,
+              const double* hw_lo, int r_lo) {
   if (!g || !digits || !out || n_img <= 0) return AMT_ERR_INVALID;
   if (!tcg_shape_ok(h, w) || ((uintptr_t)digits % 16)) return AMT_ERR_UNSUPPORTED;
+  if (raw != nullptr && (!hw_lo || r_lo < 0 || r_lo > LO_HALO || ((uintptr_t)raw % 16))) return AMT_ERR_UNSUPPORTED;
   int64_t n_sel = 0;
   AMT_TRY(sel_count(n_img, sel, &n_sel));
   if (n_sel == 0) return AMT_OK;
@@ -938,7 +1072,7 @@ int tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double 
   AMT_TRY(make_map(&dig_map, digits, (uint64_t)w, (uint64_t)h, (uint64_t)n_img * GD, 128, P2_NR, CU_TENSOR_MAP_SWIZZLE_128B));
   Pass2Params p{};
   p.digits = digits;
-  p.lo = lo;
+  p.lo = raw != nullptr ? nullptr : lo;
   p.out = out;
   p.buckets = buckets;
   p.minmax = minmax;
@@ -953,22 +1087,23 @@ int tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double 
   p.tiles_x = (int)ceil_div(w, MT);
   p.sel = sel;
   p.dbg = g_tcg_debug;
+  p.hw_lo = hw_lo;
+  p.r_lo = r_lo;
+  p.in_scale = in_scale;
   const int64_t tiles = n_sel * p.tiles_y * p.tiles_x;
-  const bool wide = (g_tcg_debug & 0x400) != 0;  // experiment: 16 epilogue warps
-  AMT_CUDA_TRY(cudaFuncSetAttribute(tcg_axis1_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM));
-  AMT_CUDA_TRY(cudaFuncSetAttribute(tcg_axis1_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM));
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  CUtensorMap lo_map = dig_map;  // unused when lo == nullptr
+  const bool wide = (g_tcg_debug & 0x400) != 0;  // experiment: 16 epilogue warps
+  CUtensorMap lo_map = dig_map;  // unused when there is no narrow operand
+  if (raw != nullptr) {
+    AMT_TRY(make_map_u16(&lo_map, raw, (uint64_t)w, (uint64_t)h, (uint64_t)n_img, P2F_RAW_W, P2F_RAW_H));
+    if (r_lo <= 2) return wide ? launch_axis1<16, 2>(grid, P2F_SMEM, dig_map, lo_map, p, st) : launch_axis1<8, 2>(grid, P2F_SMEM, dig_map, lo_map, p, st);
+    return launch_axis1<8, 4>(grid, P2F_SMEM, dig_map, lo_map, p, st);
+  }
   if (lo != nullptr) {
     if ((uintptr_t)lo % 16) return AMT_ERR_UNSUPPORTED;
     AMT_TRY(make_map_f64(&lo_map, lo, (uint64_t)w, (uint64_t)h, (uint64_t)n_img, MT, P2_NR));
   }
-  if (wide)
-    tcg_axis1_kernel<16><<<grid, (2 + 16) * 32, P2_SMEM, st>>>(dig_map, lo_map, p);
-  else
-    tcg_axis1_kernel<8><<<grid, (2 + 8) * 32, P2_SMEM, st>>>(dig_map, lo_map, p);
-  AMT_LAUNCH_CHECK();
-  return AMT_OK;
+  return wide ? launch_axis1<16, 0>(grid, P2_SMEM, dig_map, lo_map, p, st) : launch_axis1<8, 0>(grid, P2_SMEM, dig_map, lo_map, p, st);
 }
 
 int lo2d(const uint16_t* in, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w, const double* hw_lo, int r_lo,
@@ -1131,6 +1266,15 @@ int amt_tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, dou
   if (minmax_keys && n_img > 0) AMT_TRY(amt::minmax_init(minmax_keys, n_img, amt::as_stream(stream)));
   return amt::tc::tcg_axis1(g, digits, lo, in_scale, out, n_img, h, w, buckets, minmax_keys,
                             amt::tc::PlaneSel{skip_every, skip_offset}, amt::as_stream(stream));
+}
+
+int amt_tcg_axis1_dog(const amt_tcg* g, const uint8_t* digits, const uint16_t* raw, const double* half_w_lo, int r_lo,
+                      double in_scale, double* out, int64_t n_img, int64_t h, int64_t w, uint16_t* buckets,
+                      uint64_t* minmax_keys, int skip_every, int skip_offset, amt_stream_t stream) {
+  if (!raw || !half_w_lo) return AMT_ERR_INVALID;
+  if (minmax_keys && n_img > 0) AMT_TRY(amt::minmax_init(minmax_keys, n_img, amt::as_stream(stream)));
+  return amt::tc::tcg_axis1(g, digits, nullptr, in_scale, out, n_img, h, w, buckets, minmax_keys,
+                            amt::tc::PlaneSel{skip_every, skip_offset}, amt::as_stream(stream), raw, half_w_lo, r_lo);
 }
 
 int amt_gauss_lo2d(const uint16_t* in, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,

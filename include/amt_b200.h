@@ -134,6 +134,12 @@ int amt_tcg_axis0(const amt_tcg* g, const uint16_t* in, int64_t n_img, int64_t h
 int amt_tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double in_scale, double* out,
                   int64_t n_img, int64_t h, int64_t w, uint16_t* buckets, uint64_t* minmax_keys,
                   int skip_every, int skip_offset, amt_stream_t stream);
+/* amt_tcg_axis1 with the narrow Gaussian fused in (the executor's path): out = G_lo(raw) - G_hi, where G_lo (half weights
+ * half_w_lo[0..r_lo] on the device, r_lo <= 4) is computed inside the kernel from the raw uint16 planes in scipy's order
+ * (bit-identical to amt_gauss_lo2d followed by amt_tcg_axis1; the narrow Gaussian never exists in HBM). */
+int amt_tcg_axis1_dog(const amt_tcg* g, const uint8_t* digits, const uint16_t* raw, const double* half_w_lo, int r_lo,
+                      double in_scale, double* out, int64_t n_img, int64_t h, int64_t w, uint16_t* buckets,
+                      uint64_t* minmax_keys, int skip_every, int skip_offset, amt_stream_t stream);
 int amt_gauss_lo2d(const uint16_t* in, double in_scale, double* out, int64_t n_img, int64_t h, int64_t w,
                    const double* half_w_lo, int r_lo, int skip_every, int skip_offset, amt_stream_t stream);
 

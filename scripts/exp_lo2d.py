@@ -36,6 +36,7 @@ for mask in [int(a, 0) for a in sys.argv[1:]] or [0]:
     r = {"lo2d_ms": timed(lambda: _lib.check(lib.amt_gauss_lo2d(p(x), SCALE, p(lo), planes, H, W, p(d_lo), len(hw_lo) - 1, 0, 0, st))),
          "axis0_ms": timed(lambda: _lib.check(lib.amt_tcg_axis0(tcg.handle, p(x), planes, H, W, p(digits), 0, 0, st))),
          "axis1_ms": timed(lambda: _lib.check(lib.amt_tcg_axis1(tcg.handle, p(digits), p(lo), SCALE, p(out), planes, H, W, p(buckets), p(mm), 0, 0, st)))}
+    r["axis1_dog_ms"] = timed(lambda: _lib.check(lib.amt_tcg_axis1_dog(tcg.handle, p(digits), p(x), p(d_lo), len(hw_lo) - 1, SCALE, p(out), planes, H, W, p(buckets), p(mm), 0, 0, st)))
     chk = (float(lo.sum()), float(out.sum()), int(buckets.view(torch.uint8).sum()))
     if ref is None:
         ref = chk

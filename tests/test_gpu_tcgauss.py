@@ -91,6 +91,30 @@ def test_dog_planes_against_oracle():
         assert np.abs(dog[i] - want).max() <= TOL_G
 
 
+@pytest.mark.parametrize("shape,kind", [((256, 256), "noise"), ((384, 272), "blob"), ((130, 144), "dim"),
+                                        ((250, 400), "noise"), ((1100, 144), "dim"), ((128, 2048), "noise")])
+@pytest.mark.parametrize("sigma_lo", [0.6, 0.3, 1.0])
+def test_fused_narrow_gaussian_is_bit_identical_to_the_two_kernel_route(shape, kind, sigma_lo):
+    """amt_tcg_axis1_dog (the executor's path: the narrow Gaussian computed inside the tensor-core kernel from a
+    TMA-staged raw tile) against amt_gauss_lo2d + amt_tcg_axis1: planes, bucket codes and min / max bit for bit, for
+    radii 1, 2 and 4, shapes with ragged tile edges, and the image border in every direction; the narrow Gaussian
+    itself is pinned to scipy by test_dog_planes_against_oracle."""
+    tcg = _gpu.TensorCoreGaussian(16.0)
+    imgs = np.stack([_image(51 + i, shape, kind) for i in range(3)])
+    dev = _gpu.to_device(imgs)
+    digits = tcg.axis0(dev)
+    lo = _gpu.gauss_lo2d(dev, SCALE, sigma_lo)
+    want, mm_w, bk_w = tcg.axis1(digits, lo, SCALE, want_buckets=True)
+    got, mm_g, bk_g = tcg.axis1_dog(digits, dev, sigma_lo, SCALE, want_buckets=True)
+    want, got = _gpu.to_host(want), _gpu.to_host(got)
+    bad = np.argwhere(want.view(np.uint64) != got.view(np.uint64))
+    assert bad.size == 0, (shape, kind, sigma_lo, len(bad), bad[:6])
+    assert np.array_equal(_gpu.to_host(bk_w), _gpu.to_host(bk_g))
+    assert np.array_equal(_gpu.to_host(mm_w), _gpu.to_host(mm_g))
+    ref = filters.difference_of_gaussians(imgs[0], sigma_lo, 16.0)
+    assert np.abs(got[0] - ref).max() <= TOL_G
+
+
 def test_plane_skipping():
     """skip_every / skip_offset leave the named planes untouched (the executor's segmentation channel)."""
     tcg = _gpu.TensorCoreGaussian(16.0)
