@@ -29,6 +29,8 @@ struct amt_executor {
   // Measured (AMT_TRACE, scripts/overlap_probe.py): both sides are instruction-issue-bound, so the
   // overlap only recovers the other kernels' memory stalls (~0.5 ms of a 5.9 ms chunk)
   cudaStream_t s_compute, s_dog, s_in, s_out;
+  cudaStream_t s_given;        // the given-mask chain (label + per-cell tables): depends on the inputs only
+  cudaEvent_t ev_fork, ev_join;
   cudaEvent_t ev_start, ev_stop;
   cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
   cudaEvent_t ev_dog_done[2], ev_dog_free[2];
@@ -78,6 +80,9 @@ struct amt_executor {
   uint64_t* acc;
   void* shape_scratch;
   size_t shape_bytes;
+  void* label_scratch_g;     // the same three for the given-mask chain, which runs on its own stream
+  uint64_t* acc_g;
+  void* shape_scratch_g;
   // host-path staging (two slots)
   uint16_t* in_slot[2];
   int32_t* given_slot[2];
@@ -99,7 +104,7 @@ struct amt_executor {
   // amt_executor_set_profiling: an event after every stage; per-stage device milliseconds of the last run
   bool profile;
   std::vector<int>* trace_stage;   // stage id each event closes (-1: a "begin" mark), same order as trace_events
-  std::vector<int>* trace_stream;  // 0 = s_dog, 1 = s_compute
+  std::vector<int>* trace_stream;  // 0 = s_dog, 1 = s_compute, 2 = s_given
   double stage_ms[AMT_N_STAGES];
   int64_t profiled_chunks;
 };
@@ -125,6 +130,9 @@ constexpr int kDxBinCap = 16384;
 // amt_tune "exec_copy_only": 1 = amt_executor_run_host performs every H2D / D2H copy of a batch with the same staging,
 // streams and events but launches no kernel: the copy-only ceiling the host-fed path is measured against
 int g_exec_copy_only = 0;
+// amt_tune "exec_given_stream": 1 (default) = label + tables of the given masks run on a stream of their own next to
+// select / map / label / tables of the thresholded channel (they depend on the inputs only); 0 = one after the other
+int g_exec_given_stream = 1;
 int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st);  // gauss.cu
 
 static int dmalloc(amt_executor* ex, void** p, size_t bytes) {
@@ -142,7 +150,7 @@ static void trace_mark(amt_executor* ex, cudaStream_t st, const char* name, int 
   ex->trace_events->push_back(e);
   ex->trace_names->push_back(name);
   ex->trace_stage->push_back(stage);
-  ex->trace_stream->push_back(st == ex->s_dog ? 0 : 1);
+  ex->trace_stream->push_back(st == ex->s_dog ? 0 : (st == ex->s_given ? 2 : 1));
 }
 
 static void trace_dump(amt_executor* ex) {
@@ -150,7 +158,7 @@ static void trace_dump(amt_executor* ex) {
   cudaDeviceSynchronize();
   if (ex->profile) {
     // a stage lasts from the previous mark on ITS stream to its own mark
-    int last[2] = {-1, -1};
+    int last[3] = {-1, -1, -1};
     for (size_t i = 0; i < ex->trace_events->size(); ++i) {
       const int sid = (*ex->trace_stream)[i], stage = (*ex->trace_stage)[i];
       if (stage >= 0 && last[sid] >= 0) {
@@ -272,6 +280,24 @@ __global__ void fov_status_kernel(const int32_t* __restrict__ cnt_thr, const int
   status[i] = s;
 }
 
+// label + per-cell tables of the given masks of one chunk (own scratch: may run next to the thresholded channel's chain)
+static int given_chain(amt_executor* ex, const uint16_t* in, const int32_t* given, int g, double* tab_given, int32_t* cnt_given,
+                       int32_t* lab_given, int32_t* flags, cudaStream_t sg) {
+  const amt_fov_config& c = ex->cfg;
+  const int C = c.n_channels;
+  const int64_t H = c.height, W = c.width, HW = H * W;
+  AMT_TRY(label_launch(given, 2, HW, nullptr, c.max_label_value, g, H, W, 1, lab_given, cnt_given, ex->label_scratch_g,
+                       ex->label_bytes, sg, flags));
+  trace_mark(ex, sg, "    given: label done", AMT_STAGE_LABEL_GIVEN);
+  AMT_TRY(region_reduce(lab_given, in, C, (int64_t)C * HW, HW, g, H, W, c.max_labels, ex->acc_g, sg));
+  AMT_TRY(region_finalize(ex->acc_g, cnt_given, C, g, c.max_labels, tab_given, sg));
+  if (c.with_shape)
+    AMT_TRY(region_shape(lab_given, ex->acc_g, C, cnt_given, g, H, W, c.max_labels, tab_given, ex->shape_scratch_g,
+                         ex->shape_bytes, sg));
+  trace_mark(ex, sg, "    given: tables done", AMT_STAGE_REGIONS_GIVEN);
+  return AMT_OK;
+}
+
 // everything after the DoG, on s_compute
 static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* given, int g, double* tab_thr,
                          int32_t* cnt_thr, double* tab_given, int32_t* cnt_given, double* thr_out, int32_t* lab_thr_out,
@@ -292,6 +318,15 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
   // stage A2: order statistics -> plan -> map (+ histogram of the segmentation planes)
   AMT_CUDA_TRY(cudaStreamWaitEvent(st, ex->ev_dog_done[slot], 0));
   trace_mark(ex, st, "  rest: begin (dog of this chunk done)");
+  // the given-mask chain needs the inputs only: it runs next to everything below on its own stream
+  const bool with_given = c.quantify_given_mask && given;
+  cudaStream_t sg = g_exec_given_stream ? ex->s_given : st;
+  if (with_given && sg != st) {
+    AMT_CUDA_TRY(cudaEventRecord(ex->ev_fork, st));
+    AMT_CUDA_TRY(cudaStreamWaitEvent(sg, ex->ev_fork, 0));
+    trace_mark(ex, sg, "    given: begin");
+    AMT_TRY(given_chain(ex, in, given, g, tab_given, cnt_given, lab_given, flags, sg));
+  }
   if (ex->buckets_valid[slot] && HW % 8 == 0)
     AMT_TRY(select_f64_bucketed(dog, ex->buckets[slot], planes, HW, ex->ranks, 6, mm, ex->stats, ex->sel_scratch,
                                 ex->sel_bytes, st));
@@ -337,25 +372,21 @@ static int process_chunk(amt_executor* ex, const uint16_t* in, const int32_t* gi
   if (c.with_shape)
     AMT_TRY(region_shape(lab_thr, ex->acc, C, cnt_thr, g, H, W, c.max_labels, tab_thr, ex->shape_scratch, ex->shape_bytes, st));
   trace_mark(ex, st, "  rest: regions(thr) done", AMT_STAGE_REGIONS_THR);
-  if (c.quantify_given_mask && given) {
-    AMT_TRY(label_launch(given, 2, HW, nullptr, c.max_label_value, g, H, W, 1, lab_given, cnt_given, ex->label_scratch,
-                         ex->label_bytes, st, flags));
-    trace_mark(ex, st, "  rest: label(given) done", AMT_STAGE_LABEL_GIVEN);
-    AMT_TRY(region_reduce(lab_given, in, C, (int64_t)C * HW, HW, g, H, W, c.max_labels, ex->acc, st));
-    AMT_TRY(region_finalize(ex->acc, cnt_given, C, g, c.max_labels, tab_given, st));
-    if (c.with_shape)
-      AMT_TRY(region_shape(lab_given, ex->acc, C, cnt_given, g, H, W, c.max_labels, tab_given, ex->shape_scratch,
-                           ex->shape_bytes, st));
+  if (with_given && sg == st) AMT_TRY(given_chain(ex, in, given, g, tab_given, cnt_given, lab_given, flags, st));
+  if (with_given) {
+    if (sg != st) {  // join
+      AMT_CUDA_TRY(cudaEventRecord(ex->ev_join, sg));
+      AMT_CUDA_TRY(cudaStreamWaitEvent(st, ex->ev_join, 0));
+    }
   }
   if (status != nullptr || (dx && retry_out != nullptr)) {
-    const bool with_given = c.quantify_given_mask && given;
     fov_status_kernel<<<(unsigned)ceil_div(g, 128), 128, 0, st>>>(cnt_thr, with_given ? cnt_given : nullptr, flags,
                                                                    flags + c.chunk_fovs, ex->params, C, c.seg_channel,
                                                                    c.max_labels, g, status, retry_flags,
                                                                    dx ? retry_out : nullptr);
     AMT_LAUNCH_CHECK();
   }
-  trace_mark(ex, st, "  rest: end", AMT_STAGE_REGIONS_GIVEN);
+  trace_mark(ex, st, "  rest: end");
   if (ex->profile) ex->profiled_chunks += 1;
   ex->chunks_issued += 1;
   return AMT_OK;
@@ -477,6 +508,9 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
   EX_CUDA(cudaStreamCreateWithPriority(&ex->s_dog, cudaStreamNonBlocking, g_exec_swap_prio ? prio_lo : prio_hi));
   EX_CUDA(cudaStreamCreateWithFlags(&ex->s_in, cudaStreamNonBlocking));
   EX_CUDA(cudaStreamCreateWithFlags(&ex->s_out, cudaStreamNonBlocking));
+  EX_CUDA(cudaStreamCreateWithPriority(&ex->s_given, cudaStreamNonBlocking, g_exec_swap_prio ? prio_hi : prio_lo));
+  EX_CUDA(cudaEventCreateWithFlags(&ex->ev_fork, cudaEventDisableTiming));
+  EX_CUDA(cudaEventCreateWithFlags(&ex->ev_join, cudaEventDisableTiming));
   EX_CUDA(cudaEventCreate(&ex->ev_start));
   EX_CUDA(cudaEventCreate(&ex->ev_stop));
   for (int s = 0; s < 2; ++s) {
@@ -538,6 +572,12 @@ int amt_executor_create(const amt_fov_config* cfg, const double* half_w_lo_host,
     ex->shape_bytes = amt_region_shape_scratch_bytes(cfg->chunk_fovs, cfg->height, cfg->width, cfg->max_labels);
     EX_TRY(dmalloc(ex, &ex->shape_scratch, ex->shape_bytes));
   }
+  if (cfg->quantify_given_mask) {
+    EX_TRY(dmalloc(ex, &ex->label_scratch_g, ex->label_bytes));
+    EX_TRY(dmalloc(ex, (void**)&ex->acc_g,
+                   (size_t)cfg->chunk_fovs * AMT_ACC_FIELDS(C) * cfg->max_labels * sizeof(uint64_t)));
+    if (cfg->with_shape) EX_TRY(dmalloc(ex, &ex->shape_scratch_g, ex->shape_bytes));
+  }
 #undef EX_TRY
 #undef EX_CUDA
   *out = ex;
@@ -555,7 +595,7 @@ void amt_executor_destroy(amt_executor* ex) {
                   ex->buckets[0], ex->buckets[1],
                   ex->stats, ex->params,
                   ex->sel_scratch, ex->hist256, ex->thr, ex->lab_thr, ex->lab_given, ex->label_scratch, ex->acc,
-                  ex->shape_scratch};
+                  ex->shape_scratch, ex->label_scratch_g, ex->acc_g, ex->shape_scratch_g};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (int s = 0; s < 2; ++s) {
@@ -575,6 +615,9 @@ void amt_executor_destroy(amt_executor* ex) {
   if (ex->s_dog) cudaStreamDestroy(ex->s_dog);
   if (ex->s_in) cudaStreamDestroy(ex->s_in);
   if (ex->s_out) cudaStreamDestroy(ex->s_out);
+  if (ex->s_given) cudaStreamDestroy(ex->s_given);
+  if (ex->ev_fork) cudaEventDestroy(ex->ev_fork);
+  if (ex->ev_join) cudaEventDestroy(ex->ev_join);
   delete ex->trace_events;
   delete ex->trace_names;
   delete ex->trace_stage;
