@@ -264,6 +264,10 @@ map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, cons
   const bool collect = HIST && cand_count != nullptr && map_mode(p) == 3;
   const double tol = collect ? cand_eps * fabs(gain) / dsub(p.p2, p.p1) * 1.000001 + 1e-15 : -1.0;
   const int64_t img_h = HIST ? (int64_t)blockIdx.y : 0;
+  const double tol256 = tol * 256.0;
+  // every output sample is a quotient in [0, 1] (modes 2 / 3, out_range (0, 1)) and the histogram spans exactly [0, 1]
+  const bool unit_hist = HIST && (map_mode(p) == 2 || map_mode(p) == 3) && gain == 1.0 && p.o1 == 0.0 && p.hist_first == 0.0 &&
+                         p.hist_last == 1.0 && den.fast && den.b > 0.0;
   auto consider = [&](double x, int bin, int64_t index) {
     const double lo_e = s_edges[bin], hi_e = s_edges[bin + 1];
     const double centre = dmul(dadd(lo_e, hi_e), 0.5);
@@ -303,13 +307,34 @@ map_kernel(const InT* __restrict__ in, double* __restrict__ out, int64_t n, cons
           st_stream(dst + 4 * q2 + 2, v[6], v[7]);
         }
         if (HIST && do_hist) {
+          if (unit_hist) {
+            // histogram range exactly [0, 1] (a rescaled plane whose percentiles clipped something, out_range (0, 1)):
+            // np.histogram's own arithmetic is exact there, (x - 0) / 1 * 256 and edges i / 256, so the bin is
+            // floor(256 x) (256 -> 255), never corrected; distances to edges and centre come from the fraction
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (e < 4 || second) {
-              const int bin = hist_bin_table(hr, hden, s_edges, v[e]);
-              atomicAdd(&wh[bin], 1u);
-              if (collect) consider(v[e], bin, 4 * (e < 4 ? q : q2) + (e & 3));
-            }
+            for (int e = 0; e < 8; ++e)
+              if (e < 4 || second) {
+                const double t = dmul(v[e], 256.0);
+                int bin = (int)t;
+                bin = bin > 255 ? 255 : bin;
+                atomicAdd(&wh[bin], 1u);
+                if (collect) {
+                  const double fr = dsub(t, (double)bin);  // exact; 1.0 for x == 1 (bin 255)
+                  if ((bin > 0 && fr <= tol256) || (bin < 255 && dsub(1.0, fr) <= tol256) || fabs(dsub(fr, 0.5)) <= tol256) {
+                    const uint32_t pos = atomicAdd(&cand_count[img_h], 1u);
+                    if (pos < (uint32_t)cand_cap) cand_idx[img_h * cand_cap + pos] = (uint32_t)(4 * (e < 4 ? q : q2) + (e & 3));
+                  }
+                }
+              }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (e < 4 || second) {
+                const int bin = hist_bin_table(hr, hden, s_edges, v[e]);
+                atomicAdd(&wh[bin], 1u);
+                if (collect) consider(v[e], bin, 4 * (e < 4 ? q : q2) + (e & 3));
+              }
+          }
         }
       }
     } else {

@@ -425,6 +425,40 @@ sel_compact_buckets_kernel(const uint16_t* __restrict__ buckets, const double* _
         lists |= l << (4 * e);
       }
       if (!__any_sync(0xffffffffu, lists != 0xffffffffu)) continue;
+      if (n_lists <= 7) {
+        // every list at once: the lanes' per-list counts ride in one 64-bit word (9 bits per list: a warp holds at most
+        // 256 samples), ONE shuffle scan serves them all, lane l reserves list l's range with its own atomic
+        unsigned long long cnt = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t l = (lists >> (4 * e)) & 0xfu;
+          cnt += l != 0xfu ? 1ull << (9 * l) : 0ull;
+        }
+        unsigned long long incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t base = 0;
+        if (lane < n_lists) {
+          const uint32_t tl = (uint32_t)(total >> (9 * lane)) & 0x1ffu;
+          if (tl) base = atomicAdd(&pl.list_fill[lane], tl);
+        }
+        unsigned long long excl = incl - cnt;  // samples of every list in the lanes before this one
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t l = (lists >> (4 * e)) & 0xfu;
+          const uint32_t b = __shfl_sync(0xffffffffu, base, l & 7u);  // every lane takes part; l == 0xf reads lane 7, unused
+          if (l != 0xfu) {
+            const int64_t pos = (int64_t)b + (int64_t)((excl >> (9 * l)) & 0x1ffull);
+            if (pos < cap) cand[(img * AMT_MAX_RANKS + l) * cap + pos] = __ldg(dp + 8 * q + e);
+            excl += 1ull << (9 * l);
+          }
+        }
+        continue;
+      }
       for (int l = 0; l < n_lists; ++l) {
         uint32_t mine = 0;  // bit e: sample e goes to list l
 #pragma unroll
