@@ -123,7 +123,7 @@ int g_exec_tc = 1;
 // Off by default: measured SLOWER on B200 (1.11 ms against 0.65 + 0.28 ms per 32 planes): the ~450 extra instructions per
 // epilogue warp and tile run at the same ~7 clk per instruction as the rest of that latency-bound epilogue (2 warps
 // per scheduler at 168 registers), see profiles/r02_tcgauss_experiments.md.
-int g_exec_fused_lo = 0;
+int g_exec_fused_lo = 1;
 // decision-exact mode: capacities of the candidate lists per plane and window / per plane (overflow = float64 retry)
 constexpr int kDxRankCap = 1024;
 constexpr int kDxBinCap = 16384;

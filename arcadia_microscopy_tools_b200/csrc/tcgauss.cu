@@ -135,6 +135,12 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+// warpgroup-wide register re-allocation (all four warps of an aligned warpgroup execute it)
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // true in exactly one lane of a converged warp.  Code that issues tcgen05.mma must branch on THIS (not on
 // lane == 0): ptxas then keeps the instruction's operands in uniform registers; under an ordinary divergent branch it
 // wraps every MMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (measured: 60-80 clk per MMA whatever its size).
@@ -214,6 +220,7 @@ __host__ __device__ constexpr uint32_t idesc_u8(int m, int n, bool b_mn_major) {
 struct alignas(8) Barriers {
   uint64_t full[MAX_STAGES], empty[MAX_STAGES];
   uint64_t acc_full, acc_empty;
+  uint64_t lo_full[2], lo_empty[2];  // warp-specialised pass 2: narrow-Gaussian tiles handed from the lo warps to the epilogue warps
   uint64_t suffix[HALO + 2];   // pass 1: integer tail sums of the weights (clamped-edge taps)
   double suffix_f[HALO + 2];   // pass 2: the same, as float64 * 2^-16
   uint32_t tmem_base;
@@ -234,6 +241,10 @@ __device__ __forceinline__ uint32_t tcg_setup(Barriers* bars, const uint8_t* __r
     }
     mbar_init(&bars->acc_full, 1);
     mbar_init(&bars->acc_empty, epi_warps);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars->lo_full[b], epi_warps);
+      mbar_init(&bars->lo_empty[b], epi_warps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -512,30 +523,53 @@ struct Pass2Params {
   double in_scale;
 };
 
+// explicit shared-memory accesses (the tiles' pointers lose their address space in the alignment arithmetic, and
+// generic loads cost an address translation each)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
 // N consecutive axis-0 results of the narrow Gaussian down one column of a raw tile, in scipy's order (lo2d_kernel's
-// arithmetic, operation by operation): acc = x0*w0; acc += (x-j + x+j) * wj for j = RT .. 1.  rt_col = the column in the
-// raw tile, whose row 0 is global row gy0; rows outside the plane read the edge row (mode='nearest') when yedge.
-template <int RT, int N>
-__device__ __forceinline__ void lo_axis0_run(const uint16_t* __restrict__ rt_col, const int y_first, const int gy0, const int h,
-                                             const bool yedge, const double scale, const double (&wt)[RT + 1],
-                                             double* __restrict__ vdst) {
-  auto sample = [&](int y) -> double {
-    if (yedge) y = y < 0 ? 0 : (y > h - 1 ? h - 1 : y);
-    return dmul((double)rt_col[(y - gy0) * P2F_RAW_W], scale);
-  };
-  double win[2 * RT + 1];
+// arithmetic, operation by operation): acc = x0*w0; acc += (x-j + x+j) * wj for j = RT .. 1.  rt_col = shared-memory
+// address of the column in the raw tile, whose row 0 is global row gy0; rows outside the plane read the edge row
+// (mode='nearest') when CLAMP.  Branch-free: all loads, then all conversions, then N independent chains, so that the
+// float64 latencies (the chains are 4 operations deep) overlap.
+template <int RT, int N, bool CLAMP>
+__device__ __forceinline__ void lo_axis0_run_t(const uint32_t rt_col, const int y_first, const int gy0, const int h,
+                                               const double scale, const double (&wt)[RT + 1], const uint32_t vdst) {
+  uint32_t raw[N + 2 * RT];
 #pragma unroll
-  for (int i = 0; i < 2 * RT; ++i) win[i + 1] = sample(y_first - RT + i);
+  for (int i = 0; i < N + 2 * RT; ++i) {
+    int y = y_first - RT + i;
+    if (CLAMP) y = y < 0 ? 0 : (y > h - 1 ? h - 1 : y);
+    raw[i] = lds_u16(rt_col + (uint32_t)((y - gy0) * (P2F_RAW_W * 2)));
+  }
+  double sm[N + 2 * RT];
+#pragma unroll
+  for (int i = 0; i < N + 2 * RT; ++i) sm[i] = dmul((double)raw[i], scale);
 #pragma unroll
   for (int n = 0; n < N; ++n) {
+    double acc = dmul(sm[n + RT], wt[0]);
 #pragma unroll
-    for (int i = 0; i < 2 * RT; ++i) win[i] = win[i + 1];
-    win[2 * RT] = sample(y_first + n + RT);
-    double acc = dmul(win[RT], wt[0]);
-#pragma unroll
-    for (int j = RT; j >= 1; --j) acc = dadd(acc, dmul(dadd(win[RT - j], win[RT + j]), wt[j]));
-    vdst[n * P2F_V_W] = acc;
+    for (int j = RT; j >= 1; --j) acc = dadd(acc, dmul(dadd(sm[n + RT - j], sm[n + RT + j]), wt[j]));
+    sts_f64(vdst + (uint32_t)(n * P2F_V_W * 8), acc);
   }
+}
+template <int RT, int N>
+__device__ __forceinline__ void lo_axis0_run(const uint32_t rt_col, const int y_first, const int gy0, const int h, const bool yedge,
+                                             const double scale, const double (&wt)[RT + 1], const uint32_t vdst) {
+  if (yedge)
+    lo_axis0_run_t<RT, N, true>(rt_col, y_first, gy0, h, scale, wt, vdst);
+  else
+    lo_axis0_run_t<RT, N, false>(rt_col, y_first, gy0, h, scale, wt, vdst);
 }
 
 // ------------------------------------------------------------------ pass 2: digits -> float64 DoG, axis 1
@@ -546,8 +580,14 @@ __device__ __forceinline__ void lo_axis0_run(const uint16_t* __restrict__ rt_col
 // epilogue warps filter them along axis 0 (each thread its own column and rows, a few threads the halo columns) into a
 // double-buffered shared-memory tile while the tile's MMAs run, then along axis 1 where the result is used: the
 // narrow Gaussian never exists in HBM (- 8 B/px written by a kernel of its own, - 8 B/px read here, + 2 B/px).
-template <int EW, int RT>
-__global__ void __launch_bounds__((2 + EW) * 32, 1)
+// WS (with RT > 0): WARP-SPECIALISED fused variant.  Twenty warps: warpgroup 0 = TMA producer, MMA issuer and two idle
+// warps; warpgroups 1-2 = the EW = 8 epilogue warps; warpgroups 3-4 = eight "lo warps" that do nothing but the narrow
+// Gaussian of the NEXT tile (both axes, result in place in the double-buffered shared-memory tile, handed over through
+// lo_full / lo_empty).  Registers follow the roles (setmaxnreg): 32 / 160 / 64 per thread, which adds up to exactly the
+// 640 x 96 the CTA is launched with (an increase can only be served from what the CTA's own warps gave back).  The epilogue warps then
+// run exactly the instructions of the unfused kernel while the extra arithmetic has its own issue slots.
+template <int EW, int RT, bool WS = false>
+__global__ void __launch_bounds__((WS ? 4 + 2 * EW : 2 + EW) * 32, 1)
 tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_constant__ CUtensorMap lo_map,
                  const Pass2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -572,7 +612,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
   TileWalk tw;
   tw.init(t_begin, p.tiles_y, p.tiles_x);
 
-  if (warp == 0) {
+  auto producer = [&]() {
     prefetch_tmap(&dig_map);
     prefetch_tmap(&lo_map);
     int stage = 0;
@@ -598,7 +638,8 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       __syncwarp();
       if (++stage == P2_STAGES) stage = 0, phase ^= 1;
     }
-  } else if (warp == 1) {
+  };
+  auto mma_issuer = [&]() {
     constexpr uint32_t idesc = idesc_u8(MT, P2_NR, false);
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     int stage = 0;
@@ -634,8 +675,80 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       __syncwarp();
       if (++stage == P2_STAGES) stage = 0, phase ^= 1;
     }
-  } else {
-    const int ew = warp - 2;
+  };
+  auto lo_warps = [&]() {
+    // ---- lo warps: the narrow Gaussian of every tile, one tile ahead of the epilogue warps
+    const int lw = warp - (4 + EW);
+    const int quarter = warp & 3, hrow = lw >> 2;
+    const int mx = quarter * 32 + lane;
+    double wt[RT + 1];
+#pragma unroll
+    for (int j = 0; j <= RT; ++j) wt[j] = j <= p.r_lo ? __ldg(p.hw_lo + j) : 0.0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < n_tiles; ++it, tw.next()) {
+      const int tx = tw.fast, ty = tw.slow;
+      const int x = tx * MT + mx;
+      const int y0 = ty * P2_NR + hrow * RPT;
+      const int b = it & 1;
+      double* vb = vbuf + (size_t)b * (P2F_V_BYTES / 8);
+      mbar_wait(&bars->full[stage], phase);                               // the raw tile has landed
+      mbar_wait(&bars->lo_empty[b], ((uint32_t)(it >> 1) & 1u) ^ 1u);     // the epilogue warps are done with this buffer
+      const uint32_t rt = smem_u32(stage_s + stage * STAGE_BYTES + P2_DIG_BYTES);  // raw tile, uint16
+      const uint32_t vs = smem_u32(vb);                                            // result tile, float64
+      const int gy0 = ty * P2_NR - LO_HALO;
+      const bool yedge = gy0 + LO_HALO - RT < 0 || gy0 + LO_HALO + P2_NR + RT > p.h;  // warp-uniform
+      // two halves of RPT / 2 rows: 8 chains in flight fit the lo warps' 64 registers
+      lo_axis0_run<RT, RPT / 2>(rt + (mx + P2F_RAW_HX) * 2, y0, gy0, p.h, yedge, p.in_scale, wt,
+                                vs + ((hrow * RPT) * P2F_V_W + mx + LO_HALO) * 8);
+      lo_axis0_run<RT, RPT / 2>(rt + (mx + P2F_RAW_HX) * 2, y0 + RPT / 2, gy0, p.h, yedge, p.in_scale, wt,
+                                vs + ((hrow * RPT + RPT / 2) * P2F_V_W + mx + LO_HALO) * 8);
+      for (int v = lw * 32 + lane; v < 2 * RT * P2_NR; v += EW * 32) {
+        const int hc = v >> 5, row = v & 31;
+        const int c = hc < RT ? hc - RT : MT + (hc - RT);
+        lo_axis0_run<RT, 1>(rt + (c + P2F_RAW_HX) * 2, ty * P2_NR + row, gy0, p.h, yedge, p.in_scale, wt,
+                            vs + (row * P2F_V_W + c + LO_HALO) * 8);
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(EW * 32) : "memory");  // every column of the axis-0 results is in place
+      if (lane == 0) mbar_arrive(&bars->empty[stage]);            // raw tile used up (bar.sync ordered the warp's reads)
+      if (++stage == P2_STAGES) stage = 0, phase ^= 1;
+      const bool xedge = tx * MT - RT < 0 || tx * MT + MT + RT > p.w;  // warp-uniform
+      int ol[RT + 1], orr[RT + 1];
+#pragma unroll
+      for (int j = 1; j <= RT; ++j) {
+        ol[j] = -j, orr[j] = j;
+        if (xedge) {
+          const int xl = x - j < 0 ? 0 : (x - j > p.w - 1 ? p.w - 1 : x - j);
+          const int xr = x + j > p.w - 1 ? p.w - 1 : x + j;
+          ol[j] = xl - x, orr[j] = xr - x;
+        }
+      }
+      if (xedge && x > p.w - 1) {
+#pragma unroll
+        for (int j = 1; j <= RT; ++j) ol[j] = 0, orr[j] = 0;
+      }
+      const uint32_t vrow = vs + ((hrow * RPT) * P2F_V_W + mx + LO_HALO) * 8;
+      uint32_t al[RT + 1], ar[RT + 1];
+#pragma unroll
+      for (int j = 1; j <= RT; ++j) al[j] = vrow + ol[j] * 8, ar[j] = vrow + orr[j] * 8;
+      double lo[RPT];
+#pragma unroll
+      for (int n = 0; n < RPT; ++n) {
+        double acc = dmul(lds_f64(vrow + n * P2F_V_W * 8), wt[0]);
+#pragma unroll
+        for (int j = RT; j >= 1; --j)
+          acc = dadd(acc, dmul(dadd(lds_f64(al[j] + n * P2F_V_W * 8), lds_f64(ar[j] + n * P2F_V_W * 8)), wt[j]));
+        lo[n] = acc;
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(EW * 32) : "memory");  // every neighbour has been read: the results go in place
+#pragma unroll
+      for (int n = 0; n < RPT; ++n) sts_f64(vrow + n * P2F_V_W * 8, lo[n]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->lo_full[b]);
+    }
+  };
+  auto epilogue = [&]() {
+    const int ew = warp - (WS ? 4 : 2);
     const int quarter = warp & 3;
     const int hrow = ew >> 2;               // which RPT of the tile's 32 rows
     const int mx = quarter * 32 + lane;     // output column inside the tile
@@ -673,24 +786,28 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       // the narrow operand: this thread's 16 samples of the stage's float64 tile (lanes are consecutive x: no bank
       // conflicts) are read where they are used (holding them in registers across the accumulator loads spilled);
       // the stage goes back to the producer after that
-      mbar_wait(&bars->full[stage], phase);
-      const double* lt = reinterpret_cast<const double*>(stage_s + stage * STAGE_BYTES + P2_DIG_BYTES) + (hrow * RPT) * MT + mx;
+      if (!WS) mbar_wait(&bars->full[stage], phase);
+      constexpr int LT_STRIDE = WS ? P2F_V_W : MT;
+      const double* lt = WS ? vbuf + (size_t)(it & 1) * (P2F_V_BYTES / 8) + (hrow * RPT) * P2F_V_W + mx + LO_HALO
+                            : reinterpret_cast<const double*>(stage_s + stage * STAGE_BYTES + P2_DIG_BYTES) + (hrow * RPT) * MT + mx;
       uint64_t* const stage_empty = &bars->empty[stage];
       const double* vrow = nullptr;  // FUSED: this thread's first axis-0 result (row hrow * RPT, its own column)
-      if (FUSED) {
+      if (FUSED && !WS) {
         // axis 0 of the narrow Gaussian, while this tile's MMAs run.  Raw-tile / result-tile column c <-> global column
         // tile x0 - 8 + c (result tile: x0 - 4 + c), raw-tile row k <-> global row gy0 + k.
-        const uint16_t* rt = reinterpret_cast<const uint16_t*>(stage_s + stage * STAGE_BYTES + P2_DIG_BYTES);
+        const uint32_t rt = smem_u32(stage_s + stage * STAGE_BYTES + P2_DIG_BYTES);
         double* vb = vbuf + (size_t)(it & 1) * (P2F_V_BYTES / 8);
+        const uint32_t vs = smem_u32(vb);
         const int gy0 = ty * P2_NR - LO_HALO;
         const bool yedge = gy0 + LO_HALO - RT < 0 || gy0 + LO_HALO + P2_NR + RT > p.h;  // warp-uniform
-        if (!(p.dbg & 32))
-        lo_axis0_run<RT, RPT>(rt + mx + P2F_RAW_HX, y0, gy0, p.h, yedge, p.in_scale, wt, vb + (hrow * RPT) * P2F_V_W + mx + LO_HALO);
+        lo_axis0_run<RT, RPT>(rt + (mx + P2F_RAW_HX) * 2, y0, gy0, p.h, yedge, p.in_scale, wt,
+                              vs + ((hrow * RPT) * P2F_V_W + mx + LO_HALO) * 8);
         // the halo columns left and right of the tile: 2 * RT columns x 32 rows, one value per thread and round
-        for (int v = ew * 32 + lane; v < 2 * RT * P2_NR && !(p.dbg & 32); v += EW * 32) {
+        for (int v = ew * 32 + lane; v < 2 * RT * P2_NR; v += EW * 32) {
           const int hc = v >> 5, row = v & 31;
           const int c = hc < RT ? hc - RT : MT + (hc - RT);  // column relative to the tile's first
-          lo_axis0_run<RT, 1>(rt + c + P2F_RAW_HX, ty * P2_NR + row, gy0, p.h, yedge, p.in_scale, wt, vb + row * P2F_V_W + c + LO_HALO);
+          lo_axis0_run<RT, 1>(rt + (c + P2F_RAW_HX) * 2, ty * P2_NR + row, gy0, p.h, yedge, p.in_scale, wt,
+                              vs + (row * P2F_V_W + c + LO_HALO) * 8);
         }
         asm volatile("bar.sync 2, %0;" ::"n"(EW * 32) : "memory");  // every column of this tile's axis-0 results is in place
         vrow = vb + (hrow * RPT) * P2F_V_W + mx + LO_HALO;
@@ -732,7 +849,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty);
-      if (p.dbg & 2) {
+      if ((p.dbg & 2) && !WS) {
         __syncwarp();
         if (!FUSED && lane == 0) mbar_arrive(stage_empty);
         continue;
@@ -761,7 +878,13 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
         }
       }
       const double scale = p.scale;
-      if (FUSED) {
+      if (WS) {
+        mbar_wait(&bars->lo_full[it & 1], (uint32_t)(it >> 1) & 1u);  // the lo warps have finished this tile
+#pragma unroll
+        for (int n = 0; n < RPT; ++n) res[n] = lt[n * LT_STRIDE] - res[n] * scale;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->lo_empty[it & 1]);
+      } else if (FUSED) {
         // axis 1 of the narrow Gaussian from the shared-memory tile (columns beyond the plane read the edge column)
         const bool xedge = tx * MT - RT < 0 || tx * MT + MT + RT > p.w;  // warp-uniform
         int ol[RT + 1], orr[RT + 1];  // column offsets of the tap pairs relative to this thread's column
@@ -788,7 +911,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
         }
       } else if (has_lo) {
 #pragma unroll
-        for (int n = 0; n < RPT; ++n) res[n] = lt[n * MT] - res[n] * scale;
+        for (int n = 0; n < RPT; ++n) res[n] = lt[n * LT_STRIDE] - res[n] * scale;
       } else {
 #pragma unroll
         for (int n = 0; n < RPT; ++n) res[n] = res[n] * scale;
@@ -826,6 +949,23 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       }
     }
     flush();
+  };
+  if constexpr (WS) {  // registers follow the roles: every warp of a warpgroup re-allocates at the top of its branch
+    if (warp < 4) {
+      reg_dec<32>();
+      if (warp == 0) producer();
+      else if (warp == 1) mma_issuer();
+    } else if (warp < 4 + EW) {
+      reg_inc<160>();
+      epilogue();
+    } else {
+      reg_dec<64>();
+      lo_warps();
+    }
+  } else {
+    if (warp == 0) producer();
+    else if (warp == 1) mma_issuer();
+    else epilogue();
   }
   tc_fence_before();
   __syncthreads();
@@ -1048,11 +1188,11 @@ int tcg_axis0(const amt_tcg* g, const uint16_t* in, int64_t n_img, int64_t h, in
   return AMT_OK;
 }
 
-template <int EW, int RT>
+template <int EW, int RT, bool WS = false>
 static int launch_axis1(int grid, size_t smem, const CUtensorMap& dig_map, const CUtensorMap& lo_map, const Pass2Params& p,
                         cudaStream_t st) {
-  AMT_CUDA_TRY(cudaFuncSetAttribute(tcg_axis1_kernel<EW, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tcg_axis1_kernel<EW, RT><<<grid, (2 + EW) * 32, smem, st>>>(dig_map, lo_map, p);
+  AMT_CUDA_TRY(cudaFuncSetAttribute(tcg_axis1_kernel<EW, RT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tcg_axis1_kernel<EW, RT, WS><<<grid, (WS ? 4 + 2 * EW : 2 + EW) * 32, smem, st>>>(dig_map, lo_map, p);
   AMT_LAUNCH_CHECK();
   return AMT_OK;
 }
@@ -1096,8 +1236,12 @@ int tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double 
   CUtensorMap lo_map = dig_map;  // unused when there is no narrow operand
   if (raw != nullptr) {
     AMT_TRY(make_map_u16(&lo_map, raw, (uint64_t)w, (uint64_t)h, (uint64_t)n_img, P2F_RAW_W, P2F_RAW_H));
-    if (r_lo <= 2) return wide ? launch_axis1<16, 2>(grid, P2F_SMEM, dig_map, lo_map, p, st) : launch_axis1<8, 2>(grid, P2F_SMEM, dig_map, lo_map, p, st);
-    return launch_axis1<8, 4>(grid, P2F_SMEM, dig_map, lo_map, p, st);
+    if (g_tcg_debug & 0x800) {  // experiment: the epilogue warps do the narrow Gaussian themselves (measured slower)
+      if (r_lo <= 2) return wide ? launch_axis1<16, 2>(grid, P2F_SMEM, dig_map, lo_map, p, st) : launch_axis1<8, 2>(grid, P2F_SMEM, dig_map, lo_map, p, st);
+      return launch_axis1<8, 4>(grid, P2F_SMEM, dig_map, lo_map, p, st);
+    }
+    if (r_lo <= 2) return launch_axis1<8, 2, true>(grid, P2F_SMEM, dig_map, lo_map, p, st);
+    return launch_axis1<8, 4, true>(grid, P2F_SMEM, dig_map, lo_map, p, st);
   }
   if (lo != nullptr) {
     if ((uintptr_t)lo % 16) return AMT_ERR_UNSUPPORTED;

@@ -768,7 +768,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--fovs", type=int, default=256, help="FOVs per GPU per step (config 2: 256)")
     ap.add_argument("--unique", type=int, default=8, help="distinct seeded cell layouts")
-    ap.add_argument("--chunk", type=int, default=8, help="FOVs per launch wave")
+    ap.add_argument("--chunk", type=int, default=16, help="FOVs per launch wave (16 measured 5 % faster than 8: the ~25 launch-bound kernels of a chunk amortise)")
     ap.add_argument("--e2e-fovs", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline and the full-size parity check (N=1)")
