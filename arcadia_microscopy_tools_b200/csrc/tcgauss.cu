@@ -572,6 +572,44 @@ __device__ __forceinline__ void lo_axis0_run(const uint32_t rt_col, const int y_
     lo_axis0_run_t<RT, N, false>(rt_col, y_first, gy0, h, scale, wt, vdst);
 }
 
+// Axis 1 of the narrow Gaussian on the shared-memory tile of axis-0 results (vs = its address; column c of the tile <->
+// element LO_HALO + c of a row), rows 4 lw .. 4 lw + 3, results written IN PLACE.  CLAMP: columns outside the plane read
+// the edge column (mode='nearest').
+template <int RT, bool CLAMP>
+__device__ __forceinline__ void lo_axis1_rows(const uint32_t vs, const int lw, const int lane, const int x0, const int w,
+                                              const double (&wt)[RT + 1]) {
+#pragma unroll
+  for (int rr = 0; rr < 4; rr += 2) {
+    double acc[2][4];
+#pragma unroll
+    for (int r2 = 0; r2 < 2; ++r2) {
+      const uint32_t row = vs + (uint32_t)(((4 * lw + rr + r2) * P2F_V_W + LO_HALO) * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = lane + 32 * k;
+        double a = dmul(lds_f64(row + c * 8), wt[0]);
+#pragma unroll
+        for (int j = RT; j >= 1; --j) {
+          int cl = c - j, cr = c + j;
+          if (CLAMP) {
+            cl = (x0 + cl < 0 ? 0 : (x0 + cl > w - 1 ? w - 1 : x0 + cl)) - x0;
+            cr = (x0 + cr < 0 ? 0 : (x0 + cr > w - 1 ? w - 1 : x0 + cr)) - x0;
+          }
+          a = dadd(a, dmul(dadd(lds_f64(row + cl * 8), lds_f64(row + cr * 8)), wt[j]));
+        }
+        acc[r2][k] = a;
+      }
+    }
+    __syncwarp();  // every lane has read its neighbours' columns of these two rows
+#pragma unroll
+    for (int r2 = 0; r2 < 2; ++r2) {
+      const uint32_t row = vs + (uint32_t)(((4 * lw + rr + r2) * P2F_V_W + LO_HALO) * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sts_f64(row + (lane + 32 * k) * 8, acc[r2][k]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ pass 2: digits -> float64 DoG, axis 1
 // EW epilogue warps (8 or 16): TMEM lane quarter = warp % 4, the tile's 32 rows are shared out over the EW / 4 warps of
 // a quarter (RPT rows per thread).
@@ -688,7 +726,6 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
     uint32_t phase = 0;
     for (int it = 0; it < n_tiles; ++it, tw.next()) {
       const int tx = tw.fast, ty = tw.slow;
-      const int x = tx * MT + mx;
       const int y0 = ty * P2_NR + hrow * RPT;
       const int b = it & 1;
       double* vb = vbuf + (size_t)b * (P2F_V_BYTES / 8);
@@ -712,37 +749,14 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       asm volatile("bar.sync 3, %0;" ::"n"(EW * 32) : "memory");  // every column of the axis-0 results is in place
       if (lane == 0) mbar_arrive(&bars->empty[stage]);            // raw tile used up (bar.sync ordered the warp's reads)
       if (++stage == P2_STAGES) stage = 0, phase ^= 1;
+      // axis 1, ROW-partitioned: warp lw owns rows 4 lw .. 4 lw + 3 of the tile, lane l the columns l, l + 32, l + 64,
+      // l + 96.  Every read and the in-place write of a row then happen inside one warp (reads, __syncwarp, writes): no
+      // second CTA-level barrier, and two rows = eight independent float64 chains are in flight per thread.
       const bool xedge = tx * MT - RT < 0 || tx * MT + MT + RT > p.w;  // warp-uniform
-      int ol[RT + 1], orr[RT + 1];
-#pragma unroll
-      for (int j = 1; j <= RT; ++j) {
-        ol[j] = -j, orr[j] = j;
-        if (xedge) {
-          const int xl = x - j < 0 ? 0 : (x - j > p.w - 1 ? p.w - 1 : x - j);
-          const int xr = x + j > p.w - 1 ? p.w - 1 : x + j;
-          ol[j] = xl - x, orr[j] = xr - x;
-        }
-      }
-      if (xedge && x > p.w - 1) {
-#pragma unroll
-        for (int j = 1; j <= RT; ++j) ol[j] = 0, orr[j] = 0;
-      }
-      const uint32_t vrow = vs + ((hrow * RPT) * P2F_V_W + mx + LO_HALO) * 8;
-      uint32_t al[RT + 1], ar[RT + 1];
-#pragma unroll
-      for (int j = 1; j <= RT; ++j) al[j] = vrow + ol[j] * 8, ar[j] = vrow + orr[j] * 8;
-      double lo[RPT];
-#pragma unroll
-      for (int n = 0; n < RPT; ++n) {
-        double acc = dmul(lds_f64(vrow + n * P2F_V_W * 8), wt[0]);
-#pragma unroll
-        for (int j = RT; j >= 1; --j)
-          acc = dadd(acc, dmul(dadd(lds_f64(al[j] + n * P2F_V_W * 8), lds_f64(ar[j] + n * P2F_V_W * 8)), wt[j]));
-        lo[n] = acc;
-      }
-      asm volatile("bar.sync 3, %0;" ::"n"(EW * 32) : "memory");  // every neighbour has been read: the results go in place
-#pragma unroll
-      for (int n = 0; n < RPT; ++n) sts_f64(vrow + n * P2F_V_W * 8, lo[n]);
+      if (xedge)
+        lo_axis1_rows<RT, true>(vs, lw, lane, tx * MT, p.w, wt);
+      else
+        lo_axis1_rows<RT, false>(vs, lw, lane, tx * MT, p.w, wt);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->lo_full[b]);
     }

@@ -408,7 +408,12 @@ def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int, tcg, decision_
         res["tcg_axis0"] = {"ms": ms_a0, "planes": tc_planes, "bytes": tc_planes * px_plane * (2 + 5),
                             "macs": tc_planes * px_plane * 8 * 256, "kernel": "tcg_axis0_kernel"}
         res["tcg_axis1"] = {"ms": ms_a1, "planes": tc_planes, "bytes": tc_planes * px_plane * (5 + 8 + 8 + 2),
-                            "macs": tc_planes * px_plane * 17 * 256, "kernel": "tcg_axis1_kernel"}
+                            "macs": tc_planes * px_plane * 17 * 256, "kernel": "tcg_axis1_kernel<8, 0, false> (narrow Gaussian from memory)"}
+        # the executor's route: the narrow Gaussian computed inside pass 2 by its own warps (no lo2d launch, no float64 plane)
+        ms_f = timed(lambda: L.check(lib.amt_tcg_axis1_dog(tcg.handle, p(digits), p(fovs), p(d_lo), r_lo, scale, p(out), planes, H, W,
+                                                          p(buckets), p(mm), every, off, st)))
+        res["tcg_axis1_dog"] = {"ms": ms_f, "planes": tc_planes, "bytes": tc_planes * px_plane * (5 + 2 + 8 + 2),
+                                "macs": tc_planes * px_plane * 17 * 256, "kernel": "tcg_axis1_kernel<8, 2, true> (warp-specialised, narrow Gaussian fused)"}
     ms_p = timed(probe)
     res["ms_probe"] = ms_p
     res["fp64_peak_tinstr_s"] = dp.value / (ms_p * 1e-3) / 1e12
@@ -639,13 +644,15 @@ def run_b200(args) -> None:
         hw = (_gpu.gaussian_half_weights(cfg.low_sigma), _gpu.gaussian_half_weights(cfg.high_sigma))
         tcg = _gpu.TensorCoreGaussian(cfg.high_sigma) if tensor_cores else None
         k = time_kernels(lib, _gpu, fovs, hw, steps=max(args.steps, 5), warmup=args.warmup, tcg=tcg, decision_exact=decision_exact)
-        kernel_keys = [key for key in ("strip_axis0", "strip_axis1", "lo2d", "tcg_axis0", "tcg_axis1") if key in k]
-        # in decision-exact mode the strip kernels are not on the path (they serve the rare float64 retry only)
-        on_path = [key for key in kernel_keys if not (decision_exact and key.startswith("strip"))]
+        kernel_keys = [key for key in ("strip_axis0", "strip_axis1", "lo2d", "tcg_axis0", "tcg_axis1", "tcg_axis1_dog") if key in k]
+        # in decision-exact mode the strip kernels are not on the path (they serve the rare float64 retry only); lo2d +
+        # tcg_axis1 are the two-kernel route the fused pass 2 replaced (timed for comparison)
+        on_path = [key for key in kernel_keys if not (decision_exact and key.startswith("strip")) and
+                   not ("tcg_axis1_dog" in k and key in ("lo2d", "tcg_axis1"))]
         dom = max(on_path, key=lambda key: k[key]["ms"])
         dom_ms = k[dom]["ms"]
         achieved = k[dom]["bytes"] / (dom_ms * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic(k[dom]["kernel"].split("<")[0])
+        traffic, traffic_src = ncu_traffic(k[dom]["kernel"].split(" (")[0])
         ms_per_step = 1e3 * dev_s / args.steps
         value = world * args.steps * n_fov * C * H * W / dev_s / 1e6
         px_step = n_fov * H * W  # FOV-pixels of the profiled pass
@@ -710,7 +717,7 @@ def run_b200(args) -> None:
         }
         if "tcg_axis1" in k:
             nominal_i8 = 4500.0  # T int8 multiply-adds... dense int8 peak of B200: 4.5 Pop/s = 2.25 P multiply-adds per second
-            for key in ("tcg_axis0", "tcg_axis1"):
+            for key in ("tcg_axis0", "tcg_axis1", "tcg_axis1_dog"):
                 line["kernels"][key]["tmacs"] = k[key]["macs"] / (k[key]["ms"] * 1e-3) / 1e12
                 line["kernels"][key]["frac_of_nominal_int8_peak"] = 2 * line["kernels"][key]["tmacs"] / nominal_i8
         for key in ("strip_axis0", "strip_axis1"):
