@@ -315,8 +315,8 @@ def run_reference(args) -> None:
 # ------------------------------------------------------------------------------------ GPU side
 def ncu_traffic(kernel_substr: str) -> tuple[float | None, str | None]:
     """DRAM bytes per launch of the named kernel from the committed `ncu --set full` capture of this round
-    (profiles/r02_ncu_dog_kernels.json: the same 32-plane chunk, 24 planes on the tensor cores, 8 exact)."""
-    path = ROOT / "profiles" / "r02_ncu_dog_kernels.json"
+    (profiles/r02_ncu_chunk_kernels.json: the kernels of one 8-FOV executor chunk of config 2, scripts/prof_chunk.py)."""
+    path = ROOT / "profiles" / "r02_ncu_chunk_kernels.json"
     if not path.exists():
         return None, None
     for k in json.loads(path.read_text())["kernels"]:
@@ -408,12 +408,12 @@ def time_kernels(lib, gpu, fovs, cfg_hw, steps: int, warmup: int, tcg, decision_
         res["tcg_axis0"] = {"ms": ms_a0, "planes": tc_planes, "bytes": tc_planes * px_plane * (2 + 5),
                             "macs": tc_planes * px_plane * 8 * 256, "kernel": "tcg_axis0_kernel"}
         res["tcg_axis1"] = {"ms": ms_a1, "planes": tc_planes, "bytes": tc_planes * px_plane * (5 + 8 + 8 + 2),
-                            "macs": tc_planes * px_plane * 17 * 256, "kernel": "tcg_axis1_kernel<8, 0, false> (narrow Gaussian from memory)"}
+                            "macs": tc_planes * px_plane * 17 * 256, "kernel": "tcg_axis1_kernel<8, 0, false> (narrow Gaussian from memory)", "ncu_name": "tcg_axis1_kernel<8, 0, 0>"}
         # the executor's route: the narrow Gaussian computed inside pass 2 by its own warps (no lo2d launch, no float64 plane)
         ms_f = timed(lambda: L.check(lib.amt_tcg_axis1_dog(tcg.handle, p(digits), p(fovs), p(d_lo), r_lo, scale, p(out), planes, H, W,
                                                           p(buckets), p(mm), every, off, st)))
         res["tcg_axis1_dog"] = {"ms": ms_f, "planes": tc_planes, "bytes": tc_planes * px_plane * (5 + 2 + 8 + 2),
-                                "macs": tc_planes * px_plane * 17 * 256, "kernel": "tcg_axis1_kernel<8, 2, true> (warp-specialised, narrow Gaussian fused)"}
+                                "macs": tc_planes * px_plane * 17 * 256, "kernel": "tcg_axis1_kernel<8, 2, true> (warp-specialised, narrow Gaussian fused)", "ncu_name": "tcg_axis1_kernel<8, 2, 1>"}
     ms_p = timed(probe)
     res["ms_probe"] = ms_p
     res["fp64_peak_tinstr_s"] = dp.value / (ms_p * 1e-3) / 1e12
@@ -652,7 +652,7 @@ def run_b200(args) -> None:
         dom = max(on_path, key=lambda key: k[key]["ms"])
         dom_ms = k[dom]["ms"]
         achieved = k[dom]["bytes"] / (dom_ms * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic(k[dom]["kernel"].split(" (")[0])
+        traffic, traffic_src = ncu_traffic(k[dom].get("ncu_name", k[dom]["kernel"].split("<")[0]))
         ms_per_step = 1e3 * dev_s / args.steps
         value = world * args.steps * n_fov * C * H * W / dev_s / 1e6
         px_step = n_fov * H * W  # FOV-pixels of the profiled pass
