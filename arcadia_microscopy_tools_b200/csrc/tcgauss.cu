@@ -220,7 +220,6 @@ __host__ __device__ constexpr uint32_t idesc_u8(int m, int n, bool b_mn_major) {
 struct alignas(8) Barriers {
   uint64_t full[MAX_STAGES], empty[MAX_STAGES];
   uint64_t acc_full, acc_empty;
-  uint64_t acc_full_h[2], acc_empty_h[2];  // pass 2: the accumulators of rows 0-15 / 16-31 of a tile are handed over separately
   uint64_t lo_full[2], lo_empty[2];  // warp-specialised pass 2: narrow-Gaussian tiles handed from the lo warps to the epilogue warps
   uint64_t suffix[HALO + 2];   // pass 1: integer tail sums of the weights (clamped-edge taps)
   double suffix_f[HALO + 2];   // pass 2: the same, as float64 * 2^-16
@@ -243,8 +242,6 @@ __device__ __forceinline__ uint32_t tcg_setup(Barriers* bars, const uint8_t* __r
     mbar_init(&bars->acc_full, 1);
     mbar_init(&bars->acc_empty, epi_warps);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&bars->acc_full_h[b], 1);
-      mbar_init(&bars->acc_empty_h[b], epi_warps / 2);
       mbar_init(&bars->lo_full[b], epi_warps);
       mbar_init(&bars->lo_empty[b], epi_warps);
     }
@@ -624,7 +621,7 @@ __device__ __forceinline__ void lo_axis1_rows(const uint32_t vs, const int lw, c
 // WS (with RT > 0): WARP-SPECIALISED fused variant.  Twenty warps: warpgroup 0 = TMA producer, MMA issuer and two idle
 // warps; warpgroups 1-2 = the EW = 8 epilogue warps; warpgroups 3-4 = eight "lo warps" that do nothing but the narrow
 // Gaussian of the NEXT tile (both axes, result in place in the double-buffered shared-memory tile, handed over through
-// lo_full / lo_empty).  Registers follow the roles (setmaxnreg): 40 / 160 / 56 per thread, which stays within the
+// lo_full / lo_empty).  Registers follow the roles (setmaxnreg): 32 / 160 / 64 per thread, which adds up to exactly the
 // 640 x 96 the CTA is launched with (an increase can only be served from what the CTA's own warps gave back).  The epilogue warps then
 // run exactly the instructions of the unfused kernel while the extra arithmetic has its own issue slots.
 template <int EW, int RT, bool WS = false>
@@ -685,50 +682,11 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     int stage = 0;
     uint32_t phase = 0;
-    // The tile's rows 0-15 and 16-31 are two N = 16 MMA groups with accumulator columns and barriers of their own: the
-    // epilogue warps of the first half drain it while the second half's MMAs run, and the next tile's first half starts
-    // as soon as THEY have read their accumulators.  (One N = 32 group per tile made MMAs and epilogue take turns on the
-    // single accumulator set: tensor memory has no room for a second one next to the band matrix.)
-    const bool split = WS || !(p.dbg & 0x1000);
-    constexpr uint32_t idesc16 = idesc_u8(MT, 16, false);
     for (int it = 0; it < n_tiles; ++it) {
-      if (!split) mbar_wait(&bars->acc_empty, (uint32_t)(it & 1) ^ 1);
+      mbar_wait(&bars->acc_empty, (uint32_t)(it & 1) ^ 1);
       mbar_wait(&bars->full[stage], phase);
       tc_fence_after();
       const uint32_t b_base = smem_u32(stage_s + stage * STAGE_BYTES);
-      if (split) {
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          mbar_wait(&bars->acc_empty_h[hf], (uint32_t)(it & 1) ^ 1);
-          tc_fence_after();
-          if (elect_one()) {
-            if (!(p.dbg & 1)) {
-#pragma unroll
-              for (int ks = 0; ks < KBAND / 32; ++ks) {
-#pragma unroll
-                for (int d = 0; d < WD; ++d) {
-#pragma unroll
-                  for (int s = 0; s < GD; ++s) {
-                    const int j = d + s;
-                    if (j < JMIN) continue;
-                    const int d_first = j - (GD - 1) > 0 ? j - (GD - 1) : 0;
-                    // rows 16 hf .. 16 hf + 15 of the K-major panel: two 8-row swizzle atoms further on
-                    const uint64_t b_desc = smem_desc(b_base + (s * 2 + ks / 4) * P2_PANEL_BYTES + (ks % 4) * 32 + hf * 2048, 16,
-                                                      1024, LAYOUT_SW128);
-                    mma_u8_ts(tm + TMEM_ACC0 + (j - JMIN) * P2_NR + hf * 16, tm + d * TMEM_BAND_COLS_PER_DIGIT + ks * 8, b_desc,
-                              idesc16, (ks == 0 && d == d_first) ? 0u : 1u);
-                  }
-                }
-              }
-            }
-            if (hf == 1) mma_commit(&bars->empty[stage]);
-            mma_commit(&bars->acc_full_h[hf]);
-          }
-          __syncwarp();
-        }
-        if (++stage == P2_STAGES) stage = 0, phase ^= 1;
-        continue;
-      }
       if (elect_one()) {
         if (!(p.dbg & 1)) {
           // K step outermost, then weight digit, then sample digit: consecutive MMAs go to different accumulators
@@ -889,9 +847,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
         }
       }
 
-      const bool split = WS || !(p.dbg & 0x1000);
-      const int half = (hrow * RPT) >> 4;  // which 16 rows of the tile this warp's accumulators belong to
-      mbar_wait(split ? &bars->acc_full_h[half] : &bars->acc_full, (uint32_t)(it & 1));
+      mbar_wait(&bars->acc_full, (uint32_t)(it & 1));
       tc_fence_after();
       uint32_t v[NACC2][RPT];
       if (!(p.dbg & 4)) {
@@ -906,7 +862,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(split ? &bars->acc_empty_h[half] : &bars->acc_empty);
+      if (lane == 0) mbar_arrive(&bars->acc_empty);
       if ((p.dbg & 2) && !WS) {
         __syncwarp();
         if (!FUSED && lane == 0) mbar_arrive(stage_empty);
@@ -1010,14 +966,14 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
   };
   if constexpr (WS) {  // registers follow the roles: every warp of a warpgroup re-allocates at the top of its branch
     if (warp < 4) {
-      reg_dec<40>();
+      reg_dec<32>();
       if (warp == 0) producer();
       else if (warp == 1) mma_issuer();
     } else if (warp < 4 + EW) {
       reg_inc<160>();
       epilogue();
     } else {
-      reg_dec<56>();
+      reg_dec<64>();
       lo_warps();
     }
   } else {
