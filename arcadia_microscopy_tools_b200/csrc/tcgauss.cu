@@ -575,6 +575,44 @@ __device__ __forceinline__ void lo_axis0_run(const uint32_t rt_col, const int y_
 // Axis 1 of the narrow Gaussian on the shared-memory tile of axis-0 results (vs = its address; column c of the tile <->
 // element LO_HALO + c of a row), rows 4 lw .. 4 lw + 3, results written IN PLACE.  CLAMP: columns outside the plane read
 // the edge column (mode='nearest').
+__device__ __forceinline__ void lds_f64x2(uint32_t a, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+
+// The same pass for tiles whose taps all lie inside the plane, with a third of the shared-memory traffic (the MMAs'
+// operand fetch and these loads share one port, and the fused kernel is bound by it): lane l owns the column PAIRS
+// 2l, 2l+1 and 64 + 2l, 64 + 2l+1; the 2 + 2 RT values a pair needs come in as 1 + RT 16-byte loads (conflict-free:
+// consecutive lanes, consecutive 16 bytes) and the two results leave as one 16-byte store.
+template <int RT>
+__device__ __forceinline__ void lo_axis1_rows_pairs(const uint32_t vs, const int lw, const int lane, const double (&wt)[RT + 1]) {
+  static_assert(RT % 2 == 0, "the first tap of a pair must be 16-byte aligned");
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const uint32_t row = vs + (uint32_t)(((4 * lw + rr) * P2F_V_W + LO_HALO) * 8);
+    double acc[2][2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = 2 * lane + 64 * k;
+      double v[2 + 2 * RT];
+#pragma unroll
+      for (int i = 0; i < 1 + RT; ++i) lds_f64x2(row + (uint32_t)((c - RT + 2 * i) * 8), v[2 * i], v[2 * i + 1]);
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        double a = dmul(v[RT + o], wt[0]);
+#pragma unroll
+        for (int j = RT; j >= 1; --j) a = dadd(a, dmul(dadd(v[RT + o - j], v[RT + o + j]), wt[j]));
+        acc[k][o] = a;
+      }
+    }
+    __syncwarp();  // every lane has read its neighbours' columns of this row
+#pragma unroll
+    for (int k = 0; k < 2; ++k) sts_f64x2(row + (uint32_t)((2 * lane + 64 * k) * 8), acc[k][0], acc[k][1]);
+  }
+}
+
 template <int RT, bool CLAMP>
 __device__ __forceinline__ void lo_axis1_rows(const uint32_t vs, const int lw, const int lane, const int x0, const int w,
                                               const double (&wt)[RT + 1]) {
@@ -735,7 +773,9 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       const uint32_t vs = smem_u32(vb);                                            // result tile, float64
       const int gy0 = ty * P2_NR - LO_HALO;
       const bool yedge = gy0 + LO_HALO - RT < 0 || gy0 + LO_HALO + P2_NR + RT > p.h;  // warp-uniform
+      const bool lo_math = !(p.dbg & 32);  // timing experiments: the hand-shakes only
       // two halves of RPT / 2 rows: 8 chains in flight fit the lo warps' 64 registers
+      if (lo_math) {
       lo_axis0_run<RT, RPT / 2>(rt + (mx + P2F_RAW_HX) * 2, y0, gy0, p.h, yedge, p.in_scale, wt,
                                 vs + ((hrow * RPT) * P2F_V_W + mx + LO_HALO) * 8);
       lo_axis0_run<RT, RPT / 2>(rt + (mx + P2F_RAW_HX) * 2, y0 + RPT / 2, gy0, p.h, yedge, p.in_scale, wt,
@@ -746,6 +786,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
         lo_axis0_run<RT, 1>(rt + (c + P2F_RAW_HX) * 2, ty * P2_NR + row, gy0, p.h, yedge, p.in_scale, wt,
                             vs + (row * P2F_V_W + c + LO_HALO) * 8);
       }
+      }
       asm volatile("bar.sync 3, %0;" ::"n"(EW * 32) : "memory");  // every column of the axis-0 results is in place
       if (lane == 0) mbar_arrive(&bars->empty[stage]);            // raw tile used up (bar.sync ordered the warp's reads)
       if (++stage == P2_STAGES) stage = 0, phase ^= 1;
@@ -753,8 +794,11 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       // l + 96.  Every read and the in-place write of a row then happen inside one warp (reads, __syncwarp, writes): no
       // second CTA-level barrier, and two rows = eight independent float64 chains are in flight per thread.
       const bool xedge = tx * MT - RT < 0 || tx * MT + MT + RT > p.w;  // warp-uniform
-      if (xedge)
+      if (!lo_math) {
+      } else if (xedge)
         lo_axis1_rows<RT, true>(vs, lw, lane, tx * MT, p.w, wt);
+      else if (RT % 2 == 0)
+        lo_axis1_rows_pairs<(RT % 2 == 0 ? RT : 2)>(vs, lw, lane, reinterpret_cast<const double (&)[(RT % 2 == 0 ? RT : 2) + 1]>(wt));
       else
         lo_axis1_rows<RT, false>(vs, lw, lane, tx * MT, p.w, wt);
       __syncwarp();
@@ -863,9 +907,15 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->acc_empty);
-      if ((p.dbg & 2) && !WS) {
-        __syncwarp();
-        if (!FUSED && lane == 0) mbar_arrive(stage_empty);
+      if (p.dbg & 2) {  // timing experiments: no epilogue arithmetic / stores, the hand-shakes stay
+        if (WS) {
+          mbar_wait(&bars->lo_full[it & 1], (uint32_t)(it >> 1) & 1u);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->lo_empty[it & 1]);
+        } else {
+          __syncwarp();
+          if (!FUSED && lane == 0) mbar_arrive(stage_empty);
+        }
         continue;
       }
 
