@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "internal.cuh"
@@ -88,6 +89,11 @@ struct amt_executor {
   int32_t* given_slot[2];
   uint16_t* given16_slot[2];  // raw uint16 label masks (given_label_dtype == AMT_U16), widened on the device
   int64_t* given64_slot[2];   // raw int64 label masks (given_label_dtype == AMT_I64), narrowed on the device
+  uint16_t* given16_host[2];  // pinned: int64 masks narrowed to uint16 by host threads inside amt_executor_run_host (42 instead of 67 MB per FOV over PCIe)
+  bool host_narrow;           // int64 masks, max_label_value < 65535 and amt_tune("exec_host_narrow") != 0
+  int32_t* neg_host;          // per FOV of a run_host batch: a negative label was seen by the host narrowing
+  int64_t neg_host_cap;
+  bool slot_uploaded[2];      // the staging slot has an H2D in flight or behind it (its ev_in is valid)
   int32_t* flag_slot[2];      // per FOV of a chunk: [0, chunk) value > max_label_value seen, [chunk, 2 chunk) negative value seen
   int32_t* status_slot[2];
   int32_t* flags_dev;         // the same two flag arrays for the device-resident entry point
@@ -133,6 +139,11 @@ int g_exec_copy_only = 0;
 // amt_tune "exec_given_stream": 1 (default) = label + tables of the given masks run on a stream of their own next to
 // select / map / label / tables of the thresholded channel (they depend on the inputs only); 0 = one after the other
 int g_exec_given_stream = 1;
+// amt_tune "exec_host_narrow": 1 (default) = int64 label masks of a host-fed batch are narrowed to uint16 by host threads
+// into pinned staging before the H2D copy (values above 65534 saturate and are reported as out of range, as on the
+// device route); 0 = the int64 masks cross PCIe and are narrowed on the device.  "exec_host_threads": threads used.
+int g_exec_host_narrow = 1;
+int g_exec_host_threads = 8;
 int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st);  // gauss.cu
 
 static int dmalloc(amt_executor* ex, void** p, size_t bytes) {
@@ -425,15 +436,19 @@ __global__ void widen_u16_kernel(const uint16_t* __restrict__ in, int32_t* __res
 static int alloc_host_slots(amt_executor* ex) {
   if (ex->host_slots) return AMT_OK;
   const amt_fov_config& c = ex->cfg;
+  ex->host_narrow = g_exec_host_narrow && c.quantify_given_mask && c.given_label_dtype == AMT_I64 && c.max_label_value < 65535 &&
+                    ((int64_t)c.height * c.width) % 8 == 0;
   const int64_t HW = (int64_t)c.height * c.width;
   const size_t tab = (size_t)c.chunk_fovs * AMT_TABLE_COLS(c.n_channels) * c.max_labels * sizeof(double);
   for (int s = 0; s < 2; ++s) {
     AMT_TRY(dmalloc(ex, (void**)&ex->in_slot[s], (size_t)c.chunk_fovs * c.n_channels * HW * sizeof(uint16_t)));
     AMT_TRY(dmalloc(ex, (void**)&ex->given_slot[s], (size_t)c.chunk_fovs * HW * sizeof(int32_t)));
-    if (c.given_label_dtype == AMT_U16)
+    if (c.given_label_dtype == AMT_U16 || ex->host_narrow)
       AMT_TRY(dmalloc(ex, (void**)&ex->given16_slot[s], (size_t)c.chunk_fovs * HW * sizeof(uint16_t)));
-    if (c.given_label_dtype == AMT_I64)
+    if (c.given_label_dtype == AMT_I64 && !ex->host_narrow)
       AMT_TRY(dmalloc(ex, (void**)&ex->given64_slot[s], (size_t)c.chunk_fovs * HW * sizeof(int64_t)));
+    if (ex->host_narrow)
+      AMT_CUDA_TRY(cudaMallocHost((void**)&ex->given16_host[s], (size_t)c.chunk_fovs * HW * sizeof(uint16_t)));
     AMT_TRY(dmalloc(ex, (void**)&ex->flag_slot[s], (size_t)3 * c.chunk_fovs * sizeof(int32_t)));
     AMT_TRY(dmalloc(ex, (void**)&ex->retry_slot[s], (size_t)c.chunk_fovs * sizeof(int32_t)));
     AMT_TRY(dmalloc(ex, (void**)&ex->status_slot[s], (size_t)c.chunk_fovs * sizeof(int32_t)));
@@ -590,6 +605,9 @@ void amt_executor_destroy(amt_executor* ex) {
   cudaDeviceSynchronize();
   if (ex->tcg) amt_tcg_destroy(ex->tcg);
   if (ex->retry_host) cudaFreeHost(ex->retry_host);
+  for (int s2 = 0; s2 < 2; ++s2)
+    if (ex->given16_host[s2]) cudaFreeHost(ex->given16_host[s2]);
+  std::free(ex->neg_host);
   void* bufs[] = {ex->dx_ranks, ex->dx_rank_u32, ex->dx_rank_val, ex->dx_bin_count, ex->dx_bin_idx, ex->dx_bin_val, ex->retry_dev,
                   ex->flags_dev, ex->digits, ex->hw_lo, ex->hw_hi, ex->tmp_lo, ex->tmp_hi, ex->dog[0], ex->dog[1], ex->pre, ex->mm[0], ex->mm[1],
                   ex->buckets[0], ex->buckets[1],
@@ -733,6 +751,43 @@ int amt_executor_run_device(amt_executor* ex, const uint16_t* fovs, const int32_
   return AMT_OK;
 }
 
+// int64 label masks -> uint16 in pinned staging, on host threads: negative values become background and raise the FOV's
+// flag, values above 65534 saturate to 65535 (beyond max_label_value by construction: reported as out of range by the
+// labelling pass, like any value above max_label_value)
+static void narrow_i64_host(const int64_t* in, uint16_t* out, int64_t n_per_fov, int g, int32_t* negative) {
+  const int64_t total = n_per_fov * g;
+  int n_thr = amt::g_exec_host_threads;
+  const int hw_thr = (int)std::thread::hardware_concurrency();
+  if (hw_thr > 0 && n_thr > hw_thr) n_thr = hw_thr;
+  if (n_thr < 1 || total < (1 << 20)) n_thr = 1;
+  std::vector<int64_t> neg_or((size_t)n_thr * g, 0);
+  auto work = [&](int t) {
+    const int64_t lo = total * t / n_thr, hi = total * (t + 1) / n_thr;
+    int64_t i = lo;
+    while (i < hi) {
+      const int64_t fov = i / n_per_fov;
+      const int64_t end = (fov + 1) * n_per_fov < hi ? (fov + 1) * n_per_fov : hi;
+      int64_t acc = 0;
+      for (; i < end; ++i) {
+        const int64_t v = in[i];
+        acc |= v;
+        out[i] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+      }
+      neg_or[(size_t)t * g + fov] |= acc;
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < n_thr; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+  if (negative != nullptr)
+    for (int f = 0; f < g; ++f) {
+      int64_t acc = 0;
+      for (int t = 0; t < n_thr; ++t) acc |= neg_or[(size_t)t * g + f];
+      if (acc < 0) negative[f] = 1;
+    }
+}
+
 // H2D of one chunk of a host-fed batch into staging slot s (on s_in), label masks converted on the device
 static int upload_chunk(amt_executor* ex, int s, const uint16_t* fovs_host, const void* given_labels_host, int64_t f0, int g) {
   using namespace amt;
@@ -743,7 +798,15 @@ static int upload_chunk(amt_executor* ex, int s, const uint16_t* fovs_host, cons
   AMT_CUDA_TRY(cudaMemcpyAsync(ex->in_slot[s], fovs_host + f0 * C * HW, (size_t)g * C * HW * sizeof(uint16_t),
                                cudaMemcpyHostToDevice, ex->s_in));
   AMT_CUDA_TRY(cudaMemsetAsync(ex->flag_slot[s], 0, (size_t)3 * c.chunk_fovs * sizeof(int32_t), ex->s_in));
-  if (given && c.given_label_dtype == AMT_I64) {
+  if (given && ex->host_narrow) {
+    // the staging slot's previous H2D must have left the pinned buffer before host threads overwrite it
+    if (ex->slot_uploaded[s]) AMT_CUDA_TRY(cudaEventSynchronize(ex->ev_in[s]));
+    narrow_i64_host((const int64_t*)given_labels_host + f0 * HW, ex->given16_host[s], HW, g, ex->neg_host ? ex->neg_host + f0 : nullptr);
+    AMT_CUDA_TRY(cudaMemcpyAsync(ex->given16_slot[s], ex->given16_host[s], (size_t)g * HW * sizeof(uint16_t),
+                                 cudaMemcpyHostToDevice, ex->s_in));
+    widen_u16_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given16_slot[s], ex->given_slot[s], (int64_t)g * HW / 8);
+    AMT_LAUNCH_CHECK();
+  } else if (given && c.given_label_dtype == AMT_I64) {
     AMT_CUDA_TRY(cudaMemcpyAsync(ex->given64_slot[s], (const int64_t*)given_labels_host + f0 * HW,
                                  (size_t)g * HW * sizeof(int64_t), cudaMemcpyHostToDevice, ex->s_in));
     narrow_i64_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given64_slot[s], ex->given_slot[s], HW, g,
@@ -759,6 +822,7 @@ static int upload_chunk(amt_executor* ex, int s, const uint16_t* fovs_host, cons
                                  (size_t)g * HW * sizeof(int32_t), cudaMemcpyHostToDevice, ex->s_in));
   }
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_in[s], ex->s_in));
+  ex->slot_uploaded[s] = true;
   return AMT_OK;
 }
 
@@ -814,6 +878,16 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const voi
   AMT_CUDA_TRY(cudaSetDevice(c.device));
   if (ex->last.pending) AMT_TRY(amt_executor_sync(ex));
   AMT_TRY(alloc_host_slots(ex));
+  ex->slot_uploaded[0] = ex->slot_uploaded[1] = false;
+  if (ex->host_narrow && given) {
+    if (n_fov > ex->neg_host_cap) {
+      std::free(ex->neg_host);
+      ex->neg_host = (int32_t*)std::malloc((size_t)n_fov * sizeof(int32_t));
+      ex->neg_host_cap = ex->neg_host ? n_fov : 0;
+      if (!ex->neg_host) return AMT_ERR_CAPACITY;
+    }
+    std::memset(ex->neg_host, 0, (size_t)n_fov * sizeof(int32_t));
+  }
   const bool dx = ex->tcg != nullptr && g_exec_tc && ex->dx && !g_exec_copy_only;
   if (dx && n_fov > ex->retry_host_cap) {
     if (ex->retry_host) cudaFreeHost(ex->retry_host);
@@ -862,6 +936,9 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const voi
     ex->force_exact = false;
     AMT_TRY(rc);
   }
+  if (ex->host_narrow && given && status_host != nullptr && !g_exec_copy_only)
+    for (int64_t i = 0; i < n_fov; ++i)
+      if (ex->neg_host[i]) status_host[i] |= AMT_FOV_GIVEN_NEGATIVE;
   return AMT_OK;
 }
 

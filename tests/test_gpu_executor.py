@@ -276,6 +276,42 @@ def test_status_isolates_a_field_of_view_that_overflows():
             ex.check_status(dev_out)
 
 
+def test_int64_masks_narrowed_on_the_host_or_on_the_device_give_the_same_answer():
+    """amt_executor_run_host narrows int64 label masks to uint16 with host threads into pinned staging (42 instead of 67
+    MB per FOV over PCIe) when max_label_value < 65535; amt_tune('exec_host_narrow', 0) sends the int64 masks across and
+    narrows on the device.  Same tables, counts and status bits, including a value beyond uint16, one beyond int32 and
+    a negative one; large enough (2 x 1024 x 1024) for the host threads to split a chunk."""
+    from arcadia_microscopy_tools_b200 import _lib
+
+    lib = _lib.load()
+    C, shape, cells = 2, (1024, 1024), 300
+    fovs, givens = [], []
+    for i in range(3):
+        f, g, _ = make_fov(4100 + i, C, shape[0], shape[1], cells)
+        fovs.append(f), givens.append(g.astype(np.int64))
+    fovs, givens = np.stack(fovs), np.stack(givens)
+    givens[1, 500, 500] = 70000
+    givens[1, 600, 600] = 2**40
+    givens[2, 1023, 1023] = -7
+    cfg = FovPipelineConfig(n_channels=C, height=shape[0], width=shape[1], seg_channel=0, chunk_fovs=2, max_labels=512,
+                            max_label_value=int(givens[0].max()) + 5, given_label_dtype=np.int64)
+    outs = []
+    for narrow in (1, 0):
+        _lib.check(lib.amt_tune(b"exec_host_narrow", narrow))
+        try:
+            with FovBatchExecutor(cfg) as ex:
+                outs.append(ex.run_host(fovs, givens, on_error="status"))
+        finally:
+            _lib.check(lib.amt_tune(b"exec_host_narrow", 1))
+    a, b = outs
+    assert a["status"][0] == 0 and a["status"][1] & _lib.AMT_FOV_GIVEN_VALUE_RANGE and a["status"][2] & _lib.AMT_FOV_GIVEN_NEGATIVE
+    assert np.array_equal(a["status"], b["status"])
+    assert np.array_equal(a["counts_given"], b["counts_given"]) and a["counts_given"].min() > 0
+    for i in range(3):
+        k = int(a["counts_given"][i])
+        assert np.array_equal(a["tables_given"][i][:, :k], b["tables_given"][i][:, :k], equal_nan=True)
+
+
 def test_run_host_from_library_pinned_staging():
     """amt_host_alloc staging (plain and write-combined) feeds the host-fed entry point like any host buffer."""
     n_fov, C, shape = 2, 2, (128, 160)
