@@ -768,6 +768,25 @@ static void narrow_i64_host(const int64_t* in, uint16_t* out, int64_t n_per_fov,
       const int64_t fov = i / n_per_fov;
       const int64_t end = (fov + 1) * n_per_fov < hi ? (fov + 1) * n_per_fov : hi;
       int64_t acc = 0;
+      // eight labels at a time: when none of them has a bit above the 16th (the usual case) they are simply packed into
+      // two 64-bit words (4 loads, 3 shifts / ORs and one 8-byte store per four labels instead of compare / select / 2-byte
+      // store per label: the narrowing has to keep up with PCIe on a few host cores)
+      for (; i + 8 <= end && ((uintptr_t)(out + i) & 7) == 0; i += 8) {
+        const uint64_t a0 = (uint64_t)in[i], a1 = (uint64_t)in[i + 1], a2 = (uint64_t)in[i + 2], a3 = (uint64_t)in[i + 3];
+        const uint64_t a4 = (uint64_t)in[i + 4], a5 = (uint64_t)in[i + 5], a6 = (uint64_t)in[i + 6], a7 = (uint64_t)in[i + 7];
+        const uint64_t any = a0 | a1 | a2 | a3 | a4 | a5 | a6 | a7;
+        if ((any >> 16) == 0) {
+          uint64_t* o = reinterpret_cast<uint64_t*>(out + i);
+          o[0] = a0 | (a1 << 16) | (a2 << 32) | (a3 << 48);
+          o[1] = a4 | (a5 << 16) | (a6 << 32) | (a7 << 48);
+        } else {
+          for (int k = 0; k < 8; ++k) {
+            const int64_t v = in[i + k];
+            acc |= v;
+            out[i + k] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+          }
+        }
+      }
       for (; i < end; ++i) {
         const int64_t v = in[i];
         acc |= v;
