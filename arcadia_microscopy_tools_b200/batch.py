@@ -173,6 +173,16 @@ class FovBatchExecutor:
         return int(self._lib.amt_executor_retry_count(self._handle))
 
     @property
+    def last_h2d_bytes(self) -> int:
+        """Host -> device bytes of the last ``run_host`` batch (label masks cross PCIe as per-row runs of equal value)."""
+        return int(self._lib.amt_executor_last_h2d_bytes(self._handle))
+
+    @property
+    def last_plain_mask_chunks(self) -> int:
+        """Chunks of the last ``run_host`` batch whose label masks were too ragged for run-length staging."""
+        return int(self._lib.amt_executor_last_plain_mask_chunks(self._handle))
+
+    @property
     def device_bytes(self) -> int:
         return int(self._lib.amt_executor_device_bytes(self._handle))
 

@@ -91,7 +91,17 @@ struct amt_executor {
   int64_t* given64_slot[2];   // raw int64 label masks (given_label_dtype == AMT_I64), narrowed on the device
   uint16_t* given16_host[2];  // pinned: int64 masks narrowed to uint16 by host threads inside amt_executor_run_host (42 instead of 67 MB per FOV over PCIe)
   bool host_narrow;           // int64 masks, max_label_value < 65535 and amt_tune("exec_host_narrow") != 0
-  int32_t* neg_host;          // per FOV of a run_host batch: a negative label was seen by the host narrowing
+  int32_t* neg_host;          // per FOV of a run_host batch: a negative label was seen by the host narrowing / encoding
+  // run-length staging of host label masks (amt_tune "exec_host_rle", any of the three dtypes): host threads turn every
+  // row into (value, end column) runs in pinned staging; only the runs cross PCIe (~1 instead of 8.4 / 16.8 / 33.5 MB per
+  // 2048 x 2048 mask of ~2000 cells) and rle_decode_kernel writes the int32 label image
+  bool host_rle;
+  uint2* rle_host[2];         // pinned: run slots, W/4 per row (a thread packs the runs of its rows from its first row's slot)
+  uint2* rle_slot[2];         // device mirror (same sparse layout)
+  uint2* rle_rows_host[2];    // pinned: per row {first run slot, number of runs}
+  uint2* rle_rows_slot[2];
+  int64_t last_h2d_bytes;     // bytes the last run_host batch copied host -> device
+  int64_t rle_fallback_chunks;  // chunks of the last run_host batch whose runs did not fit (sent as plain masks)
   int64_t neg_host_cap;
   bool slot_uploaded[2];      // the staging slot has an H2D in flight or behind it (its ev_in is valid)
   int32_t* flag_slot[2];      // per FOV of a chunk: [0, chunk) value > max_label_value seen, [chunk, 2 chunk) negative value seen
@@ -144,6 +154,11 @@ int g_exec_given_stream = 1;
 // device route); 0 = the int64 masks cross PCIe and are narrowed on the device.  "exec_host_threads": threads used.
 int g_exec_host_narrow = 1;
 int g_exec_host_threads = 8;
+// amt_tune "exec_host_rle": 1 (default) = host label masks of a host-fed batch (int64, int32 or uint16) cross PCIe as
+// per-row runs of equal value, encoded by host threads into pinned staging inside the call and decoded on the device
+// (a label mask of ~2000 cells: ~1 MB instead of 8.4 MB as uint16).  A chunk whose runs do not fit the staging (fewer
+// than 4 pixels per run on average over a thread's rows) is sent the plain way.  0 = always the plain way.
+int g_exec_host_rle = 1;
 int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st);  // gauss.cu
 
 static int dmalloc(amt_executor* ex, void** p, size_t bytes) {
@@ -433,11 +448,56 @@ __global__ void widen_u16_kernel(const uint16_t* __restrict__ in, int32_t* __res
   }
 }
 
+// host_rle.cpp: host label masks -> per-row runs {value, end column} in pinned staging, on host threads
+bool rle_encode_host(const void* in, int dtype, int H, int W, int g, uint2* runs, uint2* rows, int32_t* negative, int n_thr,
+                     std::vector<int64_t>& first, std::vector<int64_t>& used);
+
+// run-length staging -> int32 label image: one CTA per row; a thread finds the run of its first pixel by bisection over
+// the row's run ends (in shared memory when they fit) and walks on from there, four pixels per 16-byte store
+constexpr int kRleSmemRuns = 1024;
+__global__ void __launch_bounds__(256) rle_decode_kernel(const uint2* __restrict__ runs, const uint2* __restrict__ rows,
+                                                         int32_t* __restrict__ out, int W) {
+  __shared__ uint2 s_runs[kRleSmemRuns];
+  const uint2 ri = rows[blockIdx.x];
+  const uint2* r = runs + ri.x;
+  const int n = (int)ri.y;
+  if (n <= kRleSmemRuns) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_runs[i] = __ldg(r + i);
+    __syncthreads();
+    r = s_runs;
+  }
+  int32_t* o = out + (int64_t)blockIdx.x * W;
+  const bool vec = (W & 3) == 0;
+  for (int x0 = threadIdx.x * 4; x0 < W; x0 += blockDim.x * 4) {
+    int lo = 0, hi = n - 1;  // first run whose end lies beyond x0 (the last run ends at W)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((int)r[mid].y > x0) hi = mid; else lo = mid + 1;
+    }
+    uint2 cur = r[lo];
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = x0 + k;
+      while (x < W && (int)cur.y <= x && lo + 1 < n) cur = r[++lo];
+      v[k] = (int)cur.x;
+    }
+    if (vec) {
+      *reinterpret_cast<int4*>(o + x0) = make_int4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (x0 + k < W) o[x0 + k] = v[k];
+    }
+  }
+}
+
 static int alloc_host_slots(amt_executor* ex) {
   if (ex->host_slots) return AMT_OK;
   const amt_fov_config& c = ex->cfg;
   ex->host_narrow = g_exec_host_narrow && c.quantify_given_mask && c.given_label_dtype == AMT_I64 && c.max_label_value < 65535 &&
                     ((int64_t)c.height * c.width) % 8 == 0;
+  ex->host_rle = g_exec_host_rle && c.quantify_given_mask && c.width >= 16;
   const int64_t HW = (int64_t)c.height * c.width;
   const size_t tab = (size_t)c.chunk_fovs * AMT_TABLE_COLS(c.n_channels) * c.max_labels * sizeof(double);
   for (int s = 0; s < 2; ++s) {
@@ -449,6 +509,14 @@ static int alloc_host_slots(amt_executor* ex) {
       AMT_TRY(dmalloc(ex, (void**)&ex->given64_slot[s], (size_t)c.chunk_fovs * HW * sizeof(int64_t)));
     if (ex->host_narrow)
       AMT_CUDA_TRY(cudaMallocHost((void**)&ex->given16_host[s], (size_t)c.chunk_fovs * HW * sizeof(uint16_t)));
+    if (ex->host_rle) {
+      const size_t slots = (size_t)c.chunk_fovs * c.height * (c.width / 4);
+      const size_t rows = (size_t)c.chunk_fovs * c.height;
+      AMT_CUDA_TRY(cudaMallocHost((void**)&ex->rle_host[s], slots * sizeof(uint2)));
+      AMT_CUDA_TRY(cudaMallocHost((void**)&ex->rle_rows_host[s], rows * sizeof(uint2)));
+      AMT_TRY(dmalloc(ex, (void**)&ex->rle_slot[s], slots * sizeof(uint2)));
+      AMT_TRY(dmalloc(ex, (void**)&ex->rle_rows_slot[s], rows * sizeof(uint2)));
+    }
     AMT_TRY(dmalloc(ex, (void**)&ex->flag_slot[s], (size_t)3 * c.chunk_fovs * sizeof(int32_t)));
     AMT_TRY(dmalloc(ex, (void**)&ex->retry_slot[s], (size_t)c.chunk_fovs * sizeof(int32_t)));
     AMT_TRY(dmalloc(ex, (void**)&ex->status_slot[s], (size_t)c.chunk_fovs * sizeof(int32_t)));
@@ -605,8 +673,13 @@ void amt_executor_destroy(amt_executor* ex) {
   cudaDeviceSynchronize();
   if (ex->tcg) amt_tcg_destroy(ex->tcg);
   if (ex->retry_host) cudaFreeHost(ex->retry_host);
-  for (int s2 = 0; s2 < 2; ++s2)
+  for (int s2 = 0; s2 < 2; ++s2) {
     if (ex->given16_host[s2]) cudaFreeHost(ex->given16_host[s2]);
+    if (ex->rle_host[s2]) cudaFreeHost(ex->rle_host[s2]);
+    if (ex->rle_rows_host[s2]) cudaFreeHost(ex->rle_rows_host[s2]);
+    if (ex->rle_slot[s2]) cudaFree(ex->rle_slot[s2]);
+    if (ex->rle_rows_slot[s2]) cudaFree(ex->rle_rows_slot[s2]);
+  }
   std::free(ex->neg_host);
   void* bufs[] = {ex->dx_ranks, ex->dx_rank_u32, ex->dx_rank_val, ex->dx_bin_count, ex->dx_bin_idx, ex->dx_bin_val, ex->retry_dev,
                   ex->flags_dev, ex->digits, ex->hw_lo, ex->hw_hi, ex->tmp_lo, ex->tmp_hi, ex->dog[0], ex->dog[1], ex->pre, ex->mm[0], ex->mm[1],
@@ -817,26 +890,62 @@ static int upload_chunk(amt_executor* ex, int s, const uint16_t* fovs_host, cons
   AMT_CUDA_TRY(cudaMemcpyAsync(ex->in_slot[s], fovs_host + f0 * C * HW, (size_t)g * C * HW * sizeof(uint16_t),
                                cudaMemcpyHostToDevice, ex->s_in));
   AMT_CUDA_TRY(cudaMemsetAsync(ex->flag_slot[s], 0, (size_t)3 * c.chunk_fovs * sizeof(int32_t), ex->s_in));
-  if (given && ex->host_narrow) {
+  ex->last_h2d_bytes += (int64_t)g * C * HW * sizeof(uint16_t);
+  bool sent = false;
+  if (given && ex->host_rle) {
     // the staging slot's previous H2D must have left the pinned buffer before host threads overwrite it
     if (ex->slot_uploaded[s]) AMT_CUDA_TRY(cudaEventSynchronize(ex->ev_in[s]));
+    std::vector<int64_t> first, used;
+    int32_t* neg = ex->neg_host ? ex->neg_host + f0 : nullptr;
+    const int hw_thr = (int)std::thread::hardware_concurrency();
+    const int n_thr = hw_thr > 0 && g_exec_host_threads > hw_thr ? hw_thr : g_exec_host_threads;
+    const int dt = c.given_label_dtype == AMT_I64 || c.given_label_dtype == AMT_U16 ? c.given_label_dtype : AMT_I32;
+    const size_t esz = dt == AMT_I64 ? 8 : (dt == AMT_U16 ? 2 : 4);
+    const bool ok = rle_encode_host((const char*)given_labels_host + (size_t)f0 * HW * esz, dt, c.height, c.width, g, ex->rle_host[s],
+                                    ex->rle_rows_host[s], neg, n_thr, first, used);
+    if (ok) {
+      for (size_t t = 0; t < first.size(); ++t) {
+        if (used[t] == 0) continue;
+        AMT_CUDA_TRY(cudaMemcpyAsync(ex->rle_slot[s] + first[t], ex->rle_host[s] + first[t], (size_t)used[t] * sizeof(uint2),
+                                     cudaMemcpyHostToDevice, ex->s_in));
+        ex->last_h2d_bytes += used[t] * (int64_t)sizeof(uint2);
+      }
+      const size_t rows = (size_t)g * c.height;
+      AMT_CUDA_TRY(cudaMemcpyAsync(ex->rle_rows_slot[s], ex->rle_rows_host[s], rows * sizeof(uint2), cudaMemcpyHostToDevice, ex->s_in));
+      ex->last_h2d_bytes += (int64_t)(rows * sizeof(uint2));
+      rle_decode_kernel<<<(unsigned)rows, 256, 0, ex->s_in>>>(ex->rle_slot[s], ex->rle_rows_slot[s], ex->given_slot[s], c.width);
+      AMT_LAUNCH_CHECK();
+      sent = true;
+    } else {
+      ex->rle_fallback_chunks += 1;
+      if (neg) std::memset(neg, 0, (size_t)g * sizeof(int32_t));  // the plain route below reports negatives itself
+    }
+  }
+  if (sent) {
+  } else if (given && ex->host_narrow) {
+    // the staging slot's previous H2D must have left the pinned buffer before host threads overwrite it
+    if (ex->slot_uploaded[s]) AMT_CUDA_TRY(cudaEventSynchronize(ex->ev_in[s]));
+    ex->last_h2d_bytes += (int64_t)g * HW * sizeof(uint16_t);
     narrow_i64_host((const int64_t*)given_labels_host + f0 * HW, ex->given16_host[s], HW, g, ex->neg_host ? ex->neg_host + f0 : nullptr);
     AMT_CUDA_TRY(cudaMemcpyAsync(ex->given16_slot[s], ex->given16_host[s], (size_t)g * HW * sizeof(uint16_t),
                                  cudaMemcpyHostToDevice, ex->s_in));
     widen_u16_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given16_slot[s], ex->given_slot[s], (int64_t)g * HW / 8);
     AMT_LAUNCH_CHECK();
   } else if (given && c.given_label_dtype == AMT_I64) {
+    ex->last_h2d_bytes += (int64_t)g * HW * sizeof(int64_t);
     AMT_CUDA_TRY(cudaMemcpyAsync(ex->given64_slot[s], (const int64_t*)given_labels_host + f0 * HW,
                                  (size_t)g * HW * sizeof(int64_t), cudaMemcpyHostToDevice, ex->s_in));
     narrow_i64_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given64_slot[s], ex->given_slot[s], HW, g,
                                                          ex->flag_slot[s] + c.chunk_fovs);
     AMT_LAUNCH_CHECK();
   } else if (given && c.given_label_dtype == AMT_U16) {
+    ex->last_h2d_bytes += (int64_t)g * HW * sizeof(uint16_t);
     AMT_CUDA_TRY(cudaMemcpyAsync(ex->given16_slot[s], (const uint16_t*)given_labels_host + f0 * HW,
                                  (size_t)g * HW * sizeof(uint16_t), cudaMemcpyHostToDevice, ex->s_in));
     widen_u16_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given16_slot[s], ex->given_slot[s], (int64_t)g * HW / 8);
     AMT_LAUNCH_CHECK();
   } else if (given) {
+    ex->last_h2d_bytes += (int64_t)g * HW * sizeof(int32_t);
     AMT_CUDA_TRY(cudaMemcpyAsync(ex->given_slot[s], (const int32_t*)given_labels_host + f0 * HW,
                                  (size_t)g * HW * sizeof(int32_t), cudaMemcpyHostToDevice, ex->s_in));
   }
@@ -898,7 +1007,8 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const voi
   if (ex->last.pending) AMT_TRY(amt_executor_sync(ex));
   AMT_TRY(alloc_host_slots(ex));
   ex->slot_uploaded[0] = ex->slot_uploaded[1] = false;
-  if (ex->host_narrow && given) {
+  ex->last_h2d_bytes = 0, ex->rle_fallback_chunks = 0;
+  if ((ex->host_narrow || ex->host_rle) && given) {
     if (n_fov > ex->neg_host_cap) {
       std::free(ex->neg_host);
       ex->neg_host = (int32_t*)std::malloc((size_t)n_fov * sizeof(int32_t));
@@ -955,7 +1065,7 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const voi
     ex->force_exact = false;
     AMT_TRY(rc);
   }
-  if (ex->host_narrow && given && status_host != nullptr && !g_exec_copy_only)
+  if ((ex->host_narrow || ex->host_rle) && given && status_host != nullptr && !g_exec_copy_only)
     for (int64_t i = 0; i < n_fov; ++i)
       if (ex->neg_host[i]) status_host[i] |= AMT_FOV_GIVEN_NEGATIVE;
   return AMT_OK;
@@ -970,6 +1080,24 @@ int amt_executor_sync(amt_executor* ex) {
 }
 
 int64_t amt_executor_retry_count(const amt_executor* ex) { return ex ? ex->retries : -1; }
+int amt_rle_encode_host(const void* labels_host, int dtype, int32_t n_fov, int32_t height, int32_t width, int32_t n_threads,
+                        uint32_t* runs, uint32_t* rows, int32_t* negative, int64_t* n_runs) {
+  using namespace amt;
+  if (!labels_host || !runs || !rows || n_fov < 1 || height < 1 || width < 16 || n_threads < 1) return AMT_ERR_INVALID;
+  std::vector<int64_t> first, used;
+  if (dtype != AMT_I64 && dtype != AMT_U16 && dtype != AMT_I32) return AMT_ERR_INVALID;
+  if (negative) std::memset(negative, 0, (size_t)n_fov * sizeof(int32_t));
+  if (!rle_encode_host(labels_host, dtype, height, width, n_fov, (uint2*)runs, (uint2*)rows, negative, n_threads, first, used))
+    return AMT_ERR_CAPACITY;
+  if (n_runs) {
+    *n_runs = 0;
+    for (int64_t u : used) *n_runs += u;
+  }
+  return AMT_OK;
+}
+
+int64_t amt_executor_last_h2d_bytes(const amt_executor* ex) { return ex ? ex->last_h2d_bytes : -1; }
+int64_t amt_executor_last_plain_mask_chunks(const amt_executor* ex) { return ex ? ex->rle_fallback_chunks : -1; }
 int amt_executor_decision_exact(const amt_executor* ex) { return ex && ex->dx ? 1 : 0; }
 
 float amt_executor_last_ms(amt_executor* ex) {

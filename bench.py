@@ -471,8 +471,8 @@ def run_b200(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib = _lib.load()
-    # host threads that narrow the int64 label masks inside the host-fed call: the ranks of one box share its cores
-    host_threads = max(1, min(8, len(os.sched_getaffinity(0)) // max(world, 1)))
+    # host threads that encode the label masks inside the host-fed call: the ranks of one box share its cores
+    host_threads = max(1, min(16, len(os.sched_getaffinity(0)) // max(world, 1)))
     _lib.check(lib.amt_tune(b"exec_host_threads", host_threads), "amt_tune")
 
     def barrier():
@@ -550,54 +550,71 @@ def run_b200(args) -> None:
             barrier()
             return max_ranks(dt)
 
-        # headline: int64 masks, narrowed to uint16 by host threads into pinned staging INSIDE the timed call
+        # headline: int64 masks, turned into per-row runs by host threads into pinned staging INSIDE the timed call
         s64 = timed_host(ex, h_given64.numpy())
+        h2d_head, plain_chunks = ex.last_h2d_bytes, ex.last_plain_mask_chunks
         assert np.array_equal(h_out["counts_thr"], counts[0][:n_e2e]) and np.array_equal(h_out["counts_given"], counts[1][:n_e2e])
         _lib.check(lib.amt_tune(b"exec_copy_only", 1), "amt_tune")
         try:
             c64 = timed_host(ex, h_given64.numpy())
         finally:
             _lib.check(lib.amt_tune(b"exec_copy_only", 0), "amt_tune")
-        host_narrow = cfg.max_label_value < 65535
-        # the same with the int64 masks crossing PCIe (narrowed on the device)
-        _lib.check(lib.amt_tune(b"exec_host_narrow", 0), "amt_tune")
+        # the same with plain masks over PCIe: int64 narrowed to uint16 by host threads, and int64 as they are
+        _lib.check(lib.amt_tune(b"exec_host_rle", 0), "amt_tune")
         try:
-            with FovBatchExecutor(cfg, device=local) as ex_dev:
-                s64d = timed_host(ex_dev, h_given64.numpy())
+            host_narrow = cfg.max_label_value < 65535
+            with FovBatchExecutor(cfg, device=local) as ex_n:
+                s64n = timed_host(ex_n, h_given64.numpy())
+                h2d_n = ex_n.last_h2d_bytes
                 assert np.array_equal(h_out["counts_given"], counts[1][:n_e2e])
-                _lib.check(lib.amt_tune(b"exec_copy_only", 1), "amt_tune")
-                try:
-                    c64d = timed_host(ex_dev, h_given64.numpy())
-                finally:
-                    _lib.check(lib.amt_tune(b"exec_copy_only", 0), "amt_tune")
+            _lib.check(lib.amt_tune(b"exec_host_narrow", 0), "amt_tune")
+            try:
+                with FovBatchExecutor(cfg, device=local) as ex_dev:
+                    s64d = timed_host(ex_dev, h_given64.numpy())
+                    h2d64 = ex_dev.last_h2d_bytes
+                    assert np.array_equal(h_out["counts_given"], counts[1][:n_e2e])
+                    _lib.check(lib.amt_tune(b"exec_copy_only", 1), "amt_tune")
+                    try:
+                        c64d = timed_host(ex_dev, h_given64.numpy())
+                    finally:
+                        _lib.check(lib.amt_tune(b"exec_copy_only", 0), "amt_tune")
+            finally:
+                _lib.check(lib.amt_tune(b"exec_host_narrow", 1), "amt_tune")
         finally:
-            _lib.check(lib.amt_tune(b"exec_host_narrow", 1), "amt_tune")
+            _lib.check(lib.amt_tune(b"exec_host_rle", 1), "amt_tune")
         with FovBatchExecutor(dataclasses.replace(cfg, given_label_dtype=np.uint16), device=local) as ex16:
             s16 = timed_host(ex16, h_given16.numpy().view(np.uint16))
+            h2d16 = ex16.last_h2d_bytes
             assert np.array_equal(h_out["counts_given"], counts[1][:n_e2e])
         d2h = sum(int(h_out[k].nbytes) for k in h_out)
-        h2d64 = int(np_fovs.nbytes + h_given64.numpy().nbytes)
-        h2d16 = int(np_fovs.nbytes + h_given16.numpy().nbytes)
-        h2d_head = h2d16 if host_narrow else h2d64
+        host_read = int(np_fovs.nbytes + h_given64.numpy().nbytes)
         samples = world * args.steps * n_e2e * C * H * W
         e2e = {"value": samples / s64 / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d_head, "d2h_bytes_per_step": d2h,
                "fov_per_s": world * args.steps * n_e2e / s64, "fovs_per_step": n_e2e,
-               "label_mask_dtype": "int64 in host memory (the reference's dtype at this boundary: model.py:215, masks.py:138)" +
-                                   (f", narrowed to uint16 by {host_threads} host threads into pinned staging inside the timed call "
-                                    "(max_label_value < 65535; amt_tune exec_host_narrow)" if host_narrow else ", narrowed on the device"),
-               "host_bytes_read_per_step": h2d64,
+               "label_mask_dtype": "int64 in host memory (the reference's dtype at this boundary: model.py:215, masks.py:138), "
+                                   f"turned into per-row runs of equal value by {host_threads} host threads into pinned staging "
+                                   "inside the timed call and decoded on the device (amt_tune exec_host_rle; h2d_bytes_per_step "
+                                   "is what crossed PCIe, counted by the executor)",
+               "mask_chunks_sent_plain": plain_chunks,
+               "host_bytes_read_per_step": host_read,
                "h2d_gbs": world * args.steps * h2d_head / s64 / 1e9,
                "copy_only": {"seconds_per_step": c64 / args.steps, "h2d_ceiling_gbs": world * args.steps * h2d_head / c64 / 1e9,
-                             "note": "amt_tune('exec_copy_only'): the same call, buffers, host narrowing, staging slots, streams and "
-                                     "events with no kernel launched; all ranks concurrently"},
+                             "note": "amt_tune('exec_copy_only'): the same call, buffers, host encoding, staging slots, streams and "
+                                     "events with no kernel launched (but the mask decode); all ranks concurrently"},
                "frac_of_copy_ceiling": c64 / s64,
+               "int64_narrowed_to_uint16": {"value": samples / s64n / 1e6, "fov_per_s": world * args.steps * n_e2e / s64n,
+                                            "h2d_bytes_per_step": h2d_n, "h2d_gbs": world * args.steps * h2d_n / s64n / 1e9,
+                                            "note": "amt_tune('exec_host_rle', 0): the int64 masks " +
+                                                    ("are narrowed to uint16 by the host threads (42 MB per FOV over PCIe)"
+                                                     if host_narrow else "cross PCIe as they are")},
                "int64_over_pcie": {"value": samples / s64d / 1e6, "fov_per_s": world * args.steps * n_e2e / s64d,
                                    "h2d_bytes_per_step": h2d64, "h2d_gbs": world * args.steps * h2d64 / s64d / 1e9,
                                    "frac_of_copy_ceiling": c64d / s64d,
-                                   "note": "amt_tune('exec_host_narrow', 0): the int64 masks cross PCIe (67 MB per FOV) and are narrowed on the device"},
+                                   "note": "amt_tune('exec_host_rle', 0) and ('exec_host_narrow', 0): the int64 masks cross PCIe "
+                                           "(67 MB per FOV) and are narrowed on the device"},
                "uint16_masks": {"value": samples / s16 / 1e6, "fov_per_s": world * args.steps * n_e2e / s16,
                                 "h2d_bytes_per_step": h2d16,
-                                "note": "Cellpose's own mask dtype (below 65536 cells) handed over as is: 42 MB per FOV over PCIe, no host pass"},
+                                "note": "Cellpose's own mask dtype (below 65536 cells), run-length staged the same way"},
                "timing": "wall clock around the synchronous C-ABI call, max over ranks",
                "rank0_cpu_affinity": f"{len(cpus)} CPUs local to the GPU (NVML)" if cpus else "unchanged"}
         del h_fovs, h_given64, h_given16

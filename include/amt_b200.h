@@ -449,6 +449,21 @@ int amt_executor_decision_exact(const amt_executor* ex);
 /* Fields of view recomputed with the float64 kernels since creation because a candidate list of the decision-exact
  * mode overflowed (massive ties, e.g. constant images).  Their results are exact like everybody else's. */
 int64_t amt_executor_retry_count(const amt_executor* ex);
+/* Host -> device bytes the last amt_executor_run_host batch copied (images + label masks as they crossed PCIe).  Host
+ * label masks (any of the three dtypes) cross as per-row runs of equal value, encoded by host threads into pinned
+ * staging inside the call and decoded on the device (amt_tune "exec_host_rle", default on; "exec_host_threads"): a
+ * segmentation mask is long runs by nature, ~1 MB instead of 8.4 MB (uint16) / 33.5 MB (int64) per 2048 x 2048 mask of
+ * ~2000 cells.  A chunk whose runs do not fit the staging (under 4 pixels per run on average) is sent as the plain
+ * mask instead; amt_executor_last_plain_mask_chunks counts those chunks of the last batch. */
+int64_t amt_executor_last_h2d_bytes(const amt_executor* ex);
+/* The host half of that route on its own (no GPU involved; tests and host-side timing): n_fov label masks of
+ * height x width (dtype AMT_I64 / AMT_I32 / AMT_U16) -> runs[2 k] = value, runs[2 k + 1] = end column (exclusive) of run k;
+ * rows[2 r] = first run slot of row r, rows[2 r + 1] = its number of runs.  `runs` holds n_fov * height * (width / 4)
+ * slots; thread t packs the runs of its rows from slot first_row(t) * (width / 4) on.  negative[f] = 1 when FOV f holds a
+ * negative label (stored as background); values beyond int32 saturate.  AMT_ERR_CAPACITY when the runs do not fit. */
+int amt_rle_encode_host(const void* labels_host, int dtype, int32_t n_fov, int32_t height, int32_t width, int32_t n_threads,
+                        uint32_t* runs, uint32_t* rows, int32_t* negative, int64_t* n_runs);
+int64_t amt_executor_last_plain_mask_chunks(const amt_executor* ex);
 
 /* Per-stage device time (CUDA events after every stage of both executor streams; adds a few microseconds per
  * chunk, off by default).  amt_executor_set_profiling(ex, 1) zeroes the counters; every amt_executor_run_device call

@@ -4,6 +4,8 @@ properties at the full 2048x2048 size."""
 
 from __future__ import annotations
 
+import dataclasses
+
 import hashlib
 
 import numpy as np
@@ -276,11 +278,13 @@ def test_status_isolates_a_field_of_view_that_overflows():
             ex.check_status(dev_out)
 
 
-def test_int64_masks_narrowed_on_the_host_or_on_the_device_give_the_same_answer():
-    """amt_executor_run_host narrows int64 label masks to uint16 with host threads into pinned staging (42 instead of 67
-    MB per FOV over PCIe) when max_label_value < 65535; amt_tune('exec_host_narrow', 0) sends the int64 masks across and
-    narrows on the device.  Same tables, counts and status bits, including a value beyond uint16, one beyond int32 and
-    a negative one; large enough (2 x 1024 x 1024) for the host threads to split a chunk."""
+def test_host_label_masks_give_the_same_answer_on_every_route():
+    """amt_executor_run_host sends host label masks across PCIe as per-row runs of equal value (encoded by host threads
+    into pinned staging, decoded on the device; amt_tune('exec_host_rle')); with that off, int64 masks are narrowed to
+    uint16 by host threads when max_label_value < 65535 (amt_tune('exec_host_narrow')) or cross as they are and are
+    narrowed on the device.  Same tables, counts and status bits on all three routes and for all three mask dtypes,
+    including a value beyond uint16, one beyond int32 and a negative one; large enough (2 x 1024 x 1024) for the host
+    threads to split a chunk."""
     from arcadia_microscopy_tools_b200 import _lib
 
     lib = _lib.load()
@@ -290,25 +294,81 @@ def test_int64_masks_narrowed_on_the_host_or_on_the_device_give_the_same_answer(
         f, g, _ = make_fov(4100 + i, C, shape[0], shape[1], cells)
         fovs.append(f), givens.append(g.astype(np.int64))
     fovs, givens = np.stack(fovs), np.stack(givens)
+    clean = givens.copy()
     givens[1, 500, 500] = 70000
     givens[1, 600, 600] = 2**40
     givens[2, 1023, 1023] = -7
     cfg = FovPipelineConfig(n_channels=C, height=shape[0], width=shape[1], seg_channel=0, chunk_fovs=2, max_labels=512,
                             max_label_value=int(givens[0].max()) + 5, given_label_dtype=np.int64)
-    outs = []
-    for narrow in (1, 0):
+
+    def run(config, masks, rle, narrow):
+        _lib.check(lib.amt_tune(b"exec_host_rle", rle))
         _lib.check(lib.amt_tune(b"exec_host_narrow", narrow))
+        try:
+            with FovBatchExecutor(config) as ex:
+                out = ex.run_host(fovs, masks, on_error="status")
+                return out, ex.last_h2d_bytes, ex.last_plain_mask_chunks
+        finally:
+            _lib.check(lib.amt_tune(b"exec_host_rle", 1))
+            _lib.check(lib.amt_tune(b"exec_host_narrow", 1))
+
+    def same(a, b):
+        assert np.array_equal(a["status"], b["status"])
+        assert np.array_equal(a["counts_given"], b["counts_given"]) and a["counts_given"].min() > 0
+        assert np.array_equal(a["counts_thr"], b["counts_thr"])
+        for i in range(3):
+            k = int(a["counts_given"][i])
+            assert np.array_equal(a["tables_given"][i][:, :k], b["tables_given"][i][:, :k], equal_nan=True)
+
+    (a, bytes_rle, plain), (b, bytes_narrow, _), (c, bytes_i64, _) = run(cfg, givens, 1, 1), run(cfg, givens, 0, 1), run(cfg, givens, 0, 0)
+    assert a["status"][0] == 0 and a["status"][1] & _lib.AMT_FOV_GIVEN_VALUE_RANGE and a["status"][2] & _lib.AMT_FOV_GIVEN_NEGATIVE
+    same(a, b), same(a, c)
+    px = 3 * shape[0] * shape[1]
+    assert plain == 0 and bytes_narrow == px * (2 * C + 2) and bytes_i64 == px * (2 * C + 8)
+    assert px * 2 * C < bytes_rle < px * 2 * C + px // 4  # the masks cross as runs: a small fraction of a byte per pixel
+    # the other two host dtypes, run-length staged and plain
+    for dtype in (np.int32, np.uint16):
+        cfg_d = dataclasses.replace(cfg, given_label_dtype=dtype)
+        d, bytes_d, plain_d = run(cfg_d, clean.astype(dtype), 1, 1)
+        e, bytes_e, _ = run(cfg_d, clean.astype(dtype), 0, 1)
+        same(d, e)
+        assert plain_d == 0 and px * 2 * C < bytes_d <= bytes_rle and bytes_e == px * (2 * C + np.dtype(dtype).itemsize) and not d["status"].any()
+        k = int(a["counts_given"][0])
+        assert np.array_equal(d["tables_given"][0][:, :k], a["tables_given"][0][:, :k], equal_nan=True)
+
+
+def test_ragged_label_masks_fall_back_to_the_plain_route():
+    """A label mask with fewer than four pixels per run (here: a different label in every pixel of a block) does not fit
+    the run-length staging; its chunk crosses PCIe as the plain mask and gives the same answer, next to chunks that fit."""
+    from arcadia_microscopy_tools_b200 import _lib
+
+    lib = _lib.load()
+    C, shape = 2, (1024, 1024)
+    fovs, givens = [], []
+    for i in range(4):
+        f, g, _ = make_fov(4200 + i, C, shape[0], shape[1], 200)
+        fovs.append(f), givens.append(g.astype(np.int64))
+    fovs, givens = np.stack(fovs), np.stack(givens)
+    rng = np.random.default_rng(3)
+    givens[2] = rng.integers(1, 3, shape) * 400 + np.arange(shape[1]) % 2  # every pixel differs from its neighbour
+    givens[2, :4] = 0
+    givens[2, 7, 9] = -1
+    cfg = FovPipelineConfig(n_channels=C, height=shape[0], width=shape[1], seg_channel=0, chunk_fovs=1, max_labels=2048,
+                            max_label_value=1000, given_label_dtype=np.int64)
+    outs = []
+    for rle in (1, 0):
+        _lib.check(lib.amt_tune(b"exec_host_rle", rle))
         try:
             with FovBatchExecutor(cfg) as ex:
                 outs.append(ex.run_host(fovs, givens, on_error="status"))
+                assert ex.last_plain_mask_chunks == (1 if rle else 0)
         finally:
-            _lib.check(lib.amt_tune(b"exec_host_narrow", 1))
+            _lib.check(lib.amt_tune(b"exec_host_rle", 1))
     a, b = outs
-    assert a["status"][0] == 0 and a["status"][1] & _lib.AMT_FOV_GIVEN_VALUE_RANGE and a["status"][2] & _lib.AMT_FOV_GIVEN_NEGATIVE
-    assert np.array_equal(a["status"], b["status"])
-    assert np.array_equal(a["counts_given"], b["counts_given"]) and a["counts_given"].min() > 0
-    for i in range(3):
-        k = int(a["counts_given"][i])
+    assert np.array_equal(a["status"], b["status"]) and a["status"][2] & _lib.AMT_FOV_GIVEN_NEGATIVE and not a["status"][3]
+    assert np.array_equal(a["counts_given"], b["counts_given"])
+    for i in range(4):
+        k = min(int(a["counts_given"][i]), cfg.max_labels)
         assert np.array_equal(a["tables_given"][i][:, :k], b["tables_given"][i][:, :k], equal_nan=True)
 
 
