@@ -185,6 +185,7 @@ SIGNATURES: dict[str, tuple] = {
     "amt_executor_last_h2d_bytes": (_i64, [_p]),
     "amt_rle_encode_host": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "amt_executor_last_plain_mask_chunks": (_i64, [_p]),
+    "amt_executor_last_rle_masks": (_i64, [_p]),
     "amt_tcg_error_bound": (_d, [_p]),
     "amt_executor_set_profiling": (_i, [_p, _i]),
     "amt_executor_stage_ms": (_i, [_p, _p, C.POINTER(_i64)]),

@@ -178,6 +178,12 @@ class FovBatchExecutor:
         return int(self._lib.amt_executor_last_h2d_bytes(self._handle))
 
     @property
+    def last_rle_masks(self) -> int:
+        """Label masks of the last ``run_host`` batch that crossed PCIe as runs (the others crossed plain: the executor
+        balances host encoding time against PCIe time per chunk)."""
+        return int(self._lib.amt_executor_last_rle_masks(self._handle))
+
+    @property
     def last_plain_mask_chunks(self) -> int:
         """Chunks of the last ``run_host`` batch whose label masks were too ragged for run-length staging."""
         return int(self._lib.amt_executor_last_plain_mask_chunks(self._handle))

@@ -408,7 +408,7 @@ extern int g_exec_buckets;    // executor.cu
 extern int g_exec_tc;         // executor.cu
 extern int g_exec_fused_lo;   // executor.cu
 extern int g_exec_given_stream;
-extern int g_exec_host_narrow, g_exec_host_threads, g_exec_host_rle;
+extern int g_exec_host_narrow, g_exec_host_threads, g_exec_host_rle, g_exec_rle_share;
 extern int g_exec_copy_only;  // executor.cu
 static int g_dog_only_exact = 0;  // amt_tune: the stand-alone axis0 / axis1 entry points cover the exact planes only
 namespace tc { extern int g_tcg_debug; }  // tcgauss.cu
@@ -600,6 +600,9 @@ int amt_tune(const char* key, int value) {
     g_exec_host_narrow = value != 0;
   } else if (is("exec_host_rle")) {
     g_exec_host_rle = value != 0;
+  } else if (is("exec_rle_share")) {
+    if (value < -1 || value > 100) return AMT_ERR_INVALID;
+    g_exec_rle_share = value;
   } else if (is("exec_host_threads")) {
     if (value < 1 || value > 256) return AMT_ERR_INVALID;
     g_exec_host_threads = value;

@@ -11,6 +11,7 @@
 // launched over all planes of a chunk (grid.y / grid.z = plane).  The host-fed entry point
 // double-buffers H2D copies, compute and D2H copies on three streams.
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -101,6 +102,13 @@ struct amt_executor {
   uint2* rle_rows_host[2];    // pinned: per row {first run slot, number of runs}
   uint2* rle_rows_slot[2];
   int64_t last_h2d_bytes;     // bytes the last run_host batch copied host -> device
+  // how many masks of a chunk take the run-length route is balanced per chunk between the host threads (seconds per
+  // encoded mask, rle_a) and PCIe (bytes per second of the image copy, rle_B, timed with ev_img0/1): the others cross
+  // as plain masks right behind the images while the host threads encode
+  cudaEvent_t ev_img0[2], ev_img1[2];
+  int64_t slot_img_bytes[2];
+  double rle_a, rle_B, rle_c;   // running means; 0 = not measured yet.  rle_c: bytes of runs + row table per encoded mask
+  int64_t last_rle_masks, last_plain_masks;
   int64_t rle_fallback_chunks;  // chunks of the last run_host batch whose runs did not fit (sent as plain masks)
   int64_t neg_host_cap;
   bool slot_uploaded[2];      // the staging slot has an H2D in flight or behind it (its ev_in is valid)
@@ -159,6 +167,9 @@ int g_exec_host_threads = 8;
 // (a label mask of ~2000 cells: ~1 MB instead of 8.4 MB as uint16).  A chunk whose runs do not fit the staging (fewer
 // than 4 pixels per run on average over a thread's rows) is sent the plain way.  0 = always the plain way.
 int g_exec_host_rle = 1;
+// amt_tune "exec_rle_share": -1 (default) = the number of masks of a chunk that take the run-length route is balanced
+// against PCIe from the measured encode and copy rates; 0..100 = that fixed percentage of a chunk's masks
+int g_exec_rle_share = -1;
 int minmax_init(uint64_t* mm, int64_t n_img, cudaStream_t st);  // gauss.cu
 
 static int dmalloc(amt_executor* ex, void** p, size_t bytes) {
@@ -495,9 +506,9 @@ __global__ void __launch_bounds__(256) rle_decode_kernel(const uint2* __restrict
 static int alloc_host_slots(amt_executor* ex) {
   if (ex->host_slots) return AMT_OK;
   const amt_fov_config& c = ex->cfg;
-  ex->host_narrow = g_exec_host_narrow && c.quantify_given_mask && c.given_label_dtype == AMT_I64 && c.max_label_value < 65535 &&
-                    ((int64_t)c.height * c.width) % 8 == 0;
   ex->host_rle = g_exec_host_rle && c.quantify_given_mask && c.width >= 16;
+  ex->host_narrow = !ex->host_rle && g_exec_host_narrow && c.quantify_given_mask && c.given_label_dtype == AMT_I64 &&
+                    c.max_label_value < 65535 && ((int64_t)c.height * c.width) % 8 == 0;
   const int64_t HW = (int64_t)c.height * c.width;
   const size_t tab = (size_t)c.chunk_fovs * AMT_TABLE_COLS(c.n_channels) * c.max_labels * sizeof(double);
   for (int s = 0; s < 2; ++s) {
@@ -516,6 +527,8 @@ static int alloc_host_slots(amt_executor* ex) {
       AMT_CUDA_TRY(cudaMallocHost((void**)&ex->rle_rows_host[s], rows * sizeof(uint2)));
       AMT_TRY(dmalloc(ex, (void**)&ex->rle_slot[s], slots * sizeof(uint2)));
       AMT_TRY(dmalloc(ex, (void**)&ex->rle_rows_slot[s], rows * sizeof(uint2)));
+      AMT_CUDA_TRY(cudaEventCreate(&ex->ev_img0[s]));
+      AMT_CUDA_TRY(cudaEventCreate(&ex->ev_img1[s]));
     }
     AMT_TRY(dmalloc(ex, (void**)&ex->flag_slot[s], (size_t)3 * c.chunk_fovs * sizeof(int32_t)));
     AMT_TRY(dmalloc(ex, (void**)&ex->retry_slot[s], (size_t)c.chunk_fovs * sizeof(int32_t)));
@@ -679,6 +692,8 @@ void amt_executor_destroy(amt_executor* ex) {
     if (ex->rle_rows_host[s2]) cudaFreeHost(ex->rle_rows_host[s2]);
     if (ex->rle_slot[s2]) cudaFree(ex->rle_slot[s2]);
     if (ex->rle_rows_slot[s2]) cudaFree(ex->rle_rows_slot[s2]);
+    if (ex->ev_img0[s2]) cudaEventDestroy(ex->ev_img0[s2]);
+    if (ex->ev_img1[s2]) cudaEventDestroy(ex->ev_img1[s2]);
   }
   std::free(ex->neg_host);
   void* bufs[] = {ex->dx_ranks, ex->dx_rank_u32, ex->dx_rank_val, ex->dx_bin_count, ex->dx_bin_idx, ex->dx_bin_val, ex->retry_dev,
@@ -880,6 +895,57 @@ static void narrow_i64_host(const int64_t* in, uint16_t* out, int64_t n_per_fov,
     }
 }
 
+// plain label masks of the chunk's FOVs [fa, fb) -> given_slot[s] (H2D on s_in, converted on the device)
+static int upload_plain_masks(amt_executor* ex, int s, const void* given_labels_host, int64_t f0, int fa, int fb) {
+  using namespace amt;
+  const amt_fov_config& c = ex->cfg;
+  const int64_t HW = (int64_t)c.height * c.width;
+  const int n = fb - fa;
+  if (n <= 0) return AMT_OK;
+  int32_t* out = ex->given_slot[s] + (int64_t)fa * HW;
+  if (ex->host_narrow) {
+    // the staging slot's previous H2D must have left the pinned buffer before host threads overwrite it
+    if (ex->slot_uploaded[s]) AMT_CUDA_TRY(cudaEventSynchronize(ex->ev_in[s]));
+    ex->last_h2d_bytes += (int64_t)n * HW * sizeof(uint16_t);
+    narrow_i64_host((const int64_t*)given_labels_host + (f0 + fa) * HW, ex->given16_host[s] + (int64_t)fa * HW, HW, n,
+                    ex->neg_host ? ex->neg_host + f0 + fa : nullptr);
+    AMT_CUDA_TRY(cudaMemcpyAsync(ex->given16_slot[s] + (int64_t)fa * HW, ex->given16_host[s] + (int64_t)fa * HW,
+                                 (size_t)n * HW * sizeof(uint16_t), cudaMemcpyHostToDevice, ex->s_in));
+    widen_u16_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given16_slot[s] + (int64_t)fa * HW, out, (int64_t)n * HW / 8);
+    AMT_LAUNCH_CHECK();
+  } else if (c.given_label_dtype == AMT_I64) {
+    ex->last_h2d_bytes += (int64_t)n * HW * sizeof(int64_t);
+    AMT_CUDA_TRY(cudaMemcpyAsync(ex->given64_slot[s] + (int64_t)fa * HW, (const int64_t*)given_labels_host + (f0 + fa) * HW,
+                                 (size_t)n * HW * sizeof(int64_t), cudaMemcpyHostToDevice, ex->s_in));
+    narrow_i64_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given64_slot[s] + (int64_t)fa * HW, out, HW, n,
+                                                         ex->flag_slot[s] + c.chunk_fovs + fa);
+    AMT_LAUNCH_CHECK();
+  } else if (c.given_label_dtype == AMT_U16) {
+    ex->last_h2d_bytes += (int64_t)n * HW * sizeof(uint16_t);
+    AMT_CUDA_TRY(cudaMemcpyAsync(ex->given16_slot[s] + (int64_t)fa * HW, (const uint16_t*)given_labels_host + (f0 + fa) * HW,
+                                 (size_t)n * HW * sizeof(uint16_t), cudaMemcpyHostToDevice, ex->s_in));
+    widen_u16_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given16_slot[s] + (int64_t)fa * HW, out, (int64_t)n * HW / 8);
+    AMT_LAUNCH_CHECK();
+  } else {
+    ex->last_h2d_bytes += (int64_t)n * HW * sizeof(int32_t);
+    AMT_CUDA_TRY(cudaMemcpyAsync(out, (const int32_t*)given_labels_host + (f0 + fa) * HW, (size_t)n * HW * sizeof(int32_t),
+                                 cudaMemcpyHostToDevice, ex->s_in));
+  }
+  ex->last_plain_masks += n;
+  return AMT_OK;
+}
+
+// how many of a chunk's g masks take the run-length route: the host threads need rle_a seconds per mask, PCIe moves rle_B
+// bytes per second; n masks encoded and g - n sent plain right behind the images finish together when
+//   rle_a n = (images + n rle_c + (g - n) mask_bytes) / rle_B
+static int rle_masks_of_chunk(const amt_executor* ex, int g, int64_t img_bytes, int64_t mask_bytes, int n_thr) {
+  if (amt::g_exec_rle_share >= 0) return (int)(((int64_t)g * amt::g_exec_rle_share + 50) / 100);
+  if (ex->rle_a <= 0 || ex->rle_B <= 0) return n_thr >= 8 ? g : (g + 1) / 2;  // nothing measured yet
+  const double n = ((double)img_bytes + (double)g * mask_bytes) / (ex->rle_a * ex->rle_B + (double)mask_bytes - ex->rle_c);
+  const int r = (int)(n + 0.5);
+  return r < 0 ? 0 : (r > g ? g : r);
+}
+
 // H2D of one chunk of a host-fed batch into staging slot s (on s_in), label masks converted on the device
 static int upload_chunk(amt_executor* ex, int s, const uint16_t* fovs_host, const void* given_labels_host, int64_t f0, int g) {
   using namespace amt;
@@ -887,67 +953,66 @@ static int upload_chunk(amt_executor* ex, int s, const uint16_t* fovs_host, cons
   const int C = c.n_channels;
   const int64_t HW = (int64_t)c.height * c.width;
   const bool given = c.quantify_given_mask && given_labels_host;
-  AMT_CUDA_TRY(cudaMemcpyAsync(ex->in_slot[s], fovs_host + f0 * C * HW, (size_t)g * C * HW * sizeof(uint16_t),
-                               cudaMemcpyHostToDevice, ex->s_in));
+  const int64_t img_bytes = (int64_t)g * C * HW * sizeof(uint16_t);
+  const bool rle = given && ex->host_rle;
+  if (rle && ex->slot_uploaded[s]) {
+    // the staging slot's previous H2D must have left the pinned buffer before host threads overwrite it; its image copy
+    // gives the PCIe rate this process sees right now (every rank of a box copies at the same time)
+    AMT_CUDA_TRY(cudaEventSynchronize(ex->ev_in[s]));
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, ex->ev_img0[s], ex->ev_img1[s]) == cudaSuccess && ms > 0.0f) {
+      const double B = (double)ex->slot_img_bytes[s] / (1e-3 * ms);
+      ex->rle_B = ex->rle_B > 0 ? 0.5 * ex->rle_B + 0.5 * B : B;
+    }
+  }
+  if (rle) AMT_CUDA_TRY(cudaEventRecord(ex->ev_img0[s], ex->s_in));
+  AMT_CUDA_TRY(cudaMemcpyAsync(ex->in_slot[s], fovs_host + f0 * C * HW, (size_t)img_bytes, cudaMemcpyHostToDevice, ex->s_in));
+  if (rle) AMT_CUDA_TRY(cudaEventRecord(ex->ev_img1[s], ex->s_in));
+  ex->slot_img_bytes[s] = img_bytes;
   AMT_CUDA_TRY(cudaMemsetAsync(ex->flag_slot[s], 0, (size_t)3 * c.chunk_fovs * sizeof(int32_t), ex->s_in));
-  ex->last_h2d_bytes += (int64_t)g * C * HW * sizeof(uint16_t);
-  bool sent = false;
-  if (given && ex->host_rle) {
-    // the staging slot's previous H2D must have left the pinned buffer before host threads overwrite it
-    if (ex->slot_uploaded[s]) AMT_CUDA_TRY(cudaEventSynchronize(ex->ev_in[s]));
-    std::vector<int64_t> first, used;
-    int32_t* neg = ex->neg_host ? ex->neg_host + f0 : nullptr;
+  ex->last_h2d_bytes += img_bytes;
+  if (rle) {
     const int hw_thr = (int)std::thread::hardware_concurrency();
     const int n_thr = hw_thr > 0 && g_exec_host_threads > hw_thr ? hw_thr : g_exec_host_threads;
     const int dt = c.given_label_dtype == AMT_I64 || c.given_label_dtype == AMT_U16 ? c.given_label_dtype : AMT_I32;
-    const size_t esz = dt == AMT_I64 ? 8 : (dt == AMT_U16 ? 2 : 4);
-    const bool ok = rle_encode_host((const char*)given_labels_host + (size_t)f0 * HW * esz, dt, c.height, c.width, g, ex->rle_host[s],
-                                    ex->rle_rows_host[s], neg, n_thr, first, used);
-    if (ok) {
-      for (size_t t = 0; t < first.size(); ++t) {
-        if (used[t] == 0) continue;
-        AMT_CUDA_TRY(cudaMemcpyAsync(ex->rle_slot[s] + first[t], ex->rle_host[s] + first[t], (size_t)used[t] * sizeof(uint2),
-                                     cudaMemcpyHostToDevice, ex->s_in));
-        ex->last_h2d_bytes += used[t] * (int64_t)sizeof(uint2);
+    const int64_t mask_bytes = HW * (dt == AMT_I64 ? 8 : (dt == AMT_U16 ? 2 : 4));
+    const int n_enc = rle_masks_of_chunk(ex, g, img_bytes, mask_bytes, n_thr);
+    // the masks that cross plain go first: PCIe carries them while the host threads encode the others
+    AMT_TRY(upload_plain_masks(ex, s, given_labels_host, f0, n_enc, g));
+    if (n_enc > 0) {
+      std::vector<int64_t> first, used;
+      int32_t* neg = ex->neg_host ? ex->neg_host + f0 : nullptr;
+      const auto t0 = std::chrono::steady_clock::now();
+      const bool ok = rle_encode_host((const char*)given_labels_host + (size_t)f0 * mask_bytes, dt, c.height, c.width, n_enc,
+                                      ex->rle_host[s], ex->rle_rows_host[s], neg, n_thr, first, used);
+      const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (ok) {
+        int64_t bytes = 0;
+        for (size_t t = 0; t < first.size(); ++t) {
+          if (used[t] == 0) continue;
+          AMT_CUDA_TRY(cudaMemcpyAsync(ex->rle_slot[s] + first[t], ex->rle_host[s] + first[t], (size_t)used[t] * sizeof(uint2),
+                                       cudaMemcpyHostToDevice, ex->s_in));
+          bytes += used[t] * (int64_t)sizeof(uint2);
+        }
+        const size_t rows = (size_t)n_enc * c.height;
+        AMT_CUDA_TRY(cudaMemcpyAsync(ex->rle_rows_slot[s], ex->rle_rows_host[s], rows * sizeof(uint2), cudaMemcpyHostToDevice, ex->s_in));
+        bytes += (int64_t)(rows * sizeof(uint2));
+        rle_decode_kernel<<<(unsigned)rows, 256, 0, ex->s_in>>>(ex->rle_slot[s], ex->rle_rows_slot[s], ex->given_slot[s], c.width);
+        AMT_LAUNCH_CHECK();
+        ex->last_h2d_bytes += bytes;
+        ex->last_rle_masks += n_enc;
+        const double a = sec / n_enc, cb = (double)bytes / n_enc;
+        ex->rle_a = ex->rle_a > 0 ? 0.5 * ex->rle_a + 0.5 * a : a;
+        ex->rle_c = ex->rle_c > 0 ? 0.5 * ex->rle_c + 0.5 * cb : cb;
+      } else {
+        // too ragged for the run slots: these masks cross plain as well
+        ex->rle_fallback_chunks += 1;
+        if (neg) std::memset(neg, 0, (size_t)n_enc * sizeof(int32_t));  // the plain route reports negatives itself
+        AMT_TRY(upload_plain_masks(ex, s, given_labels_host, f0, 0, n_enc));
       }
-      const size_t rows = (size_t)g * c.height;
-      AMT_CUDA_TRY(cudaMemcpyAsync(ex->rle_rows_slot[s], ex->rle_rows_host[s], rows * sizeof(uint2), cudaMemcpyHostToDevice, ex->s_in));
-      ex->last_h2d_bytes += (int64_t)(rows * sizeof(uint2));
-      rle_decode_kernel<<<(unsigned)rows, 256, 0, ex->s_in>>>(ex->rle_slot[s], ex->rle_rows_slot[s], ex->given_slot[s], c.width);
-      AMT_LAUNCH_CHECK();
-      sent = true;
-    } else {
-      ex->rle_fallback_chunks += 1;
-      if (neg) std::memset(neg, 0, (size_t)g * sizeof(int32_t));  // the plain route below reports negatives itself
     }
-  }
-  if (sent) {
-  } else if (given && ex->host_narrow) {
-    // the staging slot's previous H2D must have left the pinned buffer before host threads overwrite it
-    if (ex->slot_uploaded[s]) AMT_CUDA_TRY(cudaEventSynchronize(ex->ev_in[s]));
-    ex->last_h2d_bytes += (int64_t)g * HW * sizeof(uint16_t);
-    narrow_i64_host((const int64_t*)given_labels_host + f0 * HW, ex->given16_host[s], HW, g, ex->neg_host ? ex->neg_host + f0 : nullptr);
-    AMT_CUDA_TRY(cudaMemcpyAsync(ex->given16_slot[s], ex->given16_host[s], (size_t)g * HW * sizeof(uint16_t),
-                                 cudaMemcpyHostToDevice, ex->s_in));
-    widen_u16_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given16_slot[s], ex->given_slot[s], (int64_t)g * HW / 8);
-    AMT_LAUNCH_CHECK();
-  } else if (given && c.given_label_dtype == AMT_I64) {
-    ex->last_h2d_bytes += (int64_t)g * HW * sizeof(int64_t);
-    AMT_CUDA_TRY(cudaMemcpyAsync(ex->given64_slot[s], (const int64_t*)given_labels_host + f0 * HW,
-                                 (size_t)g * HW * sizeof(int64_t), cudaMemcpyHostToDevice, ex->s_in));
-    narrow_i64_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given64_slot[s], ex->given_slot[s], HW, g,
-                                                         ex->flag_slot[s] + c.chunk_fovs);
-    AMT_LAUNCH_CHECK();
-  } else if (given && c.given_label_dtype == AMT_U16) {
-    ex->last_h2d_bytes += (int64_t)g * HW * sizeof(uint16_t);
-    AMT_CUDA_TRY(cudaMemcpyAsync(ex->given16_slot[s], (const uint16_t*)given_labels_host + f0 * HW,
-                                 (size_t)g * HW * sizeof(uint16_t), cudaMemcpyHostToDevice, ex->s_in));
-    widen_u16_kernel<<<kNumSMs * 8, 256, 0, ex->s_in>>>(ex->given16_slot[s], ex->given_slot[s], (int64_t)g * HW / 8);
-    AMT_LAUNCH_CHECK();
   } else if (given) {
-    ex->last_h2d_bytes += (int64_t)g * HW * sizeof(int32_t);
-    AMT_CUDA_TRY(cudaMemcpyAsync(ex->given_slot[s], (const int32_t*)given_labels_host + f0 * HW,
-                                 (size_t)g * HW * sizeof(int32_t), cudaMemcpyHostToDevice, ex->s_in));
+    AMT_TRY(upload_plain_masks(ex, s, given_labels_host, f0, 0, g));
   }
   AMT_CUDA_TRY(cudaEventRecord(ex->ev_in[s], ex->s_in));
   ex->slot_uploaded[s] = true;
@@ -1007,7 +1072,7 @@ int amt_executor_run_host(amt_executor* ex, const uint16_t* fovs_host, const voi
   if (ex->last.pending) AMT_TRY(amt_executor_sync(ex));
   AMT_TRY(alloc_host_slots(ex));
   ex->slot_uploaded[0] = ex->slot_uploaded[1] = false;
-  ex->last_h2d_bytes = 0, ex->rle_fallback_chunks = 0;
+  ex->last_h2d_bytes = 0, ex->rle_fallback_chunks = 0, ex->last_rle_masks = 0, ex->last_plain_masks = 0;
   if ((ex->host_narrow || ex->host_rle) && given) {
     if (n_fov > ex->neg_host_cap) {
       std::free(ex->neg_host);
@@ -1098,6 +1163,7 @@ int amt_rle_encode_host(const void* labels_host, int dtype, int32_t n_fov, int32
 
 int64_t amt_executor_last_h2d_bytes(const amt_executor* ex) { return ex ? ex->last_h2d_bytes : -1; }
 int64_t amt_executor_last_plain_mask_chunks(const amt_executor* ex) { return ex ? ex->rle_fallback_chunks : -1; }
+int64_t amt_executor_last_rle_masks(const amt_executor* ex) { return ex ? ex->last_rle_masks : -1; }
 int amt_executor_decision_exact(const amt_executor* ex) { return ex && ex->dx ? 1 : 0; }
 
 float amt_executor_last_ms(amt_executor* ex) {

@@ -552,7 +552,7 @@ def run_b200(args) -> None:
 
         # headline: int64 masks, turned into per-row runs by host threads into pinned staging INSIDE the timed call
         s64 = timed_host(ex, h_given64.numpy())
-        h2d_head, plain_chunks = ex.last_h2d_bytes, ex.last_plain_mask_chunks
+        h2d_head, plain_chunks, rle_masks = ex.last_h2d_bytes, ex.last_plain_mask_chunks, ex.last_rle_masks
         assert np.array_equal(h_out["counts_thr"], counts[0][:n_e2e]) and np.array_equal(h_out["counts_given"], counts[1][:n_e2e])
         _lib.check(lib.amt_tune(b"exec_copy_only", 1), "amt_tune")
         try:
@@ -584,7 +584,7 @@ def run_b200(args) -> None:
             _lib.check(lib.amt_tune(b"exec_host_rle", 1), "amt_tune")
         with FovBatchExecutor(dataclasses.replace(cfg, given_label_dtype=np.uint16), device=local) as ex16:
             s16 = timed_host(ex16, h_given16.numpy().view(np.uint16))
-            h2d16 = ex16.last_h2d_bytes
+            h2d16, rle16 = ex16.last_h2d_bytes, ex16.last_rle_masks
             assert np.array_equal(h_out["counts_given"], counts[1][:n_e2e])
         d2h = sum(int(h_out[k].nbytes) for k in h_out)
         host_read = int(np_fovs.nbytes + h_given64.numpy().nbytes)
@@ -595,7 +595,10 @@ def run_b200(args) -> None:
                                    f"turned into per-row runs of equal value by {host_threads} host threads into pinned staging "
                                    "inside the timed call and decoded on the device (amt_tune exec_host_rle; h2d_bytes_per_step "
                                    "is what crossed PCIe, counted by the executor)",
-               "mask_chunks_sent_plain": plain_chunks,
+               "masks_sent_as_runs": rle_masks, "masks_sent_plain": n_e2e - rle_masks, "mask_chunks_too_ragged_for_runs": plain_chunks,
+               "mask_route": "per chunk the executor balances host encoding time against PCIe time from the rates it measures: "
+                             "masks it does not encode cross as plain int64 right behind the images while the host threads "
+                             "encode the others (counts of the last timed step)",
                "host_bytes_read_per_step": host_read,
                "h2d_gbs": world * args.steps * h2d_head / s64 / 1e9,
                "copy_only": {"seconds_per_step": c64 / args.steps, "h2d_ceiling_gbs": world * args.steps * h2d_head / c64 / 1e9,
@@ -613,7 +616,7 @@ def run_b200(args) -> None:
                                    "note": "amt_tune('exec_host_rle', 0) and ('exec_host_narrow', 0): the int64 masks cross PCIe "
                                            "(67 MB per FOV) and are narrowed on the device"},
                "uint16_masks": {"value": samples / s16 / 1e6, "fov_per_s": world * args.steps * n_e2e / s16,
-                                "h2d_bytes_per_step": h2d16,
+                                "h2d_bytes_per_step": h2d16, "masks_sent_as_runs": rle16,
                                 "note": "Cellpose's own mask dtype (below 65536 cells), run-length staged the same way"},
                "timing": "wall clock around the synchronous C-ABI call, max over ranks",
                "rank0_cpu_affinity": f"{len(cpus)} CPUs local to the GPU (NVML)" if cpus else "unchanged"}

@@ -464,6 +464,13 @@ int64_t amt_executor_last_h2d_bytes(const amt_executor* ex);
 int amt_rle_encode_host(const void* labels_host, int dtype, int32_t n_fov, int32_t height, int32_t width, int32_t n_threads,
                         uint32_t* runs, uint32_t* rows, int32_t* negative, int64_t* n_runs);
 int64_t amt_executor_last_plain_mask_chunks(const amt_executor* ex);
+/* Encoding costs host time, plain masks cost PCIe time: per chunk the executor splits the masks between the two routes
+ * so that both finish together (the plain ones cross right behind the images while the host threads encode the others),
+ * from the encode time per mask and the image-copy rate it measured on the chunks before.  With a GPU to itself and
+ * enough host threads every mask is encoded; eight ranks sharing one host's cores and PCIe root send some masks plain.
+ * amt_tune("exec_rle_share", p) fixes the encoded share at p per cent instead (-1 = balanced, the default).
+ * amt_executor_last_rle_masks: masks of the last batch that crossed as runs. */
+int64_t amt_executor_last_rle_masks(const amt_executor* ex);
 
 /* Per-stage device time (CUDA events after every stage of both executor streams; adds a few microseconds per
  * chunk, off by default).  amt_executor_set_profiling(ex, 1) zeroes the counters; every amt_executor_run_device call

@@ -301,16 +301,19 @@ def test_host_label_masks_give_the_same_answer_on_every_route():
     cfg = FovPipelineConfig(n_channels=C, height=shape[0], width=shape[1], seg_channel=0, chunk_fovs=2, max_labels=512,
                             max_label_value=int(givens[0].max()) + 5, given_label_dtype=np.int64)
 
-    def run(config, masks, rle, narrow):
+    def run(config, masks, rle, narrow, share=100):
         _lib.check(lib.amt_tune(b"exec_host_rle", rle))
         _lib.check(lib.amt_tune(b"exec_host_narrow", narrow))
+        _lib.check(lib.amt_tune(b"exec_rle_share", share))
         try:
             with FovBatchExecutor(config) as ex:
                 out = ex.run_host(fovs, masks, on_error="status")
+                assert ex.last_rle_masks == (0 if not rle else (3 if share == 100 else 2))
                 return out, ex.last_h2d_bytes, ex.last_plain_mask_chunks
         finally:
             _lib.check(lib.amt_tune(b"exec_host_rle", 1))
             _lib.check(lib.amt_tune(b"exec_host_narrow", 1))
+            _lib.check(lib.amt_tune(b"exec_rle_share", -1))
 
     def same(a, b):
         assert np.array_equal(a["status"], b["status"])
@@ -323,7 +326,12 @@ def test_host_label_masks_give_the_same_answer_on_every_route():
     (a, bytes_rle, plain), (b, bytes_narrow, _), (c, bytes_i64, _) = run(cfg, givens, 1, 1), run(cfg, givens, 0, 1), run(cfg, givens, 0, 0)
     assert a["status"][0] == 0 and a["status"][1] & _lib.AMT_FOV_GIVEN_VALUE_RANGE and a["status"][2] & _lib.AMT_FOV_GIVEN_NEGATIVE
     same(a, b), same(a, c)
+    # half of every chunk's masks as runs, the other half plain behind the images (what the executor does by itself when
+    # the host threads are slower than PCIe): FOV 0 and 2 as runs, FOV 1 as int64
+    h, bytes_half, _ = run(cfg, givens, 1, 1, share=50)
+    same(a, h)
     px = 3 * shape[0] * shape[1]
+    assert bytes_half > px * 2 * C + shape[0] * shape[1] * 8
     assert plain == 0 and bytes_narrow == px * (2 * C + 2) and bytes_i64 == px * (2 * C + 8)
     assert px * 2 * C < bytes_rle < px * 2 * C + px // 4  # the masks cross as runs: a small fraction of a byte per pixel
     # the other two host dtypes, run-length staged and plain
@@ -331,7 +339,7 @@ def test_host_label_masks_give_the_same_answer_on_every_route():
         cfg_d = dataclasses.replace(cfg, given_label_dtype=dtype)
         d, bytes_d, plain_d = run(cfg_d, clean.astype(dtype), 1, 1)
         e, bytes_e, _ = run(cfg_d, clean.astype(dtype), 0, 1)
-        same(d, e)
+        same(d, e), same(d, run(cfg_d, clean.astype(dtype), 1, 1, share=50)[0])
         assert plain_d == 0 and px * 2 * C < bytes_d <= bytes_rle and bytes_e == px * (2 * C + np.dtype(dtype).itemsize) and not d["status"].any()
         k = int(a["counts_given"][0])
         assert np.array_equal(d["tables_given"][0][:, :k], a["tables_given"][0][:, :k], equal_nan=True)
@@ -358,12 +366,14 @@ def test_ragged_label_masks_fall_back_to_the_plain_route():
     outs = []
     for rle in (1, 0):
         _lib.check(lib.amt_tune(b"exec_host_rle", rle))
+        _lib.check(lib.amt_tune(b"exec_rle_share", 100))  # every mask is tried as runs (no balancing against PCIe here)
         try:
             with FovBatchExecutor(cfg) as ex:
                 outs.append(ex.run_host(fovs, givens, on_error="status"))
-                assert ex.last_plain_mask_chunks == (1 if rle else 0)
+                assert ex.last_plain_mask_chunks == (1 if rle else 0) and ex.last_rle_masks == (3 if rle else 0)
         finally:
             _lib.check(lib.amt_tune(b"exec_host_rle", 1))
+            _lib.check(lib.amt_tune(b"exec_rle_share", -1))
     a, b = outs
     assert np.array_equal(a["status"], b["status"]) and a["status"][2] & _lib.AMT_FOV_GIVEN_NEGATIVE and not a["status"][3]
     assert np.array_equal(a["counts_given"], b["counts_given"])
