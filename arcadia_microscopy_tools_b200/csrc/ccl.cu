@@ -35,6 +35,9 @@ namespace amt {
 #ifndef AMT_CCL_TH
 #define AMT_CCL_TH 32
 #endif
+// amt_tune "ccl_touch_filter": 1 (default) = integer masks with border clearing are labelled only where it can matter
+// (the pixels of values that occur on the image border), 0 = every pixel
+int g_ccl_touch_filter = 1;
 constexpr int TW = 64, TH = AMT_CCL_TH;  // tile of kernel A (TW is the width of the 64-bit row masks)
 constexpr int TILE_WARPS = TH / 8, TILE_THREADS = TILE_WARPS * 32;
 
@@ -126,7 +129,7 @@ template <int KIND>
 __global__ void __launch_bounds__(TILE_THREADS)
 ccl_tile_kernel(const void* __restrict__ in, const int64_t in_stride, const double* __restrict__ thresholds,
                 int32_t* __restrict__ L, int32_t* __restrict__ rootlist, int32_t* __restrict__ rootcnt, const int h,
-                const int w) {
+                const int w, const int32_t* __restrict__ touch, int32_t* __restrict__ present, const int nval) {
   __shared__ int s_lab[TH * TW];                  // union-find over run starts (tile-local pixel index)
   __shared__ uint64_t s_fg[TH], s_brk[TH];        // per row: foreground, run starts
   __shared__ uint64_t s_n[KIND == 2 ? TH : 1], s_nw[KIND == 2 ? TH : 1], s_ne[KIND == 2 ? TH : 1];
@@ -160,6 +163,41 @@ ccl_tile_kernel(const void* __restrict__ in, const int64_t in_stride, const doub
         vals[q][half] = (y < h && x < w) ? ccl_cook<KIND>(raw[q][half], thr) : 0;
       }
     }
+  }
+  if (KIND == 2 && touch != nullptr) {
+    // Integer masks with border clearing: only a VALUE that occurs on the image border can lose a fragment, so only
+    // the pixels of those values need connectivity.  Every other in-range value is present as it stands (marked here,
+    // once per run) and its pixels are background for the labelling; a tile without a pixel of a border value is done.
+    const int32_t* tp = touch + img * (int64_t)nval;
+    int32_t* pp = present + img * (int64_t)nval;
+    int tch[8][2];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        int v = vals[q][half];
+        v = (v > 0 && v < nval) ? v : 0;  // values outside the declared range label nothing (relabel_final reports them)
+        vals[q][half] = v;
+        tch[q][half] = v ? __ldg(tp + v) : 0;
+      }
+    int any = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      int last = 0;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int v = vals[q][half];
+        int vl = __shfl_up_sync(0xffffffffu, v, 1);
+        if (lane == 0) vl = half ? last : 0;
+        last = __shfl_sync(0xffffffffu, v, 31);
+        if (v != 0 && !tch[q][half]) {
+          if (v != vl) pp[v] = 1;
+          vals[q][half] = 0;
+        }
+        any |= vals[q][half];
+      }
+    }
+    if (!__syncthreads_or(any)) return;
   }
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -309,7 +347,7 @@ ccl_tile_kernel(const void* __restrict__ in, const int64_t in_stride, const doub
 template <int KIND>
 __global__ void __launch_bounds__(256)
 ccl_seam_kernel(const void* __restrict__ in, const int64_t in_stride, int32_t* __restrict__ L, const int h, const int w,
-                const int n_hseams, const int n_vseams) {
+                const int n_hseams, const int n_vseams, const int32_t* __restrict__ touch, const int nval) {
   const int64_t img = blockIdx.y;
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t n_h = (int64_t)n_hseams * w;
@@ -335,6 +373,7 @@ ccl_seam_kernel(const void* __restrict__ in, const int64_t in_stride, int32_t* _
     lab = (const int32_t*)in + img * in_stride;
     v = lab[p];
     if (v == 0) return;
+    if (touch != nullptr && (v < 0 || v >= nval || !touch[img * (int64_t)nval + v])) return;  // not labelled (see the tile kernel)
   } else if (Lp[p] < 0) {
     return;
   }
@@ -399,10 +438,26 @@ ccl_roots_kernel(int32_t* __restrict__ L, const int32_t* __restrict__ rootlist, 
   }
 }
 
+// integer masks: the values that occur on the image border (the only ones clear_border can take a fragment from)
+__global__ void __launch_bounds__(256)
+ccl_touch_kernel(const int32_t* __restrict__ in, const int64_t in_stride, int32_t* __restrict__ touch, const int h, const int w,
+                 const int nval) {
+  const int64_t img = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= 2 * w + 2 * h) return;
+  int x, y;
+  if (t < w) { y = 0; x = t; }
+  else if (t < 2 * w) { y = h - 1; x = t - w; }
+  else if (t < 2 * w + h) { x = 0; y = t - 2 * w; }
+  else { x = w - 1; y = t - 2 * w - h; }
+  const int v = in[img * in_stride + (int64_t)y * w + x];
+  if (v > 0 && v < nval) touch[img * (int64_t)nval + v] = 1;
+}
+
 // components with a pixel on the image border lose their root bit (clear_border)
 __global__ void __launch_bounds__(256)
 ccl_border_kernel(const int32_t* __restrict__ L, uint32_t* __restrict__ rootbits, const int h, const int w,
-                  const int64_t words) {
+                  const int64_t words, const int32_t* __restrict__ vals, const int64_t vals_stride, const int nval) {
   const int64_t img = blockIdx.y;
   const int t = blockIdx.x * 256 + threadIdx.x;
   const int n_border = 2 * w + 2 * h;
@@ -413,6 +468,10 @@ ccl_border_kernel(const int32_t* __restrict__ L, uint32_t* __restrict__ rootbits
   else if (t < 2 * w + h) { x = 0; y = t - 2 * w; }
   else { x = w - 1; y = t - 2 * w - h; }
   const int32_t* Lp = L + img * (int64_t)h * w;
+  if (vals != nullptr) {  // filtered integer masks: only pixels of in-range values were labelled
+    const int v = vals[img * vals_stride + y * w + x];
+    if (v <= 0 || v >= nval) return;
+  }
   const int r = Lp[y * w + x];
   if (r < 0) return;
   const int g = uf_find(Lp, r);
@@ -543,12 +602,14 @@ ccl_final_kernel(int32_t* __restrict__ L, const int32_t* __restrict__ gid, const
 __global__ void __launch_bounds__(256)
 relabel_final_kernel(const int32_t* __restrict__ in, const int64_t in_stride, int32_t* __restrict__ L,
                      const int32_t* __restrict__ aux, const int64_t npx, const int32_t* __restrict__ rank,
-                     const int64_t nval, const int use_ccl, const int vec, int32_t* __restrict__ value_overflow) {
+                     const int64_t nval, const int use_ccl, const int vec, int32_t* __restrict__ value_overflow,
+                     const int32_t* __restrict__ touch) {
   const int64_t img = blockIdx.y;
   const int32_t* lab = in + img * in_stride;
   int32_t* Lp = L + img * npx;
   const int32_t* ap = aux + img * npx;
   const int32_t* rk = rank + img * nval;
+  const int32_t* tp = touch != nullptr ? touch + img * nval : nullptr;
   auto one = [&](int v, int root) -> int {
     if (v >= nval) {  // outside the declared range: background here, reported to the caller
       if (value_overflow != nullptr) value_overflow[img] = 1;
@@ -558,9 +619,26 @@ relabel_final_kernel(const int32_t* __restrict__ in, const int64_t in_stride, in
     if (use_ccl && __ldg(ap + root) == -1) return 0;
     return __ldg(rk + v);
   };
+  // filtered labelling (touch != null): only the pixels of a border value carry a tile root; everybody else keeps its value's rank
+  auto one_filtered = [&](int v, int64_t p) -> int {
+    if (v >= nval) {
+      if (value_overflow != nullptr) value_overflow[img] = 1;
+      return 0;
+    }
+    if (v <= 0) return 0;
+    if (__ldg(tp + v) && __ldg(ap + Lp[p]) == -1) return 0;
+    return __ldg(rk + v);
+  };
   const int64_t step = (int64_t)gridDim.x * 256 * 4;
   for (int64_t p0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; p0 < npx; p0 += step) {
-    if (vec && p0 + 3 < npx) {
+    if (vec && p0 + 3 < npx && use_ccl && tp != nullptr) {
+      const int4 v = *reinterpret_cast<const int4*>(lab + p0);
+      int4 o = make_int4(0, 0, 0, 0);
+      if ((v.x | v.y | v.z | v.w) != 0) o = make_int4(one_filtered(v.x, p0), one_filtered(v.y, p0 + 1), one_filtered(v.z, p0 + 2), one_filtered(v.w, p0 + 3));
+      *reinterpret_cast<int4*>(Lp + p0) = o;
+    } else if (use_ccl && tp != nullptr) {
+      for (int i = 0; i < 4 && p0 + i < npx; ++i) Lp[p0 + i] = one_filtered(lab[p0 + i], p0 + i);
+    } else if (vec && p0 + 3 < npx) {
       const int4 v = *reinterpret_cast<const int4*>(lab + p0);
       int4 r = make_int4(0, 0, 0, 0);
       if (use_ccl) r = *reinterpret_cast<const int4*>(Lp + p0);
@@ -614,6 +692,7 @@ struct LabelScratch {
   int32_t* blocksum;  // one int per 1024-word block (exclusive prefix over the plane after ccl_rank_top_kernel)
   int nblocks;
   int32_t* present;
+  int32_t* touch;     // integer masks: value occurs on the image border (right behind `present`: cleared together)
   int64_t words;
   size_t zero_bytes;  // rootcnt + rootbits are contiguous and cleared per call
   size_t total;
@@ -640,6 +719,8 @@ static LabelScratch label_scratch_layout(void* base, int64_t n_img, int64_t h, i
   s.blocksum = (int32_t*)((char*)base + off);
   off += align256((size_t)n_img * s.nblocks * sizeof(int32_t));
   s.present = (int32_t*)((char*)base + off);
+  off += (size_t)n_img * (size_t)(max_value + 1) * sizeof(int32_t);
+  s.touch = (int32_t*)((char*)base + off);
   off += align256((size_t)n_img * (size_t)(max_value + 1) * sizeof(int32_t));
   s.total = off;
   return s;
@@ -649,24 +730,25 @@ static LabelScratch label_scratch_layout(void* base, int64_t n_img, int64_t h, i
 // root, and rootbits marks the surviving global roots
 template <int KIND>
 static int ccl_core(const void* in, int64_t in_stride, const double* thresholds, int64_t n_img, int h, int w,
-                    int clear_border, int32_t* L, const LabelScratch& s, cudaStream_t st) {
+                    int clear_border, int32_t* L, const LabelScratch& s, cudaStream_t st, const int32_t* touch = nullptr,
+                    int nval = 0) {
   const int64_t npx = (int64_t)h * w;
   AMT_CUDA_TRY(cudaMemsetAsync(s.rootcnt, 0, s.zero_bytes, st));
   dim3 tgrid((unsigned)ceil_div(w, TW), (unsigned)ceil_div(h, TH), (unsigned)n_img);
-  ccl_tile_kernel<KIND><<<tgrid, TILE_THREADS, 0, st>>>(in, in_stride, thresholds, L, s.rootlist, s.rootcnt, h, w);
+  ccl_tile_kernel<KIND><<<tgrid, TILE_THREADS, 0, st>>>(in, in_stride, thresholds, L, s.rootlist, s.rootcnt, h, w, touch, s.present, nval);
   AMT_LAUNCH_CHECK();
   const int n_hseams = (int)ceil_div(h, TH) - 1, n_vseams = (int)ceil_div(w, TW) - 1;
   const int64_t seam_px = (int64_t)n_hseams * w + (int64_t)n_vseams * 2 * h;
   if (seam_px > 0) {
     ccl_seam_kernel<KIND><<<dim3((unsigned)ceil_div(seam_px, 256), (unsigned)n_img), 256, 0, st>>>(in, in_stride, L, h, w,
-                                                                                                 n_hseams, n_vseams);
+                                                                                                 n_hseams, n_vseams, touch, nval);
     AMT_LAUNCH_CHECK();
   }
   ccl_roots_kernel<<<dim3(64, (unsigned)n_img), 256, 0, st>>>(L, s.rootlist, s.rootcnt, s.rootbits, npx, s.words);
   AMT_LAUNCH_CHECK();
   if (clear_border) {
     ccl_border_kernel<<<dim3((unsigned)ceil_div(2 * (int64_t)w + 2 * h, 256), (unsigned)n_img), 256, 0, st>>>(
-        L, s.rootbits, h, w, s.words);
+        L, s.rootbits, h, w, s.words, touch != nullptr ? (const int32_t*)in : nullptr, in_stride, nval);
     AMT_LAUNCH_CHECK();
   }
   return AMT_OK;
@@ -694,9 +776,15 @@ int label_launch(const void* in, int in_kind, int64_t in_stride, const double* t
 
   if (in_kind == 2) {
     const int64_t nval = max_value + 1;
-    AMT_CUDA_TRY(cudaMemsetAsync(s.present, 0, (size_t)n_img * nval * sizeof(int32_t), st));
+    const bool filtered = clear_border && g_ccl_touch_filter && nval < (1ll << 31);
+    AMT_CUDA_TRY(cudaMemsetAsync(s.present, 0, (size_t)n_img * nval * sizeof(int32_t) * (filtered ? 2 : 1), st));
     if (clear_border) {
-      AMT_TRY(ccl_core<2>(in, in_stride, nullptr, n_img, (int)h, (int)w, 1, labels_out, s, st));
+      if (filtered) {
+        ccl_touch_kernel<<<dim3((unsigned)ceil_div(2 * w + 2 * h, 256), (unsigned)n_img), 256, 0, st>>>(
+            (const int32_t*)in, in_stride, s.touch, (int)h, (int)w, (int)nval);
+        AMT_LAUNCH_CHECK();
+      }
+      AMT_TRY(ccl_core<2>(in, in_stride, nullptr, n_img, (int)h, (int)w, 1, labels_out, s, st, filtered ? s.touch : nullptr, (int)nval));
       ccl_present_kernel<<<rgrid, 256, 0, st>>>((const int32_t*)in, in_stride, s.rootlist, s.rootcnt, s.rootbits, npx,
                                                 s.words, s.present, nval);
       AMT_LAUNCH_CHECK();
@@ -711,7 +799,7 @@ int label_launch(const void* in, int in_kind, int64_t in_stride, const double* t
     AMT_LAUNCH_CHECK();
     relabel_final_kernel<<<sgrid, 256, 0, st>>>((const int32_t*)in, in_stride, labels_out, s.gid, npx, s.present, nval,
                                                 clear_border, vec && (in_stride % 4 == 0) && (((uintptr_t)in) % 16 == 0),
-                                                value_overflow);
+                                                value_overflow, filtered ? s.touch : nullptr);
     AMT_LAUNCH_CHECK();
     return AMT_OK;
   }

@@ -408,6 +408,7 @@ extern int g_exec_buckets;    // executor.cu
 extern int g_exec_tc;         // executor.cu
 extern int g_exec_fused_lo;   // executor.cu
 extern int g_exec_given_stream;
+extern int g_ccl_touch_filter;  // ccl.cu
 extern int g_exec_host_narrow, g_exec_host_threads, g_exec_host_rle, g_exec_rle_share;
 extern int g_exec_copy_only;  // executor.cu
 static int g_dog_only_exact = 0;  // amt_tune: the stand-alone axis0 / axis1 entry points cover the exact planes only
@@ -586,6 +587,8 @@ int amt_tune(const char* key, int value) {
     g_exec_buckets = value != 0;
   } else if (is("tcg_debug")) {
     tc::g_tcg_debug = value;
+  } else if (is("ccl_touch_filter")) {
+    g_ccl_touch_filter = value != 0;
   } else if (is("exec_copy_only")) {
     g_exec_copy_only = value != 0;
   } else if (is("dog_only_exact")) {

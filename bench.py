@@ -539,6 +539,9 @@ def run_b200(args) -> None:
         np_fovs = h_fovs.numpy().view(np.uint16)
         h_out = ex.alloc_host_outputs(n_e2e)
 
+        cfg_h = dataclasses.replace(cfg, chunk_fovs=args.e2e_chunk)
+        ex_h = FovBatchExecutor(cfg_h, device=local)
+
         def timed_host(executor, masks) -> float:
             for _ in range(min(args.warmup, 2)):
                 executor.run_host(np_fovs, masks, h_out)
@@ -551,25 +554,26 @@ def run_b200(args) -> None:
             return max_ranks(dt)
 
         # headline: int64 masks, turned into per-row runs by host threads into pinned staging INSIDE the timed call
-        s64 = timed_host(ex, h_given64.numpy())
-        h2d_head, plain_chunks, rle_masks = ex.last_h2d_bytes, ex.last_plain_mask_chunks, ex.last_rle_masks
+        s64 = timed_host(ex_h, h_given64.numpy())
+        h2d_head, plain_chunks, rle_masks = ex_h.last_h2d_bytes, ex_h.last_plain_mask_chunks, ex_h.last_rle_masks
         assert np.array_equal(h_out["counts_thr"], counts[0][:n_e2e]) and np.array_equal(h_out["counts_given"], counts[1][:n_e2e])
         _lib.check(lib.amt_tune(b"exec_copy_only", 1), "amt_tune")
         try:
-            c64 = timed_host(ex, h_given64.numpy())
+            c64 = timed_host(ex_h, h_given64.numpy())
         finally:
             _lib.check(lib.amt_tune(b"exec_copy_only", 0), "amt_tune")
+        ex_h.close()
         # the same with plain masks over PCIe: int64 narrowed to uint16 by host threads, and int64 as they are
         _lib.check(lib.amt_tune(b"exec_host_rle", 0), "amt_tune")
         try:
             host_narrow = cfg.max_label_value < 65535
-            with FovBatchExecutor(cfg, device=local) as ex_n:
+            with FovBatchExecutor(cfg_h, device=local) as ex_n:
                 s64n = timed_host(ex_n, h_given64.numpy())
                 h2d_n = ex_n.last_h2d_bytes
                 assert np.array_equal(h_out["counts_given"], counts[1][:n_e2e])
             _lib.check(lib.amt_tune(b"exec_host_narrow", 0), "amt_tune")
             try:
-                with FovBatchExecutor(cfg, device=local) as ex_dev:
+                with FovBatchExecutor(cfg_h, device=local) as ex_dev:
                     s64d = timed_host(ex_dev, h_given64.numpy())
                     h2d64 = ex_dev.last_h2d_bytes
                     assert np.array_equal(h_out["counts_given"], counts[1][:n_e2e])
@@ -582,7 +586,7 @@ def run_b200(args) -> None:
                 _lib.check(lib.amt_tune(b"exec_host_narrow", 1), "amt_tune")
         finally:
             _lib.check(lib.amt_tune(b"exec_host_rle", 1), "amt_tune")
-        with FovBatchExecutor(dataclasses.replace(cfg, given_label_dtype=np.uint16), device=local) as ex16:
+        with FovBatchExecutor(dataclasses.replace(cfg_h, given_label_dtype=np.uint16), device=local) as ex16:
             s16 = timed_host(ex16, h_given16.numpy().view(np.uint16))
             h2d16, rle16 = ex16.last_h2d_bytes, ex16.last_rle_masks
             assert np.array_equal(h_out["counts_given"], counts[1][:n_e2e])
@@ -590,7 +594,7 @@ def run_b200(args) -> None:
         host_read = int(np_fovs.nbytes + h_given64.numpy().nbytes)
         samples = world * args.steps * n_e2e * C * H * W
         e2e = {"value": samples / s64 / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d_head, "d2h_bytes_per_step": d2h,
-               "fov_per_s": world * args.steps * n_e2e / s64, "fovs_per_step": n_e2e,
+               "fov_per_s": world * args.steps * n_e2e / s64, "fovs_per_step": n_e2e, "chunk_fovs": args.e2e_chunk,
                "label_mask_dtype": "int64 in host memory (the reference's dtype at this boundary: model.py:215, masks.py:138), "
                                    f"turned into per-row runs of equal value by {host_threads} host threads into pinned staging "
                                    "inside the timed call and decoded on the device (amt_tune exec_host_rle; h2d_bytes_per_step "
@@ -821,7 +825,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--fovs", type=int, default=256, help="FOVs per GPU per step (config 2: 256)")
     ap.add_argument("--unique", type=int, default=8, help="distinct seeded cell layouts")
-    ap.add_argument("--chunk", type=int, default=16, help="FOVs per launch wave (16 measured 5 % faster than 8: the ~25 launch-bound kernels of a chunk amortise)")
+    ap.add_argument("--chunk", type=int, default=32, help="FOVs per launch wave, device-resident leg (16 measured 5 % faster than 8, 32 another 2.8 %: the ~25 launch-bound kernels of a chunk amortise)")
+    ap.add_argument("--e2e-chunk", type=int, default=16, help="FOVs per launch wave, host-fed leg (a chunk is also the unit of its copy / compute pipeline)")
     ap.add_argument("--e2e-fovs", type=int, default=256)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline and the full-size parity check (N=1)")

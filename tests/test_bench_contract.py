@@ -39,12 +39,21 @@ def test_b200_line_has_the_contract_keys(name, n_gpus):
     # int64 label masks in host memory: 4 x 2 bytes of pixels + 8 bytes of label per FOV-pixel read by the call; when host
     # threads narrow the masks to uint16 inside the call, 2 bytes of label cross PCIe and the int64 route is reported beside it
     px = e2e["fovs_per_step"] * 2048 * 2048
-    if "host_bytes_read_per_step" in e2e:
+    if "masks_sent_as_runs" in e2e:
+        # label masks cross PCIe as per-row runs where the host threads keep up (the executor balances per chunk); the
+        # plain routes are reported beside it
+        n_runs, n_plain = e2e["masks_sent_as_runs"], e2e["masks_sent_plain"]
+        assert n_runs + n_plain == e2e["fovs_per_step"] and e2e["host_bytes_read_per_step"] == px * (4 * 2 + 8)
+        lo = px * 4 * 2 + n_plain * 2048 * 2048 * 8
+        assert lo < e2e["h2d_bytes_per_step"] <= lo + n_runs * 2048 * 2048 * 2
+        assert e2e["int64_over_pcie"]["h2d_bytes_per_step"] == px * (4 * 2 + 8) and 0 < e2e["int64_over_pcie"]["value"] < e2e["value"]
+        assert e2e["int64_narrowed_to_uint16"]["h2d_bytes_per_step"] == px * (4 * 2 + 2)
+    elif "host_bytes_read_per_step" in e2e:
         assert e2e["host_bytes_read_per_step"] == px * (4 * 2 + 8) and e2e["h2d_bytes_per_step"] == px * (4 * 2 + 2)
         assert e2e["int64_over_pcie"]["h2d_bytes_per_step"] == px * (4 * 2 + 8) and 0 < e2e["int64_over_pcie"]["value"] < e2e["value"]
     else:
         assert e2e["h2d_bytes_per_step"] == px * (4 * 2 + 8)
-    assert 0.5 < e2e["frac_of_copy_ceiling"] <= 1.05 and e2e["uint16_masks"]["value"] > e2e["value"]
+    assert 0.5 < e2e["frac_of_copy_ceiling"] <= 1.05 and e2e["uint16_masks"]["value"] > 0.98 * e2e["value"]
     clocks = d["clocks"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(clocks) and clocks["samples"] >= 10
     assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(clocks["reasons"])
