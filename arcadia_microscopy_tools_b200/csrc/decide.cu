@@ -118,6 +118,9 @@ exact_eval_kernel(const uint16_t* __restrict__ in, int64_t img_stride, int h, in
 // Windows of the order statistics: list (img, k), k < N_WIN; centre[k] = the approximate statistic (k < 6: the six
 // percentile ranks; 6, 7: min, max).  One pass over D': samples below the window are counted, samples inside it listed.
 constexpr int N_WIN = 8;
+}  // namespace dx
+int g_dx_collect_threads = 1024;  // amt_tune "dx_collect_threads": threads per CTA of rank_collect_buckets_kernel (256 or 1024)
+namespace dx {
 
 __global__ void __launch_bounds__(256)
 rank_collect_kernel(const double* __restrict__ dog, int64_t img_stride, int64_t n, const double* __restrict__ stats,
@@ -165,7 +168,7 @@ rank_collect_kernel(const double* __restrict__ dog, int64_t img_stride, int64_t 
 // touches the 8-byte samples of the few buckets a window end falls into only.  A per-block table maps a bucket code
 // to eight bytes, one per window: 1 = certainly below, 2 = look at the value; the "below" bytes of up to 255 samples
 // add up in one 64-bit register.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 rank_collect_buckets_kernel(const double* __restrict__ dog, const uint16_t* __restrict__ buckets, int64_t img_stride, int64_t n,
                             const double* __restrict__ stats, int64_t stats_stride, const uint64_t* __restrict__ mm,
                             int64_t mm_stride, double eps2, uint32_t* __restrict__ below, uint32_t* __restrict__ count,
@@ -187,7 +190,7 @@ rank_collect_buckets_kernel(const double* __restrict__ dog, const uint16_t* __re
   uint32_t blo[N_WIN], bhi[N_WIN];
 #pragma unroll
   for (int k = 0; k < N_WIN; ++k) blo[k] = bucket12(s_lo[k]), bhi[k] = bucket12(s_hi[k]);
-  for (int code = threadIdx.x; code < 4096; code += 256) {
+  for (int code = threadIdx.x; code < 4096; code += blockDim.x) {
     uint64_t e = 0;
 #pragma unroll
     for (int k = 0; k < N_WIN; ++k) e |= (uint64_t)((uint32_t)code < blo[k] ? 1u : ((uint32_t)code <= bhi[k] ? 2u : 0u)) << (8 * k);
@@ -290,10 +293,15 @@ int rank_exact(const uint16_t* in, int64_t in_img_stride, const double* dog, con
   int64_t blocks = ceil_div(n, 256 * 8);
   const int64_t cap_blocks = ceil_div((int64_t)kNumSMs * 8, n_img);
   if (blocks > cap_blocks) blocks = cap_blocks;
-  if (buckets != nullptr && n % 8 == 0 && ((uintptr_t)buckets % 16) == 0 && (dog_img_stride % 8) == 0)
-    rank_collect_buckets_kernel<<<dim3((unsigned)blocks, (unsigned)n_img), 256, 0, st>>>(
+  if (buckets != nullptr && n % 8 == 0 && ((uintptr_t)buckets % 16) == 0 && (dog_img_stride % 8) == 0) {
+    // every CTA builds a 4096-entry table first: fewer, larger CTAs (g_dx_collect_threads = 1024: two per SM) spend less on it
+    const int thr = g_dx_collect_threads;
+    int64_t bb = ceil_div(n, (int64_t)thr * 8);
+    const int64_t cb = ceil_div((int64_t)kNumSMs * (2048 / thr), n_img);
+    if (bb > cb) bb = cb;
+    rank_collect_buckets_kernel<<<dim3((unsigned)bb, (unsigned)n_img), thr, 0, st>>>(
         dog, buckets, dog_img_stride, n, stats, stats_stride, mm, mm_stride, 2.0 * eps, below, count, idx, cap);
-  else
+  } else
     rank_collect_kernel<<<dim3((unsigned)blocks, (unsigned)n_img), 256, 0, st>>>(dog, dog_img_stride, n, stats, stats_stride, mm,
                                                                                mm_stride, 2.0 * eps, below, count, idx, cap);
   AMT_LAUNCH_CHECK();

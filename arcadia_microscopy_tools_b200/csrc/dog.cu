@@ -409,6 +409,7 @@ extern int g_exec_tc;         // executor.cu
 extern int g_exec_fused_lo;   // executor.cu
 extern int g_exec_given_stream;
 extern int g_ccl_touch_filter;  // ccl.cu
+extern int g_dx_collect_threads;  // decide.cu
 extern int g_exec_host_narrow, g_exec_host_threads, g_exec_host_rle, g_exec_rle_share;
 extern int g_exec_copy_only;  // executor.cu
 static int g_dog_only_exact = 0;  // amt_tune: the stand-alone axis0 / axis1 entry points cover the exact planes only
@@ -587,6 +588,9 @@ int amt_tune(const char* key, int value) {
     g_exec_buckets = value != 0;
   } else if (is("tcg_debug")) {
     tc::g_tcg_debug = value;
+  } else if (is("dx_collect_threads")) {
+    if (value != 256 && value != 1024) return AMT_ERR_INVALID;
+    g_dx_collect_threads = value;
   } else if (is("ccl_touch_filter")) {
     g_ccl_touch_filter = value != 0;
   } else if (is("exec_copy_only")) {
