@@ -44,30 +44,18 @@ def main():
     n_fov = 64
     fovs, given, max_label = bench.build_device_batch(n_fov, 8, dev)
     res = {}
-    # ---- the executor (64 FOVs, chunks of 32): prefetch x threads per CTA of the decision-exact collect pass
-    ref = None
+    # (the sections of the experiments that were measured and reverted are gone with their switches; the log has the numbers)
+    # ---- the executor (64 FOVs, chunks of 32) with the decision-exact collect pass at 256 / 1024 threads per CTA
     cfg = FovPipelineConfig(n_channels=C, height=H, width=W, seg_channel=bench.SEG_CHANNEL, chunk_fovs=32, max_labels=4096,
                             max_label_value=max_label)
-    for pf, thr in ((0, 256), (0, 1024), (0, 256), (0, 1024)):
+    for thr in (256, 1024, 256, 1024):
         tune(b"dx_collect_threads", thr)
         with FovBatchExecutor(cfg, device=0) as ex:
-            out = ex.alloc_outputs(n_fov, labels=True)
+            out = ex.alloc_outputs(n_fov)
             for _ in range(2):
                 ex.run_device(fovs, given, out, sync=True)
             ms = [ex.run_device(fovs, given, out, sync=True) for _ in range(5)]
-            snap = {k: out[k].clone() for k in ("tables_thr", "tables_given", "counts_thr", "counts_given", "thresholds", "labels_given")}
-        if ref is None:
-            ref = snap
-
-        def rows_equal(k, cnt):  # tables are max_labels wide: only the first count columns of an image are written
-            a, b = ref[k], snap[k]
-            return all(torch.equal(a[i][:, :int(c)].view(torch.int64), b[i][:, :int(c)].view(torch.int64)) for i, c in enumerate(ref[cnt].tolist()))
-
-        same = (all(torch.equal(ref[k], snap[k]) for k in ("counts_thr", "counts_given", "labels_given"))
-                and torch.equal(ref["thresholds"].view(torch.int64), snap["thresholds"].view(torch.int64))
-                and rows_equal("tables_thr", "counts_thr") and rows_equal("tables_given", "counts_given"))
-        res.setdefault(f"executor_ms_per_8_fov_prefetch{pf}_collect{thr}", []).append(sum(ms) / len(ms) / (n_fov / 8))
-        res[f"executor_same_prefetch{pf}_collect{thr}"] = bool(same)
+        res.setdefault(f"executor_ms_per_8_fov_collect{thr}", []).append(sum(ms) / len(ms) / (n_fov / 8))
     tune(b"dx_collect_threads", 1024)
     print(json.dumps(res))
 
