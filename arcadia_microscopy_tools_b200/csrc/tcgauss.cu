@@ -19,8 +19,8 @@
 //     clamped-edge ('nearest') taps, rounds to 40 bits and stores five uint8 digit planes;
 //   * pass 2 (image axis 1): the five digit planes are the K-major B operand, again straight from TMA;
 //     weight digit d x sample digit s accumulates into the TMEM accumulator of d + s (products of equal
-//     significance share one accumulator; d + s < 2 is below 2^-45 of full scale and skipped): 17 digit
-//     products x 8 K-steps (M = 128, N = 32, K = 32).  The epilogue shifts the six accumulators together
+//     significance share one accumulator; d + s < 3 is at most 1.1e-11 of full scale and skipped): 14 digit
+//     products x 8 K-steps (M = 128, N = 32, K = 32).  The epilogue shifts the five accumulators together
 //     in 64-bit integers, converts ONCE to float64, subtracts from the narrow Gaussian (lo2d_kernel
 //     below, float64, scipy's order) and writes the DoG plane, its selection buckets and min / max.
 // Errors: the only approximation is the 32-bit rounding of the weights (|dw| <= 2^-37 per tap, zero
@@ -52,7 +52,7 @@ constexpr int MT = 128;          // outputs per tile along the filter axis (UMMA
 constexpr int HALO = 64;         // largest radius
 constexpr int WD = 4;            // weight digits (base 256)
 constexpr int GD = 5;            // digits of the pass-1 result (40 bits)
-constexpr int JMIN = 2;          // digit products with d + s < JMIN are dropped in pass 2
+constexpr int JMIN = 3;          // digit products with d + s < JMIN are dropped in pass 2 (amt_tcg_error_bound counts them)
 constexpr int NACC2 = WD + GD - 1 - JMIN;  // accumulators of pass 2 (j = JMIN .. WD+GD-2)
 constexpr int P1_NB = 64;        // pass 1: bytes (UMMA N) per tile along the contiguous axis = 32 pixels
 constexpr int P1_STAGES = 8;
@@ -222,7 +222,7 @@ struct alignas(8) Barriers {
   uint64_t acc_full, acc_empty;
   uint64_t lo_full[2], lo_empty[2];  // warp-specialised pass 2: narrow-Gaussian tiles handed from the lo warps to the epilogue warps
   uint64_t suffix[HALO + 2];   // pass 1: integer tail sums of the weights (clamped-edge taps)
-  double suffix_f[HALO + 2];   // pass 2: the same, as float64 * 2^-16
+  double suffix_f[HALO + 2];   // pass 2: the same, as float64 * 2^-(8 JMIN)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -511,8 +511,8 @@ struct Pass2Params {
   uint16_t* buckets;       // optional
   uint64_t* minmax;        // optional [planes][2]
   const uint8_t* band;
-  const double* suffix_f;  // (double)suffix[j] * 2^-16
-  double scale;            // in_scale * 2^-(S+8)
+  const double* suffix_f;  // (double)suffix[j] * 2^-(8 JMIN)
+  double scale;            // in_scale * 2^-(S + 24 - 8 JMIN)
   int h, w, r;
   int n_sel, tiles_y, tiles_x;
   PlaneSel sel;
@@ -726,7 +726,25 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       tc_fence_after();
       const uint32_t b_base = smem_u32(stage_s + stage * STAGE_BYTES);
       if (elect_one()) {
-        if (!(p.dbg & 1)) {
+        if (p.dbg & 0x80) {
+          // experiment: sample digit before weight digit (consecutive MMAs share their B operand)
+#pragma unroll
+          for (int ks = 0; ks < KBAND / 32; ++ks) {
+#pragma unroll
+            for (int s = 0; s < GD; ++s) {
+              const uint64_t b_desc =
+                  smem_desc(b_base + (s * 2 + ks / 4) * P2_PANEL_BYTES + (ks % 4) * 32, 16, 1024, LAYOUT_SW128);
+#pragma unroll
+              for (int d = 0; d < WD; ++d) {
+                const int j = d + s;
+                if (j < JMIN) continue;
+                const int s_first = j - (WD - 1) > 0 ? j - (WD - 1) : 0;  // the first product that lands in accumulator j
+                mma_u8_ts(tm + TMEM_ACC0 + (j - JMIN) * P2_NR, tm + d * TMEM_BAND_COLS_PER_DIGIT + ks * 8, b_desc, idesc,
+                          (ks == 0 && s == s_first) ? 0u : 1u);
+              }
+            }
+          }
+        } else if (!(p.dbg & 1)) {
           // K step outermost, then weight digit, then sample digit: consecutive MMAs go to different accumulators
 #pragma unroll
           for (int ks = 0; ks < KBAND / 32; ++ks) {
@@ -925,11 +943,11 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       double res[RPT];
 #pragma unroll
       for (int n = 0; n < RPT; ++n) {
-        // sum_a acc_a * 256^a, a = 0..5, pairwise: every pair fits 34 bits, the total 61
-        static_assert(NACC2 == 6, "the combine below is written for six accumulators");
+        // sum_a acc_a * 256^a, a = 0 .. NACC2 - 1, pairwise: every pair fits 34 bits, the total 61
+        static_assert(NACC2 == 5 || NACC2 == 6, "the combine below is written for five or six accumulators");
         const uint64_t p01 = (uint64_t)v[1][n] * 256u + v[0][n];
         const uint64_t p23 = (uint64_t)v[3][n] * 256u + v[2][n];
-        const uint64_t p45 = (uint64_t)v[5][n] * 256u + v[4][n];
+        const uint64_t p45 = NACC2 == 6 ? (uint64_t)v[NACC2 - 1][n] * 256u + v[4][n] : (uint64_t)v[4][n];
         uint64_t tot = (uint64_t)(uint32_t)p23 * 65536u + p01;
         tot += ((uint64_t)((uint32_t)(p23 >> 32) << 16) + (uint32_t)p45) << 32;
         res[n] = (double)tot;
@@ -1195,8 +1213,9 @@ struct amt_tcg {
   std::vector<uint64_t>* W;  // W[t], t = 0..r (symmetric)
   uint8_t* band;             // device [WD][128][256]
   uint64_t* suffix;          // device [HALO + 2]
-  double* suffix_f;          // device [HALO + 2]: suffix * 2^-16
+  double* suffix_f;          // device [HALO + 2]: suffix * 2^-(8 JMIN)
   double weight_l1_error;    // sum over the taps of |W[t] * 2^-S - w[t]|
+  double dropped_bound;      // largest sum of the digit products pass 2 drops, on the [0, 1] scale of a uint16 image
 };
 
 namespace amt {
@@ -1282,7 +1301,7 @@ int tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double 
   p.minmax = minmax;
   p.band = g->band;
   p.suffix_f = g->suffix_f;
-  p.scale = std::ldexp(in_scale, -(g->S + 8));
+  p.scale = std::ldexp(in_scale, -(g->S + 24 - 8 * JMIN));
   p.h = (int)h;
   p.w = (int)w;
   p.r = g->r;
@@ -1401,6 +1420,14 @@ int amt_tcg_create(const double* half_w_host, int radius, int device, amt_tcg** 
   g->W = new std::vector<uint64_t>(W);
   for (int t = 0; t <= radius; ++t)
     g->weight_l1_error += (t == 0 ? 1.0 : 2.0) * std::fabs(std::ldexp((double)W[t], -S) - half_w_host[t]);
+  // pass 2 leaves out the products (weight digit d) x (sample digit s) with d + s < JMIN: at most
+  // sum_{d + s < JMIN} 256^(d + s) * 255 * sum_t digit_d(W[t]) units of 2^-(S + 24) / 65535
+  for (int d = 0; d < WD; ++d) {
+    double l1 = 0.0;
+    for (int t = 0; t <= radius; ++t) l1 += (t == 0 ? 1.0 : 2.0) * (double)((W[t] >> (8 * d)) & 0xff);
+    for (int sd = 0; sd < GD; ++sd)
+      if (d + sd < JMIN) g->dropped_bound += std::ldexp(255.0 * l1, 8 * (d + sd) - (S + 24)) / 65535.0;
+  }
   std::vector<uint8_t> band((size_t)WD * MT * KBAND, 0);
   for (int d = 0; d < WD; ++d)
     for (int m = 0; m < MT; ++m)
@@ -1411,7 +1438,7 @@ int amt_tcg_create(const double* half_w_host, int radius, int device, amt_tcg** 
   std::vector<uint64_t> suffix(HALO + 2, 0);  // zero beyond the radius
   std::vector<double> suffix_f(HALO + 2, 0.0);
   for (int j = radius; j >= 0; --j) suffix[j] = suffix[j + 1] + W[j];
-  for (int j = 0; j <= HALO + 1; ++j) suffix_f[j] = std::ldexp((double)suffix[j], -16);
+  for (int j = 0; j <= HALO + 1; ++j) suffix_f[j] = std::ldexp((double)suffix[j], -8 * JMIN);
   auto fail = [&](int s) {
     amt_tcg_destroy(g);
     return s;
@@ -1449,12 +1476,12 @@ int amt_tcg_weights(const amt_tcg* g, uint64_t* w_host, int* scale_bits) {
  * passes, G = the float64 Gaussian in scipy's operation order.  Terms (X = 1 bounds the scaled samples):
  *   weights rounded to integers, both passes        2 * sum_t |W[t] 2^-S - w[t]|
  *   pass-1 result rounded to 40 bits                 2^-41 (half a unit of 2^-24 / 65535 per sample, times weights summing to 1)
- *   digit products dropped in pass 2 (d + s < 2)     2^-45
+ *   digit products dropped in pass 2 (d + s < 3)     sum of 256^(d+s) * 255 * |digit d of W|_1, scaled: 9e-12 for sigma = 16
  *   float64 roundings of scipy's 2 x (2 r + 2) operations and of the final conversion / scaling: < 1e-13
  * plus a 1 % margin. */
 double amt_tcg_error_bound(const amt_tcg* g) {
   if (!g) return -1.0;
-  return 1.01 * (2.0 * g->weight_l1_error + std::ldexp(1.0, -41) + std::ldexp(1.0, -45) + 1e-13);
+  return 1.01 * (2.0 * g->weight_l1_error + std::ldexp(1.0, -41) + g->dropped_bound + 1e-13);
 }
 
 int amt_tcg_supported(int64_t h, int64_t w, int radius) {

@@ -14,7 +14,7 @@ from __future__ import annotations
 import numpy as np
 
 GD = 5      # digits (base 256) of the axis-0 result
-JMIN = 2    # digit products of significance below 256**JMIN are dropped in the axis-1 pass
+JMIN = 3    # digit products of significance below 256**JMIN are dropped in the axis-1 pass
 
 
 def full_kernel(w_half: np.ndarray) -> np.ndarray:
@@ -62,7 +62,7 @@ def axis1_float(g1q: np.ndarray, w_half: np.ndarray, scale_bits: int, in_scale: 
     suffix = np.zeros(r + 2, dtype=np.uint64)
     for j in range(r, -1, -1):
         suffix[j] = suffix[j + 1] + np.uint64(w_half[j])
-    suffix_f = np.ldexp(suffix.astype(np.float64), -16)
+    suffix_f = np.ldexp(suffix.astype(np.float64), -8 * JMIN)
     xs = np.arange(w)
     f_l = np.where(xs < r, suffix_f[np.minimum(xs + 1, r + 1)], 0.0)
     f_r = np.where(xs >= w - r, suffix_f[np.clip(w - xs, 0, r + 1)], 0.0)
@@ -71,4 +71,4 @@ def axis1_float(g1q: np.ndarray, w_half: np.ndarray, scale_bits: int, in_scale: 
     edge = (f_l[None, :] * e_l + f_r[None, :] * e_r)
     # the kernel adds the edge term only in tiles that touch an edge; adding 0.0 elsewhere is the same number
     g = g + edge
-    return g * np.ldexp(np.float64(in_scale), -(scale_bits + 8))
+    return g * np.ldexp(np.float64(in_scale), -(scale_bits + 24 - 8 * JMIN))

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Round 2, step 24+: the fused pass 2 with 14 instead of 17 digit products per K step (JMIN = 3), decomposed with the
+tcg_debug switches (1 = no MMAs, 2 = no epilogue arithmetic / stores, 32 = no narrow-Gaussian arithmetic, 0x80 =
+sample digit before weight digit in the MMA order), bit-checked against the two-kernel route, then the executor.
+One JSON line."""
+
+from __future__ import annotations
+
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from arcadia_microscopy_tools_b200 import _gpu, _lib  # noqa: E402
+from arcadia_microscopy_tools_b200.batch import FovBatchExecutor, FovPipelineConfig  # noqa: E402
+
+C, H, W = 4, 2048, 2048
+SCALE = 1.0 / 65535.0
+
+
+def timed(fn, steps=8, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def main():
+    n_fov = 64
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    fovs, given, max_label = bench.build_device_batch(n_fov, 4, dev)
+    planes = 8 * C
+    x = fovs[:8].reshape(planes, H, W)
+    tcg = _gpu.TensorCoreGaussian(16.0)
+    hw_lo = _gpu.gaussian_half_weights(0.6)
+    d_lo = torch.from_numpy(hw_lo).to(dev)
+    digits = torch.empty((planes, 5, H, W), dtype=torch.uint8, device=dev)
+    out = torch.empty((planes, H, W), dtype=torch.float64, device=dev)
+    buckets = torch.empty((planes, H, W), dtype=torch.int16, device=dev)
+    mm = torch.empty((planes, 2), dtype=torch.int64, device=dev)
+    st = _gpu.stream_ptr()
+    p = _gpu.ptr
+    res = {"error_bound": float(lib.amt_tcg_error_bound(tcg.handle))}
+
+    def a0():
+        _lib.check(lib.amt_tcg_axis0(tcg.handle, p(x), planes, H, W, p(digits), 0, 0, st))
+
+    def a1():
+        _lib.check(lib.amt_tcg_axis1_dog(tcg.handle, p(digits), p(x), p(d_lo), len(hw_lo) - 1, SCALE, p(out), planes, H, W,
+                                         p(buckets), p(mm), 0, 0, st))
+
+    res["axis0_ms"] = timed(a0)
+    # the fused kernel against the two-kernel route (small: 4 planes), default order and the 0x80 order
+    lo = _gpu.gauss_lo2d(x[:4], SCALE, 0.6)
+    want, mm_w, bk_w = tcg.axis1(digits[:4], lo, SCALE, want_buckets=True)
+    for mask in (0, 0x80):
+        _lib.check(lib.amt_tune(b"tcg_debug", mask))
+        got, mm_g, bk_g = tcg.axis1_dog(digits[:4], x[:4], 0.6, SCALE, want_buckets=True)
+        torch.cuda.synchronize()
+        res[f"fused_equals_two_kernel_dbg{mask}"] = bool(torch.equal(want, got) and torch.equal(bk_w, bk_g) and torch.equal(mm_w, mm_g))
+    dec = {}
+    for mask in (0, 0x80, 1, 32, 33, 2, 34, 3, 35, 0):
+        _lib.check(lib.amt_tune(b"tcg_debug", mask))
+        dec.setdefault(f"dbg{mask}", []).append(round(timed(a1), 4))
+    _lib.check(lib.amt_tune(b"tcg_debug", 0))
+    res["fused_axis1_ms"] = dec
+    cfg = FovPipelineConfig(n_channels=C, height=H, width=W, seg_channel=1, chunk_fovs=32, max_labels=4096,
+                            max_label_value=max_label)
+    with FovBatchExecutor(cfg, device=0) as ex:
+        o = ex.alloc_outputs(n_fov)
+        for mask in (0, 0x80, 0):
+            _lib.check(lib.amt_tune(b"tcg_debug", mask))
+            for _ in range(2):
+                ex.run_device(fovs, given, o, sync=True)
+            ms = [ex.run_device(fovs, given, o, sync=True) for _ in range(5)]
+            res.setdefault(f"executor_dbg{mask}", []).append({
+                "ms_per_8_fov": float(np.median(ms)) / (n_fov / 8),
+                "gpix_s": n_fov * C * H * W / (float(np.median(ms)) * 1e-3) / 1e9,
+                "counts_thr_sum": int(o["counts_thr"].sum()), "thr_sum": float(o["thresholds"].sum())})
+        _lib.check(lib.amt_tune(b"tcg_debug", 0))
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
