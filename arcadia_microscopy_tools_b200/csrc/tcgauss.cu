@@ -205,6 +205,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// d = a * b + c with a 64-bit sum (IMAD.WIDE.U32).  The epilogues call it with b = a power of two held in a register
+// the compiler cannot see through (opaque_u32): written as shifts, ptxas spends four or five instructions on every
+// 64-bit term (SHF / IMAD.HI / IADD3 / IADD3.X) and the integer combine was a third of both epilogues.
+__device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) {
+  uint64_t d;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+
 // Shared-memory matrix descriptor (sm_100 format: version 1 in bits 46-47; offsets in 16-byte units)
 constexpr uint32_t LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -392,6 +406,7 @@ tcg_axis0_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
     const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + TMEM_ACC0 + hcol * 32;
     const uint32_t half = 1u << (p.shift - 1);
     uint8_t* my_row = out_s + m * 128;
+    const uint32_t c8 = opaque_u32(1u << 8), c16 = opaque_u32(1u << 16), c24 = opaque_u32(1u << 24);
     int it = 0;
     for (int u = 0; u < n_units; ++u, tw.next()) {
       const int plane = p.sel.phys(tw.q);
@@ -421,8 +436,7 @@ tcg_axis0_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->acc_empty);  // the MMAs of the next tile may overwrite the accumulators now
-        if (k == 0 && u > 0) {
-          // the staging tile is free once the previous unit's TMA stores have READ it
+        if ((p.dbg & 2) && k == 0 && u > 0) {
           if (warp == 2 && lane == 0) tma_store_wait_read();
           epi_barrier();
         }
@@ -430,17 +444,14 @@ tcg_axis0_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
 
         const int x0 = (xg * P1_GROUP + k) * (P1_NB / 2) + hcol * 16;  // first of this thread's 16 pixels
         // 53-bit sums, rounded to 40 bits: g = (sum_d 256^d (lo_d + 256 hi_d) + half) >> shift
+        //   = lo_0 + half + 2^8 (lo_1 + hi_0) + 2^16 (lo_2 + hi_1) + 2^24 (lo_3 + hi_2) + 2^32 hi_3, every part < 2^24
         uint32_t glo[16], ghi[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const uint32_t a0 = v[0][2 * i + 1] * 256u + v[0][2 * i] + half;  // < 2^32: the parts are < 2^23
-          const uint32_t a1 = v[1][2 * i + 1] * 256u + v[1][2 * i];
-          const uint32_t a2 = v[2][2 * i + 1] * 256u + v[2][2 * i];
-          const uint32_t a3 = v[3][2 * i + 1] * 256u + v[3][2 * i];
-          const uint64_t t01 = (uint64_t)a1 * 256u + a0;
-          const uint64_t t23 = (uint64_t)a3 * 256u + a2;
-          uint64_t tot = (uint64_t)(uint32_t)t23 * 65536u + t01;
-          tot += (uint64_t)((uint32_t)(t23 >> 32) << 16) << 32;
+          uint64_t tot = mad_wide(v[1][2 * i] + v[0][2 * i + 1], c8, 0ull);
+          tot = mad_wide(v[2][2 * i] + v[1][2 * i + 1], c16, tot);
+          tot = mad_wide(v[3][2 * i] + v[2][2 * i + 1], c24, tot);
+          tot += ((uint64_t)v[3][2 * i + 1] << 32) | (uint64_t)(v[0][2 * i] + half);
           glo[i] = (uint32_t)tot, ghi[i] = (uint32_t)(tot >> 32);
         }
         // clamped-edge taps (mode='nearest'): rows above 0 / below h-1 all read the edge row.  Only the first and
@@ -481,6 +492,12 @@ tcg_axis0_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
           dig[4][g4] = __byte_perm(__byte_perm(hb[0], hb[1], 0x0040), __byte_perm(hb[2], hb[3], 0x0040), 0x5410);
         }
         if ((p.dbg & 8) && (dig[0][0] ^ dig[1][1] ^ dig[2][2] ^ dig[3][3] ^ dig[4][0]) != 0x9e3779b9u) continue;  // timing: no stores
+        if (k == 0 && u > 0) {
+          // the staging tile is free once the previous unit's TMA stores have READ it: waited for here, behind the
+          // arithmetic of the unit's first tile, not in front of it (the epilogue warps spent 15 % of their time there)
+          if (warp == 2 && lane == 0) tma_store_wait_read();
+          epi_barrier();
+        }
         // 16 bytes per digit plane into the staging tile: chunk c of row m sits at chunk position c ^ (m & 7)
         uint8_t* dst = my_row + (((k * 2 + hcol) ^ (m & 7)) << 4);
 #pragma unroll
@@ -798,14 +815,10 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
                                 vs + ((hrow * RPT) * P2F_V_W + mx + LO_HALO) * 8);
       lo_axis0_run<RT, RPT / 2>(rt + (mx + P2F_RAW_HX) * 2, y0 + RPT / 2, gy0, p.h, yedge, p.in_scale, wt,
                                 vs + ((hrow * RPT + RPT / 2) * P2F_V_W + mx + LO_HALO) * 8);
-      for (int v = lw * 32 + lane; v < 2 * RT * P2_NR; v += EW * 32) {
-        const int hc = v >> 5, row = v & 31;
-        const int c = hc < RT ? hc - RT : MT + (hc - RT);
-        lo_axis0_run<RT, 1>(rt + (c + P2F_RAW_HX) * 2, ty * P2_NR + row, gy0, p.h, yedge, p.in_scale, wt,
-                            vs + (row * P2F_V_W + c + LO_HALO) * 8);
       }
-      }
-      asm volatile("bar.sync 3, %0;" ::"n"(EW * 32) : "memory");  // every column of the axis-0 results is in place
+      // every column of the axis-0 results is in place: this warp's, the other lo warps' and the halo columns, which
+      // the two halo warps of warpgroup 0 compute
+      asm volatile("bar.sync 3, %0;" ::"n"((EW + 2) * 32) : "memory");
       if (lane == 0) mbar_arrive(&bars->empty[stage]);            // raw tile used up (bar.sync ordered the warp's reads)
       if (++stage == P2_STAGES) stage = 0, phase ^= 1;
       // axis 1, ROW-partitioned: warp lw owns rows 4 lw .. 4 lw + 3 of the tile, lane l the columns l, l + 32, l + 64,
@@ -821,6 +834,40 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
         lo_axis1_rows<RT, false>(vs, lw, lane, tx * MT, p.w, wt);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->lo_full[b]);
+    }
+  };
+  auto halo_warps = [&]() {
+    // ---- warps 2 and 3 of warpgroup 0: axis 0 of the narrow Gaussian for the 2 RT columns left and right of the tile
+    // (2 RT x 32 single results per tile, two per thread).  On the lo warps this was a latency chain for one result
+    // per thread in front of their barrier, with half of them idle.
+    const int t = (warp - 2) * 32 + lane;
+    double wt[RT + 1];
+#pragma unroll
+    for (int j = 0; j <= RT; ++j) wt[j] = j <= p.r_lo ? __ldg(p.hw_lo + j) : 0.0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < n_tiles; ++it, tw.next()) {
+      const int tx = tw.fast, ty = tw.slow;
+      (void)tx;
+      const int b = it & 1;
+      mbar_wait(&bars->full[stage], phase);
+      mbar_wait(&bars->lo_empty[b], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      const uint32_t rt = smem_u32(stage_s + stage * STAGE_BYTES + P2_DIG_BYTES);
+      const uint32_t vs = smem_u32(vbuf + (size_t)b * (P2F_V_BYTES / 8));
+      const int gy0 = ty * P2_NR - LO_HALO;
+      const bool yedge = gy0 + LO_HALO - RT < 0 || gy0 + LO_HALO + P2_NR + RT > p.h;  // warp-uniform
+      if (!(p.dbg & 32)) {
+        for (int v = t; v < 2 * RT * P2_NR; v += 64) {
+          const int hc = v >> 5, row = v & 31;
+          const int c = hc < RT ? hc - RT : MT + (hc - RT);
+          lo_axis0_run<RT, 1>(rt + (c + P2F_RAW_HX) * 2, ty * P2_NR + row, gy0, p.h, yedge, p.in_scale, wt,
+                              vs + (row * P2F_V_W + c + LO_HALO) * 8);
+        }
+      }
+      // a blocking barrier, not bar.arrive: a halo warp that ran a tile ahead would add its arrivals to the barrier
+      // generation the lo warps have not completed yet
+      asm volatile("bar.sync 3, %0;" ::"n"((EW + 2) * 32) : "memory");
+      if (++stage == P2_STAGES) stage = 0, phase ^= 1;
     }
   };
   auto epilogue = [&]() {
@@ -839,6 +886,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
     double wt[RT + 1];
 #pragma unroll
     for (int j = 0; j <= RT; ++j) wt[j] = (FUSED && j <= p.r_lo) ? __ldg(p.hw_lo + j) : 0.0;
+    const uint32_t c8 = opaque_u32(1u << 8), c16 = opaque_u32(1u << 16), c24 = opaque_u32(1u << 24);
     auto flush = [&]() {
       if (p.minmax != nullptr && plane >= 0) {
         const uint64_t a = warp_min_u64(f64_to_key(vmin)), b = warp_max_u64(f64_to_key(vmax));
@@ -943,13 +991,13 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       double res[RPT];
 #pragma unroll
       for (int n = 0; n < RPT; ++n) {
-        // sum_a acc_a * 256^a, a = 0 .. NACC2 - 1, pairwise: every pair fits 34 bits, the total 61
-        static_assert(NACC2 == 5 || NACC2 == 6, "the combine below is written for five or six accumulators");
-        const uint64_t p01 = (uint64_t)v[1][n] * 256u + v[0][n];
-        const uint64_t p23 = (uint64_t)v[3][n] * 256u + v[2][n];
-        const uint64_t p45 = NACC2 == 6 ? (uint64_t)v[NACC2 - 1][n] * 256u + v[4][n] : (uint64_t)v[4][n];
-        uint64_t tot = (uint64_t)(uint32_t)p23 * 65536u + p01;
-        tot += ((uint64_t)((uint32_t)(p23 >> 32) << 16) + (uint32_t)p45) << 32;
+        // sum_a acc_a * 256^a, a = 0 .. 4 (every accumulator < 2^27, the total < 2^60): three IMAD.WIDE and one
+        // 64-bit addition of (acc_4 : acc_0)
+        static_assert(NACC2 == 5, "the combine below is written for five accumulators");
+        uint64_t tot = mad_wide(v[1][n], c8, 0ull);
+        tot = mad_wide(v[2][n], c16, tot);
+        tot = mad_wide(v[3][n], c24, tot);
+        tot += ((uint64_t)v[4][n] << 32) | (uint64_t)v[0][n];
         res[n] = (double)tot;
       }
       if (edge_tile) {  // warp-uniform
@@ -1034,11 +1082,12 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
   };
   if constexpr (WS) {  // registers follow the roles: every warp of a warpgroup re-allocates at the top of its branch
     if (warp < 4) {
-      reg_dec<32>();
+      reg_dec<48>();
       if (warp == 0) producer();
       else if (warp == 1) mma_issuer();
+      else if (RT > 0) halo_warps();
     } else if (warp < 4 + EW) {
-      reg_inc<160>();
+      reg_inc<152>();
       epilogue();
     } else {
       reg_dec<64>();
