@@ -44,6 +44,10 @@
 
 #include "internal.cuh"
 
+#ifndef AMT_TCG_SUSPEND_NS
+#define AMT_TCG_SUSPEND_NS 20000
+#endif
+
 namespace amt {
 namespace tc {
 
@@ -58,7 +62,8 @@ constexpr int P1_NB = 64;        // pass 1: bytes (UMMA N) per tile along the co
 constexpr int P1_STAGES = 8;
 constexpr int P1_GROUP = 4;      // x tiles per work unit: their 4 x 32 pixels leave as 128-byte rows through one staging tile
 constexpr int P2_NR = 32;        // pass 2: rows (UMMA N) per tile
-constexpr int P2_STAGES = 3;
+constexpr int P2_STAGES = 3;        // pass 2 reading the narrow Gaussian from memory: three 72 KB stages
+constexpr int P2F_STAGES = 2;       // fused pass 2: two 52 KB stages (three measured 2 % slower: 0.732 against 0.717 ms per 32 planes)
 constexpr int EPI_WARPS = 8;
 constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
 constexpr int MAX_STAGES = 8;
@@ -96,14 +101,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// The wait may suspend the thread in hardware for up to this long before it reports "not yet" (it wakes when the phase
+// completes): without the hint a waiting warp polls every ~30 ns, and ten of a CTA's twenty warps are waiting at any
+// time -- on a part that runs these kernels AT ITS POWER CAP (scripts/power_probe.py) polling costs clock.
+constexpr uint32_t kSuspendHintNs = AMT_TCG_SUSPEND_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }
@@ -686,10 +695,11 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* stage_s = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr bool FUSED = RT > 0;
+  constexpr int NSTAGE = FUSED ? P2F_STAGES : P2_STAGES;
   constexpr uint32_t STAGE_BYTES = FUSED ? P2F_STAGE_BYTES : P2_STAGE_BYTES;
   constexpr uint32_t LO_TX_BYTES = FUSED ? P2F_RAW_BYTES : P2_LO_BYTES;
-  double* const vbuf = reinterpret_cast<double*>(stage_s + P2_STAGES * STAGE_BYTES);  // FUSED: two axis-0 result tiles
-  Barriers* bars = reinterpret_cast<Barriers*>(stage_s + P2_STAGES * STAGE_BYTES + (FUSED ? 2 * P2F_V_BYTES : 0));
+  double* const vbuf = reinterpret_cast<double*>(stage_s + NSTAGE * STAGE_BYTES);  // FUSED: two axis-0 result tiles
+  Barriers* bars = reinterpret_cast<Barriers*>(stage_s + NSTAGE * STAGE_BYTES + (FUSED ? 2 * P2F_V_BYTES : 0));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int64_t tiles_total = (int64_t)p.n_sel * p.tiles_y * p.tiles_x;
@@ -700,7 +710,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
 
   // a stage is free again once the MMAs have read its digit panels AND the epilogue warps its narrow-Gaussian tile
   constexpr int RPT = P2_NR / (EW / 4);  // rows per epilogue thread
-  const uint32_t tmem = tcg_setup(bars, p.band, P2_STAGES, 1 + EW, nullptr, p.suffix_f, EW);
+  const uint32_t tmem = tcg_setup(bars, p.band, NSTAGE, 1 + EW, nullptr, p.suffix_f, EW);
   // x fastest: consecutive tiles of a CTA share half their columns
   TileWalk tw;
   tw.init(t_begin, p.tiles_y, p.tiles_x);
@@ -729,7 +739,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
           tma_load_3d(dst + P2_DIG_BYTES, &lo_map, &bars->full[stage], tw.fast * MT, tw.slow * P2_NR, plane);
       }
       __syncwarp();
-      if (++stage == P2_STAGES) stage = 0, phase ^= 1;
+      if (++stage == NSTAGE) stage = 0, phase ^= 1;
     }
   };
   auto mma_issuer = [&]() {
@@ -784,7 +794,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
         mma_commit(&bars->acc_full);
       }
       __syncwarp();
-      if (++stage == P2_STAGES) stage = 0, phase ^= 1;
+      if (++stage == NSTAGE) stage = 0, phase ^= 1;
     }
   };
   auto lo_warps = [&]() {
@@ -820,7 +830,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       // the two halo warps of warpgroup 0 compute
       asm volatile("bar.sync 3, %0;" ::"n"((EW + 2) * 32) : "memory");
       if (lane == 0) mbar_arrive(&bars->empty[stage]);            // raw tile used up (bar.sync ordered the warp's reads)
-      if (++stage == P2_STAGES) stage = 0, phase ^= 1;
+      if (++stage == NSTAGE) stage = 0, phase ^= 1;
       // axis 1, ROW-partitioned: warp lw owns rows 4 lw .. 4 lw + 3 of the tile, lane l the columns l, l + 32, l + 64,
       // l + 96.  Every read and the in-place write of a row then happen inside one warp (reads, __syncwarp, writes): no
       // second CTA-level barrier, and two rows = eight independent float64 chains are in flight per thread.
@@ -867,7 +877,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       // a blocking barrier, not bar.arrive: a halo warp that ran a tile ahead would add its arrivals to the barrier
       // generation the lo warps have not completed yet
       asm volatile("bar.sync 3, %0;" ::"n"((EW + 2) * 32) : "memory");
-      if (++stage == P2_STAGES) stage = 0, phase ^= 1;
+      if (++stage == NSTAGE) stage = 0, phase ^= 1;
     }
   };
   auto epilogue = [&]() {
@@ -938,7 +948,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(stage_empty);  // the raw tile is used up; the digit panels go back with the MMAs' commit
       }
-      if (++stage == P2_STAGES) stage = 0, phase ^= 1;
+      if (++stage == NSTAGE) stage = 0, phase ^= 1;
       // clamped-edge taps: columns left of 0 / right of w-1 all read the edge column of the same row
       const bool edge_tile = tx * MT < p.r || tx * MT + MT > p.w - p.r;  // warp-uniform
       double f_l = 0.0, f_r = 0.0, e_l = 0.0, e_r = 0.0;
@@ -1050,7 +1060,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(stage_empty);
       }
-      if (x_ok && rows > 0) {
+      if (x_ok && rows > 0 && !((p.dbg & 8) && res[0] + res[RPT - 1] + res[RPT / 2] != 0.123456)) {  // dbg 8: timing without the stores
         double* op = p.out + (int64_t)plane * hw + (int64_t)y0 * p.w + x;
         uint16_t* bp = p.buckets != nullptr ? p.buckets + (int64_t)plane * hw + (int64_t)y0 * p.w + x : nullptr;
         if (rows == RPT) {  // the whole run lies inside the plane: no per-row tests
@@ -1273,7 +1283,7 @@ namespace tc {
 int g_tcg_debug = 0;  // amt_tune "tcg_debug"
 constexpr size_t P1_SMEM = 1024 + P1_STAGES * P1_STAGE_BYTES + P1_OUT_BYTES + sizeof(Barriers);
 constexpr size_t P2_SMEM = 1024 + P2_STAGES * P2_STAGE_BYTES + sizeof(Barriers);
-constexpr size_t P2F_SMEM = 1024 + P2_STAGES * P2F_STAGE_BYTES + 2 * P2F_V_BYTES + sizeof(Barriers);
+constexpr size_t P2F_SMEM = 1024 + P2F_STAGES * P2F_STAGE_BYTES + 2 * P2F_V_BYTES + sizeof(Barriers);
 static_assert(P2F_SMEM <= 227 * 1024, "fused pass 2 exceeds the shared memory of an SM");
 
 bool tcg_shape_ok(int64_t h, int64_t w) { return h >= 128 && w >= 128 && w % 16 == 0 && h * w < (1ll << 31); }

@@ -73,7 +73,7 @@ def main():
         torch.cuda.synchronize()
         res[f"fused_equals_two_kernel_dbg{mask}"] = bool(torch.equal(want, got) and torch.equal(bk_w, bk_g) and torch.equal(mm_w, mm_g))
     dec = {}
-    for mask in (0, 0x80, 1, 32, 33, 2, 34, 3, 35, 0):
+    for mask in (0, 4, 36, 5, 8, 0x80, 1, 32, 33, 2, 34, 3, 35, 0):
         _lib.check(lib.amt_tune(b"tcg_debug", mask))
         dec.setdefault(f"dbg{mask}", []).append(round(timed(a1), 4))
     _lib.check(lib.amt_tune(b"tcg_debug", 0))
