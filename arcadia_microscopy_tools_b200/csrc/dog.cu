@@ -413,7 +413,7 @@ extern int g_dx_collect_threads;  // decide.cu
 extern int g_exec_host_narrow, g_exec_host_threads, g_exec_host_rle, g_exec_rle_share;
 extern int g_exec_copy_only;  // executor.cu
 static int g_dog_only_exact = 0;  // amt_tune: the stand-alone axis0 / axis1 entry points cover the exact planes only
-namespace tc { extern int g_tcg_debug; }  // tcgauss.cu
+namespace tc { extern int g_tcg_debug; int set_suspend_ns(int ns); }  // tcgauss.cu
 
 constexpr size_t kSmemMax = 227 * 1024;
 constexpr size_t kSmemPerSM = 228 * 1024;
@@ -586,6 +586,8 @@ int amt_tune(const char* key, int value) {
     g_stream_ctas = value;
   } else if (is("exec_buckets")) {
     g_exec_buckets = value != 0;
+  } else if (is("tcg_suspend_ns")) {
+    return tc::set_suspend_ns(value);
   } else if (is("tcg_debug")) {
     tc::g_tcg_debug = value;
   } else if (is("dx_collect_threads")) {

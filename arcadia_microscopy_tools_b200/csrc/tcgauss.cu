@@ -101,26 +101,46 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// The wait may suspend the thread in hardware for up to this long before it reports "not yet" (it wakes when the phase
-// completes): without the hint a waiting warp polls every ~30 ns, and ten of a CTA's twenty warps are waiting at any
-// time -- on a part that runs these kernels AT ITS POWER CAP (scripts/power_probe.py) polling costs clock.
-constexpr uint32_t kSuspendHintNs = AMT_TCG_SUSPEND_NS;
+// A waiting warp may sleep in hardware: with a suspend-time hint `mbarrier.try_wait` holds the thread for up to that
+// long (it wakes when the phase completes); without it a waiting warp polls every ~30 ns, and ten of a CTA's twenty
+// warps are waiting at any time -- on a part that runs these kernels AT ITS POWER CAP (scripts/power_probe.py) polling
+// costs clock.  amt_tune("tcg_suspend_ns", 0) switches the hint off (A/B measurements).
+__constant__ uint32_t c_suspend_ns = AMT_TCG_SUSPEND_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
       : "memory");
   return ok != 0;
 }
 // Every wait carries a watchdog: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+// By the clock, not by a spin count: with the hint one iteration lasts anything from 30 ns to 20 us.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  const uint32_t ns = c_suspend_ns;
+  const uint64_t t0 = global_timer_ns();
+  while (!(ns ? mbar_try_wait_hint(bar, parity, ns) : mbar_try_wait(bar, parity))) {
+    if (global_timer_ns() - t0 > 4000000000ull) __trap();  // 4 s
   }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -753,25 +773,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
       tc_fence_after();
       const uint32_t b_base = smem_u32(stage_s + stage * STAGE_BYTES);
       if (elect_one()) {
-        if (p.dbg & 0x80) {
-          // experiment: sample digit before weight digit (consecutive MMAs share their B operand)
-#pragma unroll
-          for (int ks = 0; ks < KBAND / 32; ++ks) {
-#pragma unroll
-            for (int s = 0; s < GD; ++s) {
-              const uint64_t b_desc =
-                  smem_desc(b_base + (s * 2 + ks / 4) * P2_PANEL_BYTES + (ks % 4) * 32, 16, 1024, LAYOUT_SW128);
-#pragma unroll
-              for (int d = 0; d < WD; ++d) {
-                const int j = d + s;
-                if (j < JMIN) continue;
-                const int s_first = j - (WD - 1) > 0 ? j - (WD - 1) : 0;  // the first product that lands in accumulator j
-                mma_u8_ts(tm + TMEM_ACC0 + (j - JMIN) * P2_NR, tm + d * TMEM_BAND_COLS_PER_DIGIT + ks * 8, b_desc, idesc,
-                          (ks == 0 && s == s_first) ? 0u : 1u);
-              }
-            }
-          }
-        } else if (!(p.dbg & 1)) {
+        if (!(p.dbg & 1)) {
           // K step outermost, then weight digit, then sample digit: consecutive MMAs go to different accumulators
 #pragma unroll
           for (int ks = 0; ks < KBAND / 32; ++ks) {
@@ -1281,6 +1283,10 @@ namespace amt {
 namespace tc {
 
 int g_tcg_debug = 0;  // amt_tune "tcg_debug"
+int set_suspend_ns(int ns) {  // amt_tune "tcg_suspend_ns"
+  const uint32_t v = ns < 0 ? 0u : (uint32_t)ns;
+  return cudaMemcpyToSymbol(c_suspend_ns, &v, sizeof(v)) == cudaSuccess ? AMT_OK : AMT_ERR_CUDA;
+}
 constexpr size_t P1_SMEM = 1024 + P1_STAGES * P1_STAGE_BYTES + P1_OUT_BYTES + sizeof(Barriers);
 constexpr size_t P2_SMEM = 1024 + P2_STAGES * P2_STAGE_BYTES + sizeof(Barriers);
 constexpr size_t P2F_SMEM = 1024 + P2F_STAGES * P2F_STAGE_BYTES + 2 * P2F_V_BYTES + sizeof(Barriers);

@@ -149,7 +149,9 @@ int amt_gauss_lo2d(const uint16_t* in, double in_scale, double* out, int64_t n_i
  * to the HBM-bound kernels of the other stream), 0 = as many as fit; "dog_generic" 1 = force
  * the generic tile kernels; "dog_fma" 1 = contract the DoG's multiply-adds (2 instead of 3 DP
  * instructions per tap pair; the filtered planes then differ from scipy's in the last bits: opt-in,
- * off by default). */
+ * off by default); "tcg_debug" switches parts of the tensor-core Gaussian off for timing experiments
+ * (csrc/tcgauss.cu); "tcg_suspend_ns" = suspend-time hint of the tensor-core kernels' mbarrier waits (default 20000;
+ * 0 = plain polling). */
 int amt_tune(const char* key, int value);
 
 /* Pinned host staging without torch (ref: nikon.py:25-43 / leica.py:52-80 decode into host arrays; the
