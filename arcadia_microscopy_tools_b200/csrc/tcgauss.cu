@@ -10,7 +10,7 @@
 // evaluated EXACTLY in integers on tcgen05.mma kind::i8:
 //   * the weights are integers W[t] = round(w[t] * 2^S) (S = 37 for sigma = 16: 32 significant bits,
 //     sum_t W[t] == 2^S exactly) cut into four unsigned base-256 digits -> four uint8 band tiles
-//     [128 outputs x 256 inputs], resident in shared memory for the life of a persistent CTA;
+//     [128 outputs x 256 inputs], resident in TENSOR MEMORY (the A operand) for the life of a persistent CTA;
 //   * pass 1 (image axis 0): the raw uint16 image is read BY TMA AS BYTES.  A tile of 256 rows x 64
 //     bytes (32 pixels, low and high byte interleaved) is the MN-major B operand as it lies in memory;
 //     the low / high byte columns come out as neighbouring accumulator columns and are recombined in
@@ -19,20 +19,23 @@
 //     clamped-edge ('nearest') taps, rounds to 40 bits and stores five uint8 digit planes;
 //   * pass 2 (image axis 1): the five digit planes are the K-major B operand, again straight from TMA;
 //     weight digit d x sample digit s accumulates into the TMEM accumulator of d + s (products of equal
-//     significance share one accumulator; d + s < 3 is at most 1.1e-11 of full scale and skipped): 14 digit
+//     significance share one accumulator; d + s < 3 is at most 5.2e-12 of full scale and skipped): 14 digit
 //     products x 8 K-steps (M = 128, N = 32, K = 32).  The epilogue shifts the five accumulators together
 //     in 64-bit integers, converts ONCE to float64, subtracts from the narrow Gaussian (lo2d_kernel
 //     below, float64, scipy's order) and writes the DoG plane, its selection buckets and min / max.
-// Errors: the only approximation is the 32-bit rounding of the weights (|dw| <= 2^-37 per tap, zero
-// in sum) and the 40-bit rounding between the passes: |dG| <= 129 * 2^-37 * 2 * (local contrast) in the
-// worst case, ~1e-11 of the [0, 1] scale in practice (tests/test_gpu_tcgauss.py measures it); the
-// reference's tolerance for filtered planes is 1e-5.  The segmentation channel, whose plane decides
-// labels, never takes this path (executor.cu): it keeps dog.cu's bit-exact kernels.
+// Errors: the approximations are the 32-bit rounding of the weights (|dw| <= 2^-37 per tap, zero in sum), the
+// 40-bit rounding between the passes and the digit products pass 2 leaves out: amt_tcg_error_bound adds them up
+// (5.3e-10 of the [0, 1] scale for sigma = 16, a proof), ~1.5e-11 in practice (tests/test_gpu_tcgauss.py measures
+// it); the reference's tolerance for filtered planes is 1e-5.  The thresholded channel takes this path too
+// (executor.cu): every sample a decision depends on is then re-evaluated in scipy's exact order (decide.cu).
 //
 // Kernel anatomy (both passes): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
 // (one lane), warps 2..9 = epilogue (TMEM lane quarter = warp % 4).  mbarrier rings: full/empty per
-// operand stage, acc_full/acc_empty per TMEM buffer (two buffers: the epilogue of tile i overlaps the
-// MMAs of tile i + 1).  Persistent grid: one CTA per SM, a contiguous range of tiles each.
+// operand stage, acc_full/acc_empty for the accumulators (ONE set: the band matrix holds half of tensor memory; the
+// epilogue's arithmetic overlaps the MMAs of the next tile once its tcgen05.ld have drained the accumulators).
+// Persistent grid: one CTA per SM, a contiguous range of tiles each.  The warp-specialised fused pass 2 adds two halo
+// warps and eight lo warps (the narrow Gaussian, float64, scipy's order): see tcg_axis1_kernel.
+// Both kernels run at the board's power cap (scripts/power_probe.py): what costs energy costs time.
 
 #include <cuda.h>
 
@@ -702,10 +705,11 @@ __device__ __forceinline__ void lo_axis1_rows(const uint32_t vs, const int lw, c
 // epilogue warps filter them along axis 0 (each thread its own column and rows, a few threads the halo columns) into a
 // double-buffered shared-memory tile while the tile's MMAs run, then along axis 1 where the result is used: the
 // narrow Gaussian never exists in HBM (- 8 B/px written by a kernel of its own, - 8 B/px read here, + 2 B/px).
-// WS (with RT > 0): WARP-SPECIALISED fused variant.  Twenty warps: warpgroup 0 = TMA producer, MMA issuer and two idle
-// warps; warpgroups 1-2 = the EW = 8 epilogue warps; warpgroups 3-4 = eight "lo warps" that do nothing but the narrow
-// Gaussian of the NEXT tile (both axes, result in place in the double-buffered shared-memory tile, handed over through
-// lo_full / lo_empty).  Registers follow the roles (setmaxnreg): 32 / 160 / 64 per thread, which adds up to exactly the
+// WS (with RT > 0): WARP-SPECIALISED fused variant.  Twenty warps: warpgroup 0 = TMA producer, MMA issuer and two halo
+// warps (axis 0 of the narrow Gaussian for the 2 RT columns beside the tile); warpgroups 1-2 = the EW = 8 epilogue
+// warps; warpgroups 3-4 = eight "lo warps" that do nothing but the narrow Gaussian of the NEXT tile (both axes, result
+// in place in the double-buffered shared-memory tile, handed over through lo_full / lo_empty).  Registers follow the
+// roles (setmaxnreg): 48 / 152 / 64 per thread, which adds up to exactly the
 // 640 x 96 the CTA is launched with (an increase can only be served from what the CTA's own warps gave back).  The epilogue warps then
 // run exactly the instructions of the unfused kernel while the extra arithmetic has its own issue slots.
 template <int EW, int RT, bool WS = false>
