@@ -237,18 +237,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t addr, const uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// d = a * b + c with a 64-bit sum (IMAD.WIDE.U32).  The epilogues call it with b = a power of two held in a register
-// the compiler cannot see through (opaque_u32): written as shifts, ptxas spends four or five instructions on every
-// 64-bit term (SHF / IMAD.HI / IADD3 / IADD3.X) and the integer combine was a third of both epilogues.
+// d = a * b + c with a 64-bit sum (IMAD.WIDE.U32).  The epilogues call it with b = a power of two that ptxas cannot
+// see through -- a kernel PARAMETER (Pass1Params / Pass2Params c8, c16, c24; a constant hidden behind an
+// `asm volatile mov` is folded by ptxas all the same).  With a visible power of two ptxas spends four or five
+// instructions on every 64-bit term (IMAD.SHL / IMAD.HI / IADD3 / IADD3.X) and the integer combine was a third of
+// both epilogues.
 __device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) {
   uint64_t d;
   asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
   return d;
-}
-__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
-  return r;
 }
 
 // Shared-memory matrix descriptor (sm_100 format: version 1 in bits 46-47; offsets in 16-byte units)
@@ -355,6 +352,7 @@ struct Pass1Params {
   int tiles_y, groups_x;   // per plane: 128-row tiles, groups of P1_GROUP 32-pixel tiles
   PlaneSel sel;
   int dbg;                 // amt_tune "tcg_debug" (timing experiments): 1 = no MMAs, 2 = no epilogue arithmetic / stores, 4 = no TMEM loads, 8 = no stores
+  uint32_t c8, c16, c24;   // 2^8, 2^16, 2^24 as kernel PARAMETERS: multipliers of the epilogue's IMAD.WIDE chain ptxas cannot fold
 };
 
 // ------------------------------------------------------------------ pass 1: uint16 image -> 40-bit digits, axis 0
@@ -438,7 +436,7 @@ tcg_axis0_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
     const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + TMEM_ACC0 + hcol * 32;
     const uint32_t half = 1u << (p.shift - 1);
     uint8_t* my_row = out_s + m * 128;
-    const uint32_t c8 = opaque_u32(1u << 8), c16 = opaque_u32(1u << 16), c24 = opaque_u32(1u << 24);
+    const uint32_t c8 = p.c8, c16 = p.c16, c24 = p.c24;
     int it = 0;
     for (int u = 0; u < n_units; ++u, tw.next()) {
       const int plane = p.sel.phys(tw.q);
@@ -570,6 +568,7 @@ struct Pass2Params {
   const double* hw_lo;
   int r_lo;
   double in_scale;
+  uint32_t c8, c16, c24;   // as in Pass1Params
 };
 
 // explicit shared-memory accesses (the tiles' pointers lose their address space in the alignment arithmetic, and
@@ -902,7 +901,7 @@ tcg_axis1_kernel(const __grid_constant__ CUtensorMap dig_map, const __grid_const
     double wt[RT + 1];
 #pragma unroll
     for (int j = 0; j <= RT; ++j) wt[j] = (FUSED && j <= p.r_lo) ? __ldg(p.hw_lo + j) : 0.0;
-    const uint32_t c8 = opaque_u32(1u << 8), c16 = opaque_u32(1u << 16), c24 = opaque_u32(1u << 24);
+    const uint32_t c8 = p.c8, c16 = p.c16, c24 = p.c24;
     auto flush = [&]() {
       if (p.minmax != nullptr && plane >= 0) {
         const uint64_t a = warp_min_u64(f64_to_key(vmin)), b = warp_max_u64(f64_to_key(vmax));
@@ -1332,6 +1331,7 @@ int tcg_axis0(const amt_tcg* g, const uint16_t* in, int64_t n_img, int64_t h, in
   p.groups_x = (int)ceil_div(w, P1_GROUP * P1_NB / 2);
   p.sel = sel;
   p.dbg = g_tcg_debug;
+  p.c8 = 1u << 8, p.c16 = 1u << 16, p.c24 = 1u << 24;
   const int64_t units = n_sel * p.tiles_y * p.groups_x;
   AMT_CUDA_TRY(cudaFuncSetAttribute(tcg_axis0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P1_SMEM));
   const int grid = (int)(units < kNumSMs ? units : kNumSMs);
@@ -1379,6 +1379,7 @@ int tcg_axis1(const amt_tcg* g, const uint8_t* digits, const double* lo, double 
   p.tiles_x = (int)ceil_div(w, MT);
   p.sel = sel;
   p.dbg = g_tcg_debug;
+  p.c8 = 1u << 8, p.c16 = 1u << 16, p.c24 = 1u << 24;
   p.hw_lo = hw_lo;
   p.r_lo = r_lo;
   p.in_scale = in_scale;
