@@ -143,7 +143,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t ns = c_suspend_ns;
   const uint64_t t0 = global_timer_ns();
   while (!(ns ? mbar_try_wait_hint(bar, parity, ns) : mbar_try_wait(bar, parity))) {
-    if (global_timer_ns() - t0 > 4000000000ull) __trap();  // 4 s
+    if (global_timer_ns() - t0 > 10000000000ull) __trap();  // 10 s (a pre-empted kernel keeps this clock running)
   }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
