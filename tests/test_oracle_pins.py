@@ -122,3 +122,40 @@ def test_li_threshold_is_the_fixed_point_and_a_minimum_of_the_cross_entropy(seed
     assert _cross_entropy(shifted, ts) <= ce.min() + 1e-9 * abs(ce.min())
     assert ce.max() > ce.min() + 1e-4 * abs(ce.min())  # ... and the scan does cover thresholds that are worse
     assert oracle is not None
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_float_image_otsu_is_the_maximiser_of_the_between_class_variance(seed):
+    """The float-image path of `threshold_otsu` (256 bins of np.histogram over [min, max], threshold = a bin centre;
+    what `apply_threshold` sees after `rescale_by_percentile`, ref: operations.py:186, 214): the returned threshold
+    maximises Otsu's between-class variance w0 * w1 * (mu0 - mu1)^2 evaluated from the definition -- explicit sums over
+    the two classes for every cut, no cumulative sums, no shared code -- and the mask it gives is the one OpenCV's Otsu
+    gives on the same data quantised to its 256 bins."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(seed)
+    n = 40000
+    lo = rng.normal(0.2, 0.05 + 0.01 * seed, n)
+    hi = rng.normal(0.7, 0.08, n // (2 + seed))
+    x = np.clip(np.concatenate([lo, hi]), 0.0, 1.0)
+    x = x[: (x.size // 100) * 100].reshape(-1, 100)
+    t = float(oth.threshold_otsu(x))
+    hist, edges = np.histogram(x, bins=256)
+    centers = (edges[:-1] + edges[1:]) / 2.0
+    assert np.min(np.abs(centers - t)) == 0.0  # a bin centre, bit for bit
+    best, best_k = -1.0, -1
+    for k in range(255):  # classes: bins 0..k and k+1..255
+        w0, w1 = hist[: k + 1].sum(), hist[k + 1 :].sum()
+        if w0 == 0 or w1 == 0:
+            continue
+        mu0 = float((hist[: k + 1] * centers[: k + 1]).sum()) / w0
+        mu1 = float((hist[k + 1 :] * centers[k + 1 :]).sum()) / w1
+        var = float(w0) * float(w1) * (mu0 - mu1) ** 2
+        if var > best:
+            best, best_k = var, k
+    assert abs(int(np.argmin(np.abs(centers - t))) - best_k) <= 0  # the same cut
+    # OpenCV on the image quantised to the same 256 bins: same foreground
+    q = np.clip(((x - x.min()) / (x.max() - x.min()) * 256.0).astype(np.int64), 0, 255).astype(np.uint8)
+    t_cv, _ = cv2.threshold(q, 0, 255, cv2.THRESH_BINARY + cv2.THRESH_OTSU)
+    mask_oracle = x > t
+    mask_cv = q > t_cv
+    assert np.count_nonzero(mask_oracle != mask_cv) <= 0.002 * x.size  # samples on the cut bin's edge may differ
