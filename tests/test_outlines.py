@@ -171,3 +171,52 @@ def test_cell_outlines_reference_contract():
     assert len(edge.cell_outlines[0]) > 0
     kept = edge.filter("area", min_value=1)
     assert kept.outline_extractor == "skimage"
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4])
+def test_find_contours_visits_every_crossing_edge_exactly_once(seed):
+    """An independent pin for the marching-squares restatement (`oracle.outlines.find_contours`, the "skimage"
+    extractor of ref masks.py:82-115).  On a 0/1 image at level 0.5 every contour vertex is the midpoint of two
+    4-adjacent pixels with different values, and the contours together pass through every such midpoint exactly once;
+    a segment joins the midpoints of two edges of one 2x2 square (length sqrt(1/2) or 1); a contour that does not reach
+    the image border is closed; around a high island and around a hole the contours wind in opposite directions."""
+    rng = np.random.default_rng(seed)
+    img = (ndi.gaussian_filter(rng.normal(size=(48, 56)), 2.0) > 0.02).astype(np.uint8)
+    img[20:30, 20:30] = 1
+    img[23:27, 23:27] = 0  # a hole
+    contours = oracle_outlines.find_contours(img, 0.5)
+    want = set()
+    h, w = img.shape
+    for r in range(h):
+        for c in range(w):
+            if c + 1 < w and img[r, c] != img[r, c + 1]:
+                want.add((float(r), c + 0.5))
+            if r + 1 < h and img[r, c] != img[r + 1, c]:
+                want.add((r + 0.5, float(c)))
+    seen = []
+    for contour in contours:
+        closed = np.array_equal(contour[0], contour[-1])
+        pts = contour[:-1] if closed else contour
+        seen.extend(map(tuple, pts.tolist()))
+        steps = np.linalg.norm(np.diff(contour, axis=0), axis=1)
+        assert np.all(np.isclose(steps, np.sqrt(0.5)) | np.isclose(steps, 1.0))
+        if not closed:  # an open contour starts and ends on the image border
+            for end in (contour[0], contour[-1]):
+                assert end[0] in (0.0, h - 1.0) or end[1] in (0.0, w - 1.0)
+    assert len(seen) == len(set(seen))  # no vertex twice
+    assert set(seen) == want            # and none missing
+
+    def signed_area(p):
+        return 0.5 * float(np.sum(p[:-1, 0] * p[1:, 1] - p[1:, 0] * p[:-1, 1]))
+
+    island = np.zeros((12, 12), np.uint8)
+    island[3:9, 3:9] = 1
+    ring = island.copy()
+    ring[5:7, 5:7] = 0
+    (outer,) = oracle_outlines.find_contours(island, 0.5)
+    both = oracle_outlines.find_contours(ring, 0.5)
+    assert len(both) == 2
+    areas = sorted(signed_area(c) for c in both)
+    assert areas[0] * areas[1] < 0                                   # opposite windings
+    assert np.sign(signed_area(outer)) == np.sign(signed_area(max(both, key=len)))  # island and ring: same outer winding
+    assert abs(abs(signed_area(outer)) - 35.5) < 1e-9               # 6x6 pixels minus the four cut corners (4 x 1/8)
